@@ -1,0 +1,643 @@
+"""CPU oracle for the spinterps gridded-interpolation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``spinterps_b200/`` may import this
+module: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and there only as the checker
+or the timed CPU baseline, never as part of the product path.
+
+It is a NumPy restatement (no pandas, no Cython) of what the reference does
+between ``SpInterpSteps._get_all_interp_outputs`` (interp/steps.py:478-877) and
+the Cython free functions of cyth/interpmthds.pyx.  Every function cites the
+reference lines it follows.  Parity status: PINNED -- the restatement is
+checked in ``tests/test_oracle_golden.py`` against arrays produced by running
+the unmodified reference in the build container (``tests/golden/make_golden.py``,
+fixtures ``tests/golden/*.npz``) and against the known-answer vectors listed in
+SURVEY.md section 8c.
+
+Two execution modes give the same numbers:
+  * ``faithful=True``  keeps the reference's loop nest (per cell, per step;
+    ``np.matmul`` + ``np.isclose`` per cell, steps.py:415-434).  This is the one
+    timed as the CPU baseline because it has the reference's cost structure.
+  * ``faithful=False`` vectorises the per-cell loops (same operations, batched)
+    so that parity tests on bigger problems finish in seconds.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# ---------------------------------------------------------------------------
+# Variogram functions -- cyth/interpmthds.pyx:38-95
+# ---------------------------------------------------------------------------
+
+
+def _rng_vg(h, r, s):  # pyx:38-39
+    return np.array(h, dtype=np.float64, copy=True)
+
+
+def _nug_vg(h, r, s):  # pyx:42-43  (sill for EVERY h, including 0: quirk Q1)
+    return np.full_like(h, s, dtype=np.float64)
+
+
+def _sph_vg(h, r, s):  # pyx:46-55  (h >= r -> sill)
+    a = (1.5 * h) / r
+    b = (h * h * h) / (2 * (r * r * r))
+    return np.where(h >= r, s, s * (a - b))
+
+
+def _exp_vg(h, r, s):  # pyx:58-59
+    return s * (1 - np.exp(-3 * h / r))
+
+
+def _lin_vg(h, r, s):  # pyx:62-66  (h > r -> sill)
+    return np.where(h > r, s, s * (h / r))
+
+
+def _gau_vg(h, r, s):  # pyx:69-70
+    return s * (1 - np.exp(-3 * ((h * h) / (r * r))))
+
+
+def _pow_vg(h, r, s):  # pyx:73-74
+    return s * np.power(h, r)
+
+
+def _hol_vg(h, r, s):  # pyx:77-83
+    a = (math.pi * h) / r
+    with np.errstate(invalid='ignore', divide='ignore'):
+        v = s * (1 - (np.sin(a) / a))
+    return np.where(h == 0, 0.0, v)
+
+
+ALL_VG_FTNS = {
+    'Rng': _rng_vg, 'Nug': _nug_vg, 'Sph': _sph_vg, 'Exp': _exp_vg,
+    'Lin': _lin_vg, 'Gau': _gau_vg, 'Pow': _pow_vg, 'Hol': _hol_vg}
+
+
+def parse_vg_str(vg_models_str, clamp_range=True):
+    """Split a variogram string into (sill, name, range) terms.
+
+    Grammar as parsed at pyx:174-184: split on '+', strip, split on one space,
+    then on '(' and ')'.  ``range = max(1e-5, float(range))`` (pyx:183) when
+    ``clamp_range``.
+    """
+    terms = []
+    for vg_model in str(vg_models_str).split('+'):
+        vg_model = vg_model.strip()
+        sill_s, vg_s = vg_model.split(' ')
+        vg_s, range_s = vg_s.split('(')
+        range_s = range_s.split(')')[0]
+        rng = float(range_s)
+        if clamp_range:
+            rng = max(1e-5, rng)
+        terms.append((float(sill_s), vg_s, rng))
+    return terms
+
+
+def fill_theo_vg_vals(vg_str, h_arr, r, s, vg_arr):
+    """pyx:98-120 -- accumulates one variogram term into ``vg_arr``."""
+    assert h_arr.shape[0]
+    assert h_arr.shape[0] == vg_arr.shape[0]
+    assert s >= 0
+    assert r >= 0
+    with np.errstate(invalid='ignore', divide='ignore'):
+        vg_arr += ALL_VG_FTNS[vg_str.strip()](np.asarray(h_arr, dtype=np.float64), r, s)
+    return
+
+
+def get_theo_vg_vals(in_model, h_arr):
+    """misc.py:1027-1047 (no range clamp on this route)."""
+    vg_vals = np.zeros_like(h_arr, dtype=np.float64)
+    for sill, name, rng in parse_vg_str(in_model, clamp_range=False):
+        fill_theo_vg_vals(name, h_arr, rng, sill, vg_vals)
+    return vg_vals
+
+
+# ---------------------------------------------------------------------------
+# Cython free functions -- cyth/interpmthds.pyx
+# ---------------------------------------------------------------------------
+
+
+def fill_dists_2d_mat(x1s, y1s, x2s, y2s, dists):
+    """pyx:123-143: dists[i, j] = ((x1_i-x2_j)**2 + (y1_i-y2_j)**2)**0.5."""
+    dx = x1s[:, None] - x2s[None, :]
+    dy = y1s[:, None] - y2s[None, :]
+    dists[...] = ((dx ** 2) + (dy ** 2)) ** 0.5
+    return
+
+
+def fill_dists_one_pt(x, y, xs, ys, dists):
+    """pyx:768-781."""
+    dists[...] = (((x - xs) ** 2) + ((y - ys) ** 2)) ** 0.5
+    return
+
+
+def fill_vg_var_arr(dists, in_vars, covar_flag, diag_mat_flag, vg_models_str, min_vg_val):
+    """pyx:146-226.
+
+    covar_flag=0 -> gamma(h); covar_flag=1 -> sum(sill) - gamma(h) accumulated
+    term by term; values <= min_vg_val set to 0 afterwards; with diag_mat_flag
+    the upper triangle INCLUDING the diagonal is computed and mirrored.
+    """
+    if covar_flag:
+        cov_sign, cov_mult = -1, +1
+    else:
+        cov_sign, cov_mult = +1, +0
+
+    in_vars[...] = 0.0
+    with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+        for sill_f, vg_s, range_f in parse_vg_str(vg_models_str):
+            in_vars += (cov_mult * sill_f) + (cov_sign * ALL_VG_FTNS[vg_s](dists, range_f, sill_f))
+
+        in_vars[in_vars <= min_vg_val] = 0.0
+
+    if diag_mat_flag:
+        # Upper triangle (g >= h) is authoritative; lower is its mirror.
+        iu = np.triu_indices(in_vars.shape[0], 0, in_vars.shape[1])
+        upper = np.zeros_like(in_vars)
+        upper[iu] = in_vars[iu]
+        mirrored = upper + np.triu(upper, 1).T
+        in_vars[...] = mirrored
+    return
+
+
+def copy_2d_arr_at_idxs(arr, row_idxs, col_idxs, subset_arr):
+    """pyx:229-248."""
+    subset_arr[:row_idxs.shape[0], :col_idxs.shape[0]] = arr[np.ix_(row_idxs, col_idxs)]
+    return
+
+
+def fill_wts_and_sum(dists, wts, idw_exp):
+    """pyx:784-795: w_i = 1/d_i**p, sequential sum."""
+    wts_sum = 0.0
+    with np.errstate(divide='ignore'):
+        wts[...] = 1.0 / (dists ** idw_exp)
+    for w in wts:  # sequential order as the C loop
+        wts_sum += float(w)
+    return wts_sum
+
+
+def get_mults_sum(wts, data):
+    """pyx:798-808: sequential dot product."""
+    mults_sum = 0.0
+    for w, z in zip(wts, data):
+        mults_sum += float(w) * float(z)
+    return mults_sum
+
+
+# ---------------------------------------------------------------------------
+# Host-side index logic
+# ---------------------------------------------------------------------------
+
+
+def check_full_nuggetness(in_model, min_vg_val):
+    """misc.py:1074-1105."""
+    in_model = str(in_model)
+    nuggetness = False
+    if in_model == 'nan':
+        return nuggetness
+    models = in_model.split('+')
+    Sill = 0.0
+    Range = 0.0
+    for submodel in models:
+        submodel = submodel.strip()
+        Sill += float(submodel.split('(')[0].strip()[:-3].strip())
+        Range = max(Range, float(submodel.split('(')[1].split(')')[0]))
+    if (Sill <= min_vg_val) or (Range <= min_vg_val):
+        nuggetness = True
+    # misc.py:1102 compares the un-split string with 'Nug' and can never fire.
+    return nuggetness
+
+
+def get_vgs_cluster(vgs):
+    """interp/vgclus.py:33-79: unique strings in first-occurrence order ->
+    positions of the steps carrying them."""
+    clus = {}
+    for i, vg in enumerate(vgs):
+        clus.setdefault(vg, []).append(i)
+    return {k: np.asarray(v, dtype=np.int64) for k, v in clus.items()}
+
+
+def get_grps_in_time(data):
+    """interp/grps.py:57-101 on a [T, N] array (NaN = missing).
+
+    Returns [(station index array, bool mask over steps)] in first-occurrence
+    order of each distinct availability pattern.
+    """
+    avail = ~np.isnan(data)
+    keys = [row.tobytes() for row in avail]
+    seen = {}
+    grps = []
+    for i, key in enumerate(keys):
+        if key in seen:
+            grps[seen[key]][1][i] = True
+            continue
+        seen[key] = len(grps)
+        mask = np.zeros(data.shape[0], dtype=bool)
+        mask[i] = True
+        grps.append((np.where(avail[i])[0], mask))
+    return grps
+
+
+def _get_neb_idxs_grps(all_neb_idxs):
+    """interp/grps.py:103-139: cells with identical neighbour rows, groups in
+    first-occurrence order, members ascending."""
+    seen = {}
+    grps = []
+    for i in range(all_neb_idxs.shape[0]):
+        key = all_neb_idxs[i].tobytes()
+        if key in seen:
+            grps[seen[key]].append(i)
+        else:
+            seen[key] = len(grps)
+            grps.append([i])
+    return [np.asarray(g, dtype=np.int64) for g in grps]
+
+
+def get_neb_idxs_and_grps(neb_sel_mthd, n_nebs, dst_xs, dst_ys, ref_xs, ref_ys):
+    """interp/grps.py:249-288 ('all' :141-145, 'nrst' :147-166)."""
+    n_refs = ref_xs.size
+    n_dst = dst_xs.shape[0]
+    if neb_sel_mthd == 'all':
+        all_neb_idxs = np.tile(np.arange(n_refs), (n_dst, 1))
+        # every row identical -> one group holding every cell
+        return all_neb_idxs, [np.arange(n_dst, dtype=np.int64)]
+
+    if neb_sel_mthd == 'nrst':
+        all_neb_idxs = np.full((n_dst, min(n_nebs, n_refs)), -1, dtype=int)
+        for i in range(n_dst):
+            dists = (((dst_xs[i] - ref_xs) ** 2) + ((dst_ys[i] - ref_ys) ** 2)) ** 0.5
+            all_neb_idxs[i, :] = np.sort(np.argsort(dists)[:n_nebs])
+        return all_neb_idxs, _get_neb_idxs_grps(all_neb_idxs)
+
+    raise NotImplementedError(
+        "'pie' fails in the reference on LP64 (grps.py:173 vs pyx:17); not restated")
+
+
+# ---------------------------------------------------------------------------
+# Kriging system assembly -- interp/steps.py:170-243
+# ---------------------------------------------------------------------------
+
+
+def get_vars_arr_subset(interp_type, ref_drfts, ref_ref_vars_all, dst_ref_vars_all,
+                        ref_ref_sub_idxs, cell_idxs, dst_drfts):
+    if interp_type == 'OK':
+        add_rc = 1
+    elif interp_type == 'SK':
+        add_rc = 0
+    elif interp_type == 'EDK':
+        add_rc = 1 + ref_drfts.shape[1]
+    else:
+        raise NotImplementedError
+
+    n = ref_ref_sub_idxs.size
+    A = np.full((n + add_rc, n + add_rc), np.nan)
+    copy_2d_arr_at_idxs(ref_ref_vars_all, ref_ref_sub_idxs, ref_ref_sub_idxs, A)
+    R = np.full((cell_idxs.size, n + add_rc), np.nan)
+    copy_2d_arr_at_idxs(dst_ref_vars_all, cell_idxs, ref_ref_sub_idxs, R)
+
+    if interp_type == 'OK':  # steps.py:212-216
+        A[n, :n] = 1.0
+        A[:, n] = 1.0
+        A[n, n] = 0.0
+        R[:, n] = 1.0
+    elif interp_type == 'EDK':  # steps.py:221-234
+        A[n, :n] = 1.0
+        A[:n, n] = 1.0
+        R[:, n] = 1.0
+        A[n:, n:] = 0.0
+        for k in range(ref_drfts.shape[1]):
+            A[n + 1 + k, :n] = ref_drfts[:, k]
+            A[:n, n + 1 + k] = ref_drfts[:, k]
+            R[:, n + 1 + k] = dst_drfts[k, :]
+    return A, R
+
+
+# ---------------------------------------------------------------------------
+# _get_interp -- interp/steps.py:245-401 (+ :403-435)
+# ---------------------------------------------------------------------------
+
+
+def _krige_fill_faithful(n_refs, inv, R, dists_sub, ref_data_j, dst_row, est_row):
+    """steps.py:415-434, one step, python loop over cells."""
+    for i in range(R.shape[0]):
+        lmds = np.matmul(inv, R[i])
+        if not np.isclose(lmds[:n_refs].sum(), 1.0):
+            dst_row[i] = ref_data_j[np.argmin(dists_sub[i])]
+            if est_row is not None:
+                est_row[i] = 0.0
+        else:
+            dst_row[i] = (lmds[:n_refs] * ref_data_j).sum()
+            if est_row is not None:
+                est_row[i] = (lmds * R[i]).sum() + lmds[n_refs]
+    return
+
+
+def _krige_fill_fast(n_refs, lmds_all, lsum_ok, nnb_idx, R, ref_data_j, dst_row, est_row):
+    """Vectorised equivalent of steps.py:415-434 (weights precomputed once per
+    system because they do not depend on the step)."""
+    vals = lmds_all[:, :n_refs] @ ref_data_j
+    nn = ref_data_j[nnb_idx]
+    dst_row[...] = np.where(lsum_ok, vals, nn)
+    if est_row is not None:
+        ev = (lmds_all * R).sum(axis=1) + lmds_all[:, n_refs]
+        est_row[...] = np.where(lsum_ok, ev, 0.0)
+    return
+
+
+def get_interp(ref_data, interp_type, ref_drfts, dst_drfts, idw_exp, models,
+               interp_steps_flags, nuggetness_flags, dists_sub,
+               ref_ref_vars_all, dst_ref_vars_all, ref_ref_sub_idxs, cell_idxs,
+               est_var_flag, est_dtype, prblm_steps, faithful):
+    """interp/steps.py:245-401.  ``dists_sub`` is modified in place by IDW
+    (steps.py:297-301, quirk Q7) exactly like the reference."""
+    n_dsts = dists_sub.shape[0]
+    n_time, n_refs = ref_data.shape
+
+    dst_data = np.full((n_time, n_dsts), np.nan)
+    est_vars = None
+    if est_var_flag and interp_type == 'OK':
+        est_vars = np.full((n_time, n_dsts), np.nan, dtype=est_dtype)
+
+    ref_means = ref_data.mean(axis=1)
+
+    if n_refs == 1:  # steps.py:282-283
+        for j in range(n_time):
+            dst_data[j, :] = ref_data[j, :]
+
+    elif interp_type == 'NNB':  # steps.py:285-291
+        nnb_idx = np.argmin(dists_sub, axis=1)
+        dst_data[...] = ref_data[:, nnb_idx]
+
+    elif interp_type == 'IDW':  # steps.py:293-313
+        if faithful:
+            wts = np.full(n_refs, np.nan)
+            for i in range(n_dsts):
+                dists = dists_sub[i]
+                dists_max = dists.max()
+                if dists_max > 0:
+                    dists /= dists_max
+                wts_sum = fill_wts_and_sum(dists, wts, idw_exp)
+                assert wts_sum >= 1e-14, wts_sum
+                for j in range(n_time):
+                    if interp_steps_flags[j]:
+                        dst_data[j, i] = get_mults_sum(wts, ref_data[j]) / wts_sum
+                    else:
+                        dst_data[j, i] = ref_means[j]
+        else:
+            dmax = dists_sub.max(axis=1, keepdims=True)
+            np.divide(dists_sub, dmax, out=dists_sub, where=dmax > 0)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                wts = 1.0 / (dists_sub ** idw_exp)
+                wts_sum = np.cumsum(wts, axis=1)[:, -1]  # sequential order
+                assert np.all(~(wts_sum < 1e-14)), wts_sum.min()
+                for j in range(n_time):
+                    if interp_steps_flags[j]:
+                        ms = np.cumsum(wts * ref_data[j][None, :], axis=1)[:, -1]
+                        dst_data[j, :] = ms / wts_sum
+                    else:
+                        dst_data[j, :] = ref_means[j]
+
+    elif interp_type in ('OK', 'SK', 'EDK'):  # steps.py:315-396
+        old_model = ''
+        last_failed_flag = False
+        covar_flag = 1 if interp_type == 'SK' else 0
+        nnb_idx = None
+        for j in np.argsort(models):
+            model = models[j]
+            if (not interp_steps_flags[j]) or nuggetness_flags[j]:
+                dst_data[j, :] = ref_means[j]
+                if est_vars is not None:
+                    est_vars[j, :] = 0.0
+                continue
+            if model == 'nan':
+                raise ValueError('NaN VG!')
+            if model != old_model:
+                A, R = get_vars_arr_subset(
+                    interp_type, ref_drfts,
+                    ref_ref_vars_all[(model, covar_flag)],
+                    dst_ref_vars_all[(model, covar_flag)],
+                    ref_ref_sub_idxs, cell_idxs, dst_drfts)
+                old_model = model
+                try:
+                    inv = np.linalg.pinv(A)
+                    last_failed_flag = False
+                except Exception:
+                    last_failed_flag = True
+                    if j not in prblm_steps:
+                        prblm_steps.append(j)
+                    inv = np.nan
+                if (not faithful) and (not last_failed_flag):
+                    lmds_all = R @ inv.T
+                    with np.errstate(invalid='ignore'):
+                        lsum_ok = np.isclose(lmds_all[:, :n_refs].sum(axis=1), 1.0)
+
+            if (not faithful) and nnb_idx is None:
+                nnb_idx = np.argmin(dists_sub, axis=1)
+
+            if last_failed_flag:  # steps.py:372-384
+                if faithful:
+                    for i in range(n_dsts):
+                        dst_data[j, i] = ref_data[j, np.argmin(dists_sub[i])]
+                else:
+                    dst_data[j, :] = ref_data[j, nnb_idx]
+                if est_vars is not None:
+                    est_vars[j, :] = 0.0
+            elif faithful:
+                _krige_fill_faithful(
+                    n_refs, inv, R, dists_sub, ref_data[j], dst_data[j],
+                    None if est_vars is None else est_vars[j])
+            else:
+                _krige_fill_fast(
+                    n_refs, lmds_all, lsum_ok, nnb_idx, R, ref_data[j], dst_data[j],
+                    None if est_vars is None else est_vars[j])
+    else:
+        raise NotImplementedError(interp_type)
+
+    return dst_data, est_vars
+
+
+# ---------------------------------------------------------------------------
+# _get_all_interp_outputs -- interp/steps.py:478-877
+# ---------------------------------------------------------------------------
+
+
+def interp_chunk(
+        data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args,
+        vgs=None, cntn_idxs=None, drft_arrs=None, stns_drft=None,
+        fld_beg_row=0, fld_end_row=None,
+        neb_sel_mthd='all', n_nebs=None,
+        min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
+        min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
+        faithful=False):
+    """Compute half of ``SpInterpSteps.interpolate_subset`` for one time chunk
+    and one grid-row chunk.
+
+    data [T, N] f64 (NaN = missing); stn_xs/ys [N]; cell_xs/ys = the (masked)
+    raveled cell-centre coordinates of the WHOLE grid (``_interp_x/y_crds_msh``);
+    grid_shape = ``_interp_crds_orig_shape``; interp_args = list of
+    (type, fig_dir, label[, idw_exp]) in the reference's order; vgs = list of T
+    variogram strings or None; cntn_idxs = bool mask over the raveled grid or
+    None; drft_arrs [n_drifts, cells]; stns_drft [N, n_drifts].
+
+    Returns {label: ndarray[T, rows*cols] of intrp_dtype} (element 7 of the
+    reference's 13-tuple, steps.py:864-877) and the list of problem steps.
+    """
+    data = np.asarray(data, dtype=np.float64)
+    stn_xs = np.asarray(stn_xs, dtype=np.float64)
+    stn_ys = np.asarray(stn_ys, dtype=np.float64)
+    if fld_end_row is None:
+        fld_end_row = grid_shape[0]
+
+    interp_types = [a[0] for a in interp_args]
+    interp_labels = [a[2] for a in interp_args]
+    krg_flag = any(t in interp_types for t in ('OK', 'SK', 'EDK'))
+    edk_flag = 'EDK' in interp_types
+    if krg_flag:
+        assert all(vg != 'nan' for vg in vgs), 'NaN VGs not allowed!'
+
+    n_steps = data.shape[0]
+
+    # -- cell subsetting, steps.py:512-568 --
+    fld_n_cols = grid_shape[1]
+    fld_beg_idx = fld_beg_row * fld_n_cols
+    fld_end_idx = fld_end_row * fld_n_cols
+    fld_grd_shape = ((fld_end_row - fld_beg_row), fld_n_cols)
+
+    if cntn_idxs is not None:
+        cntn_idxs_whr = np.where(cntn_idxs)[0]
+        sel = (cntn_idxs_whr >= fld_beg_idx) & (cntn_idxs_whr < fld_end_idx)
+        msh_idxs = np.arange(cntn_idxs_whr.size)[sel]
+        cntn_idxs_whr = cntn_idxs_whr[sel] - fld_beg_idx
+        dst_xs = cell_xs[msh_idxs]
+        dst_ys = cell_ys[msh_idxs]
+        if drft_arrs is not None:
+            drft_arrs = drft_arrs[:, msh_idxs]
+    else:
+        cntn_idxs_whr = None
+        dst_xs = cell_xs[fld_beg_idx:fld_end_idx]
+        dst_ys = cell_ys[fld_beg_idx:fld_end_idx]
+        if drft_arrs is not None:
+            drft_arrs = drft_arrs[:, fld_beg_idx:fld_end_idx]
+    n_dst_pts = dst_xs.shape[0]
+
+    if vgs is not None:
+        vgs = list(vgs)
+        vgs_clus = get_vgs_cluster(vgs)
+
+    # -- drop stations never selected, steps.py:592-608 (Q9) --
+    tke = np.unique(get_neb_idxs_and_grps(
+        neb_sel_mthd, n_nebs, dst_xs, dst_ys, stn_xs, stn_ys)[0])
+    if tke.size != stn_xs.shape[0]:
+        stn_xs = stn_xs[tke].copy()
+        stn_ys = stn_ys[tke].copy()
+        data = data[:, tke].copy()
+        if stns_drft is not None:
+            stns_drft = stns_drft[tke, :]
+
+    grps_in_time = get_grps_in_time(data)
+
+    # -- distance and variogram matrices, steps.py:620-653 --
+    def svars(dists, diag):
+        out = {}
+        var_flag = any(t in interp_types for t in ('OK', 'EDK'))
+        for vg in vgs_clus.keys():
+            if var_flag:
+                arr = np.full_like(dists, np.nan)
+                fill_vg_var_arr(dists, arr, 0, diag, vg, min_vg_val)
+                out[(vg, 0)] = arr
+            if 'SK' in interp_types:
+                arr = np.full_like(dists, np.nan)
+                fill_vg_var_arr(dists, arr, 1, diag, vg, min_vg_val)
+                out[(vg, 1)] = arr
+        return out
+
+    if vgs is not None:
+        rr = np.full((stn_xs.size, stn_xs.size), np.nan)
+        fill_dists_2d_mat(stn_xs, stn_ys, stn_xs, stn_ys, rr)
+        ref_ref_vars_all = svars(rr, 1)
+    else:
+        ref_ref_vars_all = None
+
+    dst_ref_dists_all = np.full((n_dst_pts, stn_xs.size), np.nan)
+    fill_dists_2d_mat(dst_xs, dst_ys, stn_xs, stn_ys, dst_ref_dists_all)
+    dst_ref_vars_all = svars(dst_ref_dists_all, 0) if vgs is not None else None
+
+    flds = {lab: np.full((n_steps, int(np.prod(fld_grd_shape))), np.nan, dtype=intrp_dtype)
+            for lab in interp_labels}
+
+    prblm_steps = []
+
+    for stn_idxs, step_mask in grps_in_time:  # HOT LOOP A, steps.py:673
+        step_idxs = np.where(step_mask)[0]
+        if not stn_idxs.size:  # steps.py:677-688 (Q11)
+            for s in step_idxs:
+                if s not in prblm_steps:
+                    prblm_steps.append(int(s))
+            continue
+
+        grp_xs = stn_xs[stn_idxs]
+        grp_ys = stn_ys[stn_idxs]
+        grp_data = data[np.ix_(step_idxs, stn_idxs)]
+        grp_drifts = stns_drft[stn_idxs] if edk_flag else None
+
+        if krg_flag:
+            vg_models = np.array([vgs[s] for s in step_idxs], dtype=object)
+            nuggetness_flags = np.array(
+                [check_full_nuggetness(vg, min_vg_val) for vg in vg_models], dtype=bool)
+        else:
+            vg_models = None
+            nuggetness_flags = None
+
+        neb_idxs, neb_grps = get_neb_idxs_and_grps(
+            neb_sel_mthd, n_nebs, dst_xs, dst_ys, grp_xs, grp_ys)
+
+        pts_done = np.zeros(n_dst_pts, dtype=bool)
+
+        for cell_grp in neb_grps:  # HOT LOOP B, steps.py:740
+            sub_ref_idxs = neb_idxs[cell_grp[0]]
+            sub_ref_data = grp_data[:, sub_ref_idxs].copy('C')
+            ref_ref_sub_idxs = stn_idxs[sub_ref_idxs]
+
+            dists_sub = np.full((cell_grp.size, ref_ref_sub_idxs.size), np.nan)
+            copy_2d_arr_at_idxs(dst_ref_dists_all, cell_grp, ref_ref_sub_idxs, dists_sub)
+
+            # steps.py:760-765
+            with np.errstate(invalid='ignore'):
+                interp_steps_flags = np.any(sub_ref_data >= min_var_thr, axis=1)
+
+            if edk_flag:
+                sub_ref_drifts = grp_drifts[sub_ref_idxs, :]
+                sub_dst_drifts = drft_arrs[:, cell_grp]
+            else:
+                sub_ref_drifts = sub_dst_drifts = None
+
+            for i, interp_type in enumerate(interp_types):
+                if interp_labels[i] == 'EST_VARS_OK':
+                    continue
+                idw_exp = interp_args[i][3] if interp_type == 'IDW' else 5
+
+                vals, est_vars = get_interp(
+                    sub_ref_data, interp_type, sub_ref_drifts, sub_dst_drifts,
+                    idw_exp, vg_models, interp_steps_flags, nuggetness_flags,
+                    dists_sub, ref_ref_vars_all, dst_ref_vars_all,
+                    ref_ref_sub_idxs, cell_grp, est_var_flag, intrp_dtype,
+                    prblm_steps, faithful)
+
+                # _mod_min_max, steps.py:466-476
+                with np.errstate(invalid='ignore'):
+                    if min_var_cut is not None:
+                        vals[vals < min_var_cut] = min_var_cut
+                    if max_var_cut is not None:
+                        vals[vals > max_var_cut] = max_var_cut
+
+                out_pos = cell_grp if cntn_idxs_whr is None else cntn_idxs_whr[cell_grp]
+                fld = flds[interp_labels[i]]
+                fld[np.ix_(step_idxs, out_pos)] = vals.astype(intrp_dtype)
+                if est_vars is not None:
+                    flds['EST_VARS_OK'][np.ix_(step_idxs, out_pos)] = est_vars
+
+            pts_done[cell_grp] = True
+        assert np.all(pts_done), 'Some points not interpolated!'
+
+    return flds, prblm_steps
