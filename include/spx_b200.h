@@ -1,0 +1,289 @@
+/*
+ * spx_b200.h -- C-ABI of the B200-native spinterps interpolation hot path.
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types in any signature
+ * (streams are passed as void* and may be NULL = default stream).
+ *
+ * Three groups of entry points:
+ *
+ *  (1) DROP-IN functions, HOST pointers.  One per `cpdef` free function of the
+ *      reference's only native module, cyth/interpmthds.pyx (the functions
+ *      interp/steps.py:14-19 and interp/grps.py:9 import).  Same argument
+ *      meaning, caller-allocated outputs filled in place.  Each call copies its
+ *      operands to the GPU, runs the sm_100a kernel and copies the result back.
+ *
+ *  (2) The same kernels on DEVICE pointers (suffix _dev) for callers that keep
+ *      data resident in HBM.
+ *
+ *  (3) The ENGINE entry points (device pointers) that together implement the
+ *      compute half of SpInterpSteps.interpolate_subset
+ *      (interp/steps.py:478-877): kriging-system assembly, batched LU factor and
+ *      solve, the fused variogram-fill + FP64 tensor-core (DMMA) estimate
+ *      contraction, fused IDW, nearest-neighbour index and the field epilogues.
+ *      spinterps_b200/engine.py drives them.
+ *
+ * Every function returns 0 on success, a negative SPX_E* code on failure;
+ * spx_last_error() returns a thread-local message for the last failure.
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with SPX_ECUDA.
+ */
+#ifndef SPX_B200_H
+#define SPX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_OK 0
+#define SPX_EINVAL (-1)  /* bad argument                                   */
+#define SPX_ECUDA (-2)   /* CUDA runtime error / no device                 */
+#define SPX_EPARSE (-3)  /* malformed variogram string                     */
+#define SPX_ENOMEM (-4)  /* shared-memory or workspace limit exceeded      */
+
+/* Variogram families, cyth/interpmthds.pyx:88-95 */
+#define SPX_VG_RNG 0
+#define SPX_VG_NUG 1
+#define SPX_VG_SPH 2
+#define SPX_VG_EXP 3
+#define SPX_VG_LIN 4
+#define SPX_VG_GAU 5
+#define SPX_VG_POW 6
+#define SPX_VG_HOL 7
+#define SPX_VG_MAX_TERMS 8
+
+/* Kriging system kinds, interp/steps.py:181-191 */
+#define SPX_KRG_OK 0
+#define SPX_KRG_SK 1
+#define SPX_KRG_EDK 2
+
+int spx_version(void);
+const char* spx_last_error(void);
+/* Number of visible CUDA devices (0 if none); never fails. */
+int spx_device_count(void);
+
+/* Parse "<sill> <Name>(<range>) + ..." exactly like cyth/interpmthds.pyx:174-184
+ * (split on '+', strip, one space between sill and name; range clamped to
+ * >= 1e-5 when clamp_range != 0).  Outputs hold up to max_terms entries. */
+int spx_parse_vg_str(const char* vg_models_str, int clamp_range, int max_terms,
+                     int* n_terms, int* types, double* sills, double* ranges);
+
+/* ---------------- (1) drop-in, host pointers ---------------------------- */
+
+/* cyth/interpmthds.pyx:123-143  fill_dists_2d_mat(x1s, y1s, x2s, y2s, dists) */
+int spx_fill_dists_2d_mat(const double* x1s, const double* y1s, int64_t n1,
+                          const double* x2s, const double* y2s, int64_t n2,
+                          double* dists /* [n1, n2] C-order */);
+
+/* cyth/interpmthds.pyx:146-226  fill_vg_var_arr(dists, in_vars, covar_flag,
+ * diag_mat_flag, vg_models_str, min_vg_val) */
+int spx_fill_vg_var_arr(const double* dists, double* in_vars, int64_t rows, int64_t cols,
+                        int covar_flag, int diag_mat_flag, const char* vg_models_str,
+                        double min_vg_val);
+
+/* cyth/interpmthds.pyx:229-248  copy_2d_arr_at_idxs(arr, row_idxs, col_idxs,
+ * subset_arr); subset_arr may be wider/taller than the index lists
+ * (subset_cols = its row pitch); untouched entries keep their value. */
+int spx_copy_2d_arr_at_idxs(const double* arr, int64_t arr_rows, int64_t arr_cols,
+                            const int64_t* row_idxs, int64_t n_row_idxs,
+                            const int64_t* col_idxs, int64_t n_col_idxs,
+                            double* subset_arr, int64_t subset_rows, int64_t subset_cols);
+
+/* cyth/interpmthds.pyx:98-120  fill_theo_vg_vals(vg_str, h_arr, r, s, vg_arr)
+ * -- ACCUMULATES into vg_arr. */
+int spx_fill_theo_vg_vals(const char* vg_name, const double* h_arr, int64_t n,
+                          double r, double s, double* vg_arr);
+
+/* cyth/interpmthds.pyx:768-781  fill_dists_one_pt(x, y, xs, ys, dists) */
+int spx_fill_dists_one_pt(double x, double y, const double* xs, const double* ys,
+                          int64_t n, double* dists);
+
+/* cyth/interpmthds.pyx:784-795  fill_wts_and_sum(dists, wts, idw_exp) -> sum */
+int spx_fill_wts_and_sum(const double* dists, double* wts, int64_t n, double idw_exp,
+                         double* wts_sum);
+
+/* cyth/interpmthds.pyx:798-808  get_mults_sum(wts, data) -> sum */
+int spx_get_mults_sum(const double* wts, const double* data, int64_t n, double* mults_sum);
+
+/* ---------------- (2) same kernels, device pointers --------------------- */
+
+int spx_fill_dists_2d_mat_dev(const double* x1s, const double* y1s, int64_t n1,
+                              const double* x2s, const double* y2s, int64_t n2,
+                              double* dists, void* stream);
+
+int spx_fill_vg_var_arr_dev(const double* dists, double* in_vars, int64_t rows, int64_t cols,
+                            int covar_flag, int diag_mat_flag, int n_terms, const int* types,
+                            const double* sills, const double* ranges, double min_vg_val,
+                            void* stream);
+
+int spx_copy_2d_arr_at_idxs_dev(const double* arr, int64_t arr_cols,
+                                const int64_t* row_idxs, int64_t n_row_idxs,
+                                const int64_t* col_idxs, int64_t n_col_idxs,
+                                double* subset_arr, int64_t subset_cols, void* stream);
+
+/* ---------------- (3) engine, device pointers --------------------------- */
+
+/* A variogram as numbers (host struct, passed by pointer). */
+typedef struct spx_vg {
+    int32_t n_terms;
+    int32_t types[SPX_VG_MAX_TERMS];
+    double sills[SPX_VG_MAX_TERMS];
+    double ranges[SPX_VG_MAX_TERMS]; /* already clamped to >= 1e-5 */
+} spx_vg;
+
+/* Rows of the packed coefficient matrix are grouped in M-tiles of
+ * SPX_BM rows; element (row, col) of a matrix with kpad columns lives at
+ *   ((row / SPX_BM) * (kpad / 4) + col / 4) * (SPX_BM * 4)
+ *     + ((row % SPX_BM) / 8) * 32 + (row % 8) * 4 + col % 4
+ * i.e. 8x4 DMMA A-fragments stored lane-major so that one bulk copy brings a
+ * whole (M-tile, k-chunk) stage into shared memory. */
+#define SPX_BM 256
+int64_t spx_coef_offset(int64_t row, int64_t col, int64_t kpad);
+
+/* Batched kriging systems (one per availability group x variogram x kind).
+ * All arrays are device pointers; per-system arrays have n_sys entries.
+ *   sys_n      stations in the system          sys_kind   SPX_KRG_*
+ *   sys_vg     index into vgs[]                sys_stn_off offset into stn_list
+ *   sys_w_off  offset (doubles) of the column-major m x m workspace, m = n + k
+ *   sys_piv_off offset (int32) of the pivot vector
+ * Assembly follows interp/steps.py:170-243 with the variogram evaluated
+ * directly from station coordinates (cyth/interpmthds.pyx:123-226 fused). */
+typedef struct spx_systems {
+    int32_t n_sys;
+    int32_t n_drifts;
+    const int32_t* sys_n;
+    const int32_t* sys_kind;
+    const int32_t* sys_vg;
+    const int64_t* sys_stn_off;
+    const int64_t* sys_w_off;
+    const int64_t* sys_piv_off;
+    const int32_t* stn_list;   /* station indices, ascending per system */
+    const double* stn_x;
+    const double* stn_y;
+    const double* stn_drift;   /* [n_stn, n_drifts] or NULL */
+    double* work;              /* matrices */
+    int32_t* piv;              /* pivots */
+    int32_t* info;             /* [n_sys] 0 ok, >0 = zero pivot at that column */
+} spx_systems;
+
+int spx_krige_assemble_dev(const spx_systems* s, const spx_vg* vgs, int n_vgs,
+                           double min_vg_val, void* stream);
+
+/* LU with partial pivoting, one thread block per system (replaces
+ * np.linalg.pinv at interp/steps.py:351 for non-singular systems). */
+int spx_krige_factor_dev(const spx_systems* s, void* stream);
+
+/* Right-hand sides.  rhs_kind: 0 = data row (rhs_arg = step index into
+ * data[n_steps, n_stn]; NaN never read because only available stations are
+ * listed), 1 = ones over the stations, 2 = unit vector e_{rhs_arg}.
+ * The solution x of A x = b is scattered into the packed coefficient matrix
+ * row rhs_row: station entries to column stn_list[i], border entries to column
+ * n_stn + i.  For kind 1 additionally resid[rhs] = ||x - e_n||_1 (the deviation
+ * of sum(lambda) from 1 per unit of right-hand side). */
+typedef struct spx_rhs {
+    int32_t n_rhs;
+    const int32_t* rhs_sys;
+    const int32_t* rhs_kind;
+    const int32_t* rhs_arg;
+    const int64_t* rhs_row;
+    const double* data;   /* [n_steps, n_stn] */
+    int32_t n_stn;
+    int32_t kpad;
+    double* coef;         /* packed, zero-initialised by the caller */
+    double* resid;        /* [n_rhs] or NULL */
+} spx_rhs;
+
+int spx_krige_solve_dev(const spx_systems* s, const spx_rhs* r, void* stream);
+
+/* The fused estimate contraction
+ *     Z[row, cell] = sum_k coef[row, k] * B[k, cell]
+ * B is never stored: each thread block generates its [kpad x cells] tile in
+ * shared memory from coordinates (distance -> variogram / IDW weight; border
+ * rows: ones, drifts), keeps it resident and sweeps all rows with DMMA
+ * (mma.sync m8n8k4 f64) while coefficient stages arrive by bulk async copy.
+ * Replaces interp/steps.py:403-435 (kriging) and :293-313 (IDW). */
+#define SPX_GEN_VG 0   /* B[k, c] = vg(dist) (covar: sum sill - vg) */
+#define SPX_GEN_IDW 1  /* B[k, c] = (dist / dist_scale) ** -idw_exp */
+
+#define SPX_EPI_FIELD 0      /* out[row_dst, cell_pos] = clamp(Z)              */
+#define SPX_EPI_AUX 1        /* aux[row_dst, cell] = Z  (f64)                   */
+#define SPX_EPI_FIELD_DIV 2  /* out[row_dst, cell_pos] = clamp(Z / aux[row_aux, cell]) */
+
+typedef struct spx_gemm {
+    const double* coef;      /* packed, segment start (row multiple of SPX_BM) */
+    int64_t n_rows;          /* rows in the segment (last M-tile may be partial) */
+    int32_t kpad;            /* multiple of 4, >= n_stn + n_border */
+    int32_t n_stn;
+    int32_t n_border;        /* 0 SK/IDW, 1 OK, 1 + n_drifts EDK */
+    const double* stn_x;
+    const double* stn_y;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    const double* cell_drift; /* [n_border - 1, n_cells] or NULL */
+    int32_t gen;              /* SPX_GEN_* */
+    int32_t covar_flag;
+    spx_vg vg;
+    double min_vg_val;
+    double idw_exp;
+    double dist_scale;
+    int32_t epi;              /* SPX_EPI_* */
+    const int32_t* row_dst;   /* [n_rows] output row (time index / aux slot), <0 skip */
+    const int32_t* row_aux;   /* [n_rows] aux slot for SPX_EPI_FIELD_DIV */
+    void* out;                /* float or double field [*, out_ld] */
+    int64_t out_ld;
+    int32_t out_f64;
+    const int32_t* cell_pos;  /* [n_cells] column in the field, NULL = identity */
+    double* aux;              /* [slots, n_cells] */
+    int32_t has_lo, has_hi;
+    double lo, hi;
+} spx_gemm;
+
+int spx_estimate_gemm_dev(const spx_gemm* g, void* stream);
+/* Launch geometry actually used for a given problem (for reporting). */
+int spx_estimate_gemm_config(const spx_gemm* g, int* cells_per_block, int* n_stages,
+                             int* smem_bytes, int* grid);
+
+/* Pack a dense row-major [n_rows, n_cols] matrix (NaN -> 0 if nan_to_zero;
+ * mask_mode: write 1.0 where finite, 0.0 where NaN) into the packed
+ * coefficient layout starting at row row0. */
+int spx_pack_rows_dev(const double* src, int64_t src_ld, const int32_t* src_rows,
+                      int64_t n_rows, int32_t n_cols, int32_t kpad, int mask_mode,
+                      double* coef, int64_t row0, void* stream);
+
+/* Nearest available station per (group, cell): argmin of the IEEE distance
+ * sqrt(dx*dx + dy*dy), first index on ties (np.argmin, interp/steps.py:288).
+ * grp_mask [n_grps, n_stn] uint8.  nnb [n_grps, n_cells] int32. */
+int spx_nnb_index_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                      const uint8_t* grp_mask, int32_t n_grps,
+                      const double* cell_x, const double* cell_y, int64_t n_cells,
+                      int32_t* nnb, void* stream);
+
+/* out[row_dst[r], cell_pos[c]] = clamp(data[row_step[r], nnb[row_grp[r], c]])
+ * for every listed row; if fail != NULL only where fail[row_fail[r], c] != 0
+ * (the kriging -> NNB fallback of interp/steps.py:418-426). */
+int spx_nnb_gather_dev(const double* data, int32_t n_stn, const int32_t* nnb,
+                       const int32_t* row_step, const int32_t* row_grp,
+                       const int32_t* row_dst, int64_t n_rows,
+                       const uint8_t* fail, const int32_t* row_fail,
+                       int64_t n_cells, const int32_t* cell_pos,
+                       void* out, int64_t out_ld, int32_t out_f64,
+                       int32_t has_lo, int32_t has_hi, double lo, double hi, void* stream);
+
+/* out[row_dst[r], cell_pos[:]] = clamp(vals[r])   (station-mean / single
+ * station steps, interp/steps.py:282-283, :325-331, :312-313) */
+int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows,
+                      int64_t n_cells, const int32_t* cell_pos,
+                      void* out, int64_t out_ld, int32_t out_f64,
+                      int32_t has_lo, int32_t has_hi, double lo, double hi, void* stream);
+
+/* fail[slot, c] = !isclose(aux[slot, c], 1.0) (rtol 1e-5, atol 1e-8, NaN ->
+ * fail) OR cell_bad[c] -- interp/steps.py:418. */
+int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
+                         const uint8_t* cell_bad, uint8_t* fail, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_B200_H */

@@ -1,0 +1,200 @@
+"""ctypes binding of libspx_b200.so (the C-ABI declared in include/spx_b200.h).
+
+The product path has NO CPU fallback: if the library is missing, or a compute
+entry point is called without a CUDA device, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / 'lib' / 'libspx_b200.so'
+
+SPX_VG_MAX_TERMS = 8
+SPX_BM = 256
+VG_NAMES = ('Rng', 'Nug', 'Sph', 'Exp', 'Lin', 'Gau', 'Pow', 'Hol')
+KRG_KINDS = {'OK': 0, 'SK': 1, 'EDK': 2}
+GEN_VG, GEN_IDW = 0, 1
+EPI_FIELD, EPI_AUX, EPI_FIELD_DIV = 0, 1, 2
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class SpxError(RuntimeError):
+    pass
+
+
+class spx_vg(C.Structure):
+    _fields_ = [('n_terms', C.c_int32),
+                ('types', C.c_int32 * SPX_VG_MAX_TERMS),
+                ('sills', C.c_double * SPX_VG_MAX_TERMS),
+                ('ranges', C.c_double * SPX_VG_MAX_TERMS)]
+
+
+# numpy mirror of spx_vg for device upload (same layout as the C struct)
+VG_DTYPE = np.dtype([('n_terms', np.int32), ('types', np.int32, SPX_VG_MAX_TERMS),
+                     ('sills', np.float64, SPX_VG_MAX_TERMS),
+                     ('ranges', np.float64, SPX_VG_MAX_TERMS)], align=True)
+assert VG_DTYPE.itemsize == C.sizeof(spx_vg), (VG_DTYPE.itemsize, C.sizeof(spx_vg))
+
+
+class spx_systems(C.Structure):
+    _fields_ = [('n_sys', C.c_int32), ('n_drifts', C.c_int32),
+                ('sys_n', C.c_void_p), ('sys_kind', C.c_void_p), ('sys_vg', C.c_void_p),
+                ('sys_stn_off', C.c_void_p), ('sys_w_off', C.c_void_p),
+                ('sys_piv_off', C.c_void_p), ('stn_list', C.c_void_p),
+                ('stn_x', C.c_void_p), ('stn_y', C.c_void_p), ('stn_drift', C.c_void_p),
+                ('work', C.c_void_p), ('piv', C.c_void_p), ('info', C.c_void_p)]
+
+
+class spx_rhs(C.Structure):
+    _fields_ = [('n_rhs', C.c_int32),
+                ('rhs_sys', C.c_void_p), ('rhs_kind', C.c_void_p), ('rhs_arg', C.c_void_p),
+                ('rhs_row', C.c_void_p), ('data', C.c_void_p),
+                ('n_stn', C.c_int32), ('kpad', C.c_int32),
+                ('coef', C.c_void_p), ('resid', C.c_void_p)]
+
+
+class spx_gemm(C.Structure):
+    _fields_ = [('coef', C.c_void_p), ('n_rows', C.c_int64),
+                ('kpad', C.c_int32), ('n_stn', C.c_int32), ('n_border', C.c_int32),
+                ('stn_x', C.c_void_p), ('stn_y', C.c_void_p),
+                ('cell_x', C.c_void_p), ('cell_y', C.c_void_p), ('n_cells', C.c_int64),
+                ('cell_drift', C.c_void_p),
+                ('gen', C.c_int32), ('covar_flag', C.c_int32),
+                ('vg', spx_vg),
+                ('min_vg_val', C.c_double), ('idw_exp', C.c_double), ('dist_scale', C.c_double),
+                ('epi', C.c_int32),
+                ('row_dst', C.c_void_p), ('row_aux', C.c_void_p),
+                ('out', C.c_void_p), ('out_ld', C.c_int64), ('out_f64', C.c_int32),
+                ('cell_pos', C.c_void_p), ('aux', C.c_void_p),
+                ('has_lo', C.c_int32), ('has_hi', C.c_int32),
+                ('lo', C.c_double), ('hi', C.c_double)]
+
+
+_SIGS = {
+    'spx_version': (C.c_int, []),
+    'spx_last_error': (C.c_char_p, []),
+    'spx_device_count': (C.c_int, []),
+    'spx_parse_vg_str': (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_i32p, c_i32p, c_f64p, c_f64p]),
+    'spx_fill_dists_2d_mat': (C.c_int, [c_f64p, c_f64p, C.c_int64, c_f64p, c_f64p, C.c_int64, c_f64p]),
+    'spx_fill_vg_var_arr': (C.c_int, [c_f64p, c_f64p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                      C.c_char_p, C.c_double]),
+    'spx_copy_2d_arr_at_idxs': (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_i64p, C.c_int64, c_i64p,
+                                          C.c_int64, c_f64p, C.c_int64, C.c_int64]),
+    'spx_fill_theo_vg_vals': (C.c_int, [C.c_char_p, c_f64p, C.c_int64, C.c_double, C.c_double, c_f64p]),
+    'spx_fill_dists_one_pt': (C.c_int, [C.c_double, C.c_double, c_f64p, c_f64p, C.c_int64, c_f64p]),
+    'spx_fill_wts_and_sum': (C.c_int, [c_f64p, c_f64p, C.c_int64, C.c_double, c_f64p]),
+    'spx_get_mults_sum': (C.c_int, [c_f64p, c_f64p, C.c_int64, c_f64p]),
+    'spx_fill_dists_2d_mat_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'spx_fill_vg_var_arr_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                          C.c_int, C.c_int, c_i32p, c_f64p, c_f64p, C.c_double,
+                                          C.c_void_p]),
+    'spx_copy_2d_arr_at_idxs_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_void_p]),
+    'spx_coef_offset': (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
+    'spx_krige_assemble_dev': (C.c_int, [C.POINTER(spx_systems), C.c_void_p, C.c_int, C.c_double,
+                                         C.c_void_p]),
+    'spx_krige_factor_dev': (C.c_int, [C.POINTER(spx_systems), C.c_void_p]),
+    'spx_krige_solve_dev': (C.c_int, [C.POINTER(spx_systems), C.POINTER(spx_rhs), C.c_void_p]),
+    'spx_estimate_gemm_dev': (C.c_int, [C.POINTER(spx_gemm), C.c_void_p]),
+    'spx_estimate_gemm_config': (C.c_int, [C.POINTER(spx_gemm), c_i32p, c_i32p, c_i32p, c_i32p]),
+    'spx_pack_rows_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    'spx_nnb_index_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'spx_nnb_gather_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    'spx_fill_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_double, C.c_double, C.c_void_p]),
+    'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+}
+
+EXPORTED = tuple(_SIGS)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SpxError(
+            f'{LIB_PATH} is missing: build it with `python -m spinterps_b200.build` '
+            '(there is no CPU fallback)')
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().spx_last_error().decode(errors='replace')
+        raise SpxError(f'{what or "spx call"} failed (code {rc}): {msg}')
+
+
+def require_gpu():
+    if load().spx_device_count() < 1:
+        raise SpxError('no CUDA device visible: the spinterps_b200 compute path has no CPU fallback')
+
+
+def f64p(a):
+    return a.ctypes.data_as(c_f64p)
+
+
+def i64p(a):
+    return a.ctypes.data_as(c_i64p)
+
+
+def parse_vg_str(vg_str, clamp_range=True):
+    """-> list of (type_code, sill, range); raises SpxError on a malformed string."""
+    lib = load()
+    n = C.c_int32(0)
+    types = (C.c_int32 * SPX_VG_MAX_TERMS)()
+    sills = (C.c_double * SPX_VG_MAX_TERMS)()
+    ranges = (C.c_double * SPX_VG_MAX_TERMS)()
+    rc = lib.spx_parse_vg_str(str(vg_str).encode(), int(bool(clamp_range)), SPX_VG_MAX_TERMS,
+                              C.byref(n), types, sills, ranges)
+    check(rc, f'parse_vg_str({vg_str!r})')
+    return [(int(types[i]), float(sills[i]), float(ranges[i])) for i in range(n.value)]
+
+
+def make_vg(vg_str):
+    v = spx_vg()
+    terms = parse_vg_str(vg_str)
+    v.n_terms = len(terms)
+    for i, (t, s, r) in enumerate(terms):
+        v.types[i] = t
+        v.sills[i] = s
+        v.ranges[i] = r
+    return v
+
+
+def vgs_to_numpy(vg_strs):
+    arr = np.zeros(len(vg_strs), dtype=VG_DTYPE)
+    for k, s in enumerate(vg_strs):
+        terms = parse_vg_str(s)
+        arr[k]['n_terms'] = len(terms)
+        for i, (t, sill, rng) in enumerate(terms):
+            arr[k]['types'][i] = t
+            arr[k]['sills'][i] = sill
+            arr[k]['ranges'][i] = rng
+    return arr

@@ -1,0 +1,73 @@
+"""Build libspx_b200.so in-tree with nvcc for sm_100a.
+
+    python -m spinterps_b200.build [--force]
+
+The shared library lands in spinterps_b200/lib/ (git-ignored, travels to the GPU
+box with the gpurun snapshot).  nvcc cross-compiles without a GPU.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / 'csrc'
+LIBDIR = PKG / 'lib'
+LIB = LIBDIR / 'libspx_b200.so'
+SOURCES = ['spx_basic.cu', 'spx_solve.cu', 'spx_gemm.cu', 'spx_misc.cu']
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+    '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default',
+    '-Xptxas', '-v', '--fmad=true']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def _digest():
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) +
+                    [ROOT / 'include' / 'spx_b200.h', Path(__file__)]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    LIBDIR.mkdir(exist_ok=True)
+    stamp = LIBDIR / 'build.stamp'
+    dig = _digest()
+    if (not force) and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+        return LIB
+    objs = []
+    log = []
+    for src in SOURCES:
+        obj = LIBDIR / (src[:-3] + '.o')
+        cmd = [_nvcc(), *NVCC_FLAGS, '-I', str(ROOT / 'include'), '-I', str(CSRC),
+               '-c', str(CSRC / src), '-o', str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f'nvcc failed on {src}')
+        objs.append(str(obj))
+    cmd = [_nvcc(), '-shared', '-o', str(LIB), *objs, '-lcudart']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('link failed')
+    (LIBDIR / 'ptxas.log').write_text('\n'.join(log))
+    stamp.write_text(dig)
+    if verbose:
+        print('\n'.join(log))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

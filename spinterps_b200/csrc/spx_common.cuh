@@ -1,0 +1,116 @@
+// Shared device helpers for the spinterps B200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "spx_b200.h"
+
+namespace spx {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SPX_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return spx::cuda_fail(e__, #call); \
+    } while (0)
+
+#define SPX_CHECK_LAUNCH(name)                                \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return spx::cuda_fail(e__, name); \
+    } while (0)
+
+// Variogram in kernel-parameter form (by value).
+struct VgDev {
+    int n_terms;
+    int types[SPX_VG_MAX_TERMS];
+    double sills[SPX_VG_MAX_TERMS];
+    double ranges[SPX_VG_MAX_TERMS];
+};
+
+inline VgDev to_dev(const spx_vg& v) {
+    VgDev d;
+    d.n_terms = v.n_terms;
+    for (int i = 0; i < SPX_VG_MAX_TERMS; ++i) {
+        d.types[i] = v.types[i];
+        d.sills[i] = v.sills[i];
+        d.ranges[i] = v.ranges[i];
+    }
+    return d;
+}
+
+// IEEE distance without FMA contraction so that index decisions taken on it
+// (nearest neighbour) reproduce NumPy's ((dx**2) + (dy**2)) ** 0.5 bit for bit
+// (interp/grps.py:158-160, cyth/interpmthds.pyx:141).
+__device__ __forceinline__ double dist_rn(double x1, double y1, double x2, double y2) {
+    const double dx = __dsub_rn(x1, x2);
+    const double dy = __dsub_rn(y1, y2);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+// One nested-variogram term, cyth/interpmthds.pyx:38-83.  Same expression
+// structure as the reference (quirks Q1, Q3 of SURVEY.md section 8a).
+__device__ __forceinline__ double vg_term(int type, double h, double r, double s) {
+    switch (type) {
+        case SPX_VG_RNG:
+            return h;
+        case SPX_VG_NUG:
+            return s;  // for every h, including 0
+        case SPX_VG_SPH: {
+            if (h >= r) return s;
+            const double a = (1.5 * h) / r;
+            const double b = (h * h * h) / (2 * (r * r * r));
+            return s * (a - b);
+        }
+        case SPX_VG_EXP:
+            return s * (1 - exp(-3 * h / r));
+        case SPX_VG_LIN:
+            return (h > r) ? s : s * (h / r);
+        case SPX_VG_GAU:
+            return s * (1 - exp(-3 * ((h * h) / (r * r))));
+        case SPX_VG_POW:
+            return s * pow(h, r);
+        case SPX_VG_HOL: {
+            if (h == 0) return 0.0;
+            const double a = (CUDART_PI * h) / r;
+            return s * (1 - (sin(a) / a));
+        }
+        default:
+            return CUDART_NAN;
+    }
+}
+
+// Sum over nested terms + covariance flip + min_vg_val cut,
+// cyth/interpmthds.pyx:162-216.
+__device__ __forceinline__ double vg_eval(const VgDev& vg, double h, int covar_flag,
+                                          double min_vg_val) {
+    double v = 0.0;
+    if (covar_flag) {
+        for (int t = 0; t < vg.n_terms; ++t)
+            v += vg.sills[t] - vg_term(vg.types[t], h, vg.ranges[t], vg.sills[t]);
+    } else {
+        for (int t = 0; t < vg.n_terms; ++t)
+            v += vg_term(vg.types[t], h, vg.ranges[t], vg.sills[t]);
+    }
+    if (v <= min_vg_val) v = 0.0;
+    return v;
+}
+
+__device__ __forceinline__ double clampd(double v, int has_lo, int has_hi, double lo, double hi) {
+    // NaN-safe like interp/steps.py:466-476 (comparisons with NaN are false)
+    if (has_lo && v < lo) v = lo;
+    if (has_hi && v > hi) v = hi;
+    return v;
+}
+
+__device__ __forceinline__ void store_out(void* out, int64_t idx, double v, int out_f64) {
+    if (out_f64)
+        reinterpret_cast<double*>(out)[idx] = v;
+    else
+        reinterpret_cast<float*>(out)[idx] = static_cast<float>(v);
+}
+
+}  // namespace spx

@@ -1,0 +1,426 @@
+// Fused "fill + contract" estimate kernel (the hot loop of the whole path).
+//
+//   Z[row, cell] = sum_k coef[row, k] * B[k, cell]
+//
+// * B (the dst<->station variogram / IDW-weight matrix with its border rows) is
+//   NEVER written to HBM: each persistent thread block owns a tile of NT*8
+//   cells, generates the full-K tile [kpad x NT*8] from coordinates once into
+//   shared memory (already in DMMA B-fragment order) and keeps it resident.
+// * The block then sweeps every coefficient row: 8 consumer warps x 32 rows per
+//   M-tile, FP64 tensor-core MMA (mma.sync.aligned.m8n8k4.f64 -> SASS
+//   DMMA.8x8x4), accumulators in registers.
+// * Coefficients arrive pre-packed in A-fragment order; a producer warp streams
+//   16 KB stages (256 rows x 8 k) with cp.async.bulk (TMA bulk copy, SASS
+//   UBLKCP) into an mbarrier full/empty ring.
+// * Epilogue: clamp (steps.py:466-476), cast, scatter to the masked field; or
+//   raw FP64 to an auxiliary buffer (sum-of-weights rows); or divide by such a
+//   row (IDW normalisation).
+//
+// Replaces interp/steps.py:403-435 (kriging estimate) and :293-313 (IDW)
+// together with the dst<->station fills of :639-650 (pyx:123-226).
+#include "spx_common.cuh"
+
+namespace spx {
+
+constexpr int CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int BK = 8;                          // k per pipeline stage
+constexpr int STAGE_DOUBLES = SPX_BM * BK;     // 2048 doubles = 16 KB
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+
+struct GemmArgs {
+    const double* coef;
+    int64_t n_rows;
+    int kpad, n_stn, n_border;
+    const double* stn_x;
+    const double* stn_y;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    const double* cell_drift;
+    int gen, covar_flag;
+    VgDev vg;
+    double min_vg_val, idw_exp, inv_scale;
+    int epi;
+    const int32_t* row_dst;
+    const int32_t* row_aux;
+    void* out;
+    int64_t out_ld;
+    int out_f64;
+    const int32_t* cell_pos;
+    double* aux;
+    int has_lo, has_hi;
+    double lo, hi;
+    int n_stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// (dist / scale) ** -p from the squared distance; small integer exponents avoid
+// pow().  Reference: w = 1 / d**p on max-normalised distances
+// (interp/steps.py:297-303, pyx:792); the common scale cancels in the ratio.
+__device__ __forceinline__ double idw_weight(double d2, double inv_scale, double p) {
+    const double q2 = d2 * inv_scale * inv_scale;  // (d/scale)^2
+    if (p == 2.0) return 1.0 / q2;
+    const double q = sqrt(q2);
+    if (p == 1.0) return 1.0 / q;
+    if (p == 3.0) return 1.0 / (q2 * q);
+    if (p == 4.0) return 1.0 / (q2 * q2);
+    if (p == 5.0) return 1.0 / (q2 * q2 * q);
+    return 1.0 / pow(q, p);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int BN = NT * 8;
+    const int KC = a.kpad >> 2;
+    const int n_ksteps = a.kpad / BK;
+    const int n_stages = a.n_stages;
+
+    double* Bs = reinterpret_cast<double*>(smem_raw);                  // [KC][NT][32]
+    double* As = Bs + (size_t)KC * NT * 32;                            // [stage][2][32][32]
+    double* sx = As + (size_t)n_stages * STAGE_DOUBLES;                // [kpad] station x
+    double* sy = sx + a.kpad;                                          // [kpad] station y
+    double* cx = sy + a.kpad;                                          // [BN]
+    double* cy = cx + BN;                                              // [BN]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(cy + BN);         // [n_stages]
+    uint64_t* empty_bar = full_bar + n_stages;                         // [n_stages]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int k = tid; k < a.kpad; k += GEMM_THREADS) {
+        sx[k] = (k < a.n_stn) ? a.stn_x[k] : 0.0;
+        sy[k] = (k < a.n_stn) ? a.stn_y[k] : 0.0;
+    }
+    __syncthreads();
+
+    const int64_t n_ctiles = (a.n_cells + BN - 1) / BN;
+    const int64_t n_mtiles = (a.n_rows + SPX_BM - 1) / SPX_BM;
+    uint32_t it = 0;  // global stage counter (same sequence in producer and consumers)
+
+    for (int64_t ct = blockIdx.x; ct < n_ctiles; ct += gridDim.x) {
+        const int64_t cell0 = ct * BN;
+        // ---- generate the resident B tile --------------------------------
+        __syncthreads();  // previous tile fully consumed
+        if (tid < BN) {
+            const int64_t c = cell0 + tid;
+            cx[tid] = (c < a.n_cells) ? a.cell_x[c] : 0.0;
+            cy[tid] = (c < a.n_cells) ? a.cell_y[c] : 0.0;
+        }
+        __syncthreads();
+        const int n_ent = KC * NT * 32;
+        for (int idx = tid; idx < n_ent; idx += GEMM_THREADS) {
+            const int ln = idx & 31;
+            const int q = idx >> 5;
+            const int j = q % NT;
+            const int kc = q / NT;
+            const int k = kc * 4 + (ln & 3);
+            const int n = j * 8 + (ln >> 2);
+            const int64_t c = cell0 + n;
+            double v = 0.0;
+            if (c < a.n_cells) {
+                if (k < a.n_stn) {
+                    if (a.gen == SPX_GEN_VG) {
+                        const double h = dist_rn(cx[n], cy[n], sx[k], sy[k]);
+                        v = vg_eval(a.vg, h, a.covar_flag, a.min_vg_val);
+                    } else {
+                        const double dx = cx[n] - sx[k], dy = cy[n] - sy[k];
+                        v = idw_weight(dx * dx + dy * dy, a.inv_scale, a.idw_exp);
+                    }
+                } else if (k < a.n_stn + a.n_border) {
+                    const int b = k - a.n_stn;
+                    v = (b == 0) ? 1.0 : a.cell_drift[(int64_t)(b - 1) * a.n_cells + c];
+                }
+            }
+            Bs[idx] = v;
+        }
+        __syncthreads();
+
+        if (warp == CONSUMER_WARPS) {
+            // ---- producer: stream coefficient stages ----------------------
+            if (lane == 0) {
+                uint32_t pit = it;
+                for (int64_t mt = 0; mt < n_mtiles; ++mt) {
+                    const double* src = a.coef + (size_t)mt * KC * (SPX_BM * 4);
+                    for (int ks = 0; ks < n_ksteps; ++ks, ++pit) {
+                        const int s = pit % n_stages;
+                        const uint32_t ph = (pit / n_stages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        bulk_g2s(As + (size_t)s * STAGE_DOUBLES, src + (size_t)ks * STAGE_DOUBLES,
+                                 STAGE_BYTES, &full_bar[s]);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- consumers: DMMA sweep over all rows ---------------------
+            const int g = lane >> 2, t4 = lane & 3;
+            uint32_t cit = it;
+            for (int64_t mt = 0; mt < n_mtiles; ++mt) {
+                const int64_t row_base = mt * SPX_BM + warp * 32;
+                const bool active = row_base < a.n_rows;
+                double acc[4][NT][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+                for (int ks = 0; ks < n_ksteps; ++ks, ++cit) {
+                    const int s = cit % n_stages;
+                    const uint32_t ph = (cit / n_stages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    if (active) {
+                        const double* Ast = As + (size_t)s * STAGE_DOUBLES;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            double af[4], bf[NT];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                af[i] = Ast[(kk * 32 + warp * 4 + i) * 32 + lane];
+                            const double* Bk = Bs + (size_t)(ks * 2 + kk) * NT * 32;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) bf[j] = Bk[j * 32 + lane];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int j = 0; j < NT; ++j)
+                                    dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                }
+                if (!active) continue;
+                // ---- epilogue -------------------------------------------
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t R = row_base + i * 8 + g;
+                    if (R >= a.n_rows) continue;
+                    const int dst = a.row_dst[R];
+                    if (dst < 0) continue;
+                    const int64_t aux_row =
+                        (a.epi == SPX_EPI_FIELD_DIV) ? (int64_t)a.row_aux[R] * a.n_cells : 0;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int64_t c = cell0 + j * 8 + t4 * 2 + e;
+                            if (c >= a.n_cells) continue;
+                            double v = acc[i][j][e];
+                            if (a.epi == SPX_EPI_AUX) {
+                                a.aux[(int64_t)dst * a.n_cells + c] = v;
+                            } else {
+                                if (a.epi == SPX_EPI_FIELD_DIV) v = v / a.aux[aux_row + c];
+                                v = clampd(v, a.has_lo, a.has_hi, a.lo, a.hi);
+                                const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+                                store_out(a.out, (int64_t)dst * a.out_ld + col, v, a.out_f64);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        it += (uint32_t)(n_mtiles * n_ksteps);
+    }
+}
+
+static size_t gemm_smem_bytes(int kpad, int nt, int n_stages) {
+    const size_t dbl = (size_t)(kpad / 4) * nt * 32 + (size_t)n_stages * STAGE_DOUBLES +
+                       2 * (size_t)kpad + 2 * (size_t)nt * 8;
+    return dbl * 8 + 2 * (size_t)n_stages * 8;
+}
+
+struct GemmCfg {
+    int nt, n_stages, grid;
+    size_t smem;
+};
+
+static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
+    int dev = 0, max_smem = 0, n_sm = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    static const int nts[] = {8, 6, 5, 4, 3, 2, 1};
+    for (int nt : nts) {
+        for (int st = 4; st >= 2; --st) {
+            if (st == 2 && nt > 1) continue;  // prefer fewer cells over a 2-deep ring
+            const size_t sm = gemm_smem_bytes(g->kpad, nt, st);
+            if (sm <= (size_t)max_smem) {
+                // do not use tiles wider than the problem
+                int use_nt = nt;
+                while (use_nt > 1 && (int64_t)(use_nt - 1) * 8 >= g->n_cells) --use_nt;
+                if (use_nt != nt) continue;
+                cfg->nt = nt;
+                cfg->n_stages = st;
+                cfg->smem = sm;
+                const int64_t tiles = (g->n_cells + nt * 8 - 1) / (nt * 8);
+                cfg->grid = (int)(tiles < n_sm ? tiles : n_sm);
+                return SPX_OK;
+            }
+        }
+    }
+    set_error("estimate_gemm: kpad=%d does not fit in %d bytes of shared memory", g->kpad,
+              max_smem);
+    return SPX_ENOMEM;
+}
+
+template <int NT>
+static int launch(const GemmArgs& a, const GemmCfg& cfg, cudaStream_t st) {
+    SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)cfg.smem));
+    k_estimate_gemm<NT><<<cfg.grid, GEMM_THREADS, cfg.smem, st>>>(a);
+    SPX_CHECK_LAUNCH("k_estimate_gemm");
+    return SPX_OK;
+}
+
+static int validate(const spx_gemm* g) {
+    if (!g) {
+        set_error("estimate_gemm: null argument");
+        return SPX_EINVAL;
+    }
+    if (g->kpad <= 0 || g->kpad % BK != 0 || g->kpad < g->n_stn + g->n_border) {
+        set_error("estimate_gemm: kpad=%d must be a multiple of %d and >= n_stn + n_border = %d",
+                  g->kpad, BK, g->n_stn + g->n_border);
+        return SPX_EINVAL;
+    }
+    if (g->n_border > 1 && !g->cell_drift) {
+        set_error("estimate_gemm: drift rows requested without cell_drift");
+        return SPX_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(g->coef) & 15) != 0) {
+        set_error("estimate_gemm: coef must be 16-byte aligned");
+        return SPX_EINVAL;
+    }
+    if (g->gen == SPX_GEN_VG && (g->vg.n_terms < 0 || g->vg.n_terms > SPX_VG_MAX_TERMS)) {
+        set_error("estimate_gemm: bad variogram");
+        return SPX_EINVAL;
+    }
+    if (g->gen == SPX_GEN_IDW && !(g->dist_scale > 0)) {
+        set_error("estimate_gemm: dist_scale must be > 0");
+        return SPX_EINVAL;
+    }
+    return SPX_OK;
+}
+
+}  // namespace spx
+
+using namespace spx;
+
+extern "C" {
+
+int spx_estimate_gemm_config(const spx_gemm* g, int* cells_per_block, int* n_stages,
+                             int* smem_bytes, int* grid) {
+    int rc = validate(g);
+    if (rc) return rc;
+    GemmCfg cfg;
+    if ((rc = pick_config(g, &cfg))) return rc;
+    if (cells_per_block) *cells_per_block = cfg.nt * 8;
+    if (n_stages) *n_stages = cfg.n_stages;
+    if (smem_bytes) *smem_bytes = (int)cfg.smem;
+    if (grid) *grid = cfg.grid;
+    return SPX_OK;
+}
+
+int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
+    int rc = validate(g);
+    if (rc) return rc;
+    if (g->n_rows == 0 || g->n_cells == 0) return SPX_OK;
+    GemmCfg cfg;
+    if ((rc = pick_config(g, &cfg))) return rc;
+
+    GemmArgs a;
+    a.coef = g->coef;
+    a.n_rows = g->n_rows;
+    a.kpad = g->kpad;
+    a.n_stn = g->n_stn;
+    a.n_border = g->n_border;
+    a.stn_x = g->stn_x;
+    a.stn_y = g->stn_y;
+    a.cell_x = g->cell_x;
+    a.cell_y = g->cell_y;
+    a.n_cells = g->n_cells;
+    a.cell_drift = g->cell_drift;
+    a.gen = g->gen;
+    a.covar_flag = g->covar_flag;
+    a.vg = to_dev(g->vg);
+    a.min_vg_val = g->min_vg_val;
+    a.idw_exp = g->idw_exp;
+    a.inv_scale = (g->gen == SPX_GEN_IDW) ? 1.0 / g->dist_scale : 1.0;
+    a.epi = g->epi;
+    a.row_dst = g->row_dst;
+    a.row_aux = g->row_aux;
+    a.out = g->out;
+    a.out_ld = g->out_ld;
+    a.out_f64 = g->out_f64;
+    a.cell_pos = g->cell_pos;
+    a.aux = g->aux;
+    a.has_lo = g->has_lo;
+    a.has_hi = g->has_hi;
+    a.lo = g->lo;
+    a.hi = g->hi;
+    a.n_stages = cfg.n_stages;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cfg.nt) {
+        case 8: return launch<8>(a, cfg, st);
+        case 6: return launch<6>(a, cfg, st);
+        case 5: return launch<5>(a, cfg, st);
+        case 4: return launch<4>(a, cfg, st);
+        case 3: return launch<3>(a, cfg, st);
+        case 2: return launch<2>(a, cfg, st);
+        default: return launch<1>(a, cfg, st);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// Supporting kernels of the engine: coefficient packing, nearest-neighbour
+// index / gather, constant-row fill and the sum(lambda) ~ 1 check.
+#include "spx_common.cuh"
+
+namespace spx {
+
+__host__ __device__ __forceinline__ int64_t coef_offset2(int64_t row, int64_t col, int64_t kpad) {
+    return ((row / SPX_BM) * (kpad >> 2) + (col >> 2)) * (int64_t)(SPX_BM * 4) +
+           ((row % SPX_BM) >> 3) * 32 + (row & 7) * 4 + (col & 3);
+}
+
+// One thread per (row, column); consecutive threads walk the columns of a row
+// (coalesced reads of the dense source).
+__global__ void __launch_bounds__(256) k_pack_rows(const double* __restrict__ src, int64_t src_ld,
+                                                   const int32_t* __restrict__ src_rows,
+                                                   int64_t n_rows, int n_cols, int kpad,
+                                                   int mask_mode, double* __restrict__ coef,
+                                                   int64_t row0) {
+    const int64_t total = n_rows * n_cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / n_cols;
+        const int c = (int)(i - r * n_cols);
+        const int64_t sr = src_rows ? (int64_t)src_rows[r] : r;
+        double v = src[sr * src_ld + c];
+        const bool isn = (v != v);
+        if (mask_mode)
+            v = isn ? 0.0 : 1.0;
+        else if (isn)
+            v = 0.0;
+        coef[coef_offset2(row0 + r, c, kpad)] = v;
+    }
+}
+
+// Nearest available station.  Block = 256 cells x one chunk of groups; station
+// coordinates and the group's availability bytes are staged in shared memory.
+constexpr int NNB_STN_TILE = 1024;
+
+__global__ void __launch_bounds__(256) k_nnb_index(const double* __restrict__ stn_x,
+                                                   const double* __restrict__ stn_y, int n_stn,
+                                                   const uint8_t* __restrict__ grp_mask,
+                                                   int n_grps, const double* __restrict__ cell_x,
+                                                   const double* __restrict__ cell_y,
+                                                   int64_t n_cells, int32_t* __restrict__ nnb) {
+    __shared__ double sx[NNB_STN_TILE];
+    __shared__ double sy[NNB_STN_TILE];
+    __shared__ uint8_t sm[NNB_STN_TILE];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double x = (c < n_cells) ? cell_x[c] : 0.0;
+    const double y = (c < n_cells) ? cell_y[c] : 0.0;
+    for (int gi = blockIdx.y; gi < n_grps; gi += gridDim.y) {
+        double best = CUDART_INF;
+        int bidx = -1;
+        for (int s0 = 0; s0 < n_stn; s0 += NNB_STN_TILE) {
+            const int ns = min(NNB_STN_TILE, n_stn - s0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+                sx[k] = stn_x[s0 + k];
+                sy[k] = stn_y[s0 + k];
+                sm[k] = grp_mask[(int64_t)gi * n_stn + s0 + k];
+            }
+            __syncthreads();
+            for (int k = 0; k < ns; ++k) {
+                if (!sm[k]) continue;
+                const double d = dist_rn(x, y, sx[k], sy[k]);
+                // np.argmin: first minimum; a NaN distance would win in NumPy but
+                // coordinates are asserted finite (interp/grps.py:44-45, :264-265)
+                if (d < best || bidx < 0) {
+                    best = d;
+                    bidx = s0 + k;
+                }
+            }
+        }
+        if (c < n_cells) nnb[(int64_t)gi * n_cells + c] = bidx;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nnb_gather(
+    const double* __restrict__ data, int n_stn, const int32_t* __restrict__ nnb,
+    const int32_t* __restrict__ row_step, const int32_t* __restrict__ row_grp,
+    const int32_t* __restrict__ row_dst, int64_t n_rows, const uint8_t* __restrict__ fail,
+    const int32_t* __restrict__ row_fail, int64_t n_cells, const int32_t* __restrict__ cell_pos,
+    void* __restrict__ out, int64_t out_ld, int out_f64, int has_lo, int has_hi, double lo,
+    double hi) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int64_t col = cell_pos ? (int64_t)cell_pos[c] : c;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        if (fail != nullptr && !fail[(int64_t)row_fail[r] * n_cells + c]) continue;
+        const int st = nnb[(int64_t)row_grp[r] * n_cells + c];
+        double v = data[(int64_t)row_step[r] * n_stn + st];
+        v = clampd(v, has_lo, has_hi, lo, hi);
+        store_out(out, (int64_t)row_dst[r] * out_ld + col, v, out_f64);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_rows(const double* __restrict__ vals,
+                                                   const int32_t* __restrict__ row_dst,
+                                                   int64_t n_rows, int64_t n_cells,
+                                                   const int32_t* __restrict__ cell_pos,
+                                                   void* __restrict__ out, int64_t out_ld,
+                                                   int out_f64, int has_lo, int has_hi, double lo,
+                                                   double hi) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int64_t col = cell_pos ? (int64_t)cell_pos[c] : c;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        const double v = clampd(vals[r], has_lo, has_hi, lo, hi);
+        store_out(out, (int64_t)row_dst[r] * out_ld + col, v, out_f64);
+    }
+}
+
+// np.isclose(a, 1.0): |a - 1| <= atol + rtol * |1| with rtol=1e-5, atol=1e-8;
+// NaN / inf are not close (interp/steps.py:418).
+__global__ void __launch_bounds__(256) k_lambda_check(const double* __restrict__ aux,
+                                                      int64_t n_slots, int64_t n_cells,
+                                                      const uint8_t* __restrict__ cell_bad,
+                                                      uint8_t* __restrict__ fail) {
+    const int64_t total = n_slots * n_cells;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const double a = aux[i];
+        bool ok = fabs(a - 1.0) <= (1e-8 + 1e-5);
+        if (!(a == a) || isinf(a)) ok = false;
+        if (cell_bad != nullptr && cell_bad[i % n_cells]) ok = false;
+        fail[i] = ok ? 0 : 1;
+    }
+}
+
+static inline unsigned grid_y(int64_t n) { return (unsigned)(n < 1 ? 1 : (n > 65535 ? 65535 : n)); }
+
+}  // namespace spx
+
+using namespace spx;
+
+extern "C" {
+
+int spx_pack_rows_dev(const double* src, int64_t src_ld, const int32_t* src_rows, int64_t n_rows,
+                      int32_t n_cols, int32_t kpad, int mask_mode, double* coef, int64_t row0,
+                      void* stream) {
+    if (n_cols > kpad || kpad % 4 != 0) {
+        set_error("pack_rows: n_cols=%d kpad=%d", n_cols, kpad);
+        return SPX_EINVAL;
+    }
+    const int64_t total = n_rows * n_cols;
+    if (total == 0) return SPX_OK;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    k_pack_rows<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, src_rows, n_rows, n_cols,
+                                                          kpad, mask_mode, coef, row0);
+    SPX_CHECK_LAUNCH("k_pack_rows");
+    return SPX_OK;
+}
+
+int spx_nnb_index_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                      const uint8_t* grp_mask, int32_t n_grps, const double* cell_x,
+                      const double* cell_y, int64_t n_cells, int32_t* nnb, void* stream) {
+    if (n_grps == 0 || n_cells == 0) return SPX_OK;
+    if (n_stn <= 0) {
+        set_error("nnb_index: no stations");
+        return SPX_EINVAL;
+    }
+    dim3 grid((unsigned)((n_cells + 255) / 256), grid_y(n_grps));
+    k_nnb_index<<<grid, 256, 0, (cudaStream_t)stream>>>(stn_x, stn_y, n_stn, grp_mask, n_grps,
+                                                        cell_x, cell_y, n_cells, nnb);
+    SPX_CHECK_LAUNCH("k_nnb_index");
+    return SPX_OK;
+}
+
+int spx_nnb_gather_dev(const double* data, int32_t n_stn, const int32_t* nnb,
+                       const int32_t* row_step, const int32_t* row_grp, const int32_t* row_dst,
+                       int64_t n_rows, const uint8_t* fail, const int32_t* row_fail,
+                       int64_t n_cells, const int32_t* cell_pos, void* out, int64_t out_ld,
+                       int32_t out_f64, int32_t has_lo, int32_t has_hi, double lo, double hi,
+                       void* stream) {
+    if (n_rows == 0 || n_cells == 0) return SPX_OK;
+    if (fail != nullptr && row_fail == nullptr) {
+        set_error("nnb_gather: fail without row_fail");
+        return SPX_EINVAL;
+    }
+    dim3 grid((unsigned)((n_cells + 255) / 256), grid_y(n_rows));
+    k_nnb_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(data, n_stn, nnb, row_step, row_grp,
+                                                         row_dst, n_rows, fail, row_fail, n_cells,
+                                                         cell_pos, out, out_ld, out_f64, has_lo,
+                                                         has_hi, lo, hi);
+    SPX_CHECK_LAUNCH("k_nnb_gather");
+    return SPX_OK;
+}
+
+int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows, int64_t n_cells,
+                      const int32_t* cell_pos, void* out, int64_t out_ld, int32_t out_f64,
+                      int32_t has_lo, int32_t has_hi, double lo, double hi, void* stream) {
+    if (n_rows == 0 || n_cells == 0) return SPX_OK;
+    dim3 grid((unsigned)((n_cells + 255) / 256), grid_y(n_rows));
+    k_fill_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(vals, row_dst, n_rows, n_cells, cell_pos,
+                                                        out, out_ld, out_f64, has_lo, has_hi, lo,
+                                                        hi);
+    SPX_CHECK_LAUNCH("k_fill_rows");
+    return SPX_OK;
+}
+
+int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
+                         const uint8_t* cell_bad, uint8_t* fail, void* stream) {
+    const int64_t total = n_slots * n_cells;
+    if (total == 0) return SPX_OK;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    k_lambda_check<<<blocks, 256, 0, (cudaStream_t)stream>>>(aux, n_slots, n_cells, cell_bad,
+                                                             fail);
+    SPX_CHECK_LAUNCH("k_lambda_check");
+    return SPX_OK;
+}
+
+}  // extern "C"

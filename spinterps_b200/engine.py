@@ -1,0 +1,643 @@
+"""GPU engine for one (time chunk x grid-row chunk) of the interpolation.
+
+This is the B200 replacement of the compute half of
+``SpInterpSteps.interpolate_subset`` (reference interp/steps.py:478-877).  The
+host side (this file) keeps the reference's *index* logic -- cell subsetting,
+availability groups, variogram clusters, per-step flags -- and turns it into
+dense descriptor arrays; all floating-point work runs in the sm_100a kernels of
+``csrc/`` through the C-ABI (include/spx_b200.h):
+
+  assemble -> LU factor -> solve          (one system per group x variogram)
+  fused variogram-fill + DMMA contraction  (dual form: Z = C . RHS^T)
+  fused IDW (same contraction with d**-p weights and a sum-of-weights row)
+  nearest neighbour index / gather, constant rows
+
+torch is used for device memory, streams and host<->device copies only.
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .vgs import check_full_nuggetness, vg_abs_bound
+
+_I32 = torch.int32
+_I64 = torch.int64
+_F64 = torch.float64
+
+
+def _pad_up(n, m):
+    return ((int(n) + m - 1) // m) * m
+
+
+def availability_groups(avail):
+    """Distinct rows of the [T, N] availability matrix in first-occurrence
+    order (interp/grps.py:57-101 groups steps by the set of non-NaN stations).
+
+    Returns grp_of_step [T] int32 and grp_mask [n_grps, N] bool.
+    """
+    T, N = avail.shape
+    packed = np.packbits(avail, axis=1)
+    keys = np.ascontiguousarray(packed).view(np.dtype((np.void, packed.shape[1]))).ravel()
+    _, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind='stable')          # unique-id -> rank by first occurrence
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    grp_of_step = rank[inv.ravel()].astype(np.int32)
+    grp_mask = avail[first[order]]
+    return grp_of_step, grp_mask
+
+
+class ChunkEngine:
+    """Holds the device and tunables; ``interp_chunk`` is re-entrant."""
+
+    def __init__(self, device=None, work_limit_bytes=4 << 30, aux_limit_bytes=8 << 30,
+                 lambda_tol=1e-7):
+        _lib.require_gpu()
+        if not torch.cuda.is_available():
+            raise _lib.SpxError('torch sees no CUDA device (no CPU fallback)')
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None
+                                   else int(device))
+        self.lib = _lib.load()
+        self.work_limit = int(work_limit_bytes)
+        self.aux_limit = int(aux_limit_bytes)
+        self.lambda_tol = float(lambda_tol)
+        self.stats = {}
+
+    # ------------------------------------------------------------ helpers
+    def _dev(self, arr, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _count(self, key, n=1):
+        self.stats[key] = self.stats.get(key, 0) + n
+
+    # ------------------------------------------------------------ public
+    def interp_chunk(
+            self, data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args,
+            vgs=None, cntn_idxs=None, drft_arrs=None, stns_drft=None,
+            fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
+            min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
+            min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
+            return_device=False):
+        """Same contract as the reference's ``_get_all_interp_outputs`` reduced
+        to arrays (see oracle/spinterp_oracle.py:interp_chunk for the argument
+        meaning).  Returns ({label: ndarray[T, rows*cols]}, problem_steps)."""
+        with torch.cuda.device(self.device):
+            return self._interp_chunk(
+                data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
+                cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
+                n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
+                intrp_dtype, return_device)
+
+    # ------------------------------------------------------------ impl
+    def _interp_chunk(
+            self, data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
+            cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
+            n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
+            intrp_dtype, return_device):
+        self.stats = {}
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        stn_xs = np.ascontiguousarray(stn_xs, dtype=np.float64)
+        stn_ys = np.ascontiguousarray(stn_ys, dtype=np.float64)
+        n_steps, n_stn = data.shape
+        assert stn_xs.shape == stn_ys.shape == (n_stn,)
+        if fld_end_row is None:
+            fld_end_row = grid_shape[0]
+        intrp_dtype = np.dtype(intrp_dtype)
+        assert intrp_dtype in (np.dtype(np.float32), np.dtype(np.float64))
+        out_f64 = int(intrp_dtype == np.dtype(np.float64))
+
+        interp_types = [a[0] for a in interp_args]
+        interp_labels = [a[2] for a in interp_args]
+        krg_types = [t for t in ('OK', 'SK', 'EDK') if t in interp_types]
+        edk_flag = 'EDK' in interp_types
+        if krg_types:
+            assert vgs is not None
+            vgs = [str(v) for v in vgs]
+            assert len(vgs) == n_steps
+            assert all(v != 'nan' for v in vgs), (   # steps.py:504-507
+                'NaN VGs not allowed! Use Nugget or any other appropriate one!')
+        if neb_sel_mthd != 'all':
+            raise NotImplementedError(
+                f"neighbor selection '{neb_sel_mthd}' is not on the GPU path yet "
+                "(SURVEY.md section 8f row 2)")
+        if est_var_flag and 'OK' in interp_types:
+            raise NotImplementedError('EST_VARS_OK is not on the GPU path yet')
+
+        # ---- cell subsetting, steps.py:512-568 ------------------------------
+        fld_n_cols = int(grid_shape[1])
+        fld_beg_idx = fld_beg_row * fld_n_cols
+        fld_end_idx = fld_end_row * fld_n_cols
+        fld_size = (fld_end_row - fld_beg_row) * fld_n_cols
+        if cntn_idxs is not None:
+            whr = np.where(cntn_idxs)[0]
+            sel = (whr >= fld_beg_idx) & (whr < fld_end_idx)
+            msh_idxs = np.arange(whr.size)[sel]
+            out_pos = (whr[sel] - fld_beg_idx).astype(np.int32)
+            dst_xs = cell_xs[msh_idxs]
+            dst_ys = cell_ys[msh_idxs]
+            if drft_arrs is not None:
+                drft_arrs = drft_arrs[:, msh_idxs]
+        else:
+            out_pos = None
+            dst_xs = cell_xs[fld_beg_idx:fld_end_idx]
+            dst_ys = cell_ys[fld_beg_idx:fld_end_idx]
+            if drft_arrs is not None:
+                drft_arrs = drft_arrs[:, fld_beg_idx:fld_end_idx]
+        n_cells = int(dst_xs.shape[0])
+        assert n_cells > 0
+
+        # ---- per-step host logic --------------------------------------------
+        avail = ~np.isnan(data)
+        grp_of_step, grp_mask = availability_groups(avail)       # grps.py:57-101
+        n_grps = grp_mask.shape[0]
+        grp_n = grp_mask.sum(axis=1).astype(np.int64)
+        n_avail = grp_n[grp_of_step]
+        problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
+
+        data0 = np.where(avail, data, 0.0)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            ref_means = data0.sum(axis=1) / n_avail                  # steps.py:276
+            steps_flags = (np.where(avail, data, -np.inf) >= min_var_thr).any(axis=1)  # :760-765
+        single_val = data0.sum(axis=1)                               # value when n_avail == 1
+
+        # ---- device residents -----------------------------------------------
+        d_stn_x = self._dev(stn_xs)
+        d_stn_y = self._dev(stn_ys)
+        d_cell_x = self._dev(dst_xs)
+        d_cell_y = self._dev(dst_ys)
+        d_pos = self._dev(out_pos) if out_pos is not None else None
+        d_data = self._dev(data)
+        d_data0 = self._dev(data0)
+        ctx = dict(
+            n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
+            d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
+            d_data=d_data, d_data0=d_data0, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
+            has_lo=int(min_var_cut is not None), has_hi=int(max_var_cut is not None),
+            lo=float(min_var_cut) if min_var_cut is not None else 0.0,
+            hi=float(max_var_cut) if max_var_cut is not None else 0.0,
+            grp_of_step=grp_of_step, grp_mask=grp_mask, grp_n=grp_n, n_avail=n_avail,
+            min_vg_val=float(min_vg_val), nnb_cache={})
+
+        tdtype = torch.float64 if out_f64 else torch.float32
+        flds = {lab: torch.full((n_steps, fld_size), float('nan'), dtype=tdtype,
+                                device=self.device) for lab in interp_labels}
+
+        # steps that bypass interpolation for every method
+        single_steps = np.where(n_avail == 1)[0]                    # steps.py:282-283
+
+        for i, itype in enumerate(interp_types):
+            lab = interp_labels[i]
+            if lab == 'EST_VARS_OK':
+                continue
+            out = flds[lab]
+            if single_steps.size:
+                self._fill_rows(ctx, out, single_steps, single_val[single_steps])
+            multi = n_avail >= 2
+            if itype == 'NNB':
+                self._nnb_label(ctx, out, np.where(multi)[0])
+            elif itype == 'IDW':
+                mean_steps = np.where(multi & ~steps_flags)[0]       # steps.py:312-313
+                if mean_steps.size:
+                    self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
+                self._idw(ctx, out, np.where(multi & steps_flags)[0], float(interp_args[i][3]))
+            elif itype in ('OK', 'SK', 'EDK'):
+                uniq_vgs = list(dict.fromkeys(vgs))
+                vg_id = {v: k for k, v in enumerate(uniq_vgs)}
+                nug = np.array([check_full_nuggetness(v, min_vg_val) for v in uniq_vgs])
+                step_vg = np.array([vg_id[v] for v in vgs], dtype=np.int32)
+                bypass = (~steps_flags) | nug[step_vg]               # steps.py:325-331
+                mean_steps = np.where(multi & bypass)[0]
+                if mean_steps.size:
+                    self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
+                self._krige(ctx, out, itype, np.where(multi & ~bypass)[0], step_vg, uniq_vgs,
+                            drft_arrs if itype == 'EDK' else None,
+                            stns_drft if itype == 'EDK' else None, problem_steps)
+            else:
+                raise NotImplementedError(itype)
+
+        if return_device:
+            return flds, problem_steps
+        torch.cuda.current_stream(self.device).synchronize()
+        return {lab: t.cpu().numpy() for lab, t in flds.items()}, problem_steps
+
+    # ------------------------------------------------------------ pieces
+    def _fill_rows(self, ctx, out, steps, vals):
+        d_vals = self._dev(np.asarray(vals, dtype=np.float64))
+        d_rows = self._dev(np.asarray(steps, dtype=np.int32))
+        _lib.check(self.lib.spx_fill_rows_dev(
+            self._ptr(d_vals), self._ptr(d_rows), len(steps), ctx['n_cells'], self._ptr(ctx['d_pos']),
+            self._ptr(out), ctx['fld_size'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'],
+            ctx['lo'], ctx['hi'], self._stream()), 'fill_rows')
+        self._count('launches')
+
+    def _nnb_index(self, ctx, grp_ids, cells=None):
+        """nnb[len(grp_ids), n_cells] int32 for the listed groups (cached for
+        the full cell set)."""
+        key = (tuple(int(g) for g in grp_ids), None if cells is None else cells.tobytes())
+        if key in ctx['nnb_cache']:
+            return ctx['nnb_cache'][key]
+        mask = self._dev(ctx['grp_mask'][np.asarray(grp_ids)].astype(np.uint8))
+        if cells is None:
+            cx, cy, nc = ctx['d_cell_x'], ctx['d_cell_y'], ctx['n_cells']
+        else:
+            cx = self._dev(ctx['dst_xs'][cells])
+            cy = self._dev(ctx['dst_ys'][cells])
+            nc = int(cells.size)
+        nnb = torch.empty((len(grp_ids), nc), dtype=_I32, device=self.device)
+        _lib.check(self.lib.spx_nnb_index_dev(
+            self._ptr(ctx['d_stn_x']), self._ptr(ctx['d_stn_y']), ctx['n_stn'], self._ptr(mask),
+            len(grp_ids), self._ptr(cx), self._ptr(cy), nc, self._ptr(nnb), self._stream()),
+            'nnb_index')
+        self._count('launches')
+        ctx['nnb_cache'][key] = nnb
+        return nnb
+
+    def _nnb_gather(self, ctx, out, nnb, row_step, row_grp_slot, fail=None, row_fail=None,
+                    n_cells=None, d_pos=None):
+        n_cells = ctx['n_cells'] if n_cells is None else n_cells
+        d_pos = ctx['d_pos'] if d_pos is None else d_pos
+        d_step = self._dev(np.asarray(row_step, dtype=np.int32))
+        d_grp = self._dev(np.asarray(row_grp_slot, dtype=np.int32))
+        d_rf = self._dev(np.asarray(row_fail, dtype=np.int32)) if row_fail is not None else None
+        _lib.check(self.lib.spx_nnb_gather_dev(
+            self._ptr(ctx['d_data']), ctx['n_stn'], self._ptr(nnb), self._ptr(d_step),
+            self._ptr(d_grp), self._ptr(d_step), len(row_step), self._ptr(fail), self._ptr(d_rf),
+            n_cells, self._ptr(d_pos), self._ptr(out), ctx['fld_size'], ctx['out_f64'],
+            ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi'], self._stream()), 'nnb_gather')
+        self._count('launches')
+
+    def _nnb_label(self, ctx, out, steps):
+        """interp/steps.py:285-291."""
+        if not steps.size:
+            return
+        grp_of_step = ctx['grp_of_step']
+        grps = np.unique(grp_of_step[steps])
+        # bound the index buffer: groups in batches
+        per_grp = ctx['n_cells'] * 4
+        batch = max(1, int(self.aux_limit // max(per_grp, 1)))
+        for b0 in range(0, grps.size, batch):
+            gb = grps[b0:b0 + batch]
+            slot = {int(g): k for k, g in enumerate(gb)}
+            st = steps[np.isin(grp_of_step[steps], gb)]
+            nnb = self._nnb_index(ctx, gb)
+            self._nnb_gather(ctx, out, nnb, st, [slot[int(grp_of_step[s])] for s in st])
+
+    def _gemm(self, ctx, *, coef, n_rows, kpad, n_border, gen, epi, row_dst, row_aux=None,
+              out=None, aux=None, vg=None, covar_flag=0, idw_exp=0.0, dist_scale=1.0,
+              cell_drift=None):
+        g = _lib.spx_gemm()
+        g.coef = coef.data_ptr()
+        g.n_rows = int(n_rows)
+        g.kpad = int(kpad)
+        g.n_stn = ctx['n_stn']
+        g.n_border = int(n_border)
+        g.stn_x = ctx['d_stn_x'].data_ptr()
+        g.stn_y = ctx['d_stn_y'].data_ptr()
+        g.cell_x = ctx['d_cell_x'].data_ptr()
+        g.cell_y = ctx['d_cell_y'].data_ptr()
+        g.n_cells = ctx['n_cells']
+        g.cell_drift = cell_drift.data_ptr() if cell_drift is not None else None
+        g.gen = gen
+        g.covar_flag = int(covar_flag)
+        if vg is not None:
+            g.vg = vg
+        g.min_vg_val = ctx['min_vg_val']
+        g.idw_exp = float(idw_exp)
+        g.dist_scale = float(dist_scale)
+        g.epi = epi
+        g.row_dst = row_dst.data_ptr()
+        g.row_aux = row_aux.data_ptr() if row_aux is not None else None
+        g.out = out.data_ptr() if out is not None else None
+        g.out_ld = ctx['fld_size']
+        g.out_f64 = ctx['out_f64']
+        g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+        g.aux = aux.data_ptr() if aux is not None else None
+        g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+        _lib.check(self.lib.spx_estimate_gemm_dev(C.byref(g), self._stream()), 'estimate_gemm')
+        self._count('launches')
+        self._count('gemm_flop', 2 * int(n_rows) * int(kpad) * ctx['n_cells'])
+
+    # ---- IDW ------------------------------------------------------------
+    def _idw(self, ctx, out, steps, idw_exp):
+        """interp/steps.py:293-313 as  (Z0 . W^T) / (M . W^T)  with W = d**-p."""
+        if not steps.size:
+            return
+        n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
+        kpad = _pad_up(n_stn, 8)
+        grp_of_step = ctx['grp_of_step']
+        # distance scale common to every cell (cancels in the ratio)
+        xs = np.concatenate([ctx['dst_xs'], ctx['d_stn_x'].cpu().numpy()])
+        ys = np.concatenate([ctx['dst_ys'], ctx['d_stn_y'].cpu().numpy()])
+        scale = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
+        scale = scale if scale > 0 else 1.0
+
+        max_grps = max(1, int(self.aux_limit // (n_cells * 8)))
+        grps_all = np.unique(grp_of_step[steps])
+        for b0 in range(0, grps_all.size, max_grps):
+            gb = grps_all[b0:b0 + max_grps]
+            slot_of = np.full(ctx['grp_mask'].shape[0], -1, dtype=np.int32)
+            slot_of[gb] = np.arange(gb.size, dtype=np.int32)
+            st = steps[slot_of[grp_of_step[steps]] >= 0]
+            # phase A: sum of weights over the available stations of each group
+            n_a = gb.size
+            coef_a = torch.zeros(_pad_up(n_a, _lib.SPX_BM) * kpad, dtype=_F64, device=self.device)
+            d_mask = self._dev(np.where(ctx['grp_mask'][gb], 1.0, np.nan))
+            _lib.check(self.lib.spx_pack_rows_dev(
+                self._ptr(d_mask), n_stn, None, n_a, n_stn, kpad, 1, self._ptr(coef_a), 0,
+                self._stream()), 'pack_rows')
+            aux = torch.empty((n_a, n_cells), dtype=_F64, device=self.device)
+            d_slots = torch.arange(n_a, dtype=_I32, device=self.device)
+            self._gemm(ctx, coef=coef_a, n_rows=n_a, kpad=kpad, n_border=0, gen=_lib.GEN_IDW,
+                       epi=_lib.EPI_AUX, row_dst=d_slots, aux=aux, idw_exp=idw_exp,
+                       dist_scale=scale)
+            # phase B: data rows, divided by their group's row
+            n_b = st.size
+            coef_b = torch.zeros(_pad_up(n_b, _lib.SPX_BM) * kpad, dtype=_F64, device=self.device)
+            d_st = self._dev(st.astype(np.int32))
+            _lib.check(self.lib.spx_pack_rows_dev(
+                self._ptr(ctx['d_data0']), n_stn, self._ptr(d_st), n_b, n_stn, kpad, 0,
+                self._ptr(coef_b), 0, self._stream()), 'pack_rows')
+            d_row_aux = self._dev(slot_of[grp_of_step[st]])
+            self._gemm(ctx, coef=coef_b, n_rows=n_b, kpad=kpad, n_border=0, gen=_lib.GEN_IDW,
+                       epi=_lib.EPI_FIELD_DIV, row_dst=d_st, row_aux=d_row_aux, out=out, aux=aux,
+                       idw_exp=idw_exp, dist_scale=scale)
+            self._count('launches', 2)   # the two pack_rows launches
+
+    # ---- kriging --------------------------------------------------------
+    def _krige(self, ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs, stns_drft,
+               problem_steps):
+        """OK / SK / EDK in dual form:
+        Z[t, i] = rhs_i . A_g^-1 [z_t; 0]."""
+        if not steps.size:
+            return
+        lib = self.lib
+        kind = _lib.KRG_KINDS[kind_name]
+        n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
+        n_drifts = 0 if kind != 2 else int(stns_drft.shape[1])
+        n_border = {0: 1, 1: 0, 2: 1 + n_drifts}[kind]
+        kpad = _pad_up(n_stn + n_border, 8)
+        grp_of_step, grp_mask, grp_n = ctx['grp_of_step'], ctx['grp_mask'], ctx['grp_n']
+
+        d_cell_drift = d_stn_drift = None
+        bad_cells = np.zeros(0, dtype=np.int64)
+        if kind == 2:
+            drft = np.ascontiguousarray(drft_arrs, dtype=np.float64)
+            assert drft.shape == (n_drifts, n_cells)
+            d_cell_drift = self._dev(drft)
+            d_stn_drift = self._dev(np.ascontiguousarray(stns_drft, dtype=np.float64))
+            bad_cells = np.where(np.isnan(drft).any(axis=0))[0]
+
+        # station lists per group (ascending station index = reference order)
+        grps_used = np.unique(grp_of_step[steps])
+        stn_off = np.zeros(grp_mask.shape[0], dtype=np.int64)
+        stn_off[grps_used] = np.concatenate([[0], np.cumsum(grp_n[grps_used])])[:-1]
+        stn_list = np.where(grp_mask[grps_used])[1].astype(np.int32)   # row-major: per group, ascending
+        d_stn_list = self._dev(stn_list)
+
+        # systems = distinct (group, variogram) among the steps, grouped by variogram
+        pair = grp_of_step[steps].astype(np.int64) * len(uniq_vgs) + step_vg[steps]
+        upair, sys_of_row = np.unique(pair, return_inverse=True)
+        sys_grp = (upair // len(uniq_vgs)).astype(np.int32)
+        sys_vg = (upair % len(uniq_vgs)).astype(np.int32)
+        n_sys = upair.size
+        sys_n = grp_n[sys_grp].astype(np.int32)
+        sys_m = sys_n.astype(np.int64) + n_border
+
+        # coefficient rows: steps ordered by variogram, one SPX_BM-aligned segment each
+        order = np.argsort(step_vg[steps], kind='stable')
+        steps_o = steps[order]
+        sys_o = sys_of_row[order]
+        vg_o = step_vg[steps_o]
+        seg_vgs, seg_first, seg_cnt = np.unique(vg_o, return_index=True, return_counts=True)
+        seg_row0 = np.zeros(seg_vgs.size, dtype=np.int64)
+        acc = 0
+        for k in range(seg_vgs.size):
+            seg_row0[k] = acc
+            acc += _pad_up(seg_cnt[k], _lib.SPX_BM)
+        total_rows = acc
+        row_of = np.empty(steps_o.size, dtype=np.int64)
+        for k in range(seg_vgs.size):
+            row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = seg_row0[k] + np.arange(seg_cnt[k])
+        coef = torch.zeros(total_rows * kpad, dtype=_F64, device=self.device)
+        row_dst_np = np.full(total_rows, -1, dtype=np.int32)
+        row_dst_np[row_of] = steps_o
+        d_row_dst = self._dev(row_dst_np)
+
+        d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8))
+
+        # bound for the sum(lambda) screening: |rhs| <= max(vg bound, 1, |drift|)
+        xs = np.concatenate([ctx['dst_xs'], ctx['d_stn_x'].cpu().numpy()])
+        ys = np.concatenate([ctx['dst_ys'], ctx['d_stn_y'].cpu().numpy()])
+        max_dist = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
+        rhs_bound = np.array([max(1.0, vg_abs_bound(v, max_dist)) for v in uniq_vgs])
+        if kind == 2:
+            with np.errstate(invalid='ignore'):
+                dmax = np.nanmax(np.abs(drft)) if np.isfinite(drft).any() else 1.0
+            rhs_bound = np.maximum(rhs_bound, dmax)
+
+        # ---- factor + solve in batches bounded by the workspace limit -----
+        flagged = np.zeros(n_sys, dtype=bool)
+        singular = np.zeros(n_sys, dtype=bool)
+        sys_bytes = sys_m * sys_m * 8
+        b0 = 0
+        rows_by_sys = np.argsort(sys_o, kind='stable')
+        sys_row_cnt = np.bincount(sys_o, minlength=n_sys)
+        sys_row_beg = np.concatenate([[0], np.cumsum(sys_row_cnt)])
+        keep = {}
+        while b0 < n_sys:
+            b1 = b0 + 1
+            tot = int(sys_bytes[b0])
+            while b1 < n_sys and tot + int(sys_bytes[b1]) <= self.work_limit and (b1 - b0) < 60000:
+                tot += int(sys_bytes[b1])
+                b1 += 1
+            sl = slice(b0, b1)
+            nb = b1 - b0
+            w_off = np.concatenate([[0], np.cumsum(sys_m[sl] * sys_m[sl])])[:-1].astype(np.int64)
+            p_off = np.concatenate([[0], np.cumsum(sys_m[sl])])[:-1].astype(np.int64)
+            work = torch.empty(int((sys_m[sl] * sys_m[sl]).sum()), dtype=_F64, device=self.device)
+            piv = torch.empty(int(sys_m[sl].sum()), dtype=_I32, device=self.device)
+            info = torch.zeros(nb, dtype=_I32, device=self.device)
+            t_sys_n = self._dev(sys_n[sl])
+            t_kind = self._dev(np.full(nb, kind, dtype=np.int32))
+            t_vg = self._dev(sys_vg[sl])
+            t_stn_off = self._dev(stn_off[sys_grp[sl]])
+            t_w_off = self._dev(w_off)
+            t_p_off = self._dev(p_off)
+            S = _lib.spx_systems()
+            S.n_sys = nb
+            S.n_drifts = n_drifts
+            S.sys_n = t_sys_n.data_ptr()
+            S.sys_kind = t_kind.data_ptr()
+            S.sys_vg = t_vg.data_ptr()
+            S.sys_stn_off = t_stn_off.data_ptr()
+            S.sys_w_off = t_w_off.data_ptr()
+            S.sys_piv_off = t_p_off.data_ptr()
+            S.stn_list = d_stn_list.data_ptr()
+            S.stn_x = ctx['d_stn_x'].data_ptr()
+            S.stn_y = ctx['d_stn_y'].data_ptr()
+            S.stn_drift = d_stn_drift.data_ptr() if d_stn_drift is not None else None
+            S.work = work.data_ptr()
+            S.piv = piv.data_ptr()
+            S.info = info.data_ptr()
+            _lib.check(lib.spx_krige_assemble_dev(C.byref(S), self._ptr(d_vgs), len(uniq_vgs),
+                                                  ctx['min_vg_val'], self._stream()), 'assemble')
+            _lib.check(lib.spx_krige_factor_dev(C.byref(S), self._stream()), 'factor')
+            self._count('launches', 2)
+            self._count('lu_flop', int((2 * sys_m[sl] ** 3 // 3).sum()))
+
+            # right-hand sides: every data row of these systems + one ones-vector each
+            ridx = np.concatenate([rows_by_sys[sys_row_beg[s]:sys_row_beg[s + 1]]
+                                   for s in range(b0, b1)])
+            n_data = ridx.size
+            rhs_sys = np.concatenate([sys_o[ridx] - b0, np.arange(nb)]).astype(np.int32)
+            rhs_kind = np.concatenate([np.zeros(n_data), np.ones(nb)]).astype(np.int32)
+            rhs_arg = np.concatenate([steps_o[ridx], np.zeros(nb)]).astype(np.int32)
+            rhs_row = np.concatenate([row_of[ridx], np.full(nb, -1)]).astype(np.int64)
+            resid = torch.zeros(rhs_sys.size, dtype=_F64, device=self.device)
+            t_rs, t_rk, t_ra, t_rr = (self._dev(rhs_sys), self._dev(rhs_kind), self._dev(rhs_arg),
+                                      self._dev(rhs_row))
+            R = _lib.spx_rhs()
+            R.n_rhs = int(rhs_sys.size)
+            R.rhs_sys, R.rhs_kind = t_rs.data_ptr(), t_rk.data_ptr()
+            R.rhs_arg, R.rhs_row = t_ra.data_ptr(), t_rr.data_ptr()
+            R.data = ctx['d_data'].data_ptr()
+            R.n_stn = n_stn
+            R.kpad = kpad
+            R.coef = coef.data_ptr()
+            R.resid = resid.data_ptr()
+            _lib.check(lib.spx_krige_solve_dev(C.byref(S), C.byref(R), self._stream()), 'solve')
+            self._count('launches')
+
+            info_h = info.cpu().numpy()
+            resid_h = resid[n_data:].cpu().numpy()
+            singular[sl] = info_h != 0
+            with np.errstate(invalid='ignore'):
+                dev = resid_h * rhs_bound[sys_vg[sl]]
+            flagged[sl] = (kind == 1) | singular[sl] | ~(dev <= self.lambda_tol)
+            if flagged[sl].any():
+                keep[b0] = (S, work, piv, info, t_sys_n, t_kind, t_vg, t_stn_off, t_w_off, t_p_off)
+            b0 = b1
+
+        self.stats['n_systems'] = self.stats.get('n_systems', 0) + n_sys
+        self.stats['n_flagged'] = self.stats.get('n_flagged', 0) + int(flagged.sum())
+
+        # ---- main contraction: one launch per variogram segment ----------
+        for k in range(seg_vgs.size):
+            seg_coef = coef[seg_row0[k] * kpad:]
+            self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad, n_border=n_border,
+                       gen=_lib.GEN_VG, epi=_lib.EPI_FIELD,
+                       row_dst=d_row_dst[seg_row0[k]:], out=out,
+                       vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]), covar_flag=int(kind == 1),
+                       cell_drift=d_cell_drift)
+
+        # ---- fallbacks to the nearest neighbour (steps.py:418-426) --------
+        if bad_cells.size:
+            # NaN drift at a cell -> sum(lambda) is NaN -> NNB there, every step
+            gl = np.unique(grp_of_step[steps_o])
+            slot = {int(g): i for i, g in enumerate(gl)}
+            nnb = self._nnb_index(ctx, gl, cells=bad_cells)
+            pos = ctx['out_pos'][bad_cells] if ctx['out_pos'] is not None else bad_cells
+            self._nnb_gather(ctx, out, nnb, steps_o, [slot[int(grp_of_step[s])] for s in steps_o],
+                             n_cells=int(bad_cells.size), d_pos=self._dev(pos.astype(np.int32)))
+
+        if flagged.any():
+            self._krige_flagged(ctx, out, kind, kpad, n_border, flagged, singular, keep, sys_vg,
+                                sys_grp, sys_o, steps_o, uniq_vgs, d_cell_drift, bad_cells,
+                                problem_steps)
+
+    def _krige_flagged(self, ctx, out, kind, kpad, n_border, flagged, singular, keep, sys_vg,
+                       sys_grp, sys_o, steps_o, uniq_vgs, d_cell_drift, bad_cells, problem_steps):
+        """Systems whose computed weights may not sum to one (always for SK,
+        quirk Q6): evaluate sum(lambda) per cell exactly like steps.py:418 and
+        overwrite failing cells with the nearest available station."""
+        lib = self.lib
+        n_cells = ctx['n_cells']
+        fl = np.where(flagged)[0]
+        max_slots = max(1, int(self.aux_limit // (n_cells * 13)))
+        d_cell_bad = None
+        if bad_cells.size:
+            cb = np.zeros(n_cells, dtype=np.uint8)
+            cb[bad_cells] = 1
+            d_cell_bad = self._dev(cb)
+        batch_starts = sorted(keep)
+        for c0 in range(0, fl.size, max_slots):
+            fb = fl[c0:c0 + max_slots]
+            n_f = fb.size
+            fail = torch.ones((n_f, n_cells), dtype=torch.uint8, device=self.device)
+            aux = torch.empty((n_f, n_cells), dtype=_F64, device=self.device)
+            # ones-vector solutions of the non-singular flagged systems, by variogram
+            ok = fb[~singular[fb]]
+            for v in np.unique(sys_vg[ok]):
+                sv = ok[sys_vg[ok] == v]
+                coef_a = torch.zeros(_pad_up(sv.size, _lib.SPX_BM) * kpad, dtype=_F64,
+                                     device=self.device)
+                slots = np.searchsorted(fb, sv).astype(np.int32)
+                for bstart in batch_starts:
+                    S = keep[bstart][0]
+                    in_b = sv[(sv >= bstart) & (sv < bstart + S.n_sys)]
+                    if not in_b.size:
+                        continue
+                    rows = np.searchsorted(sv, in_b).astype(np.int64)
+                    t_rs = self._dev((in_b - bstart).astype(np.int32))
+                    t_rk = self._dev(np.ones(in_b.size, dtype=np.int32))
+                    t_ra = self._dev(np.zeros(in_b.size, dtype=np.int32))
+                    t_rr = self._dev(rows)
+                    R = _lib.spx_rhs()
+                    R.n_rhs = int(in_b.size)
+                    R.rhs_sys, R.rhs_kind = t_rs.data_ptr(), t_rk.data_ptr()
+                    R.rhs_arg, R.rhs_row = t_ra.data_ptr(), t_rr.data_ptr()
+                    R.data = ctx['d_data'].data_ptr()
+                    R.n_stn = ctx['n_stn']
+                    R.kpad = kpad
+                    R.coef = coef_a.data_ptr()
+                    R.resid = None
+                    _lib.check(lib.spx_krige_solve_dev(C.byref(S), C.byref(R), self._stream()),
+                               'solve(ones)')
+                    self._count('launches')
+                d_slots = self._dev(slots)
+                self._gemm(ctx, coef=coef_a, n_rows=int(sv.size), kpad=kpad, n_border=n_border,
+                           gen=_lib.GEN_VG, epi=_lib.EPI_AUX, row_dst=d_slots, aux=aux,
+                           vg=_lib.make_vg(uniq_vgs[int(v)]), covar_flag=int(kind == 1),
+                           cell_drift=d_cell_drift)
+            if ok.size:
+                ok_slots = torch.from_numpy(np.searchsorted(fb, ok)).to(self.device)
+                aux_ok = aux[ok_slots]
+                fail_ok = torch.empty((ok.size, n_cells), dtype=torch.uint8, device=self.device)
+                _lib.check(lib.spx_lambda_check_dev(
+                    self._ptr(aux_ok), int(ok.size), n_cells, self._ptr(d_cell_bad),
+                    self._ptr(fail_ok), self._stream()), 'lambda_check')
+                self._count('launches')
+                fail[ok_slots] = fail_ok
+            # rows of the flagged systems
+            slot_of_sys = np.full(flagged.size, -1, dtype=np.int64)
+            slot_of_sys[fb] = np.arange(n_f)
+            rsel = np.where(slot_of_sys[sys_o] >= 0)[0]
+            if not rsel.size:
+                continue
+            r_steps = steps_o[rsel]
+            gl = np.unique(sys_grp[fb])
+            gslot = {int(g): i for i, g in enumerate(gl)}
+            nnb = self._nnb_index(ctx, gl)
+            self._nnb_gather(ctx, out, nnb, r_steps,
+                             [gslot[int(ctx['grp_of_step'][s])] for s in r_steps],
+                             fail=fail, row_fail=slot_of_sys[sys_o[rsel]])
+            for s in fb[singular[fb]]:
+                for t in steps_o[sys_o == s]:
+                    if int(t) not in problem_steps:
+                        problem_steps.append(int(t))
