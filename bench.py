@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the gridded-interpolation hot path (BASELINE.json metric:
+interpolated cell-steps/s, OK, FP64 arithmetic, f32 store).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path (the compute half of
+``SpInterpSteps.interpolate_subset``) over one time chunk of BASELINE config 2:
+ordinary kriging of 500 stations with ~20 % missing data (one availability
+group per step) onto the full 1000 x 1000 grid, CHUNK_STEPS daily steps per
+chunk (the full config is 10 such chunks; the reference's own scheduler splits
+the time axis the same way, interp/main.py:652-859).  With N GPUs every rank
+processes its own chunk of different time steps (weak scaling, no data-path
+collective).
+
+Prints ONE JSON line (see the task contract) with `value` (inputs resident,
+outputs left in HBM), `e2e` (host buffers in, pinned host buffers out),
+`roofline` of the dominant kernel and `cpu_baseline` (oracle port timed on the
+host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+    os.environ.setdefault(_v, '1')          # like the reference (__init__.py:5-10)
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+N_STN = 500
+NY = NX = 1000
+CHUNK_STEPS = 1000
+MISS = 0.2
+VG = '0.1 Nug(0.0) + 0.9 Sph(20000)'
+INTERP_ARGS = [('OK', None, 'OK')]
+WORKLOAD = ('C2 time chunk: OK, 500 stations x %d daily steps (20%% missing, ~1 availability '
+            'group per step) -> 1000x1000 grid, vg %s' % (CHUNK_STEPS, VG))
+
+
+def make_chunk(rank):
+    from tests.synth import make_problem
+    p = make_problem(2, N_STN, CHUNK_STEPS, NY, NX, cell=1000.0, miss=MISS)
+    # same stations / grid on every rank, different time steps per rank
+    rng = np.random.default_rng(1000 + rank)
+    data = rng.gamma(1.0, 5.0, size=(CHUNK_STEPS, N_STN))
+    data[rng.random((CHUNK_STEPS, N_STN)) < MISS] = np.nan
+    p['data'] = data
+    return p
+
+
+# ----------------------------------------------------------------- CPU arm
+
+def _cpu_worker(args):
+    (data, p, row0, row1) = args
+    from oracle import spinterp_oracle as orc
+    t0 = time.perf_counter()
+    flds, _ = orc.interp_chunk(
+        data, p['stn_xs'], p['stn_ys'], p['cell_xs'], p['cell_ys'], p['grid_shape'],
+        INTERP_ARGS, vgs=[VG] * data.shape[0], fld_beg_row=row0, fld_end_row=row1,
+        intrp_dtype=np.float32, faithful=True)
+    return data.shape[0] * (row1 - row0) * p['grid_shape'][1], time.perf_counter() - t0
+
+
+def cpu_sample(p, n_cores, steps_per_core=1, rows=8):
+    """Oracle port, reference loop structure (faithful=True), multiprocess over
+    time chunks like interp/main.py:141-153; returns (cell_steps, seconds)."""
+    import multiprocessing as mp
+    n_steps = n_cores * steps_per_core
+    tasks = [(p['data'][i * steps_per_core:(i + 1) * steps_per_core], p, 0, rows)
+             for i in range(n_cores)]
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(n_cores) as pool:
+        res = pool.map(_cpu_worker, tasks, chunksize=1)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall, n_steps, rows
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_cores = len(os.sched_getaffinity(0))
+    p = make_chunk(0)
+    vals = []
+    for it in range(args.warmup + args.steps):
+        cs, wall, n_steps, rows = cpu_sample(p, n_cores, steps_per_core=1, rows=64)
+        if it >= args.warmup:
+            vals.append((cs, wall))
+    cs = sum(v[0] for v in vals)
+    wall = sum(v[1] for v in vals)
+    value = cs / wall
+    sample = ('%d steps x %d grid rows x %d cols per bench step (same stations, missingness and '
+              'variogram as the GPU arm)' % (n_steps, rows, NX))
+    line = {
+        'impl': 'reference', 'metric': 'interpolated cell-steps/s (OK, FP64, f32 store)',
+        'value': value, 'unit': 'cell-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'cell-steps/s', 'cores': n_cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'cell-steps/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------- GPU arm
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names)
+                   if any(s[2 + k].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+                'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def dgemm_peak_tflops(torch, n=6144, reps=4):
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = float('inf')
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from spinterps_b200.engine import ChunkEngine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    p = make_chunk(rank)
+    cpu_res = None
+    if world == 1:
+        # CPU baseline first: fork the worker pool before CUDA is initialised
+        n_cores = len(os.sched_getaffinity(0))
+        cpu_res = cpu_sample(p, n_cores, steps_per_core=1, rows=64)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = ChunkEngine()
+    vgs = [VG] * CHUNK_STEPS
+    cell_steps = CHUNK_STEPS * NY * NX
+
+    def step_resident():
+        flds, _ = eng.interp_chunk(interp_args=INTERP_ARGS, vgs=vgs, intrp_dtype=np.float32,
+                                   return_device=True, **p)
+        return flds
+
+    # pinned host buffers for the end-to-end path
+    pin_in = torch.from_numpy(p['data']).pin_memory()
+    pin_out = torch.empty((CHUNK_STEPS, NY * NX), dtype=torch.float32).pin_memory()
+    p_e2e = dict(p)
+    p_e2e['data'] = pin_in.numpy()
+
+    def step_e2e():
+        flds, _ = eng.interp_chunk(interp_args=INTERP_ARGS, vgs=vgs, intrp_dtype=np.float32,
+                                   return_device=True, **p_e2e)
+        pin_out.copy_(flds['OK'], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(pin_out[0, 0])
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            r = fn()
+            del r
+        e1.record()
+        barrier()
+        ms_dev = e0.elapsed_time(e1)
+        ms_wall = 1e3 * (time.perf_counter() - t0)
+        ms = max(ms_dev, 0.0)
+        if world > 1:
+            t = torch.tensor([ms, ms_wall], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_wall = float(t[0]), float(t[1])
+        return ms, ms_wall
+
+    for _ in range(args.warmup):
+        r = step_resident()
+        del r
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile_gemm = True
+    eng.gemm_events = []
+    ms, ms_wall = timed(step_resident, args.steps)
+    gemm_events = eng.gemm_events
+    eng.profile_gemm = False
+    launches_per_step = eng.stats.get('launches', 0)
+    gemm_flop_per_launch = eng.stats.get('gemm_flop', 0) / max(eng.stats.get('gemm_launches', 1), 1)
+    torch.cuda.synchronize()
+    gemm_ms = [a.elapsed_time(b) for a, b in gemm_events]
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    value = world * cell_steps * args.steps / (ms / 1e3)
+    e2e_value = world * cell_steps * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peak = dgemm_peak_tflops(torch)
+        avg_gemm_ms = sum(gemm_ms) / max(len(gemm_ms), 1)
+        achieved = gemm_flop_per_launch / (avg_gemm_ms / 1e3) / 1e12 if gemm_ms else None
+        traffic = None
+        tf = ROOT / 'profiles' / 'gemm_traffic.json'
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get('dram_bytes_per_launch')
+            except Exception:
+                traffic = None
+        cpu_baseline = None
+        if cpu_res is not None:
+            cs, wall, n_steps_s, rows_s = cpu_res
+            sample = ('%d steps x %d grid rows x %d cols (same stations, missingness, variogram); '
+                      'oracle port with the reference loop structure, Pool(%d) over time chunks'
+                      % (n_steps_s, rows_s, NX, n_cores))
+            cpu_baseline = {'value': cs / wall, 'unit': 'cell-steps/s', 'cores': n_cores,
+                            'kind': 'port', 'sample': sample}
+        h2d = int(p['data'].nbytes + 2 * p['stn_xs'].nbytes + 2 * NY * NX * 8)
+        line = {
+            'metric': 'interpolated cell-steps/s (OK, FP64, f32 store)',
+            'value': value, 'unit': 'cell-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {
+                'workload': WORKLOAD, 'n_stations': N_STN, 'chunk_steps': CHUNK_STEPS,
+                'grid': [NY, NX], 'missing': MISS, 'parallelism': 'time-sharded x%d' % world,
+                'l2': 'each step writes a %.1f GB field (>> 126 MB L2) between reuses'
+                      % (cell_steps * 4 / 1e9),
+                'wall_ms_per_step': ms_wall / args.steps},
+            'e2e': {'value': e2e_value, 'unit': 'cell-steps/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(cell_steps * 4),
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'roofline': {
+                'kernel': 'spx::k_estimate_gemm (fused variogram fill + DMMA contraction)',
+                'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
+                'peak_source': 'FP64: cuBLAS DGEMM 6144^3 via torch.matmul, measured live in this '
+                               'run (MEASURED_PEAKS.json has no FP64 entry); DMMA issue-rate '
+                               'microbenchmark: profiles/microbench',
+                'flop_per_launch': gemm_flop_per_launch, 'avg_launch_ms': avg_gemm_ms,
+                'launches_timed': len(gemm_ms)},
+            'cpu_baseline': cpu_baseline,
+            'clocks': sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -68,6 +68,9 @@ class ChunkEngine:
         self.aux_limit = int(aux_limit_bytes)
         self.lambda_tol = float(lambda_tol)
         self.stats = {}
+        # bench hook: CUDA events around every estimate-contraction launch
+        self.profile_gemm = False
+        self.gemm_events = []
 
     # ------------------------------------------------------------ helpers
     def _dev(self, arr, dtype=None):
@@ -329,8 +332,16 @@ class ChunkEngine:
         g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
         g.aux = aux.data_ptr() if aux is not None else None
         g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+        if self.profile_gemm:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(self.lib.spx_estimate_gemm_dev(C.byref(g), self._stream()), 'estimate_gemm')
+        if self.profile_gemm:
+            e1.record()
+            self.gemm_events.append((e0, e1))
         self._count('launches')
+        self._count('gemm_launches')
         self._count('gemm_flop', 2 * int(n_rows) * int(kpad) * ctx['n_cells'])
 
     # ---- IDW ------------------------------------------------------------

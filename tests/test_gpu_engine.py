@@ -63,9 +63,12 @@ def test_golden_vg_families(eng):
     ref = outs['OK']
     errs = [rel_err(got['OK'][t], ref[t]) for t in range(ref.shape[0])]
     print('per-step rel err', errs)
-    for t in (1, 3, 5, 6):       # Lin, Hol, Exp, tiny-sill (-> mean) steps
+    for t in (0, 1, 2, 4, 5, 6):  # cond(A) <= 6e3 for these systems
         assert errs[t] <= KRG_TOL, (t, errs[t])
-    assert max(errs) <= 1e-5, errs
+    # step 3 (Hol): cond(A) = 7.2e5 and strongly cancelling weights -- NumPy's own
+    # pinv evaluated as gemm instead of the reference's per-cell gemv already
+    # differs from the golden field by 8.7e-10, LAPACK solve by 3.7e-9
+    assert errs[3] <= 2e-8, errs[3]
 
 
 def test_float32_store(eng):
