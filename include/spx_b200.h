@@ -165,9 +165,12 @@ typedef struct spx_systems {
     double* work;              /* matrices */
     int32_t* piv;              /* pivots */
     int32_t* info;             /* [n_sys] 0 ok, >0 = zero pivot at that column */
+    int32_t max_m;             /* largest n + border in the batch (host-known; sizes the
+                                  shared-memory panel of the blocked LU; 0 = unknown ->
+                                  unblocked kernel) */
 } spx_systems;
 
-int spx_krige_assemble_dev(const spx_systems* s, const spx_vg* vgs, int n_vgs,
+int spx_krige_assemble_dev(const spx_systems* s, const spx_vg* vgs_dev /* device array */, int n_vgs,
                            double min_vg_val, void* stream);
 
 /* LU with partial pivoting, one thread block per system (replaces
@@ -192,9 +195,52 @@ typedef struct spx_rhs {
     int32_t kpad;
     double* coef;         /* packed, zero-initialised by the caller */
     double* resid;        /* [n_rhs] or NULL */
+    double* dense;        /* optional: x also written to dense[rhs * dense_ld + i] */
+    int64_t dense_ld;
 } spx_rhs;
 
 int spx_krige_solve_dev(const spx_systems* s, const spx_rhs* r, void* stream);
+
+/* Downdated solves.  Every availability group's system A_g is a principal
+ * sub-matrix of the full system F over all stations (+ border).  With
+ * G = F^-1, kept rows K (stations of the group + border) and missing stations
+ * Mi (r of them):
+ *     A_g^-1 b = u_K - G[K, Mi] * (G[Mi, Mi]^-1 u_Mi),     u = G b~
+ * (b~ = b zero-extended; block-inverse identity).  u for all right-hand sides
+ * is one dense product Ut = B~^T G done by the caller; this kernel factors the
+ * r x r matrix G[Mi, Mi] in SHARED memory (LU, partial pivoting), solves every
+ * right-hand side of the system with warp-level substitutions and scatters the
+ * coefficients exactly like spx_krige_solve_dev.  Cost per system O(r^3 + r n)
+ * instead of O(n^3); used when r <= max_r fits in shared memory.
+ * rhs_kind: 0 data, 1 ones-vector (resid[rhs] += ||x - e_n||_1; resid must be
+ * zero-initialised).  Right-hand sides of one system are contiguous. */
+typedef struct spx_downdate {
+    int32_t n_sys;
+    int32_t n_stn;
+    int32_t n_border;
+    int32_t max_r;
+    const double* ginv;          /* [M, M], M = n_stn + n_border, symmetric */
+    const int32_t* sys_r;
+    const int64_t* sys_miss_off; /* into miss_list */
+    const int32_t* miss_list;    /* missing station indices, ascending */
+    const int32_t* sys_n;
+    const int64_t* sys_stn_off;  /* into stn_list */
+    const int32_t* stn_list;     /* kept station indices, ascending */
+    const int64_t* sys_rhs_off;
+    const int32_t* sys_rhs_cnt;
+    const int32_t* rhs_urow;     /* row of ut */
+    const int64_t* rhs_row;      /* packed coefficient row, < 0 = none */
+    const int32_t* rhs_kind;
+    const double* ut;            /* [n_urows, M] */
+    int32_t kpad;
+    double* coef;
+    double* resid;               /* [n_rhs] */
+    int32_t* info;               /* [n_sys] */
+} spx_downdate;
+
+int spx_krige_downdate_dev(const spx_downdate* d, void* stream);
+/* Largest r that fits the device's shared memory. */
+int spx_krige_downdate_max_r(void);
 
 /* The fused estimate contraction
  *     Z[row, cell] = sum_k coef[row, k] * B[k, cell]

@@ -24,6 +24,8 @@ def main():
     print('cuBLAS DGEMM 8192^3 TFLOP/s:', dgemm_peak())
     p = make_problem(2, n_stn, T, ny, nx, miss=miss)
     eng = ChunkEngine()
+    import os
+    eng.sync_timing = bool(int(os.environ.get('SPX_SYNC_TIMING', '0')))
     for args in ([('OK', None, 'OK')], [('IDW', None, 'IDW_000', 2.0)], [('NNB', None, 'NNB')]):
         for rep in range(2):
             torch.cuda.synchronize(); t0 = time.time()
@@ -34,6 +36,6 @@ def main():
             ms = e0.elapsed_time(e1); wall = time.time() - t0
             cs = T * ny * nx
             print(args[0][0], 'rep', rep, f'dev {ms:.1f} ms wall {wall*1e3:.1f} ms  cell-steps/s {cs/ms*1e3:.3e}',
-                  'stats', eng.stats, 'TFLOP/s(gemm)', eng.stats.get('gemm_flop', 0) / ms / 1e9)
+                  'stats', eng.stats, 'TFLOP/s(gemm)', eng.stats.get('gemm_flop', 0) / ms / 1e9, 'timing', {k: round(v, 2) for k, v in eng.timing.items()})
             del flds
 main()

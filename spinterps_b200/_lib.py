@@ -50,7 +50,8 @@ class spx_systems(C.Structure):
                 ('sys_stn_off', C.c_void_p), ('sys_w_off', C.c_void_p),
                 ('sys_piv_off', C.c_void_p), ('stn_list', C.c_void_p),
                 ('stn_x', C.c_void_p), ('stn_y', C.c_void_p), ('stn_drift', C.c_void_p),
-                ('work', C.c_void_p), ('piv', C.c_void_p), ('info', C.c_void_p)]
+                ('work', C.c_void_p), ('piv', C.c_void_p), ('info', C.c_void_p),
+                ('max_m', C.c_int32)]
 
 
 class spx_rhs(C.Structure):
@@ -58,7 +59,19 @@ class spx_rhs(C.Structure):
                 ('rhs_sys', C.c_void_p), ('rhs_kind', C.c_void_p), ('rhs_arg', C.c_void_p),
                 ('rhs_row', C.c_void_p), ('data', C.c_void_p),
                 ('n_stn', C.c_int32), ('kpad', C.c_int32),
-                ('coef', C.c_void_p), ('resid', C.c_void_p)]
+                ('coef', C.c_void_p), ('resid', C.c_void_p),
+                ('dense', C.c_void_p), ('dense_ld', C.c_int64)]
+
+
+class spx_downdate(C.Structure):
+    _fields_ = [('n_sys', C.c_int32), ('n_stn', C.c_int32), ('n_border', C.c_int32),
+                ('max_r', C.c_int32), ('ginv', C.c_void_p),
+                ('sys_r', C.c_void_p), ('sys_miss_off', C.c_void_p), ('miss_list', C.c_void_p),
+                ('sys_n', C.c_void_p), ('sys_stn_off', C.c_void_p), ('stn_list', C.c_void_p),
+                ('sys_rhs_off', C.c_void_p), ('sys_rhs_cnt', C.c_void_p),
+                ('rhs_urow', C.c_void_p), ('rhs_row', C.c_void_p), ('rhs_kind', C.c_void_p),
+                ('ut', C.c_void_p), ('kpad', C.c_int32), ('coef', C.c_void_p),
+                ('resid', C.c_void_p), ('info', C.c_void_p)]
 
 
 class spx_gemm(C.Structure):
@@ -105,6 +118,8 @@ _SIGS = {
                                          C.c_void_p]),
     'spx_krige_factor_dev': (C.c_int, [C.POINTER(spx_systems), C.c_void_p]),
     'spx_krige_solve_dev': (C.c_int, [C.POINTER(spx_systems), C.POINTER(spx_rhs), C.c_void_p]),
+    'spx_krige_downdate_dev': (C.c_int, [C.POINTER(spx_downdate), C.c_void_p]),
+    'spx_krige_downdate_max_r': (C.c_int, []),
     'spx_estimate_gemm_dev': (C.c_int, [C.POINTER(spx_gemm), C.c_void_p]),
     'spx_estimate_gemm_config': (C.c_int, [C.POINTER(spx_gemm), c_i32p, c_i32p, c_i32p, c_i32p]),
     'spx_pack_rows_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,

@@ -94,9 +94,7 @@ __global__ void __launch_bounds__(256) k_lu_factor(spx_systems s) {
         const double* colk = W + (int64_t)k * m;
         for (int i = k + tid; i < m; i += 256) {
             const double a = fabs(colk[i]);
-            if (a > bv || !(a == a)) {  // NaN wins so that it surfaces in info
-                if (!(bv != bv)) { bv = a; bi = i; }
-            }
+            if (a > bv) { bv = a; bi = i; }  // first largest; NaN never selected
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -147,6 +145,205 @@ __global__ void __launch_bounds__(256) k_lu_factor(spx_systems s) {
             for (int i = k + 1 + lane; i < m; i += 32) cj[i] = fma(-ck[i], ukj, cj[i]);
         }
         __syncthreads();
+    }
+    if (tid == 0) s.info[sys] = s_info;
+}
+
+// ------------------------------------------------------------- blocked LU
+
+// Right-looking blocked LU with partial pivoting, one thread block per system.
+// Per panel of NB columns: (a) the panel (all remaining rows) is staged in
+// shared memory and factored there (warp-shuffle pivot search), (b) row swaps
+// are applied to the other columns, (c) U12 = L11^-1 A12 one column per thread,
+// (d) the trailing matrix is updated A22 -= L21 U12 with FP64 tensor-core MMA
+// (DMMA m8n8k4): L21 fragments straight from the panel in shared memory, U12
+// tiles staged in shared memory, 32x32 accumulator tiles per warp read from and
+// written back to global memory (L2) once per panel.
+constexpr int LU_UT = 64;        // columns of U12 staged per trailing-update block
+constexpr int LU_UP = LU_UT + 4; // pitch: == 4 (mod 16) -> conflict-free B fragments
+
+__device__ __forceinline__ void dmma_lu(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256) k_lu_blocked(spx_systems s, int ldp) {
+    extern __shared__ double lsm[];
+    double* P = lsm;                       // [NB][ldp] panel, column-major
+    double* Us = P + (size_t)NB * ldp;     // [NB][LU_UP] U12 tile, row-major (k, col)
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int s_p;
+    __shared__ double s_pv;
+    __shared__ int s_info;
+    __shared__ int s_piv[NB];
+
+    const int sys = blockIdx.x;
+    const int m = s.sys_n[sys] + border_of(s.sys_kind[sys], s.n_drifts);
+    double* __restrict__ W = s.work + s.sys_w_off[sys];
+    int32_t* __restrict__ piv = s.piv + s.sys_piv_off[sys];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    if (tid == 0) s_info = 0;
+
+    for (int k0 = 0; k0 < m; k0 += NB) {
+        const int nb = min(NB, m - k0);
+        const int rows = m - k0;
+        // ---- (a) stage + factor the panel
+        for (int c = wid; c < nb; c += 8) {
+            const double* src = W + (int64_t)(k0 + c) * m + k0;
+            for (int i = lane; i < rows; i += 32) P[(size_t)c * ldp + i] = src[i];
+        }
+        __syncthreads();
+        for (int j = 0; j < nb; ++j) {
+            double bv = -1.0;
+            int bi = j;
+            const double* colj = P + (size_t)j * ldp;
+            for (int i = j + tid; i < rows; i += 256) {
+                const double a = fabs(colj[i]);
+                if (a > bv) { bv = a; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+            __syncthreads();
+            if (wid == 0) {
+                bv = lane < 8 ? red_v[lane] : -2.0;
+                bi = lane < 8 ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) {
+                    s_p = bi;
+                    s_pv = colj[bi];
+                    s_piv[j] = bi;
+                    piv[k0 + j] = k0 + bi;
+                    if (!(bv > 0.0) && s_info == 0) s_info = k0 + j + 1;
+                }
+            }
+            __syncthreads();
+            const int p = s_p;
+            const double pvv = s_pv;
+            if (p != j && tid < nb) {
+                const double t = P[(size_t)tid * ldp + j];
+                P[(size_t)tid * ldp + j] = P[(size_t)tid * ldp + p];
+                P[(size_t)tid * ldp + p] = t;
+            }
+            __syncthreads();
+            double* cj = P + (size_t)j * ldp;
+            if (pvv != 0.0)
+                for (int i = j + 1 + tid; i < rows; i += 256) cj[i] = cj[i] / pvv;
+            __syncthreads();
+            for (int c = j + 1 + wid; c < nb; c += 8) {
+                double* cc = P + (size_t)c * ldp;
+                const double ujc = cc[j];
+                for (int i = j + 1 + lane; i < rows; i += 32) cc[i] = fma(-cj[i], ujc, cc[i]);
+            }
+            __syncthreads();
+        }
+        // ---- write the factored panel back
+        for (int c = wid; c < nb; c += 8) {
+            double* dst = W + (int64_t)(k0 + c) * m + k0;
+            for (int i = lane; i < rows; i += 32) dst[i] = P[(size_t)c * ldp + i];
+        }
+        // ---- (b) row swaps on the columns outside the panel, (c) U12
+        for (int c = tid; c < m; c += 256) {
+            if (c >= k0 && c < k0 + nb) continue;
+            double* col = W + (int64_t)c * m + k0;
+            for (int j = 0; j < nb; ++j) {
+                const int p = s_piv[j];
+                if (p != j) {
+                    const double t = col[j];
+                    col[j] = col[p];
+                    col[p] = t;
+                }
+            }
+            if (c >= k0 + nb) {
+                double x[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? col[j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    if (j < nb) {
+#pragma unroll
+                        for (int i = j + 1; i < NB; ++i)
+                            if (i < nb) x[i] = fma(-P[(size_t)j * ldp + i], x[j], x[i]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (j < nb) col[j] = x[j];
+            }
+        }
+        __syncthreads();
+        // ---- (d) trailing update with DMMA
+        const int r0 = k0 + nb;            // first trailing row / column
+        const int nt = m - r0;             // trailing size
+        if (nt <= 0) break;
+        const int row_tiles = (nt + 31) / 32;
+        for (int cb = 0; cb < nt; cb += LU_UT) {
+            const int ncol = min(LU_UT, nt - cb);
+            // stage U12[:, cb:cb+ncol] -> Us[k][col]
+            for (int idx = tid; idx < NB * LU_UT; idx += 256) {
+                const int col = idx / NB, k = idx - col * NB;  // k fastest: contiguous in W
+                double v = 0.0;
+                if (col < ncol && k < nb) v = W[(int64_t)(r0 + cb + col) * m + k0 + k];
+                Us[(size_t)k * LU_UP + col] = v;
+            }
+            __syncthreads();
+            const int col_tiles = (ncol + 31) / 32;
+            for (int tile = wid; tile < row_tiles * col_tiles; tile += 8) {
+                const int rt = tile / col_tiles, ctile = tile - rt * col_tiles;
+                const int prow0 = nb + rt * 32;          // row inside the panel
+                const int grow0 = r0 + rt * 32;          // global row
+                const int ccol0 = ctile * 32;            // column inside the U tile
+                double acc[4][4][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < NB; kk += 4) {
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        af[i] = P[(size_t)(kk + t4) * ldp + prow0 + i * 8 + g];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        bf[j] = Us[(size_t)(kk + t4) * LU_UP + ccol0 + j * 8 + g];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dmma_lu(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = grow0 + i * 8 + g;
+                    if (row >= m) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int col = r0 + cb + ccol0 + j * 8 + t4 * 2 + e;
+                            if (col < m && (ccol0 + j * 8 + t4 * 2 + e) < ncol) {
+                                double* a = W + (int64_t)col * m + row;
+                                *a = *a - acc[i][j][e];
+                            }
+                        }
+                }
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0) s.info[sys] = s_info;
 }
@@ -217,6 +414,8 @@ __global__ void __launch_bounds__(256) k_lu_solve(spx_systems s, spx_rhs r) {
             r.coef[coef_offset(row, col, r.kpad)] = b[i];
         }
     }
+    if (r.dense != nullptr)
+        for (int i = tid; i < m; i += 256) r.dense[(int64_t)q * r.dense_ld + i] = b[i];
     if (r.resid != nullptr) {
         // || x - e_n ||_1 : exact solution of A x = [1_n; 0] is e_n for OK / EDK
         double acc = 0.0;
@@ -230,6 +429,157 @@ __global__ void __launch_bounds__(256) k_lu_solve(spx_systems s, spx_rhs r) {
             for (int w = 0; w < 8; ++w) t += red[w];
             r.resid[q] = t;
         }
+    }
+}
+
+
+// ------------------------------------------------------------- downdated solves
+
+constexpr int DD_RB = 8;  // right-hand sides per batch (one per warp)
+
+__global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
+    extern __shared__ double dsm[];
+    const int sys = blockIdx.x;
+    const int r = d.sys_r[sys];
+    const int n = d.sys_n[sys];
+    const int M = d.n_stn + d.n_border;
+    const int ld = d.max_r | 1;  // odd pitch: row swaps hit distinct banks
+    double* S = dsm;                                   // [ld * max_r] column-major
+    double* ys = S + (size_t)ld * d.max_r;             // [DD_RB][ld]
+    int* mi = reinterpret_cast<int*>(ys + (size_t)DD_RB * ld);  // [max_r]
+    int* pv = mi + d.max_r;                            // [max_r]
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int s_p;
+    __shared__ double s_pv;
+    __shared__ int s_info;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t* __restrict__ miss = d.miss_list + d.sys_miss_off[sys];
+    const int32_t* __restrict__ stn = d.stn_list + d.sys_stn_off[sys];
+    const double* __restrict__ G = d.ginv;
+    if (tid == 0) s_info = 0;
+    for (int i = tid; i < r; i += 256) mi[i] = miss[i];
+    __syncthreads();
+    // S = G[Mi, Mi]; row mi[j] of G is read along ascending mi[i] (G symmetric)
+    for (int idx = tid; idx < r * r; idx += 256) {
+        const int j = idx / r, i = idx - j * r;
+        S[i + (size_t)j * ld] = G[(int64_t)mi[j] * M + mi[i]];
+    }
+    __syncthreads();
+    // ---- LU of S in shared memory, partial pivoting
+    for (int k = 0; k < r; ++k) {
+        double bv = -1.0;
+        int bi = k;
+        const double* colk = S + (size_t)k * ld;
+        for (int i = k + tid; i < r; i += 256) {
+            const double a = fabs(colk[i]);
+            if (a > bv) { bv = a; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            bv = lane < 8 ? red_v[lane] : -2.0;
+            bi = lane < 8 ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                s_p = bi;
+                s_pv = colk[bi];
+                pv[k] = bi;
+                if (!(bv > 0.0) && s_info == 0) s_info = k + 1;
+            }
+        }
+        __syncthreads();
+        const int p = s_p;
+        const double pvv = s_pv;
+        if (p != k)
+            for (int j = tid; j < r; j += 256) {
+                const double t = S[k + (size_t)j * ld];
+                S[k + (size_t)j * ld] = S[p + (size_t)j * ld];
+                S[p + (size_t)j * ld] = t;
+            }
+        __syncthreads();
+        double* ck = S + (size_t)k * ld;
+        if (pvv != 0.0)
+            for (int i = k + 1 + tid; i < r; i += 256) ck[i] = ck[i] / pvv;
+        __syncthreads();
+        for (int j = k + 1 + wid; j < r; j += 8) {
+            double* cj = S + (size_t)j * ld;
+            const double ukj = cj[k];
+            for (int i = k + 1 + lane; i < r; i += 32) cj[i] = fma(-ck[i], ukj, cj[i]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) d.info[sys] = s_info;
+
+    // ---- right-hand sides, DD_RB at a time
+    const int64_t q0 = d.sys_rhs_off[sys];
+    const int nq = d.sys_rhs_cnt[sys];
+    const int nk = n + d.n_border;
+    for (int base = 0; base < nq; base += DD_RB) {
+        const int nb = min(DD_RB, nq - base);
+        if (wid < nb && r > 0) {
+            // y = S^-1 u[Mi] : one warp per right-hand side, warp-synchronous
+            double* y = ys + (size_t)wid * ld;
+            const double* u = d.ut + (int64_t)d.rhs_urow[q0 + base + wid] * M;
+            for (int i = lane; i < r; i += 32) y[i] = u[mi[i]];
+            __syncwarp();
+            if (lane == 0)
+                for (int k = 0; k < r; ++k) {
+                    const int p = pv[k];
+                    if (p != k) { const double t = y[k]; y[k] = y[p]; y[p] = t; }
+                }
+            __syncwarp();
+            for (int k = 0; k < r - 1; ++k) {
+                const double xk = y[k];
+                const double* ck = S + (size_t)k * ld;
+                for (int i = k + 1 + lane; i < r; i += 32) y[i] = fma(-ck[i], xk, y[i]);
+                __syncwarp();
+            }
+            for (int k = r - 1; k >= 0; --k) {
+                const double* ck = S + (size_t)k * ld;
+                const double xk = y[k] / ck[k];
+                __syncwarp();
+                if (lane == 0) y[k] = xk;
+                for (int i = lane; i < k; i += 32) y[i] = fma(-ck[i], xk, y[i]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // c_K = u_K - G[K, Mi] y  for the nb right-hand sides at once
+        for (int i = tid; i < nk; i += 256) {
+            const int ki = (i < n) ? stn[i] : (d.n_stn + (i - n));
+            double acc[DD_RB];
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w)
+                acc[w] = (w < nb) ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + ki] : 0.0;
+            for (int j = 0; j < r; ++j) {
+                const double gv = G[(int64_t)mi[j] * M + ki];
+#pragma unroll
+                for (int w = 0; w < DD_RB; ++w) acc[w] = fma(-gv, ys[(size_t)w * ld + j], acc[w]);
+            }
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w) {
+                if (w >= nb) break;
+                const int64_t q = q0 + base + w;
+                const int64_t row = d.rhs_row[q];
+                if (row >= 0) d.coef[coef_offset(row, ki, d.kpad)] = acc[w];
+                if (d.rhs_kind[q] == 1)
+                    atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -267,7 +617,38 @@ int spx_krige_factor_dev(const spx_systems* s, void* stream) {
         return SPX_EINVAL;
     }
     if (s->n_sys == 0) return SPX_OK;
-    k_lu_factor<<<s->n_sys, 256, 0, (cudaStream_t)stream>>>(*s);
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, max_smem = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (s->max_m > 0) {
+        // panel pitch: >= rows rounded up to the 32-row MMA tiles, == 4 (mod 16)
+        const int ldp = ((s->max_m + 31) / 32) * 32 + 32 + 4;
+        const int nbs[3] = {32, 16, 8};
+        for (int nb : nbs) {
+            const size_t smem = ((size_t)nb * ldp + (size_t)nb * LU_UP) * sizeof(double);
+            if (smem + 1024 > (size_t)max_smem) continue;
+            if (nb == 32) {
+                SPX_CUDA(cudaFuncSetAttribute(k_lu_blocked<32>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+                k_lu_blocked<32><<<s->n_sys, 256, smem, st>>>(*s, ldp);
+            } else if (nb == 16) {
+                SPX_CUDA(cudaFuncSetAttribute(k_lu_blocked<16>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+                k_lu_blocked<16><<<s->n_sys, 256, smem, st>>>(*s, ldp);
+            } else {
+                SPX_CUDA(cudaFuncSetAttribute(k_lu_blocked<8>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+                k_lu_blocked<8><<<s->n_sys, 256, smem, st>>>(*s, ldp);
+            }
+            SPX_CHECK_LAUNCH("k_lu_blocked");
+            return SPX_OK;
+        }
+    }
+    k_lu_factor<<<s->n_sys, 256, 0, st>>>(*s);  // unblocked fallback (any size)
     SPX_CHECK_LAUNCH("k_lu_factor");
     return SPX_OK;
 }
@@ -294,6 +675,53 @@ int spx_krige_solve_dev(const spx_systems* s, const spx_rhs* r, void* stream) {
                                       (int)smem));
     k_lu_solve<<<r->n_rhs, 256, smem, (cudaStream_t)stream>>>(*s, *r);
     SPX_CHECK_LAUNCH("k_lu_solve");
+    return SPX_OK;
+}
+
+static size_t dd_smem_bytes(int max_r) {
+    const size_t ld = (size_t)(max_r | 1);
+    return (ld * max_r + (size_t)DD_RB * ld) * sizeof(double) + 2 * (size_t)max_r * sizeof(int);
+}
+
+int spx_krige_downdate_max_r(void) {
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) !=
+            cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int r = 0;
+    while (dd_smem_bytes(r + 8) + 256 <= (size_t)max_smem) r += 8;
+    return r;
+}
+
+int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
+    if (!d) {
+        set_error("krige_downdate: null argument");
+        return SPX_EINVAL;
+    }
+    if (d->n_sys == 0) return SPX_OK;
+    if (d->kpad % 4 != 0 || d->max_r < 0) {
+        set_error("krige_downdate: bad kpad / max_r");
+        return SPX_EINVAL;
+    }
+    const size_t smem = dd_smem_bytes(d->max_r > 0 ? d->max_r : 1);
+    int dev = 0, max_smem = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem + 256 > (size_t)max_smem) {
+        set_error("krige_downdate: max_r=%d needs %zu bytes of shared memory (limit %d)",
+                  d->max_r, smem, max_smem);
+        return SPX_ENOMEM;
+    }
+    spx_downdate dd = *d;
+    if (dd.max_r < 1) dd.max_r = 1;
+    if (smem > 48 * 1024)
+        SPX_CUDA(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    k_downdate<<<d->n_sys, 256, smem, (cudaStream_t)stream>>>(dd);
+    SPX_CHECK_LAUNCH("k_downdate");
     return SPX_OK;
 }
 

@@ -17,8 +17,11 @@ There is no CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
+import time
+import types
 
 import numpy as np
 import torch
@@ -67,10 +70,16 @@ class ChunkEngine:
         self.work_limit = int(work_limit_bytes)
         self.aux_limit = int(aux_limit_bytes)
         self.lambda_tol = float(lambda_tol)
+        # downdated solves (spx_krige_downdate_dev) when a variogram is shared by at
+        # least this many availability groups
+        self.downdate = True
+        self.downdate_min_systems = 4
         self.stats = {}
         # bench hook: CUDA events around every estimate-contraction launch
         self.profile_gemm = False
         self.gemm_events = []
+        self.sync_timing = False
+        self.timing = {}
 
     # ------------------------------------------------------------ helpers
     def _dev(self, arr, dtype=None):
@@ -88,6 +97,19 @@ class ChunkEngine:
 
     def _count(self, key, n=1):
         self.stats[key] = self.stats.get(key, 0) + n
+
+    @contextlib.contextmanager
+    def _phase(self, name):
+        """Wall-clock per phase (with device syncs) when self.sync_timing is set;
+        a debugging aid, off in normal runs."""
+        if not self.sync_timing:
+            yield
+            return
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        yield
+        torch.cuda.synchronize(self.device)
+        self.timing[name] = self.timing.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     # ------------------------------------------------------------ public
     def interp_chunk(
@@ -114,6 +136,7 @@ class ChunkEngine:
             n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
             intrp_dtype, return_device):
         self.stats = {}
+        self.timing = {}
         data = np.ascontiguousarray(data, dtype=np.float64)
         stn_xs = np.ascontiguousarray(stn_xs, dtype=np.float64)
         stn_ys = np.ascontiguousarray(stn_ys, dtype=np.float64)
@@ -166,6 +189,7 @@ class ChunkEngine:
         assert n_cells > 0
 
         # ---- per-step host logic --------------------------------------------
+        t_host0 = time.perf_counter()
         avail = ~np.isnan(data)
         grp_of_step, grp_mask = availability_groups(avail)       # grps.py:57-101
         n_grps = grp_mask.shape[0]
@@ -179,6 +203,7 @@ class ChunkEngine:
             steps_flags = (np.where(avail, data, -np.inf) >= min_var_thr).any(axis=1)  # :760-765
         single_val = data0.sum(axis=1)                               # value when n_avail == 1
 
+        self.timing['host_groups'] = 1e3 * (time.perf_counter() - t_host0)
         # ---- device residents -----------------------------------------------
         d_stn_x = self._dev(stn_xs)
         d_stn_y = self._dev(stn_ys)
@@ -191,6 +216,7 @@ class ChunkEngine:
             n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
             d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
             d_data=d_data, d_data0=d_data0, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
+            stn_xs=stn_xs, stn_ys=stn_ys,
             has_lo=int(min_var_cut is not None), has_hi=int(max_var_cut is not None),
             lo=float(min_var_cut) if min_var_cut is not None else 0.0,
             hi=float(max_var_cut) if max_var_cut is not None else 0.0,
@@ -353,8 +379,8 @@ class ChunkEngine:
         kpad = _pad_up(n_stn, 8)
         grp_of_step = ctx['grp_of_step']
         # distance scale common to every cell (cancels in the ratio)
-        xs = np.concatenate([ctx['dst_xs'], ctx['d_stn_x'].cpu().numpy()])
-        ys = np.concatenate([ctx['dst_ys'], ctx['d_stn_y'].cpu().numpy()])
+        xs = np.concatenate([ctx['dst_xs'], ctx['stn_xs']])
+        ys = np.concatenate([ctx['dst_ys'], ctx['stn_ys']])
         scale = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
         scale = scale if scale > 0 else 1.0
 
@@ -397,7 +423,6 @@ class ChunkEngine:
         Z[t, i] = rhs_i . A_g^-1 [z_t; 0]."""
         if not steps.size:
             return
-        lib = self.lib
         kind = _lib.KRG_KINDS[kind_name]
         n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
         n_drifts = 0 if kind != 2 else int(stns_drft.shape[1])
@@ -405,36 +430,44 @@ class ChunkEngine:
         kpad = _pad_up(n_stn + n_border, 8)
         grp_of_step, grp_mask, grp_n = ctx['grp_of_step'], ctx['grp_mask'], ctx['grp_n']
 
-        d_cell_drift = d_stn_drift = None
+        K = types.SimpleNamespace(kind=kind, n_drifts=n_drifts, n_border=n_border, kpad=kpad,
+                                  uniq_vgs=uniq_vgs, keep={})
+        K.d_cell_drift = K.d_stn_drift = None
         bad_cells = np.zeros(0, dtype=np.int64)
+        drft = None
         if kind == 2:
             drft = np.ascontiguousarray(drft_arrs, dtype=np.float64)
             assert drft.shape == (n_drifts, n_cells)
-            d_cell_drift = self._dev(drft)
-            d_stn_drift = self._dev(np.ascontiguousarray(stns_drft, dtype=np.float64))
+            K.d_cell_drift = self._dev(drft)
+            K.d_stn_drift = self._dev(np.ascontiguousarray(stns_drft, dtype=np.float64))
             bad_cells = np.where(np.isnan(drft).any(axis=0))[0]
 
-        # station lists per group (ascending station index = reference order)
+        # station lists per group (ascending station index = reference order); the
+        # pseudo-group n_grps holds every station (the "full" system of the downdate)
+        n_grps = grp_mask.shape[0]
         grps_used = np.unique(grp_of_step[steps])
-        stn_off = np.zeros(grp_mask.shape[0], dtype=np.int64)
+        stn_off = np.zeros(n_grps + 1, dtype=np.int64)
         stn_off[grps_used] = np.concatenate([[0], np.cumsum(grp_n[grps_used])])[:-1]
-        stn_list = np.where(grp_mask[grps_used])[1].astype(np.int32)   # row-major: per group, ascending
-        d_stn_list = self._dev(stn_list)
+        stn_off[n_grps] = int(grp_n[grps_used].sum())
+        stn_list = np.concatenate([np.where(grp_mask[grps_used])[1],
+                                   np.arange(n_stn)]).astype(np.int32)
+        K.stn_off = stn_off
+        K.d_stn_list = self._dev(stn_list)
+        K.full_grp = n_grps
 
-        # systems = distinct (group, variogram) among the steps, grouped by variogram
+        # systems = distinct (group, variogram) pairs among the steps
         pair = grp_of_step[steps].astype(np.int64) * len(uniq_vgs) + step_vg[steps]
         upair, sys_of_row = np.unique(pair, return_inverse=True)
-        sys_grp = (upair // len(uniq_vgs)).astype(np.int32)
-        sys_vg = (upair % len(uniq_vgs)).astype(np.int32)
+        K.sys_grp = (upair // len(uniq_vgs)).astype(np.int32)
+        K.sys_vg = (upair % len(uniq_vgs)).astype(np.int32)
         n_sys = upair.size
-        sys_n = grp_n[sys_grp].astype(np.int32)
-        sys_m = sys_n.astype(np.int64) + n_border
+        K.sys_n = grp_n[K.sys_grp].astype(np.int32)
 
         # coefficient rows: steps ordered by variogram, one SPX_BM-aligned segment each
         order = np.argsort(step_vg[steps], kind='stable')
-        steps_o = steps[order]
-        sys_o = sys_of_row[order]
-        vg_o = step_vg[steps_o]
+        K.steps_o = steps[order]
+        K.sys_o = sys_of_row[order]
+        vg_o = step_vg[K.steps_o]
         seg_vgs, seg_first, seg_cnt = np.unique(vg_o, return_index=True, return_counts=True)
         seg_row0 = np.zeros(seg_vgs.size, dtype=np.int64)
         acc = 0
@@ -442,138 +475,289 @@ class ChunkEngine:
             seg_row0[k] = acc
             acc += _pad_up(seg_cnt[k], _lib.SPX_BM)
         total_rows = acc
-        row_of = np.empty(steps_o.size, dtype=np.int64)
+        K.row_of = np.empty(K.steps_o.size, dtype=np.int64)
         for k in range(seg_vgs.size):
-            row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = seg_row0[k] + np.arange(seg_cnt[k])
-        coef = torch.zeros(total_rows * kpad, dtype=_F64, device=self.device)
+            K.row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = seg_row0[k] + np.arange(seg_cnt[k])
+        K.coef = torch.zeros(total_rows * kpad, dtype=_F64, device=self.device)
         row_dst_np = np.full(total_rows, -1, dtype=np.int32)
-        row_dst_np[row_of] = steps_o
+        row_dst_np[K.row_of] = K.steps_o
         d_row_dst = self._dev(row_dst_np)
+        K.rows_by_sys = np.argsort(K.sys_o, kind='stable')
+        cnt = np.bincount(K.sys_o, minlength=n_sys)
+        K.sys_row_beg = np.concatenate([[0], np.cumsum(cnt)])
 
-        d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8))
+        K.d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8))
 
         # bound for the sum(lambda) screening: |rhs| <= max(vg bound, 1, |drift|)
-        xs = np.concatenate([ctx['dst_xs'], ctx['d_stn_x'].cpu().numpy()])
-        ys = np.concatenate([ctx['dst_ys'], ctx['d_stn_y'].cpu().numpy()])
+        xs = np.concatenate([ctx['dst_xs'], ctx['stn_xs']])
+        ys = np.concatenate([ctx['dst_ys'], ctx['stn_ys']])
         max_dist = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
         rhs_bound = np.array([max(1.0, vg_abs_bound(v, max_dist)) for v in uniq_vgs])
         if kind == 2:
             with np.errstate(invalid='ignore'):
                 dmax = np.nanmax(np.abs(drft)) if np.isfinite(drft).any() else 1.0
             rhs_bound = np.maximum(rhs_bound, dmax)
+        K.rhs_bound = rhs_bound
 
-        # ---- factor + solve in batches bounded by the workspace limit -----
-        flagged = np.zeros(n_sys, dtype=bool)
+        # ---- solve: downdated where it pays, direct LU otherwise ----------
+        resid = np.full(n_sys, np.inf)
         singular = np.zeros(n_sys, dtype=bool)
-        sys_bytes = sys_m * sys_m * 8
-        b0 = 0
-        rows_by_sys = np.argsort(sys_o, kind='stable')
-        sys_row_cnt = np.bincount(sys_o, minlength=n_sys)
-        sys_row_beg = np.concatenate([[0], np.cumsum(sys_row_cnt)])
-        keep = {}
-        while b0 < n_sys:
-            b1 = b0 + 1
-            tot = int(sys_bytes[b0])
-            while b1 < n_sys and tot + int(sys_bytes[b1]) <= self.work_limit and (b1 - b0) < 60000:
-                tot += int(sys_bytes[b1])
-                b1 += 1
-            sl = slice(b0, b1)
-            nb = b1 - b0
-            w_off = np.concatenate([[0], np.cumsum(sys_m[sl] * sys_m[sl])])[:-1].astype(np.int64)
-            p_off = np.concatenate([[0], np.cumsum(sys_m[sl])])[:-1].astype(np.int64)
-            work = torch.empty(int((sys_m[sl] * sys_m[sl]).sum()), dtype=_F64, device=self.device)
-            piv = torch.empty(int(sys_m[sl].sum()), dtype=_I32, device=self.device)
-            info = torch.zeros(nb, dtype=_I32, device=self.device)
-            t_sys_n = self._dev(sys_n[sl])
-            t_kind = self._dev(np.full(nb, kind, dtype=np.int32))
-            t_vg = self._dev(sys_vg[sl])
-            t_stn_off = self._dev(stn_off[sys_grp[sl]])
-            t_w_off = self._dev(w_off)
-            t_p_off = self._dev(p_off)
-            S = _lib.spx_systems()
-            S.n_sys = nb
-            S.n_drifts = n_drifts
-            S.sys_n = t_sys_n.data_ptr()
-            S.sys_kind = t_kind.data_ptr()
-            S.sys_vg = t_vg.data_ptr()
-            S.sys_stn_off = t_stn_off.data_ptr()
-            S.sys_w_off = t_w_off.data_ptr()
-            S.sys_piv_off = t_p_off.data_ptr()
-            S.stn_list = d_stn_list.data_ptr()
-            S.stn_x = ctx['d_stn_x'].data_ptr()
-            S.stn_y = ctx['d_stn_y'].data_ptr()
-            S.stn_drift = d_stn_drift.data_ptr() if d_stn_drift is not None else None
-            S.work = work.data_ptr()
-            S.piv = piv.data_ptr()
-            S.info = info.data_ptr()
-            _lib.check(lib.spx_krige_assemble_dev(C.byref(S), self._ptr(d_vgs), len(uniq_vgs),
-                                                  ctx['min_vg_val'], self._stream()), 'assemble')
-            _lib.check(lib.spx_krige_factor_dev(C.byref(S), self._stream()), 'factor')
-            self._count('launches', 2)
-            self._count('lu_flop', int((2 * sys_m[sl] ** 3 // 3).sum()))
-
-            # right-hand sides: every data row of these systems + one ones-vector each
-            ridx = np.concatenate([rows_by_sys[sys_row_beg[s]:sys_row_beg[s + 1]]
-                                   for s in range(b0, b1)])
-            n_data = ridx.size
-            rhs_sys = np.concatenate([sys_o[ridx] - b0, np.arange(nb)]).astype(np.int32)
-            rhs_kind = np.concatenate([np.zeros(n_data), np.ones(nb)]).astype(np.int32)
-            rhs_arg = np.concatenate([steps_o[ridx], np.zeros(nb)]).astype(np.int32)
-            rhs_row = np.concatenate([row_of[ridx], np.full(nb, -1)]).astype(np.int64)
-            resid = torch.zeros(rhs_sys.size, dtype=_F64, device=self.device)
-            t_rs, t_rk, t_ra, t_rr = (self._dev(rhs_sys), self._dev(rhs_kind), self._dev(rhs_arg),
-                                      self._dev(rhs_row))
-            R = _lib.spx_rhs()
-            R.n_rhs = int(rhs_sys.size)
-            R.rhs_sys, R.rhs_kind = t_rs.data_ptr(), t_rk.data_ptr()
-            R.rhs_arg, R.rhs_row = t_ra.data_ptr(), t_rr.data_ptr()
-            R.data = ctx['d_data'].data_ptr()
-            R.n_stn = n_stn
-            R.kpad = kpad
-            R.coef = coef.data_ptr()
-            R.resid = resid.data_ptr()
-            _lib.check(lib.spx_krige_solve_dev(C.byref(S), C.byref(R), self._stream()), 'solve')
-            self._count('launches')
-
-            info_h = info.cpu().numpy()
-            resid_h = resid[n_data:].cpu().numpy()
-            singular[sl] = info_h != 0
-            with np.errstate(invalid='ignore'):
-                dev = resid_h * rhs_bound[sys_vg[sl]]
-            flagged[sl] = (kind == 1) | singular[sl] | ~(dev <= self.lambda_tol)
-            if flagged[sl].any():
-                keep[b0] = (S, work, piv, info, t_sys_n, t_kind, t_vg, t_stn_off, t_w_off, t_p_off)
-            b0 = b1
+        vg_cnt = np.bincount(K.sys_vg, minlength=len(uniq_vgs))
+        r_sys = n_stn - K.sys_n
+        use_dd = np.zeros(n_sys, dtype=bool)
+        if self.downdate and kind != 1:
+            max_r = self.lib.spx_krige_downdate_max_r()
+            use_dd = (vg_cnt[K.sys_vg] >= self.downdate_min_systems) & (r_sys <= max_r)
+        if use_dd.any():
+            with self._phase('solve_downdate'):
+                done = self._solve_downdate(ctx, K, np.where(use_dd)[0], resid, singular)
+            use_dd &= done
+        direct = np.where(~use_dd)[0]
+        if direct.size:
+            with self._phase('solve_direct'):
+                self._solve_direct(ctx, K, direct, resid, singular, want_resid=(kind != 1))
+        with np.errstate(invalid='ignore'):
+            dev = resid * rhs_bound[K.sys_vg]
+        flagged = (kind == 1) | singular | ~(dev <= self.lambda_tol)
 
         self.stats['n_systems'] = self.stats.get('n_systems', 0) + n_sys
+        self.stats['n_downdated'] = self.stats.get('n_downdated', 0) + int(use_dd.sum())
         self.stats['n_flagged'] = self.stats.get('n_flagged', 0) + int(flagged.sum())
 
         # ---- main contraction: one launch per variogram segment ----------
         for k in range(seg_vgs.size):
-            seg_coef = coef[seg_row0[k] * kpad:]
-            self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad, n_border=n_border,
-                       gen=_lib.GEN_VG, epi=_lib.EPI_FIELD,
-                       row_dst=d_row_dst[seg_row0[k]:], out=out,
-                       vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]), covar_flag=int(kind == 1),
-                       cell_drift=d_cell_drift)
+            seg_coef = K.coef[seg_row0[k] * kpad:]
+            with self._phase('gemm'):
+                self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad,
+                           n_border=n_border, gen=_lib.GEN_VG, epi=_lib.EPI_FIELD,
+                           row_dst=d_row_dst[seg_row0[k]:], out=out,
+                           vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]),
+                           covar_flag=int(kind == 1), cell_drift=K.d_cell_drift)
 
         # ---- fallbacks to the nearest neighbour (steps.py:418-426) --------
         if bad_cells.size:
             # NaN drift at a cell -> sum(lambda) is NaN -> NNB there, every step
-            gl = np.unique(grp_of_step[steps_o])
+            gl = np.unique(grp_of_step[K.steps_o])
             slot = {int(g): i for i, g in enumerate(gl)}
             nnb = self._nnb_index(ctx, gl, cells=bad_cells)
             pos = ctx['out_pos'][bad_cells] if ctx['out_pos'] is not None else bad_cells
-            self._nnb_gather(ctx, out, nnb, steps_o, [slot[int(grp_of_step[s])] for s in steps_o],
+            self._nnb_gather(ctx, out, nnb, K.steps_o,
+                             [slot[int(grp_of_step[s])] for s in K.steps_o],
                              n_cells=int(bad_cells.size), d_pos=self._dev(pos.astype(np.int32)))
 
         if flagged.any():
-            self._krige_flagged(ctx, out, kind, kpad, n_border, flagged, singular, keep, sys_vg,
-                                sys_grp, sys_o, steps_o, uniq_vgs, d_cell_drift, bad_cells,
-                                problem_steps)
+            # flagged systems need their factors: (re)do the downdated ones directly
+            redo = np.where(flagged & use_dd)[0]
+            if redo.size:
+                self._solve_direct(ctx, K, redo, resid, singular, want_resid=False)
+            self._krige_flagged(ctx, out, K, flagged, singular, bad_cells, problem_steps)
 
-    def _krige_flagged(self, ctx, out, kind, kpad, n_border, flagged, singular, keep, sys_vg,
-                       sys_grp, sys_o, steps_o, uniq_vgs, d_cell_drift, bad_cells, problem_steps):
+    # ---- direct path: assemble + LU + substitution per system --------------
+    def _systems_struct(self, ctx, K, sys_ids, grp_ids, vg_ids):
+        """Device descriptors for a batch of systems (groups may be K.full_grp)."""
+        n_stn = ctx['n_stn']
+        nb = len(sys_ids)
+        grp_n_ext = np.concatenate([ctx['grp_n'], [n_stn]])
+        n = grp_n_ext[grp_ids].astype(np.int32)
+        m = n.astype(np.int64) + K.n_border
+        w_off = np.concatenate([[0], np.cumsum(m * m)])[:-1].astype(np.int64)
+        p_off = np.concatenate([[0], np.cumsum(m)])[:-1].astype(np.int64)
+        T = types.SimpleNamespace()
+        T.work = torch.empty(int((m * m).sum()), dtype=_F64, device=self.device)
+        T.piv = torch.empty(int(m.sum()), dtype=_I32, device=self.device)
+        T.info = torch.zeros(nb, dtype=_I32, device=self.device)
+        T.t = [self._dev(n), self._dev(np.full(nb, K.kind, dtype=np.int32)),
+               self._dev(np.asarray(vg_ids, dtype=np.int32)), self._dev(K.stn_off[grp_ids]),
+               self._dev(w_off), self._dev(p_off)]
+        S = _lib.spx_systems()
+        S.n_sys = nb
+        S.n_drifts = K.n_drifts
+        (S.sys_n, S.sys_kind, S.sys_vg, S.sys_stn_off, S.sys_w_off, S.sys_piv_off) = (
+            x.data_ptr() for x in T.t)
+        S.stn_list = K.d_stn_list.data_ptr()
+        S.stn_x = ctx['d_stn_x'].data_ptr()
+        S.stn_y = ctx['d_stn_y'].data_ptr()
+        S.stn_drift = K.d_stn_drift.data_ptr() if K.d_stn_drift is not None else None
+        S.work = T.work.data_ptr()
+        S.piv = T.piv.data_ptr()
+        S.info = T.info.data_ptr()
+        S.max_m = int(m.max())
+        T.S = S
+        T.m = m
+        return T
+
+    def _factor(self, ctx, K, T):
+        _lib.check(self.lib.spx_krige_assemble_dev(
+            C.byref(T.S), self._ptr(K.d_vgs), len(K.uniq_vgs), ctx['min_vg_val'], self._stream()),
+            'assemble')
+        _lib.check(self.lib.spx_krige_factor_dev(C.byref(T.S), self._stream()), 'factor')
+        self._count('launches', 2)
+        self._count('lu_flop', int((2 * T.m ** 3 // 3).sum()))
+
+    def _lu_solve(self, ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, coef, want_resid=False,
+                  dense=None, dense_ld=0):
+        n_rhs = len(rhs_sys)
+        resid = torch.zeros(n_rhs, dtype=_F64, device=self.device) if want_resid else None
+        ts = [self._dev(np.asarray(rhs_sys, dtype=np.int32)),
+              self._dev(np.asarray(rhs_kind, dtype=np.int32)),
+              self._dev(np.asarray(rhs_arg, dtype=np.int32)),
+              self._dev(np.asarray(rhs_row, dtype=np.int64))]
+        R = _lib.spx_rhs()
+        R.n_rhs = n_rhs
+        R.rhs_sys, R.rhs_kind, R.rhs_arg, R.rhs_row = (x.data_ptr() for x in ts)
+        R.data = ctx['d_data'].data_ptr()
+        R.n_stn = ctx['n_stn']
+        R.kpad = K.kpad
+        R.coef = coef.data_ptr()
+        R.resid = resid.data_ptr() if resid is not None else None
+        R.dense = dense.data_ptr() if dense is not None else None
+        R.dense_ld = int(dense_ld)
+        _lib.check(self.lib.spx_krige_solve_dev(C.byref(T.S), C.byref(R), self._stream()), 'solve')
+        self._count('launches')
+        return resid
+
+    def _solve_direct(self, ctx, K, sys_ids, resid_out, singular_out, want_resid=True):
+        """Assemble, factor and solve the listed systems in batches bounded by the
+        workspace limit; data rows go to K.coef, one ones-vector per system gives
+        the sum(lambda) residual.  Workspaces are kept in K.keep for the flagged
+        handler."""
+        m_all = K.sys_n[sys_ids].astype(np.int64) + K.n_border
+        nbytes = m_all * m_all * 8
+        b0 = 0
+        while b0 < sys_ids.size:
+            b1 = b0 + 1
+            tot = int(nbytes[b0])
+            while (b1 < sys_ids.size and tot + int(nbytes[b1]) <= self.work_limit
+                   and (b1 - b0) < 60000):
+                tot += int(nbytes[b1])
+                b1 += 1
+            ids = sys_ids[b0:b1]
+            nb = ids.size
+            T = self._systems_struct(ctx, K, ids, K.sys_grp[ids], K.sys_vg[ids])
+            self._factor(ctx, K, T)
+            ridx = np.concatenate([K.rows_by_sys[K.sys_row_beg[s]:K.sys_row_beg[s + 1]]
+                                   for s in ids])
+            local = np.full(K.sys_n.size, -1, dtype=np.int64)
+            local[ids] = np.arange(nb)
+            n_data = ridx.size
+            rhs_sys = np.concatenate([local[K.sys_o[ridx]], np.arange(nb)])
+            rhs_kind = np.concatenate([np.zeros(n_data), np.ones(nb)])
+            rhs_arg = np.concatenate([K.steps_o[ridx], np.zeros(nb)])
+            rhs_row = np.concatenate([K.row_of[ridx], np.full(nb, -1)])
+            if not want_resid:
+                rhs_sys, rhs_kind = rhs_sys[:n_data], rhs_kind[:n_data]
+                rhs_arg, rhs_row = rhs_arg[:n_data], rhs_row[:n_data]
+            resid = None
+            if rhs_sys.size:
+                resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
+                                       want_resid=want_resid)
+            singular_out[ids] = T.info.cpu().numpy() != 0
+            if want_resid:
+                resid_out[ids] = resid[n_data:].cpu().numpy()
+            # keep the factors only where the flagged handler may need them
+            with np.errstate(invalid='ignore'):
+                need = (K.kind == 1) | singular_out[ids] | ~(
+                    resid_out[ids] * K.rhs_bound[K.sys_vg[ids]] <= self.lambda_tol)
+            if need.any() or not want_resid:
+                for k, s in enumerate(ids):
+                    K.keep[int(s)] = (T, k)
+            b0 = b1
+
+    # ---- downdated path -------------------------------------------------
+    def _solve_downdate(self, ctx, K, sys_ids, resid_out, singular_out):
+        """A_g^-1 b from the inverse of the full system of each variogram
+        (include/spx_b200.h: spx_downdate).  Returns a bool mask over ALL systems
+        marking those actually handled here."""
+        lib = self.lib
+        n_stn = ctx['n_stn']
+        M = n_stn + K.n_border
+        done = np.zeros(K.sys_n.size, dtype=bool)
+        vgs_here = np.unique(K.sys_vg[sys_ids])
+        # full systems, one per variogram, factored together
+        T = self._systems_struct(ctx, K, np.arange(vgs_here.size),
+                                 np.full(vgs_here.size, K.full_grp), vgs_here)
+        self._factor(ctx, K, T)
+        ginv = torch.empty((vgs_here.size, M, M), dtype=_F64, device=self.device)
+        n_full = vgs_here.size
+        rhs_sys = np.repeat(np.arange(n_full), M + 1)
+        rhs_kind = np.tile(np.concatenate([np.full(M, 2), [1]]), n_full)
+        rhs_arg = np.tile(np.concatenate([np.arange(M), [0]]), n_full)
+        rhs_row = np.full(rhs_sys.size, -1)
+        dense = torch.empty((n_full * (M + 1), M), dtype=_F64, device=self.device)
+        resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
+                               want_resid=True, dense=dense, dense_ld=M)
+        full_info = T.info.cpu().numpy()
+        full_resid = resid.view(n_full, M + 1)[:, M].cpu().numpy()
+        dense = dense.view(n_full, M + 1, M)
+        miss_mask_all = ~ctx['grp_mask']
+        for vi, v in enumerate(vgs_here):
+            healthy = (full_info[vi] == 0) and (full_resid[vi] <= 1e-9)
+            ids = sys_ids[K.sys_vg[sys_ids] == v]
+            if not healthy or not ids.size:
+                continue
+            G = dense[vi, :M, :]
+            grp = K.sys_grp[ids]
+            r = (n_stn - K.sys_n[ids]).astype(np.int32)
+            miss_list = np.where(miss_mask_all[grp])[1].astype(np.int32)
+            miss_off = np.concatenate([[0], np.cumsum(r)])[:-1].astype(np.int64)
+            # right-hand sides: data rows of every system + one ones-vector each
+            ridx = np.concatenate([K.rows_by_sys[K.sys_row_beg[s]:K.sys_row_beg[s + 1]]
+                                   for s in ids])
+            cnt = (K.sys_row_beg[ids + 1] - K.sys_row_beg[ids]).astype(np.int64)
+            n_data = ridx.size
+            nsys = ids.size
+            # Bt rows: [data rows in ridx order | group masks]
+            d_steps = self._dev(K.steps_o[ridx].astype(np.int64))
+            Bt = torch.zeros((n_data + nsys, M), dtype=_F64, device=self.device)
+            Bt[:n_data, :n_stn] = ctx['d_data0'].index_select(0, d_steps)
+            Bt[n_data:, :n_stn] = self._dev(ctx['grp_mask'][grp].astype(np.float64))
+            Ut = torch.matmul(Bt, G)
+            self._count('launches')
+            # per-system contiguous rhs lists: its data rows then its ones-vector
+            beg = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+            rhs_off = (beg + np.arange(nsys)).astype(np.int64)
+            rhs_cnt = (cnt + 1).astype(np.int32)
+            n_rhs = int(n_data + nsys)
+            urow = np.empty(n_rhs, dtype=np.int32)
+            rrow = np.empty(n_rhs, dtype=np.int64)
+            rkind = np.zeros(n_rhs, dtype=np.int32)
+            pos_data = np.arange(n_data) + np.repeat(np.arange(nsys), cnt)
+            urow[pos_data] = np.arange(n_data)
+            rrow[pos_data] = K.row_of[ridx]
+            pos_ones = rhs_off + cnt
+            urow[pos_ones] = n_data + np.arange(nsys)
+            rrow[pos_ones] = -1
+            rkind[pos_ones] = 1
+            d_resid = torch.zeros(n_rhs, dtype=_F64, device=self.device)
+            d_info = torch.zeros(nsys, dtype=_I32, device=self.device)
+            ts = [self._dev(r), self._dev(miss_off), self._dev(miss_list),
+                  self._dev(K.sys_n[ids]), self._dev(K.stn_off[grp]),
+                  self._dev(rhs_off), self._dev(rhs_cnt), self._dev(urow), self._dev(rrow),
+                  self._dev(rkind)]
+            D = _lib.spx_downdate()
+            D.n_sys = nsys
+            D.n_stn = n_stn
+            D.n_border = K.n_border
+            D.max_r = int(r.max()) if r.size else 0
+            D.ginv = G.data_ptr()
+            (D.sys_r, D.sys_miss_off, D.miss_list, D.sys_n, D.sys_stn_off, D.sys_rhs_off,
+             D.sys_rhs_cnt, D.rhs_urow, D.rhs_row, D.rhs_kind) = (x.data_ptr() for x in ts)
+            D.stn_list = K.d_stn_list.data_ptr()
+            D.ut = Ut.data_ptr()
+            D.kpad = K.kpad
+            D.coef = K.coef.data_ptr()
+            D.resid = d_resid.data_ptr()
+            D.info = d_info.data_ptr()
+            _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')
+            self._count('launches')
+            info_h = d_info.cpu().numpy()
+            res_h = d_resid.cpu().numpy()[pos_ones]
+            ok = info_h == 0
+            resid_out[ids[ok]] = res_h[ok]
+            done[ids[ok]] = True
+        return done
+
+    def _krige_flagged(self, ctx, out, K, flagged, singular, bad_cells, problem_steps):
         """Systems whose computed weights may not sum to one (always for SK,
         quirk Q6): evaluate sum(lambda) per cell exactly like steps.py:418 and
         overwrite failing cells with the nearest available station."""
@@ -586,46 +770,31 @@ class ChunkEngine:
             cb = np.zeros(n_cells, dtype=np.uint8)
             cb[bad_cells] = 1
             d_cell_bad = self._dev(cb)
-        batch_starts = sorted(keep)
         for c0 in range(0, fl.size, max_slots):
             fb = fl[c0:c0 + max_slots]
             n_f = fb.size
             fail = torch.ones((n_f, n_cells), dtype=torch.uint8, device=self.device)
             aux = torch.empty((n_f, n_cells), dtype=_F64, device=self.device)
-            # ones-vector solutions of the non-singular flagged systems, by variogram
             ok = fb[~singular[fb]]
-            for v in np.unique(sys_vg[ok]):
-                sv = ok[sys_vg[ok] == v]
-                coef_a = torch.zeros(_pad_up(sv.size, _lib.SPX_BM) * kpad, dtype=_F64,
+            for v in np.unique(K.sys_vg[ok]):
+                sv = ok[K.sys_vg[ok] == v]
+                coef_a = torch.zeros(_pad_up(sv.size, _lib.SPX_BM) * K.kpad, dtype=_F64,
                                      device=self.device)
-                slots = np.searchsorted(fb, sv).astype(np.int32)
-                for bstart in batch_starts:
-                    S = keep[bstart][0]
-                    in_b = sv[(sv >= bstart) & (sv < bstart + S.n_sys)]
-                    if not in_b.size:
-                        continue
-                    rows = np.searchsorted(sv, in_b).astype(np.int64)
-                    t_rs = self._dev((in_b - bstart).astype(np.int32))
-                    t_rk = self._dev(np.ones(in_b.size, dtype=np.int32))
-                    t_ra = self._dev(np.zeros(in_b.size, dtype=np.int32))
-                    t_rr = self._dev(rows)
-                    R = _lib.spx_rhs()
-                    R.n_rhs = int(in_b.size)
-                    R.rhs_sys, R.rhs_kind = t_rs.data_ptr(), t_rk.data_ptr()
-                    R.rhs_arg, R.rhs_row = t_ra.data_ptr(), t_rr.data_ptr()
-                    R.data = ctx['d_data'].data_ptr()
-                    R.n_stn = ctx['n_stn']
-                    R.kpad = kpad
-                    R.coef = coef_a.data_ptr()
-                    R.resid = None
-                    _lib.check(lib.spx_krige_solve_dev(C.byref(S), C.byref(R), self._stream()),
-                               'solve(ones)')
-                    self._count('launches')
-                d_slots = self._dev(slots)
-                self._gemm(ctx, coef=coef_a, n_rows=int(sv.size), kpad=kpad, n_border=n_border,
-                           gen=_lib.GEN_VG, epi=_lib.EPI_AUX, row_dst=d_slots, aux=aux,
-                           vg=_lib.make_vg(uniq_vgs[int(v)]), covar_flag=int(kind == 1),
-                           cell_drift=d_cell_drift)
+                # ones-vector solutions, grouped by the kept factor batch
+                by_T = {}
+                for row, s in enumerate(sv):
+                    T, k = K.keep[int(s)]
+                    by_T.setdefault(id(T), (T, [], []))
+                    by_T[id(T)][1].append(k)
+                    by_T[id(T)][2].append(row)
+                for T, ks, rows in by_T.values():
+                    self._lu_solve(ctx, K, T, ks, np.ones(len(ks)), np.zeros(len(ks)), rows,
+                                   coef_a)
+                d_slots = self._dev(np.searchsorted(fb, sv).astype(np.int32))
+                self._gemm(ctx, coef=coef_a, n_rows=int(sv.size), kpad=K.kpad,
+                           n_border=K.n_border, gen=_lib.GEN_VG, epi=_lib.EPI_AUX,
+                           row_dst=d_slots, aux=aux, vg=_lib.make_vg(K.uniq_vgs[int(v)]),
+                           covar_flag=int(K.kind == 1), cell_drift=K.d_cell_drift)
             if ok.size:
                 ok_slots = torch.from_numpy(np.searchsorted(fb, ok)).to(self.device)
                 aux_ok = aux[ok_slots]
@@ -635,20 +804,19 @@ class ChunkEngine:
                     self._ptr(fail_ok), self._stream()), 'lambda_check')
                 self._count('launches')
                 fail[ok_slots] = fail_ok
-            # rows of the flagged systems
             slot_of_sys = np.full(flagged.size, -1, dtype=np.int64)
             slot_of_sys[fb] = np.arange(n_f)
-            rsel = np.where(slot_of_sys[sys_o] >= 0)[0]
+            rsel = np.where(slot_of_sys[K.sys_o] >= 0)[0]
             if not rsel.size:
                 continue
-            r_steps = steps_o[rsel]
-            gl = np.unique(sys_grp[fb])
+            r_steps = K.steps_o[rsel]
+            gl = np.unique(K.sys_grp[fb])
             gslot = {int(g): i for i, g in enumerate(gl)}
             nnb = self._nnb_index(ctx, gl)
             self._nnb_gather(ctx, out, nnb, r_steps,
                              [gslot[int(ctx['grp_of_step'][s])] for s in r_steps],
-                             fail=fail, row_fail=slot_of_sys[sys_o[rsel]])
+                             fail=fail, row_fail=slot_of_sys[K.sys_o[rsel]])
             for s in fb[singular[fb]]:
-                for t in steps_o[sys_o == s]:
+                for t in K.steps_o[K.sys_o == s]:
                     if int(t) not in problem_steps:
                         problem_steps.append(int(t))

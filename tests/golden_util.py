@@ -43,7 +43,7 @@ def load_case(name):
     return case, outs
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-3):
     """max |a-b| / max(|b|, floor) with NaN positions required to coincide."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -53,4 +53,4 @@ def rel_err(a, b):
     if not (~nb).any():
         return 0.0
     d = np.abs(a[~nb] - b[~nb])
-    return float((d / np.maximum(np.abs(b[~nb]), 1e-3)).max())
+    return float((d / np.maximum(np.abs(b[~nb]), floor)).max())

@@ -30,9 +30,16 @@ def _tol(label):
     return KRG_TOL
 
 
+def _floor(ref):
+    """Relative errors are taken against max(|ref|, 1 % of the field's largest
+    value): estimates are weighted sums of data of that magnitude, so cells whose
+    value cancels to ~0 carry the same ABSOLUTE rounding error as the others."""
+    return max(1e-3, 0.01 * float(np.nanmax(np.abs(ref)))) if np.isfinite(ref).any() else 1e-3
+
+
 def _check(got, exp, name):
     for lab, ref in exp.items():
-        e = rel_err(got[lab], ref)
+        e = rel_err(got[lab], ref, _floor(ref))
         assert e <= _tol(lab), (name, lab, e)
 
 
