@@ -329,6 +329,12 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
 int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
                          const uint8_t* cell_bad, uint8_t* fail, void* stream);
 
+/* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
+ * instead of a DMA engine, so that the copy cannot queue behind a large field
+ * download in flight; n_bytes and both pointers multiples of 4. */
+int spx_copy_to_mapped_host_dev(void* dst_host_mapped, const void* src_dev, int64_t n_bytes,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

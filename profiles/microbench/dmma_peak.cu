@@ -81,8 +81,8 @@ template<typename F> float timeit(F f){
 int main(){
   double* out; cudaMalloc(&out, 148*8*1024*sizeof(double));
   int iters=20000;
-  for(int wpb : {4,8,16,32}){
-    int threads=wpb*32; int blocks=148*(wpb<=16?2:1);
+  for(int wpb : {2,4,8,16}){
+    int threads=wpb*32; int blocks=148*(wpb<=4?1:2);
     double nw=(double)blocks*wpb;
     float ms;
     ms=timeit([&]{k884<16><<<blocks,threads>>>(out,iters,1.0000001,0.999999);});

@@ -133,6 +133,7 @@ _SIGS = {
     'spx_fill_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_double, C.c_double, C.c_void_p]),
+    'spx_copy_to_mapped_host_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
 }

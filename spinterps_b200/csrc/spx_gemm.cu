@@ -18,15 +18,57 @@
 //
 // Replaces interp/steps.py:403-435 (kriging estimate) and :293-313 (IDW)
 // together with the dst<->station fills of :639-650 (pyx:123-226).
+#include <cstdlib>
+
 #include "spx_common.cuh"
 
 namespace spx {
 
-constexpr int CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+// consumer warps per block: 8 (32 rows each) or 16 (16 rows each)
 constexpr int BK = 8;                          // k per pipeline stage
 constexpr int STAGE_DOUBLES = SPX_BM * BK;     // 2048 doubles = 16 KB
 constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+
+// Per-term constants precomputed on the host so that the B-tile generator needs
+// no FP64 division: Sph s*(h*ca - h^3*cb), Exp/Gau s*(1 - exp(ca * h or h^2)),
+// Lin s*h*ca.  Same functions as cyth/interpmthds.pyx:46-70, operations
+// re-associated (differences ~1 ulp, far inside the 1e-9 estimate tolerance; the
+// drop-in spx_fill_vg_var_arr keeps the reference's exact expression order).
+struct VgFast {
+    int n_terms;
+    int all_fast;  // every term is one of Nug / Sph / Exp / Lin / Gau
+    int types[SPX_VG_MAX_TERMS];
+    double sills[SPX_VG_MAX_TERMS];
+    double ranges[SPX_VG_MAX_TERMS];
+    double ca[SPX_VG_MAX_TERMS];
+    double cb[SPX_VG_MAX_TERMS];
+};
+
+__device__ __forceinline__ double vg_eval_fast(const VgFast& v, double h, int covar_flag,
+                                               double min_vg_val) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < v.n_terms; ++t) {
+        const int ty = v.types[t];
+        const double s = v.sills[t];
+        double g;
+        if (ty == SPX_VG_NUG) {
+            g = s;
+        } else if (ty == SPX_VG_SPH) {
+            const double h2 = h * h;
+            g = (h >= v.ranges[t]) ? s : s * (h * v.ca[t] - h2 * h * v.cb[t]);
+        } else if (ty == SPX_VG_EXP) {
+            g = s * (1.0 - exp(v.ca[t] * h));
+        } else if (ty == SPX_VG_GAU) {
+            g = s * (1.0 - exp(v.ca[t] * (h * h)));
+        } else {  // SPX_VG_LIN
+            g = (h > v.ranges[t]) ? s : s * (h * v.ca[t]);
+        }
+        acc += covar_flag ? (s - g) : g;
+    }
+    if (acc <= min_vg_val) acc = 0.0;
+    return acc;
+}
 
 struct GemmArgs {
     const double* coef;
@@ -40,6 +82,7 @@ struct GemmArgs {
     const double* cell_drift;
     int gen, covar_flag;
     VgDev vg;
+    VgFast vgf;
     double min_vg_val, idw_exp, inv_scale;
     int epi;
     const int32_t* row_dst;
@@ -109,10 +152,14 @@ __device__ __forceinline__ double idw_weight(double d2, double inv_scale, double
     return 1.0 / pow(q, p);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArgs a) {
+template <int NT, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int BN = NT * 8;
+    constexpr int CONSUMER_WARPS = CW;
+    constexpr int GEMM_THREADS = (CW + 1) * 32;
+    constexpr int RW = SPX_BM / CW;   // rows per warp
+    constexpr int MI = RW / 8;        // 8-row MMA tiles per warp
     const int KC = a.kpad >> 2;
     const int n_ksteps = a.kpad / BK;
     const int n_stages = a.n_stages;
@@ -146,7 +193,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArg
 
     const int64_t n_ctiles = (a.n_cells + BN - 1) / BN;
     const int64_t n_mtiles = (a.n_rows + SPX_BM - 1) / SPX_BM;
-    uint32_t it = 0;  // global stage counter (same sequence in producer and consumers)
+    int stage = 0;        // ring position at the start of the current tile (identical in
+    uint32_t phase = 0;   // the producer and in every consumer)
 
     for (int64_t ct = blockIdx.x; ct < n_ctiles; ct += gridDim.x) {
         const int64_t cell0 = ct * BN;
@@ -171,8 +219,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArg
             if (c < a.n_cells) {
                 if (k < a.n_stn) {
                     if (a.gen == SPX_GEN_VG) {
-                        const double h = dist_rn(cx[n], cy[n], sx[k], sy[k]);
-                        v = vg_eval(a.vg, h, a.covar_flag, a.min_vg_val);
+                        const double dx = cx[n] - sx[k], dy = cy[n] - sy[k];
+                        const double h = sqrt(dx * dx + dy * dy);
+                        v = a.vgf.all_fast ? vg_eval_fast(a.vgf, h, a.covar_flag, a.min_vg_val)
+                                           : vg_eval(a.vg, h, a.covar_flag, a.min_vg_val);
                     } else {
                         const double dx = cx[n] - sx[k], dy = cy[n] - sy[k];
                         v = idw_weight(dx * dx + dy * dy, a.inv_scale, a.idw_exp);
@@ -189,16 +239,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArg
         if (warp == CONSUMER_WARPS) {
             // ---- producer: stream coefficient stages ----------------------
             if (lane == 0) {
-                uint32_t pit = it;
+                int s = stage;
+                uint32_t ph = phase;
                 for (int64_t mt = 0; mt < n_mtiles; ++mt) {
                     const double* src = a.coef + (size_t)mt * KC * (SPX_BM * 4);
-                    for (int ks = 0; ks < n_ksteps; ++ks, ++pit) {
-                        const int s = pit % n_stages;
-                        const uint32_t ph = (pit / n_stages) & 1;
+                    for (int ks = 0; ks < n_ksteps; ++ks) {
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                         bulk_g2s(As + (size_t)s * STAGE_DOUBLES, src + (size_t)ks * STAGE_DOUBLES,
                                  STAGE_BYTES, &full_bar[s]);
+                        if (++s == n_stages) { s = 0; ph ^= 1; }
                     }
                 }
             }
@@ -206,33 +256,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArg
         } else {
             // ---- consumers: DMMA sweep over all rows ---------------------
             const int g = lane >> 2, t4 = lane & 3;
-            uint32_t cit = it;
+            int s = stage;
+            uint32_t ph = phase;
             for (int64_t mt = 0; mt < n_mtiles; ++mt) {
-                const int64_t row_base = mt * SPX_BM + warp * 32;
+                const int64_t row_base = mt * SPX_BM + warp * RW;
                 const bool active = row_base < a.n_rows;
-                double acc[4][NT][2];
+                // destination rows of this lane's 4 accumulator rows, fetched before the
+                // k loop so that the latency is hidden
+                int dst_r[MI], aux_r[MI];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < MI; ++i) {
+                    const int64_t R = row_base + i * 8 + g;
+                    dst_r[i] = (R < a.n_rows) ? a.row_dst[R] : -1;
+                    aux_r[i] = (a.epi == SPX_EPI_FIELD_DIV && R < a.n_rows) ? a.row_aux[R] : 0;
+                }
+                double acc[MI][NT][2];
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-                for (int ks = 0; ks < n_ksteps; ++ks, ++cit) {
-                    const int s = cit % n_stages;
-                    const uint32_t ph = (cit / n_stages) & 1;
+                for (int ks = 0; ks < n_ksteps; ++ks) {
                     mbar_wait(&full_bar[s], ph);
                     if (active) {
                         const double* Ast = As + (size_t)s * STAGE_DOUBLES;
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
-                            double af[4], bf[NT];
+                            double af[MI], bf[NT];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                af[i] = Ast[(kk * 32 + warp * 4 + i) * 32 + lane];
+                            for (int i = 0; i < MI; ++i)
+                                af[i] = Ast[(kk * 32 + warp * MI + i) * 32 + lane];
                             const double* Bk = Bs + (size_t)(ks * 2 + kk) * NT * 32;
 #pragma unroll
                             for (int j = 0; j < NT; ++j) bf[j] = Bk[j * 32 + lane];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
+                            for (int i = 0; i < MI; ++i)
 #pragma unroll
                                 for (int j = 0; j < NT; ++j)
                                     dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
@@ -240,38 +298,66 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_estimate_gemm(const GemmArg
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    if (++s == n_stages) { s = 0; ph ^= 1; }
                 }
                 if (!active) continue;
                 // ---- epilogue -------------------------------------------
+                const bool pair_ok = (a.cell_pos == nullptr) && ((a.out_ld & 1) == 0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t R = row_base + i * 8 + g;
-                    if (R >= a.n_rows) continue;
-                    const int dst = a.row_dst[R];
+                for (int i = 0; i < MI; ++i) {
+                    const int dst = dst_r[i];
                     if (dst < 0) continue;
-                    const int64_t aux_row =
-                        (a.epi == SPX_EPI_FIELD_DIV) ? (int64_t)a.row_aux[R] * a.n_cells : 0;
+                    const int64_t aux_row = (int64_t)aux_r[i] * a.n_cells;
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int64_t c = cell0 + j * 8 + t4 * 2 + e;
-                            if (c >= a.n_cells) continue;
-                            double v = acc[i][j][e];
-                            if (a.epi == SPX_EPI_AUX) {
-                                a.aux[(int64_t)dst * a.n_cells + c] = v;
+                        const int64_t c = cell0 + j * 8 + t4 * 2;   // even
+                        if (c >= a.n_cells) continue;
+                        const bool has2 = (c + 1 < a.n_cells);
+                        double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                        if (a.epi == SPX_EPI_AUX) {
+                            double* dstp = a.aux + (int64_t)dst * a.n_cells + c;
+                            if (has2 && ((a.n_cells & 1) == 0)) {
+                                *reinterpret_cast<double2*>(dstp) = make_double2(v0, v1);
                             } else {
-                                if (a.epi == SPX_EPI_FIELD_DIV) v = v / a.aux[aux_row + c];
-                                v = clampd(v, a.has_lo, a.has_hi, a.lo, a.hi);
-                                const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
-                                store_out(a.out, (int64_t)dst * a.out_ld + col, v, a.out_f64);
+                                dstp[0] = v0;
+                                if (has2) dstp[1] = v1;
+                            }
+                            continue;
+                        }
+                        if (a.epi == SPX_EPI_FIELD_DIV) {
+                            v0 = v0 / a.aux[aux_row + c];
+                            if (has2) v1 = v1 / a.aux[aux_row + c + 1];
+                        }
+                        v0 = clampd(v0, a.has_lo, a.has_hi, a.lo, a.hi);
+                        v1 = clampd(v1, a.has_lo, a.has_hi, a.lo, a.hi);
+                        if (pair_ok && has2) {
+                            const int64_t o = (int64_t)dst * a.out_ld + c;
+                            if (a.out_f64)
+                                *reinterpret_cast<double2*>(reinterpret_cast<double*>(a.out) + o) =
+                                    make_double2(v0, v1);
+                            else
+                                *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + o) =
+                                    make_float2((float)v0, (float)v1);
+                        } else {
+                            const int64_t col0 = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+                            store_out(a.out, (int64_t)dst * a.out_ld + col0, v0, a.out_f64);
+                            if (has2) {
+                                const int64_t col1 = a.cell_pos ? (int64_t)a.cell_pos[c + 1] : c + 1;
+                                store_out(a.out, (int64_t)dst * a.out_ld + col1, v1, a.out_f64);
                             }
                         }
                     }
                 }
             }
         }
-        it += (uint32_t)(n_mtiles * n_ksteps);
+        // advance the ring position by the stages this tile consumed
+        {
+            const uint32_t adv = (uint32_t)((n_mtiles * n_ksteps) % (2 * n_stages));
+            uint32_t pos = (uint32_t)stage + (phase ? n_stages : 0) + adv;
+            pos %= (uint32_t)(2 * n_stages);
+            phase = pos >= (uint32_t)n_stages;
+            stage = (int)(pos - (phase ? n_stages : 0));
+        }
     }
 }
 
@@ -315,11 +401,19 @@ static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
     return SPX_ENOMEM;
 }
 
+static int g_consumer_warps = 16;  // SPX_GEMM_WARPS=8|16 overrides (tuning knob)
+
 template <int NT>
 static int launch(const GemmArgs& a, const GemmCfg& cfg, cudaStream_t st) {
-    SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)cfg.smem));
-    k_estimate_gemm<NT><<<cfg.grid, GEMM_THREADS, cfg.smem, st>>>(a);
+    if (g_consumer_warps == 8) {
+        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 8>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        k_estimate_gemm<NT, 8><<<cfg.grid, 9 * 32, cfg.smem, st>>>(a);
+    } else {
+        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        k_estimate_gemm<NT, 16><<<cfg.grid, 17 * 32, cfg.smem, st>>>(a);
+    }
     SPX_CHECK_LAUNCH("k_estimate_gemm");
     return SPX_OK;
 }
@@ -378,6 +472,7 @@ int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
     if (g->n_rows == 0 || g->n_cells == 0) return SPX_OK;
     GemmCfg cfg;
     if ((rc = pick_config(g, &cfg))) return rc;
+    if (const char* e = getenv("SPX_GEMM_WARPS")) g_consumer_warps = (atoi(e) == 8) ? 8 : 16;
 
     GemmArgs a;
     a.coef = g->coef;
@@ -394,6 +489,25 @@ int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
     a.gen = g->gen;
     a.covar_flag = g->covar_flag;
     a.vg = to_dev(g->vg);
+    a.vgf.n_terms = g->vg.n_terms;
+    a.vgf.all_fast = 1;
+    for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
+        const int ty = (t < g->vg.n_terms) ? g->vg.types[t] : SPX_VG_NUG;
+        const double r = g->vg.ranges[t], sl = g->vg.sills[t];
+        a.vgf.types[t] = ty;
+        a.vgf.sills[t] = sl;
+        a.vgf.ranges[t] = r;
+        a.vgf.ca[t] = a.vgf.cb[t] = 0.0;
+        if (t >= g->vg.n_terms) continue;
+        switch (ty) {
+            case SPX_VG_NUG: break;
+            case SPX_VG_SPH: a.vgf.ca[t] = 1.5 / r; a.vgf.cb[t] = 1.0 / (2 * (r * r * r)); break;
+            case SPX_VG_EXP: a.vgf.ca[t] = -3.0 / r; break;
+            case SPX_VG_GAU: a.vgf.ca[t] = -3.0 / (r * r); break;
+            case SPX_VG_LIN: a.vgf.ca[t] = 1.0 / r; break;
+            default: a.vgf.all_fast = 0;
+        }
+    }
     a.min_vg_val = g->min_vg_val;
     a.idw_exp = g->idw_exp;
     a.inv_scale = (g->gen == SPX_GEN_IDW) ? 1.0 / g->dist_scale : 1.0;

@@ -127,6 +127,16 @@ __global__ void __launch_bounds__(256) k_lambda_check(const double* __restrict__
     }
 }
 
+// Small device -> (mapped, pinned) host copy done by SMs instead of a DMA engine:
+// a cudaMemcpyAsync D2H would queue behind any large field download in flight on
+// the copy engine and stall the compute stream for its whole duration.
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                             int64_t n_words) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride)
+        dst[i] = src[i];
+}
+
 static inline unsigned grid_y(int64_t n) { return (unsigned)(n < 1 ? 1 : (n > 65535 ? 65535 : n)); }
 
 }  // namespace spx
@@ -195,6 +205,23 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
                                                         out, out_ld, out_f64, has_lo, has_hi, lo,
                                                         hi);
     SPX_CHECK_LAUNCH("k_fill_rows");
+    return SPX_OK;
+}
+
+int spx_copy_to_mapped_host_dev(void* dst_host_mapped, const void* src_dev, int64_t n_bytes,
+                                void* stream) {
+    if (n_bytes == 0) return SPX_OK;
+    if (n_bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(dst_host_mapped) & 3) ||
+        (reinterpret_cast<uintptr_t>(src_dev) & 3)) {
+        set_error("copy_to_mapped_host: size and pointers must be multiples of 4 bytes");
+        return SPX_EINVAL;
+    }
+    const int64_t n_words = n_bytes / 4;
+    const int blocks = (int)((n_words + 255) / 256 < 64 ? (n_words + 255) / 256 : 64);
+    k_copy_words<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint32_t*>(dst_host_mapped), reinterpret_cast<const uint32_t*>(src_dev),
+        n_words);
+    SPX_CHECK_LAUNCH("k_copy_words");
     return SPX_OK;
 }
 

@@ -56,6 +56,40 @@ def availability_groups(avail):
     return grp_of_step, grp_mask
 
 
+class PendingChunk:
+    """A chunk whose kernels are queued on the stream.  ``result()`` runs the
+    deferred health checks (reading back a few flags copied to pinned memory
+    before the contraction was queued), applies the rare fix-ups and returns the
+    fields.  Submitting chunk i+1 before asking for the result of chunk i hides
+    the host-side preparation behind the GPU work of the previous chunk."""
+
+    def __init__(self, engine, flds, problem_steps, deferred, stats):
+        self.engine = engine
+        self.flds = flds
+        self.problem_steps = problem_steps
+        self.deferred = deferred
+        self.stats = stats
+        self.done_event = torch.cuda.Event()
+        self.done_event.record(torch.cuda.current_stream(engine.device))
+
+    def result(self, to_host=True):
+        eng = self.engine
+        with torch.cuda.device(eng.device):
+            n0 = eng.total_launches
+            for fn in self.deferred:
+                fn()
+            self.deferred = []
+            if eng.total_launches != n0:
+                # fix-up kernels were queued: the fields are final only after them
+                self.done_event = torch.cuda.Event()
+                self.done_event.record(torch.cuda.current_stream(eng.device))
+            if not to_host:
+                return self.flds, self.problem_steps
+            torch.cuda.current_stream(eng.device).synchronize()
+            return ({lab: t.cpu().numpy() for lab, t in self.flds.items()},
+                    self.problem_steps)
+
+
 class ChunkEngine:
     """Holds the device and tunables; ``interp_chunk`` is re-entrant."""
 
@@ -80,23 +114,59 @@ class ChunkEngine:
         self.gemm_events = []
         self.sync_timing = False
         self.timing = {}
+        self.total_launches = 0
+        self.h2d_stream = torch.cuda.Stream(self.device)
+        self._h2d_dirty = False
 
     # ------------------------------------------------------------ helpers
     def _dev(self, arr, dtype=None):
+        """Host -> device copy on a dedicated upload stream.  A pageable-memory
+        cudaMemcpyAsync first synchronises its stream, so issuing it on the compute
+        stream would stall the host behind every queued kernel; the compute stream
+        instead waits for the upload stream right before the next launch."""
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if dtype is not None:
             t = t.to(dtype)
-        return t.to(self.device, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.h2d_stream):
+            d = t.to(self.device, non_blocking=True)
+        d.record_stream(main)
+        self._h2d_dirty = True
+        return d
+
+    def _sync_uploads(self):
+        """Make the compute stream wait for every upload issued so far."""
+        if self._h2d_dirty:
+            torch.cuda.current_stream(self.device).wait_stream(self.h2d_stream)
+            self._h2d_dirty = False
 
     @staticmethod
     def _ptr(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
     def _stream(self):
+        self._sync_uploads()
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _fetch_async(self, t):
+        """Queue a device->pinned-host copy of a small tensor; the caller reads
+        the returned host tensor after synchronising a later event."""
+        t = t.contiguous()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        nbytes = t.numel() * t.element_size()
+        if nbytes:
+            # SM copy into UVA-mapped pinned memory (not the DMA engine, which may be
+            # busy for ~100 ms with a field download of the previous chunk)
+            _lib.check(self.lib.spx_copy_to_mapped_host_dev(
+                C.c_void_p(h.data_ptr()), C.c_void_p(t.data_ptr()), nbytes, self._stream()),
+                'copy_to_mapped_host')
+            self._count('launches')
+        return h
 
     def _count(self, key, n=1):
         self.stats[key] = self.stats.get(key, 0) + n
+        if key == 'launches':
+            self.total_launches += n
 
     @contextlib.contextmanager
     def _phase(self, name):
@@ -122,20 +192,37 @@ class ChunkEngine:
         """Same contract as the reference's ``_get_all_interp_outputs`` reduced
         to arrays (see oracle/spinterp_oracle.py:interp_chunk for the argument
         meaning).  Returns ({label: ndarray[T, rows*cols]}, problem_steps)."""
+        pend = self.submit_chunk(
+            data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs=vgs,
+            cntn_idxs=cntn_idxs, drft_arrs=drft_arrs, stns_drft=stns_drft,
+            fld_beg_row=fld_beg_row, fld_end_row=fld_end_row, neb_sel_mthd=neb_sel_mthd,
+            n_nebs=n_nebs, min_var_thr=min_var_thr, min_var_cut=min_var_cut,
+            max_var_cut=max_var_cut, min_vg_val=min_vg_val, est_var_flag=est_var_flag,
+            intrp_dtype=intrp_dtype)
+        return pend.result(to_host=not return_device)
+
+    def submit_chunk(
+            self, data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args,
+            vgs=None, cntn_idxs=None, drft_arrs=None, stns_drft=None,
+            fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
+            min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
+            min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32):
+        """Queue every kernel of the chunk and return a PendingChunk."""
         with torch.cuda.device(self.device):
             return self._interp_chunk(
                 data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
                 cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
                 n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
-                intrp_dtype, return_device)
+                intrp_dtype)
 
     # ------------------------------------------------------------ impl
     def _interp_chunk(
             self, data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
             cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
             n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
-            intrp_dtype, return_device):
+            intrp_dtype):
         self.stats = {}
+        deferred = []
         self.timing = {}
         data = np.ascontiguousarray(data, dtype=np.float64)
         stn_xs = np.ascontiguousarray(stn_xs, dtype=np.float64)
@@ -254,16 +341,15 @@ class ChunkEngine:
                 mean_steps = np.where(multi & bypass)[0]
                 if mean_steps.size:
                     self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
-                self._krige(ctx, out, itype, np.where(multi & ~bypass)[0], step_vg, uniq_vgs,
-                            drft_arrs if itype == 'EDK' else None,
-                            stns_drft if itype == 'EDK' else None, problem_steps)
+                fn = self._krige(ctx, out, itype, np.where(multi & ~bypass)[0], step_vg,
+                                 uniq_vgs, drft_arrs if itype == 'EDK' else None,
+                                 stns_drft if itype == 'EDK' else None, problem_steps)
+                if fn is not None:
+                    deferred.append(fn)
             else:
                 raise NotImplementedError(itype)
 
-        if return_device:
-            return flds, problem_steps
-        torch.cuda.current_stream(self.device).synchronize()
-        return {lab: t.cpu().numpy() for lab, t in flds.items()}, problem_steps
+        return PendingChunk(self, flds, problem_steps, deferred, dict(self.stats))
 
     # ------------------------------------------------------------ pieces
     def _fill_rows(self, ctx, out, steps, vals):
@@ -322,10 +408,11 @@ class ChunkEngine:
         batch = max(1, int(self.aux_limit // max(per_grp, 1)))
         for b0 in range(0, grps.size, batch):
             gb = grps[b0:b0 + batch]
-            slot = {int(g): k for k, g in enumerate(gb)}
-            st = steps[np.isin(grp_of_step[steps], gb)]
+            slot_of = np.full(ctx['grp_mask'].shape[0], -1, dtype=np.int32)
+            slot_of[gb] = np.arange(gb.size, dtype=np.int32)
+            st = steps[slot_of[grp_of_step[steps]] >= 0]
             nnb = self._nnb_index(ctx, gb)
-            self._nnb_gather(ctx, out, nnb, st, [slot[int(grp_of_step[s])] for s in st])
+            self._nnb_gather(ctx, out, nnb, st, slot_of[grp_of_step[st]])
 
     def _gemm(self, ctx, *, coef, n_rows, kpad, n_border, gen, epi, row_dst, row_aux=None,
               out=None, aux=None, vg=None, covar_flag=0, idw_exp=0.0, dist_scale=1.0,
@@ -418,7 +505,7 @@ class ChunkEngine:
 
     # ---- kriging --------------------------------------------------------
     def _krige(self, ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs, stns_drft,
-               problem_steps):
+               problem_steps, force_direct=False):
         """OK / SK / EDK in dual form:
         Z[t, i] = rhs_i . A_g^-1 [z_t; 0]."""
         if not steps.size:
@@ -500,29 +587,28 @@ class ChunkEngine:
         K.rhs_bound = rhs_bound
 
         # ---- solve: downdated where it pays, direct LU otherwise ----------
+        # Everything below is only QUEUED on the stream; residuals / info flags are
+        # read back after the contraction has been launched so that the host never
+        # idles the GPU (the rare unhealthy cases are then redone).
         resid = np.full(n_sys, np.inf)
         singular = np.zeros(n_sys, dtype=bool)
         vg_cnt = np.bincount(K.sys_vg, minlength=len(uniq_vgs))
         r_sys = n_stn - K.sys_n
         use_dd = np.zeros(n_sys, dtype=bool)
-        if self.downdate and kind != 1:
+        if self.downdate and kind != 1 and not force_direct:
             max_r = self.lib.spx_krige_downdate_max_r()
             use_dd = (vg_cnt[K.sys_vg] >= self.downdate_min_systems) & (r_sys <= max_r)
+        pending = []
         if use_dd.any():
             with self._phase('solve_downdate'):
-                done = self._solve_downdate(ctx, K, np.where(use_dd)[0], resid, singular)
-            use_dd &= done
+                pending += self._solve_downdate(ctx, K, np.where(use_dd)[0])
         direct = np.where(~use_dd)[0]
         if direct.size:
             with self._phase('solve_direct'):
-                self._solve_direct(ctx, K, direct, resid, singular, want_resid=(kind != 1))
-        with np.errstate(invalid='ignore'):
-            dev = resid * rhs_bound[K.sys_vg]
-        flagged = (kind == 1) | singular | ~(dev <= self.lambda_tol)
+                pending += self._solve_direct(ctx, K, direct, want_resid=(kind != 1))
 
-        self.stats['n_systems'] = self.stats.get('n_systems', 0) + n_sys
-        self.stats['n_downdated'] = self.stats.get('n_downdated', 0) + int(use_dd.sum())
-        self.stats['n_flagged'] = self.stats.get('n_flagged', 0) + int(flagged.sum())
+        K.flags_event = torch.cuda.Event()
+        K.flags_event.record(torch.cuda.current_stream(self.device))
 
         # ---- main contraction: one launch per variogram segment ----------
         for k in range(seg_vgs.size):
@@ -534,23 +620,54 @@ class ChunkEngine:
                            vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]),
                            covar_flag=int(kind == 1), cell_drift=K.d_cell_drift)
 
-        # ---- fallbacks to the nearest neighbour (steps.py:418-426) --------
+        # ---- fallbacks that need no host decision (steps.py:418-426) -------
         if bad_cells.size:
             # NaN drift at a cell -> sum(lambda) is NaN -> NNB there, every step
             gl = np.unique(grp_of_step[K.steps_o])
-            slot = {int(g): i for i, g in enumerate(gl)}
+            slot_of = np.full(n_grps, -1, dtype=np.int32)
+            slot_of[gl] = np.arange(gl.size, dtype=np.int32)
             nnb = self._nnb_index(ctx, gl, cells=bad_cells)
             pos = ctx['out_pos'][bad_cells] if ctx['out_pos'] is not None else bad_cells
-            self._nnb_gather(ctx, out, nnb, K.steps_o,
-                             [slot[int(grp_of_step[s])] for s in K.steps_o],
+            self._nnb_gather(ctx, out, nnb, K.steps_o, slot_of[grp_of_step[K.steps_o]],
                              n_cells=int(bad_cells.size), d_pos=self._dev(pos.astype(np.int32)))
 
-        if flagged.any():
-            # flagged systems need their factors: (re)do the downdated ones directly
-            redo = np.where(flagged & use_dd)[0]
-            if redo.size:
-                self._solve_direct(ctx, K, redo, resid, singular, want_resid=False)
-            self._krige_flagged(ctx, out, K, flagged, singular, bad_cells, problem_steps)
+        self.stats['n_systems'] = self.stats.get('n_systems', 0) + n_sys
+        self.stats['n_downdated'] = self.stats.get('n_downdated', 0) + int(use_dd.sum())
+        flags_event = K.flags_event
+
+        def deferred():
+            """Read the health flags (already in pinned memory), then handle the
+            rare unhealthy systems."""
+            flags_event.synchronize()
+            dd_failed = False
+            for fin in pending:
+                dd_failed |= fin(resid, singular)
+            if dd_failed:
+                # an unhealthy full system or r x r block: redo without downdating
+                self._count('downdate_redo')
+                fn = self._krige(ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs,
+                                 stns_drft, problem_steps, force_direct=True)
+                if fn is not None:
+                    fn()
+                return
+            with np.errstate(invalid='ignore'):
+                dev = resid * rhs_bound[K.sys_vg]
+            flagged = (kind == 1) | singular | ~(dev <= self.lambda_tol)
+            for sid in [k_ for k_ in K.keep if not flagged[k_]]:
+                del K.keep[sid]
+            self.stats['n_flagged'] = self.stats.get('n_flagged', 0) + int(flagged.sum())
+            if flagged.any():
+                # flagged systems need their factors: (re)do the downdated ones directly
+                redo = np.where(flagged & use_dd)[0]
+                if redo.size:
+                    fins = self._solve_direct(ctx, K, redo, want_resid=False)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    for fin in fins:
+                        fin(resid, singular)
+                self._krige_flagged(ctx, out, K, flagged, singular, bad_cells, problem_steps)
+            K.keep.clear()
+
+        return deferred
 
     # ---- direct path: assemble + LU + substitution per system --------------
     def _systems_struct(self, ctx, K, sys_ids, grp_ids, vg_ids):
@@ -616,13 +733,14 @@ class ChunkEngine:
         self._count('launches')
         return resid
 
-    def _solve_direct(self, ctx, K, sys_ids, resid_out, singular_out, want_resid=True):
+    def _solve_direct(self, ctx, K, sys_ids, want_resid=True):
         """Assemble, factor and solve the listed systems in batches bounded by the
         workspace limit; data rows go to K.coef, one ones-vector per system gives
         the sum(lambda) residual.  Workspaces are kept in K.keep for the flagged
         handler."""
         m_all = K.sys_n[sys_ids].astype(np.int64) + K.n_border
         nbytes = m_all * m_all * 8
+        finishers = []
         b0 = 0
         while b0 < sys_ids.size:
             b1 = b0 + 1
@@ -635,8 +753,7 @@ class ChunkEngine:
             nb = ids.size
             T = self._systems_struct(ctx, K, ids, K.sys_grp[ids], K.sys_vg[ids])
             self._factor(ctx, K, T)
-            ridx = np.concatenate([K.rows_by_sys[K.sys_row_beg[s]:K.sys_row_beg[s + 1]]
-                                   for s in ids])
+            ridx = K.rows_by_sys[np.isin(K.sys_o[K.rows_by_sys], ids)]   # grouped by system
             local = np.full(K.sys_n.size, -1, dtype=np.int64)
             local[ids] = np.arange(nb)
             n_data = ridx.size
@@ -651,27 +768,31 @@ class ChunkEngine:
             if rhs_sys.size:
                 resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
                                        want_resid=want_resid)
-            singular_out[ids] = T.info.cpu().numpy() != 0
-            if want_resid:
-                resid_out[ids] = resid[n_data:].cpu().numpy()
-            # keep the factors only where the flagged handler may need them
-            with np.errstate(invalid='ignore'):
-                need = (K.kind == 1) | singular_out[ids] | ~(
-                    resid_out[ids] * K.rhs_bound[K.sys_vg[ids]] <= self.lambda_tol)
-            if need.any() or not want_resid:
-                for k, s in enumerate(ids):
-                    K.keep[int(s)] = (T, k)
+            for k, sid in enumerate(ids):
+                K.keep[int(sid)] = (T, k)
+
+            h_info = self._fetch_async(T.info)
+            h_resid = self._fetch_async(resid[n_data:]) if want_resid else None
+
+            def finish(resid_out, singular_out, ids=ids, h_info=h_info, h_resid=h_resid):
+                singular_out[ids] = h_info.numpy() != 0
+                if h_resid is not None:
+                    resid_out[ids] = h_resid.numpy()
+                return False
+            finishers.append(finish)
             b0 = b1
+        return finishers
 
     # ---- downdated path -------------------------------------------------
-    def _solve_downdate(self, ctx, K, sys_ids, resid_out, singular_out):
+    def _solve_downdate(self, ctx, K, sys_ids):
         """A_g^-1 b from the inverse of the full system of each variogram
-        (include/spx_b200.h: spx_downdate).  Returns a bool mask over ALL systems
-        marking those actually handled here."""
+        (include/spx_b200.h: spx_downdate).  Only queues work; returns finisher
+        callables that later read the health flags (True = something was unhealthy
+        and the caller must redo the solve without downdating)."""
         lib = self.lib
         n_stn = ctx['n_stn']
         M = n_stn + K.n_border
-        done = np.zeros(K.sys_n.size, dtype=bool)
+        finishers = []
         vgs_here = np.unique(K.sys_vg[sys_ids])
         # full systems, one per variogram, factored together
         T = self._systems_struct(ctx, K, np.arange(vgs_here.size),
@@ -686,14 +807,18 @@ class ChunkEngine:
         dense = torch.empty((n_full * (M + 1), M), dtype=_F64, device=self.device)
         resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
                                want_resid=True, dense=dense, dense_ld=M)
-        full_info = T.info.cpu().numpy()
-        full_resid = resid.view(n_full, M + 1)[:, M].cpu().numpy()
+        h_full_info = self._fetch_async(T.info)
+        h_full_resid = self._fetch_async(resid.view(n_full, M + 1)[:, M].contiguous())
+
+        def finish_full(resid_out, singular_out):
+            bad = (h_full_info.numpy() != 0) | ~(h_full_resid.numpy() <= 1e-9)
+            return bool(bad.any())
+        finishers.append(finish_full)
         dense = dense.view(n_full, M + 1, M)
         miss_mask_all = ~ctx['grp_mask']
         for vi, v in enumerate(vgs_here):
-            healthy = (full_info[vi] == 0) and (full_resid[vi] <= 1e-9)
             ids = sys_ids[K.sys_vg[sys_ids] == v]
-            if not healthy or not ids.size:
+            if not ids.size:
                 continue
             G = dense[vi, :M, :]
             grp = K.sys_grp[ids]
@@ -701,16 +826,18 @@ class ChunkEngine:
             miss_list = np.where(miss_mask_all[grp])[1].astype(np.int32)
             miss_off = np.concatenate([[0], np.cumsum(r)])[:-1].astype(np.int64)
             # right-hand sides: data rows of every system + one ones-vector each
-            ridx = np.concatenate([K.rows_by_sys[K.sys_row_beg[s]:K.sys_row_beg[s + 1]]
-                                   for s in ids])
+            ridx = K.rows_by_sys[np.isin(K.sys_o[K.rows_by_sys], ids)]   # grouped by system
             cnt = (K.sys_row_beg[ids + 1] - K.sys_row_beg[ids]).astype(np.int64)
             n_data = ridx.size
             nsys = ids.size
             # Bt rows: [data rows in ridx order | group masks]
             d_steps = self._dev(K.steps_o[ridx].astype(np.int64))
+            self._sync_uploads()
             Bt = torch.zeros((n_data + nsys, M), dtype=_F64, device=self.device)
             Bt[:n_data, :n_stn] = ctx['d_data0'].index_select(0, d_steps)
-            Bt[n_data:, :n_stn] = self._dev(ctx['grp_mask'][grp].astype(np.float64))
+            d_maskf = self._dev(ctx['grp_mask'][grp].astype(np.float64))
+            self._sync_uploads()
+            Bt[n_data:, :n_stn] = d_maskf
             Ut = torch.matmul(Bt, G)
             self._count('launches')
             # per-system contiguous rhs lists: its data rows then its ones-vector
@@ -750,12 +877,16 @@ class ChunkEngine:
             D.info = d_info.data_ptr()
             _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')
             self._count('launches')
-            info_h = d_info.cpu().numpy()
-            res_h = d_resid.cpu().numpy()[pos_ones]
-            ok = info_h == 0
-            resid_out[ids[ok]] = res_h[ok]
-            done[ids[ok]] = True
-        return done
+
+            h_info = self._fetch_async(d_info)
+            h_resid = self._fetch_async(d_resid)
+
+            def finish(resid_out, singular_out, ids=ids, h_info=h_info, h_resid=h_resid,
+                       pos_ones=pos_ones):
+                resid_out[ids] = h_resid.numpy()[pos_ones]
+                return bool((h_info.numpy() != 0).any())
+            finishers.append(finish)
+        return finishers
 
     def _krige_flagged(self, ctx, out, K, flagged, singular, bad_cells, problem_steps):
         """Systems whose computed weights may not sum to one (always for SK,
@@ -796,7 +927,8 @@ class ChunkEngine:
                            row_dst=d_slots, aux=aux, vg=_lib.make_vg(K.uniq_vgs[int(v)]),
                            covar_flag=int(K.kind == 1), cell_drift=K.d_cell_drift)
             if ok.size:
-                ok_slots = torch.from_numpy(np.searchsorted(fb, ok)).to(self.device)
+                ok_slots = self._dev(np.searchsorted(fb, ok).astype(np.int64))
+                self._sync_uploads()
                 aux_ok = aux[ok_slots]
                 fail_ok = torch.empty((ok.size, n_cells), dtype=torch.uint8, device=self.device)
                 _lib.check(lib.spx_lambda_check_dev(
