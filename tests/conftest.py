@@ -13,3 +13,11 @@ os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _built_library():
+    """Build libspx_b200.so if it is missing or stale (nvcc cross-compiles
+    without a GPU; ~1 min the first time, cached by a source digest)."""
+    from spinterps_b200 import build
+    build.build()

@@ -1,0 +1,97 @@
+"""End to end through the reference-facing surface on the GPU: SpInterpSteps
+(operator seam, the reference's 12-tuple in / 13-tuple out) and SpInterpMain
+(setters -> verify -> interpolate -> output file + stats.csv)."""
+import types
+from threading import Lock
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import spinterp_oracle as orc
+from tests.golden_util import load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_steps_seam_matches_golden():
+    from spinterps_b200.steps import SpInterpSteps
+    case, outs = load_case('d_sk_ok_mask_rows')
+    n_stn = case['stn_xs'].size
+    labels = [f'S{i:05d}' for i in range(n_stn)]
+    T = case['data'].shape[0]
+    tidx = pd.date_range('2000-01-01', periods=T)
+    main = types.SimpleNamespace(
+        _vb=False, _n_cpus=1, _mp_flag=False,
+        _crds_df=pd.DataFrame({'X': case['stn_xs'], 'Y': case['stn_ys']}, index=labels),
+        _min_var_thr=case['min_var_thr'], _min_var_cut=case['min_var_cut'],
+        _max_var_cut=case['max_var_cut'], _cntn_idxs=case['cntn_idxs'],
+        _interp_crds_orig_shape=case['grid_shape'], _interp_x_crds_msh=case['cell_xs'],
+        _interp_y_crds_msh=case['cell_ys'], _nc_file_path=None, _nc_nmrl_prcn=2,
+        _neb_sel_mthd='all', _n_nebs=None, _n_pies=None, _min_vg_val=case['min_vg_val'],
+        _interp_flag_est_vars=False, _intrp_dtype=np.float64)
+    args = (pd.DataFrame(case['data'], index=tidx, columns=labels), 0, T, 1,
+            case['interp_args'], Lock(), None, None,
+            pd.Series(case['vgs'], index=tidx, dtype=object), pd.Series(np.arange(T), index=tidx),
+            case['fld_beg_row'], case['fld_end_row'])
+    out = SpInterpSteps(main)._get_all_interp_outputs(args)
+    assert len(out) == 13 and out[6] == [a[2] for a in case['interp_args']]
+    for lab, ref in outs.items():
+        tol = 1e-12 if lab.startswith('IDW') else 1e-9
+        assert rel_err(out[7][lab], ref, 0.2) <= tol, lab
+
+
+def test_main_end_to_end(tmp_path):
+    from spinterps_b200 import ncwriter
+    from spinterps_b200.main import SpInterpMain
+    rng = np.random.default_rng(4)
+    n_stn, T = 30, 9
+    idx = pd.date_range('2001-03-01', periods=T, freq='D')
+    labs = [f'P{i:03d}' for i in range(n_stn)]
+    vals = rng.gamma(1.0, 5.0, (T, n_stn))
+    vals[rng.random((T, n_stn)) < 0.15] = np.nan
+    data = pd.DataFrame(vals, index=idx, columns=labs)
+    crds = pd.DataFrame({'X': rng.uniform(0, 6e4, n_stn), 'Y': rng.uniform(0, 5e4, n_stn)},
+                        index=labs)
+    vg = '0.1 Nug(0.0) + 0.9 Sph(20000)'
+    vgs_ser = pd.Series([vg] * T, index=idx, dtype=object)
+
+    m = SpInterpMain(False)
+    m.set_data(data, crds)
+    m.set_vgs_ser(vgs_ser)
+    m.set_out_dir(tmp_path / 'run')
+    m.set_netcdf4_parameters('precip.nc', 'mm', 'precipitation', 'days since 1900-01-01',
+                             'gregorian', 2, 1)
+    m.set_interp_time_parameters('2001-03-01', '2001-03-09', 'D', '%Y-%m-%d')
+    m.set_neighbor_selection_method('all')
+    m.set_misc_settings(cell_size=2000.0, min_cutoff_value=0.0, max_steps_per_chunk=4)
+    m.set_cell_selection_mask(lambda x, y: (x - 3e4) ** 2 + (y - 2.5e4) ** 2 <= 2.4e4 ** 2,
+                              polygon_cell_buffer_distance=1000.0)
+    m.turn_ordinary_kriging_on()
+    m.turn_inverse_distance_weighting_on([2])
+    m.turn_nearest_neighbor_on()
+    m.verify()
+    m.interpolate()
+
+    exp, _ = orc.interp_chunk(
+        m._data_df.values, m._crds_df['X'].values, m._crds_df['Y'].values,
+        m._interp_x_crds_msh, m._interp_y_crds_msh, m._interp_crds_orig_shape, m._interp_args,
+        vgs=[vg] * T, cntn_idxs=m._cntn_idxs, min_var_cut=0.0, intrp_dtype=np.float32)
+    h = ncwriter.open_for_read(m._nc_file_path)
+    ny, nx = m._interp_crds_orig_shape
+    for lab in ('OK', 'IDW_000', 'NNB'):
+        ref = np.round(exp[lab], 2).reshape(T, ny, nx)
+        for t in range(T):
+            got = h.read(lab, t)
+            assert np.array_equal(np.isnan(got), np.isnan(ref[t]))
+            # both sides round f32 values to 2 decimals; a value on a rounding boundary
+            # may land on the neighbouring cent
+            assert np.nanmax(np.abs(got - ref[t])) <= 0.0101, (lab, t)
+            assert np.nanmean(np.abs(got - ref[t]) > 1e-6) < 1e-3
+    h.close()
+    stats = pd.read_csv(tmp_path / 'run' / 'stats.csv', sep=';', index_col=0)
+    assert stats.shape[0] == T
+    for lab in ('data', 'OK', 'IDW_000', 'NNB'):
+        for st in ('min', 'mean', 'max', 'std', 'count'):
+            assert f'{lab}_{st}' in stats.columns
+    assert np.allclose(stats['OK_count'].values, m._cntn_idxs.sum())
