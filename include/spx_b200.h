@@ -255,6 +255,10 @@ int spx_krige_downdate_max_r(void);
 #define SPX_EPI_FIELD 0      /* out[row_dst, cell_pos] = clamp(Z)              */
 #define SPX_EPI_AUX 1        /* aux[row_dst, cell] = Z  (f64)                   */
 #define SPX_EPI_FIELD_DIV 2  /* out[row_dst, cell_pos] = clamp(Z / aux[row_aux, cell]) */
+#define SPX_EPI_QUADFORM 3   /* rows = rows of ONE system's inverse, row_dst = their K index:
+                                aux[quad_slot, cell] = sum_rows Z[row, cell] * (B[K(row), cell]
+                                + [K(row) == n_stn])  = rhs' A^-1 rhs + lambda[n], the OK
+                                estimation variance of interp/steps.py:431-434 */
 
 typedef struct spx_gemm {
     const double* coef;      /* packed, segment start (row multiple of SPX_BM) */
@@ -284,6 +288,7 @@ typedef struct spx_gemm {
     double* aux;              /* [slots, n_cells] */
     int32_t has_lo, has_hi;
     double lo, hi;
+    int32_t quad_slot;        /* SPX_EPI_QUADFORM: output row of aux */
 } spx_gemm;
 
 int spx_estimate_gemm_dev(const spx_gemm* g, void* stream);
@@ -328,6 +333,15 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
  * fail) OR cell_bad[c] -- interp/steps.py:418. */
 int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
                          const uint8_t* cell_bad, uint8_t* fail, void* stream);
+
+/* out[row_dst[r], cell_pos[c]] = aux[row_slot[r], c] (0.0 if aux == NULL), restricted to
+ * fail[row_fail[r], c] != 0 when fail != NULL; no clamp.  Spreads the per-system
+ * estimation variance to the steps of the system (interp/steps.py:431-434, :821-831)
+ * and zeroes it where kriging fell back to NNB (:425-426). */
+int spx_bcast_rows_dev(const double* aux, const int32_t* row_slot, const int32_t* row_dst,
+                       int64_t n_rows, const uint8_t* fail, const int32_t* row_fail,
+                       int64_t n_cells, const int32_t* cell_pos, void* out, int64_t out_ld,
+                       int32_t out_f64, void* stream);
 
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field

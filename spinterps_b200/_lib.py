@@ -18,7 +18,7 @@ SPX_BM = 256
 VG_NAMES = ('Rng', 'Nug', 'Sph', 'Exp', 'Lin', 'Gau', 'Pow', 'Hol')
 KRG_KINDS = {'OK': 0, 'SK': 1, 'EDK': 2}
 GEN_VG, GEN_IDW = 0, 1
-EPI_FIELD, EPI_AUX, EPI_FIELD_DIV = 0, 1, 2
+EPI_FIELD, EPI_AUX, EPI_FIELD_DIV, EPI_QUADFORM = 0, 1, 2, 3
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -88,7 +88,7 @@ class spx_gemm(C.Structure):
                 ('out', C.c_void_p), ('out_ld', C.c_int64), ('out_f64', C.c_int32),
                 ('cell_pos', C.c_void_p), ('aux', C.c_void_p),
                 ('has_lo', C.c_int32), ('has_hi', C.c_int32),
-                ('lo', C.c_double), ('hi', C.c_double)]
+                ('lo', C.c_double), ('hi', C.c_double), ('quad_slot', C.c_int32)]
 
 
 _SIGS = {
@@ -133,6 +133,9 @@ _SIGS = {
     'spx_fill_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_double, C.c_double, C.c_void_p]),
+    'spx_bcast_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int32, C.c_void_p]),
     'spx_copy_to_mapped_host_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

@@ -95,6 +95,7 @@ struct GemmArgs {
     int has_lo, has_hi;
     double lo, hi;
     int n_stages;
+    int quad_slot;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -152,7 +153,7 @@ __device__ __forceinline__ double idw_weight(double d2, double inv_scale, double
     return 1.0 / pow(q, p);
 }
 
-template <int NT, int CW>
+template <int NT, int CW, bool QUAD>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int BN = NT * 8;
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
     double* sy = sx + a.kpad;                                          // [kpad] station y
     double* cx = sy + a.kpad;                                          // [BN]
     double* cy = cx + BN;                                              // [BN]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(cy + BN);         // [n_stages]
+    double* qs = cy + BN;                                              // [BN] quadratic forms
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(qs + BN);         // [n_stages]
     uint64_t* empty_bar = full_bar + n_stages;                         // [n_stages]
 
     const int tid = threadIdx.x;
@@ -201,6 +203,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
         // ---- generate the resident B tile --------------------------------
         __syncthreads();  // previous tile fully consumed
         if (tid < BN) {
+            if (QUAD) {
+                if (ct != (int64_t)blockIdx.x) {   // result of the previous tile
+                    const int64_t pc = cell0 - (int64_t)gridDim.x * BN + tid;
+                    if (pc < a.n_cells) a.aux[(int64_t)a.quad_slot * a.n_cells + pc] = qs[tid];
+                }
+                qs[tid] = 0.0;
+            }
             const int64_t c = cell0 + tid;
             cx[tid] = (c < a.n_cells) ? a.cell_x[c] : 0.0;
             cy[tid] = (c < a.n_cells) ? a.cell_y[c] : 0.0;
@@ -258,6 +267,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
             const int g = lane >> 2, t4 = lane & 3;
             int s = stage;
             uint32_t ph = phase;
+            double quad[QUAD ? NT : 1][2];
+#pragma unroll
+            for (int j = 0; j < (QUAD ? NT : 1); ++j) quad[j][0] = quad[j][1] = 0.0;
             for (int64_t mt = 0; mt < n_mtiles; ++mt) {
                 const int64_t row_base = mt * SPX_BM + warp * RW;
                 const bool active = row_base < a.n_rows;
@@ -307,6 +319,23 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                 for (int i = 0; i < MI; ++i) {
                     const int dst = dst_r[i];
                     if (dst < 0) continue;
+                    if (QUAD) {
+                        // row = one row of A^-1 (K index dst): accumulate
+                        // lambda[dst] * rhs[dst] (+ lambda[n], steps.py:431-434)
+                        const int kc = dst >> 2, kt = dst & 3;
+                        const double extra = (dst == a.n_stn) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const double* Bk = Bs + ((size_t)kc * NT + j) * 32;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int n8 = t4 * 2 + e;
+                                quad[QUAD ? j : 0][e] =
+                                    fma(acc[i][j][e], Bk[n8 * 4 + kt] + extra, quad[QUAD ? j : 0][e]);
+                            }
+                        }
+                        continue;
+                    }
                     const int64_t aux_row = (int64_t)aux_r[i] * a.n_cells;
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
@@ -349,6 +378,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                     }
                 }
             }
+            if (QUAD) {
+                // sum over this warp's rows (lanes with equal t4), then over warps
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double v = quad[QUAD ? j : 0][e];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (g == 0) atomicAdd(&qs[j * 8 + t4 * 2 + e], v);
+                    }
+            }
         }
         // advance the ring position by the stages this tile consumed
         {
@@ -359,11 +401,22 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
             stage = (int)(pos - (phase ? n_stages : 0));
         }
     }
+    if (QUAD) {
+        // result of the last tile this block processed
+        __syncthreads();
+        const int64_t n_mine = (n_ctiles > (int64_t)blockIdx.x)
+                                   ? (n_ctiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        if (n_mine > 0 && tid < BN) {
+            const int64_t last_ct = blockIdx.x + (n_mine - 1) * (int64_t)gridDim.x;
+            const int64_t pc = last_ct * BN + tid;
+            if (pc < a.n_cells) a.aux[(int64_t)a.quad_slot * a.n_cells + pc] = qs[tid];
+        }
+    }
 }
 
 static size_t gemm_smem_bytes(int kpad, int nt, int n_stages) {
     const size_t dbl = (size_t)(kpad / 4) * nt * 32 + (size_t)n_stages * STAGE_DOUBLES +
-                       2 * (size_t)kpad + 2 * (size_t)nt * 8;
+                       2 * (size_t)kpad + 3 * (size_t)nt * 8;
     return dbl * 8 + 2 * (size_t)n_stages * 8;
 }
 
@@ -405,14 +458,18 @@ static int g_consumer_warps = 16;  // SPX_GEMM_WARPS=8|16 overrides (tuning knob
 
 template <int NT>
 static int launch(const GemmArgs& a, const GemmCfg& cfg, cudaStream_t st) {
-    if (g_consumer_warps == 8) {
-        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 8>,
+    if (a.epi == SPX_EPI_QUADFORM) {
+        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 8, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        k_estimate_gemm<NT, 8><<<cfg.grid, 9 * 32, cfg.smem, st>>>(a);
+        k_estimate_gemm<NT, 8, true><<<cfg.grid, 9 * 32, cfg.smem, st>>>(a);
+    } else if (g_consumer_warps == 8) {
+        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 8, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        k_estimate_gemm<NT, 8, false><<<cfg.grid, 9 * 32, cfg.smem, st>>>(a);
     } else {
-        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 16>,
+        SPX_CUDA(cudaFuncSetAttribute(k_estimate_gemm<NT, 16, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        k_estimate_gemm<NT, 16><<<cfg.grid, 17 * 32, cfg.smem, st>>>(a);
+        k_estimate_gemm<NT, 16, false><<<cfg.grid, 17 * 32, cfg.smem, st>>>(a);
     }
     SPX_CHECK_LAUNCH("k_estimate_gemm");
     return SPX_OK;
@@ -524,6 +581,7 @@ int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
     a.lo = g->lo;
     a.hi = g->hi;
     a.n_stages = cfg.n_stages;
+    a.quad_slot = g->quad_slot;
 
     cudaStream_t st = (cudaStream_t)stream;
     switch (cfg.nt) {

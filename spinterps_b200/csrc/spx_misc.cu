@@ -110,6 +110,24 @@ __global__ void __launch_bounds__(256) k_fill_rows(const double* __restrict__ va
     }
 }
 
+// out[row_dst[r], cell_pos[c]] = aux[row_slot[r], c]  (aux == NULL: 0.0), only where
+// fail[row_fail[r], c] != 0 when a fail mask is given.  No clamp: estimation
+// variances are not passed through _mod_min_max (interp/steps.py:805-831).
+__global__ void __launch_bounds__(256) k_bcast_rows(
+    const double* __restrict__ aux, const int32_t* __restrict__ row_slot,
+    const int32_t* __restrict__ row_dst, int64_t n_rows, const uint8_t* __restrict__ fail,
+    const int32_t* __restrict__ row_fail, int64_t n_cells, const int32_t* __restrict__ cell_pos,
+    void* __restrict__ out, int64_t out_ld, int out_f64) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int64_t col = cell_pos ? (int64_t)cell_pos[c] : c;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        if (fail != nullptr && !fail[(int64_t)row_fail[r] * n_cells + c]) continue;
+        const double v = aux ? aux[(int64_t)row_slot[r] * n_cells + c] : 0.0;
+        store_out(out, (int64_t)row_dst[r] * out_ld + col, v, out_f64);
+    }
+}
+
 // np.isclose(a, 1.0): |a - 1| <= atol + rtol * |1| with rtol=1e-5, atol=1e-8;
 // NaN / inf are not close (interp/steps.py:418).
 __global__ void __launch_bounds__(256) k_lambda_check(const double* __restrict__ aux,
@@ -205,6 +223,23 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
                                                         out, out_ld, out_f64, has_lo, has_hi, lo,
                                                         hi);
     SPX_CHECK_LAUNCH("k_fill_rows");
+    return SPX_OK;
+}
+
+int spx_bcast_rows_dev(const double* aux, const int32_t* row_slot, const int32_t* row_dst,
+                       int64_t n_rows, const uint8_t* fail, const int32_t* row_fail,
+                       int64_t n_cells, const int32_t* cell_pos, void* out, int64_t out_ld,
+                       int32_t out_f64, void* stream) {
+    if (n_rows == 0 || n_cells == 0) return SPX_OK;
+    if ((aux != nullptr && row_slot == nullptr) || (fail != nullptr && row_fail == nullptr)) {
+        set_error("bcast_rows: aux without row_slot or fail without row_fail");
+        return SPX_EINVAL;
+    }
+    dim3 grid((unsigned)((n_cells + 255) / 256), grid_y(n_rows));
+    k_bcast_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(aux, row_slot, row_dst, n_rows, fail,
+                                                         row_fail, n_cells, cell_pos, out, out_ld,
+                                                         out_f64);
+    SPX_CHECK_LAUNCH("k_bcast_rows");
     return SPX_OK;
 }
 

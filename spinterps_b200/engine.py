@@ -249,8 +249,9 @@ class ChunkEngine:
             raise NotImplementedError(
                 f"neighbor selection '{neb_sel_mthd}' is not on the GPU path yet "
                 "(SURVEY.md section 8f row 2)")
-        if est_var_flag and 'OK' in interp_types:
-            raise NotImplementedError('EST_VARS_OK is not on the GPU path yet')
+        ev_flag = bool(est_var_flag) and ('OK' in interp_types)
+        if ev_flag:
+            assert 'EST_VARS_OK' in interp_labels, 'est_var_flag needs an EST_VARS_OK label'
 
         # ---- cell subsetting, steps.py:512-568 ------------------------------
         fld_n_cols = int(grid_shape[1])
@@ -341,9 +342,14 @@ class ChunkEngine:
                 mean_steps = np.where(multi & bypass)[0]
                 if mean_steps.size:
                     self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
+                ev_out = flds['EST_VARS_OK'] if (ev_flag and itype == 'OK') else None
+                if ev_out is not None and mean_steps.size:          # steps.py:329
+                    self._fill_rows(ctx, ev_out, mean_steps, np.zeros(mean_steps.size),
+                                    clamp=False)
                 fn = self._krige(ctx, out, itype, np.where(multi & ~bypass)[0], step_vg,
                                  uniq_vgs, drft_arrs if itype == 'EDK' else None,
-                                 stns_drft if itype == 'EDK' else None, problem_steps)
+                                 stns_drft if itype == 'EDK' else None, problem_steps,
+                                 ev_out=ev_out)
                 if fn is not None:
                     deferred.append(fn)
             else:
@@ -352,13 +358,13 @@ class ChunkEngine:
         return PendingChunk(self, flds, problem_steps, deferred, dict(self.stats))
 
     # ------------------------------------------------------------ pieces
-    def _fill_rows(self, ctx, out, steps, vals):
+    def _fill_rows(self, ctx, out, steps, vals, clamp=True):
         d_vals = self._dev(np.asarray(vals, dtype=np.float64))
         d_rows = self._dev(np.asarray(steps, dtype=np.int32))
         _lib.check(self.lib.spx_fill_rows_dev(
             self._ptr(d_vals), self._ptr(d_rows), len(steps), ctx['n_cells'], self._ptr(ctx['d_pos']),
-            self._ptr(out), ctx['fld_size'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'],
-            ctx['lo'], ctx['hi'], self._stream()), 'fill_rows')
+            self._ptr(out), ctx['fld_size'], ctx['out_f64'], ctx['has_lo'] if clamp else 0,
+            ctx['has_hi'] if clamp else 0, ctx['lo'], ctx['hi'], self._stream()), 'fill_rows')
         self._count('launches')
 
     def _nnb_index(self, ctx, grp_ids, cells=None):
@@ -416,7 +422,7 @@ class ChunkEngine:
 
     def _gemm(self, ctx, *, coef, n_rows, kpad, n_border, gen, epi, row_dst, row_aux=None,
               out=None, aux=None, vg=None, covar_flag=0, idw_exp=0.0, dist_scale=1.0,
-              cell_drift=None):
+              cell_drift=None, quad_slot=0):
         g = _lib.spx_gemm()
         g.coef = coef.data_ptr()
         g.n_rows = int(n_rows)
@@ -445,6 +451,7 @@ class ChunkEngine:
         g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
         g.aux = aux.data_ptr() if aux is not None else None
         g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+        g.quad_slot = int(quad_slot)
         if self.profile_gemm:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -505,7 +512,7 @@ class ChunkEngine:
 
     # ---- kriging --------------------------------------------------------
     def _krige(self, ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs, stns_drft,
-               problem_steps, force_direct=False):
+               problem_steps, force_direct=False, ev_out=None):
         """OK / SK / EDK in dual form:
         Z[t, i] = rhs_i . A_g^-1 [z_t; 0]."""
         if not steps.size:
@@ -595,7 +602,8 @@ class ChunkEngine:
         vg_cnt = np.bincount(K.sys_vg, minlength=len(uniq_vgs))
         r_sys = n_stn - K.sys_n
         use_dd = np.zeros(n_sys, dtype=bool)
-        if self.downdate and kind != 1 and not force_direct:
+        K.ev_out = ev_out
+        if self.downdate and kind != 1 and not force_direct and ev_out is None:
             max_r = self.lib.spx_krige_downdate_max_r()
             use_dd = (vg_cnt[K.sys_vg] >= self.downdate_min_systems) & (r_sys <= max_r)
         pending = []
@@ -619,6 +627,9 @@ class ChunkEngine:
                            row_dst=d_row_dst[seg_row0[k]:], out=out,
                            vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]),
                            covar_flag=int(kind == 1), cell_drift=K.d_cell_drift)
+
+        if ev_out is not None:
+            self._est_vars(ctx, K, ev_out)
 
         # ---- fallbacks that need no host decision (steps.py:418-426) -------
         if bad_cells.size:
@@ -646,7 +657,7 @@ class ChunkEngine:
                 # an unhealthy full system or r x r block: redo without downdating
                 self._count('downdate_redo')
                 fn = self._krige(ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs,
-                                 stns_drft, problem_steps, force_direct=True)
+                                 stns_drft, problem_steps, force_direct=True, ev_out=ev_out)
                 if fn is not None:
                     fn()
                 return
@@ -668,6 +679,44 @@ class ChunkEngine:
             K.keep.clear()
 
         return deferred
+
+    # ---- OK estimation variance (weights form) -----------------------------
+    def _est_vars(self, ctx, K, ev_out):
+        """est_var = rhs' A^-1 rhs + lambda[n] per (system, cell)
+        (interp/steps.py:431-434; the Lagrange term counted twice is the
+        reference's, quirk Q8), spread to the steps of the system.  The inverse's
+        rows are the coefficient rows of one more contraction whose epilogue
+        contracts with the resident right-hand-side tile (SPX_EPI_QUADFORM)."""
+        n_cells, n_stn = ctx['n_cells'], ctx['n_stn']
+        n_sys = K.sys_n.size
+        max_slots = max(1, int(self.aux_limit // (n_cells * 8)))
+        for c0 in range(0, n_sys, max_slots):
+            ids = np.arange(c0, min(n_sys, c0 + max_slots))
+            aux = torch.empty((ids.size, n_cells), dtype=_F64, device=self.device)
+            for slot, sid in enumerate(ids):
+                T, k = K.keep[int(sid)]
+                n = int(K.sys_n[sid])
+                m = n + K.n_border
+                coef_i = torch.zeros(_pad_up(m, _lib.SPX_BM) * K.kpad, dtype=_F64,
+                                     device=self.device)
+                self._lu_solve(ctx, K, T, np.full(m, k), np.full(m, 2), np.arange(m),
+                               np.arange(m), coef_i)
+                grp = int(K.sys_grp[sid])
+                kidx = np.full(_pad_up(m, _lib.SPX_BM), -1, dtype=np.int32)
+                kidx[:n] = np.where(ctx['grp_mask'][grp])[0]
+                kidx[n:m] = n_stn + np.arange(K.n_border)
+                g = self._gemm(ctx, coef=coef_i, n_rows=m, kpad=K.kpad, n_border=K.n_border,
+                               gen=_lib.GEN_VG, epi=_lib.EPI_QUADFORM, row_dst=self._dev(kidx),
+                               aux=aux, vg=_lib.make_vg(K.uniq_vgs[int(K.sys_vg[sid])]),
+                               covar_flag=0, cell_drift=K.d_cell_drift, quad_slot=slot)
+            sel = np.where((K.sys_o >= ids[0]) & (K.sys_o <= ids[-1]))[0]
+            d_slot = self._dev((K.sys_o[sel] - ids[0]).astype(np.int32))
+            d_dst = self._dev(K.steps_o[sel].astype(np.int32))
+            _lib.check(self.lib.spx_bcast_rows_dev(
+                self._ptr(aux), self._ptr(d_slot), self._ptr(d_dst), int(sel.size), None, None,
+                n_cells, self._ptr(ctx['d_pos']), self._ptr(ev_out), ctx['fld_size'],
+                ctx['out_f64'], self._stream()), 'bcast_rows')
+            self._count('launches')
 
     # ---- direct path: assemble + LU + substitution per system --------------
     def _systems_struct(self, ctx, K, sys_ids, grp_ids, vg_ids):
@@ -948,6 +997,14 @@ class ChunkEngine:
             self._nnb_gather(ctx, out, nnb, r_steps,
                              [gslot[int(ctx['grp_of_step'][s])] for s in r_steps],
                              fail=fail, row_fail=slot_of_sys[K.sys_o[rsel]])
+            if K.ev_out is not None:                       # steps.py:425-426, :384
+                d_rs = self._dev(r_steps.astype(np.int32))
+                d_rf = self._dev(slot_of_sys[K.sys_o[rsel]].astype(np.int32))
+                _lib.check(lib.spx_bcast_rows_dev(
+                    None, None, self._ptr(d_rs), int(r_steps.size), self._ptr(fail),
+                    self._ptr(d_rf), n_cells, self._ptr(ctx['d_pos']), self._ptr(K.ev_out),
+                    ctx['fld_size'], ctx['out_f64'], self._stream()), 'bcast_rows(zero)')
+                self._count('launches')
             for s in fb[singular[fb]]:
                 for t in K.steps_o[K.sys_o == s]:
                     if int(t) not in problem_steps:

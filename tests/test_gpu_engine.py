@@ -52,12 +52,12 @@ def test_golden_cases(eng, name):
 
 
 def test_golden_groups_flags(eng):
-    """Case b without the estimation-variance label (not on the GPU path yet)."""
+    """Case b: several availability groups, three variograms (one nugget-only),
+    low-value steps, a single-station step, a step without stations, cut-offs and
+    the OK estimation variance."""
     case, outs = load_case('b_ok_groups_flags')
-    case['interp_args'] = [a for a in case['interp_args'] if a[2] != 'EST_VARS_OK']
-    case['est_var_flag'] = False
-    outs.pop('EST_VARS_OK')
     got, prob = eng.interp_chunk(intrp_dtype=np.float64, **case)
+    assert set(got) == set(outs)
     _check(got, outs, 'b')
     assert prob == [10]          # the step without any station
 
