@@ -311,6 +311,20 @@ int spx_nnb_index_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
                       const double* cell_x, const double* cell_y, int64_t n_cells,
                       int32_t* nnb, void* stream);
 
+/* Same result through candidate lists: cand[n_cells, W] (W =
+ * spx_nnb_candidates_width()) holds for every cell its W nearest stations among ALL
+ * stations ordered by (distance, index); the nearest available station of a group
+ * is the first available candidate (full scan only if all W are missing).  One
+ * distance pass per chunk instead of one per availability group. */
+int spx_nnb_candidates_width(void);
+int spx_nnb_candidates_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                           const double* cell_x, const double* cell_y, int64_t n_cells,
+                           int32_t* cand, void* stream);
+int spx_nnb_index_cand_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                           const uint8_t* grp_mask, int32_t n_grps,
+                           const double* cell_x, const double* cell_y, int64_t n_cells,
+                           const int32_t* cand, int32_t* nnb, void* stream);
+
 /* out[row_dst[r], cell_pos[c]] = clamp(data[row_step[r], nnb[row_grp[r], c]])
  * for every listed row; if fail != NULL only where fail[row_fail[r], c] != 0
  * (the kriging -> NNB fallback of interp/steps.py:418-426). */

@@ -126,6 +126,12 @@ _SIGS = {
                                     C.c_int32, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     'spx_nnb_index_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'spx_nnb_candidates_width': (C.c_int, []),
+    'spx_nnb_candidates_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]),
+    'spx_nnb_index_cand_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     'spx_nnb_gather_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

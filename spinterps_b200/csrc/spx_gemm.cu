@@ -431,8 +431,12 @@ static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
     SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     SPX_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     static const int nts[] = {8, 6, 5, 4, 3, 2, 1};
+    // tuning knobs (benchmark experiments only)
+    const int force_nt = getenv("SPX_GEMM_NT") ? atoi(getenv("SPX_GEMM_NT")) : 0;
+    const int max_st = getenv("SPX_GEMM_STAGES") ? atoi(getenv("SPX_GEMM_STAGES")) : 4;
     for (int nt : nts) {
-        for (int st = 4; st >= 2; --st) {
+        if (force_nt > 0 && nt > force_nt) continue;
+        for (int st = max_st; st >= 2; --st) {
             if (st == 2 && nt > 1) continue;  // prefer fewer cells over a 2-deep ring
             const size_t sm = gemm_smem_bytes(g->kpad, nt, st);
             if (sm <= (size_t)max_smem) {

@@ -75,6 +75,89 @@ __global__ void __launch_bounds__(256) k_nnb_index(const double* __restrict__ st
     }
 }
 
+// Candidate lists: the NNB_L stations nearest to every cell among ALL stations,
+// ordered by (IEEE distance, station index).  The nearest AVAILABLE station of a
+// group is then the first available candidate -- the same station np.argmin
+// returns (first minimum) -- and only cells whose NNB_L nearest stations are all
+// missing need the full scan.  One distance pass per chunk instead of one per
+// availability group.
+constexpr int NNB_L = 16;
+
+__global__ void __launch_bounds__(256) k_nnb_candidates(const double* __restrict__ stn_x,
+                                                        const double* __restrict__ stn_y,
+                                                        int n_stn,
+                                                        const double* __restrict__ cell_x,
+                                                        const double* __restrict__ cell_y,
+                                                        int64_t n_cells,
+                                                        int32_t* __restrict__ cand) {
+    __shared__ double sx[NNB_STN_TILE];
+    __shared__ double sy[NNB_STN_TILE];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double x = (c < n_cells) ? cell_x[c] : 0.0;
+    const double y = (c < n_cells) ? cell_y[c] : 0.0;
+    double bd[NNB_L];
+    int bi[NNB_L];
+#pragma unroll
+    for (int j = 0; j < NNB_L; ++j) { bd[j] = CUDART_INF; bi[j] = -1; }
+    for (int s0 = 0; s0 < n_stn; s0 += NNB_STN_TILE) {
+        const int ns = min(NNB_STN_TILE, n_stn - s0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+            sx[k] = stn_x[s0 + k];
+            sy[k] = stn_y[s0 + k];
+        }
+        __syncthreads();
+        for (int k = 0; k < ns; ++k) {
+            const double d = dist_rn(x, y, sx[k], sy[k]);
+            if (d < bd[NNB_L - 1]) {   // stations arrive in index order: ties stay behind
+                bd[NNB_L - 1] = d;
+                bi[NNB_L - 1] = s0 + k;
+#pragma unroll
+                for (int j = NNB_L - 1; j > 0; --j) {
+                    if (bd[j] < bd[j - 1]) {
+                        const double td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
+                        const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (c < n_cells) {
+#pragma unroll
+        for (int j = 0; j < NNB_L; ++j) cand[c * NNB_L + j] = bi[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nnb_from_candidates(
+    const double* __restrict__ stn_x, const double* __restrict__ stn_y, int n_stn,
+    const uint8_t* __restrict__ grp_mask, int n_grps, const double* __restrict__ cell_x,
+    const double* __restrict__ cell_y, int64_t n_cells, const int32_t* __restrict__ cand,
+    int32_t* __restrict__ nnb) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    int cd[NNB_L];
+#pragma unroll
+    for (int j = 0; j < NNB_L; ++j) cd[j] = cand[c * NNB_L + j];
+    for (int gi = blockIdx.y; gi < n_grps; gi += gridDim.y) {
+        const uint8_t* __restrict__ m = grp_mask + (int64_t)gi * n_stn;
+        int found = -1;
+#pragma unroll
+        for (int j = 0; j < NNB_L; ++j) {
+            if (found < 0 && cd[j] >= 0 && m[cd[j]]) found = cd[j];
+        }
+        if (found < 0) {   // every candidate missing: full scan (rare)
+            const double x = cell_x[c], y = cell_y[c];
+            double best = CUDART_INF;
+            for (int k = 0; k < n_stn; ++k) {
+                if (!m[k]) continue;
+                const double d = dist_rn(x, y, stn_x[k], stn_y[k]);
+                if (d < best || found < 0) { best = d; found = k; }
+            }
+        }
+        nnb[(int64_t)gi * n_cells + c] = found;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_nnb_gather(
     const double* __restrict__ data, int n_stn, const int32_t* __restrict__ nnb,
     const int32_t* __restrict__ row_step, const int32_t* __restrict__ row_grp,
@@ -191,6 +274,34 @@ int spx_nnb_index_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
     k_nnb_index<<<grid, 256, 0, (cudaStream_t)stream>>>(stn_x, stn_y, n_stn, grp_mask, n_grps,
                                                         cell_x, cell_y, n_cells, nnb);
     SPX_CHECK_LAUNCH("k_nnb_index");
+    return SPX_OK;
+}
+
+int spx_nnb_candidates_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                           const double* cell_x, const double* cell_y, int64_t n_cells,
+                           int32_t* cand, void* stream) {
+    if (n_cells == 0) return SPX_OK;
+    if (n_stn <= 0) {
+        set_error("nnb_candidates: no stations");
+        return SPX_EINVAL;
+    }
+    k_nnb_candidates<<<(unsigned)((n_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        stn_x, stn_y, n_stn, cell_x, cell_y, n_cells, cand);
+    SPX_CHECK_LAUNCH("k_nnb_candidates");
+    return SPX_OK;
+}
+
+int spx_nnb_candidates_width(void) { return NNB_L; }
+
+int spx_nnb_index_cand_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                           const uint8_t* grp_mask, int32_t n_grps, const double* cell_x,
+                           const double* cell_y, int64_t n_cells, const int32_t* cand,
+                           int32_t* nnb, void* stream) {
+    if (n_grps == 0 || n_cells == 0) return SPX_OK;
+    dim3 grid((unsigned)((n_cells + 255) / 256), grid_y(n_grps < 64 ? n_grps : 64));
+    k_nnb_from_candidates<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        stn_x, stn_y, n_stn, grp_mask, n_grps, cell_x, cell_y, n_cells, cand, nnb);
+    SPX_CHECK_LAUNCH("k_nnb_from_candidates");
     return SPX_OK;
 }
 

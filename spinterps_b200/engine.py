@@ -108,6 +108,11 @@ class ChunkEngine:
         # least this many availability groups
         self.downdate = True
         self.downdate_min_systems = 4
+        # full-system inverses are reused across chunks with the same stations and
+        # variogram (they do not depend on the data)
+        self.ginv_cache = True
+        self.ginv_cache_size = 8
+        self._ginv_cache = {}
         self.stats = {}
         # bench hook: CUDA events around every estimate-contraction launch
         self.profile_gemm = False
@@ -381,10 +386,28 @@ class ChunkEngine:
             cy = self._dev(ctx['dst_ys'][cells])
             nc = int(cells.size)
         nnb = torch.empty((len(grp_ids), nc), dtype=_I32, device=self.device)
-        _lib.check(self.lib.spx_nnb_index_dev(
-            self._ptr(ctx['d_stn_x']), self._ptr(ctx['d_stn_y']), ctx['n_stn'], self._ptr(mask),
-            len(grp_ids), self._ptr(cx), self._ptr(cy), nc, self._ptr(nnb), self._stream()),
-            'nnb_index')
+        if len(grp_ids) >= 4 and ctx['n_stn'] > self.lib.spx_nnb_candidates_width():
+            # candidate lists once per (chunk, cell set), then a cheap pass per group
+            ckey = ('cand', None if cells is None else cells.tobytes())
+            cand = ctx['nnb_cache'].get(ckey)
+            if cand is None:
+                cand = torch.empty((nc, self.lib.spx_nnb_candidates_width()), dtype=_I32,
+                                   device=self.device)
+                _lib.check(self.lib.spx_nnb_candidates_dev(
+                    self._ptr(ctx['d_stn_x']), self._ptr(ctx['d_stn_y']), ctx['n_stn'],
+                    self._ptr(cx), self._ptr(cy), nc, self._ptr(cand), self._stream()),
+                    'nnb_candidates')
+                self._count('launches')
+                ctx['nnb_cache'][ckey] = cand
+            _lib.check(self.lib.spx_nnb_index_cand_dev(
+                self._ptr(ctx['d_stn_x']), self._ptr(ctx['d_stn_y']), ctx['n_stn'],
+                self._ptr(mask), len(grp_ids), self._ptr(cx), self._ptr(cy), nc,
+                self._ptr(cand), self._ptr(nnb), self._stream()), 'nnb_index_cand')
+        else:
+            _lib.check(self.lib.spx_nnb_index_dev(
+                self._ptr(ctx['d_stn_x']), self._ptr(ctx['d_stn_y']), ctx['n_stn'],
+                self._ptr(mask), len(grp_ids), self._ptr(cx), self._ptr(cy), nc,
+                self._ptr(nnb), self._stream()), 'nnb_index')
         self._count('launches')
         ctx['nnb_cache'][key] = nnb
         return nnb
@@ -534,6 +557,7 @@ class ChunkEngine:
             assert drft.shape == (n_drifts, n_cells)
             K.d_cell_drift = self._dev(drft)
             K.d_stn_drift = self._dev(np.ascontiguousarray(stns_drft, dtype=np.float64))
+            ctx['stns_drft_bytes'] = np.ascontiguousarray(stns_drft, dtype=np.float64).tobytes()
             bad_cells = np.where(np.isnan(drft).any(axis=0))[0]
 
         # station lists per group (ascending station index = reference order); the
@@ -843,33 +867,56 @@ class ChunkEngine:
         M = n_stn + K.n_border
         finishers = []
         vgs_here = np.unique(K.sys_vg[sys_ids])
-        # full systems, one per variogram, factored together
-        T = self._systems_struct(ctx, K, np.arange(vgs_here.size),
-                                 np.full(vgs_here.size, K.full_grp), vgs_here)
-        self._factor(ctx, K, T)
-        ginv = torch.empty((vgs_here.size, M, M), dtype=_F64, device=self.device)
-        n_full = vgs_here.size
-        rhs_sys = np.repeat(np.arange(n_full), M + 1)
-        rhs_kind = np.tile(np.concatenate([np.full(M, 2), [1]]), n_full)
-        rhs_arg = np.tile(np.concatenate([np.arange(M), [0]]), n_full)
-        rhs_row = np.full(rhs_sys.size, -1)
-        dense = torch.empty((n_full * (M + 1), M), dtype=_F64, device=self.device)
-        resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
-                               want_resid=True, dense=dense, dense_ld=M)
-        h_full_info = self._fetch_async(T.info)
-        h_full_resid = self._fetch_async(resid.view(n_full, M + 1)[:, M].contiguous())
+        # Inverse of the full system of every variogram.  It depends on the station
+        # set and the variogram only (not on the data), so it is kept across the
+        # chunks of a job in a small cache.
+        base_key = (K.kind, K.n_drifts, ctx['min_vg_val'], ctx['stn_xs'].tobytes(),
+                    ctx['stn_ys'].tobytes(),
+                    None if K.d_stn_drift is None else ctx['stns_drft_bytes'])
+        ginv_of = {}
+        need = []
+        for v in vgs_here:
+            hit = self._ginv_cache.get((base_key, K.uniq_vgs[int(v)])) if self.ginv_cache else None
+            if hit is not None:
+                ginv_of[int(v)] = hit
+                self._count('ginv_cache_hits')
+            else:
+                need.append(int(v))
+        if need:
+            need = np.asarray(need)
+            T = self._systems_struct(ctx, K, np.arange(need.size),
+                                     np.full(need.size, K.full_grp), need)
+            self._factor(ctx, K, T)
+            n_full = need.size
+            rhs_sys = np.repeat(np.arange(n_full), M + 1)
+            rhs_kind = np.tile(np.concatenate([np.full(M, 2), [1]]), n_full)
+            rhs_arg = np.tile(np.concatenate([np.arange(M), [0]]), n_full)
+            rhs_row = np.full(rhs_sys.size, -1)
+            dense = torch.empty((n_full * (M + 1), M), dtype=_F64, device=self.device)
+            resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
+                                   want_resid=True, dense=dense, dense_ld=M)
+            h_full_info = self._fetch_async(T.info)
+            h_full_resid = self._fetch_async(resid.view(n_full, M + 1)[:, M].contiguous())
+            dense = dense.view(n_full, M + 1, M)
+            for vi, v in enumerate(need):
+                ginv_of[int(v)] = dense[vi, :M, :]
 
-        def finish_full(resid_out, singular_out):
-            bad = (h_full_info.numpy() != 0) | ~(h_full_resid.numpy() <= 1e-9)
-            return bool(bad.any())
-        finishers.append(finish_full)
-        dense = dense.view(n_full, M + 1, M)
+            def finish_full(resid_out, singular_out):
+                bad = (h_full_info.numpy() != 0) | ~(h_full_resid.numpy() <= 1e-9)
+                if self.ginv_cache:
+                    for vi, v in enumerate(need):
+                        if not bad[vi]:
+                            while len(self._ginv_cache) >= self.ginv_cache_size:
+                                self._ginv_cache.pop(next(iter(self._ginv_cache)))
+                            self._ginv_cache[(base_key, K.uniq_vgs[int(v)])] = ginv_of[int(v)]
+                return bool(bad.any())
+            finishers.append(finish_full)
         miss_mask_all = ~ctx['grp_mask']
         for vi, v in enumerate(vgs_here):
             ids = sys_ids[K.sys_vg[sys_ids] == v]
             if not ids.size:
                 continue
-            G = dense[vi, :M, :]
+            G = ginv_of[int(v)]
             grp = K.sys_grp[ids]
             r = (n_stn - K.sys_n[ids]).astype(np.int32)
             miss_list = np.where(miss_mask_all[grp])[1].astype(np.int32)

@@ -121,3 +121,16 @@ def test_linearity_and_constant_field(eng):
                              intrp_dtype=np.float64, **base)
     for lab in ('OK', 'IDW_000'):
         np.testing.assert_allclose(rc[lab], 7.25, rtol=1e-11)
+
+
+def test_nnb_candidate_lists_and_full_scan_fallback(eng):
+    """Nearest neighbour through candidate lists (16 nearest stations per cell):
+    with 85 % missing data most cells have no available candidate and take the
+    full-scan branch; indices must equal np.argmin of the oracle exactly."""
+    p = make_problem(21, 70, 12, 37, 29, cell=3000.0, miss=0.85)
+    p['data'][3, :] = np.nan
+    p['data'][3, 5] = 1.5                      # a single-station step
+    args = [('NNB', None, 'NNB')]
+    exp, _ = orc.interp_chunk(interp_args=args, intrp_dtype=np.float64, **p)
+    got, _ = eng.interp_chunk(interp_args=args, intrp_dtype=np.float64, **p)
+    assert rel_err(got['NNB'], exp['NNB']) == 0.0
