@@ -357,6 +357,53 @@ int spx_bcast_rows_dev(const double* aux, const int32_t* row_slot, const int32_t
                        int64_t n_cells, const int32_t* cell_pos, void* out, int64_t out_ld,
                        int32_t out_f64, void* stream);
 
+/* ---- 'nrst' neighbour selection (interp/grps.py:147-166, :103-139) --------------
+ * Every cell uses its k nearest available stations; cells with the same neighbour
+ * set share one (k + border) system. */
+typedef struct spx_nrst {
+    int32_t n_grp;            /* cell groups = systems                              */
+    int64_t n_cells;
+    int32_t k, n_border, n_drifts, kind, n_stn;
+    const int32_t* nbu;       /* [n_grp, k] neighbour station indices, ascending    */
+    const int32_t* cell_grp;  /* [n_cells] system of each cell                      */
+    const double* stn_x;
+    const double* stn_y;
+    const double* stn_drift;  /* [n_stn, n_drifts] or NULL                          */
+    const double* cell_x;
+    const double* cell_y;
+    const double* cell_drift; /* [n_drifts, n_cells] or NULL                        */
+    spx_vg vg;
+    double min_vg_val;
+    const double* data;       /* [*, n_stn]                                         */
+    const int32_t* steps;     /* [n_t] rows of data / output rows                   */
+    int32_t n_t;
+    double min_var_thr;       /* interp/steps.py:760-765                            */
+    const uint8_t* step_bypass; /* [n_t] 1 = nugget-only variogram (station mean)   */
+    double* coef;             /* [n_grp, n_t + 1, k + n_border] dual coefficients   */
+    double* ovr;              /* [n_grp, n_t] NaN = krige, else value to write      */
+    int32_t* info;            /* [n_grp] LU status                                  */
+    const int32_t* cell_pos;
+    void* out;
+    int64_t out_ld;
+    int32_t out_f64, has_lo, has_hi;
+    double lo, hi;
+    double idw_exp;
+} spx_nrst;
+
+int spx_nrst_max_neighbors(void);
+/* nb[n_cells, k]: the k nearest stations with mask[s] != 0 (all if mask == NULL) by
+ * IEEE distance, indices ascending (np.sort(np.argsort(d)[:k])); hash[n_cells]: a
+ * 63-bit hash of the row (cells are grouped by it, like grps.py:109-111). */
+int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                      const uint8_t* mask, const double* cell_x, const double* cell_y,
+                      int64_t n_cells, int32_t k, int32_t* nb, int64_t* hash, void* stream);
+/* Assemble + LU + solve every step (and the ones-vector) of every cell-group system. */
+int spx_nrst_solve_dev(const spx_nrst* n, void* stream);
+/* Per cell: rhs from coordinates, sum(lambda) test, NNB fallback, estimate, store. */
+int spx_nrst_krige_dev(const spx_nrst* n, void* stream);
+/* Per cell: IDW over its own neighbour row nb[n_cells, k]. */
+int spx_nrst_idw_dev(const spx_nrst* n, const int32_t* nb, void* stream);
+
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field
  * download in flight; n_bytes and both pointers multiples of 4. */

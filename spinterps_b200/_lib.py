@@ -74,6 +74,22 @@ class spx_downdate(C.Structure):
                 ('resid', C.c_void_p), ('info', C.c_void_p)]
 
 
+class spx_nrst(C.Structure):
+    _fields_ = [('n_grp', C.c_int32), ('n_cells', C.c_int64),
+                ('k', C.c_int32), ('n_border', C.c_int32), ('n_drifts', C.c_int32),
+                ('kind', C.c_int32), ('n_stn', C.c_int32),
+                ('nbu', C.c_void_p), ('cell_grp', C.c_void_p),
+                ('stn_x', C.c_void_p), ('stn_y', C.c_void_p), ('stn_drift', C.c_void_p),
+                ('cell_x', C.c_void_p), ('cell_y', C.c_void_p), ('cell_drift', C.c_void_p),
+                ('vg', spx_vg), ('min_vg_val', C.c_double),
+                ('data', C.c_void_p), ('steps', C.c_void_p), ('n_t', C.c_int32),
+                ('min_var_thr', C.c_double), ('step_bypass', C.c_void_p),
+                ('coef', C.c_void_p), ('ovr', C.c_void_p), ('info', C.c_void_p),
+                ('cell_pos', C.c_void_p), ('out', C.c_void_p), ('out_ld', C.c_int64),
+                ('out_f64', C.c_int32), ('has_lo', C.c_int32), ('has_hi', C.c_int32),
+                ('lo', C.c_double), ('hi', C.c_double), ('idw_exp', C.c_double)]
+
+
 class spx_gemm(C.Structure):
     _fields_ = [('coef', C.c_void_p), ('n_rows', C.c_int64),
                 ('kpad', C.c_int32), ('n_stn', C.c_int32), ('n_border', C.c_int32),
@@ -139,6 +155,13 @@ _SIGS = {
     'spx_fill_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_double, C.c_double, C.c_void_p]),
+    'spx_nrst_max_neighbors': (C.c_int, []),
+    'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    'spx_nrst_solve_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
+    'spx_nrst_krige_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
+    'spx_nrst_idw_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p, C.c_void_p]),
     'spx_bcast_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int32, C.c_void_p]),

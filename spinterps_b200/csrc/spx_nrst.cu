@@ -1,0 +1,472 @@
+// 'nrst' neighbour selection (interp/grps.py:147-166, :103-139) and the
+// estimators that go with it: every cell uses only its k nearest available
+// stations, cells sharing the same neighbour set share one (k + border) kriging
+// system.  Four kernels:
+//   k_topk        per cell: the k nearest available stations (IEEE distances,
+//                 indices returned ascending like np.sort(np.argsort(d)[:k])) and a
+//                 64-bit hash of the index row used to group cells
+//   k_nrst_solve  per cell group: assemble the small system from coordinates in
+//                 shared memory, LU with partial pivoting, solve every step of the
+//                 availability group (dual coefficients) + the ones-vector
+//   k_nrst_krige  per cell: right-hand side from coordinates, sum(lambda) test,
+//                 NNB fallback, estimate, clamp, store (interp/steps.py:403-435)
+//   k_nrst_idw    per cell: IDW over its neighbours (interp/steps.py:293-313)
+#include "spx_common.cuh"
+
+namespace spx {
+
+constexpr int NRST_KMAX = 64;   // neighbours per cell
+constexpr int NRST_MMAX = 72;   // k + border
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    return h;
+}
+
+__global__ void __launch_bounds__(128) k_topk(const double* __restrict__ stn_x,
+                                              const double* __restrict__ stn_y, int n_stn,
+                                              const uint8_t* __restrict__ mask,  // [n_stn] or null
+                                              const double* __restrict__ cell_x,
+                                              const double* __restrict__ cell_y, int64_t n_cells,
+                                              int k, int32_t* __restrict__ nb,   // [n_cells, k]
+                                              int64_t* __restrict__ hash) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double x = cell_x[c], y = cell_y[c];
+    double bd[NRST_KMAX];
+    int bi[NRST_KMAX];
+    int cnt = 0;
+    for (int s = 0; s < n_stn; ++s) {
+        if (mask != nullptr && !mask[s]) continue;
+        const double d = dist_rn(x, y, stn_x[s], stn_y[s]);
+        if (cnt == k && !(d < bd[k - 1])) continue;   // ties keep the earlier station
+        int j = (cnt < k) ? cnt : k - 1;
+        while (j > 0 && d < bd[j - 1]) {
+            bd[j] = bd[j - 1];
+            bi[j] = bi[j - 1];
+            --j;
+        }
+        bd[j] = d;
+        bi[j] = s;
+        if (cnt < k) ++cnt;
+    }
+    // indices ascending (np.sort)
+    for (int i = 1; i < cnt; ++i) {
+        const int v = bi[i];
+        int j = i;
+        while (j > 0 && bi[j - 1] > v) {
+            bi[j] = bi[j - 1];
+            --j;
+        }
+        bi[j] = v;
+    }
+    uint64_t h = 0x243f6a8885a308d3ull;
+    for (int i = 0; i < k; ++i) {
+        const int v = (i < cnt) ? bi[i] : -1;
+        nb[c * k + i] = v;
+        h = mix64(h, (uint64_t)(uint32_t)v);
+    }
+    hash[c] = (int64_t)(h >> 1);   // non-negative
+}
+
+struct NrstSolveArgs {
+    int n_grp;                    // cell groups (systems)
+    int k, n_border, n_drifts, kind;
+    const int32_t* nbu;           // [n_grp, k] neighbour station indices, ascending
+    const double* stn_x;
+    const double* stn_y;
+    const double* stn_drift;      // [n_stn, n_drifts]
+    VgDev vg;
+    double min_vg_val;
+    const double* data;           // [n_steps_total, n_stn]
+    int n_stn;
+    const int32_t* steps;         // [n_t] step indices of this launch
+    int n_t;
+    double min_var_thr;
+    const uint8_t* step_bypass;   // [n_t] 1 = nugget-only variogram -> mean
+    double* coef;                 // [n_grp, n_t + 1, m]  (row n_t = ones-vector solution)
+    double* ovr;                  // [n_grp, n_t]  NaN = krige, else the value to write
+    int32_t* info;                // [n_grp]
+};
+
+__global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
+    extern __shared__ double ssm[];
+    const int u = blockIdx.x;
+    const int k = a.k, m = a.k + a.n_border;
+    const int ld = m | 1;
+    double* S = ssm;                        // [ld * m] column-major
+    double* ys = S + (size_t)ld * m;        // [4][ld]
+    int* pv = reinterpret_cast<int*>(ys + 4 * (size_t)ld);   // [m]
+    int* st = pv + m;                       // [k]
+    __shared__ double red_v[4];
+    __shared__ int red_i[4];
+    __shared__ int s_p;
+    __shared__ double s_pv;
+    __shared__ int s_info;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_info = 0;
+    for (int i = tid; i < k; i += 128) st[i] = a.nbu[(int64_t)u * k + i];
+    __syncthreads();
+    const int covar = (a.kind == SPX_KRG_SK);
+    for (int idx = tid; idx < m * m; idx += 128) {
+        const int j = idx / m, i = idx - j * m;
+        double v;
+        if (i < k && j < k) {
+            const double h = dist_rn(a.stn_x[st[i]], a.stn_y[st[i]], a.stn_x[st[j]], a.stn_y[st[j]]);
+            v = vg_eval(a.vg, h, covar, a.min_vg_val);
+        } else if (i >= k && j >= k) {
+            v = 0.0;
+        } else {
+            const int b = (i >= k) ? (i - k) : (j - k);
+            const int s = (i >= k) ? j : i;
+            v = (b == 0) ? 1.0 : a.stn_drift[(int64_t)st[s] * a.n_drifts + (b - 1)];
+        }
+        S[i + (size_t)j * ld] = v;
+    }
+    __syncthreads();
+    // ---- LU, partial pivoting
+    for (int c = 0; c < m; ++c) {
+        double bv = -1.0;
+        int bi = c;
+        const double* colc = S + (size_t)c * ld;
+        for (int i = c + tid; i < m; i += 128) {
+            const double v = fabs(colc[i]);
+            if (v > bv) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 4; ++w)
+                if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+            s_p = bi;
+            s_pv = colc[bi];
+            pv[c] = bi;
+            if (!(bv > 0.0) && s_info == 0) s_info = c + 1;
+        }
+        __syncthreads();
+        const int p = s_p;
+        const double pvv = s_pv;
+        if (p != c)
+            for (int j = tid; j < m; j += 128) {
+                const double t = S[c + (size_t)j * ld];
+                S[c + (size_t)j * ld] = S[p + (size_t)j * ld];
+                S[p + (size_t)j * ld] = t;
+            }
+        __syncthreads();
+        double* cc = S + (size_t)c * ld;
+        if (pvv != 0.0)
+            for (int i = c + 1 + tid; i < m; i += 128) cc[i] = cc[i] / pvv;
+        __syncthreads();
+        for (int j = c + 1 + wid; j < m; j += 4) {
+            double* cj = S + (size_t)j * ld;
+            const double ucj = cj[c];
+            for (int i = c + 1 + lane; i < m; i += 32) cj[i] = fma(-cc[i], ucj, cj[i]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.info[u] = s_info;
+    // ---- right-hand sides: n_t data steps + the ones vector, one per warp
+    double* y = ys + (size_t)wid * ld;
+    for (int q = wid; q <= a.n_t; q += 4) {
+        const bool ones = (q == a.n_t);
+        double zmax = -CUDART_INF, zsum = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            double v = 0.0;
+            if (i < k) {
+                v = ones ? 1.0 : a.data[(int64_t)a.steps[q] * a.n_stn + st[i]];
+                if (!ones) { zmax = fmax(zmax, v); zsum += v; }
+            }
+            y[i] = v;
+        }
+        __syncwarp();
+        if (!ones) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+            }
+            // steps.py:760-765 (all values below the threshold) and :325-331
+            const bool bypass = !(zmax >= a.min_var_thr) || a.step_bypass[q];
+            if (lane == 0)
+                a.ovr[(int64_t)u * a.n_t + q] = bypass ? (zsum / k) : CUDART_NAN;
+        }
+        if (lane == 0)
+            for (int c = 0; c < m; ++c) {
+                const int p = pv[c];
+                if (p != c) { const double t = y[c]; y[c] = y[p]; y[p] = t; }
+            }
+        __syncwarp();
+        for (int c = 0; c < m - 1; ++c) {
+            const double xc = y[c];
+            const double* cc = S + (size_t)c * ld;
+            for (int i = c + 1 + lane; i < m; i += 32) y[i] = fma(-cc[i], xc, y[i]);
+            __syncwarp();
+        }
+        for (int c = m - 1; c >= 0; --c) {
+            const double* cc = S + (size_t)c * ld;
+            const double xc = y[c] / cc[c];
+            __syncwarp();
+            if (lane == 0) y[c] = xc;
+            for (int i = lane; i < c; i += 32) y[i] = fma(-cc[i], xc, y[i]);
+            __syncwarp();
+        }
+        double* dst = a.coef + ((int64_t)u * (a.n_t + 1) + q) * m;
+        for (int i = lane; i < m; i += 32) dst[i] = y[i];
+        __syncwarp();
+    }
+}
+
+struct NrstEstArgs {
+    int64_t n_cells;
+    int k, n_border, n_drifts, kind, n_stn;
+    const int32_t* cell_grp;      // [n_cells] -> system
+    const int32_t* nbu;           // [n_grp, k]
+    const double* stn_x;
+    const double* stn_y;
+    const double* cell_x;
+    const double* cell_y;
+    const double* cell_drift;     // [n_drifts, n_cells]
+    VgDev vg;
+    double min_vg_val;
+    const double* data;
+    const int32_t* steps;
+    int n_t;
+    const double* coef;
+    const double* ovr;
+    const int32_t* info;
+    const int32_t* cell_pos;
+    void* out;
+    int64_t out_ld;
+    int out_f64, has_lo, has_hi;
+    double lo, hi;
+    double idw_exp;
+    double min_var_thr;
+};
+
+__global__ void __launch_bounds__(128) k_nrst_krige(NrstEstArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;
+    const int k = a.k, m = a.k + a.n_border;
+    const int u = a.cell_grp[c];
+    const int32_t* __restrict__ st = a.nbu + (int64_t)u * k;
+    const double x = a.cell_x[c], y = a.cell_y[c];
+    double rhs[NRST_MMAX];
+    const int covar = (a.kind == SPX_KRG_SK);
+    double dmin = CUDART_INF;
+    int nn = st[0];
+    for (int j = 0; j < k; ++j) {
+        const int s = st[j];
+        const double d = dist_rn(x, y, a.stn_x[s], a.stn_y[s]);
+        if (d < dmin) { dmin = d; nn = s; }          // np.argmin: first minimum
+        rhs[j] = vg_eval(a.vg, d, covar, a.min_vg_val);
+    }
+    for (int b = 0; b < a.n_border; ++b)
+        rhs[k + b] = (b == 0) ? 1.0 : a.cell_drift[(int64_t)(b - 1) * a.n_cells + c];
+    // sum(lambda) = s . rhs with s = A^-1 [1; 0]  (steps.py:418)
+    const double* __restrict__ cu = a.coef + (int64_t)u * (a.n_t + 1) * m;
+    double lsum = 0.0;
+    {
+        const double* sv = cu + (int64_t)a.n_t * m;
+        for (int j = 0; j < m; ++j) lsum = fma(sv[j], rhs[j], lsum);
+    }
+    bool ok = fabs(lsum - 1.0) <= (1e-8 + 1e-5);
+    if (!(lsum == lsum) || isinf(lsum) || a.info[u] != 0) ok = false;
+    const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+    for (int q = 0; q < a.n_t; ++q) {
+        const int t = a.steps[q];
+        const double ov = a.ovr[(int64_t)u * a.n_t + q];
+        double v;
+        if (ov == ov) {
+            v = ov;
+        } else if (!ok) {
+            v = a.data[(int64_t)t * a.n_stn + nn];
+        } else {
+            const double* cq = cu + (int64_t)q * m;
+            v = 0.0;
+            for (int j = 0; j < m; ++j) v = fma(cq[j], rhs[j], v);
+        }
+        v = clampd(v, a.has_lo, a.has_hi, a.lo, a.hi);
+        store_out(a.out, (int64_t)t * a.out_ld + col, v, a.out_f64);
+    }
+}
+
+// IDW over the cell's neighbours; nb = the per-cell neighbour rows of k_topk.
+__global__ void __launch_bounds__(128) k_nrst_idw(NrstEstArgs a, const int32_t* __restrict__ nb) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;
+    const int k = a.k;
+    const int32_t* __restrict__ st = nb + c * k;
+    const double x = a.cell_x[c], y = a.cell_y[c];
+    double w[NRST_KMAX];
+    double dmax = 0.0;
+    for (int j = 0; j < k; ++j) {
+        w[j] = dist_rn(x, y, a.stn_x[st[j]], a.stn_y[st[j]]);
+        dmax = fmax(dmax, w[j]);
+    }
+    double wsum = 0.0;
+    for (int j = 0; j < k; ++j) {
+        double d = w[j];
+        if (dmax > 0) d = d / dmax;              // steps.py:297-301
+        w[j] = 1.0 / pow(d, a.idw_exp);          // pyx:792
+        wsum += w[j];
+    }
+    const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+    for (int q = 0; q < a.n_t; ++q) {
+        const int t = a.steps[q];
+        const double* __restrict__ z = a.data + (int64_t)t * a.n_stn;
+        double acc = 0.0, zmax = -CUDART_INF, zsum = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const double zj = z[st[j]];
+            acc = fma(w[j], zj, acc);
+            zmax = fmax(zmax, zj);
+            zsum += zj;
+        }
+        double v = (zmax >= a.min_var_thr) ? (acc / wsum) : (zsum / k);   // steps.py:308-313
+        v = clampd(v, a.has_lo, a.has_hi, a.lo, a.hi);
+        store_out(a.out, (int64_t)t * a.out_ld + col, v, a.out_f64);
+    }
+}
+
+}  // namespace spx
+
+using namespace spx;
+
+extern "C" {
+
+int spx_nrst_max_neighbors(void) { return NRST_KMAX; }
+
+int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                      const uint8_t* mask, const double* cell_x, const double* cell_y,
+                      int64_t n_cells, int32_t k, int32_t* nb, int64_t* hash, void* stream) {
+    if (n_cells == 0) return SPX_OK;
+    if (k < 1 || k > NRST_KMAX) {
+        set_error("nrst_topk: k=%d outside 1..%d", k, NRST_KMAX);
+        return SPX_EINVAL;
+    }
+    k_topk<<<(unsigned)((n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, nb, hash);
+    SPX_CHECK_LAUNCH("k_topk");
+    return SPX_OK;
+}
+
+int spx_nrst_solve_dev(const spx_nrst* n, void* stream) {
+    if (!n) {
+        set_error("nrst_solve: null argument");
+        return SPX_EINVAL;
+    }
+    if (n->n_grp == 0) return SPX_OK;
+    const int m = n->k + n->n_border;
+    if (n->k < 1 || n->k > NRST_KMAX || m > NRST_MMAX) {
+        set_error("nrst_solve: k=%d / m=%d outside the supported range (%d / %d)", n->k, m,
+                  NRST_KMAX, NRST_MMAX);
+        return SPX_EINVAL;
+    }
+    NrstSolveArgs a;
+    a.n_grp = n->n_grp;
+    a.k = n->k;
+    a.n_border = n->n_border;
+    a.n_drifts = n->n_drifts;
+    a.kind = n->kind;
+    a.nbu = n->nbu;
+    a.stn_x = n->stn_x;
+    a.stn_y = n->stn_y;
+    a.stn_drift = n->stn_drift;
+    a.vg = to_dev(n->vg);
+    a.min_vg_val = n->min_vg_val;
+    a.data = n->data;
+    a.n_stn = n->n_stn;
+    a.steps = n->steps;
+    a.n_t = n->n_t;
+    a.min_var_thr = n->min_var_thr;
+    a.step_bypass = n->step_bypass;
+    a.coef = n->coef;
+    a.ovr = n->ovr;
+    a.info = n->info;
+    const int ld = m | 1;
+    const size_t smem = ((size_t)ld * m + 4 * (size_t)ld) * sizeof(double) +
+                        ((size_t)m + n->k) * sizeof(int);
+    if (smem > 48 * 1024)
+        SPX_CUDA(cudaFuncSetAttribute(k_nrst_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    k_nrst_solve<<<n->n_grp, 128, smem, (cudaStream_t)stream>>>(a);
+    SPX_CHECK_LAUNCH("k_nrst_solve");
+    return SPX_OK;
+}
+
+static void fill_est(NrstEstArgs& a, const spx_nrst* n) {
+    a.n_cells = n->n_cells;
+    a.k = n->k;
+    a.n_border = n->n_border;
+    a.n_drifts = n->n_drifts;
+    a.kind = n->kind;
+    a.n_stn = n->n_stn;
+    a.cell_grp = n->cell_grp;
+    a.nbu = n->nbu;
+    a.stn_x = n->stn_x;
+    a.stn_y = n->stn_y;
+    a.cell_x = n->cell_x;
+    a.cell_y = n->cell_y;
+    a.cell_drift = n->cell_drift;
+    a.vg = to_dev(n->vg);
+    a.min_vg_val = n->min_vg_val;
+    a.data = n->data;
+    a.steps = n->steps;
+    a.n_t = n->n_t;
+    a.coef = n->coef;
+    a.ovr = n->ovr;
+    a.info = n->info;
+    a.cell_pos = n->cell_pos;
+    a.out = n->out;
+    a.out_ld = n->out_ld;
+    a.out_f64 = n->out_f64;
+    a.has_lo = n->has_lo;
+    a.has_hi = n->has_hi;
+    a.lo = n->lo;
+    a.hi = n->hi;
+    a.idw_exp = n->idw_exp;
+    a.min_var_thr = n->min_var_thr;
+}
+
+int spx_nrst_krige_dev(const spx_nrst* n, void* stream) {
+    if (!n) {
+        set_error("nrst_krige: null argument");
+        return SPX_EINVAL;
+    }
+    if (n->n_cells == 0 || n->n_t == 0) return SPX_OK;
+    if (n->k + n->n_border > NRST_MMAX) {
+        set_error("nrst_krige: system too large");
+        return SPX_EINVAL;
+    }
+    NrstEstArgs a;
+    fill_est(a, n);
+    k_nrst_krige<<<(unsigned)((n->n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    SPX_CHECK_LAUNCH("k_nrst_krige");
+    return SPX_OK;
+}
+
+int spx_nrst_idw_dev(const spx_nrst* n, const int32_t* nb, void* stream) {
+    if (!n || !nb) {
+        set_error("nrst_idw: null argument");
+        return SPX_EINVAL;
+    }
+    if (n->n_cells == 0 || n->n_t == 0) return SPX_OK;
+    if (n->k > NRST_KMAX) {
+        set_error("nrst_idw: k too large");
+        return SPX_EINVAL;
+    }
+    NrstEstArgs a;
+    fill_est(a, n);
+    k_nrst_idw<<<(unsigned)((n->n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, nb);
+    SPX_CHECK_LAUNCH("k_nrst_idw");
+    return SPX_OK;
+}
+
+}  // extern "C"

@@ -250,10 +250,20 @@ class ChunkEngine:
             assert len(vgs) == n_steps
             assert all(v != 'nan' for v in vgs), (   # steps.py:504-507
                 'NaN VGs not allowed! Use Nugget or any other appropriate one!')
-        if neb_sel_mthd != 'all':
+        if neb_sel_mthd not in ('all', 'nrst'):
             raise NotImplementedError(
-                f"neighbor selection '{neb_sel_mthd}' is not on the GPU path yet "
-                "(SURVEY.md section 8f row 2)")
+                f"neighbor selection '{neb_sel_mthd}' is not supported ('pie' cannot run in "
+                "the reference on LP64 platforms either, SURVEY.md top table)")
+        nrst = neb_sel_mthd == 'nrst'
+        if nrst:
+            assert isinstance(n_nebs, (int, np.integer)) and n_nebs > 0
+            if n_nebs >= n_stn:
+                nrst = False            # interp/prepare.py:434-463 falls back to 'all'
+            elif n_nebs > self.lib.spx_nrst_max_neighbors():
+                raise NotImplementedError(
+                    f'n_neighbors > {self.lib.spx_nrst_max_neighbors()} is not supported')
+            elif est_var_flag and 'OK' in interp_types:
+                raise NotImplementedError('EST_VARS_OK with nrst neighbours is not supported')
         ev_flag = bool(est_var_flag) and ('OK' in interp_types)
         if ev_flag:
             assert 'EST_VARS_OK' in interp_labels, 'est_var_flag needs an EST_VARS_OK label'
@@ -280,6 +290,20 @@ class ChunkEngine:
                 drft_arrs = drft_arrs[:, fld_beg_idx:fld_end_idx]
         n_cells = int(dst_xs.shape[0])
         assert n_cells > 0
+
+        if nrst:
+            # stations never among the n_nebs nearest of any cell are dropped up-front
+            # (interp/steps.py:592-608, quirk Q9)
+            nb0, _ = self._topk(self._dev(stn_xs), self._dev(stn_ys), n_stn, None,
+                                self._dev(dst_xs), self._dev(dst_ys), n_cells, int(n_nebs))
+            tke = torch.unique(nb0).cpu().numpy()
+            if tke.size != n_stn:
+                stn_xs = np.ascontiguousarray(stn_xs[tke])
+                stn_ys = np.ascontiguousarray(stn_ys[tke])
+                data = np.ascontiguousarray(data[:, tke])
+                if stns_drft is not None:
+                    stns_drft = np.ascontiguousarray(np.asarray(stns_drft)[tke])
+                n_stn = int(tke.size)
 
         # ---- per-step host logic --------------------------------------------
         t_host0 = time.perf_counter()
@@ -333,11 +357,23 @@ class ChunkEngine:
             multi = n_avail >= 2
             if itype == 'NNB':
                 self._nnb_label(ctx, out, np.where(multi)[0])
+            elif itype == 'IDW' and nrst:
+                self._nrst(ctx, out, 'IDW', np.where(multi)[0], int(n_nebs),
+                           idw_exp=float(interp_args[i][3]), min_var_thr=float(min_var_thr))
             elif itype == 'IDW':
                 mean_steps = np.where(multi & ~steps_flags)[0]       # steps.py:312-313
                 if mean_steps.size:
                     self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
                 self._idw(ctx, out, np.where(multi & steps_flags)[0], float(interp_args[i][3]))
+            elif itype in ('OK', 'SK', 'EDK') and nrst:
+                uniq_vgs = list(dict.fromkeys(vgs))
+                vg_id = {v: k for k, v in enumerate(uniq_vgs)}
+                nug = np.array([check_full_nuggetness(v, min_vg_val) for v in uniq_vgs])
+                step_vg = np.array([vg_id[v] for v in vgs], dtype=np.int32)
+                self._nrst(ctx, out, itype, np.where(multi)[0], int(n_nebs), step_vg=step_vg,
+                           uniq_vgs=uniq_vgs, nug=nug, min_var_thr=float(min_var_thr),
+                           drft_arrs=drft_arrs if itype == 'EDK' else None,
+                           stns_drft=stns_drft if itype == 'EDK' else None)
             elif itype in ('OK', 'SK', 'EDK'):
                 uniq_vgs = list(dict.fromkeys(vgs))
                 vg_id = {v: k for k, v in enumerate(uniq_vgs)}
@@ -486,6 +522,110 @@ class ChunkEngine:
         self._count('launches')
         self._count('gemm_launches')
         self._count('gemm_flop', 2 * int(n_rows) * int(kpad) * ctx['n_cells'])
+
+    # ---- 'nrst' neighbour selection ---------------------------------------
+    def _topk(self, d_sx, d_sy, n_stn, d_mask, d_cx, d_cy, n_cells, k):
+        nb = torch.empty((n_cells, k), dtype=_I32, device=self.device)
+        hsh = torch.empty(n_cells, dtype=_I64, device=self.device)
+        _lib.check(self.lib.spx_nrst_topk_dev(
+            self._ptr(d_sx), self._ptr(d_sy), n_stn, self._ptr(d_mask), self._ptr(d_cx),
+            self._ptr(d_cy), n_cells, k, self._ptr(nb), self._ptr(hsh), self._stream()),
+            'nrst_topk')
+        self._count('launches')
+        return nb, hsh
+
+    def _nrst_groups(self, ctx, g, n_nebs):
+        """Neighbour rows and cell groups of availability group g, cached per
+        chunk (interp/grps.py:249-288 is called per group, steps.py:732)."""
+        key = ('nrst', int(g))
+        if key in ctx['nnb_cache']:
+            return ctx['nnb_cache'][key]
+        k = int(min(n_nebs, ctx['grp_n'][g]))
+        d_mask = self._dev(ctx['grp_mask'][g].astype(np.uint8))
+        nb, hsh = self._topk(ctx['d_stn_x'], ctx['d_stn_y'], ctx['n_stn'], d_mask,
+                             ctx['d_cell_x'], ctx['d_cell_y'], ctx['n_cells'], k)
+        uh, inv = torch.unique(hsh, return_inverse=True)
+        n_grp = int(uh.numel())
+        rep = torch.full((n_grp,), ctx['n_cells'], dtype=_I64, device=self.device)
+        rep.scatter_reduce_(0, inv, torch.arange(ctx['n_cells'], device=self.device), 'amin')
+        nbu = nb.index_select(0, rep).contiguous()
+        res = (k, nb, nbu, inv.to(_I32).contiguous(), n_grp)
+        ctx['nnb_cache'] = {kk: vv for kk, vv in ctx['nnb_cache'].items()
+                            if not (isinstance(kk, tuple) and kk and kk[0] == 'nrst')}
+        ctx['nnb_cache'][key] = res
+        return res
+
+    def _nrst(self, ctx, out, itype, steps, n_nebs, step_vg=None, uniq_vgs=None, nug=None,
+              idw_exp=0.0, min_var_thr=-np.inf, drft_arrs=None, stns_drft=None):
+        """Kriging / IDW with the k nearest available stations per cell
+        (interp/steps.py:740-833 with neb_sel_mthd == 'nrst')."""
+        if not steps.size:
+            return
+        lib = self.lib
+        n_cells, n_stn = ctx['n_cells'], ctx['n_stn']
+        grp_of_step = ctx['grp_of_step']
+        kind = _lib.KRG_KINDS.get(itype, 0)
+        n_drifts = 0
+        d_cell_drift = d_stn_drift = None
+        if itype == 'EDK':
+            n_drifts = int(np.asarray(stns_drft).shape[1])
+            d_cell_drift = self._dev(np.ascontiguousarray(drft_arrs, dtype=np.float64))
+            d_stn_drift = self._dev(np.ascontiguousarray(stns_drft, dtype=np.float64))
+        n_border = {'OK': 1, 'SK': 0, 'EDK': 1 + n_drifts}.get(itype, 0)
+
+        for g in np.unique(grp_of_step[steps]):
+            st_g = steps[grp_of_step[steps] == g]
+            k, nb, nbu, cell_grp, n_grp = self._nrst_groups(ctx, g, n_nebs)
+            N = _lib.spx_nrst()
+            N.n_grp = n_grp
+            N.n_cells = n_cells
+            N.k, N.n_border, N.n_drifts, N.kind, N.n_stn = k, n_border, n_drifts, kind, n_stn
+            N.nbu = nbu.data_ptr()
+            N.cell_grp = cell_grp.data_ptr()
+            N.stn_x = ctx['d_stn_x'].data_ptr()
+            N.stn_y = ctx['d_stn_y'].data_ptr()
+            N.stn_drift = d_stn_drift.data_ptr() if d_stn_drift is not None else None
+            N.cell_x = ctx['d_cell_x'].data_ptr()
+            N.cell_y = ctx['d_cell_y'].data_ptr()
+            N.cell_drift = d_cell_drift.data_ptr() if d_cell_drift is not None else None
+            N.min_vg_val = ctx['min_vg_val']
+            N.data = ctx['d_data'].data_ptr()
+            N.min_var_thr = float(min_var_thr)
+            N.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+            N.out = out.data_ptr()
+            N.out_ld = ctx['fld_size']
+            N.out_f64 = ctx['out_f64']
+            N.has_lo, N.has_hi, N.lo, N.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            N.idw_exp = float(idw_exp)
+            if itype == 'IDW':
+                d_steps = self._dev(st_g.astype(np.int32))
+                N.steps = d_steps.data_ptr()
+                N.n_t = int(st_g.size)
+                _lib.check(lib.spx_nrst_idw_dev(C.byref(N), self._ptr(nb), self._stream()),
+                           'nrst_idw')
+                self._count('launches')
+                continue
+            m = k + n_border
+            t_max = max(1, int(self.aux_limit // (n_grp * m * 8)) - 1)
+            for v in np.unique(step_vg[st_g]):
+                st_v = st_g[step_vg[st_g] == v]
+                N.vg = _lib.make_vg(uniq_vgs[int(v)])
+                for b0 in range(0, st_v.size, t_max):
+                    sb = st_v[b0:b0 + t_max]
+                    n_t = int(sb.size)
+                    d_steps = self._dev(sb.astype(np.int32))
+                    d_byp = self._dev(np.full(n_t, int(bool(nug[int(v)])), dtype=np.uint8))
+                    coef = torch.empty((n_grp, n_t + 1, m), dtype=_F64, device=self.device)
+                    ovr = torch.empty((n_grp, n_t), dtype=_F64, device=self.device)
+                    info = torch.zeros(n_grp, dtype=_I32, device=self.device)
+                    N.steps = d_steps.data_ptr()
+                    N.n_t = n_t
+                    N.step_bypass = d_byp.data_ptr()
+                    N.coef, N.ovr, N.info = coef.data_ptr(), ovr.data_ptr(), info.data_ptr()
+                    _lib.check(lib.spx_nrst_solve_dev(C.byref(N), self._stream()), 'nrst_solve')
+                    _lib.check(lib.spx_nrst_krige_dev(C.byref(N), self._stream()), 'nrst_krige')
+                    self._count('launches', 2)
+            self.stats['nrst_systems'] = self.stats.get('nrst_systems', 0) + n_grp
 
     # ---- IDW ------------------------------------------------------------
     def _idw(self, ctx, out, steps, idw_exp):

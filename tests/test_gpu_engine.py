@@ -43,7 +43,8 @@ def _check(got, exp, name):
         assert e <= _tol(lab), (name, lab, e)
 
 
-@pytest.mark.parametrize('name', ['a_ok_idw_nnb', 'c_edk_drift', 'd_sk_ok_mask_rows', 'g_idw_only'])
+@pytest.mark.parametrize('name', ['a_ok_idw_nnb', 'c_edk_drift', 'd_sk_ok_mask_rows', 'e_nrst',
+                                  'g_idw_only'])
 def test_golden_cases(eng, name):
     case, outs = load_case(name)
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **case)
@@ -134,3 +135,26 @@ def test_nnb_candidate_lists_and_full_scan_fallback(eng):
     exp, _ = orc.interp_chunk(interp_args=args, intrp_dtype=np.float64, **p)
     got, _ = eng.interp_chunk(interp_args=args, intrp_dtype=np.float64, **p)
     assert rel_err(got['NNB'], exp['NNB']) == 0.0
+
+
+def test_nrst_vs_oracle(eng):
+    """'nrst' neighbour selection: per-cell k nearest available stations, cells
+    grouped by neighbour set, small systems; OK / SK / EDK / IDW / NNB with missing
+    data, a low-value step (-> neighbour mean) and a nugget-only variogram."""
+    p = make_problem(31, 45, 7, 21, 17, cell=4000.0, miss=0.15)
+    cx, cy = p['cell_xs'], p['cell_ys']
+    p['data'][2, :] = np.where(np.isnan(p['data'][2, :]), np.nan, 0.02)
+    vgs = [VG_C1] * 7
+    vgs[4] = '0.2 Nug(0.0) + 0.8 Exp(30000)'
+    vgs[5] = '0.0 Nug(0.0)'
+    drft = np.vstack([200 + 0.003 * cx + 0.001 * cy + 30 * np.sin(cx / 9000.0)])
+    sdrft = np.column_stack([200 + 0.003 * p['stn_xs'] + 0.001 * p['stn_ys']
+                             + 30 * np.sin(p['stn_xs'] / 9000.0)])
+    args = [('OK', None, 'OK'), ('SK', None, 'SK'), ('EDK', None, 'EDK'),
+            ('IDW', None, 'IDW_000', 1.5), ('NNB', None, 'NNB')]
+    kw = dict(interp_args=args, vgs=vgs, neb_sel_mthd='nrst', n_nebs=9, min_var_thr=0.1,
+              min_var_cut=0.0, drft_arrs=drft, stns_drft=sdrft, **p)
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
+    _check(got, exp, 'nrst')
+    assert eng.stats.get('nrst_systems', 0) > 10
