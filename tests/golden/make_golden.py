@@ -249,6 +249,37 @@ def kats(im, misc):
     k.update(cp_arr=arr, cp_ri=ri, cp_ci=ci, cp_out=sub)
     for s in ['0.0 Nug(0.0)', '0.1 Nug(0.0) + 0.9 Sph(20000)', '0.00001 Nug(0.0) + 0.00002 Sph(20000)']:
         k['nugget__' + s] = np.array(misc.check_full_nuggetness(s, 1e-4))
+
+    # stand-alone kriging classes (pyx:251-765)
+    n_in, n_out = 14, 9
+    xi, yi = rng.uniform(0, 100, n_in), rng.uniform(0, 100, n_in)
+    zi = rng.gamma(1.0, 5.0, n_in)
+    xk, yk = rng.uniform(0, 100, n_out), rng.uniform(0, 100, n_out)
+    xk[0], yk[0] = xi[3], yi[3]                       # a target on top of a station
+    si = np.vstack([50 + 0.5 * xi + 0.1 * yi, np.cos(xi / 30.0)])
+    sk = np.vstack([50 + 0.5 * xk + 0.1 * yk, np.cos(xk / 30.0)])
+    model = '0.1 Nug(0.0) + 0.9 Sph(60)'
+    k.update(kc_xi=xi, kc_yi=yi, kc_zi=zi, kc_xk=xk, kc_yk=yk, kc_si=si, kc_sk=sk,
+             kc_model=np.array(model))
+    c = im.OrdinaryKriging(xi, yi, zi, xk, yk, model); c.krige()
+    k.update(ok_zk=c.zk, ok_lambdas=c.lambdas, ok_mus=c.mus, ok_est_vars=c.est_vars,
+             ok_rhss=c.rhss, ok_in_vars=c.in_vars)
+    c = im.SimpleKriging(xi, yi, zi, xk, yk, model); c.krige()
+    k.update(sk_zk=c.zk, sk_lambdas=c.lambdas, sk_est_covars=c.est_covars, sk_rhss=c.rhss,
+             sk_in_covars=c.in_covars)
+    c = im.ExternalDriftKriging(xi, yi, zi, si[0], xk, yk, sk[0], model); c.krige()
+    k.update(edk_zk=c.zk, edk_lambdas=c.lambdas, edk_mus_1=c.mus_1, edk_mus_2=c.mus_2)
+    c = im.ExternalDriftKriging_MD(xi, yi, zi, si, xk, yk, sk, model); c.krige()
+    k.update(md_zk=c.zk, md_lambdas=c.lambdas, md_mus_arr=c.mus_arr)
+    c = im.OrdinaryIndicatorKriging(xi, yi, zi, xk, yk, 4.0, model); c.ikrige()
+    k.update(oik_ik=c.ik, oik_est_vars=c.est_vars)
+    c = im.SimpleIndicatorKriging(xi, yi, zi, xk, yk, 4.0, model); c.ikrige()
+    k.update(sik_ik=c.ik, sik_est_covars=c.est_covars)
+    # the survey's known answer
+    c = im.OrdinaryKriging(np.array([0., 10., 0.]), np.array([0., 0., 10.]), np.array([1., 2., 4.]),
+                           np.array([5., 2.]), np.array([5., 1.]), '0.1 Nug(0.0) + 0.9 Sph(20)')
+    c.krige()
+    k.update(svy_zk=c.zk, svy_lambdas=c.lambdas, svy_mus=c.mus, svy_est_vars=c.est_vars)
     return k
 
 
@@ -273,6 +304,8 @@ def save_case(name, case, flds):
 def main():
     im, SpInterpSteps, misc = import_reference()
     np.savez_compressed(HERE / 'kats.npz', **kats(im, misc))
+    if '--kats-only' in sys.argv:
+        return
     for name, case in cases().items():
         flds = run_reference(SpInterpSteps, case)
         save_case(name, case, flds)
