@@ -197,6 +197,7 @@ typedef struct spx_rhs {
     double* resid;        /* [n_rhs] or NULL */
     double* dense;        /* optional: x also written to dense[rhs * dense_ld + i] */
     int64_t dense_ld;
+    int32_t coef_row_major; /* 0: packed fragment layout; 1: coef[row * kpad + col] */
 } spx_rhs;
 
 int spx_krige_solve_dev(const spx_systems* s, const spx_rhs* r, void* stream);
@@ -236,6 +237,7 @@ typedef struct spx_downdate {
     double* coef;
     double* resid;               /* [n_rhs] */
     int32_t* info;               /* [n_sys] */
+    int32_t coef_row_major;      /* 0: packed fragment layout; 1: coef[row * kpad + col] */
 } spx_downdate;
 
 int spx_krige_downdate_dev(const spx_downdate* d, void* stream);
@@ -403,6 +405,36 @@ int spx_nrst_solve_dev(const spx_nrst* n, void* stream);
 int spx_nrst_krige_dev(const spx_nrst* n, void* stream);
 /* Per cell: IDW over its own neighbour row nb[n_cells, k]. */
 int spx_nrst_idw_dev(const spx_nrst* n, const int32_t* nb, void* stream);
+
+/* Estimate with one variogram PER ROW (per-step variogram series):
+ *   Z[row, cell] = sum_k coef[row, k] * vg_{row_vg[row]}(dist(station k, cell)) + border
+ * coef is ROW-MAJOR [n_rows, kpad] here.  The distances of a 64-cell tile are
+ * computed once into shared memory and every row re-evaluates only its variogram
+ * on them (the tensor-core contraction would regenerate its whole operand tile
+ * per variogram). */
+typedef struct spx_multivg {
+    const double* coef;
+    int64_t n_rows;
+    int32_t kpad, n_stn, n_border;
+    const double* stn_x;
+    const double* stn_y;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    const double* cell_drift;
+    const spx_vg* vgs;         /* device table */
+    const int32_t* row_vg;     /* [n_rows] */
+    int32_t covar_flag;
+    double min_vg_val;
+    const int32_t* row_dst;    /* [n_rows] output row, < 0 skip */
+    void* out;
+    int64_t out_ld;
+    int32_t out_f64;
+    const int32_t* cell_pos;
+    int32_t has_lo, has_hi;
+    double lo, hi;
+} spx_multivg;
+int spx_estimate_multivg_dev(const spx_multivg* g, void* stream);
 
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field

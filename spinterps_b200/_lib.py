@@ -60,7 +60,7 @@ class spx_rhs(C.Structure):
                 ('rhs_row', C.c_void_p), ('data', C.c_void_p),
                 ('n_stn', C.c_int32), ('kpad', C.c_int32),
                 ('coef', C.c_void_p), ('resid', C.c_void_p),
-                ('dense', C.c_void_p), ('dense_ld', C.c_int64)]
+                ('dense', C.c_void_p), ('dense_ld', C.c_int64), ('coef_row_major', C.c_int32)]
 
 
 class spx_downdate(C.Structure):
@@ -71,7 +71,20 @@ class spx_downdate(C.Structure):
                 ('sys_rhs_off', C.c_void_p), ('sys_rhs_cnt', C.c_void_p),
                 ('rhs_urow', C.c_void_p), ('rhs_row', C.c_void_p), ('rhs_kind', C.c_void_p),
                 ('ut', C.c_void_p), ('kpad', C.c_int32), ('coef', C.c_void_p),
-                ('resid', C.c_void_p), ('info', C.c_void_p)]
+                ('resid', C.c_void_p), ('info', C.c_void_p), ('coef_row_major', C.c_int32)]
+
+
+class spx_multivg(C.Structure):
+    _fields_ = [('coef', C.c_void_p), ('n_rows', C.c_int64),
+                ('kpad', C.c_int32), ('n_stn', C.c_int32), ('n_border', C.c_int32),
+                ('stn_x', C.c_void_p), ('stn_y', C.c_void_p),
+                ('cell_x', C.c_void_p), ('cell_y', C.c_void_p), ('n_cells', C.c_int64),
+                ('cell_drift', C.c_void_p), ('vgs', C.c_void_p), ('row_vg', C.c_void_p),
+                ('covar_flag', C.c_int32), ('min_vg_val', C.c_double),
+                ('row_dst', C.c_void_p), ('out', C.c_void_p), ('out_ld', C.c_int64),
+                ('out_f64', C.c_int32), ('cell_pos', C.c_void_p),
+                ('has_lo', C.c_int32), ('has_hi', C.c_int32),
+                ('lo', C.c_double), ('hi', C.c_double)]
 
 
 class spx_nrst(C.Structure):
@@ -155,6 +168,7 @@ _SIGS = {
     'spx_fill_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_double, C.c_double, C.c_void_p]),
+    'spx_estimate_multivg_dev': (C.c_int, [C.POINTER(spx_multivg), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

@@ -91,6 +91,34 @@ __global__ void __launch_bounds__(256) k_fill_vg(const double* __restrict__ dist
     }
 }
 
+// Streaming variant for rectangular (dst <-> station) matrices and the
+// division-free variogram families: 4 elements per thread as two 16-byte
+// accesses in flight, 16 bytes of HBM traffic per element.
+__global__ void __launch_bounds__(256) k_fill_vg_fast(const double2* __restrict__ dists,
+                                                      double2* __restrict__ in_vars,
+                                                      int64_t n_pairs, int covar_flag,
+                                                      VgFast vg, double min_vg_val) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n_pairs;
+         i += stride) {
+        const double2 a = dists[i];
+        const bool two = (i + 1 < n_pairs);
+        const double2 b = two ? dists[i + 1] : a;
+        double2 ra, rb;
+        ra.x = vg_eval_fast(vg, a.x, covar_flag, min_vg_val);
+        ra.y = vg_eval_fast(vg, a.y, covar_flag, min_vg_val);
+        rb.x = vg_eval_fast(vg, b.x, covar_flag, min_vg_val);
+        rb.y = vg_eval_fast(vg, b.y, covar_flag, min_vg_val);
+        in_vars[i] = ra;
+        if (two) in_vars[i + 1] = rb;
+    }
+}
+
+// sub[r, c] = arr[row_idxs[r], col_idxs[c]]: threads walk the columns of a row
+// strip (coalesced stores, near-coalesced loads when the column list is mostly
+// contiguous); 4 rows per thread keep 4 independent loads in flight.
+constexpr int GA_ROWS = 4;
+
 __global__ void __launch_bounds__(256) k_gather_2d(const double* __restrict__ arr,
                                                    int64_t arr_cols,
                                                    const int64_t* __restrict__ row_idxs,
@@ -98,11 +126,18 @@ __global__ void __launch_bounds__(256) k_gather_2d(const double* __restrict__ ar
                                                    const int64_t* __restrict__ col_idxs,
                                                    int64_t n_cols, double* __restrict__ sub,
                                                    int64_t sub_cols) {
-    const int64_t n = n_rows * n_cols;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t r = i / n_cols, c = i - r * n_cols;
-        sub[r * sub_cols + c] = arr[row_idxs[r] * arr_cols + col_idxs[c]];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int64_t src_c = col_idxs[c];
+    for (int64_t r0 = (int64_t)blockIdx.y * GA_ROWS; r0 < n_rows;
+         r0 += (int64_t)gridDim.y * GA_ROWS) {
+        double v[GA_ROWS];
+#pragma unroll
+        for (int k = 0; k < GA_ROWS; ++k)
+            if (r0 + k < n_rows) v[k] = arr[row_idxs[r0 + k] * arr_cols + src_c];
+#pragma unroll
+        for (int k = 0; k < GA_ROWS; ++k)
+            if (r0 + k < n_rows) sub[(r0 + k) * sub_cols + c] = v[k];
     }
 }
 
@@ -307,6 +342,18 @@ int spx_fill_vg_var_arr_dev(const double* dists, double* in_vars, int64_t rows, 
         vg.ranges[i] = ranges[i];
     }
     const int64_t n = rows * cols;
+    const VgFast vf = make_vg_fast(n_terms, types, sills, ranges);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dists) | reinterpret_cast<uintptr_t>(in_vars)) & 15) == 0;
+    if (vf.all_fast && !diag_mat_flag && aligned && (n % 2 == 0)) {
+        const int64_t n_pairs = n / 2;
+        const int64_t want = (n_pairs / 2 + 255) / 256;
+        const int blocks = (int)(want < 148 * 32 ? (want < 1 ? 1 : want) : 148 * 32);
+        k_fill_vg_fast<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const double2*>(dists), reinterpret_cast<double2*>(in_vars), n_pairs,
+            covar_flag, vf, min_vg_val);
+        SPX_CHECK_LAUNCH("k_fill_vg_fast");
+        return SPX_OK;
+    }
     int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
     k_fill_vg<<<blocks, 256, 0, (cudaStream_t)stream>>>(dists, in_vars, rows, cols, covar_flag,
                                                         diag_mat_flag, vg, min_vg_val);
@@ -319,10 +366,12 @@ int spx_copy_2d_arr_at_idxs_dev(const double* arr, int64_t arr_cols, const int64
                                 double* subset_arr, int64_t subset_cols, void* stream) {
     const int64_t n = n_row_idxs * n_col_idxs;
     if (n == 0) return SPX_OK;
-    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    k_gather_2d<<<blocks, 256, 0, (cudaStream_t)stream>>>(arr, arr_cols, row_idxs, n_row_idxs,
-                                                          col_idxs, n_col_idxs, subset_arr,
-                                                          subset_cols);
+    const int64_t row_blocks = (n_row_idxs + GA_ROWS - 1) / GA_ROWS;
+    dim3 grid((unsigned)((n_col_idxs + 255) / 256),
+              (unsigned)(row_blocks < 65535 ? row_blocks : 65535));
+    k_gather_2d<<<grid, 256, 0, (cudaStream_t)stream>>>(arr, arr_cols, row_idxs, n_row_idxs,
+                                                        col_idxs, n_col_idxs, subset_arr,
+                                                        subset_cols);
     SPX_CHECK_LAUNCH("k_gather_2d");
     return SPX_OK;
 }

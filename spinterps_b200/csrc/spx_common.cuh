@@ -99,6 +99,94 @@ __device__ __forceinline__ double vg_eval(const VgDev& vg, double h, int covar_f
     return v;
 }
 
+// Per-term constants precomputed on the host so that the B-tile generator needs
+// no FP64 division: Sph s*(h*ca - h^3*cb), Exp/Gau s*(1 - exp(ca * h or h^2)),
+// Lin s*h*ca.  Same functions as cyth/interpmthds.pyx:46-70, operations
+// re-associated: (1.5*h)/r becomes h*(1.5/r) etc., a difference of a few ulp
+// (tests compare the drop-in fill at 1e-13, the estimates at 1e-9).  Pow / Hol /
+// Rng and the symmetric (diag) fill take the exact-expression path vg_eval().
+struct VgFast {
+    int n_terms;
+    int all_fast;  // every term is one of Nug / Sph / Exp / Lin / Gau
+    int types[SPX_VG_MAX_TERMS];
+    double sills[SPX_VG_MAX_TERMS];
+    double ranges[SPX_VG_MAX_TERMS];
+    double ca[SPX_VG_MAX_TERMS];
+    double cb[SPX_VG_MAX_TERMS];
+};
+
+__device__ __forceinline__ double vg_eval_fast(const VgFast& v, double h, int covar_flag,
+                                               double min_vg_val) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < v.n_terms; ++t) {
+        const int ty = v.types[t];
+        const double s = v.sills[t];
+        double g;
+        if (ty == SPX_VG_NUG) {
+            g = s;
+        } else if (ty == SPX_VG_SPH) {
+            const double h2 = h * h;
+            g = (h >= v.ranges[t]) ? s : s * (h * v.ca[t] - h2 * h * v.cb[t]);
+        } else if (ty == SPX_VG_EXP) {
+            g = s * (1.0 - exp(v.ca[t] * h));
+        } else if (ty == SPX_VG_GAU) {
+            g = s * (1.0 - exp(v.ca[t] * (h * h)));
+        } else {  // SPX_VG_LIN
+            g = (h > v.ranges[t]) ? s : s * (h * v.ca[t]);
+        }
+        acc += covar_flag ? (s - g) : g;
+    }
+    if (acc <= min_vg_val) acc = 0.0;
+    return acc;
+}
+
+inline VgFast make_vg_fast(int n_terms, const int* types, const double* sills,
+                             const double* ranges) {
+    VgFast f;
+    f.n_terms = n_terms;
+    f.all_fast = 1;
+    for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
+        const int ty = (t < n_terms) ? types[t] : SPX_VG_NUG;
+        const double r = (t < n_terms) ? ranges[t] : 1.0, sl = (t < n_terms) ? sills[t] : 0.0;
+        f.types[t] = ty;
+        f.sills[t] = sl;
+        f.ranges[t] = r;
+        f.ca[t] = f.cb[t] = 0.0;
+        if (t >= n_terms) continue;
+        switch (ty) {
+            case SPX_VG_NUG: break;
+            case SPX_VG_SPH: f.ca[t] = 1.5 / r; f.cb[t] = 1.0 / (2 * (r * r * r)); break;
+            case SPX_VG_EXP: f.ca[t] = -3.0 / r; break;
+            case SPX_VG_GAU: f.ca[t] = -3.0 / (r * r); break;
+            case SPX_VG_LIN: f.ca[t] = 1.0 / r; break;
+            default: f.all_fast = 0;
+        }
+    }
+    return f;
+}
+
+__device__ __forceinline__ VgFast make_vg_fast_dev(const spx_vg& v) {
+    VgFast f;
+    f.n_terms = v.n_terms;
+    f.all_fast = 1;
+    for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
+        const int ty = (t < v.n_terms) ? v.types[t] : SPX_VG_NUG;
+        const double r = (t < v.n_terms) ? v.ranges[t] : 1.0;
+        f.types[t] = ty;
+        f.sills[t] = (t < v.n_terms) ? v.sills[t] : 0.0;
+        f.ranges[t] = r;
+        f.ca[t] = f.cb[t] = 0.0;
+        if (t >= v.n_terms) continue;
+        if (ty == SPX_VG_SPH) { f.ca[t] = 1.5 / r; f.cb[t] = 1.0 / (2 * (r * r * r)); }
+        else if (ty == SPX_VG_EXP) f.ca[t] = -3.0 / r;
+        else if (ty == SPX_VG_GAU) f.ca[t] = -3.0 / (r * r);
+        else if (ty == SPX_VG_LIN) f.ca[t] = 1.0 / r;
+        else if (ty != SPX_VG_NUG) f.all_fast = 0;
+    }
+    return f;
+}
+
 __device__ __forceinline__ double clampd(double v, int has_lo, int has_hi, double lo, double hi) {
     // NaN-safe like interp/steps.py:466-476 (comparisons with NaN are false)
     if (has_lo && v < lo) v = lo;

@@ -29,47 +29,6 @@ constexpr int BK = 8;                          // k per pipeline stage
 constexpr int STAGE_DOUBLES = SPX_BM * BK;     // 2048 doubles = 16 KB
 constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
 
-// Per-term constants precomputed on the host so that the B-tile generator needs
-// no FP64 division: Sph s*(h*ca - h^3*cb), Exp/Gau s*(1 - exp(ca * h or h^2)),
-// Lin s*h*ca.  Same functions as cyth/interpmthds.pyx:46-70, operations
-// re-associated (differences ~1 ulp, far inside the 1e-9 estimate tolerance; the
-// drop-in spx_fill_vg_var_arr keeps the reference's exact expression order).
-struct VgFast {
-    int n_terms;
-    int all_fast;  // every term is one of Nug / Sph / Exp / Lin / Gau
-    int types[SPX_VG_MAX_TERMS];
-    double sills[SPX_VG_MAX_TERMS];
-    double ranges[SPX_VG_MAX_TERMS];
-    double ca[SPX_VG_MAX_TERMS];
-    double cb[SPX_VG_MAX_TERMS];
-};
-
-__device__ __forceinline__ double vg_eval_fast(const VgFast& v, double h, int covar_flag,
-                                               double min_vg_val) {
-    double acc = 0.0;
-#pragma unroll 1
-    for (int t = 0; t < v.n_terms; ++t) {
-        const int ty = v.types[t];
-        const double s = v.sills[t];
-        double g;
-        if (ty == SPX_VG_NUG) {
-            g = s;
-        } else if (ty == SPX_VG_SPH) {
-            const double h2 = h * h;
-            g = (h >= v.ranges[t]) ? s : s * (h * v.ca[t] - h2 * h * v.cb[t]);
-        } else if (ty == SPX_VG_EXP) {
-            g = s * (1.0 - exp(v.ca[t] * h));
-        } else if (ty == SPX_VG_GAU) {
-            g = s * (1.0 - exp(v.ca[t] * (h * h)));
-        } else {  // SPX_VG_LIN
-            g = (h > v.ranges[t]) ? s : s * (h * v.ca[t]);
-        }
-        acc += covar_flag ? (s - g) : g;
-    }
-    if (acc <= min_vg_val) acc = 0.0;
-    return acc;
-}
-
 struct GemmArgs {
     const double* coef;
     int64_t n_rows;
@@ -550,25 +509,7 @@ int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
     a.gen = g->gen;
     a.covar_flag = g->covar_flag;
     a.vg = to_dev(g->vg);
-    a.vgf.n_terms = g->vg.n_terms;
-    a.vgf.all_fast = 1;
-    for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
-        const int ty = (t < g->vg.n_terms) ? g->vg.types[t] : SPX_VG_NUG;
-        const double r = g->vg.ranges[t], sl = g->vg.sills[t];
-        a.vgf.types[t] = ty;
-        a.vgf.sills[t] = sl;
-        a.vgf.ranges[t] = r;
-        a.vgf.ca[t] = a.vgf.cb[t] = 0.0;
-        if (t >= g->vg.n_terms) continue;
-        switch (ty) {
-            case SPX_VG_NUG: break;
-            case SPX_VG_SPH: a.vgf.ca[t] = 1.5 / r; a.vgf.cb[t] = 1.0 / (2 * (r * r * r)); break;
-            case SPX_VG_EXP: a.vgf.ca[t] = -3.0 / r; break;
-            case SPX_VG_GAU: a.vgf.ca[t] = -3.0 / (r * r); break;
-            case SPX_VG_LIN: a.vgf.ca[t] = 1.0 / r; break;
-            default: a.vgf.all_fast = 0;
-        }
-    }
+    a.vgf = make_vg_fast(g->vg.n_terms, g->vg.types, g->vg.sills, g->vg.ranges);
     a.min_vg_val = g->min_vg_val;
     a.idw_exp = g->idw_exp;
     a.inv_scale = (g->gen == SPX_GEN_IDW) ? 1.0 / g->dist_scale : 1.0;

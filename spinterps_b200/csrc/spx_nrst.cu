@@ -470,3 +470,192 @@ int spx_nrst_idw_dev(const spx_nrst* n, const int32_t* nb, void* stream) {
 }
 
 }  // extern "C"
+
+// ===========================================================================
+// Estimate with ONE VARIOGRAM PER ROW (per-step variogram series, config 3):
+//     Z[row, cell] = sum_k coef[row, k] * vg_row(dist(station k, cell))  (+ border)
+// The contraction kernel of spx_gemm.cu regenerates its right-hand-side tile for
+// every variogram, i.e. one sqrt + evaluation per (row, station, cell).  Here the
+// DISTANCES of a cell tile are computed once into shared memory ([k][cell], 64
+// cells) and every row only re-evaluates its variogram on them: 4 threads per
+// cell split the stations, 4 rows are processed per pass so that each distance
+// read feeds 4 evaluations.  FP64 ALU bound (no tensor-core shape: the operand
+// changes with the row).
+namespace spx {
+
+constexpr int MV_CELLS = 64;
+constexpr int MV_KQ = 4;       // threads per cell
+constexpr int MV_ROWS = 4;     // rows per pass
+
+struct MultiVgArgs {
+    const double* coef;        // [n_rows, kpad] row-major
+    int64_t n_rows;
+    int kpad, n_stn, n_border;
+    const double* stn_x;
+    const double* stn_y;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    const double* cell_drift;
+    const spx_vg* vgs;         // device table
+    const int32_t* row_vg;     // [n_rows]
+    int covar_flag;
+    double min_vg_val;
+    const int32_t* row_dst;
+    void* out;
+    int64_t out_ld;
+    int out_f64;
+    const int32_t* cell_pos;
+    int has_lo, has_hi;
+    double lo, hi;
+};
+
+__global__ void __launch_bounds__(MV_CELLS * MV_KQ) k_estimate_multivg(MultiVgArgs a) {
+    extern __shared__ double msm[];
+    const int kp = a.n_stn + a.n_border;                 // used K
+    double* D = msm;                                     // [kp][MV_CELLS] distances / border values
+    double* Cs = D + (size_t)kp * MV_CELLS;              // [MV_ROWS][kp] coefficient rows
+    double* Ps = Cs + (size_t)MV_ROWS * kp;              // [MV_ROWS][MV_KQ][MV_CELLS] partial sums
+    __shared__ VgFast vf[MV_ROWS];
+    __shared__ VgDev vd[MV_ROWS];
+    const int tid = threadIdx.x;
+    const int cl = tid % MV_CELLS, kq = tid / MV_CELLS;
+    const int64_t n_tiles = (a.n_cells + MV_CELLS - 1) / MV_CELLS;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t c = tile * MV_CELLS + cl;
+        const bool cell_ok = c < a.n_cells;
+        const double x = cell_ok ? a.cell_x[c] : 0.0, y = cell_ok ? a.cell_y[c] : 0.0;
+        __syncthreads();
+        for (int k = kq; k < kp; k += MV_KQ) {
+            double v;
+            if (k < a.n_stn) {
+                const double dx = x - a.stn_x[k], dy = y - a.stn_y[k];
+                v = sqrt(dx * dx + dy * dy);
+            } else {
+                const int b = k - a.n_stn;
+                v = (b == 0) ? 1.0 : (cell_ok ? a.cell_drift[(int64_t)(b - 1) * a.n_cells + c] : 0.0);
+            }
+            D[(size_t)k * MV_CELLS + cl] = v;
+        }
+        for (int64_t r0 = 0; r0 < a.n_rows; r0 += MV_ROWS) {
+            const int nr = (int)min((int64_t)MV_ROWS, a.n_rows - r0);
+            __syncthreads();   // D ready / previous pass consumed
+            for (int idx = tid; idx < nr * kp; idx += MV_CELLS * MV_KQ) {
+                const int rr = idx / kp, k = idx - rr * kp;
+                Cs[(size_t)rr * kp + k] = a.coef[(r0 + rr) * (int64_t)a.kpad + k];
+            }
+            if (tid < nr) {
+                const spx_vg& v = a.vgs[a.row_vg[r0 + tid]];
+                vf[tid] = make_vg_fast_dev(v);
+                vd[tid].n_terms = v.n_terms;
+                for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
+                    vd[tid].types[t] = v.types[t];
+                    vd[tid].sills[t] = v.sills[t];
+                    vd[tid].ranges[t] = v.ranges[t];
+                }
+            }
+            __syncthreads();
+            double acc[MV_ROWS];
+#pragma unroll
+            for (int rr = 0; rr < MV_ROWS; ++rr) acc[rr] = 0.0;
+            for (int k = kq; k < a.n_stn; k += MV_KQ) {
+                const double h = D[(size_t)k * MV_CELLS + cl];
+#pragma unroll
+                for (int rr = 0; rr < MV_ROWS; ++rr) {
+                    if (rr < nr) {
+                        const double g = vf[rr].all_fast
+                                             ? vg_eval_fast(vf[rr], h, a.covar_flag, a.min_vg_val)
+                                             : vg_eval(vd[rr], h, a.covar_flag, a.min_vg_val);
+                        acc[rr] = fma(Cs[(size_t)rr * kp + k], g, acc[rr]);
+                    }
+                }
+            }
+            for (int k = a.n_stn + kq; k < kp; k += MV_KQ) {
+                const double bv = D[(size_t)k * MV_CELLS + cl];
+#pragma unroll
+                for (int rr = 0; rr < MV_ROWS; ++rr)
+                    if (rr < nr) acc[rr] = fma(Cs[(size_t)rr * kp + k], bv, acc[rr]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < MV_ROWS; ++rr)
+                Ps[((size_t)rr * MV_KQ + kq) * MV_CELLS + cl] = acc[rr];
+            __syncthreads();
+            // MV_ROWS x MV_CELLS results, one per thread
+            {
+                const int rr = tid / MV_CELLS;   // MV_ROWS == MV_KQ
+                if (rr < nr && cell_ok) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = 0; q < MV_KQ; ++q) v += Ps[((size_t)rr * MV_KQ + q) * MV_CELLS + cl];
+                    const int dst = a.row_dst[r0 + rr];
+                    if (dst >= 0) {
+                        v = clampd(v, a.has_lo, a.has_hi, a.lo, a.hi);
+                        const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+                        store_out(a.out, (int64_t)dst * a.out_ld + col, v, a.out_f64);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace spx
+
+extern "C" int spx_estimate_multivg_dev(const spx_multivg* g, void* stream) {
+    using namespace spx;
+    if (!g) {
+        set_error("estimate_multivg: null argument");
+        return SPX_EINVAL;
+    }
+    if (g->n_rows == 0 || g->n_cells == 0) return SPX_OK;
+    if (g->kpad < g->n_stn + g->n_border || (g->n_border > 1 && !g->cell_drift)) {
+        set_error("estimate_multivg: bad kpad / drift");
+        return SPX_EINVAL;
+    }
+    MultiVgArgs a;
+    a.coef = g->coef;
+    a.n_rows = g->n_rows;
+    a.kpad = g->kpad;
+    a.n_stn = g->n_stn;
+    a.n_border = g->n_border;
+    a.stn_x = g->stn_x;
+    a.stn_y = g->stn_y;
+    a.cell_x = g->cell_x;
+    a.cell_y = g->cell_y;
+    a.n_cells = g->n_cells;
+    a.cell_drift = g->cell_drift;
+    a.vgs = g->vgs;
+    a.row_vg = g->row_vg;
+    a.covar_flag = g->covar_flag;
+    a.min_vg_val = g->min_vg_val;
+    a.row_dst = g->row_dst;
+    a.out = g->out;
+    a.out_ld = g->out_ld;
+    a.out_f64 = g->out_f64;
+    a.cell_pos = g->cell_pos;
+    a.has_lo = g->has_lo;
+    a.has_hi = g->has_hi;
+    a.lo = g->lo;
+    a.hi = g->hi;
+    const int kp = g->n_stn + g->n_border;
+    const size_t smem = ((size_t)kp * MV_CELLS + (size_t)MV_ROWS * kp +
+                         (size_t)MV_ROWS * MV_KQ * MV_CELLS) * sizeof(double);
+    int dev = 0, max_smem = 0, n_sm = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SPX_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (smem + 4096 > (size_t)max_smem) {
+        set_error("estimate_multivg: %d stations do not fit in shared memory", g->n_stn);
+        return SPX_ENOMEM;
+    }
+    SPX_CUDA(cudaFuncSetAttribute(k_estimate_multivg, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int64_t tiles = (g->n_cells + MV_CELLS - 1) / MV_CELLS;
+    const int per_sm = (int)((size_t)max_smem / (smem + 4096));
+    const int64_t want = (int64_t)n_sm * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    const int grid = (int)(tiles < want ? tiles : want);
+    k_estimate_multivg<<<grid, MV_CELLS * MV_KQ, smem, (cudaStream_t)stream>>>(a);
+    SPX_CHECK_LAUNCH("k_estimate_multivg");
+    return SPX_OK;
+}

@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(256) k_lu_solve(spx_systems s, spx_rhs r) {
     if (row >= 0) {
         for (int i = tid; i < m; i += 256) {
             const int col = (i < n) ? stn[i] : (r.n_stn + (i - n));
-            r.coef[coef_offset(row, col, r.kpad)] = b[i];
+            r.coef[r.coef_row_major ? row * (int64_t)r.kpad + col
+                                    : coef_offset(row, col, r.kpad)] = b[i];
         }
     }
     if (r.dense != nullptr)
@@ -574,7 +575,9 @@ __global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
                 if (w >= nb) break;
                 const int64_t q = q0 + base + w;
                 const int64_t row = d.rhs_row[q];
-                if (row >= 0) d.coef[coef_offset(row, ki, d.kpad)] = acc[w];
+                if (row >= 0)
+                    d.coef[d.coef_row_major ? row * (int64_t)d.kpad + ki
+                                            : coef_offset(row, ki, d.kpad)] = acc[w];
                 if (d.rhs_kind[q] == 1)
                     atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
             }

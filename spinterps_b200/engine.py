@@ -110,6 +110,7 @@ class ChunkEngine:
         self.downdate_min_systems = 4
         # full-system inverses are reused across chunks with the same stations and
         # variogram (they do not depend on the data)
+        self.multivg = True      # per-row-variogram estimator for variogram series
         self.ginv_cache = True
         self.ginv_cache_size = 8
         self._ginv_cache = {}
@@ -733,9 +734,20 @@ class ChunkEngine:
             seg_row0[k] = acc
             acc += _pad_up(seg_cnt[k], _lib.SPX_BM)
         total_rows = acc
+        # Many variograms with few steps each (per-step variogram series): the
+        # contraction would regenerate its operand tile per variogram; use the
+        # per-row-variogram estimator (row-major coefficients) instead.
+        mv_smem = ((n_stn + n_border) * 64 + 4 * (n_stn + n_border) + 1024) * 8 + 4096
+        K.use_mv = bool(self.multivg and seg_vgs.size >= 8
+                        and K.steps_o.size / seg_vgs.size < 32 and mv_smem <= 220 * 1024)
         K.row_of = np.empty(K.steps_o.size, dtype=np.int64)
-        for k in range(seg_vgs.size):
-            K.row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = seg_row0[k] + np.arange(seg_cnt[k])
+        if K.use_mv:
+            K.row_of[:] = np.arange(K.steps_o.size)
+            total_rows = K.steps_o.size
+        else:
+            for k in range(seg_vgs.size):
+                K.row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = (
+                    seg_row0[k] + np.arange(seg_cnt[k]))
         K.coef = torch.zeros(total_rows * kpad, dtype=_F64, device=self.device)
         row_dst_np = np.full(total_rows, -1, dtype=np.int32)
         row_dst_np[K.row_of] = K.steps_o
@@ -782,8 +794,34 @@ class ChunkEngine:
         K.flags_event = torch.cuda.Event()
         K.flags_event.record(torch.cuda.current_stream(self.device))
 
+        if K.use_mv:
+            d_row_vg = self._dev(step_vg[K.steps_o].astype(np.int32))
+            g = _lib.spx_multivg()
+            g.coef = K.coef.data_ptr()
+            g.n_rows = int(K.steps_o.size)
+            g.kpad, g.n_stn, g.n_border = kpad, n_stn, n_border
+            g.stn_x, g.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
+            g.cell_x, g.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
+            g.n_cells = n_cells
+            g.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
+            g.vgs = K.d_vgs.data_ptr()
+            g.row_vg = d_row_vg.data_ptr()
+            g.covar_flag = int(kind == 1)
+            g.min_vg_val = ctx['min_vg_val']
+            g.row_dst = d_row_dst.data_ptr()
+            g.out = out.data_ptr()
+            g.out_ld = ctx['fld_size']
+            g.out_f64 = ctx['out_f64']
+            g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+            g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            with self._phase('multivg'):
+                _lib.check(self.lib.spx_estimate_multivg_dev(C.byref(g), self._stream()),
+                           'estimate_multivg')
+            self._count('launches')
+            self._count('multivg_evals', int(K.steps_o.size) * n_stn * n_cells)
+
         # ---- main contraction: one launch per variogram segment ----------
-        for k in range(seg_vgs.size):
+        for k in range(seg_vgs.size if not K.use_mv else 0):
             seg_coef = K.coef[seg_row0[k] * kpad:]
             with self._phase('gemm'):
                 self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad,
@@ -925,7 +963,7 @@ class ChunkEngine:
         self._count('lu_flop', int((2 * T.m ** 3 // 3).sum()))
 
     def _lu_solve(self, ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, coef, want_resid=False,
-                  dense=None, dense_ld=0):
+                  dense=None, dense_ld=0, row_major=False):
         n_rhs = len(rhs_sys)
         resid = torch.zeros(n_rhs, dtype=_F64, device=self.device) if want_resid else None
         ts = [self._dev(np.asarray(rhs_sys, dtype=np.int32)),
@@ -942,6 +980,7 @@ class ChunkEngine:
         R.resid = resid.data_ptr() if resid is not None else None
         R.dense = dense.data_ptr() if dense is not None else None
         R.dense_ld = int(dense_ld)
+        R.coef_row_major = int(bool(row_major))
         _lib.check(self.lib.spx_krige_solve_dev(C.byref(T.S), C.byref(R), self._stream()), 'solve')
         self._count('launches')
         return resid
@@ -980,7 +1019,7 @@ class ChunkEngine:
             resid = None
             if rhs_sys.size:
                 resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
-                                       want_resid=want_resid)
+                                       want_resid=want_resid, row_major=K.use_mv)
             for k, sid in enumerate(ids):
                 K.keep[int(sid)] = (T, k)
 
@@ -1109,6 +1148,7 @@ class ChunkEngine:
             D.ut = Ut.data_ptr()
             D.kpad = K.kpad
             D.coef = K.coef.data_ptr()
+            D.coef_row_major = int(K.use_mv)
             D.resid = d_resid.data_ptr()
             D.info = d_info.data_ptr()
             _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')

@@ -158,3 +158,35 @@ def test_nrst_vs_oracle(eng):
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
     _check(got, exp, 'nrst')
     assert eng.stats.get('nrst_systems', 0) > 10
+
+
+def test_per_step_variograms_multivg(eng):
+    """One variogram per step (config 3 style): the per-row-variogram estimator
+    (distances of a cell tile shared by all rows) with OK, EDK and SK, missing
+    data (downdated and direct systems), a mask and every variogram family."""
+    p = make_problem(41, 50, 14, 23, 19, cell=3000.0, miss=0.1)
+    rng = np.random.default_rng(5)
+    fam = ['Sph', 'Exp', 'Gau', 'Lin', 'Hol', 'Pow']
+    vgs = []
+    for t in range(14):
+        f = fam[t % len(fam)]
+        rg = rng.uniform(1.5e4, 5e4) if f != 'Pow' else 0.5
+        sill = rng.uniform(0.5, 1.5) if f != 'Pow' else 0.002
+        vgs.append('%0.5f Nug(0.0) + %0.5f %s(%0.5f)' % (rng.uniform(0.15, 0.3), sill, f, rg))
+    cx, cy = p['cell_xs'], p['cell_ys']
+    mask = (cx + 0.7 * cy) < 6.0e4
+    drft = (100 + 0.002 * cx + 0.001 * cy)[None, mask]
+    sdrft = (100 + 0.002 * p['stn_xs'] + 0.001 * p['stn_ys'])[:, None]
+    p['cell_xs'], p['cell_ys'] = cx[mask], cy[mask]
+    args = [('OK', None, 'OK'), ('SK', None, 'SK'), ('EDK', None, 'EDK')]
+    kw = dict(interp_args=args, vgs=vgs, cntn_idxs=mask, drft_arrs=drft, stns_drft=sdrft, **p)
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
+    assert eng.stats.get('multivg_evals', 0) > 0
+    for lab, ref in exp.items():
+        e = rel_err(got[lab], ref, _floor(ref))
+        # Gau / Hol systems are moderately ill-conditioned (cond ~1e5-1e6)
+        assert e <= 5e-8, (lab, e)
+        per_step = [rel_err(got[lab][t], ref[t], _floor(ref)) for t in range(14)]
+        good = [per_step[t] for t in range(14) if fam[t % 6] in ('Sph', 'Exp', 'Lin')]
+        assert max(good) <= KRG_TOL, (lab, per_step)
