@@ -111,6 +111,7 @@ class ChunkEngine:
         # full-system inverses are reused across chunks with the same stations and
         # variogram (they do not depend on the data)
         self.multivg = True      # per-row-variogram estimator for variogram series
+        self.pinv_flagged = True  # np.linalg.pinv semantics for untrustworthy OK/EDK systems
         self.ginv_cache = True
         self.ginv_cache_size = 8
         self._ginv_cache = {}
@@ -882,6 +883,68 @@ class ChunkEngine:
 
         return deferred
 
+    # ---- pseudo-inverse path for numerically singular systems ---------------
+    def _pinv_systems(self, ctx, out, K, sids, sv, v, coef_a):
+        """np.linalg.pinv semantics (rcond = 1e-15) through a symmetric
+        eigendecomposition on the device.  Rewrites the estimates of the steps of
+        the listed systems and puts pinv(A) [1; 0] into the rows of ``coef_a`` that
+        the caller contracts for the sum(lambda) test.  Rare path (cuSOLVER syevd
+        via torch.linalg.eigh)."""
+        n_stn, kpad = ctx['n_stn'], K.kpad
+        rows_all, cols_all, step_all = [], [], []
+        blocks = []
+        for sid in sids:
+            sid = int(sid)
+            n = int(K.sys_n[sid])
+            m = n + K.n_border
+            T = self._systems_struct(ctx, K, np.array([sid]), K.sys_grp[[sid]], K.sys_vg[[sid]])
+            _lib.check(self.lib.spx_krige_assemble_dev(
+                C.byref(T.S), self._ptr(K.d_vgs), len(K.uniq_vgs), ctx['min_vg_val'],
+                self._stream()), 'assemble')
+            self._count('launches')
+            A = T.work.view(m, m)
+            A = 0.5 * (A + A.T)
+            w, V = torch.linalg.eigh(A)
+            big = w.abs() > 1e-15 * w.abs().max()
+            winv = torch.where(big, 1.0 / torch.where(big, w, torch.ones_like(w)),
+                               torch.zeros_like(w))
+            pinv = (V * winv[None, :]) @ V.T
+            stn = np.where(ctx['grp_mask'][int(K.sys_grp[sid])])[0]
+            cols = self._dev(np.concatenate([stn, n_stn + np.arange(K.n_border)]).astype(np.int64))
+            ridx = K.rows_by_sys[K.sys_row_beg[sid]:K.sys_row_beg[sid + 1]]
+            st = K.steps_o[ridx]
+            d_st = self._dev(st.astype(np.int64))
+            d_stn = self._dev(stn.astype(np.int64))
+            self._sync_uploads()
+            B = torch.zeros((st.size + 1, m), dtype=_F64, device=self.device)
+            B[:st.size, :n] = ctx['d_data'].index_select(0, d_st).index_select(1, d_stn)
+            B[st.size, :n] = 1.0
+            Csol = B @ pinv                                   # pinv is symmetric
+            full = torch.zeros((st.size + 1, kpad), dtype=_F64, device=self.device)
+            full[:, cols] = Csol
+            blocks.append((full, st, int(np.searchsorted(sv, sid))))
+            self._count('pinv_systems')
+        # data rows of all listed systems: one packed segment, one contraction
+        n_rows = sum(b[1].size for b in blocks)
+        if n_rows:
+            dense = torch.cat([b[0][:-1] for b in blocks], dim=0).contiguous()
+            coef_p = torch.zeros(_pad_up(n_rows, _lib.SPX_BM) * kpad, dtype=_F64,
+                                 device=self.device)
+            _lib.check(self.lib.spx_pack_rows_dev(
+                self._ptr(dense), kpad, None, n_rows, kpad, kpad, 0, self._ptr(coef_p), 0,
+                self._stream()), 'pack_rows')
+            d_dst = self._dev(np.concatenate([b[1] for b in blocks]).astype(np.int32))
+            self._gemm(ctx, coef=coef_p, n_rows=n_rows, kpad=kpad, n_border=K.n_border,
+                       gen=_lib.GEN_VG, epi=_lib.EPI_FIELD, row_dst=d_dst, out=out,
+                       vg=_lib.make_vg(K.uniq_vgs[v]), covar_flag=int(K.kind == 1),
+                       cell_drift=K.d_cell_drift)
+        # ones-vector rows into the caller's segment
+        for full, st, row in blocks:
+            _lib.check(self.lib.spx_pack_rows_dev(
+                self._ptr(full[-1:].contiguous()), kpad, None, 1, kpad, kpad, 0,
+                self._ptr(coef_a), row, self._stream()), 'pack_rows')
+        self._count('launches', 1 + len(blocks))
+
     # ---- OK estimation variance (weights form) -----------------------------
     def _est_vars(self, ctx, K, ev_out):
         """est_var = rhs' A^-1 rhs + lambda[n] per (system, cell)
@@ -1182,14 +1245,26 @@ class ChunkEngine:
             n_f = fb.size
             fail = torch.ones((n_f, n_cells), dtype=torch.uint8, device=self.device)
             aux = torch.empty((n_f, n_cells), dtype=_F64, device=self.device)
-            ok = fb[~singular[fb]]
+            # OK / EDK systems end up here only when LU cannot be trusted (zero pivot or
+            # a large ones-vector residual): redo them with the reference's own
+            # operator, the SVD pseudo-inverse with rcond = 1e-15 (np.linalg.pinv,
+            # steps.py:351) -- for the symmetric A it is V diag(1/w) V' over the
+            # eigenvalues with |w| > rcond * max|w| -- so that truncated systems give
+            # the reference's weights, its sum(lambda) verdict and its estimates.
+            use_pinv = np.zeros(flagged.size, dtype=bool)
+            if K.kind != 1 and self.pinv_flagged:
+                use_pinv[fb] = True
+            ok = fb[~singular[fb] | use_pinv[fb]]
             for v in np.unique(K.sys_vg[ok]):
                 sv = ok[K.sys_vg[ok] == v]
                 coef_a = torch.zeros(_pad_up(sv.size, _lib.SPX_BM) * K.kpad, dtype=_F64,
                                      device=self.device)
+                sv_lu = sv[~use_pinv[sv]]
+                sv_pi = sv[use_pinv[sv]]
                 # ones-vector solutions, grouped by the kept factor batch
                 by_T = {}
-                for row, s in enumerate(sv):
+                for s in sv_lu:
+                    row = int(np.searchsorted(sv, s))
                     T, k = K.keep[int(s)]
                     by_T.setdefault(id(T), (T, [], []))
                     by_T[id(T)][1].append(k)
@@ -1197,6 +1272,8 @@ class ChunkEngine:
                 for T, ks, rows in by_T.values():
                     self._lu_solve(ctx, K, T, ks, np.ones(len(ks)), np.zeros(len(ks)), rows,
                                    coef_a)
+                if sv_pi.size:
+                    self._pinv_systems(ctx, out, K, sv_pi, sv, int(v), coef_a)
                 d_slots = self._dev(np.searchsorted(fb, sv).astype(np.int32))
                 self._gemm(ctx, coef=coef_a, n_rows=int(sv.size), kpad=K.kpad,
                            n_border=K.n_border, gen=_lib.GEN_VG, epi=_lib.EPI_AUX,
@@ -1232,7 +1309,7 @@ class ChunkEngine:
                     self._ptr(d_rf), n_cells, self._ptr(ctx['d_pos']), self._ptr(K.ev_out),
                     ctx['fld_size'], ctx['out_f64'], self._stream()), 'bcast_rows(zero)')
                 self._count('launches')
-            for s in fb[singular[fb]]:
+            for s in fb[singular[fb] & ~use_pinv[fb]]:
                 for t in K.steps_o[K.sys_o == s]:
                     if int(t) not in problem_steps:
                         problem_steps.append(int(t))
