@@ -433,6 +433,7 @@ typedef struct spx_multivg {
     const int32_t* cell_pos;
     int32_t has_lo, has_hi;
     double lo, hi;
+    int32_t all_fast;          /* every variogram uses only Nug/Sph/Exp/Lin/Gau terms */
 } spx_multivg;
 int spx_estimate_multivg_dev(const spx_multivg* g, void* stream);
 

@@ -84,7 +84,7 @@ class spx_multivg(C.Structure):
                 ('row_dst', C.c_void_p), ('out', C.c_void_p), ('out_ld', C.c_int64),
                 ('out_f64', C.c_int32), ('cell_pos', C.c_void_p),
                 ('has_lo', C.c_int32), ('has_hi', C.c_int32),
-                ('lo', C.c_double), ('hi', C.c_double)]
+                ('lo', C.c_double), ('hi', C.c_double), ('all_fast', C.c_int32)]
 
 
 class spx_nrst(C.Structure):

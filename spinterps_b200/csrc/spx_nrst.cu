@@ -487,6 +487,76 @@ constexpr int MV_CELLS = 64;
 constexpr int MV_KQ = 4;       // threads per cell
 constexpr int MV_ROWS = 4;     // rows per pass
 
+// A variogram "compiled" for the inner loop: no per-term type dispatch and no
+// divisions.  Two closed forms cover the common families:
+//   polynomial  s * (hc * ca - hc^3 * cb), hc = min(h, r)   Sph (cb = 1/(2 r^3)) and
+//                                                           Lin (cb = 0); at h >= r it
+//                                                           gives s * (1.5 - 0.5) = s
+//   exponential s * (1 - exp(ca * x)), x = h or h^2         Exp / Gau
+// Nug terms are summed.  At most two terms of each form; anything else (Pow, Hol,
+// Rng, longer nests) takes the generic vg_eval().
+struct RowP {
+    double nug, tot;
+    double ps[2], pr[2], pca[2], pcb[2];
+    double es[2], eca[2];
+    int esq[2];
+    int np, ne, ok;
+};
+
+__device__ __forceinline__ void build_row_p(RowP& o, const spx_vg& v) {
+    o.nug = 0.0;
+    o.tot = 0.0;
+    o.np = o.ne = 0;
+    o.ok = 1;
+    for (int i = 0; i < 2; ++i) {
+        o.ps[i] = o.pca[i] = o.pcb[i] = o.es[i] = o.eca[i] = 0.0;
+        o.pr[i] = 1.0;
+        o.esq[i] = 0;
+    }
+    for (int t = 0; t < v.n_terms; ++t) {
+        const int ty = v.types[t];
+        const double sl = v.sills[t], r = v.ranges[t];
+        o.tot += sl;
+        if (ty == SPX_VG_NUG) {
+            o.nug += sl;
+        } else if (ty == SPX_VG_SPH || ty == SPX_VG_LIN) {
+            if (o.np >= 2) { o.ok = 0; continue; }
+            const int i = o.np++;
+            o.ps[i] = sl;
+            o.pr[i] = r;
+            o.pca[i] = (ty == SPX_VG_SPH) ? 1.5 / r : 1.0 / r;
+            o.pcb[i] = (ty == SPX_VG_SPH) ? 1.0 / (2 * (r * r * r)) : 0.0;
+        } else if (ty == SPX_VG_EXP || ty == SPX_VG_GAU) {
+            if (o.ne >= 2) { o.ok = 0; continue; }
+            const int i = o.ne++;
+            o.es[i] = sl;
+            o.eca[i] = (ty == SPX_VG_EXP) ? -3.0 / r : -3.0 / (r * r);
+            o.esq[i] = (ty == SPX_VG_GAU);
+        } else {
+            o.ok = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ double eval_row_p(const RowP& o, double h, int covar_flag,
+                                             double min_vg_val) {
+    double g = o.nug;
+    if (o.np > 0) {
+        const double hc = fmin(h, o.pr[0]);
+        g = fma(o.ps[0], hc * o.pca[0] - hc * hc * hc * o.pcb[0], g);
+        if (o.np > 1) {
+            const double hd = fmin(h, o.pr[1]);
+            g = fma(o.ps[1], hd * o.pca[1] - hd * hd * hd * o.pcb[1], g);
+        }
+    }
+    if (o.ne > 0) {
+        g = fma(o.es[0], 1.0 - exp(o.eca[0] * (o.esq[0] ? h * h : h)), g);
+        if (o.ne > 1) g = fma(o.es[1], 1.0 - exp(o.eca[1] * (o.esq[1] ? h * h : h)), g);
+    }
+    if (covar_flag) g = o.tot - g;
+    return (g <= min_vg_val) ? 0.0 : g;
+}
+
 struct MultiVgArgs {
     const double* coef;        // [n_rows, kpad] row-major
     int64_t n_rows;
@@ -510,13 +580,14 @@ struct MultiVgArgs {
     double lo, hi;
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(MV_CELLS * MV_KQ) k_estimate_multivg(MultiVgArgs a) {
     extern __shared__ double msm[];
     const int kp = a.n_stn + a.n_border;                 // used K
     double* D = msm;                                     // [kp][MV_CELLS] distances / border values
     double* Cs = D + (size_t)kp * MV_CELLS;              // [MV_ROWS][kp] coefficient rows
     double* Ps = Cs + (size_t)MV_ROWS * kp;              // [MV_ROWS][MV_KQ][MV_CELLS] partial sums
-    __shared__ VgFast vf[MV_ROWS];
+    __shared__ RowP rv[MV_ROWS];
     __shared__ VgDev vd[MV_ROWS];
     const int tid = threadIdx.x;
     const int cl = tid % MV_CELLS, kq = tid / MV_CELLS;
@@ -547,7 +618,7 @@ __global__ void __launch_bounds__(MV_CELLS * MV_KQ) k_estimate_multivg(MultiVgAr
             }
             if (tid < nr) {
                 const spx_vg& v = a.vgs[a.row_vg[r0 + tid]];
-                vf[tid] = make_vg_fast_dev(v);
+                build_row_p(rv[tid], v);
                 vd[tid].n_terms = v.n_terms;
                 for (int t = 0; t < SPX_VG_MAX_TERMS; ++t) {
                     vd[tid].types[t] = v.types[t];
@@ -559,23 +630,32 @@ __global__ void __launch_bounds__(MV_CELLS * MV_KQ) k_estimate_multivg(MultiVgAr
             double acc[MV_ROWS];
 #pragma unroll
             for (int rr = 0; rr < MV_ROWS; ++rr) acc[rr] = 0.0;
-            for (int k = kq; k < a.n_stn; k += MV_KQ) {
-                const double h = D[(size_t)k * MV_CELLS + cl];
-#pragma unroll
-                for (int rr = 0; rr < MV_ROWS; ++rr) {
-                    if (rr < nr) {
-                        const double g = vf[rr].all_fast
-                                             ? vg_eval_fast(vf[rr], h, a.covar_flag, a.min_vg_val)
-                                             : vg_eval(vd[rr], h, a.covar_flag, a.min_vg_val);
-                        acc[rr] = fma(Cs[(size_t)rr * kp + k], g, acc[rr]);
+            // rows outermost: the row's compiled variogram lives in registers for the
+            // whole station loop (two partial sums for instruction-level parallelism)
+#pragma unroll 1
+            for (int rr = 0; rr < nr; ++rr) {
+                const RowP p = rv[rr];
+                const double* __restrict__ crow = Cs + (size_t)rr * kp;
+                double a0 = 0.0, a1 = 0.0;
+                if (FAST || p.ok) {
+                    int k = kq;
+                    for (; k + MV_KQ < a.n_stn; k += 2 * MV_KQ) {
+                        const double h0 = D[(size_t)k * MV_CELLS + cl];
+                        const double h1 = D[(size_t)(k + MV_KQ) * MV_CELLS + cl];
+                        a0 = fma(crow[k], eval_row_p(p, h0, a.covar_flag, a.min_vg_val), a0);
+                        a1 = fma(crow[k + MV_KQ], eval_row_p(p, h1, a.covar_flag, a.min_vg_val), a1);
                     }
+                    for (; k < a.n_stn; k += MV_KQ)
+                        a0 = fma(crow[k], eval_row_p(p, D[(size_t)k * MV_CELLS + cl], a.covar_flag,
+                                                     a.min_vg_val), a0);
+                } else {
+                    for (int k = kq; k < a.n_stn; k += MV_KQ)
+                        a0 = fma(crow[k], vg_eval(vd[rr], D[(size_t)k * MV_CELLS + cl],
+                                                  a.covar_flag, a.min_vg_val), a0);
                 }
-            }
-            for (int k = a.n_stn + kq; k < kp; k += MV_KQ) {
-                const double bv = D[(size_t)k * MV_CELLS + cl];
-#pragma unroll
-                for (int rr = 0; rr < MV_ROWS; ++rr)
-                    if (rr < nr) acc[rr] = fma(Cs[(size_t)rr * kp + k], bv, acc[rr]);
+                for (int k = a.n_stn + kq; k < kp; k += MV_KQ)
+                    a0 = fma(crow[k], D[(size_t)k * MV_CELLS + cl], a0);
+                acc[rr] = a0 + a1;
             }
 #pragma unroll
             for (int rr = 0; rr < MV_ROWS; ++rr)
@@ -649,13 +729,18 @@ extern "C" int spx_estimate_multivg_dev(const spx_multivg* g, void* stream) {
         set_error("estimate_multivg: %d stations do not fit in shared memory", g->n_stn);
         return SPX_ENOMEM;
     }
-    SPX_CUDA(cudaFuncSetAttribute(k_estimate_multivg, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    SPX_CUDA(cudaFuncSetAttribute(k_estimate_multivg<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPX_CUDA(cudaFuncSetAttribute(k_estimate_multivg<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (g->n_cells + MV_CELLS - 1) / MV_CELLS;
     const int per_sm = (int)((size_t)max_smem / (smem + 4096));
     const int64_t want = (int64_t)n_sm * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
     const int grid = (int)(tiles < want ? tiles : want);
-    k_estimate_multivg<<<grid, MV_CELLS * MV_KQ, smem, (cudaStream_t)stream>>>(a);
+    if (g->all_fast)
+        k_estimate_multivg<true><<<grid, MV_CELLS * MV_KQ, smem, (cudaStream_t)stream>>>(a);
+    else
+        k_estimate_multivg<false><<<grid, MV_CELLS * MV_KQ, smem, (cudaStream_t)stream>>>(a);
     SPX_CHECK_LAUNCH("k_estimate_multivg");
     return SPX_OK;
 }

@@ -815,6 +815,17 @@ class ChunkEngine:
             g.out_f64 = ctx['out_f64']
             g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
             g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            def _fast(vg_s):       # <= 2 Sph/Lin and <= 2 Exp/Gau terms plus nuggets
+                n_poly = n_exp = 0
+                for (t, _, _) in _lib.parse_vg_str(vg_s):
+                    if t in (2, 4):
+                        n_poly += 1
+                    elif t in (3, 5):
+                        n_exp += 1
+                    elif t != 1:
+                        return False
+                return n_poly <= 2 and n_exp <= 2
+            g.all_fast = int(all(_fast(vg_s) for vg_s in uniq_vgs))
             with self._phase('multivg'):
                 _lib.check(self.lib.spx_estimate_multivg_dev(C.byref(g), self._stream()),
                            'estimate_multivg')
