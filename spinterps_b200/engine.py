@@ -131,7 +131,10 @@ class ChunkEngine:
         cudaMemcpyAsync first synchronises its stream, so issuing it on the compute
         stream would stall the host behind every queued kernel; the compute stream
         instead waits for the upload stream right before the next launch."""
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:       # e.g. a read-only pandas view
+            arr = arr.copy()
+        t = torch.from_numpy(arr)
         if dtype is not None:
             t = t.to(dtype)
         main = torch.cuda.current_stream(self.device)

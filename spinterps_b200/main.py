@@ -518,7 +518,13 @@ class SpInterpMain:
         else:
             self._vgs_rord_tidxs_ser = None
 
-        self._initiate_nc()
+        import torch.distributed as tdist
+        if (not tdist.is_initialized()) or tdist.get_rank() == 0:
+            self._initiate_nc()
+        else:
+            self._nc_file_path = self._out_dir / (self._nc_out.split('.', 1)[0] + '.nc')
+        if tdist.is_initialized():
+            tdist.barrier()
         self._prpd_flag = True
 
     def _initiate_nc(self):
@@ -601,8 +607,12 @@ class SpInterpMain:
         t0 = timeit.default_timer()
         lock = Lock()
         n_steps = self._data_df.shape[0]
-        if tdist.is_initialized() and tdist.get_world_size() > 1:
-            beg_all, end_all = sdist.my_shard(n_steps)
+        multi = tdist.is_initialized() and tdist.get_world_size() > 1
+        rank = tdist.get_rank() if multi else 0
+        writer = 0
+        if multi:
+            shard_b = sdist.shard_bounds(n_steps, tdist.get_world_size())
+            beg_all, end_all = int(shard_b[rank]), int(shard_b[rank + 1])
         else:
             beg_all, end_all = 0, n_steps
         steps_cls = SpInterpSteps(self)
@@ -611,12 +621,45 @@ class SpInterpMain:
         if bounds.size < 2:
             bounds = np.array([beg_all, end_all])
         stats_rows = {}
-        for i in range(bounds.size - 1):
-            args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
-            out = steps_cls._get_all_interp_outputs(args)
-            self._collect_stats(out, stats_rows)
-            steps_cls._write_to_disk(out)
-        self._save_stats_sers(stats_rows)
+        if not multi:
+            for i in range(bounds.size - 1):
+                if bounds[i + 1] == bounds[i]:
+                    continue
+                args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
+                out = steps_cls._get_all_interp_outputs(args)
+                self._collect_stats(out, stats_rows)
+                steps_cls._write_to_disk(out)
+        else:
+            # every rank interpolates its block of time steps; the f32 slabs are sent
+            # to the writer rank over NCCL (NVLink) and only that rank touches the file
+            import torch
+            labels = [a[2] for a in self._interp_args]
+            fld = int(np.prod(self._interp_crds_orig_shape))
+            dev = torch.device('cuda', torch.cuda.current_device())
+            tdt = torch.float32 if np.dtype(self._intrp_dtype) == np.float32 else torch.float64
+            parts = []
+            for i in range(bounds.size - 1):
+                if bounds[i + 1] == bounds[i]:
+                    continue
+                args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
+                parts.append(steps_cls._get_all_interp_outputs(args)[7])
+            for lab in labels:
+                if parts:
+                    slab = torch.from_numpy(np.concatenate([p_[lab] for p_ in parts])).to(dev)
+                else:
+                    slab = torch.empty((0, fld), dtype=tdt, device=dev)
+                full = sdist.gather_slabs(slab, shard_b, dst=writer)
+                if rank == writer:
+                    arr = full.cpu().numpy()
+                    args = self._chunk_args(0, n_steps, 1, lock)
+                    out = (lock, 0, n_steps, args[0], args[8], 1, [lab], {lab: arr}, 0,
+                           int(self._interp_crds_orig_shape[0]), args[9], args[0].index,
+                           timeit.default_timer())
+                    self._collect_stats(out, stats_rows)
+                    steps_cls._write_to_disk(out)
+            tdist.barrier()
+        if rank == writer:
+            self._save_stats_sers(stats_rows)
         if self._vb:
             print(f'Done with the interpolation in {timeit.default_timer() - t0:0.1f} seconds.')
 
