@@ -284,15 +284,31 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     eng.profile_gemm = True
-    eng.gemm_events = []
+    eng.kernel_events = []
     l0 = eng.total_launches
     ms, ms_wall = timed(run_resident, args.steps)
     launches_timed = eng.total_launches - l0
-    gemm_events = eng.gemm_events
+    kernel_events = eng.kernel_events
     eng.profile_gemm = False
-    gemm_flop_per_launch = eng.stats.get('gemm_flop', 0) / max(eng.stats.get('gemm_launches', 1), 1)
     torch.cuda.synchronize()
-    gemm_ms = [a.elapsed_time(b) for a, b in gemm_events]
+    engine_stats = dict(eng.stats)
+
+    def summarise(events):
+        """Dominant estimate kernel of the timed region: total time, work, rate."""
+        by = {}
+        for name, bound, work, e0, e1 in events:
+            d = by.setdefault(name, dict(bound=bound, work=0.0, ms=0.0, n=0))
+            d['work'] += work
+            d['ms'] += e0.elapsed_time(e1)
+            d['n'] += 1
+        if not by:
+            return None
+        name = max(by, key=lambda k_: by[k_]['ms'])
+        d = by[name]
+        d['kernel'] = name
+        return d
+
+    dom = summarise(kernel_events)
 
     run_e2e(min(args.warmup, 2))
     ms_e2e, _ = timed(run_e2e, args.steps)
@@ -300,20 +316,61 @@ def run_gpu(args):
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
+    # the tensor-core contraction on the same workload (local estimator off), so that
+    # both estimators are on record
+    eng.local_support = False
+    run_resident(1)
+    eng.profile_gemm = True
+    eng.kernel_events = []
+    n_dense = max(2, min(args.steps, 3))
+    ms_dense, _ = timed(run_resident, n_dense)
+    dense_dom = summarise(eng.kernel_events)
+    eng.profile_gemm = False
+    eng.local_support = True
+
     value = world * cell_steps * args.steps / (ms / 1e3)
     e2e_value = world * cell_steps * args.steps / (ms_e2e / 1e3)
+    value_dense = world * cell_steps * n_dense / (ms_dense / 1e3)
 
     if rank == 0:
-        peak = dgemm_peak_tflops(torch)
-        avg_gemm_ms = sum(gemm_ms) / max(len(gemm_ms), 1)
-        achieved = gemm_flop_per_launch / (avg_gemm_ms / 1e3) / 1e12 if gemm_ms else None
-        traffic = None
-        tf = ROOT / 'profiles' / 'gemm_traffic.json'
+        peak_f64 = dgemm_peak_tflops(torch)
+        hbm_peak, hbm_src = 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+        mp = ROOT / 'MEASURED_PEAKS.json'
+        if mp.exists():
+            try:
+                hbm_peak = float(json.loads(mp.read_text())['hbm_gbs'])
+                hbm_src = 'MEASURED_PEAKS.json hbm_gbs (copy, read + write)'
+            except Exception:
+                pass
+        traffic_tbl = {}
+        tf = ROOT / 'profiles' / 'kernel_traffic.json'
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get('dram_bytes_per_launch')
+                traffic_tbl = json.loads(tf.read_text())
             except Exception:
-                traffic = None
+                traffic_tbl = {}
+
+        def roofline(d):
+            if d is None:
+                return None
+            avg_ms = d['ms'] / d['n']
+            per_launch = d['work'] / d['n']
+            if d['bound'] == 'tensor':
+                ach = per_launch / (avg_ms / 1e3) / 1e12
+                peak, unit = peak_f64, 'TFLOP/s'
+                src = ('FP64 tensor: cuBLAS DGEMM 6144^3 via torch.matmul measured live in this '
+                       'run (MEASURED_PEAKS.json has no FP64 entry); DMMA issue-rate '
+                       'microbenchmark 37.15 TFLOP/s in profiles/microbench')
+            else:
+                ach = per_launch / (avg_ms / 1e3) / 1e9
+                peak, unit, src = hbm_peak, 'GB/s', hbm_src
+            t = traffic_tbl.get(d['kernel'], {})
+            return {'kernel': 'spx::' + d['kernel'], 'bound': d['bound'], 'achieved': ach,
+                    'peak': peak, 'unit': unit, 'frac': ach / peak,
+                    'traffic': t.get('dram_bytes_per_launch'),
+                    'algorithmic_per_launch': per_launch, 'avg_launch_ms': avg_ms,
+                    'launches_timed': d['n'], 'peak_source': src}
+
         cpu_baseline = None
         if cpu_res is not None:
             cs, wall, n_steps_s, rows_s = cpu_res
@@ -334,23 +391,22 @@ def run_gpu(args):
                 'l2': 'each step writes a %.1f GB field (>> 126 MB L2) between reuses'
                       % (cell_steps * 4 / 1e9),
                 'pipeline': 'chunk i+1 is prepared/queued while chunk i runs (engine.submit_chunk)',
-                'chunks': '%d distinct chunks of time steps cycled; the inverse of the full '
-                          'station system (data-independent, per job) is cached across chunks'
-                          % N_VARIANTS,
+                'chunks': '%d distinct chunks of time steps cycled; data-independent per-job '
+                          'structures (inverse of the full station system, stations within the '
+                          'variogram range of each cell) are cached across chunks' % N_VARIANTS,
+                'estimator': ('local (compact-support) estimator: %s' % bool(
+                    engine_stats.get('local_rows'))),
                 'wall_ms_per_step': ms_wall / args.steps},
             'e2e': {'value': e2e_value, 'unit': 'cell-steps/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(cell_steps * 4),
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches_timed),
-            'roofline': {
-                'kernel': 'spx::k_estimate_gemm (fused variogram fill + DMMA contraction)',
-                'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
-                'peak_source': 'FP64: cuBLAS DGEMM 6144^3 via torch.matmul, measured live in this '
-                               'run (MEASURED_PEAKS.json has no FP64 entry); DMMA issue-rate '
-                               'microbenchmark: profiles/microbench',
-                'flop_per_launch': gemm_flop_per_launch, 'avg_launch_ms': avg_gemm_ms,
-                'launches_timed': len(gemm_ms)},
+            'roofline': roofline(dom),
+            'dense_path': {
+                'note': 'same workload with the local estimator disabled: every estimate goes '
+                        'through the fused variogram-fill + DMMA contraction',
+                'value': value_dense, 'unit': 'cell-steps/s', 'ms_per_step': ms_dense / n_dense,
+                'roofline': roofline(dense_dom)},
             'cpu_baseline': cpu_baseline,
             'clocks': sampler.summary(),
         }

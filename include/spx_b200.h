@@ -437,6 +437,51 @@ typedef struct spx_multivg {
 } spx_multivg;
 int spx_estimate_multivg_dev(const spx_multivg* g, void* stream);
 
+/* LOCAL estimator for compactly supported variograms (only Nug / Sph / Lin terms):
+ * beyond the largest range R the cell<->station variogram is the constant
+ * F = sum(sills) (0 in covariance form) exactly, so
+ *   Z[row, cell] = base[row] + drift terms + sum_{k: dist < R} coef[row, k] (vg(dist) - F),
+ *   base[row] = F * sum_k coef[row, k] + coef[row, n_stn]   (the caller computes it).
+ * spx_local_build_dev finds, through a uniform bin grid of size R over the stations,
+ * the stations within R of every cell (cnt may exceed cap: rebuild with a larger
+ * cap); spx_estimate_local_dev streams the field (HBM-write bound).
+ * coef is ROW-MAJOR [n_rows, kpad]. */
+typedef struct spx_local {
+    const double* stn_x;
+    const double* stn_y;
+    const int32_t* bin_start;  /* [nbx * nby + 1] */
+    const int32_t* bin_stn;    /* station ids ordered by bin */
+    double x0, y0, inv_bin;
+    int32_t nbx, nby;
+    double R, F;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    int32_t cap;
+    int32_t* cnt;              /* [n_cells] */
+    int32_t* idx;              /* [n_cells, cap] */
+    double* val;               /* [n_cells, cap] */
+    spx_vg vg;
+    int32_t covar_flag;
+    double min_vg_val;
+    /* estimate */
+    const double* coef;
+    const double* base;
+    int64_t n_rows;
+    int32_t kpad, n_stn, n_drifts;
+    const double* cell_drift;
+    const int32_t* row_dst;
+    void* out;
+    int64_t out_ld;
+    int32_t out_f64;
+    const int32_t* cell_pos;
+    int32_t has_lo, has_hi;
+    double lo, hi;
+    int32_t rows_all_valid;    /* every row_dst[r] >= 0 (enables the streamlined kernel) */
+} spx_local;
+int spx_local_build_dev(const spx_local* l, void* stream);
+int spx_estimate_local_dev(const spx_local* l, void* stream);
+
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field
  * download in flight; n_bytes and both pointers multiples of 4. */

@@ -87,6 +87,22 @@ class spx_multivg(C.Structure):
                 ('lo', C.c_double), ('hi', C.c_double), ('all_fast', C.c_int32)]
 
 
+class spx_local(C.Structure):
+    _fields_ = [('stn_x', C.c_void_p), ('stn_y', C.c_void_p),
+                ('bin_start', C.c_void_p), ('bin_stn', C.c_void_p),
+                ('x0', C.c_double), ('y0', C.c_double), ('inv_bin', C.c_double),
+                ('nbx', C.c_int32), ('nby', C.c_int32), ('R', C.c_double), ('F', C.c_double),
+                ('cell_x', C.c_void_p), ('cell_y', C.c_void_p), ('n_cells', C.c_int64),
+                ('cap', C.c_int32), ('cnt', C.c_void_p), ('idx', C.c_void_p), ('val', C.c_void_p),
+                ('vg', spx_vg), ('covar_flag', C.c_int32), ('min_vg_val', C.c_double),
+                ('coef', C.c_void_p), ('base', C.c_void_p), ('n_rows', C.c_int64),
+                ('kpad', C.c_int32), ('n_stn', C.c_int32), ('n_drifts', C.c_int32),
+                ('cell_drift', C.c_void_p), ('row_dst', C.c_void_p), ('out', C.c_void_p),
+                ('out_ld', C.c_int64), ('out_f64', C.c_int32), ('cell_pos', C.c_void_p),
+                ('has_lo', C.c_int32), ('has_hi', C.c_int32),
+                ('lo', C.c_double), ('hi', C.c_double), ('rows_all_valid', C.c_int32)]
+
+
 class spx_nrst(C.Structure):
     _fields_ = [('n_grp', C.c_int32), ('n_cells', C.c_int64),
                 ('k', C.c_int32), ('n_border', C.c_int32), ('n_drifts', C.c_int32),
@@ -169,6 +185,8 @@ _SIGS = {
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_double, C.c_double, C.c_void_p]),
     'spx_estimate_multivg_dev': (C.c_int, [C.POINTER(spx_multivg), C.c_void_p]),
+    'spx_local_build_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
+    'spx_estimate_local_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

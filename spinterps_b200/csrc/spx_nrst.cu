@@ -11,6 +11,8 @@
 //   k_nrst_krige  per cell: right-hand side from coordinates, sum(lambda) test,
 //                 NNB fallback, estimate, clamp, store (interp/steps.py:403-435)
 //   k_nrst_idw    per cell: IDW over its neighbours (interp/steps.py:293-313)
+#include <cstdlib>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -742,5 +744,346 @@ extern "C" int spx_estimate_multivg_dev(const spx_multivg* g, void* stream) {
     else
         k_estimate_multivg<false><<<grid, MV_CELLS * MV_KQ, smem, (cudaStream_t)stream>>>(a);
     SPX_CHECK_LAUNCH("k_estimate_multivg");
+    return SPX_OK;
+}
+
+// ===========================================================================
+// LOCAL estimator for compactly supported variograms (Nug + Sph / Lin terms).
+// Beyond the largest range R every entry of the cell<->station variogram matrix
+// equals the constant F = sum(sills) (0 for the covariance form), exactly as in
+// the reference (pyx:50-51, :63-64).  Hence
+//   Z[row, cell] = F * sum_k coef[row, k] + border terms
+//                  + sum_{k : dist(k, cell) < R} coef[row, k] * (vg(dist) - F)
+// and only the stations within R of a cell (found through a uniform bin grid of
+// size R) contribute individually.  Work per cell-step drops from 2 (N + k) flop
+// to ~2 per near station; the kernel is bound by the HBM write of the field.
+namespace spx {
+
+struct LocalBuildArgs {
+    const double* stn_x;
+    const double* stn_y;
+    const int32_t* bin_start;   // [nbx * nby + 1]
+    const int32_t* bin_stn;     // station ids ordered by bin
+    double x0, y0, inv_bin;
+    int nbx, nby;
+    double R, F;
+    const double* cell_x;
+    const double* cell_y;
+    int64_t n_cells;
+    int cap;
+    int32_t* cnt;               // [n_cells]
+    int32_t* idx;               // [n_cells, cap]
+    double* val;                // [n_cells, cap]
+    VgDev vg;
+    int covar_flag;
+    double min_vg_val;
+};
+
+__global__ void __launch_bounds__(256) k_local_build(LocalBuildArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;
+    const double x = a.cell_x[c], y = a.cell_y[c];
+    const int bx = (int)floor((x - a.x0) * a.inv_bin);
+    const int by = (int)floor((y - a.y0) * a.inv_bin);
+    int n = 0;
+    for (int jy = by - 1; jy <= by + 1; ++jy) {
+        if (jy < 0 || jy >= a.nby) continue;
+        for (int jx = bx - 1; jx <= bx + 1; ++jx) {
+            if (jx < 0 || jx >= a.nbx) continue;
+            const int b = jy * a.nbx + jx;
+            for (int p = a.bin_start[b]; p < a.bin_start[b + 1]; ++p) {
+                const int s = a.bin_stn[p];
+                const double d = dist_rn(x, y, a.stn_x[s], a.stn_y[s]);
+                if (d < a.R) {
+                    if (n < a.cap) {
+                        a.idx[c * a.cap + n] = s;
+                        a.val[c * a.cap + n] = vg_eval(a.vg, d, a.covar_flag, a.min_vg_val) - a.F;
+                    }
+                    ++n;
+                }
+            }
+        }
+    }
+    a.cnt[c] = n;   // may exceed cap: the caller rebuilds with a larger cap
+}
+
+constexpr int LOC_REG = 4;      // near stations kept in registers
+constexpr int LOC_ROWS = 64;    // rows per block
+
+struct LocalEstArgs {
+    const double* coef;         // [n_rows, kpad] row-major
+    const double* base;         // [n_rows] F * sum_k coef + constant border term
+    int64_t n_rows;
+    int kpad, n_stn, n_drifts;
+    const double* cell_drift;   // [n_drifts, n_cells]
+    int64_t n_cells;
+    int cap;
+    const int32_t* cnt;
+    const int32_t* idx;
+    const double* val;
+    const int32_t* row_dst;
+    void* out;
+    int64_t out_ld;
+    int out_f64;
+    const int32_t* cell_pos;
+    int has_lo, has_hi;
+    double lo, hi;
+};
+
+// One thread per cell, LOC_ROWS rows per block.  The cell's near stations live in
+// registers; the loop over them is bounded by the warp-wide maximum so that the
+// (typical) cells with 0-2 stations in range issue no dead instructions.  Per
+// row: a broadcast read of base / destination, <= n gathers from the coefficient
+// row (L1 / L2 resident) and one coalesced store.
+template <typename OutT, bool DRIFT>
+__global__ void __launch_bounds__(256) k_estimate_local(LocalEstArgs a) {
+    __shared__ double sbase[LOC_ROWS];
+    __shared__ int sdst[LOC_ROWS];
+    const int64_t r_beg = (int64_t)blockIdx.y * LOC_ROWS;
+    const int nr = (int)min((int64_t)LOC_ROWS, a.n_rows - r_beg);
+    if (threadIdx.x < nr) {
+        sbase[threadIdx.x] = a.base[r_beg + threadIdx.x];
+        sdst[threadIdx.x] = a.row_dst[r_beg + threadIdx.x];
+    }
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = c < a.n_cells;
+    const int n = ok ? min(a.cnt[c], a.cap) : 0;
+    int ri[LOC_REG];
+    double rv[LOC_REG];
+#pragma unroll
+    for (int j = 0; j < LOC_REG; ++j) {
+        ri[j] = (j < n) ? a.idx[c * a.cap + j] : 0;
+        rv[j] = (j < n) ? a.val[c * a.cap + j] : 0.0;
+    }
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    double dr[4] = {0.0, 0.0, 0.0, 0.0};
+    if (DRIFT && ok) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (d < a.n_drifts) dr[d] = a.cell_drift[(int64_t)d * a.n_cells + c];
+    }
+    const int64_t col = ok ? (a.cell_pos ? (int64_t)a.cell_pos[c] : c) : 0;
+    OutT* __restrict__ outp = reinterpret_cast<OutT*>(a.out) + col;
+    const double* __restrict__ crow = a.coef + r_beg * a.kpad;
+    constexpr int RU = 8;   // rows in flight: the gathers of RU rows are issued together
+    for (int r0 = 0; r0 < nr; r0 += RU, crow += (int64_t)RU * a.kpad) {
+        double g0[RU], g1[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const bool live = (r0 + u < nr);
+            g0[u] = (live && 0 < n) ? crow[(int64_t)u * a.kpad + ri[0]] : 0.0;
+            g1[u] = (live && 1 < n) ? crow[(int64_t)u * a.kpad + ri[1]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u;
+            if (r >= nr) break;
+            const double* __restrict__ cr = crow + (int64_t)u * a.kpad;
+            const int dst = sdst[r];
+            double z = sbase[r];
+            if (DRIFT) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    if (d < a.n_drifts) z = fma(cr[a.n_stn + 1 + d], dr[d], z);
+            }
+            z = fma(g0[u], rv[0], z);
+            z = fma(g1[u], rv[1], z);
+            if (nmax > 2) {
+                if (2 < n) z = fma(cr[ri[2]], rv[2], z);
+                if (3 < n) z = fma(cr[ri[3]], rv[3], z);
+                for (int j = LOC_REG; j < n; ++j)
+                    z = fma(cr[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
+            }
+            if (a.has_lo && z < a.lo) z = a.lo;
+            if (a.has_hi && z > a.hi) z = a.hi;
+            if (ok && dst >= 0) outp[(int64_t)dst * a.out_ld] = static_cast<OutT>(z);
+        }
+    }
+}
+
+// Fast variant: float output, identity cell order, no drift.  Written for a low
+// instruction count per (cell, row) -- the kernel is issue bound, not bandwidth
+// bound, if every row pays for flag tests, 64-bit index arithmetic and clamps on
+// doubles: per-row destination offsets are precomputed in shared memory, the number
+// of gathers is a warp-uniform compile-time case (NG = 0, 1, 2 or "many"), the
+// clamp is a compile-time option applied after the conversion (rounding is
+// monotone, so float(clamp(z)) == clamp(float(z)) with float(lo), float(hi)) and
+// rows are processed four at a time without per-row bounds checks.
+template <int NG, bool CLAMP>
+__device__ __forceinline__ void local_rows(const LocalEstArgs& a, const double* sbase,
+                                           const int64_t* soff, int nr, int64_t c, int n,
+                                           const int* ri, const double* rv, float* outp,
+                                           const double* crow, float flo, float fhi) {
+    const int64_t kp = a.kpad;
+    int r = 0;
+    for (; r + 4 <= nr; r += 4, crow += 4 * kp) {
+        double g0[4], g1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            g0[u] = (NG >= 1 && 0 < n) ? crow[u * kp + ri[0]] : 0.0;
+            g1[u] = (NG >= 2 && 1 < n) ? crow[u * kp + ri[1]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double z = sbase[r + u];
+            if (NG >= 1) z = fma(g0[u], rv[0], z);
+            if (NG >= 2) z = fma(g1[u], rv[1], z);
+            if (NG >= 3) {
+                const double* cr = crow + u * kp;
+                for (int j = 2; j < n; ++j)
+                    z = fma(cr[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
+            }
+            float f = (float)z;
+            if (CLAMP) {
+                f = (f < flo) ? flo : f;
+                f = (f > fhi) ? fhi : f;
+            }
+            outp[soff[r + u]] = f;
+        }
+    }
+    for (; r < nr; ++r, crow += kp) {
+        double z = sbase[r];
+        if (NG >= 1 && 0 < n) z = fma(crow[ri[0]], rv[0], z);
+        if (NG >= 2 && 1 < n) z = fma(crow[ri[1]], rv[1], z);
+        if (NG >= 3)
+            for (int j = 2; j < n; ++j)
+                z = fma(crow[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
+        float f = (float)z;
+        if (CLAMP) {
+            f = (f < flo) ? flo : f;
+            f = (f > fhi) ? fhi : f;
+        }
+        outp[soff[r]] = f;
+    }
+}
+
+template <bool CLAMP>
+__global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
+    __shared__ double sbase[LOC_ROWS];
+    __shared__ int64_t soff[LOC_ROWS];
+    const int64_t r_beg = (int64_t)blockIdx.y * LOC_ROWS;
+    const int nr = (int)min((int64_t)LOC_ROWS, a.n_rows - r_beg);
+    if (threadIdx.x < nr) {
+        sbase[threadIdx.x] = a.base[r_beg + threadIdx.x];
+        soff[threadIdx.x] = (int64_t)a.row_dst[r_beg + threadIdx.x] * a.out_ld;
+    }
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;                  // no further block-wide barrier below
+    const int n = min(a.cnt[c], a.cap);
+    int ri[2];
+    double rv[2];
+    ri[0] = (0 < n) ? a.idx[c * a.cap] : 0;
+    ri[1] = (1 < n) ? a.idx[c * a.cap + 1] : 0;
+    rv[0] = (0 < n) ? a.val[c * a.cap] : 0.0;
+    rv[1] = (1 < n) ? a.val[c * a.cap + 1] : 0.0;
+    const int nmax = __reduce_max_sync(__activemask(), n);
+    const float flo = a.has_lo ? (float)a.lo : -CUDART_INF_F;
+    const float fhi = a.has_hi ? (float)a.hi : CUDART_INF_F;
+    float* outp = reinterpret_cast<float*>(a.out) + c;
+    const double* crow = a.coef + r_beg * a.kpad;
+    if (nmax == 0)
+        local_rows<0, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+    else if (nmax == 1)
+        local_rows<1, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+    else if (nmax == 2)
+        local_rows<2, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+    else
+        local_rows<3, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+}
+
+}  // namespace spx
+
+extern "C" int spx_local_build_dev(const spx_local* l, void* stream) {
+    using namespace spx;
+    if (!l || l->cap < 1) {
+        set_error("local_build: bad argument");
+        return SPX_EINVAL;
+    }
+    if (l->n_cells == 0) return SPX_OK;
+    LocalBuildArgs a;
+    a.stn_x = l->stn_x;
+    a.stn_y = l->stn_y;
+    a.bin_start = l->bin_start;
+    a.bin_stn = l->bin_stn;
+    a.x0 = l->x0;
+    a.y0 = l->y0;
+    a.inv_bin = l->inv_bin;
+    a.nbx = l->nbx;
+    a.nby = l->nby;
+    a.R = l->R;
+    a.F = l->F;
+    a.cell_x = l->cell_x;
+    a.cell_y = l->cell_y;
+    a.n_cells = l->n_cells;
+    a.cap = l->cap;
+    a.cnt = l->cnt;
+    a.idx = l->idx;
+    a.val = l->val;
+    a.vg = to_dev(l->vg);
+    a.covar_flag = l->covar_flag;
+    a.min_vg_val = l->min_vg_val;
+    k_local_build<<<(unsigned)((l->n_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    SPX_CHECK_LAUNCH("k_local_build");
+    return SPX_OK;
+}
+
+extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
+    using namespace spx;
+    if (!l) {
+        set_error("estimate_local: null argument");
+        return SPX_EINVAL;
+    }
+    if (l->n_cells == 0 || l->n_rows == 0) return SPX_OK;
+    if (l->n_drifts > 4) {
+        set_error("estimate_local: more than 4 drifts");
+        return SPX_EINVAL;
+    }
+    LocalEstArgs a;
+    a.coef = l->coef;
+    a.base = l->base;
+    a.n_rows = l->n_rows;
+    a.kpad = l->kpad;
+    a.n_stn = l->n_stn;
+    a.n_drifts = l->n_drifts;
+    a.cell_drift = l->cell_drift;
+    a.n_cells = l->n_cells;
+    a.cap = l->cap;
+    a.cnt = l->cnt;
+    a.idx = l->idx;
+    a.val = l->val;
+    a.row_dst = l->row_dst;
+    a.out = l->out;
+    a.out_ld = l->out_ld;
+    a.out_f64 = l->out_f64;
+    a.cell_pos = l->cell_pos;
+    a.has_lo = l->has_lo;
+    a.has_hi = l->has_hi;
+    a.lo = l->lo;
+    a.hi = l->hi;
+    const int64_t row_blocks = (l->n_rows + LOC_ROWS - 1) / LOC_ROWS;
+    if (row_blocks > 65535) {
+        set_error("estimate_local: too many rows in one launch");
+        return SPX_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool drift = l->n_drifts > 0;
+    if (!l->out_f64 && !drift && l->cell_pos == nullptr && l->rows_all_valid) {
+        dim3 g1((unsigned)((l->n_cells + 255) / 256), (unsigned)row_blocks);
+        if (l->has_lo || l->has_hi) k_estimate_local_fast<true><<<g1, 256, 0, st>>>(a);
+        else k_estimate_local_fast<false><<<g1, 256, 0, st>>>(a);
+        SPX_CHECK_LAUNCH("k_estimate_local_fast");
+        return SPX_OK;
+    }
+    dim3 grid((unsigned)((l->n_cells + 255) / 256), (unsigned)row_blocks);
+    if (l->out_f64) {
+        if (drift) k_estimate_local<double, true><<<grid, 256, 0, st>>>(a);
+        else k_estimate_local<double, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (drift) k_estimate_local<float, true><<<grid, 256, 0, st>>>(a);
+        else k_estimate_local<float, false><<<grid, 256, 0, st>>>(a);
+    }
+    SPX_CHECK_LAUNCH("k_estimate_local");
     return SPX_OK;
 }

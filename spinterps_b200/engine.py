@@ -111,6 +111,12 @@ class ChunkEngine:
         # full-system inverses are reused across chunks with the same stations and
         # variogram (they do not depend on the data)
         self.multivg = True      # per-row-variogram estimator for variogram series
+        # local estimator for compactly supported variograms (Nug + Sph / Lin): used
+        # when a cell has on average at most this many stations within the range
+        self.local_support = True
+        self.local_max_near = 24.0
+        self._local_cache = {}
+        self._geom_cache = {}
         self.pinv_flagged = True  # np.linalg.pinv semantics for untrustworthy OK/EDK systems
         self.ginv_cache = True
         self.ginv_cache_size = 8
@@ -119,6 +125,7 @@ class ChunkEngine:
         # bench hook: CUDA events around every estimate-contraction launch
         self.profile_gemm = False
         self.gemm_events = []
+        self.kernel_events = []   # (kernel, bound, work [flop | bytes], start, end)
         self.sync_timing = False
         self.timing = {}
         self.total_launches = 0
@@ -143,6 +150,27 @@ class ChunkEngine:
         d.record_stream(main)
         self._h2d_dirty = True
         return d
+
+    def _dev_pack(self, arrays):
+        """Upload several small arrays with ONE host->device copy; returns device
+        views (16-byte aligned) in the same order."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        offs = []
+        total = 0
+        for a in arrays:
+            total = (total + 15) & ~15
+            offs.append(total)
+            total += a.nbytes
+        host = np.empty(max(total, 16), dtype=np.uint8)
+        for a, o in zip(arrays, offs):
+            host[o:o + a.nbytes] = a.view(np.uint8).ravel()
+        d = self._dev(host)
+        out = []
+        for a, o in zip(arrays, offs):
+            tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+                   np.dtype(np.float64): torch.float64, np.dtype(np.uint8): torch.uint8}[a.dtype]
+            out.append(d[o:o + a.nbytes].view(tdt).view(a.shape))
+        return out
 
     def _sync_uploads(self):
         """Make the compute stream wait for every upload issued so far."""
@@ -172,6 +200,20 @@ class ChunkEngine:
                 'copy_to_mapped_host')
             self._count('launches')
         return h
+
+    def _prof_begin(self):
+        if not self.profile_gemm:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        return e0
+
+    def _prof_end(self, e0, name, bound, work):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream(self.device))
+        self.kernel_events.append((name, bound, float(work), e0, e1))
 
     def _count(self, key, n=1):
         self.stats[key] = self.stats.get(key, 0) + n
@@ -274,27 +316,50 @@ class ChunkEngine:
             assert 'EST_VARS_OK' in interp_labels, 'est_var_flag needs an EST_VARS_OK label'
 
         # ---- cell subsetting, steps.py:512-568 ------------------------------
+        # Depends on the grid only: cached per job (same coordinate arrays passed for
+        # every chunk), together with the device copies and the bounding box.
+        cell_xs = np.asarray(cell_xs)
+        cell_ys = np.asarray(cell_ys)
         fld_n_cols = int(grid_shape[1])
         fld_beg_idx = fld_beg_row * fld_n_cols
         fld_end_idx = fld_end_row * fld_n_cols
         fld_size = (fld_end_row - fld_beg_row) * fld_n_cols
-        if cntn_idxs is not None:
-            whr = np.where(cntn_idxs)[0]
-            sel = (whr >= fld_beg_idx) & (whr < fld_end_idx)
-            msh_idxs = np.arange(whr.size)[sel]
-            out_pos = (whr[sel] - fld_beg_idx).astype(np.int32)
-            dst_xs = cell_xs[msh_idxs]
-            dst_ys = cell_ys[msh_idxs]
-            if drft_arrs is not None:
-                drft_arrs = drft_arrs[:, msh_idxs]
-        else:
-            out_pos = None
-            dst_xs = cell_xs[fld_beg_idx:fld_end_idx]
-            dst_ys = cell_ys[fld_beg_idx:fld_end_idx]
-            if drft_arrs is not None:
-                drft_arrs = drft_arrs[:, fld_beg_idx:fld_end_idx]
+        mid = cell_xs.size // 2
+        gkey = (cell_xs.__array_interface__['data'][0], cell_ys.__array_interface__['data'][0],
+                cell_xs.size, fld_beg_row, fld_end_row, fld_n_cols,
+                None if cntn_idxs is None else (np.asarray(cntn_idxs).__array_interface__['data'][0],
+                                                int(np.asarray(cntn_idxs).size)),
+                float(cell_xs[0]), float(cell_xs[-1]), float(cell_xs[mid]),
+                float(cell_ys[0]), float(cell_ys[-1]), float(cell_ys[mid]))
+        geo = self._geom_cache.get(gkey)
+        if geo is None:
+            if cntn_idxs is not None:
+                whr = np.where(cntn_idxs)[0]
+                sel = (whr >= fld_beg_idx) & (whr < fld_end_idx)
+                msh_idxs = np.arange(whr.size)[sel]
+                out_pos = (whr[sel] - fld_beg_idx).astype(np.int32)
+                dst_xs = np.ascontiguousarray(cell_xs[msh_idxs], dtype=np.float64)
+                dst_ys = np.ascontiguousarray(cell_ys[msh_idxs], dtype=np.float64)
+            else:
+                msh_idxs = None
+                out_pos = None
+                dst_xs = np.ascontiguousarray(cell_xs[fld_beg_idx:fld_end_idx], dtype=np.float64)
+                dst_ys = np.ascontiguousarray(cell_ys[fld_beg_idx:fld_end_idx], dtype=np.float64)
+            assert dst_xs.shape[0] > 0
+            geo = dict(msh_idxs=msh_idxs, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
+                       d_cell_x=self._dev(dst_xs), d_cell_y=self._dev(dst_ys),
+                       d_pos=self._dev(out_pos) if out_pos is not None else None,
+                       bbox=(float(dst_xs.min()), float(dst_xs.max()), float(dst_ys.min()),
+                             float(dst_ys.max())),
+                       fp=(int(dst_xs.size), float(dst_xs.sum()), float(dst_ys.sum())))
+            while len(self._geom_cache) >= 4:
+                self._geom_cache.pop(next(iter(self._geom_cache)))
+            self._geom_cache[gkey] = geo
+        out_pos, dst_xs, dst_ys = geo['out_pos'], geo['dst_xs'], geo['dst_ys']
+        if drft_arrs is not None:
+            drft_arrs = (drft_arrs[:, geo['msh_idxs']] if geo['msh_idxs'] is not None
+                         else drft_arrs[:, fld_beg_idx:fld_end_idx])
         n_cells = int(dst_xs.shape[0])
-        assert n_cells > 0
 
         if nrst:
             # stations never among the n_nebs nearest of any cell are dropped up-front
@@ -319,19 +384,24 @@ class ChunkEngine:
         n_avail = grp_n[grp_of_step]
         problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
 
-        data0 = np.where(avail, data, 0.0)
-        with np.errstate(invalid='ignore', divide='ignore'):
-            ref_means = data0.sum(axis=1) / n_avail                  # steps.py:276
-            steps_flags = (np.where(avail, data, -np.inf) >= min_var_thr).any(axis=1)  # :760-765
-        single_val = data0.sum(axis=1)                               # value when n_avail == 1
+        data0 = np.nan_to_num(data, nan=0.0, posinf=np.inf, neginf=-np.inf)
+        if min_var_thr == -np.inf:
+            steps_flags = n_avail >= 1                               # nothing is below -inf
+        else:
+            with np.errstate(invalid='ignore'):
+                steps_flags = (np.where(avail, data, -np.inf) >= min_var_thr).any(axis=1)  # :760-765
+        row_sums = None
+
+        def ref_means_of(idx):                                       # steps.py:276, on demand
+            return data0[idx].sum(axis=1) / n_avail[idx]
+
+        single_val_of = lambda idx: data0[idx].sum(axis=1)          # noqa: E731  n_avail == 1
 
         self.timing['host_groups'] = 1e3 * (time.perf_counter() - t_host0)
         # ---- device residents -----------------------------------------------
         d_stn_x = self._dev(stn_xs)
         d_stn_y = self._dev(stn_ys)
-        d_cell_x = self._dev(dst_xs)
-        d_cell_y = self._dev(dst_ys)
-        d_pos = self._dev(out_pos) if out_pos is not None else None
+        d_cell_x, d_cell_y, d_pos = geo['d_cell_x'], geo['d_cell_y'], geo['d_pos']
         d_data = self._dev(data)
         d_data0 = self._dev(data0)
         ctx = dict(
@@ -343,11 +413,20 @@ class ChunkEngine:
             lo=float(min_var_cut) if min_var_cut is not None else 0.0,
             hi=float(max_var_cut) if max_var_cut is not None else 0.0,
             grp_of_step=grp_of_step, grp_mask=grp_mask, grp_n=grp_n, n_avail=n_avail,
-            min_vg_val=float(min_vg_val), nnb_cache={})
+            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'])
 
         tdtype = torch.float64 if out_f64 else torch.float32
-        flds = {lab: torch.full((n_steps, fld_size), float('nan'), dtype=tdtype,
-                                device=self.device) for lab in interp_labels}
+        # NaN marks cells outside the mask and steps without stations
+        # (steps.py:659-663); when every cell of every step is written the 4-byte
+        # per cell-step prefill is skipped
+        full_cover = (out_pos is None) and bool((n_avail >= 1).all())
+        flds = {}
+        for lab in interp_labels:
+            if full_cover and lab != 'EST_VARS_OK':
+                flds[lab] = torch.empty((n_steps, fld_size), dtype=tdtype, device=self.device)
+            else:
+                flds[lab] = torch.full((n_steps, fld_size), float('nan'), dtype=tdtype,
+                                       device=self.device)
 
         # steps that bypass interpolation for every method
         single_steps = np.where(n_avail == 1)[0]                    # steps.py:282-283
@@ -358,7 +437,7 @@ class ChunkEngine:
                 continue
             out = flds[lab]
             if single_steps.size:
-                self._fill_rows(ctx, out, single_steps, single_val[single_steps])
+                self._fill_rows(ctx, out, single_steps, single_val_of(single_steps))
             multi = n_avail >= 2
             if itype == 'NNB':
                 self._nnb_label(ctx, out, np.where(multi)[0])
@@ -368,7 +447,7 @@ class ChunkEngine:
             elif itype == 'IDW':
                 mean_steps = np.where(multi & ~steps_flags)[0]       # steps.py:312-313
                 if mean_steps.size:
-                    self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
+                    self._fill_rows(ctx, out, mean_steps, ref_means_of(mean_steps))
                 self._idw(ctx, out, np.where(multi & steps_flags)[0], float(interp_args[i][3]))
             elif itype in ('OK', 'SK', 'EDK') and nrst:
                 uniq_vgs = list(dict.fromkeys(vgs))
@@ -387,7 +466,7 @@ class ChunkEngine:
                 bypass = (~steps_flags) | nug[step_vg]               # steps.py:325-331
                 mean_steps = np.where(multi & bypass)[0]
                 if mean_steps.size:
-                    self._fill_rows(ctx, out, mean_steps, ref_means[mean_steps])
+                    self._fill_rows(ctx, out, mean_steps, ref_means_of(mean_steps))
                 ev_out = flds['EST_VARS_OK'] if (ev_flag and itype == 'OK') else None
                 if ev_out is not None and mean_steps.size:          # steps.py:329
                     self._fill_rows(ctx, ev_out, mean_steps, np.zeros(mean_steps.size),
@@ -524,9 +603,92 @@ class ChunkEngine:
         if self.profile_gemm:
             e1.record()
             self.gemm_events.append((e0, e1))
+            self.kernel_events.append(('k_estimate_gemm', 'tensor',
+                                       2.0 * int(n_rows) * int(kpad) * ctx['n_cells'], e0, e1))
         self._count('launches')
         self._count('gemm_launches')
         self._count('gemm_flop', 2 * int(n_rows) * int(kpad) * ctx['n_cells'])
+
+    # ---- local estimator (compact support) ---------------------------------
+    def _local_plan(self, ctx, vg_strs):
+        """[(R, F_var, F_cov)] per variogram if every one is compactly supported
+        (only Nug / Sph / Lin terms) and sparse enough for the local estimator, else
+        None."""
+        x0, x1, y0, y1 = ctx['bbox']
+        area = max((x1 - x0) * (y1 - y0), 1e-300)
+        plan = []
+        for vg_s in vg_strs:
+            terms = _lib.parse_vg_str(vg_s)
+            R = 0.0
+            tot = 0.0
+            for t, sill, rng in terms:
+                if t not in (1, 2, 4):
+                    return None
+                tot = tot + sill                  # same order as pyx:192-201 accumulates
+                if t != 1:
+                    R = max(R, rng)
+            if R <= 0.0:
+                return None
+            if ctx['n_stn'] * math.pi * R * R / area > self.local_max_near:
+                return None
+            plan.append((R, tot))
+        return plan
+
+    def _local_neighbours(self, ctx, K, vg_s, plan_entry):
+        """Stations within the range of every cell and their (vg - F) values;
+        depends on the geometry and the variogram only -> cached across chunks."""
+        R, tot = plan_entry
+        covar = int(K.kind == 1)
+        mv = ctx['min_vg_val']
+        F = 0.0 if covar else tot
+        if F <= mv:
+            F = 0.0                               # pyx:203-216
+        fp = (ctx['geom_fp'], ctx['bbox'], ctx['n_stn'], ctx['stn_xs'].tobytes(),
+              ctx['stn_ys'].tobytes())
+        key = (vg_s, covar, mv, fp)
+        hit = self._local_cache.get(key)
+        if hit is not None:
+            self._count('local_cache_hits')
+            return hit
+        sx, sy = ctx['stn_xs'], ctx['stn_ys']
+        x0, y0 = sx.min() - R, sy.min() - R
+        nbx = int(math.floor((sx.max() + R - x0) / R)) + 1
+        nby = int(math.floor((sy.max() + R - y0) / R)) + 1
+        b = (np.floor((sy - y0) / R).astype(np.int64) * nbx
+             + np.floor((sx - x0) / R).astype(np.int64))
+        order = np.argsort(b, kind='stable').astype(np.int32)
+        bin_start = np.searchsorted(b[order], np.arange(nbx * nby + 1)).astype(np.int32)
+        d_bs, d_bo = self._dev(bin_start), self._dev(order)
+        n_cells = ctx['n_cells']
+        cap = 8
+        while True:
+            cnt = torch.empty(n_cells, dtype=_I32, device=self.device)
+            idx = torch.empty((n_cells, cap), dtype=_I32, device=self.device)
+            val = torch.empty((n_cells, cap), dtype=_F64, device=self.device)
+            L = _lib.spx_local()
+            L.stn_x, L.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
+            L.bin_start, L.bin_stn = d_bs.data_ptr(), d_bo.data_ptr()
+            L.x0, L.y0, L.inv_bin, L.nbx, L.nby = float(x0), float(y0), 1.0 / R, nbx, nby
+            L.R, L.F = float(R), float(F)
+            L.cell_x, L.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
+            L.n_cells = n_cells
+            L.cap = cap
+            L.cnt, L.idx, L.val = cnt.data_ptr(), idx.data_ptr(), val.data_ptr()
+            L.vg = _lib.make_vg(vg_s)
+            L.covar_flag = covar
+            L.min_vg_val = mv
+            _lib.check(self.lib.spx_local_build_dev(C.byref(L), self._stream()), 'local_build')
+            self._count('launches')
+            mx = int(cnt.max().item())
+            if mx <= cap:
+                break
+            cap = mx
+        res = dict(struct=L, F=F, cap=cap, keep=(cnt, idx, val, d_bs, d_bo), max_near=mx)
+        while len(self._local_cache) >= 4:
+            self._local_cache.pop(next(iter(self._local_cache)))
+        self._local_cache[key] = res
+        self.stats['local_max_near'] = mx
+        return res
 
     # ---- 'nrst' neighbour selection ---------------------------------------
     def _topk(self, d_sx, d_sy, n_stn, d_mask, d_cx, d_cy, n_cells, k):
@@ -641,9 +803,9 @@ class ChunkEngine:
         kpad = _pad_up(n_stn, 8)
         grp_of_step = ctx['grp_of_step']
         # distance scale common to every cell (cancels in the ratio)
-        xs = np.concatenate([ctx['dst_xs'], ctx['stn_xs']])
-        ys = np.concatenate([ctx['dst_ys'], ctx['stn_ys']])
-        scale = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
+        bx0, bx1, by0, by1 = ctx['bbox']
+        scale = math.hypot(max(bx1, ctx['stn_xs'].max()) - min(bx0, ctx['stn_xs'].min()),
+                           max(by1, ctx['stn_ys'].max()) - min(by0, ctx['stn_ys'].min()))
         scale = scale if scale > 0 else 1.0
 
         max_grps = max(1, int(self.aux_limit // (n_cells * 8)))
@@ -741,11 +903,15 @@ class ChunkEngine:
         # Many variograms with few steps each (per-step variogram series): the
         # contraction would regenerate its operand tile per variogram; use the
         # per-row-variogram estimator (row-major coefficients) instead.
+        K.local = None
+        if self.local_support and ev_out is None and n_drifts <= 4:
+            K.local = self._local_plan(ctx, [uniq_vgs[int(v)] for v in seg_vgs])
         mv_smem = ((n_stn + n_border) * 64 + 4 * (n_stn + n_border) + 1024) * 8 + 4096
-        K.use_mv = bool(self.multivg and seg_vgs.size >= 8
+        K.use_mv = bool(K.local is None and self.multivg and seg_vgs.size >= 8
                         and K.steps_o.size / seg_vgs.size < 32 and mv_smem <= 220 * 1024)
+        K.row_major = K.use_mv or (K.local is not None)
         K.row_of = np.empty(K.steps_o.size, dtype=np.int64)
-        if K.use_mv:
+        if K.row_major:
             K.row_of[:] = np.arange(K.steps_o.size)
             total_rows = K.steps_o.size
         else:
@@ -763,9 +929,9 @@ class ChunkEngine:
         K.d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8))
 
         # bound for the sum(lambda) screening: |rhs| <= max(vg bound, 1, |drift|)
-        xs = np.concatenate([ctx['dst_xs'], ctx['stn_xs']])
-        ys = np.concatenate([ctx['dst_ys'], ctx['stn_ys']])
-        max_dist = math.hypot(xs.max() - xs.min(), ys.max() - ys.min())
+        bx0, bx1, by0, by1 = ctx['bbox']
+        max_dist = math.hypot(max(bx1, ctx['stn_xs'].max()) - min(bx0, ctx['stn_xs'].min()),
+                              max(by1, ctx['stn_ys'].max()) - min(by0, ctx['stn_ys'].min()))
         rhs_bound = np.array([max(1.0, vg_abs_bound(v, max_dist)) for v in uniq_vgs])
         if kind == 2:
             with np.errstate(invalid='ignore'):
@@ -797,6 +963,36 @@ class ChunkEngine:
 
         K.flags_event = torch.cuda.Event()
         K.flags_event.record(torch.cuda.current_stream(self.device))
+
+        if K.local is not None:
+            coef2d = K.coef.view(-1, kpad)
+            for k in range(seg_vgs.size):
+                r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
+                nbr = self._local_neighbours(ctx, K, uniq_vgs[int(seg_vgs[k])], K.local[k])
+                base = nbr['F'] * coef2d[r0:r1, :n_stn].sum(dim=1)
+                if n_border >= 1:
+                    base = base + coef2d[r0:r1, n_stn]
+                base = base.contiguous()
+                L = nbr['struct']
+                L.coef = coef2d[r0:r1].data_ptr()
+                L.base = base.data_ptr()
+                L.n_rows = r1 - r0
+                L.kpad, L.n_stn, L.n_drifts = kpad, n_stn, n_drifts
+                L.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
+                L.row_dst = d_row_dst[r0:].data_ptr()
+                L.out = out.data_ptr()
+                L.out_ld = ctx['fld_size']
+                L.out_f64 = ctx['out_f64']
+                L.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+                L.has_lo, L.has_hi, L.lo, L.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+                L.rows_all_valid = 1          # row-major rows are exactly the kriged steps
+                stream = self._stream()
+                ev = self._prof_begin()
+                _lib.check(self.lib.spx_estimate_local_dev(C.byref(L), stream), 'estimate_local')
+                self._prof_end(ev, 'k_estimate_local', 'hbm',
+                               (r1 - r0) * n_cells * (8 if ctx['out_f64'] else 4))
+                self._count('launches')
+                self._count('local_rows', r1 - r0)
 
         if K.use_mv:
             d_row_vg = self._dev(step_vg[K.steps_o].astype(np.int32))
@@ -836,7 +1032,7 @@ class ChunkEngine:
             self._count('multivg_evals', int(K.steps_o.size) * n_stn * n_cells)
 
         # ---- main contraction: one launch per variogram segment ----------
-        for k in range(seg_vgs.size if not K.use_mv else 0):
+        for k in range(seg_vgs.size if not K.row_major else 0):
             seg_coef = K.coef[seg_row0[k] * kpad:]
             with self._phase('gemm'):
                 self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad,
@@ -1096,7 +1292,7 @@ class ChunkEngine:
             resid = None
             if rhs_sys.size:
                 resid = self._lu_solve(ctx, K, T, rhs_sys, rhs_kind, rhs_arg, rhs_row, K.coef,
-                                       want_resid=want_resid, row_major=K.use_mv)
+                                       want_resid=want_resid, row_major=K.row_major)
             for k, sid in enumerate(ids):
                 K.keep[int(sid)] = (T, k)
 
@@ -1209,10 +1405,8 @@ class ChunkEngine:
             rkind[pos_ones] = 1
             d_resid = torch.zeros(n_rhs, dtype=_F64, device=self.device)
             d_info = torch.zeros(nsys, dtype=_I32, device=self.device)
-            ts = [self._dev(r), self._dev(miss_off), self._dev(miss_list),
-                  self._dev(K.sys_n[ids]), self._dev(K.stn_off[grp]),
-                  self._dev(rhs_off), self._dev(rhs_cnt), self._dev(urow), self._dev(rrow),
-                  self._dev(rkind)]
+            ts = self._dev_pack([r, miss_off, miss_list, K.sys_n[ids], K.stn_off[grp],
+                                 rhs_off, rhs_cnt, urow, rrow, rkind])
             D = _lib.spx_downdate()
             D.n_sys = nsys
             D.n_stn = n_stn
@@ -1225,7 +1419,7 @@ class ChunkEngine:
             D.ut = Ut.data_ptr()
             D.kpad = K.kpad
             D.coef = K.coef.data_ptr()
-            D.coef_row_major = int(K.use_mv)
+            D.coef_row_major = int(K.row_major)
             D.resid = d_resid.data_ptr()
             D.info = d_info.data_ptr()
             _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')

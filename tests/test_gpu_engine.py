@@ -16,10 +16,16 @@ KRG_TOL = 1e-9
 IDW_TOL = 1e-12
 
 
-@pytest.fixture(scope='module')
-def eng():
+@pytest.fixture(scope='module', params=['auto', 'dense'])
+def eng(request):
+    """'auto': the engine picks its estimator (local compact-support estimator for
+    Nug + Sph / Lin variograms with few stations in range, tensor-core contraction
+    otherwise); 'dense': always the contraction."""
     from spinterps_b200.engine import ChunkEngine
-    return ChunkEngine()
+    e = ChunkEngine()
+    if request.param == 'dense':
+        e.local_support = False
+    return e
 
 
 def _tol(label):
@@ -182,7 +188,8 @@ def test_per_step_variograms_multivg(eng):
     kw = dict(interp_args=args, vgs=vgs, cntn_idxs=mask, drft_arrs=drft, stns_drft=sdrft, **p)
     exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
-    assert eng.stats.get('multivg_evals', 0) > 0
+    if not eng.local_support:
+        assert eng.stats.get('multivg_evals', 0) > 0
     assert eng.stats.get('pinv_systems', 0) > 0      # the Hol systems (cond > 1e16)
     for lab, ref in exp.items():
         per_step = [rel_err(got[lab][t], ref[t], _floor(ref)) for t in range(14)]
@@ -201,3 +208,32 @@ def test_per_step_variograms_multivg(eng):
                 m = np.isfinite(ref[t])
                 same = np.abs(got[lab][t][m] - ref[t][m]) <= 1e-6 * np.maximum(1.0, np.abs(ref[t][m]))
                 assert same.mean() >= 0.8, (lab, t, same.mean())
+
+
+def test_local_estimator_is_used_and_matches_dense():
+    """Compact variogram, sparse stations: the local estimator (stations within the
+    range of each cell + the constant far field) must give the dense contraction's
+    numbers; EDK with two drifts, SK, a mask, cut-offs, missing data."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(51, 150, 30, 60, 70, cell=3000.0, miss=0.2)
+    cx, cy = p['cell_xs'], p['cell_ys']
+    mask = ((cx - 1.0e5) / 9e4) ** 2 + ((cy - 9e4) / 8e4) ** 2 <= 1.0
+    drft = np.vstack([100 + 0.002 * cx + 0.001 * cy, np.cos(cx / 4e4)])[:, mask]
+    sdrft = np.column_stack([100 + 0.002 * p['stn_xs'] + 0.001 * p['stn_ys'],
+                             np.cos(p['stn_xs'] / 4e4)])
+    p['cell_xs'], p['cell_ys'] = cx[mask], cy[mask]
+    vgs = ['0.1 Nug(0.0) + 0.9 Sph(20000)'] * 15 + ['0.2 Nug(0.0) + 0.5 Sph(15000) + 0.3 Lin(30000)'] * 15
+    args = [('OK', None, 'OK'), ('SK', None, 'SK'), ('EDK', None, 'EDK')]
+    kw = dict(interp_args=args, vgs=vgs, cntn_idxs=mask, drft_arrs=drft, stns_drft=sdrft,
+              min_var_cut=0.0, max_var_cut=30.0, **p)
+    e1 = ChunkEngine()
+    got, _ = e1.interp_chunk(intrp_dtype=np.float64, **kw)
+    assert e1.stats.get('local_rows', 0) > 0 and e1.stats.get('gemm_launches', 0) <= 2
+    e2 = ChunkEngine()
+    e2.local_support = False
+    ref, _ = e2.interp_chunk(intrp_dtype=np.float64, **kw)
+    assert e2.stats.get('local_rows', 0) == 0
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    for lab in ('OK', 'SK', 'EDK'):
+        assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
+        assert rel_err(got[lab], exp[lab], _floor(exp[lab])) <= KRG_TOL, lab
