@@ -350,6 +350,14 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
 int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
                          const uint8_t* cell_bad, uint8_t* fail, void* stream);
 
+/* Ascending column indices of the set (want = 1) / clear (want = 0) entries of the
+ * rows row_sel[0..n_sel) of a [*, n_cols] byte mask, written to out + off[i] (offsets
+ * computed by the caller from the per-row counts): station / missing-station lists
+ * of the availability groups (interp/grps.py:57-101) on the device. */
+int spx_mask_lists_dev(const uint8_t* mask, int32_t n_cols, const int32_t* row_sel,
+                       int32_t n_sel, const int64_t* off, int32_t want, int32_t* out,
+                       void* stream);
+
 /* out[row_dst[r], cell_pos[c]] = aux[row_slot[r], c] (0.0 if aux == NULL), restricted to
  * fail[row_fail[r], c] != 0 when fail != NULL; no clamp.  Spreads the per-system
  * estimation variance to the steps of the system (interp/steps.py:431-434, :821-831)

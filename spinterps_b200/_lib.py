@@ -194,6 +194,8 @@ _SIGS = {
     'spx_nrst_solve_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
     'spx_nrst_krige_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
     'spx_nrst_idw_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p, C.c_void_p]),
+    'spx_mask_lists_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_void_p]),
     'spx_bcast_rows_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int32, C.c_void_p]),

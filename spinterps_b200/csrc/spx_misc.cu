@@ -228,6 +228,29 @@ __global__ void __launch_bounds__(256) k_lambda_check(const double* __restrict__
     }
 }
 
+// Column indices of the set (want = 1) or clear (want = 0) entries of selected rows
+// of a [*, n_cols] byte mask, written at host-computed offsets: the station lists of
+// the availability groups without a host-side np.where over the whole mask.  One
+// warp per selected row, ballot / popc compaction (ascending order).
+__global__ void __launch_bounds__(256) k_mask_lists(const uint8_t* __restrict__ mask, int n_cols,
+                                                    const int32_t* __restrict__ row_sel,
+                                                    int n_sel, const int64_t* __restrict__ off,
+                                                    int want, int32_t* __restrict__ out) {
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= n_sel) return;
+    const uint8_t* __restrict__ m = mask + (int64_t)row_sel[w] * n_cols;
+    int32_t* __restrict__ o = out + off[w];
+    int base = 0;
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int c = c0 + lane;
+        const bool hit = (c < n_cols) && ((m[c] != 0) == (want != 0));
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hit) o[base + __popc(b & ((1u << lane) - 1u))] = c;
+        base += __popc(b);
+    }
+}
+
 // Small device -> (mapped, pinned) host copy done by SMs instead of a DMA engine:
 // a cudaMemcpyAsync D2H would queue behind any large field download in flight on
 // the copy engine and stall the compute stream for its whole duration.
@@ -334,6 +357,17 @@ int spx_fill_rows_dev(const double* vals, const int32_t* row_dst, int64_t n_rows
                                                         out, out_ld, out_f64, has_lo, has_hi, lo,
                                                         hi);
     SPX_CHECK_LAUNCH("k_fill_rows");
+    return SPX_OK;
+}
+
+int spx_mask_lists_dev(const uint8_t* mask, int32_t n_cols, const int32_t* row_sel,
+                       int32_t n_sel, const int64_t* off, int32_t want, int32_t* out,
+                       void* stream) {
+    if (n_sel == 0) return SPX_OK;
+    const int64_t threads = (int64_t)n_sel * 32;
+    k_mask_lists<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        mask, n_cols, row_sel, n_sel, off, want, out);
+    SPX_CHECK_LAUNCH("k_mask_lists");
     return SPX_OK;
 }
 

@@ -172,6 +172,17 @@ class ChunkEngine:
             out.append(d[o:o + a.nbytes].view(tdt).view(a.shape))
         return out
 
+    def _mask_lists(self, ctx, rows_sel, offs, total, want):
+        """Station index lists of mask rows on the device (spx_mask_lists_dev)."""
+        out = torch.empty(max(int(total), 1), dtype=_I32, device=self.device)
+        d_rows, d_off = self._dev_pack([np.asarray(rows_sel, dtype=np.int32),
+                                        np.asarray(offs, dtype=np.int64)])
+        _lib.check(self.lib.spx_mask_lists_dev(
+            self._ptr(ctx['d_grp_mask']), ctx['n_stn'], self._ptr(d_rows), int(len(rows_sel)),
+            self._ptr(d_off), int(want), self._ptr(out), self._stream()), 'mask_lists')
+        self._count('launches')
+        return out
+
     def _sync_uploads(self):
         """Make the compute stream wait for every upload issued so far."""
         if self._h2d_dirty:
@@ -384,7 +395,6 @@ class ChunkEngine:
         n_avail = grp_n[grp_of_step]
         problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
 
-        data0 = np.nan_to_num(data, nan=0.0, posinf=np.inf, neginf=-np.inf)
         if min_var_thr == -np.inf:
             steps_flags = n_avail >= 1                               # nothing is below -inf
         else:
@@ -393,9 +403,9 @@ class ChunkEngine:
         row_sums = None
 
         def ref_means_of(idx):                                       # steps.py:276, on demand
-            return data0[idx].sum(axis=1) / n_avail[idx]
+            return np.nansum(data[idx], axis=1) / n_avail[idx]
 
-        single_val_of = lambda idx: data0[idx].sum(axis=1)          # noqa: E731  n_avail == 1
+        single_val_of = lambda idx: np.nansum(data[idx], axis=1)    # noqa: E731  n_avail == 1
 
         self.timing['host_groups'] = 1e3 * (time.perf_counter() - t_host0)
         # ---- device residents -----------------------------------------------
@@ -403,7 +413,11 @@ class ChunkEngine:
         d_stn_y = self._dev(stn_ys)
         d_cell_x, d_cell_y, d_pos = geo['d_cell_x'], geo['d_cell_y'], geo['d_pos']
         d_data = self._dev(data)
-        d_data0 = self._dev(data0)
+        self._sync_uploads()
+        d_data0 = torch.nan_to_num(d_data, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
+        # availability masks on the device (+ one all-ones row = "every station")
+        d_grp_mask = self._dev(np.concatenate(
+            [grp_mask.view(np.uint8), np.ones((1, n_stn), dtype=np.uint8)], axis=0))
         ctx = dict(
             n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
             d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
@@ -413,7 +427,8 @@ class ChunkEngine:
             lo=float(min_var_cut) if min_var_cut is not None else 0.0,
             hi=float(max_var_cut) if max_var_cut is not None else 0.0,
             grp_of_step=grp_of_step, grp_mask=grp_mask, grp_n=grp_n, n_avail=n_avail,
-            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'])
+            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'],
+            d_grp_mask=d_grp_mask)
 
         tdtype = torch.float64 if out_f64 else torch.float32
         # NaN marks cells outside the mask and steps without stations
@@ -874,11 +889,11 @@ class ChunkEngine:
         stn_off = np.zeros(n_grps + 1, dtype=np.int64)
         stn_off[grps_used] = np.concatenate([[0], np.cumsum(grp_n[grps_used])])[:-1]
         stn_off[n_grps] = int(grp_n[grps_used].sum())
-        stn_list = np.concatenate([np.where(grp_mask[grps_used])[1],
-                                   np.arange(n_stn)]).astype(np.int32)
         K.stn_off = stn_off
-        K.d_stn_list = self._dev(stn_list)
         K.full_grp = n_grps
+        rows_sel = np.concatenate([grps_used, [n_grps]]).astype(np.int32)
+        K.d_stn_list = self._mask_lists(ctx, rows_sel, stn_off[rows_sel],
+                                        int(stn_off[n_grps]) + n_stn, want=1)
 
         # systems = distinct (group, variogram) pairs among the steps
         pair = grp_of_step[steps].astype(np.int64) * len(uniq_vgs) + step_vg[steps]
@@ -1363,7 +1378,6 @@ class ChunkEngine:
                             self._ginv_cache[(base_key, K.uniq_vgs[int(v)])] = ginv_of[int(v)]
                 return bool(bad.any())
             finishers.append(finish_full)
-        miss_mask_all = ~ctx['grp_mask']
         for vi, v in enumerate(vgs_here):
             ids = sys_ids[K.sys_vg[sys_ids] == v]
             if not ids.size:
@@ -1371,8 +1385,9 @@ class ChunkEngine:
             G = ginv_of[int(v)]
             grp = K.sys_grp[ids]
             r = (n_stn - K.sys_n[ids]).astype(np.int32)
-            miss_list = np.where(miss_mask_all[grp])[1].astype(np.int32)
             miss_off = np.concatenate([[0], np.cumsum(r)])[:-1].astype(np.int64)
+            d_miss_list = self._mask_lists(ctx, grp.astype(np.int32), miss_off, int(r.sum()),
+                                           want=0)
             # right-hand sides: data rows of every system + one ones-vector each
             ridx = K.rows_by_sys[np.isin(K.sys_o[K.rows_by_sys], ids)]   # grouped by system
             cnt = (K.sys_row_beg[ids + 1] - K.sys_row_beg[ids]).astype(np.int64)
@@ -1383,9 +1398,10 @@ class ChunkEngine:
             self._sync_uploads()
             Bt = torch.zeros((n_data + nsys, M), dtype=_F64, device=self.device)
             Bt[:n_data, :n_stn] = ctx['d_data0'].index_select(0, d_steps)
-            d_maskf = self._dev(ctx['grp_mask'][grp].astype(np.float64))
+            d_grp = self._dev(grp.astype(np.int64))
             self._sync_uploads()
-            Bt[n_data:, :n_stn] = d_maskf
+            d_maskf = ctx['d_grp_mask'].index_select(0, d_grp)
+            Bt[n_data:, :n_stn] = d_maskf.to(_F64)
             Ut = torch.matmul(Bt, G)
             self._count('launches')
             # per-system contiguous rhs lists: its data rows then its ones-vector
@@ -1405,8 +1421,9 @@ class ChunkEngine:
             rkind[pos_ones] = 1
             d_resid = torch.zeros(n_rhs, dtype=_F64, device=self.device)
             d_info = torch.zeros(nsys, dtype=_I32, device=self.device)
-            ts = self._dev_pack([r, miss_off, miss_list, K.sys_n[ids], K.stn_off[grp],
-                                 rhs_off, rhs_cnt, urow, rrow, rkind])
+            ts = self._dev_pack([r, miss_off, np.zeros(1, dtype=np.int32), K.sys_n[ids],
+                                 K.stn_off[grp], rhs_off, rhs_cnt, urow, rrow, rkind])
+            ts[2] = d_miss_list
             D = _lib.spx_downdate()
             D.n_sys = nsys
             D.n_stn = n_stn

@@ -62,12 +62,28 @@ def test_coef_offset_is_a_bijection_on_a_tile():
     assert lib.spx_coef_offset(256, 0, kpad) == 256 * kpad
 
 
-def test_struct_layouts_match_header_sizes():
-    # a changed header without the matching ctypes change would corrupt arguments
-    assert C.sizeof(_lib.spx_vg) == 168
-    assert _lib.VG_DTYPE.itemsize == 168
-    assert C.sizeof(_lib.spx_systems) == 8 + 13 * 8 + 8
-    assert C.sizeof(_lib.spx_rhs) == 8 + 5 * 8 + 8 + 2 * 8 + 2 * 8
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """sizeof / last-field offset of every struct of the header, as the C compiler
+    sees them, equal the ctypes mirrors (a drifted mirror would corrupt arguments)."""
+    import subprocess
+    structs = {'spx_vg': 'ranges', 'spx_systems': 'max_m', 'spx_rhs': 'coef_row_major',
+               'spx_downdate': 'coef_row_major', 'spx_gemm': 'quad_slot',
+               'spx_multivg': 'all_fast', 'spx_local': 'rows_all_valid', 'spx_nrst': 'idw_exp'}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "spx_b200.h"', 'int main(void){']
+    for name, last in structs.items():
+        src.append(f'printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {last}));')
+    src.append('return 0;}')
+    c = tmp_path / 'sz.c'
+    c.write_text('\n'.join(src))
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', '-I', str(ROOT / 'include'), str(c), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        name, size, off = line.split()
+        ct = getattr(_lib, name)
+        assert C.sizeof(ct) == int(size), (name, C.sizeof(ct), size)
+        assert getattr(ct, structs[name]).offset == int(off), (name, 'last field offset')
+    assert _lib.VG_DTYPE.itemsize == C.sizeof(_lib.spx_vg)
 
 
 def test_compute_fails_loudly_without_gpu():
