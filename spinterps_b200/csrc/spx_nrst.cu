@@ -958,12 +958,16 @@ __device__ __forceinline__ void local_rows(const LocalEstArgs& a, const double* 
     }
 }
 
-template <bool CLAMP>
+template <bool CLAMP, int ROWS>
 __global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
-    __shared__ double sbase[LOC_ROWS];
-    __shared__ int64_t soff[LOC_ROWS];
-    const int64_t r_beg = (int64_t)blockIdx.y * LOC_ROWS;
-    const int nr = (int)min((int64_t)LOC_ROWS, a.n_rows - r_beg);
+    __shared__ double sbase[ROWS];
+    __shared__ int64_t soff[ROWS];
+    const int64_t r_beg = (int64_t)blockIdx.y * ROWS;
+    const int nr = (int)min((int64_t)ROWS, a.n_rows - r_beg);
+    for (int i = threadIdx.x + 256; i < nr; i += 256) {   // ROWS > 256 not used, kept general
+        sbase[i] = a.base[r_beg + i];
+        soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
+    }
     if (threadIdx.x < nr) {
         sbase[threadIdx.x] = a.base[r_beg + threadIdx.x];
         soff[threadIdx.x] = (int64_t)a.row_dst[r_beg + threadIdx.x] * a.out_ld;
@@ -1070,9 +1074,20 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const bool drift = l->n_drifts > 0;
     if (!l->out_f64 && !drift && l->cell_pos == nullptr && l->rows_all_valid) {
-        dim3 g1((unsigned)((l->n_cells + 255) / 256), (unsigned)row_blocks);
-        if (l->has_lo || l->has_hi) k_estimate_local_fast<true><<<g1, 256, 0, st>>>(a);
-        else k_estimate_local_fast<false><<<g1, 256, 0, st>>>(a);
+        static const int rows_knob = getenv("SPX_LOCAL_ROWS") ? atoi(getenv("SPX_LOCAL_ROWS")) : 64;
+        const bool clamp = l->has_lo || l->has_hi;
+        const int rows = (rows_knob == 16 || rows_knob == 256) ? rows_knob : 64;
+        dim3 g1((unsigned)((l->n_cells + 255) / 256), (unsigned)((l->n_rows + rows - 1) / rows));
+        if (rows == 16) {
+            if (clamp) k_estimate_local_fast<true, 16><<<g1, 256, 0, st>>>(a);
+            else k_estimate_local_fast<false, 16><<<g1, 256, 0, st>>>(a);
+        } else if (rows == 256) {
+            if (clamp) k_estimate_local_fast<true, 256><<<g1, 256, 0, st>>>(a);
+            else k_estimate_local_fast<false, 256><<<g1, 256, 0, st>>>(a);
+        } else {
+            if (clamp) k_estimate_local_fast<true, 64><<<g1, 256, 0, st>>>(a);
+            else k_estimate_local_fast<false, 64><<<g1, 256, 0, st>>>(a);
+        }
         SPX_CHECK_LAUNCH("k_estimate_local_fast");
         return SPX_OK;
     }
