@@ -316,6 +316,17 @@ def run_gpu(args):
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
+    # per-entry-point breakdown of one resident step (events around every library call;
+    # separate from the timed region above)
+    eng.trace = []
+    eng.trace_launches = True
+    n_tr = max(2, min(args.steps, 4))
+    ms_tr, _ = timed(run_resident, n_tr)
+    eng.trace_launches = False
+    breakdown = {k_: {'ms_per_step': round(v['ms'] / n_tr, 4), 'calls_per_step': v['n'] / n_tr}
+                 for k_, v in sorted(eng.trace_summary().items(), key=lambda kv: -kv[1]['ms'])}
+    eng.trace = []
+
     # the tensor-core contraction on the same workload (local estimator off), so that
     # both estimators are on record
     eng.local_support = False
@@ -402,6 +413,7 @@ def run_gpu(args):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches_timed),
             'roofline': roofline(dom),
+            'step_breakdown': {'ms_per_step_traced': ms_tr / n_tr, 'entry_points': breakdown},
             'dense_path': {
                 'note': 'same workload with the local estimator disabled: every estimate goes '
                         'through the fused variogram-fill + DMMA contraction',

@@ -438,10 +438,11 @@ __global__ void __launch_bounds__(256) k_lu_solve(spx_systems s, spx_rhs r) {
 
 constexpr int DD_RB = 8;  // right-hand sides per batch (one per warp)
 
-__global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
+__global__ void __launch_bounds__(256) k_downdate(spx_downdate d, int r_lo) {
     extern __shared__ double dsm[];
     const int sys = blockIdx.x;
     const int r = d.sys_r[sys];
+    if (r <= r_lo) return;   // handled by k_downdate_reg
     const int n = d.sys_n[sys];
     const int M = d.n_stn + d.n_border;
     const int ld = d.max_r | 1;  // odd pitch: row swaps hit distinct banks
@@ -468,60 +469,90 @@ __global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
         S[i + (size_t)j * ld] = G[(int64_t)mi[j] * M + mi[i]];
     }
     __syncthreads();
-    // ---- LU of S in shared memory, partial pivoting
-    for (int k = 0; k < r; ++k) {
-        double bv = -1.0;
-        int bi = k;
-        const double* colk = S + (size_t)k * ld;
-        for (int i = k + tid; i < r; i += 256) {
-            const double a = fabs(colk[i]);
-            if (a > bv) { bv = a; bi = i; }
-        }
+    // ---- LU of S in shared memory, partial pivoting, ONE block barrier per column.
+    // For r ~ 100 the factorisation is a chain of r dependent steps, so barriers and
+    // shared-memory round trips (not flops) set its duration:
+    //  * pivoting is implicit (rows stay in place, each lane keeps a bit mask of the rows
+    //    it owns that were already used as pivots) -- no swap phase;
+    //  * every warp repeats the pivot search of column k for itself -- no broadcast phase;
+    //  * the multipliers l_i are kept in registers and written over column k one step
+    //    later, when nobody reads that column any more -- no scale phase.
+    // Rows are brought into pivot order afterwards, one warp per column.
+    {
+        constexpr int RT = 128, NCG = 2, RQ = 2;   // 128 row slots x 2 column groups
+        const int rslot = tid & (RT - 1), cg = tid >> 7;
+        uint32_t used = 0;          // bit b: row lane + 32 b has been a pivot row
+        double lprev[RQ] = {0.0, 0.0};
+        for (int k = 0; k < r; ++k) {
+            const double* ck = S + (size_t)k * ld;
+            double bv = -1.0;
+            int bi = 0x7fffffff;
+            for (int i = lane, b = 0; i < r; i += 32, ++b) {
+                if ((used >> b) & 1u) continue;
+                const double a = fabs(ck[i]);
+                if (a > bv) { bv = a; bi = i; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
-        __syncthreads();
-        if (wid == 0) {
-            bv = lane < 8 ? red_v[lane] : -2.0;
-            bi = lane < 8 ? red_i[lane] : 0x7fffffff;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            if (lane == 0) {
-                s_p = bi;
-                s_pv = colk[bi];
-                pv[k] = bi;
+            const int p = bi;
+            if (tid == 0) {
+                pv[k] = p;
                 if (!(bv > 0.0) && s_info == 0) s_info = k + 1;
             }
-        }
-        __syncthreads();
-        const int p = s_p;
-        const double pvv = s_pv;
-        if (p != k)
-            for (int j = tid; j < r; j += 256) {
-                const double t = S[k + (size_t)j * ld];
-                S[k + (size_t)j * ld] = S[p + (size_t)j * ld];
-                S[p + (size_t)j * ld] = t;
+            const double pvv = ck[p];
+            const double* rowp = S + p;
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) {
+                const int i = rslot + RT * q;
+                const bool live = i < r && !((used >> (i >> 5)) & 1u) && i != p;
+                // multipliers of the previous column (deferred store, see above)
+                if (cg == 0 && k > 0 && i < r && !((used >> (i >> 5)) & 1u) )
+                    S[i + (size_t)(k - 1) * ld] = lprev[q];
+                if (!live) { lprev[q] = 0.0; continue; }
+                const double li = (pvv != 0.0) ? ck[i] / pvv : ck[i];
+                lprev[q] = li;
+                double* rowi = S + i;
+                int j = k + 1 + cg;
+                for (; j + 3 * NCG < r; j += 4 * NCG) {
+                    const size_t o0 = (size_t)j * ld, o1 = o0 + (size_t)NCG * ld,
+                                 o2 = o1 + (size_t)NCG * ld, o3 = o2 + (size_t)NCG * ld;
+                    const double u0 = rowp[o0], u1 = rowp[o1], u2 = rowp[o2], u3 = rowp[o3];
+                    const double a0 = rowi[o0], a1 = rowi[o1], a2 = rowi[o2], a3 = rowi[o3];
+                    rowi[o0] = fma(-li, u0, a0);
+                    rowi[o1] = fma(-li, u1, a1);
+                    rowi[o2] = fma(-li, u2, a2);
+                    rowi[o3] = fma(-li, u3, a3);
+                }
+                for (; j < r; j += NCG) {
+                    const size_t o0 = (size_t)j * ld;
+                    rowi[o0] = fma(-li, rowp[o0], rowi[o0]);
+                }
             }
-        __syncthreads();
-        double* ck = S + (size_t)k * ld;
-        if (pvv != 0.0)
-            for (int i = k + 1 + tid; i < r; i += 256) ck[i] = ck[i] / pvv;
-        __syncthreads();
-        for (int j = k + 1 + wid; j < r; j += 8) {
-            double* cj = S + (size_t)j * ld;
-            const double ukj = cj[k];
-            for (int i = k + 1 + lane; i < r; i += 32) cj[i] = fma(-ck[i], ukj, cj[i]);
+            if ((p & 31) == lane) used |= 1u << (p >> 5);
+            __syncthreads();
         }
-        __syncthreads();
+        // rows into pivot order: S[m, j] <- S[pv[m], j]; a column belongs to one warp
+        for (int j = wid; j < r; j += 8) {
+            double* cj = S + (size_t)j * ld;
+            double t[6];
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const int m = lane + 32 * b;
+                t[b] = (m < r) ? cj[pv[m]] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const int m = lane + 32 * b;
+                if (m < r) cj[m] = t[b];
+            }
+        }
     }
+    __syncthreads();
     if (tid == 0) d.info[sys] = s_info;
 
     // ---- right-hand sides, DD_RB at a time
@@ -534,13 +565,7 @@ __global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
             // y = S^-1 u[Mi] : one warp per right-hand side, warp-synchronous
             double* y = ys + (size_t)wid * ld;
             const double* u = d.ut + (int64_t)d.rhs_urow[q0 + base + wid] * M;
-            for (int i = lane; i < r; i += 32) y[i] = u[mi[i]];
-            __syncwarp();
-            if (lane == 0)
-                for (int k = 0; k < r; ++k) {
-                    const int p = pv[k];
-                    if (p != k) { const double t = y[k]; y[k] = y[p]; y[p] = t; }
-                }
+            for (int i = lane; i < r; i += 32) y[i] = u[mi[pv[i]]];   // rows in pivot order
             __syncwarp();
             for (int k = 0; k < r - 1; ++k) {
                 const double xk = y[k];
@@ -569,6 +594,256 @@ __global__ void __launch_bounds__(256) k_downdate(spx_downdate d) {
                 const double gv = G[(int64_t)mi[j] * M + ki];
 #pragma unroll
                 for (int w = 0; w < DD_RB; ++w) acc[w] = fma(-gv, ys[(size_t)w * ld + j], acc[w]);
+            }
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w) {
+                if (w >= nb) break;
+                const int64_t q = q0 + base + w;
+                const int64_t row = d.rhs_row[q];
+                if (row >= 0)
+                    d.coef[d.coef_row_major ? row * (int64_t)d.kpad + ki
+                                            : coef_offset(row, ki, d.kpad)] = acc[w];
+                if (d.rhs_kind[q] == 1)
+                    atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// Register-resident variant: S = G[Mi, Mi] never touches shared memory.  The CTA is a
+// 16 x 32 thread grid (warp = row class, lane = column class, both cyclic), thread
+// (w, l) keeps S[w + 16 a, l + 32 b] in registers.  S is inverted in place by
+// Gauss-Jordan elimination with implicit row pivoting: rows never move (they could
+// not, in registers); a step publishes column k and the scaled pivot row through two
+// small shared buffers and every thread updates its TA x TB tile -- all rows, all
+// columns, so that no substitution phase is left:  y = S^-1 u_Mi  is a product with
+// the tile.  With rows in place the result is phys[p_k, j] = S^-1[k, p_j]  (p_k = pivot
+// row of column k), hence  y_k = sum_j phys[p_k, j] u_Mi[p_j].
+// Two block barriers per column, ~TA + TB shared loads and TA * TB DFMA per thread;
+// the LU-in-shared-memory kernel above spends its time on shared-memory wavefronts
+// (r^3 / 3 elements read + written) and on barriers instead.
+template <int TA, int TB>
+__global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_lo, int r_hi, int force_pivot) {
+    constexpr int RP = 32 * TB;          // padded order (columns); rows: 16 * TA <= RP
+    static_assert(16 * TA <= RP, "tile shape");
+    const int sys = blockIdx.x;
+    const int r = d.sys_r[sys];
+    if (r <= r_lo || r > r_hi) return;   // another instantiation's system
+    const int n = d.sys_n[sys];
+    const int M = d.n_stn + d.n_border;
+    __shared__ double colbuf[2][RP];
+    __shared__ double rowbuf[2][RP];
+    __shared__ double ys[DD_RB][RP];
+    __shared__ double bp[DD_RB][RP];
+    __shared__ int mi[RP];
+    __shared__ int pv[RP];               // pivot row of column k
+    __shared__ int rk[RP];               // column whose pivot row is i
+    __shared__ int s_info;
+    __shared__ int s_fail;
+    __shared__ double s_sgn;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t* __restrict__ miss = d.miss_list + d.sys_miss_off[sys];
+    const int32_t* __restrict__ stn = d.stn_list + d.sys_stn_off[sys];
+    const double* __restrict__ G = d.ginv;
+    if (tid == 0) s_info = 0;
+    for (int i = tid; i < RP; i += 512) mi[i] = (i < r) ? miss[i] : 0;
+    __syncthreads();
+
+    double S[TA][TB];
+    auto load_S = [&]() {
+#pragma unroll
+        for (int a = 0; a < TA; ++a) {
+            const int i = wid + 16 * a;
+#pragma unroll
+            for (int b = 0; b < TB; ++b) {
+                const int j = lane + 32 * b;
+                S[a][b] = (i < r && j < r) ? G[(int64_t)mi[i] * M + mi[j]] : 0.0;
+            }
+        }
+    };
+    load_S();
+
+    // ---- fast path: no pivoting.  For a valid variogram S is a principal submatrix of
+    // the inverse of a (conditionally) definite system and is itself definite, so the
+    // diagonal pivots are safe and known in advance: the owners of row k and column k
+    // publish them at the top of step k straight from their registers, ONE barrier per
+    // column, every tile index a compile-time constant (outer loops unrolled over the
+    // register slots).  A pivot that is zero, not finite or of the wrong sign (S not
+    // definite) abandons the result and the pivoted elimination below runs instead.
+    if (tid < RP) { pv[tid] = tid; rk[tid] = tid; }
+    if (tid == 0) s_fail = force_pivot;
+    __syncthreads();
+    if (!force_pivot) {
+#pragma unroll
+        for (int a0 = 0; a0 < TA; ++a0) {
+                        const int kb = a0 >> 1;          // 32-column slot of columns 16 a0 .. 16 a0 + 15
+#pragma unroll 1
+            for (int w = 0; w < 16; ++w) {
+                const int k = 16 * a0 + w;
+                if (k >= r) break;
+                const int cur = k & 1, kl = k & 31;
+                const bool prow = wid == w;
+                if (prow) {
+                    const double pvv = __shfl_sync(0xffffffffu, S[a0][kb], kl);
+                    const double inv = (pvv != 0.0) ? 1.0 / pvv : 1.0;
+                    if (lane == 0) {
+                        if (k == 0) s_sgn = pvv;
+                        const double sg = (k == 0) ? pvv : s_sgn;
+                        if (!(pvv * sg > 0.0) || !(fabs(pvv) < 1.0e300)) s_fail = 1;
+                    }
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) {
+                        const double v = (b == kb && lane == kl) ? inv : S[a0][b] * inv;
+                        S[a0][b] = v;
+                        rowbuf[cur][lane + 32 * b] = v;
+                    }
+                }
+                if (lane == kl) {
+#pragma unroll
+                    for (int a = 0; a < TA; ++a) {
+                        const bool piv = prow && a == a0;
+                        colbuf[cur][wid + 16 * a] = piv ? 0.0 : S[a][kb];
+                        if (!piv) S[a][kb] = 0.0;
+                    }
+                }
+                __syncthreads();
+                double u[TB];
+#pragma unroll
+                for (int b = 0; b < TB; ++b) u[b] = rowbuf[cur][lane + 32 * b];
+#pragma unroll
+                for (int a = 0; a < TA; ++a) {
+                    const double f = colbuf[cur][wid + 16 * a];
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) S[a][b] = fma(-f, u[b], S[a][b]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const bool pivoted = s_fail != 0;
+    if (pivoted) {
+    __syncthreads();
+    load_S();
+    uint32_t used = 0;   // bit q: row lane + 32 q has been a pivot row (search bookkeeping)
+    // The column loop is split by register slot kb = k / 32 (unrolled), so that the tile
+    // index of column k is a compile-time constant inside: no selects over registers.
+#pragma unroll
+    for (int kb = 0; kb < TB; ++kb) {
+        const int kend = min(r, 32 * (kb + 1));
+        for (int k = 32 * kb; k < kend; ++k) {
+            const int cur = k & 1;
+            const bool kcol = lane == (k & 31);
+            // (1) publish column k and replace it by zeros: with the 1 / pivot put into
+            // the pivot row below, the column becomes e_p * (1 / pivot) and the uniform
+            // row operation of (3) turns it into column k of the in-place inverse
+            if (kcol) {
+#pragma unroll
+                for (int a = 0; a < TA; ++a) {
+                    colbuf[cur][wid + 16 * a] = S[a][kb];
+                    S[a][kb] = 0.0;
+                }
+            }
+            __syncthreads();
+            // (2) every warp finds the pivot row for itself.  The comparison key is the
+            // high word of |v| (sign stripped): monotone in |v|, 20 mantissa bits -- any
+            // element within 1e-6 of the largest is as good a pivot -- and it turns the
+            // warp arg-max into one REDUX + one ballot.
+            unsigned key = 0;
+            int bi = 0;
+#pragma unroll
+            for (int q = 0; q < TB; ++q) {
+                const int i = lane + 32 * q;
+                if (i < r && !((used >> q) & 1u)) {
+                    const unsigned kk =
+                        ((unsigned)__double2hiint(colbuf[cur][i]) & 0x7fffffffu) + 1u;
+                    if (kk > key) { key = kk; bi = i; }
+                }
+            }
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+            const unsigned bal = __ballot_sync(0xffffffffu, key == kmax);
+            const int p = __shfl_sync(0xffffffffu, bi, __ffs(bal) - 1);
+            if ((p & 31) == lane) used |= 1u << (p >> 5);
+            if (wid == (p & 15)) {       // the warp that owns the pivot row scales it
+                const double pvv = colbuf[cur][p];
+                const double inv = (pvv != 0.0) ? 1.0 / pvv : 1.0;
+                const int a0 = p >> 4;
+                if (lane == 0) {
+                    pv[k] = p;
+                    rk[p] = k;
+                    if (!(fabs(pvv) > 0.0) && s_info == 0) s_info = k + 1;
+                }
+#pragma unroll
+                for (int a = 0; a < TA; ++a)
+                    if (a == a0) {
+#pragma unroll
+                        for (int b = 0; b < TB; ++b) {
+                            const double v = (b == kb && kcol) ? inv : S[a][b] * inv;
+                            S[a][b] = v;
+                            rowbuf[cur][lane + 32 * b] = v;
+                        }
+                    }
+            }
+            __syncthreads();
+            // (3) eliminate column k from every other row
+            double u[TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) u[b] = rowbuf[cur][lane + 32 * b];
+#pragma unroll
+            for (int a = 0; a < TA; ++a) {
+                const int i = wid + 16 * a;
+                const double f = (i == p) ? 0.0 : colbuf[cur][i];
+#pragma unroll
+                for (int b = 0; b < TB; ++b) S[a][b] = fma(-f, u[b], S[a][b]);
+            }
+            // the buffers of parity cur are rewritten two barriers from here: safe
+        }
+    }
+    }   // pivoted
+    __syncthreads();
+    if (tid == 0) d.info[sys] = s_info;
+
+    // ---- right-hand sides, DD_RB at a time
+    const int64_t q0 = d.sys_rhs_off[sys];
+    const int nq = d.sys_rhs_cnt[sys];
+    const int nk = n + d.n_border;
+    for (int base = 0; base < nq; base += DD_RB) {
+        const int nb = min(DD_RB, nq - base);
+        for (int idx = tid; idx < nb * RP; idx += 512) {
+            const int w = idx / RP, j = idx - w * RP;
+            bp[w][j] = (j < r) ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + mi[pv[j]]] : 0.0;
+        }
+        __syncthreads();
+        for (int w = 0; w < nb; ++w) {
+            double bw[TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) bw[b] = bp[w][lane + 32 * b];
+#pragma unroll
+            for (int a = 0; a < TA; ++a) {
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < TB; ++b) acc = fma(S[a][b], bw[b], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                const int i = wid + 16 * a;
+                if (lane == 0 && i < r) ys[w][rk[i]] = acc;
+            }
+        }
+        __syncthreads();
+        // c_K = u_K - G[K, Mi] y  for the nb right-hand sides at once
+        for (int i = tid; i < nk; i += 512) {
+            const int ki = (i < n) ? stn[i] : (d.n_stn + (i - n));
+            double acc[DD_RB];
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w)
+                acc[w] = (w < nb) ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + ki] : 0.0;
+#pragma unroll 4
+            for (int j = 0; j < r; ++j) {
+                const double gv = G[(int64_t)mi[j] * M + ki];
+#pragma unroll
+                for (int w = 0; w < DD_RB; ++w) acc[w] = fma(-gv, ys[w][j], acc[w]);
             }
 #pragma unroll
             for (int w = 0; w < DD_RB; ++w) {
@@ -686,6 +961,28 @@ static size_t dd_smem_bytes(int max_r) {
     return (ld * max_r + (size_t)DD_RB * ld) * sizeof(double) + 2 * (size_t)max_r * sizeof(int);
 }
 
+// r <= DD_REG_MAX: register-resident Gauss-Jordan (k_downdate_reg); larger r (up to what
+// shared memory holds): LU in shared memory (k_downdate).  SPX_DD_SMEM=1 forces the latter.
+constexpr int DD_REG_MAX = 160;
+
+static bool dd_force_smem() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPX_DD_SMEM");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+static int dd_force_pivot() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPX_DD_PIVOT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 int spx_krige_downdate_max_r(void) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -709,7 +1006,28 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
         set_error("krige_downdate: bad kpad / max_r");
         return SPX_EINVAL;
     }
-    const size_t smem = dd_smem_bytes(d->max_r > 0 ? d->max_r : 1);
+    spx_downdate dd = *d;
+    if (dd.max_r < 1) dd.max_r = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int smem_lo = 0;   // systems with r > smem_lo go to the shared-memory kernel
+    if (!dd_force_smem()) {
+        const int fp = dd_force_pivot();
+        // one launch per tile shape that has work; a CTA whose system belongs to
+        // another shape returns at once
+        k_downdate_reg<7, 4><<<d->n_sys, 512, 0, st>>>(dd, -1, 112, fp);
+        SPX_CHECK_LAUNCH("k_downdate_reg<7,4>");
+        if (dd.max_r > 112) {
+            k_downdate_reg<8, 4><<<d->n_sys, 512, 0, st>>>(dd, 112, 128, fp);
+            SPX_CHECK_LAUNCH("k_downdate_reg<8,4>");
+        }
+        if (dd.max_r > 128) {
+            k_downdate_reg<10, 5><<<d->n_sys, 512, 0, st>>>(dd, 128, DD_REG_MAX, fp);
+            SPX_CHECK_LAUNCH("k_downdate_reg<10,5>");
+        }
+        if (dd.max_r <= DD_REG_MAX) return SPX_OK;
+        smem_lo = DD_REG_MAX;
+    }
+    const size_t smem = dd_smem_bytes(dd.max_r);
     int dev = 0, max_smem = 0;
     SPX_CUDA(cudaGetDevice(&dev));
     SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -718,12 +1036,10 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
                   d->max_r, smem, max_smem);
         return SPX_ENOMEM;
     }
-    spx_downdate dd = *d;
-    if (dd.max_r < 1) dd.max_r = 1;
     if (smem > 48 * 1024)
         SPX_CUDA(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    k_downdate<<<d->n_sys, 256, smem, (cudaStream_t)stream>>>(dd);
+    k_downdate<<<d->n_sys, 256, smem, st>>>(dd, smem_lo);
     SPX_CHECK_LAUNCH("k_downdate");
     return SPX_OK;
 }

@@ -90,6 +90,35 @@ class PendingChunk:
                     self.problem_steps)
 
 
+class _TracedLib:
+    """Wraps the ctypes library so that every ``spx_*_dev`` entry point is bracketed by
+    CUDA events on the compute stream (ChunkEngine.trace_launches).  A measuring aid:
+    bench.py uses it for the per-kernel breakdown of a step."""
+
+    def __init__(self, eng, lib):
+        self._eng = eng
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.endswith('_dev'):
+            return fn
+        eng = self._eng
+
+        def traced(*a):
+            if not eng.trace_launches:
+                return fn(*a)
+            st = torch.cuda.current_stream(eng.device)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = fn(*a)
+            e1.record(st)
+            eng.trace.append((name, e0, e1))
+            return rc
+        return traced
+
+
 class ChunkEngine:
     """Holds the device and tunables; ``interp_chunk`` is re-entrant."""
 
@@ -100,7 +129,9 @@ class ChunkEngine:
             raise _lib.SpxError('torch sees no CUDA device (no CPU fallback)')
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None
                                    else int(device))
-        self.lib = _lib.load()
+        self.lib = _TracedLib(self, _lib.load())
+        self.trace_launches = False
+        self.trace = []           # (entry point, start event, end event)
         self.work_limit = int(work_limit_bytes)
         self.aux_limit = int(aux_limit_bytes)
         self.lambda_tol = float(lambda_tol)
@@ -225,6 +256,16 @@ class ChunkEngine:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream(self.device))
         self.kernel_events.append((name, bound, float(work), e0, e1))
+
+    def trace_summary(self):
+        """ms per entry point over self.trace (synchronises the device)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, e0, e1 in self.trace:
+            d = out.setdefault(name, {'ms': 0.0, 'n': 0})
+            d['ms'] += e0.elapsed_time(e1)
+            d['n'] += 1
+        return out
 
     def _count(self, key, n=1):
         self.stats[key] = self.stats.get(key, 0) + n

@@ -98,6 +98,8 @@ def test_float32_store(eng):
     (120, 40, 64, 64, 0.2),      # many availability groups
     (100, 37, 50, 41, 0.0),      # one group, ragged tile sizes
     (259, 300, 30, 33, 0.05),    # more than one M-tile of rows, K not a multiple of 8
+    (600, 30, 20, 20, 0.21),     # ~126 +- 10 missing stations per step: every tile shape
+                                 # of the register-resident downdate kernel
 ])
 def test_seeded_vs_oracle(eng, n_stn, n_steps, ny, nx, miss):
     p = make_problem(11, n_stn, n_steps, ny, nx, cell=1000.0 * 200 / max(ny, nx), miss=miss)
@@ -107,6 +109,24 @@ def test_seeded_vs_oracle(eng, n_stn, n_steps, ny, nx, miss):
     exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
     _check(got, exp, 'seeded')
+
+
+@pytest.mark.parametrize('knob', ['SPX_DD_PIVOT', 'SPX_DD_SMEM'])
+def test_downdate_kernel_variants(knob):
+    """The downdated solves have a fast path (Gauss-Jordan without pivoting, definite
+    S) with two fall-backs: pivoted elimination in registers and LU in shared memory.
+    The environment knobs force each of them; same parity bar."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env[knob] = '1'
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_engine.py', '-q', '-x',
+                        '-m', 'gpu', '-k', 'test_seeded_vs_oracle and auto'],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '4 passed' in r.stdout, r.stdout[-500:]
 
 
 def test_linearity_and_constant_field(eng):
