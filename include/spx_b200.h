@@ -467,8 +467,8 @@ typedef struct spx_local {
     int64_t n_cells;
     int32_t cap;
     int32_t* cnt;              /* [n_cells] */
-    int32_t* idx;              /* [n_cells, cap] */
-    double* val;               /* [n_cells, cap] */
+    int32_t* idx;              /* [cap, n_cells] station of the j-th near station of a cell */
+    double* val;               /* [cap, n_cells] its vg(dist) - F */
     spx_vg vg;
     int32_t covar_flag;
     double min_vg_val;
@@ -486,6 +486,10 @@ typedef struct spx_local {
     int32_t has_lo, has_hi;
     double lo, hi;
     int32_t rows_all_valid;    /* every row_dst[r] >= 0 (enables the streamlined kernel) */
+    const double* coef_t;      /* optional transposed copy [kpad, coef_t_ld] of coef (rows
+                                  beyond n_rows zero); with f32 output, no drift, no cell_pos
+                                  and rows_all_valid it selects the streamlined kernel */
+    int64_t coef_t_ld;         /* multiple of 4, >= n_rows */
 } spx_local;
 int spx_local_build_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);

@@ -65,5 +65,5 @@ for i in range(4):
     eng.submit_chunk(**kw, **chunks[i % 3]).result(to_host=False)
 pr.disable()
 s_ = io.StringIO()
-pstats.Stats(pr, stream=s_).sort_stats('tottime').print_stats(28)
-print(s_.getvalue()[:6000])
+pstats.Stats(pr, stream=s_).sort_stats('cumulative').print_stats(70)
+print(s_.getvalue()[:14000])

@@ -100,7 +100,8 @@ class spx_local(C.Structure):
                 ('cell_drift', C.c_void_p), ('row_dst', C.c_void_p), ('out', C.c_void_p),
                 ('out_ld', C.c_int64), ('out_f64', C.c_int32), ('cell_pos', C.c_void_p),
                 ('has_lo', C.c_int32), ('has_hi', C.c_int32),
-                ('lo', C.c_double), ('hi', C.c_double), ('rows_all_valid', C.c_int32)]
+                ('lo', C.c_double), ('hi', C.c_double), ('rows_all_valid', C.c_int32),
+                ('coef_t', C.c_void_p), ('coef_t_ld', C.c_int64)]
 
 
 class spx_nrst(C.Structure):

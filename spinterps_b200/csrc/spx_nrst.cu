@@ -796,8 +796,8 @@ __global__ void __launch_bounds__(256) k_local_build(LocalBuildArgs a) {
                 const double d = dist_rn(x, y, a.stn_x[s], a.stn_y[s]);
                 if (d < a.R) {
                     if (n < a.cap) {
-                        a.idx[c * a.cap + n] = s;
-                        a.val[c * a.cap + n] = vg_eval(a.vg, d, a.covar_flag, a.min_vg_val) - a.F;
+                        a.idx[(int64_t)n * a.n_cells + c] = s;
+                        a.val[(int64_t)n * a.n_cells + c] = vg_eval(a.vg, d, a.covar_flag, a.min_vg_val) - a.F;
                     }
                     ++n;
                 }
@@ -812,6 +812,8 @@ constexpr int LOC_ROWS = 64;    // rows per block
 
 struct LocalEstArgs {
     const double* coef;         // [n_rows, kpad] row-major
+    const double* coef_t;       // [kpad, coef_t_ld] transposed copy (fast kernel) or NULL
+    int64_t coef_t_ld;
     const double* base;         // [n_rows] F * sum_k coef + constant border term
     int64_t n_rows;
     int kpad, n_stn, n_drifts;
@@ -853,8 +855,8 @@ __global__ void __launch_bounds__(256) k_estimate_local(LocalEstArgs a) {
     double rv[LOC_REG];
 #pragma unroll
     for (int j = 0; j < LOC_REG; ++j) {
-        ri[j] = (j < n) ? a.idx[c * a.cap + j] : 0;
-        rv[j] = (j < n) ? a.val[c * a.cap + j] : 0.0;
+        ri[j] = (j < n) ? a.idx[(int64_t)j * a.n_cells + c] : 0;
+        rv[j] = (j < n) ? a.val[(int64_t)j * a.n_cells + c] : 0.0;
     }
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     double dr[4] = {0.0, 0.0, 0.0, 0.0};
@@ -893,7 +895,7 @@ __global__ void __launch_bounds__(256) k_estimate_local(LocalEstArgs a) {
                 if (2 < n) z = fma(cr[ri[2]], rv[2], z);
                 if (3 < n) z = fma(cr[ri[3]], rv[3], z);
                 for (int j = LOC_REG; j < n; ++j)
-                    z = fma(cr[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
+                    z = fma(cr[a.idx[(int64_t)j * a.n_cells + c]], a.val[(int64_t)j * a.n_cells + c], z);
             }
             if (a.has_lo && z < a.lo) z = a.lo;
             if (a.has_hi && z > a.hi) z = a.hi;
@@ -902,99 +904,147 @@ __global__ void __launch_bounds__(256) k_estimate_local(LocalEstArgs a) {
     }
 }
 
-// Fast variant: float output, identity cell order, no drift.  Written for a low
-// instruction count per (cell, row) -- the kernel is issue bound, not bandwidth
-// bound, if every row pays for flag tests, 64-bit index arithmetic and clamps on
-// doubles: per-row destination offsets are precomputed in shared memory, the number
-// of gathers is a warp-uniform compile-time case (NG = 0, 1, 2 or "many"), the
-// clamp is a compile-time option applied after the conversion (rounding is
-// monotone, so float(clamp(z)) == clamp(float(z)) with float(lo), float(hi)) and
-// rows are processed four at a time without per-row bounds checks.
-template <int NG, bool CLAMP>
-__device__ __forceinline__ void local_rows(const LocalEstArgs& a, const double* sbase,
-                                           const int64_t* soff, int nr, int64_t c, int n,
-                                           const int* ri, const double* rv, float* outp,
-                                           const double* crow, float flo, float fhi) {
-    const int64_t kp = a.kpad;
+// Fast variant: float output, identity cell order, no drift.  The kernel only writes
+// (4 B per cell-step) and is bound by instruction issue unless every row is cheap, so:
+//  * the coefficients are read from a TRANSPOSED copy  coef_t[k, row]: the four rows of
+//    one unrolled step are two 16-byte loads at an immediate offset from a per-thread
+//    pointer (row-major: one load + 64-bit address arithmetic per row and station);
+//  * per-row base values / destination offsets come from shared memory, four rows per
+//    pair of 16-byte loads;
+//  * the number of gathers is a warp-uniform compile-time case (NG = 0, 1, 2, "many");
+//  * the clamp is a compile-time option applied after the conversion (rounding is
+//    monotone: float(clamp(z)) == clamp(float(z)) with float(lo), float(hi)).
+template <int NG, bool CLAMP, int CPT>
+__device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double* sbase,
+                                             const int64_t* soff, int nr, int64_t c0,
+                                             const int* n, const double* const* p0,
+                                             const double* const* p1, const double* v0,
+                                             const double* v1, float* outp, const double* ct,
+                                             float flo, float fhi, bool pair) {
     int r = 0;
-    for (; r + 4 <= nr; r += 4, crow += 4 * kp) {
-        double g0[4], g1[4];
+    for (; r + 4 <= nr; r += 4) {
+        const double2 b01 = *reinterpret_cast<const double2*>(sbase + r);
+        const double2 b23 = *reinterpret_cast<const double2*>(sbase + r + 2);
+        float f[CPT][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            g0[u] = (NG >= 1 && 0 < n) ? crow[u * kp + ri[0]] : 0.0;
-            g1[u] = (NG >= 2 && 1 < n) ? crow[u * kp + ri[1]] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double z = sbase[r + u];
-            if (NG >= 1) z = fma(g0[u], rv[0], z);
-            if (NG >= 2) z = fma(g1[u], rv[1], z);
+        for (int q = 0; q < CPT; ++q) {
+            double z0 = b01.x, z1 = b01.y, z2 = b23.x, z3 = b23.y;
+            if (NG >= 1 && 0 < n[q]) {
+                const double2 g01 = __ldg(reinterpret_cast<const double2*>(p0[q] + r));
+                const double2 g23 = __ldg(reinterpret_cast<const double2*>(p0[q] + r + 2));
+                z0 = fma(g01.x, v0[q], z0); z1 = fma(g01.y, v0[q], z1);
+                z2 = fma(g23.x, v0[q], z2); z3 = fma(g23.y, v0[q], z3);
+            }
+            if (NG >= 2 && 1 < n[q]) {
+                const double2 g01 = __ldg(reinterpret_cast<const double2*>(p1[q] + r));
+                const double2 g23 = __ldg(reinterpret_cast<const double2*>(p1[q] + r + 2));
+                z0 = fma(g01.x, v1[q], z0); z1 = fma(g01.y, v1[q], z1);
+                z2 = fma(g23.x, v1[q], z2); z3 = fma(g23.y, v1[q], z3);
+            }
             if (NG >= 3) {
-                const double* cr = crow + u * kp;
-                for (int j = 2; j < n; ++j)
-                    z = fma(cr[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
+                const int64_t c = c0 + q;
+                for (int j = 2; j < n[q]; ++j) {
+                    const double* pj =
+                        ct + (int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r;
+                    const double vj = a.val[(int64_t)j * a.n_cells + c];
+                    const double2 g01 = __ldg(reinterpret_cast<const double2*>(pj));
+                    const double2 g23 = __ldg(reinterpret_cast<const double2*>(pj + 2));
+                    z0 = fma(g01.x, vj, z0); z1 = fma(g01.y, vj, z1);
+                    z2 = fma(g23.x, vj, z2); z3 = fma(g23.y, vj, z3);
+                }
             }
-            float f = (float)z;
+            f[q][0] = (float)z0; f[q][1] = (float)z1; f[q][2] = (float)z2; f[q][3] = (float)z3;
             if (CLAMP) {
-                f = (f < flo) ? flo : f;
-                f = (f > fhi) ? fhi : f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // comparisons with NaN are false: a NaN estimate stays NaN
+                    f[q][u] = (f[q][u] < flo) ? flo : f[q][u];
+                    f[q][u] = (f[q][u] > fhi) ? fhi : f[q][u];
+                }
             }
-            outp[soff[r + u]] = f;
+        }
+        const longlong2 o01 = *reinterpret_cast<const longlong2*>(soff + r);
+        const longlong2 o23 = *reinterpret_cast<const longlong2*>(soff + r + 2);
+        const int64_t o[4] = {o01.x, o01.y, o23.x, o23.y};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (CPT == 2) {
+                if (pair)
+                    *reinterpret_cast<float2*>(outp + o[u]) = make_float2(f[0][u], f[CPT - 1][u]);
+                else
+                    outp[o[u]] = f[0][u];
+            } else {
+                outp[o[u]] = f[0][u];
+            }
         }
     }
-    for (; r < nr; ++r, crow += kp) {
-        double z = sbase[r];
-        if (NG >= 1 && 0 < n) z = fma(crow[ri[0]], rv[0], z);
-        if (NG >= 2 && 1 < n) z = fma(crow[ri[1]], rv[1], z);
-        if (NG >= 3)
-            for (int j = 2; j < n; ++j)
-                z = fma(crow[a.idx[c * a.cap + j]], a.val[c * a.cap + j], z);
-        float f = (float)z;
-        if (CLAMP) {
-            f = (f < flo) ? flo : f;
-            f = (f > fhi) ? fhi : f;
+    for (; r < nr; ++r) {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+            if (q == 1 && !pair) break;
+            const int64_t c = c0 + q;
+            double z = sbase[r];
+            if (NG >= 1 && 0 < n[q]) z = fma(p0[q][r], v0[q], z);
+            if (NG >= 2 && 1 < n[q]) z = fma(p1[q][r], v1[q], z);
+            if (NG >= 3)
+                for (int j = 2; j < n[q]; ++j)
+                    z = fma(ct[(int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r],
+                            a.val[(int64_t)j * a.n_cells + c], z);
+            float fv = (float)z;
+            if (CLAMP) {
+                fv = (fv < flo) ? flo : fv;
+                fv = (fv > fhi) ? fhi : fv;
+            }
+            outp[soff[r] + q] = fv;
         }
-        outp[soff[r]] = f;
     }
 }
 
-template <bool CLAMP, int ROWS>
+// CPT cells per thread (2: one 8-byte store per row and thread; needs an even out_ld).
+template <bool CLAMP, int ROWS, int CPT>
 __global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
-    __shared__ double sbase[ROWS];
-    __shared__ int64_t soff[ROWS];
+    __shared__ __align__(16) double sbase[ROWS];
+    __shared__ __align__(16) int64_t soff[ROWS];
     const int64_t r_beg = (int64_t)blockIdx.y * ROWS;
     const int nr = (int)min((int64_t)ROWS, a.n_rows - r_beg);
-    for (int i = threadIdx.x + 256; i < nr; i += 256) {   // ROWS > 256 not used, kept general
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
         sbase[i] = a.base[r_beg + i];
         soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
     }
-    if (threadIdx.x < nr) {
-        sbase[threadIdx.x] = a.base[r_beg + threadIdx.x];
-        soff[threadIdx.x] = (int64_t)a.row_dst[r_beg + threadIdx.x] * a.out_ld;
-    }
     __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cells) return;                  // no further block-wide barrier below
-    const int n = min(a.cnt[c], a.cap);
-    int ri[2];
-    double rv[2];
-    ri[0] = (0 < n) ? a.idx[c * a.cap] : 0;
-    ri[1] = (1 < n) ? a.idx[c * a.cap + 1] : 0;
-    rv[0] = (0 < n) ? a.val[c * a.cap] : 0.0;
-    rv[1] = (1 < n) ? a.val[c * a.cap + 1] : 0.0;
-    const int nmax = __reduce_max_sync(__activemask(), n);
+    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
+    if (c0 >= a.n_cells) return;                 // no further block-wide barrier below
+    const bool pair = (CPT == 2) && (c0 + 1 < a.n_cells);
+    const double* ct = a.coef_t + r_beg;
+    int n[CPT];
+    const double* p0[CPT];
+    const double* p1[CPT];
+    double v0[CPT], v1[CPT];
+    int nloc = 0;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int64_t c = min(c0 + q, a.n_cells - 1);
+        n[q] = (q == 0 || pair) ? min(a.cnt[c], a.cap) : 0;
+        const int i0 = (0 < n[q]) ? a.idx[c] : 0;
+        const int i1 = (1 < n[q]) ? a.idx[a.n_cells + c] : 0;
+        v0[q] = (0 < n[q]) ? a.val[c] : 0.0;
+        v1[q] = (1 < n[q]) ? a.val[a.n_cells + c] : 0.0;
+        p0[q] = ct + (int64_t)i0 * a.coef_t_ld;
+        p1[q] = ct + (int64_t)i1 * a.coef_t_ld;
+        nloc = max(nloc, n[q]);
+    }
+    const int nmax = __reduce_max_sync(__activemask(), nloc);
     const float flo = a.has_lo ? (float)a.lo : -CUDART_INF_F;
     const float fhi = a.has_hi ? (float)a.hi : CUDART_INF_F;
-    float* outp = reinterpret_cast<float*>(a.out) + c;
-    const double* crow = a.coef + r_beg * a.kpad;
+    float* outp = reinterpret_cast<float*>(a.out) + c0;
     if (nmax == 0)
-        local_rows<0, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+        local_rows_t<0, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
     else if (nmax == 1)
-        local_rows<1, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+        local_rows_t<1, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
     else if (nmax == 2)
-        local_rows<2, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+        local_rows_t<2, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
     else
-        local_rows<3, CLAMP>(a, sbase, soff, nr, c, n, ri, rv, outp, crow, flo, fhi);
+        local_rows_t<3, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
 }
 
 }  // namespace spx
@@ -1046,6 +1096,8 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     }
     LocalEstArgs a;
     a.coef = l->coef;
+    a.coef_t = l->coef_t;
+    a.coef_t_ld = l->coef_t_ld;
     a.base = l->base;
     a.n_rows = l->n_rows;
     a.kpad = l->kpad;
@@ -1073,21 +1125,31 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     }
     cudaStream_t st = (cudaStream_t)stream;
     const bool drift = l->n_drifts > 0;
-    if (!l->out_f64 && !drift && l->cell_pos == nullptr && l->rows_all_valid) {
-        static const int rows_knob = getenv("SPX_LOCAL_ROWS") ? atoi(getenv("SPX_LOCAL_ROWS")) : 64;
-        const bool clamp = l->has_lo || l->has_hi;
-        const int rows = (rows_knob == 16 || rows_knob == 256) ? rows_knob : 64;
-        dim3 g1((unsigned)((l->n_cells + 255) / 256), (unsigned)((l->n_rows + rows - 1) / rows));
-        if (rows == 16) {
-            if (clamp) k_estimate_local_fast<true, 16><<<g1, 256, 0, st>>>(a);
-            else k_estimate_local_fast<false, 16><<<g1, 256, 0, st>>>(a);
-        } else if (rows == 256) {
-            if (clamp) k_estimate_local_fast<true, 256><<<g1, 256, 0, st>>>(a);
-            else k_estimate_local_fast<false, 256><<<g1, 256, 0, st>>>(a);
-        } else {
-            if (clamp) k_estimate_local_fast<true, 64><<<g1, 256, 0, st>>>(a);
-            else k_estimate_local_fast<false, 64><<<g1, 256, 0, st>>>(a);
+    if (!l->out_f64 && !drift && l->cell_pos == nullptr && l->rows_all_valid &&
+        l->coef_t != nullptr) {
+        if (l->coef_t_ld % 4 != 0 || l->coef_t_ld < l->n_rows) {
+            set_error("estimate_local: coef_t_ld must be a multiple of 4 and >= n_rows");
+            return SPX_EINVAL;
         }
+        static const int rows_knob = getenv("SPX_LOCAL_ROWS") ? atoi(getenv("SPX_LOCAL_ROWS")) : 128;
+        static const int cpt_knob = getenv("SPX_LOCAL_CPT") ? atoi(getenv("SPX_LOCAL_CPT")) : 1;
+        const bool clamp = l->has_lo || l->has_hi;
+        const int rows = (rows_knob == 64) ? 64 : 128;
+        // two cells per thread need 8-byte aligned row starts
+        const int cpt = (cpt_knob == 2 && l->out_ld % 2 == 0 &&
+                         (reinterpret_cast<uintptr_t>(l->out) & 7) == 0) ? 2 : 1;
+        const int64_t per_blk = 256 * (int64_t)cpt;
+        dim3 g1((unsigned)((l->n_cells + per_blk - 1) / per_blk),
+                (unsigned)((l->n_rows + rows - 1) / rows));
+#define SPX_LOCAL_LAUNCH(CL, RW, CP) k_estimate_local_fast<CL, RW, CP><<<g1, 256, 0, st>>>(a)
+        if (rows == 64) {
+            if (cpt == 2) { if (clamp) SPX_LOCAL_LAUNCH(true, 64, 2); else SPX_LOCAL_LAUNCH(false, 64, 2); }
+            else { if (clamp) SPX_LOCAL_LAUNCH(true, 64, 1); else SPX_LOCAL_LAUNCH(false, 64, 1); }
+        } else {
+            if (cpt == 2) { if (clamp) SPX_LOCAL_LAUNCH(true, 128, 2); else SPX_LOCAL_LAUNCH(false, 128, 2); }
+            else { if (clamp) SPX_LOCAL_LAUNCH(true, 128, 1); else SPX_LOCAL_LAUNCH(false, 128, 1); }
+        }
+#undef SPX_LOCAL_LAUNCH
         SPX_CHECK_LAUNCH("k_estimate_local_fast");
         return SPX_OK;
     }

@@ -719,8 +719,8 @@ class ChunkEngine:
         cap = 8
         while True:
             cnt = torch.empty(n_cells, dtype=_I32, device=self.device)
-            idx = torch.empty((n_cells, cap), dtype=_I32, device=self.device)
-            val = torch.empty((n_cells, cap), dtype=_F64, device=self.device)
+            idx = torch.empty((cap, n_cells), dtype=_I32, device=self.device)
+            val = torch.empty((cap, n_cells), dtype=_F64, device=self.device)
             L = _lib.spx_local()
             L.stn_x, L.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
             L.bin_start, L.bin_stn = d_bs.data_ptr(), d_bo.data_ptr()
@@ -1042,6 +1042,13 @@ class ChunkEngine:
                 L.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
                 L.has_lo, L.has_hi, L.lo, L.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
                 L.rows_all_valid = 1          # row-major rows are exactly the kriged steps
+                L.coef_t, L.coef_t_ld = None, 0
+                if (not ctx['out_f64'] and n_drifts == 0 and ctx['d_pos'] is None):
+                    # transposed copy for the streamlined kernel (5 MB at 1250 x 504)
+                    ld_t = _pad_up(r1 - r0, 4)
+                    coef_t = torch.zeros((kpad, ld_t), dtype=_F64, device=self.device)
+                    coef_t[:, :r1 - r0] = coef2d[r0:r1].t()
+                    L.coef_t, L.coef_t_ld = coef_t.data_ptr(), ld_t
                 stream = self._stream()
                 ev = self._prof_begin()
                 _lib.check(self.lib.spx_estimate_local_dev(C.byref(L), stream), 'estimate_local')
