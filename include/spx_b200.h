@@ -238,6 +238,8 @@ typedef struct spx_downdate {
     double* resid;               /* [n_rhs] */
     int32_t* info;               /* [n_sys] */
     int32_t coef_row_major;      /* 0: packed fragment layout; 1: coef[row * kpad + col] */
+    const int32_t* sys_order;    /* optional [n_sys]: block b works on system sys_order[b]
+                                    (largest r first shortens the tail); NULL = identity */
 } spx_downdate;
 
 int spx_krige_downdate_dev(const spx_downdate* d, void* stream);

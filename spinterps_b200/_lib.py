@@ -71,7 +71,8 @@ class spx_downdate(C.Structure):
                 ('sys_rhs_off', C.c_void_p), ('sys_rhs_cnt', C.c_void_p),
                 ('rhs_urow', C.c_void_p), ('rhs_row', C.c_void_p), ('rhs_kind', C.c_void_p),
                 ('ut', C.c_void_p), ('kpad', C.c_int32), ('coef', C.c_void_p),
-                ('resid', C.c_void_p), ('info', C.c_void_p), ('coef_row_major', C.c_int32)]
+                ('resid', C.c_void_p), ('info', C.c_void_p), ('coef_row_major', C.c_int32),
+                ('sys_order', C.c_void_p)]
 
 
 class spx_multivg(C.Structure):

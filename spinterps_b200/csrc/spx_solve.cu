@@ -440,7 +440,7 @@ constexpr int DD_RB = 8;  // right-hand sides per batch (one per warp)
 
 __global__ void __launch_bounds__(256) k_downdate(spx_downdate d, int r_lo) {
     extern __shared__ double dsm[];
-    const int sys = blockIdx.x;
+    const int sys = d.sys_order ? d.sys_order[blockIdx.x] : blockIdx.x;
     const int r = d.sys_r[sys];
     if (r <= r_lo) return;   // handled by k_downdate_reg
     const int n = d.sys_n[sys];
@@ -624,25 +624,38 @@ __global__ void __launch_bounds__(256) k_downdate(spx_downdate d, int r_lo) {
 // Two block barriers per column, ~TA + TB shared loads and TA * TB DFMA per thread;
 // the LU-in-shared-memory kernel above spends its time on shared-memory wavefronts
 // (r^3 / 3 elements read + written) and on barriers instead.
+constexpr int DD_RPMAX = 160;   // largest padded order of the register kernel
+
+struct DdShared {
+    double colbuf[2][DD_RPMAX];
+    double rowbuf[2][DD_RPMAX];
+    double ys[DD_RB][DD_RPMAX];
+    double bp[DD_RB][DD_RPMAX];
+    int mi[DD_RPMAX];
+    int pv[DD_RPMAX];               // pivot row of column k
+    int rk[DD_RPMAX];               // column whose pivot row is i
+    int s_info;
+    int s_fail;
+    double s_sgn;
+};
+
 template <int TA, int TB>
-__global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_lo, int r_hi, int force_pivot) {
+__device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShared& sm, int sys,
+                                                  int r, int force_pivot) {
     constexpr int RP = 32 * TB;          // padded order (columns); rows: 16 * TA <= RP
-    static_assert(16 * TA <= RP, "tile shape");
-    const int sys = blockIdx.x;
-    const int r = d.sys_r[sys];
-    if (r <= r_lo || r > r_hi) return;   // another instantiation's system
+    static_assert(16 * TA <= RP && RP <= DD_RPMAX, "tile shape");
     const int n = d.sys_n[sys];
     const int M = d.n_stn + d.n_border;
-    __shared__ double colbuf[2][RP];
-    __shared__ double rowbuf[2][RP];
-    __shared__ double ys[DD_RB][RP];
-    __shared__ double bp[DD_RB][RP];
-    __shared__ int mi[RP];
-    __shared__ int pv[RP];               // pivot row of column k
-    __shared__ int rk[RP];               // column whose pivot row is i
-    __shared__ int s_info;
-    __shared__ int s_fail;
-    __shared__ double s_sgn;
+    auto& colbuf = sm.colbuf;
+    auto& rowbuf = sm.rowbuf;
+    auto& ys = sm.ys;
+    auto& bp = sm.bp;
+    auto& mi = sm.mi;
+    auto& pv = sm.pv;
+    auto& rk = sm.rk;
+    int& s_info = sm.s_info;
+    int& s_fail = sm.s_fail;
+    double& s_sgn = sm.s_sgn;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int32_t* __restrict__ miss = d.miss_list + d.sys_miss_off[sys];
@@ -861,6 +874,18 @@ __global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_l
     }
 }
 
+// One launch for every tile shape: systems of different order run side by side (three
+// launches, one per shape, serialise behind each other's stragglers).
+__global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_max, int force_pivot) {
+    __shared__ DdShared sm;
+    const int sys = d.sys_order ? d.sys_order[blockIdx.x] : blockIdx.x;
+    const int r = d.sys_r[sys];
+    if (r > r_max) return;               // left to the shared-memory kernel
+    if (r <= 112) downdate_reg_body<7, 4>(d, sm, sys, r, force_pivot);
+    else if (r <= 128) downdate_reg_body<8, 4>(d, sm, sys, r, force_pivot);
+    else downdate_reg_body<10, 5>(d, sm, sys, r, force_pivot);
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -1012,18 +1037,8 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
     int smem_lo = 0;   // systems with r > smem_lo go to the shared-memory kernel
     if (!dd_force_smem()) {
         const int fp = dd_force_pivot();
-        // one launch per tile shape that has work; a CTA whose system belongs to
-        // another shape returns at once
-        k_downdate_reg<7, 4><<<d->n_sys, 512, 0, st>>>(dd, -1, 112, fp);
-        SPX_CHECK_LAUNCH("k_downdate_reg<7,4>");
-        if (dd.max_r > 112) {
-            k_downdate_reg<8, 4><<<d->n_sys, 512, 0, st>>>(dd, 112, 128, fp);
-            SPX_CHECK_LAUNCH("k_downdate_reg<8,4>");
-        }
-        if (dd.max_r > 128) {
-            k_downdate_reg<10, 5><<<d->n_sys, 512, 0, st>>>(dd, 128, DD_REG_MAX, fp);
-            SPX_CHECK_LAUNCH("k_downdate_reg<10,5>");
-        }
+        k_downdate_reg<<<d->n_sys, 512, 0, st>>>(dd, DD_REG_MAX, fp);
+        SPX_CHECK_LAUNCH("k_downdate_reg");
         if (dd.max_r <= DD_REG_MAX) return SPX_OK;
         smem_lo = DD_REG_MAX;
     }

@@ -1469,8 +1469,10 @@ class ChunkEngine:
             rkind[pos_ones] = 1
             d_resid = torch.zeros(n_rhs, dtype=_F64, device=self.device)
             d_info = torch.zeros(nsys, dtype=_I32, device=self.device)
+            order = np.argsort(-r, kind='stable').astype(np.int32)   # largest systems first
             ts = self._dev_pack([r, miss_off, np.zeros(1, dtype=np.int32), K.sys_n[ids],
-                                 K.stn_off[grp], rhs_off, rhs_cnt, urow, rrow, rkind])
+                                 K.stn_off[grp], rhs_off, rhs_cnt, urow, rrow, rkind, order])
+            d_order = ts.pop()
             ts[2] = d_miss_list
             D = _lib.spx_downdate()
             D.n_sys = nsys
@@ -1485,6 +1487,7 @@ class ChunkEngine:
             D.kpad = K.kpad
             D.coef = K.coef.data_ptr()
             D.coef_row_major = int(K.row_major)
+            D.sys_order = d_order.data_ptr()
             D.resid = d_resid.data_ptr()
             D.info = d_info.data_ptr()
             _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')
