@@ -496,6 +496,17 @@ typedef struct spx_local {
 int spx_local_build_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
 
+/* Round a field to `decimals` decimal places in its own dtype, in place, exactly like
+ * np.round (interp/steps.py:907-912: rint(x * 10^d) / 10^d; decimals < 0 = no rounding),
+ * and return per-row statistics of the (rounded) values, NaN ignored:
+ * stats[0..4][row] = min, mean, max, std (ddof 0), count of finite values -- what
+ * interp/main.py:474-525 obtains by re-reading the netCDF file (there in the field
+ * dtype; here accumulated in FP64).  Rows without any value give NaN, count 0.
+ * workspace: spx_round_stats_workspace(n_rows, row_len) bytes of device memory. */
+int64_t spx_round_stats_workspace(int64_t n_rows, int64_t row_len);
+int spx_round_stats_dev(void* fld, int32_t is_f64, int64_t n_rows, int64_t row_len, int64_t ld,
+                        int32_t decimals, double* stats, void* workspace, void* stream);
+
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field
  * download in flight; n_bytes and both pointers multiples of 4. */

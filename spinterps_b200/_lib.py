@@ -202,6 +202,9 @@ _SIGS = {
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int32, C.c_void_p]),
     'spx_copy_to_mapped_host_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'spx_round_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),
+    'spx_round_stats_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
 }

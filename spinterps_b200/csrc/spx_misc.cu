@@ -1,5 +1,7 @@
 // Supporting kernels of the engine: coefficient packing, nearest-neighbour
 // index / gather, constant-row fill and the sum(lambda) ~ 1 check.
+#include <type_traits>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -263,6 +265,150 @@ __global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restr
 
 static inline unsigned grid_y(int64_t n) { return (unsigned)(n < 1 ? 1 : (n > 65535 ? 65535 : n)); }
 
+
+// ------------------------------------------------------------- rounding + statistics
+// interp/steps.py:907-912 rounds every field to nmrl_prcn decimals in the field dtype
+// before it is written (np.round: rint(x * 10^d) / 10^d, both operations rounded in that
+// dtype) and interp/main.py:474-525 re-reads the file to get per-step min / mean / max /
+// std / count.  Both in one pass over the field while it is still in HBM.
+struct StatPart {
+    double n, mean, m2, mn, mx, nfin;
+};
+
+__device__ __forceinline__ void stat_merge(StatPart& a, const StatPart& b) {
+    // Chan et al. pairwise update of (n, mean, M2)
+    if (b.n > 0.0) {
+        if (a.n == 0.0) {
+            a.n = b.n; a.mean = b.mean; a.m2 = b.m2;
+        } else {
+            const double n = a.n + b.n;
+            const double dlt = b.mean - a.mean;
+            a.mean += dlt * (b.n / n);
+            a.m2 += b.m2 + dlt * dlt * (a.n * b.n / n);
+            a.n = n;
+        }
+    }
+    a.mn = fmin(a.mn, b.mn);     // fmin / fmax ignore NaN: nanmin / nanmax
+    a.mx = fmax(a.mx, b.mx);
+    a.nfin += b.nfin;
+}
+
+__device__ __forceinline__ StatPart stat_shfl(const StatPart& a, int o) {
+    StatPart b;
+    b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+    b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
+    b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
+    b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
+    b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+    b.nfin = __shfl_xor_sync(0xffffffffu, a.nfin, o);
+    return b;
+}
+
+template <typename T>
+__device__ __forceinline__ T round_dec(T x, T p);
+template <>
+__device__ __forceinline__ float round_dec<float>(float x, float p) {
+    return __fdiv_rn(rintf(__fmul_rn(x, p)), p);
+}
+template <>
+__device__ __forceinline__ double round_dec<double>(double x, double p) {
+    return __ddiv_rn(rint(__dmul_rn(x, p)), p);
+}
+
+constexpr int RS_THREADS = 256;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(RS_THREADS) k_round_stats(T* fld, int64_t row_len, int64_t ld,
+                                                           int64_t seg_len, int do_round, T pw,
+                                                           StatPart* parts) {
+    const int64_t row = blockIdx.y;
+    const int seg = blockIdx.x;
+    T* base = fld + row * ld;
+    const int64_t beg = (int64_t)seg * seg_len;
+    const int64_t end = min(row_len, beg + seg_len);
+    // shift by the first value of the segment (if usable) against cancellation
+    double K = (beg < end) ? (double)base[beg] : 0.0;
+    if (!(fabs(K) < 1.0e300)) K = 0.0;
+    if (do_round && beg < end) {
+        const double Kr = (double)round_dec<T>((T)K, pw);
+        if (fabs(Kr) < 1.0e300) K = Kr;
+    }
+    double n = 0.0, s = 0.0, q = 0.0, nfin = 0.0;
+    double mn = CUDART_INF, mx = -CUDART_INF;
+    auto take = [&](T v) {
+        if (v == v) {
+            const double d = (double)v - K;
+            n += 1.0;
+            s += d;
+            q = fma(d, d, q);
+            mn = fmin(mn, (double)v);
+            mx = fmax(mx, (double)v);
+            if (fabs((double)v) <= 1.7976931348623157e308) nfin += 1.0;
+        }
+    };
+    if (VEC) {
+        constexpr int W = 16 / sizeof(T);
+        typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
+        for (int64_t i = beg + (int64_t)threadIdx.x * W; i < end; i += (int64_t)RS_THREADS * W) {
+            if (i + W <= end) {
+                V v = *reinterpret_cast<V*>(base + i);
+                T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    if (do_round) e[u] = round_dec<T>(e[u], pw);
+                    take(e[u]);
+                }
+                if (do_round) *reinterpret_cast<V*>(base + i) = v;
+            } else {
+                for (int64_t j = i; j < end; ++j) {
+                    T v = base[j];
+                    if (do_round) { v = round_dec<T>(v, pw); base[j] = v; }
+                    take(v);
+                }
+            }
+        }
+    } else {
+        for (int64_t i = beg + threadIdx.x; i < end; i += RS_THREADS) {
+            T v = base[i];
+            if (do_round) { v = round_dec<T>(v, pw); base[i] = v; }
+            take(v);
+        }
+    }
+    StatPart a;
+    a.n = n;
+    a.mean = (n > 0.0) ? K + s / n : 0.0;
+    a.m2 = (n > 0.0) ? q - s * (s / n) : 0.0;
+    a.mn = mn;
+    a.mx = mx;
+    a.nfin = nfin;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const StatPart b = stat_shfl(a, o);
+        stat_merge(a, b);
+    }
+    __shared__ StatPart sp[RS_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatPart t = sp[0];
+        for (int w = 1; w < RS_THREADS / 32; ++w) stat_merge(t, sp[w]);
+        parts[row * gridDim.x + seg] = t;
+    }
+}
+
+__global__ void k_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, double* stats) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    StatPart t = parts[row * n_seg];
+    for (int sgi = 1; sgi < n_seg; ++sgi) stat_merge(t, parts[row * n_seg + sgi]);
+    const bool any = t.n > 0.0;
+    stats[0 * n_rows + row] = any ? t.mn : CUDART_NAN;
+    stats[1 * n_rows + row] = any ? t.mean : CUDART_NAN;
+    stats[2 * n_rows + row] = any ? t.mx : CUDART_NAN;
+    stats[3 * n_rows + row] = any ? sqrt(fmax(t.m2, 0.0) / t.n) : CUDART_NAN;
+    stats[4 * n_rows + row] = t.nfin;
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -413,6 +559,63 @@ int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
     k_lambda_check<<<blocks, 256, 0, (cudaStream_t)stream>>>(aux, n_slots, n_cells, cell_bad,
                                                              fail);
     SPX_CHECK_LAUNCH("k_lambda_check");
+    return SPX_OK;
+}
+
+static int rs_segments(int64_t n_rows, int64_t row_len) {
+    // enough blocks to fill the GPU a few times over, at least 4096 elements each
+    int64_t seg = (148 * 16 + n_rows - 1) / n_rows;
+    const int64_t max_seg = (row_len + 4095) / 4096;
+    if (seg > max_seg) seg = max_seg;
+    if (seg < 1) seg = 1;
+    if (seg > 1024) seg = 1024;
+    return (int)seg;
+}
+
+int64_t spx_round_stats_workspace(int64_t n_rows, int64_t row_len) {
+    return (int64_t)sizeof(StatPart) * n_rows * rs_segments(n_rows > 0 ? n_rows : 1, row_len);
+}
+
+int spx_round_stats_dev(void* fld, int32_t is_f64, int64_t n_rows, int64_t row_len, int64_t ld,
+                        int32_t decimals, double* stats, void* workspace, void* stream) {
+    if (n_rows == 0 || row_len == 0) return SPX_OK;
+    if (!fld || !stats || !workspace || ld < row_len) {
+        set_error("round_stats: null argument or ld < row_len");
+        return SPX_EINVAL;
+    }
+    if (decimals > 15) {
+        set_error("round_stats: decimals > 15");
+        return SPX_EINVAL;
+    }
+    if (n_rows > 65535) {
+        set_error("round_stats: more than 65535 rows in one call");
+        return SPX_EINVAL;
+    }
+    const int do_round = decimals >= 0;
+    double pw = 1.0;
+    for (int i = 0; i < decimals; ++i) pw *= 10.0;
+    const int n_seg = rs_segments(n_rows, row_len);
+    int64_t seg_len = (row_len + n_seg - 1) / n_seg;
+    seg_len = (seg_len + 3) / 4 * 4;                      // keeps 16-byte alignment per segment
+    const bool vec = (reinterpret_cast<uintptr_t>(fld) & 15) == 0 &&
+                     (ld % (is_f64 ? 2 : 4)) == 0;
+    dim3 grid((unsigned)n_seg, (unsigned)n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    StatPart* parts = reinterpret_cast<StatPart*>(workspace);
+    if (is_f64) {
+        if (vec) k_round_stats<double, true><<<grid, RS_THREADS, 0, st>>>(
+            (double*)fld, row_len, ld, seg_len, do_round, pw, parts);
+        else k_round_stats<double, false><<<grid, RS_THREADS, 0, st>>>(
+            (double*)fld, row_len, ld, seg_len, do_round, pw, parts);
+    } else {
+        if (vec) k_round_stats<float, true><<<grid, RS_THREADS, 0, st>>>(
+            (float*)fld, row_len, ld, seg_len, do_round, (float)pw, parts);
+        else k_round_stats<float, false><<<grid, RS_THREADS, 0, st>>>(
+            (float*)fld, row_len, ld, seg_len, do_round, (float)pw, parts);
+    }
+    SPX_CHECK_LAUNCH("k_round_stats");
+    k_stats_final<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(parts, n_seg, n_rows, stats);
+    SPX_CHECK_LAUNCH("k_stats_final");
     return SPX_OK;
 }
 

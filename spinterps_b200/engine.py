@@ -69,8 +69,37 @@ class PendingChunk:
         self.problem_steps = problem_steps
         self.deferred = deferred
         self.stats = stats
+        # optional output stage (interp/steps.py:907-912, interp/main.py:474-525):
+        # round to `round_decimals` places and / or reduce per-step field statistics
+        self.round_decimals = None
+        self.want_field_stats = False
+        self.field_stats = None        # {label: ndarray[5, T]} min, mean, max, std, count
+        self._d_field_stats = None
         self.done_event = torch.cuda.Event()
         self.done_event.record(torch.cuda.current_stream(engine.device))
+
+    def _output_stage(self):
+        eng = self.engine
+        if self._d_field_stats is not None or (
+                self.round_decimals is None and not self.want_field_stats):
+            return
+        dec = -1 if self.round_decimals is None else int(self.round_decimals)
+        self._d_field_stats = {}
+        for lab, t in self.flds.items():
+            n_rows, row_len = t.shape
+            st = torch.empty((5, n_rows), dtype=_F64, device=eng.device)
+            for r0 in range(0, n_rows, 65535):
+                r1 = min(n_rows, r0 + 65535)
+                ws = torch.empty(max(1, eng.lib.spx_round_stats_workspace(r1 - r0, row_len)),
+                                 dtype=torch.uint8, device=eng.device)
+                sub = torch.empty((5, r1 - r0), dtype=_F64, device=eng.device)
+                _lib.check(eng.lib.spx_round_stats_dev(
+                    C.c_void_p(t[r0:r1].data_ptr()), int(t.dtype == _F64), r1 - r0, row_len,
+                    t.stride(0), dec, C.c_void_p(sub.data_ptr()), C.c_void_p(ws.data_ptr()),
+                    eng._stream()), 'round_stats')
+                eng._count('launches', 2)
+                st[:, r0:r1] = sub
+            self._d_field_stats[lab] = st
 
     def result(self, to_host=True):
         eng = self.engine
@@ -79,6 +108,11 @@ class PendingChunk:
             for fn in self.deferred:
                 fn()
             self.deferred = []
+            self._output_stage()
+            if self._d_field_stats is not None and self.field_stats is None:
+                hs = {lab: eng._fetch_async(t) for lab, t in self._d_field_stats.items()}
+                torch.cuda.current_stream(eng.device).synchronize()
+                self.field_stats = {lab: h.numpy().copy() for lab, h in hs.items()}
             if eng.total_launches != n0:
                 # fix-up kernels were queued: the fields are final only after them
                 self.done_event = torch.cuda.Event()
@@ -257,6 +291,27 @@ class ChunkEngine:
         e1.record(torch.cuda.current_stream(self.device))
         self.kernel_events.append((name, bound, float(work), e0, e1))
 
+    def round_and_stats(self, fld, decimals=None):
+        """Round a device field [T, cells] in place (None: leave it) and return its
+        per-step statistics as ndarray[5, T] (min, mean, max, std, count);
+        spx_round_stats_dev."""
+        n_rows, row_len = fld.shape
+        out = np.empty((5, n_rows))
+        dec = -1 if decimals is None else int(decimals)
+        with torch.cuda.device(self.device):
+            for r0 in range(0, n_rows, 65535):
+                r1 = min(n_rows, r0 + 65535)
+                ws = torch.empty(max(1, self.lib.spx_round_stats_workspace(r1 - r0, row_len)),
+                                 dtype=torch.uint8, device=self.device)
+                sub = torch.empty((5, r1 - r0), dtype=_F64, device=self.device)
+                _lib.check(self.lib.spx_round_stats_dev(
+                    C.c_void_p(fld[r0:r1].data_ptr()), int(fld.dtype == _F64), r1 - r0, row_len,
+                    fld.stride(0), dec, C.c_void_p(sub.data_ptr()), C.c_void_p(ws.data_ptr()),
+                    self._stream()), 'round_stats')
+                self._count('launches', 2)
+                out[:, r0:r1] = sub.cpu().numpy()
+        return out
+
     def trace_summary(self):
         """ms per entry point over self.trace (synchronises the device)."""
         torch.cuda.synchronize(self.device)
@@ -310,14 +365,22 @@ class ChunkEngine:
             vgs=None, cntn_idxs=None, drft_arrs=None, stns_drft=None,
             fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
             min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
-            min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32):
-        """Queue every kernel of the chunk and return a PendingChunk."""
+            min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
+            round_decimals=None, field_stats=False):
+        """Queue every kernel of the chunk and return a PendingChunk.
+
+        round_decimals / field_stats: the output stage of the reference on the device --
+        fields rounded like ``np.round(flds, nmrl_prcn)`` before they leave the GPU and
+        per-step min / mean / max / std / count in ``PendingChunk.field_stats``."""
         with torch.cuda.device(self.device):
-            return self._interp_chunk(
+            pend = self._interp_chunk(
                 data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
                 cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
                 n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
                 intrp_dtype)
+            pend.round_decimals = round_decimals
+            pend.want_field_stats = bool(field_stats)
+            return pend
 
     # ------------------------------------------------------------ impl
     def _interp_chunk(

@@ -29,7 +29,7 @@ import numpy as np
 import pandas as pd
 
 from . import ncwriter
-from .steps import SpInterpSteps
+from .steps import InterpFields, SpInterpSteps
 
 
 def _print_sl():
@@ -622,11 +622,22 @@ class SpInterpMain:
             bounds = np.array([beg_all, end_all])
         stats_rows = {}
         if not multi:
+            # one chunk in flight: chunk i+1 is prepared and queued on the GPU while the
+            # fields of chunk i are downloaded, reduced to statistics and written
+            prev = None
             for i in range(bounds.size - 1):
                 if bounds[i + 1] == bounds[i]:
                     continue
                 args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
-                out = steps_cls._get_all_interp_outputs(args)
+                cur = (steps_cls._submit_interp(args, output_stage=True), args,
+                       timeit.default_timer())
+                if prev is not None:
+                    out = steps_cls._finish_interp(*prev)
+                    self._collect_stats(out, stats_rows)
+                    steps_cls._write_to_disk(out)
+                prev = cur
+            if prev is not None:
+                out = steps_cls._finish_interp(*prev)
                 self._collect_stats(out, stats_rows)
                 steps_cls._write_to_disk(out)
         else:
@@ -642,17 +653,25 @@ class SpInterpMain:
                 if bounds[i + 1] == bounds[i]:
                     continue
                 args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
-                parts.append(steps_cls._get_all_interp_outputs(args)[7])
+                pend = steps_cls._submit_interp(args, output_stage=True)
+                # rounded fields stay in HBM: they go to the writer over NVLink
+                parts.append(steps_cls._finish_interp(pend, args, to_host=False)[7])
+            eng = steps_cls._get_engine()
             for lab in labels:
                 if parts:
-                    slab = torch.from_numpy(np.concatenate([p_[lab] for p_ in parts])).to(dev)
+                    slab = torch.cat([p_[lab] for p_ in parts]) if len(parts) > 1 \
+                        else parts[0][lab]
                 else:
                     slab = torch.empty((0, fld), dtype=tdt, device=dev)
                 full = sdist.gather_slabs(slab, shard_b, dst=writer)
                 if rank == writer:
-                    arr = full.cpu().numpy()
+                    flds = InterpFields()
+                    flds.rounded = True
+                    flds.stats = {lab: eng.round_and_stats(full)}
+                    flds[lab] = full.cpu().numpy()
+                    del full
                     args = self._chunk_args(0, n_steps, 1, lock)
-                    out = (lock, 0, n_steps, args[0], args[8], 1, [lab], {lab: arr}, 0,
+                    out = (lock, 0, n_steps, args[0], args[8], 1, [lab], flds, 0,
                            int(self._interp_crds_orig_shape[0]), args[9], args[0].index,
                            timeit.default_timer())
                     self._collect_stats(out, stats_rows)
@@ -669,15 +688,20 @@ class SpInterpMain:
         (interp/main.py:474-525 computes them by re-reading the netCDF; here they
         are taken from the rounded field before it is written)."""
         labels, flds, time_steps = out[6], out[7], out[11]
+        dev_stats = getattr(flds, 'stats', None)
         for lab in labels:
             if lab == 'EST_VARS_OK':
                 continue
-            f = np.round(flds[lab], self._nc_nmrl_prcn)
-            with np.errstate(invalid='ignore'), np.testing.suppress_warnings() as sup:
-                sup.filter(RuntimeWarning)
-                stats = dict(min=np.nanmin(f, axis=1), mean=np.nanmean(f, axis=1),
-                             max=np.nanmax(f, axis=1), std=np.nanstd(f, axis=1),
-                             count=np.isfinite(f).sum(axis=1).astype(np.float64))
+            if dev_stats is not None and lab in dev_stats:
+                st = dev_stats[lab]       # reduced on the GPU (spx_round_stats_dev)
+                stats = dict(min=st[0], mean=st[1], max=st[2], std=st[3], count=st[4])
+            else:
+                f = np.round(flds[lab], self._nc_nmrl_prcn)
+                with np.errstate(invalid='ignore'), np.testing.suppress_warnings() as sup:
+                    sup.filter(RuntimeWarning)
+                    stats = dict(min=np.nanmin(f, axis=1), mean=np.nanmean(f, axis=1),
+                                 max=np.nanmax(f, axis=1), std=np.nanstd(f, axis=1),
+                                 count=np.isfinite(f).sum(axis=1).astype(np.float64))
             for stat, vals in stats.items():
                 col = stats_rows.setdefault(f'{lab}_{stat}', {})
                 for t, v in zip(time_steps, vals):

@@ -22,6 +22,14 @@ _READ_LABS = (  # interp/steps.py:33-53
     '_n_pies', '_min_vg_val', '_interp_flag_est_vars', '_intrp_dtype')
 
 
+class InterpFields(dict):
+    """``{label: field}`` (element 7 of the reference's 13-tuple) plus what the GPU
+    output stage already did: ``rounded`` (fields are rounded to ``nmrl_prcn`` decimals)
+    and ``stats`` ({label: ndarray[5, T]} per-step min / mean / max / std / count)."""
+    rounded = False
+    stats = None
+
+
 class SpInterpSteps:
 
     def __init__(self, spinterp_main_cls, engine=None):
@@ -37,7 +45,8 @@ class SpInterpSteps:
     def interpolate_subset(self, args_for_interp):
         """interp/steps.py:61-71.  Unlike the reference's traceback_wrapper
         (misc.py:95-117) errors are raised, not printed and swallowed."""
-        self._write_to_disk(self._get_all_interp_outputs(args_for_interp))
+        pend = self._submit_interp(args_for_interp, output_stage=True)
+        self._write_to_disk(self._finish_interp(pend, args_for_interp))
         return
 
     # -- compute half ------------------------------------------------------
@@ -74,13 +83,25 @@ class SpInterpSteps:
             max_var_cut=self._max_var_cut, min_vg_val=self._min_vg_val,
             est_var_flag=bool(self._interp_flag_est_vars), intrp_dtype=self._intrp_dtype)
 
-    def _get_all_interp_outputs(self, args):
+    def _submit_interp(self, args, output_stage=False):
+        """Queue the chunk on the GPU (engine.submit_chunk); returns the pending chunk.
+        output_stage: also run the rounding of interp/steps.py:907-912 and the per-step
+        statistics of interp/main.py:474-525 on the device (the fields then come back
+        rounded, which ``_get_all_interp_outputs`` of the reference does not do)."""
+        return self._get_engine().submit_chunk(
+            round_decimals=int(self._nc_nmrl_prcn) if output_stage else None,
+            field_stats=bool(output_stage), **self._chunk_kwargs(args))
+
+    def _finish_interp(self, pend, args, interp_beg_time=None, to_host=True):
         (data_df, beg_idx, end_idx, max_rng, interp_args, lock, drft_arrs, stns_drft_df,
          vgs_ser, vgs_rord_tidxs_ser, fld_beg_row, fld_end_row) = args
-        interp_beg_time = timeit.default_timer()
+        if interp_beg_time is None:
+            interp_beg_time = timeit.default_timer()
         interp_labels = [a[2] for a in interp_args]
-
-        flds, prblm = self._get_engine().interp_chunk(**self._chunk_kwargs(args))
+        raw, prblm = pend.result(to_host=to_host)
+        flds = InterpFields(raw)
+        flds.rounded = pend.round_decimals is not None
+        flds.stats = pend.field_stats
 
         time_steps = data_df.index
         if prblm and self._vb:   # steps.py:847-860
@@ -90,6 +111,10 @@ class SpInterpSteps:
 
         return (lock, beg_idx, end_idx, data_df, vgs_ser, max_rng, interp_labels, flds,
                 fld_beg_row, fld_end_row, vgs_rord_tidxs_ser, time_steps, interp_beg_time)
+
+    def _get_all_interp_outputs(self, args):
+        interp_beg_time = timeit.default_timer()
+        return self._finish_interp(self._submit_interp(args), args, interp_beg_time)
 
     # -- output half -------------------------------------------------------
     def _write_to_disk(self, args):
@@ -106,7 +131,8 @@ class SpInterpSteps:
             try:
                 for label in interp_labels:
                     flds = interp_flds_dict[label]
-                    if np.issubdtype(flds.dtype, np.floating):
+                    if (np.issubdtype(flds.dtype, np.floating)
+                            and not getattr(interp_flds_dict, 'rounded', False)):
                         np.round(flds, self._nc_nmrl_prcn, flds)
                     nrows = fld_end_row - fld_beg_row
                     flds3 = flds.reshape(flds.shape[0], nrows, -1)

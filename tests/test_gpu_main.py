@@ -95,3 +95,47 @@ def test_main_end_to_end(tmp_path):
         for st in ('min', 'mean', 'max', 'std', 'count'):
             assert f'{lab}_{st}' in stats.columns
     assert np.allclose(stats['OK_count'].values, m._cntn_idxs.sum())
+    # the statistics come from the GPU output stage; the reference computes them from
+    # the file content with numpy (interp/main.py:503-520)
+    h = ncwriter.open_for_read(m._nc_file_path)
+    for lab in ('OK', 'IDW_000', 'NNB'):
+        for t in range(T):
+            f = np.asarray(h.read(lab, t), dtype=np.float64)
+            for st in ('min', 'mean', 'max', 'std'):
+                exp_v = getattr(np, f'nan{st}')(f)
+                assert abs(stats[f'{lab}_{st}'].values[t] - exp_v) <= 2e-6 + 1e-6 * abs(exp_v), (
+                    lab, t, st)
+    h.close()
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_round_stats_kernel(dtype):
+    """spx_round_stats_dev: bit-exact np.round in the field dtype + per-row statistics."""
+    import torch
+    from spinterps_b200.engine import ChunkEngine
+    eng = ChunkEngine()
+    rng = np.random.default_rng(5)
+    for (T, n, ld, dec) in [(7, 10007, 10007, 2), (3, 4096, 4100, 1), (5, 33, 36, 3),
+                            (4, 50000, 50000, None)]:
+        a = (rng.gamma(1.0, 5.0, (T, ld)) * rng.choice([1.0, 100.0], (T, 1))).astype(dtype)
+        a[rng.random((T, ld)) < 0.1] = np.nan
+        a[1, :] = np.nan                      # a step without any value
+        a[0, 5] = 0.125                       # ties: round half to even
+        a[0, 6] = 0.375
+        d = torch.from_numpy(a.copy()).cuda()
+        view = d[:, :n]
+        st = eng.round_and_stats(view, dec)
+        got = d.cpu().numpy()
+        ref = a.copy()
+        if dec is not None:
+            ref[:, :n] = np.round(a[:, :n], dec)
+        assert np.array_equal(got, ref, equal_nan=True), (T, n, ld, dec)
+        f = ref[:, :n].astype(np.float64)
+        with np.errstate(all='ignore'), np.testing.suppress_warnings() as sup:
+            sup.filter(RuntimeWarning)
+            exp = np.stack([np.nanmin(f, 1), np.nanmean(f, 1), np.nanmax(f, 1), np.nanstd(f, 1),
+                            np.isfinite(f).sum(1).astype(float)])
+        assert np.array_equal(np.isnan(st), np.isnan(exp))
+        assert np.array_equal(st[4], exp[4])
+        ok = ~np.isnan(exp)
+        assert np.all(np.abs(st[ok] - exp[ok]) <= 1e-11 * np.maximum(1.0, np.abs(exp[ok])))
