@@ -99,6 +99,22 @@ int spx_fill_theo_vg_vals(const char* vg_name, const double* h_arr, int64_t n,
 int spx_fill_dists_one_pt(double x, double y, const double* xs, const double* ys,
                           int64_t n, double* dists);
 
+/* cyth/interpmthds.pyx:811-890  sel_equidist_refs: angular sector (ref_pie_idxs) of every
+ * reference point around the destination, members per sector (ref_pie_cts) and the distance
+ * rank of every point INSIDE its sector (ref_sel_pie_idxs); a point within min_dist_thresh
+ * short-cuts to "only the nearest point, rank 0, everything else not_neb_flag" (sector
+ * outputs are then left untouched, as in the reference).  The reference's DT_UL is
+ * unsigned long: uint64_t on LP64.  tem_ref_sel_dists is the reference's scratch (unused).
+ * Equal distances are ranked by index (the reference: np.argsort, unstable). */
+int spx_sel_equidist_refs(double dst_x, double dst_y, const double* ref_xs, const double* ref_ys,
+                          int64_t n_refs, uint64_t n_pies, double min_dist_thresh,
+                          int64_t not_neb_flag, double* dists, double* tem_ref_sel_dists,
+                          int64_t* ref_sel_pie_idxs, uint64_t* ref_pie_idxs,
+                          uint64_t* ref_pie_cts);
+/* cyth/interpmthds.pyx:893-925  get_nd_dists: Euclidean distance of every pair i > j of
+ * pts[n_pts, n_dims], row by row: dists[i (i - 1) / 2 + j]. */
+int spx_get_nd_dists(const double* pts, int64_t n_pts, int64_t n_dims, double* dists);
+
 /* cyth/interpmthds.pyx:784-795  fill_wts_and_sum(dists, wts, idw_exp) -> sum */
 int spx_fill_wts_and_sum(const double* dists, double* wts, int64_t n, double idw_exp,
                          double* wts_sum);
@@ -409,6 +425,14 @@ int spx_nrst_max_neighbors(void);
 int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
                       const uint8_t* mask, const double* cell_x, const double* cell_y,
                       int64_t n_cells, int32_t k, int32_t* nb, int64_t* hash, void* stream);
+/* 'pie' selection (interp/grps.py:168-247 with cyth/interpmthds.pyx:811-890): stations
+ * binned into n_pies angular sectors around the cell, ranked by distance inside their
+ * sector; nb = the first k stations in (rank, distance) order, indices ascending; hash
+ * as above.  n_pies <= 64. */
+int spx_pie_select_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                       const uint8_t* mask, const double* cell_x, const double* cell_y,
+                       int64_t n_cells, int32_t k, int32_t n_pies, int32_t* nb, int64_t* hash,
+                       void* stream);
 /* Assemble + LU + solve every step (and the ones-vector) of every cell-group system. */
 int spx_nrst_solve_dev(const spx_nrst* n, void* stream);
 /* Per cell: rhs from coordinates, sum(lambda) test, NNB fallback, estimate, store. */
@@ -495,6 +519,11 @@ typedef struct spx_local {
 } spx_local;
 int spx_local_build_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
+
+/* Host -> device copy of n_bytes on `stream` (cudaMemcpyAsync; from pageable memory the call
+ * returns once the source has been staged).  The engine's small per-chunk uploads go
+ * through this on a dedicated upload stream. */
+int spx_upload_dev(void* dst_dev, const void* src_host, int64_t n_bytes, void* stream);
 
 /* Round a field to `decimals` decimal places in its own dtype, in place, exactly like
  * np.round (interp/steps.py:907-912: rint(x * 10^d) / 10^d; decimals < 0 = no rounding),

@@ -254,8 +254,8 @@ def _get_neb_idxs_grps(all_neb_idxs):
     return [np.asarray(g, dtype=np.int64) for g in grps]
 
 
-def get_neb_idxs_and_grps(neb_sel_mthd, n_nebs, dst_xs, dst_ys, ref_xs, ref_ys):
-    """interp/grps.py:249-288 ('all' :141-145, 'nrst' :147-166)."""
+def get_neb_idxs_and_grps(neb_sel_mthd, n_nebs, dst_xs, dst_ys, ref_xs, ref_ys, n_pies=None):
+    """interp/grps.py:249-288 ('all' :141-145, 'nrst' :147-166, 'pie' :168-247)."""
     n_refs = ref_xs.size
     n_dst = dst_xs.shape[0]
     if neb_sel_mthd == 'all':
@@ -270,8 +270,96 @@ def get_neb_idxs_and_grps(neb_sel_mthd, n_nebs, dst_xs, dst_ys, ref_xs, ref_ys):
             all_neb_idxs[i, :] = np.sort(np.argsort(dists)[:n_nebs])
         return all_neb_idxs, _get_neb_idxs_grps(all_neb_idxs)
 
-    raise NotImplementedError(
-        "'pie' fails in the reference on LP64 (grps.py:173 vs pyx:17); not restated")
+    if neb_sel_mthd == 'pie':
+        return (lambda a: (a, _get_neb_idxs_grps(a)))(
+            _get_pie_neb_idxs(n_nebs, n_pies, dst_xs, dst_ys, ref_xs, ref_ys))
+
+    raise NotImplementedError(neb_sel_mthd)
+
+
+def sel_equidist_refs(dst_x, dst_y, ref_xs, ref_ys, n_pies, min_dist_thresh, not_neb_flag,
+                      dists, tem_ref_sel_dists, ref_sel_pie_idxs, ref_pie_idxs, ref_pie_cts):
+    """cyth/interpmthds.pyx:811-890.  Angular sector of every reference point seen
+    from the destination, and its distance rank INSIDE its sector
+    (``ref_sel_pie_idxs``).  A point within ``min_dist_thresh`` short-cuts to rank 0
+    for the nearest point only (the caller always passes -1: never)."""
+    n_refs = ref_xs.size
+    two_pi = 2 * math.pi
+    ref_sel_pie_idxs[:] = not_neb_flag
+    fill_dists_one_pt(dst_x, dst_y, ref_xs, ref_ys, dists)
+    min_dist, min_dist_idx = np.inf, -1
+    for i in range(n_refs):
+        if (dists[i] <= min_dist_thresh) and (dists[i] < min_dist):
+            min_dist_idx, min_dist = i, dists[i]
+    if min_dist < np.inf:
+        ref_sel_pie_idxs[min_dist_idx] = 0
+        return
+    ref_pie_cts[:] = 0
+    for j in range(n_refs):
+        x_dist = ref_xs[j] - dst_x
+        y_dist = ref_ys[j] - dst_y
+        if not x_dist:
+            ang = 0.0
+        else:
+            ang = math.atan(y_dist / x_dist)
+            if (x_dist < 0) and (y_dist > 0):
+                ang = math.pi + ang
+            elif (x_dist < 0) and (y_dist < 0):
+                ang = math.pi + ang
+            elif (x_dist > 0) and (y_dist < 0):
+                ang = two_pi + ang
+        pie = int(ang * n_pies / two_pi)   # x_dist < 0, y_dist == 0 gives -0.0 -> sector 0
+        ref_pie_idxs[j] = pie
+        ref_pie_cts[pie] += 1
+    for j in range(n_pies):
+        if not ref_pie_cts[j]:
+            continue
+        tem_ref_sel_dists[:] = np.where(np.asarray(ref_pie_idxs) == j, dists, np.inf)
+        srtd = np.argsort(tem_ref_sel_dists)
+        for i in range(n_refs):
+            if tem_ref_sel_dists[srtd[i]] == np.inf:
+                break
+            ref_sel_pie_idxs[srtd[i]] = i
+
+
+def get_nd_dists(pts):
+    """cyth/interpmthds.pyx:893-925: distances of all point pairs i > j, row by row."""
+    pts = np.asarray(pts, dtype=np.float64)
+    n_pts = pts.shape[0]
+    out = np.full((n_pts * (n_pts - 1)) // 2, np.nan)
+    c = 0
+    for i in range(n_pts):
+        for j in range(i):
+            d = 0.0
+            for k in range(pts.shape[1]):
+                d += (pts[i, k] - pts[j, k]) ** 2
+            out[c] = d ** 0.5
+            c += 1
+    return out
+
+
+def _get_pie_neb_idxs(n_nebs, n_pies, dst_xs, dst_ys, ref_xs, ref_ys):
+    """interp/grps.py:168-247: stations ordered by (rank inside their sector, distance);
+    the first n_nebs of that order, ascending.  (The reference passes uint32 work arrays
+    where the compiled helper wants unsigned long, so this only runs on LLP64; the golden
+    case h_pie was produced with a cast at that call boundary.)"""
+    n_refs = ref_xs.size
+    dists = np.zeros(n_refs)
+    ref_pie_idxs = np.zeros(n_refs, dtype=np.int64)
+    tem = np.zeros(n_refs)
+    sel = np.zeros(n_refs, dtype=np.int64)
+    cts = np.zeros(n_pies, dtype=np.int64)
+    all_neb_idxs = np.full((dst_xs.size, n_nebs), -1, dtype=int)
+    for i in range(dst_xs.size):
+        sel_equidist_refs(dst_xs[i], dst_ys[i], ref_xs, ref_ys, n_pies, -1, -1, dists, tem,
+                          sel, ref_pie_idxs, cts)
+        assert np.all(sel != -1)
+        order = []
+        for u in np.unique(sel):
+            same = np.where(sel == u)[0]
+            order.extend(same[np.argsort(dists[same])].tolist())
+        all_neb_idxs[i, :] = np.sort(np.array(order)[:n_nebs])
+    return all_neb_idxs
 
 
 # ---------------------------------------------------------------------------
@@ -469,7 +557,7 @@ def interp_chunk(
         neb_sel_mthd='all', n_nebs=None,
         min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
         min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
-        faithful=False):
+        faithful=False, n_pies=None):
     """Compute half of ``SpInterpSteps.interpolate_subset`` for one time chunk
     and one grid-row chunk.
 
@@ -527,7 +615,7 @@ def interp_chunk(
 
     # -- drop stations never selected, steps.py:592-608 (Q9) --
     tke = np.unique(get_neb_idxs_and_grps(
-        neb_sel_mthd, n_nebs, dst_xs, dst_ys, stn_xs, stn_ys)[0])
+        neb_sel_mthd, n_nebs, dst_xs, dst_ys, stn_xs, stn_ys, n_pies)[0])
     if tke.size != stn_xs.shape[0]:
         stn_xs = stn_xs[tke].copy()
         stn_ys = stn_ys[tke].copy()
@@ -590,7 +678,7 @@ def interp_chunk(
             nuggetness_flags = None
 
         neb_idxs, neb_grps = get_neb_idxs_and_grps(
-            neb_sel_mthd, n_nebs, dst_xs, dst_ys, grp_xs, grp_ys)
+            neb_sel_mthd, n_nebs, dst_xs, dst_ys, grp_xs, grp_ys, n_pies)
 
         pts_done = np.zeros(n_dst_pts, dtype=bool)
 

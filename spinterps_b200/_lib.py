@@ -193,6 +193,13 @@ _SIGS = {
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    'spx_pie_select_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    'spx_sel_equidist_refs': (C.c_int, [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_uint64, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    'spx_get_nd_dists': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'spx_nrst_solve_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
     'spx_nrst_krige_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p]),
     'spx_nrst_idw_dev': (C.c_int, [C.POINTER(spx_nrst), C.c_void_p, C.c_void_p]),
@@ -202,6 +209,7 @@ _SIGS = {
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int32, C.c_void_p]),
     'spx_copy_to_mapped_host_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'spx_upload_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'spx_round_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),
     'spx_round_stats_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

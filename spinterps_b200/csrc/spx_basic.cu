@@ -177,6 +177,61 @@ __global__ void k_seq_sum(const double* __restrict__ a, const double* __restrict
     }
 }
 
+// cyth/interpmthds.pyx:811-890 for one destination point: thread per reference point.
+__global__ void k_sel_equidist(double x, double y, const double* __restrict__ xs,
+                               const double* __restrict__ ys, int n, int n_pies,
+                               double min_dist_thresh, long long not_neb_flag,
+                               double* __restrict__ dists, long long* __restrict__ sel,
+                               unsigned long long* __restrict__ pidx,
+                               unsigned long long* __restrict__ cts) {
+    extern __shared__ double sd[];       // [n] distances, then [n] sectors (as int)
+    int* sp = reinterpret_cast<int*>(sd + n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sd[i] = dist_rn(x, y, xs[i], ys[i]);
+        sp[i] = pie_sector(__dsub_rn(xs[i], x), __dsub_rn(ys[i], y), n_pies);
+        dists[i] = sd[i];
+        sel[i] = not_neb_flag;
+    }
+    __syncthreads();
+    // a reference point within the threshold: only the nearest such point is selected
+    __shared__ int s_near;
+    if (threadIdx.x == 0) {
+        int best = -1;
+        for (int i = 0; i < n; ++i)
+            if (sd[i] <= min_dist_thresh && (best < 0 || sd[i] < sd[best])) best = i;
+        s_near = best;
+        if (best >= 0) sel[best] = 0;
+    }
+    __syncthreads();
+    if (s_near >= 0) return;
+    for (int j = threadIdx.x; j < n_pies; j += blockDim.x) {
+        unsigned long long c = 0;
+        for (int i = 0; i < n; ++i) c += (sp[i] == j);
+        cts[j] = c;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        pidx[i] = (unsigned long long)sp[i];
+        long long rank = 0;              // points of the same sector that come first
+        for (int q = 0; q < n; ++q)
+            if (sp[q] == sp[i] && (sd[q] < sd[i] || (sd[q] == sd[i] && q < i))) ++rank;
+        sel[i] = rank;
+    }
+}
+
+// cyth/interpmthds.pyx:893-925: pair (i > j) -> slot i (i - 1) / 2 + j.
+__global__ void k_nd_dists(const double* __restrict__ pts, int64_t n_pts, int64_t n_dims,
+                           double* __restrict__ out) {
+    const int64_t i = blockIdx.y;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= i) return;
+    double d = 0.0;
+    for (int64_t k = 0; k < n_dims; ++k) {
+        const double t = __dsub_rn(pts[i * n_dims + k], pts[j * n_dims + k]);
+        d = __dadd_rn(d, __dmul_rn(t, t));
+    }
+    out[i * (i - 1) / 2 + j] = __dsqrt_rn(d);
+}
+
 // ---------------------------------------------------------------- helpers
 
 struct DevBuf {
@@ -491,6 +546,52 @@ int spx_fill_dists_one_pt(double x, double y, const double* xs, const double* ys
                                                          o.as<double>());
     SPX_CHECK_LAUNCH("k_dists_one_pt");
     SPX_CUDA(cudaMemcpy(dists, o.p, n * 8, cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+
+int spx_sel_equidist_refs(double dst_x, double dst_y, const double* ref_xs, const double* ref_ys,
+                          int64_t n_refs, uint64_t n_pies, double min_dist_thresh,
+                          int64_t not_neb_flag, double* dists, double* tem_ref_sel_dists,
+                          int64_t* ref_sel_pie_idxs, uint64_t* ref_pie_idxs,
+                          uint64_t* ref_pie_cts) {
+    if (n_refs < 0 || n_pies < 1 || n_pies > 1024 || n_refs > 4096) {
+        set_error("sel_equidist_refs: n_refs outside 0..4096 or n_pies outside 1..1024");
+        return SPX_EINVAL;
+    }
+    if (n_refs == 0) return SPX_OK;
+    (void)tem_ref_sel_dists;   // scratch of the reference's per-sector argsort; not needed
+    DevBuf a, b, d, s, p, c;
+    int rc;
+    if ((rc = upload(a, ref_xs, n_refs * 8)) || (rc = upload(b, ref_ys, n_refs * 8)) ||
+        (rc = d.alloc(n_refs * 8)) || (rc = s.alloc(n_refs * 8)) ||
+        (rc = upload(p, ref_pie_idxs, n_refs * 8)) || (rc = upload(c, ref_pie_cts, n_pies * 8)))
+        return rc;
+    k_sel_equidist<<<1, 256, (size_t)n_refs * 12 + 16>>>(
+        dst_x, dst_y, a.as<double>(), b.as<double>(), (int)n_refs, (int)n_pies, min_dist_thresh,
+        (long long)not_neb_flag, d.as<double>(), s.as<long long>(),
+        p.as<unsigned long long>(), c.as<unsigned long long>());
+    SPX_CHECK_LAUNCH("k_sel_equidist");
+    SPX_CUDA(cudaMemcpy(dists, d.p, n_refs * 8, cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(ref_sel_pie_idxs, s.p, n_refs * 8, cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(ref_pie_idxs, p.p, n_refs * 8, cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(ref_pie_cts, c.p, n_pies * 8, cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+
+int spx_get_nd_dists(const double* pts, int64_t n_pts, int64_t n_dims, double* dists) {
+    if (n_pts < 0 || n_dims < 0 || n_pts > 65535) {
+        set_error("get_nd_dists: bad sizes (n_pts <= 65535)");
+        return SPX_EINVAL;
+    }
+    const int64_t n_d = n_pts * (n_pts - 1) / 2;
+    if (n_d <= 0) return SPX_OK;
+    DevBuf a, o;
+    int rc;
+    if ((rc = upload(a, pts, n_pts * n_dims * 8)) || (rc = o.alloc(n_d * 8))) return rc;
+    dim3 grid((unsigned)((n_pts + 127) / 128), (unsigned)n_pts);
+    k_nd_dists<<<grid, 128>>>(a.as<double>(), n_pts, n_dims, o.as<double>());
+    SPX_CHECK_LAUNCH("k_nd_dists");
+    SPX_CUDA(cudaMemcpy(dists, o.p, n_d * 8, cudaMemcpyDeviceToHost));
     return SPX_OK;
 }
 

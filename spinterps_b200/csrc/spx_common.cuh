@@ -187,6 +187,26 @@ __device__ __forceinline__ VgFast make_vg_fast_dev(const spx_vg& v) {
     return f;
 }
 
+// Angular sector of a reference point seen from a destination, cyth/interpmthds.pyx:849-866:
+// atan of the slope plus quadrant fix-ups (xd == 0 -> 0; xd < 0, yd == 0 -> atan(-0.0) ->
+// sector 0).  CUDA's atan may differ from libm's in the last bit, which can only matter
+// for a point exactly on a sector edge.  The reference indexes out of range when the
+// product rounds up to n_pies; clamped here.
+__device__ __forceinline__ int pie_sector(double xd, double yd, int n_pies) {
+    const double two_pi = 2.0 * CUDART_PI;
+    double ang;
+    if (xd == 0.0) {
+        ang = 0.0;
+    } else {
+        ang = atan(__ddiv_rn(yd, xd));
+        if (xd < 0.0 && yd > 0.0) ang = __dadd_rn(CUDART_PI, ang);
+        else if (xd < 0.0 && yd < 0.0) ang = __dadd_rn(CUDART_PI, ang);
+        else if (xd > 0.0 && yd < 0.0) ang = __dadd_rn(two_pi, ang);
+    }
+    const int p = (int)__ddiv_rn(__dmul_rn(ang, (double)n_pies), two_pi);
+    return min(max(p, 0), n_pies - 1);
+}
+
 __device__ __forceinline__ double clampd(double v, int has_lo, int has_hi, double lo, double hi) {
     // NaN-safe like interp/steps.py:466-476 (comparisons with NaN are false)
     if (has_lo && v < lo) v = lo;

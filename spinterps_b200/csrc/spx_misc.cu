@@ -551,6 +551,17 @@ int spx_copy_to_mapped_host_dev(void* dst_host_mapped, const void* src_dev, int6
     return SPX_OK;
 }
 
+int spx_upload_dev(void* dst_dev, const void* src_host, int64_t n_bytes, void* stream) {
+    if (n_bytes == 0) return SPX_OK;
+    if (!dst_dev || !src_host || n_bytes < 0) {
+        set_error("upload: null pointer or negative size");
+        return SPX_EINVAL;
+    }
+    SPX_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)n_bytes, cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+    return SPX_OK;
+}
+
 int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
                          const uint8_t* cell_bad, uint8_t* fail, void* stream) {
     const int64_t total = n_slots * n_cells;

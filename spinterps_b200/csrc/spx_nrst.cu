@@ -73,6 +73,76 @@ __global__ void __launch_bounds__(128) k_topk(const double* __restrict__ stn_x,
     hash[c] = (int64_t)(h >> 1);   // non-negative
 }
 
+// 'pie' neighbour selection (interp/grps.py:168-247 + cyth/interpmthds.pyx:811-890): the
+// stations are binned into n_pies angular sectors around the cell and ranked by distance
+// inside their sector; the neighbours are the first k stations in (rank, distance) order,
+// i.e. the nearest station of every sector, then the second nearest of every sector, ...
+// One thread per cell, one pass over the stations per rank level (k / n_pies levels).
+// Sector expression: pie_sector() in spx_common.cuh.
+constexpr int PIE_MAX = 64;
+
+__global__ void __launch_bounds__(128) k_pie_select(const double* __restrict__ stn_x,
+                                                    const double* __restrict__ stn_y, int n_stn,
+                                                    const uint8_t* __restrict__ mask,
+                                                    const double* __restrict__ cell_x,
+                                                    const double* __restrict__ cell_y,
+                                                    int64_t n_cells, int k, int n_pies,
+                                                    int32_t* __restrict__ nb,
+                                                    int64_t* __restrict__ hash) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double x = cell_x[c], y = cell_y[c];
+    double last_d[PIE_MAX], cand_d[PIE_MAX];
+    int last_i[PIE_MAX], cand_i[PIE_MAX];
+    int sel[NRST_KMAX];
+    for (int p = 0; p < n_pies; ++p) { last_d[p] = -1.0; last_i[p] = -1; }
+    int cnt = 0;
+    while (cnt < k) {
+        for (int p = 0; p < n_pies; ++p) { cand_d[p] = CUDART_INF; cand_i[p] = -1; }
+        for (int s = 0; s < n_stn; ++s) {
+            if (mask != nullptr && !mask[s]) continue;
+            const double sx = stn_x[s], sy = stn_y[s];
+            const double d = dist_rn(x, y, sx, sy);
+            const int p = pie_sector(__dsub_rn(sx, x), __dsub_rn(sy, y), n_pies);
+            // strictly after the station taken at the previous level, in (d, index) order
+            const bool after = d > last_d[p] || (d == last_d[p] && s > last_i[p]);
+            if (after && (cand_i[p] < 0 || d < cand_d[p])) {
+                cand_d[p] = d;
+                cand_i[p] = s;
+            }
+        }
+        // the level's stations in distance order
+        int taken = 0;
+        for (;;) {
+            int bp = -1;
+            for (int p = 0; p < n_pies; ++p)
+                if (cand_i[p] >= 0 && (bp < 0 || cand_d[p] < cand_d[bp] ||
+                                       (cand_d[p] == cand_d[bp] && cand_i[p] < cand_i[bp])))
+                    bp = p;
+            if (bp < 0) break;
+            if (cnt < k) sel[cnt++] = cand_i[bp];
+            last_d[bp] = cand_d[bp];
+            last_i[bp] = cand_i[bp];
+            cand_i[bp] = -1;
+            ++taken;
+        }
+        if (taken == 0) break;   // fewer than k stations available
+    }
+    for (int i = 1; i < cnt; ++i) {           // indices ascending (np.sort)
+        const int v = sel[i];
+        int j = i;
+        while (j > 0 && sel[j - 1] > v) { sel[j] = sel[j - 1]; --j; }
+        sel[j] = v;
+    }
+    uint64_t h = 0x243f6a8885a308d3ull;
+    for (int i = 0; i < k; ++i) {
+        const int v = (i < cnt) ? sel[i] : -1;
+        nb[c * k + i] = v;
+        h = mix64(h, (uint64_t)(uint32_t)v);
+    }
+    hash[c] = (int64_t)(h >> 1);
+}
+
 struct NrstSolveArgs {
     int n_grp;                    // cell groups (systems)
     int k, n_border, n_drifts, kind;
@@ -356,6 +426,22 @@ int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
     k_topk<<<(unsigned)((n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, nb, hash);
     SPX_CHECK_LAUNCH("k_topk");
+    return SPX_OK;
+}
+
+int spx_pie_select_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
+                       const uint8_t* mask, const double* cell_x, const double* cell_y,
+                       int64_t n_cells, int32_t k, int32_t n_pies, int32_t* nb, int64_t* hash,
+                       void* stream) {
+    if (n_cells == 0) return SPX_OK;
+    if (k < 1 || k > NRST_KMAX || n_pies < 1 || n_pies > PIE_MAX) {
+        set_error("pie_select: k=%d outside 1..%d or n_pies=%d outside 1..%d", k, NRST_KMAX,
+                  n_pies, PIE_MAX);
+        return SPX_EINVAL;
+    }
+    k_pie_select<<<(unsigned)((n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, n_pies, nb, hash);
+    SPX_CHECK_LAUNCH("k_pie_select");
     return SPX_OK;
 }
 

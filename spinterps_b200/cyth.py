@@ -112,3 +112,37 @@ def get_theo_vg_vals(in_model, h_arr):
     for t, s, r in _lib.parse_vg_str(in_model, clamp_range=False):
         fill_theo_vg_vals(_lib.VG_NAMES[t], h, r, s, vals)
     return vals
+
+
+def sel_equidist_refs(dst_x, dst_y, ref_xs, ref_ys, n_pies, min_dist_thresh, not_neb_flag,
+                      dists, tem_ref_sel_dists, ref_sel_pie_idxs, ref_pie_idxs, ref_pie_cts):
+    """cyth/interpmthds.pyx:811-890.  ``ref_pie_idxs`` / ``ref_pie_cts`` are the
+    reference's ``unsigned long`` buffers: uint64 on LP64."""
+    _c64(ref_xs, 'ref_xs', 1), _c64(ref_ys, 'ref_ys', 1), _c64(dists, 'dists', 1)
+    _c64(tem_ref_sel_dists, 'tem_ref_sel_dists', 1)
+    for name, a, dt in (('ref_sel_pie_idxs', ref_sel_pie_idxs, np.int64),
+                        ('ref_pie_idxs', ref_pie_idxs, np.uint64),
+                        ('ref_pie_cts', ref_pie_cts, np.uint64)):
+        if not (isinstance(a, np.ndarray) and a.dtype == dt and a.ndim == 1
+                and a.flags.c_contiguous):
+            raise ValueError(f'Buffer dtype mismatch, expected {np.dtype(dt).name}: {name}')
+    n = ref_xs.size
+    assert ref_ys.size == dists.size == ref_sel_pie_idxs.size == ref_pie_idxs.size == n
+    assert ref_pie_cts.size >= n_pies
+    lib = _lib.load()
+    _lib.check(lib.spx_sel_equidist_refs(
+        float(dst_x), float(dst_y), ref_xs.ctypes.data, ref_ys.ctypes.data, n, int(n_pies),
+        float(min_dist_thresh), int(not_neb_flag), dists.ctypes.data,
+        tem_ref_sel_dists.ctypes.data, ref_sel_pie_idxs.ctypes.data, ref_pie_idxs.ctypes.data,
+        ref_pie_cts.ctypes.data), 'sel_equidist_refs')
+
+
+def get_nd_dists(pts):
+    """cyth/interpmthds.pyx:893-925 -> ndarray[n (n - 1) / 2]."""
+    _c64(pts, 'pts', 2)
+    n = pts.shape[0]
+    out = np.full((n * (n - 1)) // 2, np.nan, dtype=np.float64)
+    lib = _lib.load()
+    _lib.check(lib.spx_get_nd_dists(pts.ctypes.data, n, pts.shape[1], out.ctypes.data),
+               'get_nd_dists')
+    return out

@@ -104,6 +104,7 @@ class PendingChunk:
     def result(self, to_host=True):
         eng = self.engine
         with torch.cuda.device(eng.device):
+            eng._begin_call()
             n0 = eng.total_launches
             for fn in self.deferred:
                 fn()
@@ -135,7 +136,7 @@ class _TracedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
-        if not name.endswith('_dev'):
+        if not name.endswith('_dev') or name == 'spx_upload_dev':
             return fn
         eng = self._eng
 
@@ -195,26 +196,71 @@ class ChunkEngine:
         self.timing = {}
         self.total_launches = 0
         self.h2d_stream = torch.cuda.Stream(self.device)
+        self._h2d_handle = C.c_void_p(self.h2d_stream.cuda_stream)
         self._h2d_dirty = False
+        self._main = None          # compute stream, cached per public call
+        self._main_handle = None
+        self._arena = None         # per-chunk upload arena (see _arena_take)
+        self._arena_off = 0
 
     # ------------------------------------------------------------ helpers
+    _TORCH_OF = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+                 np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+                 np.dtype(np.uint8): torch.uint8, np.dtype(np.bool_): torch.bool}
+    _ARENA_MAX_ITEM = 32 << 20
+
+    def _main_stream(self):
+        if self._main is None:
+            self._main = torch.cuda.current_stream(self.device)
+            self._main_handle = C.c_void_p(self._main.cuda_stream)
+        return self._main
+
+    def _begin_call(self):
+        """Refresh the cached compute stream (public entry points call this)."""
+        self._main = None
+        self._main_stream()
+
+    def _arena_take(self, nbytes):
+        """Device bytes for one upload, carved from a per-chunk arena that belongs to
+        the upload stream's allocator pool (one stream-context switch per arena, not
+        per upload) and is marked as used by the compute stream."""
+        need = (nbytes + 255) & ~255
+        if self._arena is None or self._arena_off + need > self._arena.numel():
+            size = max(16 << 20, 2 * need)
+            with torch.cuda.stream(self.h2d_stream):
+                self._arena = torch.empty(size, dtype=torch.uint8, device=self.device)
+            self._arena.record_stream(self._main_stream())
+            self._arena_off = 0
+        o = self._arena_off
+        self._arena_off += need
+        return self._arena[o:o + nbytes]
+
     def _dev(self, arr, dtype=None):
         """Host -> device copy on a dedicated upload stream.  A pageable-memory
         cudaMemcpyAsync first synchronises its stream, so issuing it on the compute
         stream would stall the host behind every queued kernel; the compute stream
         instead waits for the upload stream right before the next launch."""
         arr = np.ascontiguousarray(arr)
-        if not arr.flags.writeable:       # e.g. a read-only pandas view
-            arr = arr.copy()
-        t = torch.from_numpy(arr)
-        if dtype is not None:
-            t = t.to(dtype)
-        main = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self.h2d_stream):
-            d = t.to(self.device, non_blocking=True)
-        d.record_stream(main)
+        tdt = self._TORCH_OF.get(arr.dtype)
+        if dtype is not None or tdt is None or arr.nbytes > self._ARENA_MAX_ITEM:
+            if not arr.flags.writeable:       # e.g. a read-only pandas view
+                arr = arr.copy()
+            t = torch.from_numpy(arr)
+            if dtype is not None:
+                t = t.to(dtype)
+            main = self._main_stream()
+            with torch.cuda.stream(self.h2d_stream):
+                d = t.to(self.device, non_blocking=True)
+            d.record_stream(main)
+            self._h2d_dirty = True
+            return d
+        if arr.nbytes == 0:
+            return torch.empty(arr.shape, dtype=tdt, device=self.device)
+        d = self._arena_take(arr.nbytes)
+        _lib.check(self.lib.spx_upload_dev(C.c_void_p(d.data_ptr()), C.c_void_p(arr.ctypes.data),
+                                           arr.nbytes, self._h2d_handle), 'upload')
         self._h2d_dirty = True
-        return d
+        return d.view(tdt).view(arr.shape)
 
     def _dev_pack(self, arrays):
         """Upload several small arrays with ONE host->device copy; returns device
@@ -251,7 +297,7 @@ class ChunkEngine:
     def _sync_uploads(self):
         """Make the compute stream wait for every upload issued so far."""
         if self._h2d_dirty:
-            torch.cuda.current_stream(self.device).wait_stream(self.h2d_stream)
+            self._main_stream().wait_stream(self.h2d_stream)
             self._h2d_dirty = False
 
     @staticmethod
@@ -260,7 +306,8 @@ class ChunkEngine:
 
     def _stream(self):
         self._sync_uploads()
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._main_stream()
+        return self._main_handle
 
     def _fetch_async(self, t):
         """Queue a device->pinned-host copy of a small tensor; the caller reads
@@ -281,14 +328,14 @@ class ChunkEngine:
         if not self.profile_gemm:
             return None
         e0 = torch.cuda.Event(enable_timing=True)
-        e0.record(torch.cuda.current_stream(self.device))
+        e0.record(self._main_stream())
         return e0
 
     def _prof_end(self, e0, name, bound, work):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
-        e1.record(torch.cuda.current_stream(self.device))
+        e1.record(self._main_stream())
         self.kernel_events.append((name, bound, float(work), e0, e1))
 
     def round_and_stats(self, fld, decimals=None):
@@ -299,6 +346,7 @@ class ChunkEngine:
         out = np.empty((5, n_rows))
         dec = -1 if decimals is None else int(decimals)
         with torch.cuda.device(self.device):
+            self._begin_call()
             for r0 in range(0, n_rows, 65535):
                 r1 = min(n_rows, r0 + 65535)
                 ws = torch.empty(max(1, self.lib.spx_round_stats_workspace(r1 - r0, row_len)),
@@ -347,7 +395,7 @@ class ChunkEngine:
             fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
             min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
             min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
-            return_device=False):
+            return_device=False, n_pies=None):
         """Same contract as the reference's ``_get_all_interp_outputs`` reduced
         to arrays (see oracle/spinterp_oracle.py:interp_chunk for the argument
         meaning).  Returns ({label: ndarray[T, rows*cols]}, problem_steps)."""
@@ -357,7 +405,7 @@ class ChunkEngine:
             fld_beg_row=fld_beg_row, fld_end_row=fld_end_row, neb_sel_mthd=neb_sel_mthd,
             n_nebs=n_nebs, min_var_thr=min_var_thr, min_var_cut=min_var_cut,
             max_var_cut=max_var_cut, min_vg_val=min_vg_val, est_var_flag=est_var_flag,
-            intrp_dtype=intrp_dtype)
+            intrp_dtype=intrp_dtype, n_pies=n_pies)
         return pend.result(to_host=not return_device)
 
     def submit_chunk(
@@ -366,18 +414,20 @@ class ChunkEngine:
             fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
             min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None,
             min_vg_val=0.0, est_var_flag=False, intrp_dtype=np.float32,
-            round_decimals=None, field_stats=False):
+            round_decimals=None, field_stats=False, n_pies=None):
         """Queue every kernel of the chunk and return a PendingChunk.
 
         round_decimals / field_stats: the output stage of the reference on the device --
         fields rounded like ``np.round(flds, nmrl_prcn)`` before they leave the GPU and
         per-step min / mean / max / std / count in ``PendingChunk.field_stats``."""
         with torch.cuda.device(self.device):
+            self._begin_call()
+            self._arena = None
             pend = self._interp_chunk(
                 data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
                 cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
                 n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
-                intrp_dtype)
+                intrp_dtype, n_pies)
             pend.round_decimals = round_decimals
             pend.want_field_stats = bool(field_stats)
             return pend
@@ -387,7 +437,7 @@ class ChunkEngine:
             self, data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
             cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
             n_nebs, min_var_thr, min_var_cut, max_var_cut, min_vg_val, est_var_flag,
-            intrp_dtype):
+            intrp_dtype, n_pies=None):
         self.stats = {}
         deferred = []
         self.timing = {}
@@ -408,24 +458,34 @@ class ChunkEngine:
         edk_flag = 'EDK' in interp_types
         if krg_types:
             assert vgs is not None
-            vgs = [str(v) for v in vgs]
+            vgs = list(vgs)
+            if set(map(type, vgs)) != {str}:
+                vgs = [str(v) for v in vgs]
             assert len(vgs) == n_steps
-            assert all(v != 'nan' for v in vgs), (   # steps.py:504-507
+            assert 'nan' not in set(vgs), (          # steps.py:504-507
                 'NaN VGs not allowed! Use Nugget or any other appropriate one!')
-        if neb_sel_mthd not in ('all', 'nrst'):
-            raise NotImplementedError(
-                f"neighbor selection '{neb_sel_mthd}' is not supported ('pie' cannot run in "
-                "the reference on LP64 platforms either, SURVEY.md top table)")
-        nrst = neb_sel_mthd == 'nrst'
+        if neb_sel_mthd not in ('all', 'nrst', 'pie'):
+            raise NotImplementedError(f"neighbor selection '{neb_sel_mthd}'")
+        # 'nrst' and 'pie' differ only in how a cell picks its n_nebs stations
+        # (interp/grps.py:147-166 / :168-247); everything after that is shared
+        nrst = neb_sel_mthd in ('nrst', 'pie')
+        self._n_pies = 0
         if nrst:
             assert isinstance(n_nebs, (int, np.integer)) and n_nebs > 0
+            if neb_sel_mthd == 'pie':
+                assert isinstance(n_pies, (int, np.integer)) and 0 < n_pies <= n_nebs, (
+                    'n_pies should be > 0 and <= n_neighbors!')
+                if n_pies > 64:
+                    raise NotImplementedError('n_pies > 64 is not supported')
+                self._n_pies = int(n_pies)
             if n_nebs >= n_stn:
                 nrst = False            # interp/prepare.py:434-463 falls back to 'all'
             elif n_nebs > self.lib.spx_nrst_max_neighbors():
                 raise NotImplementedError(
                     f'n_neighbors > {self.lib.spx_nrst_max_neighbors()} is not supported')
             elif est_var_flag and 'OK' in interp_types:
-                raise NotImplementedError('EST_VARS_OK with nrst neighbours is not supported')
+                raise NotImplementedError(
+                    'EST_VARS_OK with nrst / pie neighbours is not supported')
         ev_flag = bool(est_var_flag) and ('OK' in interp_types)
         if ev_flag:
             assert 'EST_VARS_OK' in interp_labels, 'est_var_flag needs an EST_VARS_OK label'
@@ -495,7 +555,7 @@ class ChunkEngine:
         avail = ~np.isnan(data)
         grp_of_step, grp_mask = availability_groups(avail)       # grps.py:57-101
         n_grps = grp_mask.shape[0]
-        grp_n = grp_mask.sum(axis=1).astype(np.int64)
+        grp_n = np.count_nonzero(grp_mask, axis=1).astype(np.int64)
         n_avail = grp_n[grp_of_step]
         problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
 
@@ -572,7 +632,7 @@ class ChunkEngine:
                 uniq_vgs = list(dict.fromkeys(vgs))
                 vg_id = {v: k for k, v in enumerate(uniq_vgs)}
                 nug = np.array([check_full_nuggetness(v, min_vg_val) for v in uniq_vgs])
-                step_vg = np.array([vg_id[v] for v in vgs], dtype=np.int32)
+                step_vg = np.fromiter(map(vg_id.__getitem__, vgs), dtype=np.int32, count=len(vgs))
                 self._nrst(ctx, out, itype, np.where(multi)[0], int(n_nebs), step_vg=step_vg,
                            uniq_vgs=uniq_vgs, nug=nug, min_var_thr=float(min_var_thr),
                            drft_arrs=drft_arrs if itype == 'EDK' else None,
@@ -581,7 +641,7 @@ class ChunkEngine:
                 uniq_vgs = list(dict.fromkeys(vgs))
                 vg_id = {v: k for k, v in enumerate(uniq_vgs)}
                 nug = np.array([check_full_nuggetness(v, min_vg_val) for v in uniq_vgs])
-                step_vg = np.array([vg_id[v] for v in vgs], dtype=np.int32)
+                step_vg = np.fromiter(map(vg_id.__getitem__, vgs), dtype=np.int32, count=len(vgs))
                 bypass = (~steps_flags) | nug[step_vg]               # steps.py:325-331
                 mean_steps = np.where(multi & bypass)[0]
                 if mean_steps.size:
@@ -813,10 +873,16 @@ class ChunkEngine:
     def _topk(self, d_sx, d_sy, n_stn, d_mask, d_cx, d_cy, n_cells, k):
         nb = torch.empty((n_cells, k), dtype=_I32, device=self.device)
         hsh = torch.empty(n_cells, dtype=_I64, device=self.device)
-        _lib.check(self.lib.spx_nrst_topk_dev(
-            self._ptr(d_sx), self._ptr(d_sy), n_stn, self._ptr(d_mask), self._ptr(d_cx),
-            self._ptr(d_cy), n_cells, k, self._ptr(nb), self._ptr(hsh), self._stream()),
-            'nrst_topk')
+        if self._n_pies:
+            _lib.check(self.lib.spx_pie_select_dev(
+                self._ptr(d_sx), self._ptr(d_sy), n_stn, self._ptr(d_mask), self._ptr(d_cx),
+                self._ptr(d_cy), n_cells, k, self._n_pies, self._ptr(nb), self._ptr(hsh),
+                self._stream()), 'pie_select')
+        else:
+            _lib.check(self.lib.spx_nrst_topk_dev(
+                self._ptr(d_sx), self._ptr(d_sy), n_stn, self._ptr(d_mask), self._ptr(d_cx),
+                self._ptr(d_cy), n_cells, k, self._ptr(nb), self._ptr(hsh), self._stream()),
+                'nrst_topk')
         self._count('launches')
         return nb, hsh
 
@@ -1081,7 +1147,7 @@ class ChunkEngine:
                 pending += self._solve_direct(ctx, K, direct, want_resid=(kind != 1))
 
         K.flags_event = torch.cuda.Event()
-        K.flags_event.record(torch.cuda.current_stream(self.device))
+        K.flags_event.record(self._main_stream())
 
         if K.local is not None:
             coef2d = K.coef.view(-1, kpad)

@@ -78,7 +78,7 @@ class SpInterpSteps:
             stns_drft=None if stns_drft_df is None else np.ascontiguousarray(
                 stns_drft_df.loc[self._crds_df.index].values, dtype=np.float64),
             fld_beg_row=int(fld_beg_row), fld_end_row=int(fld_end_row),
-            neb_sel_mthd=self._neb_sel_mthd, n_nebs=self._n_nebs,
+            neb_sel_mthd=self._neb_sel_mthd, n_nebs=self._n_nebs, n_pies=self._n_pies,
             min_var_thr=self._min_var_thr, min_var_cut=self._min_var_cut,
             max_var_cut=self._max_var_cut, min_vg_val=self._min_vg_val,
             est_var_flag=bool(self._interp_flag_est_vars), intrp_dtype=self._intrp_dtype)

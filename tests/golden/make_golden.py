@@ -75,7 +75,8 @@ def run_reference(SpInterpSteps, case):
         _interp_x_crds_msh=case['cell_xs'].copy(),
         _interp_y_crds_msh=case['cell_ys'].copy(),
         _nc_file_path=None, _nc_nmrl_prcn=2,
-        _neb_sel_mthd=case['neb_sel_mthd'], _n_nebs=case['n_nebs'], _n_pies=None,
+        _neb_sel_mthd=case['neb_sel_mthd'], _n_nebs=case['n_nebs'],
+        _n_pies=case.get('n_pies'),
         _min_vg_val=case['min_vg_val'],
         _interp_flag_est_vars=case['est_var_flag'], _intrp_dtype=np.float64)
 
@@ -111,7 +112,7 @@ def make_inputs(seed, n_stn, T, ny, nx, cell=5000.0, miss=0.0):
 def base_case(**kw):
     case = dict(
         vgs=None, cntn_idxs=None, drft_arrs=None, stns_drft=None,
-        fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None,
+        fld_beg_row=0, fld_end_row=None, neb_sel_mthd='all', n_nebs=None, n_pies=None,
         min_var_thr=-np.inf, min_var_cut=None, max_var_cut=None, min_vg_val=0.0,
         est_var_flag=False)
     case.update(kw)
@@ -183,6 +184,16 @@ def cases():
     out['e_nrst'] = base_case(
         stn_xs=sx, stn_ys=sy, data=data, cell_xs=cx, cell_ys=cy, grid_shape=(10, 10),
         vgs=[VG] * 4, neb_sel_mthd='nrst', n_nebs=8,
+        interp_args=[('OK', None, 'OK'), ('IDW', None, 'IDW_000', 2.0), ('NNB', None, 'NNB')])
+
+    # H: 'pie' neighbour selection (sector round-robin).  The reference's caller passes
+    # uint32 work arrays to a Cython signature that wants `unsigned long` (grps.py:173,176
+    # vs pyx:822-823), which only matches on LLP64 (Windows); main() installs a shim that
+    # casts those two arrays at the call boundary, the reference code itself is untouched.
+    rng, sx, sy, data, cx, cy = make_inputs(8, 36, 4, 9, 11, miss=0.1)
+    out['h_pie'] = base_case(
+        stn_xs=sx, stn_ys=sy, data=data, cell_xs=cx, cell_ys=cy, grid_shape=(9, 11),
+        vgs=[VG] * 4, neb_sel_mthd='pie', n_nebs=10, n_pies=4,
         interp_args=[('OK', None, 'OK'), ('IDW', None, 'IDW_000', 2.0), ('NNB', None, 'NNB')])
 
     # F: every variogram family, min_vg_val > 0
@@ -275,6 +286,28 @@ def kats(im, misc):
     k.update(oik_ik=c.ik, oik_est_vars=c.est_vars)
     c = im.SimpleIndicatorKriging(xi, yi, zi, xk, yk, 4.0, model); c.ikrige()
     k.update(sik_ik=c.ik, sik_est_covars=c.est_covars)
+    # pie helper (pyx:811-890; DT_UL = unsigned long, 64-bit here) and get_nd_dists (:893)
+    n_ref = 23
+    rx, ry = rng.uniform(0, 1e5, n_ref), rng.uniform(0, 1e5, n_ref)
+    rx[5], ry[6] = 4.0e4, 5.5e4          # stations due north/south and east/west of a target
+    pts = np.array([[4.0e4, 5.5e4], [1.2e4, 9.0e4], [7.7e4, 3.1e4], [-5.0e3, 2.0e4], [5.0e4, 5.0e4]])
+    k.update(pie_rx=rx, pie_ry=ry, pie_pts=pts)
+    for n_pies in (3, 4, 8):
+        sel_all, pidx_all, cts_all, d_all = [], [], [], []
+        for px, py in pts:
+            dists = np.zeros(n_ref)
+            tem = np.zeros(n_ref)
+            sel = np.zeros(n_ref, dtype=np.int64)
+            pidx = np.zeros(n_ref, dtype=np.uint64)
+            cts = np.zeros(n_pies, dtype=np.uint64)
+            im.sel_equidist_refs(px, py, rx, ry, n_pies, -1.0, -1, dists, tem, sel, pidx, cts)
+            sel_all.append(sel); pidx_all.append(pidx); cts_all.append(cts); d_all.append(dists)
+        k[f'pie{n_pies}_sel'] = np.array(sel_all)
+        k[f'pie{n_pies}_pidx'] = np.array(pidx_all).astype(np.int64)
+        k[f'pie{n_pies}_cts'] = np.array(cts_all).astype(np.int64)
+        k[f'pie{n_pies}_dists'] = np.array(d_all)
+    nd = rng.normal(size=(9, 3))
+    k.update(nd_pts=nd, nd_out=np.asarray(im.get_nd_dists(nd)))
     # the survey's known answer
     c = im.OrdinaryKriging(np.array([0., 10., 0.]), np.array([0., 0., 10.]), np.array([1., 2., 4.]),
                            np.array([5., 2.]), np.array([5., 1.]), '0.1 Nug(0.0) + 0.9 Sph(20)')
@@ -301,12 +334,31 @@ def save_case(name, case, flds):
     np.savez_compressed(HERE / f'{name}.npz', **d)
 
 
+def install_pie_shim(im):
+    """grps.py calls sel_equidist_refs with uint32 work arrays; the compiled signature
+    takes `unsigned long` buffers (64-bit on LP64).  Cast the two arrays going in and copy
+    them back, nothing else changes."""
+    import spinterps.interp.grps as grps
+    real = im.sel_equidist_refs
+
+    def shim(dst_x, dst_y, ref_xs, ref_ys, n_pies, thr, flag, dists, tem, sel, pidx, cts):
+        p64, c64 = pidx.astype(np.uint64), cts.astype(np.uint64)
+        real(dst_x, dst_y, ref_xs, ref_ys, n_pies, thr, flag, dists, tem, sel, p64, c64)
+        pidx[:] = p64
+        cts[:] = c64
+    grps.sel_equidist_refs = shim
+
+
 def main():
     im, SpInterpSteps, misc = import_reference()
+    install_pie_shim(im)
     np.savez_compressed(HERE / 'kats.npz', **kats(im, misc))
     if '--kats-only' in sys.argv:
         return
+    only = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--only=')]
     for name, case in cases().items():
+        if only and name not in only:
+            continue
         flds = run_reference(SpInterpSteps, case)
         save_case(name, case, flds)
         msg = ', '.join(f'{lab}[{np.nanmin(a):.6g},{np.nanmax(a):.6g}] nan={np.isnan(a).sum()}'

@@ -6,7 +6,7 @@ import numpy as np
 GOLDEN = Path(__file__).resolve().parent / 'golden'
 
 CASES = ['a_ok_idw_nnb', 'b_ok_groups_flags', 'c_edk_drift', 'd_sk_ok_mask_rows',
-         'e_nrst', 'f_vg_families', 'g_idw_only']
+         'e_nrst', 'f_vg_families', 'g_idw_only', 'h_pie']
 
 
 def _opt(z, key, conv=None):
@@ -39,6 +39,8 @@ def load_case(name):
         min_var_thr=float(z['min_var_thr']),
         min_var_cut=_opt(z, 'min_var_cut', float), max_var_cut=_opt(z, 'max_var_cut', float),
         min_vg_val=float(z['min_vg_val']), est_var_flag=bool(z['est_var_flag']))
+    if 'n_pies' in z.files:
+        case['n_pies'] = int(z['n_pies'])
     outs = {k[5:]: z[k] for k in z.files if k.startswith('out__')}
     return case, outs
 

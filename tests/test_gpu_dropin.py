@@ -80,3 +80,33 @@ def test_gather_theo_idw(cy, kats):
     exp = np.full(5, np.nan)
     orc.fill_dists_one_pt(3.0, 4.0, kats['d_x2'], kats['d_y2'], exp)
     assert np.array_equal(dist, exp)
+
+
+def test_pie_helper_and_nd_dists(cy, kats):
+    """sel_equidist_refs (sector index, members per sector, rank inside the sector) and
+    get_nd_dists against the known answers of the compiled reference: bit-exact."""
+    rx, ry = kats['pie_rx'], kats['pie_ry']
+    n = rx.size
+    for n_pies in (3, 4, 8):
+        for pi, (px, py) in enumerate(kats['pie_pts']):
+            dists, tem = np.zeros(n), np.zeros(n)
+            sel = np.zeros(n, dtype=np.int64)
+            pidx = np.zeros(n, dtype=np.uint64)
+            cts = np.zeros(n_pies, dtype=np.uint64)
+            cy.sel_equidist_refs(px, py, rx, ry, n_pies, -1.0, -1, dists, tem, sel, pidx, cts)
+            assert np.array_equal(sel, kats[f'pie{n_pies}_sel'][pi])
+            assert np.array_equal(pidx.astype(np.int64), kats[f'pie{n_pies}_pidx'][pi])
+            assert np.array_equal(cts.astype(np.int64), kats[f'pie{n_pies}_cts'][pi])
+            assert np.array_equal(dists, kats[f'pie{n_pies}_dists'][pi])
+    # a reference point within the threshold: only the nearest one is selected (rank 0)
+    dists, tem = np.zeros(n), np.zeros(n)
+    sel = np.zeros(n, dtype=np.int64)
+    pidx, cts = np.zeros(n, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+    cy.sel_equidist_refs(rx[7] + 1.0, ry[7], rx, ry, 4, 50.0, -1, dists, tem, sel, pidx, cts)
+    exp = np.full(n, -1)
+    exp[7] = 0
+    assert np.array_equal(sel, exp)
+    assert np.array_equal(cy.get_nd_dists(kats['nd_pts']), kats['nd_out'])
+    with pytest.raises(ValueError):
+        cy.sel_equidist_refs(0.0, 0.0, rx, ry, 4, -1.0, -1, dists, tem, sel,
+                             np.zeros(n, dtype=np.uint32), cts)

@@ -50,7 +50,7 @@ def _check(got, exp, name):
 
 
 @pytest.mark.parametrize('name', ['a_ok_idw_nnb', 'c_edk_drift', 'd_sk_ok_mask_rows', 'e_nrst',
-                                  'g_idw_only'])
+                                  'g_idw_only', 'h_pie'])
 def test_golden_cases(eng, name):
     case, outs = load_case(name)
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **case)
@@ -183,6 +183,28 @@ def test_nrst_vs_oracle(eng):
     exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
     got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
     _check(got, exp, 'nrst')
+    assert eng.stats.get('nrst_systems', 0) > 10
+
+
+def test_pie_vs_oracle(eng):
+    """'pie' neighbour selection (sector round-robin, interp/grps.py:168-247): same
+    estimators as 'nrst' behind a different per-cell station choice; stations placed
+    exactly north / east / west of cell centres exercise the sector edge rules."""
+    p = make_problem(33, 60, 6, 19, 23, cell=4000.0, miss=0.12)
+    cx, cy = p['cell_xs'], p['cell_ys']
+    p['stn_xs'][0], p['stn_ys'][0] = cx[40], cy[40] + 7000.0     # due north of cell 40
+    p['stn_xs'][1], p['stn_ys'][1] = cx[41] - 9500.0, cy[41]     # due west of cell 41
+    p['stn_xs'][2], p['stn_ys'][2] = cx[42] + 5000.0, cy[42]     # due east of cell 42
+    vgs = [VG_C1] * 6
+    vgs[3] = '0.2 Nug(0.0) + 0.8 Exp(30000)'
+    args = [('OK', None, 'OK'), ('SK', None, 'SK'), ('IDW', None, 'IDW_000', 2.0),
+            ('NNB', None, 'NNB')]
+    for n_nebs, n_pies in ((9, 4), (12, 5), (8, 8)):   # (no two stations equidistant from a cell)
+        kw = dict(interp_args=args, vgs=vgs, neb_sel_mthd='pie', n_nebs=n_nebs, n_pies=n_pies,
+                  min_var_cut=0.0, **p)
+        exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+        got, _ = eng.interp_chunk(intrp_dtype=np.float64, **kw)
+        _check(got, exp, 'pie %d/%d' % (n_nebs, n_pies))
     assert eng.stats.get('nrst_systems', 0) > 10
 
 

@@ -64,6 +64,20 @@ def test_free_function_kats(kats):
     for key in kats.files:
         if key.startswith('nugget__'):
             assert orc.check_full_nuggetness(key[8:], 1e-4) == bool(kats[key])
+    # pie helper and pairwise distances: index outputs bit-exact
+    rx, ry = kats['pie_rx'], kats['pie_ry']
+    for n_pies in (3, 4, 8):
+        for pi, (px, py) in enumerate(kats['pie_pts']):
+            n = rx.size
+            dists, tem = np.zeros(n), np.zeros(n)
+            sel, pidx = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+            cts = np.zeros(n_pies, dtype=np.int64)
+            orc.sel_equidist_refs(px, py, rx, ry, n_pies, -1.0, -1, dists, tem, sel, pidx, cts)
+            assert np.array_equal(sel, kats[f'pie{n_pies}_sel'][pi])
+            assert np.array_equal(pidx, kats[f'pie{n_pies}_pidx'][pi])
+            assert np.array_equal(cts, kats[f'pie{n_pies}_cts'][pi])
+            assert np.array_equal(dists, kats[f'pie{n_pies}_dists'][pi])
+    assert np.array_equal(orc.get_nd_dists(kats['nd_pts']), kats['nd_out'])
 
 
 @pytest.mark.parametrize('faithful', [True, False])
