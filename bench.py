@@ -122,11 +122,44 @@ def run_reference(args):
 # ----------------------------------------------------------------- GPU arm
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region.  Sampled in-process through
+    NVML (pynvml): forking nvidia-smi from a process that holds a CUDA context and ~10 GB
+    of pinned memory stalls the main thread for milliseconds -- longer than a bench step.
+    nvidia-smi is only the fallback when pynvml is missing."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    idx = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        nv = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)]
+        return [str(sm), str(mx)] + ['Active' if (r & b) else 'Not Active' for b in bits]
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
@@ -134,15 +167,19 @@ class ClockSampler(threading.Thread):
              'clocks_event_reasons.sw_power_cap')
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(
-                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
-                parts = [x.strip() for x in out.stdout.strip().split(',')]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(
+                        ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                         '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                        timeout=5)
+                    parts = [x.strip() for x in out.stdout.strip().split(',')]
+                    if len(parts) >= 6:
+                        self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.samples:
@@ -153,7 +190,8 @@ class ClockSampler(threading.Thread):
                    if any(s[2 + k].lower().startswith('active') for s in self.samples)]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None,
                 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples),
+                'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def dgemm_peak_tflops(torch, n=6144, reps=4):
@@ -430,7 +468,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     args = ap.parse_args()

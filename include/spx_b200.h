@@ -256,11 +256,78 @@ typedef struct spx_downdate {
     int32_t coef_row_major;      /* 0: packed fragment layout; 1: coef[row * kpad + col] */
     const int32_t* sys_order;    /* optional [n_sys]: block b works on system sys_order[b]
                                     (largest r first shortens the tail); NULL = identity */
+    /* Optional fused outputs for the local estimator (need max_r <=
+     * spx_krige_downdate_reg_max_r(), n_border >= 1 and rhs_row = row index): */
+    double* coef_t;              /* transposed copy coef_t[col * coef_t_ld + row]; entries of
+                                    missing stations are written as zeros */
+    int64_t coef_t_ld;
+    double* base;                /* base[row] = base_f * sum_{stations} c + c[n_stn] */
+    double base_f;
 } spx_downdate;
 
 int spx_krige_downdate_dev(const spx_downdate* d, void* stream);
 /* Largest r that fits the device's shared memory. */
 int spx_krige_downdate_max_r(void);
+/* Largest r of the register-resident kernel (the one that writes coef_t / base). */
+int spx_krige_downdate_reg_max_r(void);
+
+/* ---- native host-side planning of a time chunk --------------------------------
+ * Pure index work on HOST pointers (no GPU involved): the NumPy version of the same
+ * logic cost more per chunk than the kernels it feeds. */
+
+/* Availability groups of a [n_steps, n_stn] data block (row pitch ld, NaN = missing):
+ * steps with identical sets of non-NaN stations share a group, groups numbered in
+ * first-occurrence order (interp/grps.py:57-101).  Caller-allocated outputs with room
+ * for n_steps groups: grp_first (first step of each group), grp_n (stations per
+ * group), grp_mask [*, n_stn] (1 = available; optional) and / or grp_bits
+ * [*, ceil(n_stn / 64)] (the same masks, bit j % 64 of word j / 64; optional); per step
+ * n_avail and step_flag (any
+ * available value >= min_var_thr, interp/steps.py:760-765).  data_copy (optional):
+ * dense [n_steps, n_stn] copy of the data written in the same pass (e.g. a pinned
+ * staging buffer for the upload). */
+int spx_avail_groups_host(const double* data, int64_t n_steps, int32_t n_stn, int64_t ld,
+                          double min_var_thr, int32_t* grp_of_step, int32_t* grp_first,
+                          int32_t* grp_n, uint8_t* grp_mask, int32_t* n_avail,
+                          uint8_t* step_flag, double* data_copy, uint64_t* grp_bits,
+                          int32_t* n_grps_out);
+
+/* Descriptor arrays of one spx_downdate call, packed into ONE buffer (upload it with a
+ * single copy; device pointer = device base + off_*).  Systems = the groups that occur
+ * among `steps` (ascending group id); right-hand sides of a system = its steps in the
+ * order given (coefficient row rows[i]) followed by its ones-vector; rhs_urow indexes
+ * the rows of Bt / Ut: data rows first (bt_step = their step), then one mask row per
+ * system.  sys_order sorts by r descending; pos_ones[s] = rhs index of the ones-vector
+ * of system s (host use: resid[pos_ones] is the sum(lambda) screening value). */
+typedef struct spx_dd_plan {
+    int32_t n_sys, n_data, n_rhs, max_r;
+    int64_t total_r, total_n;
+    int64_t off_sys_r, off_sys_miss_off, off_miss_list, off_sys_n, off_sys_stn_off,
+        off_stn_list, off_sys_rhs_off, off_sys_rhs_cnt, off_rhs_urow, off_rhs_row,
+        off_rhs_kind, off_sys_order, off_bt_step, off_sys_grp, off_pos_ones;
+    int64_t n_upload_bytes;      /* host-written prefix (everything but the two station
+                                    lists, which spx_avail_lists_dev fills on the device) */
+    int64_t n_bytes;             /* bytes of the device buffer in use */
+} spx_dd_plan;
+
+/* Upper bounds for n_sel selected steps: of the whole (device) buffer, and of the
+ * host-written prefix (the size `buf` of spx_downdate_plan_host must have). */
+int64_t spx_downdate_plan_bytes(int64_t n_sel, int32_t n_stn);
+int64_t spx_downdate_plan_host_bytes(int64_t n_sel);
+int spx_downdate_plan_host(const int32_t* grp_of_step, const int32_t* grp_n, int32_t n_grps,
+                           int32_t n_stn, const int32_t* steps, const int64_t* rows,
+                           int64_t n_sel, void* buf, int64_t buf_bytes, spx_dd_plan* plan);
+/* stn_list / miss_list of the plan: ascending available / missing station indices of
+ * step src_step[s] (= the plan's bt_step + n_data) for every system s. */
+int spx_avail_lists_dev(const double* data, int32_t n_stn, int64_t data_ld,
+                        const int32_t* src_step, int32_t n_sys, const int64_t* stn_off,
+                        int32_t* stn_list, const int64_t* miss_off, int32_t* miss_list,
+                        void* stream);
+
+/* Bt [n_rows, n_stn + n_border] of the downdate from the resident data block: row i <
+ * n_data = data[src_step[i]] with NaN -> 0, row i >= n_data = availability mask (1.0 /
+ * 0.0) of step src_step[i]; border columns zero.  (Ut = Bt . ginv is a plain GEMM.) */
+int spx_build_bt_dev(const double* data, int32_t n_stn, int64_t data_ld, const int32_t* src_step,
+                     int64_t n_rows, int64_t n_data, int32_t n_border, double* bt, void* stream);
 
 /* The fused estimate contraction
  *     Z[row, cell] = sum_k coef[row, k] * B[k, cell]
@@ -516,8 +583,19 @@ typedef struct spx_local {
                                   beyond n_rows zero); with f32 output, no drift, no cell_pos
                                   and rows_all_valid it selects the streamlined kernel */
     int64_t coef_t_ld;         /* multiple of 4, >= n_rows */
+    /* Optional tile tables (spx_local_tiles_dev): per tile of SPX_LOCAL_TILE consecutive
+     * cells the distinct near stations of its cells.  The streamlined kernel then stages
+     * the tile's coefficient slices in shared memory and gathers from there. */
+    int32_t* tile_cnt;         /* [n_tiles] stations of the tile, -1 = more than SPX_LOCAL_TILE_CAP */
+    int32_t* tile_stn;         /* [n_tiles, SPX_LOCAL_TILE_CAP] ascending station ids */
+    uint8_t* slot;             /* [cap, n_cells] position of idx[j, c] in its tile's list */
 } spx_local;
+#define SPX_LOCAL_TILE 256
+#define SPX_LOCAL_TILE_CAP 32
 int spx_local_build_dev(const spx_local* l, void* stream);
+/* Fill tile_cnt / tile_stn / slot from cnt / idx (after spx_local_build_dev; n_stn <=
+ * 65536). */
+int spx_local_tiles_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
 
 /* Host -> device copy of n_bytes on `stream` (cudaMemcpyAsync; from pageable memory the call

@@ -72,7 +72,23 @@ class spx_downdate(C.Structure):
                 ('rhs_urow', C.c_void_p), ('rhs_row', C.c_void_p), ('rhs_kind', C.c_void_p),
                 ('ut', C.c_void_p), ('kpad', C.c_int32), ('coef', C.c_void_p),
                 ('resid', C.c_void_p), ('info', C.c_void_p), ('coef_row_major', C.c_int32),
-                ('sys_order', C.c_void_p)]
+                ('sys_order', C.c_void_p),
+                ('coef_t', C.c_void_p), ('coef_t_ld', C.c_int64), ('base', C.c_void_p),
+                ('base_f', C.c_double)]
+
+
+class spx_dd_plan(C.Structure):
+    _fields_ = [('n_sys', C.c_int32), ('n_data', C.c_int32), ('n_rhs', C.c_int32),
+                ('max_r', C.c_int32), ('total_r', C.c_int64), ('total_n', C.c_int64),
+                ('off_sys_r', C.c_int64), ('off_sys_miss_off', C.c_int64),
+                ('off_miss_list', C.c_int64), ('off_sys_n', C.c_int64),
+                ('off_sys_stn_off', C.c_int64), ('off_stn_list', C.c_int64),
+                ('off_sys_rhs_off', C.c_int64), ('off_sys_rhs_cnt', C.c_int64),
+                ('off_rhs_urow', C.c_int64), ('off_rhs_row', C.c_int64),
+                ('off_rhs_kind', C.c_int64), ('off_sys_order', C.c_int64),
+                ('off_bt_step', C.c_int64), ('off_sys_grp', C.c_int64),
+                ('off_pos_ones', C.c_int64), ('n_upload_bytes', C.c_int64),
+                ('n_bytes', C.c_int64)]
 
 
 class spx_multivg(C.Structure):
@@ -102,7 +118,12 @@ class spx_local(C.Structure):
                 ('out_ld', C.c_int64), ('out_f64', C.c_int32), ('cell_pos', C.c_void_p),
                 ('has_lo', C.c_int32), ('has_hi', C.c_int32),
                 ('lo', C.c_double), ('hi', C.c_double), ('rows_all_valid', C.c_int32),
-                ('coef_t', C.c_void_p), ('coef_t_ld', C.c_int64)]
+                ('coef_t', C.c_void_p), ('coef_t_ld', C.c_int64),
+                ('tile_cnt', C.c_void_p), ('tile_stn', C.c_void_p), ('slot', C.c_void_p)]
+
+
+SPX_LOCAL_TILE = 256
+SPX_LOCAL_TILE_CAP = 32
 
 
 class spx_nrst(C.Structure):
@@ -167,6 +188,19 @@ _SIGS = {
     'spx_krige_solve_dev': (C.c_int, [C.POINTER(spx_systems), C.POINTER(spx_rhs), C.c_void_p]),
     'spx_krige_downdate_dev': (C.c_int, [C.POINTER(spx_downdate), C.c_void_p]),
     'spx_krige_downdate_max_r': (C.c_int, []),
+    'spx_krige_downdate_reg_max_r': (C.c_int, []),
+    'spx_avail_groups_host': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_double,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i32p]),
+    'spx_downdate_plan_bytes': (C.c_int64, [C.c_int64, C.c_int32]),
+    'spx_downdate_plan_host_bytes': (C.c_int64, [C.c_int64]),
+    'spx_downdate_plan_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.POINTER(spx_dd_plan)]),
+    'spx_avail_lists_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'spx_build_bt_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                                   C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     'spx_estimate_gemm_dev': (C.c_int, [C.POINTER(spx_gemm), C.c_void_p]),
     'spx_estimate_gemm_config': (C.c_int, [C.POINTER(spx_gemm), c_i32p, c_i32p, c_i32p, c_i32p]),
     'spx_pack_rows_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
@@ -189,6 +223,7 @@ _SIGS = {
     'spx_estimate_multivg_dev': (C.c_int, [C.POINTER(spx_multivg), C.c_void_p]),
     'spx_local_build_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_estimate_local_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
+    'spx_local_tiles_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
@@ -244,6 +279,42 @@ def check(rc, what=''):
     if rc != 0:
         msg = load().spx_last_error().decode(errors='replace')
         raise SpxError(f'{what or "spx call"} failed (code {rc}): {msg}')
+
+
+def unpack_group_bits(bits, n_stn):
+    """[n_grps, W] uint64 availability words -> bool [n_grps, n_stn]."""
+    b8 = np.ascontiguousarray(bits).view(np.uint8)
+    return np.unpackbits(b8, axis=1, count=n_stn, bitorder='little').view(np.bool_)
+
+
+def avail_groups(data, min_var_thr=-np.inf, data_copy=None, want_mask=True):
+    """Availability groups of a [T, N] float64 block on the host (spx_avail_groups_host;
+    interp/grps.py:57-101).  Returns grp_of_step [T] int32, grp_mask [n_grps, N] bool
+    (want_mask=False: the packed words [n_grps, ceil(N / 64)] uint64 instead, see
+    unpack_group_bits), grp_n [n_grps] int64, grp_first [n_grps] int32, n_avail [T]
+    int64, step_flag [T] bool.  data_copy: optional address of a writable float64 buffer
+    of T*N elements that receives a dense copy of the data in the same pass."""
+    data = np.asarray(data)
+    assert data.dtype == np.float64 and data.ndim == 2
+    T, N = data.shape
+    assert T == 0 or (data.strides[1] == 8 and data.strides[0] % 8 == 0 and data.strides[0] >= 8 * N)
+    W = (N + 63) // 64
+    ints = np.empty((4, max(T, 1)), dtype=np.int32)     # grp_of_step, grp_first, grp_n, n_avail
+    step_flag = np.empty(max(T, 1), dtype=np.uint8)
+    grp_mask = np.empty((T, N), dtype=np.uint8) if want_mask else None
+    grp_bits = None if want_mask else np.empty((max(T, 1), W), dtype=np.uint64)
+    n_grps = C.c_int32(0)
+    if T:
+        check(load().spx_avail_groups_host(
+            data.ctypes.data, T, N, data.strides[0] // 8, float(min_var_thr), ints[0].ctypes.data,
+            ints[1].ctypes.data, ints[2].ctypes.data,
+            grp_mask.ctypes.data if want_mask else None, ints[3].ctypes.data,
+            step_flag.ctypes.data, None if data_copy is None else int(data_copy),
+            None if want_mask else grp_bits.ctypes.data, C.byref(n_grps)), 'avail_groups_host')
+    g = n_grps.value
+    masks = grp_mask[:g].view(np.bool_) if want_mask else grp_bits[:g]
+    return (ints[0, :T], masks, ints[2, :g].astype(np.int64), ints[1, :g],
+            ints[3, :T].astype(np.int64), step_flag[:T].view(np.bool_))
 
 
 def require_gpu():

@@ -916,7 +916,73 @@ struct LocalEstArgs {
     const int32_t* cell_pos;
     int has_lo, has_hi;
     double lo, hi;
+    const int32_t* tile_cnt;    // optional tile tables (see spx_local)
+    const int32_t* tile_stn;
+    const uint8_t* slot;
 };
+
+// Distinct near stations of every tile of SPX_LOCAL_TILE cells: a station bitmap in shared
+// memory (atomicOr), word prefix sums -> ascending list and the slot of every (cell, j).
+constexpr int LOC_TILE_WORDS = 2048;        // up to 65536 stations
+
+__global__ void __launch_bounds__(SPX_LOCAL_TILE) k_local_tiles(
+    const int32_t* __restrict__ cnt, const int32_t* __restrict__ idx, int64_t n_cells, int cap,
+    int n_stn, int32_t* __restrict__ tile_cnt, int32_t* __restrict__ tile_stn,
+    uint8_t* __restrict__ slot) {
+    __shared__ uint32_t bm[LOC_TILE_WORDS];
+    __shared__ int pre[LOC_TILE_WORDS];
+    __shared__ int part[SPX_LOCAL_TILE];
+    const int tid = threadIdx.x;
+    const int n_words = (n_stn + 31) >> 5;
+    for (int w = tid; w < n_words; w += SPX_LOCAL_TILE) bm[w] = 0u;
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * SPX_LOCAL_TILE + tid;
+    const int n = (c < n_cells) ? min(cnt[c], cap) : 0;
+    for (int j = 0; j < n; ++j) {
+        const int id = idx[(int64_t)j * n_cells + c];
+        atomicOr(&bm[id >> 5], 1u << (id & 31));
+    }
+    __syncthreads();
+    // exclusive prefix of the word popcounts: each thread owns a contiguous run of words
+    const int per = (n_words + SPX_LOCAL_TILE - 1) / SPX_LOCAL_TILE;
+    const int w0 = tid * per, w1 = min(n_words, w0 + per);
+    int sum = 0;
+    for (int w = w0; w < w1; ++w) sum += __popc(bm[w]);
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < SPX_LOCAL_TILE; o <<= 1) {
+        const int v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = part[tid] - sum;
+    for (int w = w0; w < w1; ++w) {
+        pre[w] = run;
+        run += __popc(bm[w]);
+    }
+    const int total = part[SPX_LOCAL_TILE - 1];
+    __syncthreads();
+    if (total > SPX_LOCAL_TILE_CAP) {
+        if (tid == 0) tile_cnt[blockIdx.x] = -1;
+        return;
+    }
+    if (tid == 0) tile_cnt[blockIdx.x] = total;
+    for (int w = tid; w < n_words; w += SPX_LOCAL_TILE) {
+        uint32_t b = bm[w];
+        int k = pre[w];
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            tile_stn[(int64_t)blockIdx.x * SPX_LOCAL_TILE_CAP + k++] = (w << 5) + bit;
+            b &= b - 1;
+        }
+    }
+    for (int j = 0; j < n; ++j) {
+        const int id = idx[(int64_t)j * n_cells + c];
+        slot[(int64_t)j * n_cells + c] =
+            (uint8_t)(pre[id >> 5] + __popc(bm[id >> 5] & ((1u << (id & 31)) - 1u)));
+    }
+}
 
 // One thread per cell, LOC_ROWS rows per block.  The cell's near stations live in
 // registers; the loop over them is bounded by the warp-wide maximum so that the
@@ -1000,7 +1066,18 @@ __global__ void __launch_bounds__(256) k_estimate_local(LocalEstArgs a) {
 //  * the number of gathers is a warp-uniform compile-time case (NG = 0, 1, 2, "many");
 //  * the clamp is a compile-time option applied after the conversion (rounding is
 //    monotone: float(clamp(z)) == clamp(float(z)) with float(lo), float(hi)).
-template <int NG, bool CLAMP, int CPT>
+constexpr int LOC_SLD = 130;    // row pitch of a staged coefficient slice (128 rows + 2: slices
+                                // of different stations start 4 banks apart)
+
+template <bool SM>
+__device__ __forceinline__ double2 ld_coef2(const double* p) {
+    if (SM) return *reinterpret_cast<const double2*>(p);
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// SM: the gathers read the tile's staged slices in shared memory (ct = its base, slice
+// pitch LOC_SLD, station -> a.slot) instead of the global transposed copy.
+template <int NG, bool CLAMP, int CPT, bool SM>
 __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double* sbase,
                                              const int64_t* soff, int nr, int64_t c0,
                                              const int* n, const double* const* p0,
@@ -1016,14 +1093,14 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
         for (int q = 0; q < CPT; ++q) {
             double z0 = b01.x, z1 = b01.y, z2 = b23.x, z3 = b23.y;
             if (NG >= 1 && 0 < n[q]) {
-                const double2 g01 = __ldg(reinterpret_cast<const double2*>(p0[q] + r));
-                const double2 g23 = __ldg(reinterpret_cast<const double2*>(p0[q] + r + 2));
+                const double2 g01 = ld_coef2<SM>(p0[q] + r);
+                const double2 g23 = ld_coef2<SM>(p0[q] + r + 2);
                 z0 = fma(g01.x, v0[q], z0); z1 = fma(g01.y, v0[q], z1);
                 z2 = fma(g23.x, v0[q], z2); z3 = fma(g23.y, v0[q], z3);
             }
             if (NG >= 2 && 1 < n[q]) {
-                const double2 g01 = __ldg(reinterpret_cast<const double2*>(p1[q] + r));
-                const double2 g23 = __ldg(reinterpret_cast<const double2*>(p1[q] + r + 2));
+                const double2 g01 = ld_coef2<SM>(p1[q] + r);
+                const double2 g23 = ld_coef2<SM>(p1[q] + r + 2);
                 z0 = fma(g01.x, v1[q], z0); z1 = fma(g01.y, v1[q], z1);
                 z2 = fma(g23.x, v1[q], z2); z3 = fma(g23.y, v1[q], z3);
             }
@@ -1031,10 +1108,11 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
                 const int64_t c = c0 + q;
                 for (int j = 2; j < n[q]; ++j) {
                     const double* pj =
-                        ct + (int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r;
+                        SM ? ct + (int)a.slot[(int64_t)j * a.n_cells + c] * LOC_SLD + r
+                           : ct + (int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r;
                     const double vj = a.val[(int64_t)j * a.n_cells + c];
-                    const double2 g01 = __ldg(reinterpret_cast<const double2*>(pj));
-                    const double2 g23 = __ldg(reinterpret_cast<const double2*>(pj + 2));
+                    const double2 g01 = ld_coef2<SM>(pj);
+                    const double2 g23 = ld_coef2<SM>(pj + 2);
                     z0 = fma(g01.x, vj, z0); z1 = fma(g01.y, vj, z1);
                     z2 = fma(g23.x, vj, z2); z3 = fma(g23.y, vj, z3);
                 }
@@ -1074,7 +1152,8 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
             if (NG >= 2 && 1 < n[q]) z = fma(p1[q][r], v1[q], z);
             if (NG >= 3)
                 for (int j = 2; j < n[q]; ++j)
-                    z = fma(ct[(int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r],
+                    z = fma(SM ? ct[(int)a.slot[(int64_t)j * a.n_cells + c] * LOC_SLD + r]
+                               : ct[(int64_t)a.idx[(int64_t)j * a.n_cells + c] * a.coef_t_ld + r],
                             a.val[(int64_t)j * a.n_cells + c], z);
             float fv = (float)z;
             if (CLAMP) {
@@ -1087,21 +1166,44 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
 }
 
 // CPT cells per thread (2: one 8-byte store per row and thread; needs an even out_ld).
-template <bool CLAMP, int ROWS, int CPT>
+// TILE (CPT == 1, ROWS == 128, tile tables present): the block first copies the
+// coefficient slices coef_t[stn, r_beg : r_beg + 128] of its tile's <= SPX_LOCAL_TILE_CAP
+// distinct near stations into shared memory (coalesced 16-byte loads, ~1 KB per station
+// against 128 KB of output per block) and every gather of the row loop becomes a
+// shared-memory load: no L1 misses, a fraction of the latency of the global gathers
+// the untiled variant waits on.
+template <bool CLAMP, int ROWS, int CPT, bool TILE>
 __global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
     __shared__ __align__(16) double sbase[ROWS];
     __shared__ __align__(16) int64_t soff[ROWS];
+    __shared__ __align__(16) double sct[TILE ? SPX_LOCAL_TILE_CAP * LOC_SLD : 2];
+    static_assert(!TILE || (CPT == 1 && ROWS == 128), "tile variant: 256 cells x 128 rows");
     const int64_t r_beg = (int64_t)blockIdx.y * ROWS;
     const int nr = (int)min((int64_t)ROWS, a.n_rows - r_beg);
     for (int i = threadIdx.x; i < nr; i += blockDim.x) {
         sbase[i] = a.base[r_beg + i];
         soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
     }
+    const double* ct = a.coef_t + r_beg;
+    bool staged = false;
+    if (TILE) {
+        const int U = a.tile_cnt[blockIdx.x];
+        staged = U >= 0;                         // block-uniform
+        if (staged) {
+            const int32_t* __restrict__ tl = a.tile_stn + (int64_t)blockIdx.x * SPX_LOCAL_TILE_CAP;
+            const int r_lim = (int)min((int64_t)ROWS, a.coef_t_ld - r_beg);   // even
+            for (int i = threadIdx.x; i < U * (ROWS / 2); i += blockDim.x) {
+                const int s = i / (ROWS / 2), r2 = 2 * (i - s * (ROWS / 2));
+                if (r2 < r_lim)
+                    *reinterpret_cast<double2*>(sct + s * LOC_SLD + r2) = __ldg(
+                        reinterpret_cast<const double2*>(ct + (int64_t)tl[s] * a.coef_t_ld + r2));
+            }
+        }
+    }
     __syncthreads();
     const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
     if (c0 >= a.n_cells) return;                 // no further block-wide barrier below
     const bool pair = (CPT == 2) && (c0 + 1 < a.n_cells);
-    const double* ct = a.coef_t + r_beg;
     int n[CPT];
     const double* p0[CPT];
     const double* p1[CPT];
@@ -1111,26 +1213,39 @@ __global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
     for (int q = 0; q < CPT; ++q) {
         const int64_t c = min(c0 + q, a.n_cells - 1);
         n[q] = (q == 0 || pair) ? min(a.cnt[c], a.cap) : 0;
-        const int i0 = (0 < n[q]) ? a.idx[c] : 0;
-        const int i1 = (1 < n[q]) ? a.idx[a.n_cells + c] : 0;
         v0[q] = (0 < n[q]) ? a.val[c] : 0.0;
         v1[q] = (1 < n[q]) ? a.val[a.n_cells + c] : 0.0;
-        p0[q] = ct + (int64_t)i0 * a.coef_t_ld;
-        p1[q] = ct + (int64_t)i1 * a.coef_t_ld;
+        if (TILE && staged) {
+            const int s0 = (0 < n[q]) ? a.slot[c] : 0;
+            const int s1 = (1 < n[q]) ? a.slot[a.n_cells + c] : 0;
+            p0[q] = sct + s0 * LOC_SLD;
+            p1[q] = sct + s1 * LOC_SLD;
+        } else {
+            const int i0 = (0 < n[q]) ? a.idx[c] : 0;
+            const int i1 = (1 < n[q]) ? a.idx[a.n_cells + c] : 0;
+            p0[q] = ct + (int64_t)i0 * a.coef_t_ld;
+            p1[q] = ct + (int64_t)i1 * a.coef_t_ld;
+        }
         nloc = max(nloc, n[q]);
     }
     const int nmax = __reduce_max_sync(__activemask(), nloc);
     const float flo = a.has_lo ? (float)a.lo : -CUDART_INF_F;
     const float fhi = a.has_hi ? (float)a.hi : CUDART_INF_F;
     float* outp = reinterpret_cast<float*>(a.out) + c0;
-    if (nmax == 0)
-        local_rows_t<0, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
-    else if (nmax == 1)
-        local_rows_t<1, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
-    else if (nmax == 2)
-        local_rows_t<2, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
-    else
-        local_rows_t<3, CLAMP, CPT>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, ct, flo, fhi, pair);
+#define SPX_LOCAL_ROWS_CALL(NG, SM, CT) \
+    local_rows_t<NG, CLAMP, CPT, SM>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, CT, flo, fhi, pair)
+    if (TILE && staged) {
+        if (nmax == 0) SPX_LOCAL_ROWS_CALL(0, true, sct);
+        else if (nmax == 1) SPX_LOCAL_ROWS_CALL(1, true, sct);
+        else if (nmax == 2) SPX_LOCAL_ROWS_CALL(2, true, sct);
+        else SPX_LOCAL_ROWS_CALL(3, true, sct);
+    } else {
+        if (nmax == 0) SPX_LOCAL_ROWS_CALL(0, false, ct);
+        else if (nmax == 1) SPX_LOCAL_ROWS_CALL(1, false, ct);
+        else if (nmax == 2) SPX_LOCAL_ROWS_CALL(2, false, ct);
+        else SPX_LOCAL_ROWS_CALL(3, false, ct);
+    }
+#undef SPX_LOCAL_ROWS_CALL
 }
 
 }  // namespace spx
@@ -1169,6 +1284,24 @@ extern "C" int spx_local_build_dev(const spx_local* l, void* stream) {
     return SPX_OK;
 }
 
+extern "C" int spx_local_tiles_dev(const spx_local* l, void* stream) {
+    using namespace spx;
+    if (!l || !l->cnt || !l->idx || !l->tile_cnt || !l->tile_stn || !l->slot || l->cap < 1) {
+        set_error("local_tiles: null argument");
+        return SPX_EINVAL;
+    }
+    if (l->n_stn < 1 || l->n_stn > LOC_TILE_WORDS * 32) {
+        set_error("local_tiles: n_stn must be in [1, %d]", LOC_TILE_WORDS * 32);
+        return SPX_EINVAL;
+    }
+    if (l->n_cells == 0) return SPX_OK;
+    const int64_t n_tiles = (l->n_cells + SPX_LOCAL_TILE - 1) / SPX_LOCAL_TILE;
+    k_local_tiles<<<(unsigned)n_tiles, SPX_LOCAL_TILE, 0, (cudaStream_t)stream>>>(
+        l->cnt, l->idx, l->n_cells, l->cap, l->n_stn, l->tile_cnt, l->tile_stn, l->slot);
+    SPX_CHECK_LAUNCH("k_local_tiles");
+    return SPX_OK;
+}
+
 extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     using namespace spx;
     if (!l) {
@@ -1204,6 +1337,9 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     a.has_hi = l->has_hi;
     a.lo = l->lo;
     a.hi = l->hi;
+    a.tile_cnt = nullptr;
+    a.tile_stn = nullptr;
+    a.slot = nullptr;
     const int64_t row_blocks = (l->n_rows + LOC_ROWS - 1) / LOC_ROWS;
     if (row_blocks > 65535) {
         set_error("estimate_local: too many rows in one launch");
@@ -1227,7 +1363,18 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
         const int64_t per_blk = 256 * (int64_t)cpt;
         dim3 g1((unsigned)((l->n_cells + per_blk - 1) / per_blk),
                 (unsigned)((l->n_rows + rows - 1) / rows));
-#define SPX_LOCAL_LAUNCH(CL, RW, CP) k_estimate_local_fast<CL, RW, CP><<<g1, 256, 0, st>>>(a)
+#define SPX_LOCAL_LAUNCH(CL, RW, CP) \
+    k_estimate_local_fast<CL, RW, CP, false><<<g1, 256, 0, st>>>(a)
+        static const int tile_knob = getenv("SPX_LOCAL_TILES") ? atoi(getenv("SPX_LOCAL_TILES")) : 1;
+        if (tile_knob && rows == 128 && cpt == 1 && l->tile_cnt && l->tile_stn && l->slot) {
+            a.tile_cnt = l->tile_cnt;
+            a.tile_stn = l->tile_stn;
+            a.slot = l->slot;
+            if (clamp) k_estimate_local_fast<true, 128, 1, true><<<g1, 256, 0, st>>>(a);
+            else k_estimate_local_fast<false, 128, 1, true><<<g1, 256, 0, st>>>(a);
+            SPX_CHECK_LAUNCH("k_estimate_local_fast(tile)");
+            return SPX_OK;
+        }
         if (rows == 64) {
             if (cpt == 2) { if (clamp) SPX_LOCAL_LAUNCH(true, 64, 2); else SPX_LOCAL_LAUNCH(false, 64, 2); }
             else { if (clamp) SPX_LOCAL_LAUNCH(true, 64, 1); else SPX_LOCAL_LAUNCH(false, 64, 1); }

@@ -846,28 +846,69 @@ __device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShare
         }
         __syncthreads();
         // c_K = u_K - G[K, Mi] y  for the nb right-hand sides at once
-        for (int i = tid; i < nk; i += 512) {
-            const int ki = (i < n) ? stn[i] : (d.n_stn + (i - n));
+        const bool want_base = d.base != nullptr;
+        if (want_base && lane == 0) {
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w) bp[w][wid] = 0.0;   // bp is free here (see above)
+        }
+        for (int i0 = 0; i0 < nk; i0 += 512) {
+            const int i = i0 + tid;
+            const bool act = i < nk;
+            const int ki = !act ? 0 : ((i < n) ? stn[i] : (d.n_stn + (i - n)));
             double acc[DD_RB];
 #pragma unroll
             for (int w = 0; w < DD_RB; ++w)
-                acc[w] = (w < nb) ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + ki] : 0.0;
+                acc[w] = (act && w < nb) ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + ki] : 0.0;
+            if (act) {
 #pragma unroll 4
-            for (int j = 0; j < r; ++j) {
-                const double gv = G[(int64_t)mi[j] * M + ki];
+                for (int j = 0; j < r; ++j) {
+                    const double gv = G[(int64_t)mi[j] * M + ki];
 #pragma unroll
-                for (int w = 0; w < DD_RB; ++w) acc[w] = fma(-gv, ys[w][j], acc[w]);
+                    for (int w = 0; w < DD_RB; ++w) acc[w] = fma(-gv, ys[w][j], acc[w]);
+                }
+#pragma unroll
+                for (int w = 0; w < DD_RB; ++w) {
+                    if (w >= nb) break;
+                    const int64_t q = q0 + base + w;
+                    const int64_t row = d.rhs_row[q];
+                    if (row >= 0) {
+                        d.coef[d.coef_row_major ? row * (int64_t)d.kpad + ki
+                                                : coef_offset(row, ki, d.kpad)] = acc[w];
+                        if (d.coef_t) d.coef_t[(int64_t)ki * d.coef_t_ld + row] = acc[w];
+                    }
+                    if (d.rhs_kind[q] == 1)
+                        atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
+                }
             }
+            if (want_base) {
+                // local estimator: base = F * sum of the station coefficients + the
+                // coefficient of the ones-border (drift coefficients are not part of it);
+                // fixed-order reduction: lanes by shuffle, warps below
+                const double bf = !act ? 0.0 : ((i < n) ? d.base_f : ((i == n) ? 1.0 : 0.0));
 #pragma unroll
-            for (int w = 0; w < DD_RB; ++w) {
-                if (w >= nb) break;
-                const int64_t q = q0 + base + w;
-                const int64_t row = d.rhs_row[q];
-                if (row >= 0)
-                    d.coef[d.coef_row_major ? row * (int64_t)d.kpad + ki
-                                            : coef_offset(row, ki, d.kpad)] = acc[w];
-                if (d.rhs_kind[q] == 1)
-                    atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
+                for (int w = 0; w < DD_RB; ++w) {
+                    double v = bf * acc[w];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) bp[w][wid] += v;
+                }
+            }
+        }
+        if (d.coef_t) {           // missing stations: explicit zeros (the buffer is not pre-set)
+            for (int idx = tid; idx < nb * r; idx += 512) {
+                const int w = idx / r, j = idx - w * r;
+                const int64_t row = d.rhs_row[q0 + base + w];
+                if (row >= 0) d.coef_t[(int64_t)mi[j] * d.coef_t_ld + row] = 0.0;
+            }
+        }
+        if (want_base) {
+            __syncthreads();
+            if (tid < nb) {
+                const int64_t row = d.rhs_row[q0 + base + tid];
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v += bp[tid][k];
+                if (row >= 0) d.base[row] = v;
             }
         }
         __syncthreads();
@@ -1008,6 +1049,8 @@ static int dd_force_pivot() {
     return v;
 }
 
+int spx_krige_downdate_reg_max_r(void) { return DD_REG_MAX; }
+
 int spx_krige_downdate_max_r(void) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -1033,6 +1076,13 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
     }
     spx_downdate dd = *d;
     if (dd.max_r < 1) dd.max_r = 1;
+    if ((d->coef_t || d->base) &&
+        (d->max_r > DD_REG_MAX || dd_force_smem() || d->n_border < 1 ||
+         (d->coef_t && d->coef_t_ld < 1))) {
+        set_error("krige_downdate: coef_t / base need the register kernel (max_r <= %d), "
+                  "n_border >= 1 and coef_t_ld >= 1", DD_REG_MAX);
+        return SPX_EINVAL;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int smem_lo = 0;   // systems with r > smem_lo go to the shared-memory kernel
     if (!dd_force_smem()) {

@@ -56,6 +56,20 @@ def availability_groups(avail):
     return grp_of_step, grp_mask
 
 
+class _LazyCtx(dict):
+    """Per-chunk context; entries of ``lazy`` (byte masks, NaN -> 0 data, ...) are built on
+    first use -- the common path needs none of them."""
+    lazy = None
+
+    def __missing__(self, key):
+        fn = (self.lazy or {}).get(key)
+        if fn is None:
+            raise KeyError(key)
+        val = fn()
+        self[key] = val
+        return val
+
+
 class PendingChunk:
     """A chunk whose kernels are queued on the stream.  ``result()`` runs the
     deferred health checks (reading back a few flags copied to pinned memory
@@ -174,6 +188,9 @@ class ChunkEngine:
         # least this many availability groups
         self.downdate = True
         self.downdate_min_systems = 4
+        # all-downdated chunks are planned by the native host planner (csrc/spx_plan.cu)
+        # instead of the NumPy index logic of _krige / _solve_downdate
+        self.native_plan = True
         # full-system inverses are reused across chunks with the same stations and
         # variogram (they do not depend on the data)
         self.multivg = True      # per-row-variogram estimator for variogram series
@@ -181,6 +198,7 @@ class ChunkEngine:
         # when a cell has on average at most this many stations within the range
         self.local_support = True
         self.local_max_near = 24.0
+        self.local_tiles = True     # shared-memory staging of the coefficient slices
         self._local_cache = {}
         self._geom_cache = {}
         self.pinv_flagged = True  # np.linalg.pinv semantics for untrustworthy OK/EDK systems
@@ -202,6 +220,10 @@ class ChunkEngine:
         self._main_handle = None
         self._arena = None         # per-chunk upload arena (see _arena_take)
         self._arena_off = 0
+        self._arenas = [None] * self._N_ARENAS
+        self._arena_events = [None] * self._N_ARENAS
+        self._arena_k = 0
+        self._const_cache = {}
 
     # ------------------------------------------------------------ helpers
     _TORCH_OF = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
@@ -220,20 +242,59 @@ class ChunkEngine:
         self._main = None
         self._main_stream()
 
+    _N_ARENAS = 4
+
+    def _arena_next_chunk(self):
+        """Switch to the next upload arena of a small ring (a fresh torch allocation per
+        chunk costs a cudaMalloc: the previous arenas are still referenced by queued
+        kernels).  An arena is reused only after the chunk that used it last has
+        finished on the compute stream."""
+        if self._arena is not None:                 # close the arena of the previous chunk
+            ev = self._arena_events[self._arena_k]
+            if ev is None:
+                ev = self._arena_events[self._arena_k] = torch.cuda.Event()
+            ev.record(self._main_stream())
+        self._arena_k = (self._arena_k + 1) % self._N_ARENAS
+        ev = self._arena_events[self._arena_k]
+        if ev is not None:
+            ev.synchronize()
+        self._arena = self._arenas[self._arena_k]
+        self._arena_off = 0
+
     def _arena_take(self, nbytes):
-        """Device bytes for one upload, carved from a per-chunk arena that belongs to
-        the upload stream's allocator pool (one stream-context switch per arena, not
-        per upload) and is marked as used by the compute stream."""
+        """Device bytes for one upload, carved from the chunk's arena (allocated in the
+        upload stream's pool, marked as used by the compute stream).  Requests that do
+        not fit get a one-off allocation."""
         need = (nbytes + 255) & ~255
-        if self._arena is None or self._arena_off + need > self._arena.numel():
-            size = max(16 << 20, 2 * need)
+        if self._arena is None:
             with torch.cuda.stream(self.h2d_stream):
-                self._arena = torch.empty(size, dtype=torch.uint8, device=self.device)
+                self._arena = torch.empty(max(16 << 20, 2 * need), dtype=torch.uint8,
+                                          device=self.device)
             self._arena.record_stream(self._main_stream())
+            self._arenas[self._arena_k] = self._arena
             self._arena_off = 0
+        if self._arena_off + need > self._arena.numel():
+            with torch.cuda.stream(self.h2d_stream):
+                t = torch.empty(need, dtype=torch.uint8, device=self.device)
+            t.record_stream(self._main_stream())
+            return t[:nbytes]
         o = self._arena_off
         self._arena_off += need
         return self._arena[o:o + nbytes]
+
+    def _dev_const(self, arr):
+        """Device copy of a small per-job constant (station coordinates): cached by
+        content, so that the chunks of a job upload it once."""
+        arr = np.ascontiguousarray(arr)
+        key = (arr.dtype.str, arr.shape, arr.tobytes())
+        hit = self._const_cache.get(key)
+        if hit is None:
+            self._sync_uploads()
+            hit = torch.from_numpy(arr.copy()).to(self.device)
+            while len(self._const_cache) >= 16:
+                self._const_cache.pop(next(iter(self._const_cache)))
+            self._const_cache[key] = hit
+        return hit
 
     def _dev(self, arr, dtype=None):
         """Host -> device copy on a dedicated upload stream.  A pageable-memory
@@ -422,7 +483,7 @@ class ChunkEngine:
         per-step min / mean / max / std / count in ``PendingChunk.field_stats``."""
         with torch.cuda.device(self.device):
             self._begin_call()
-            self._arena = None
+            self._arena_next_chunk()
             pend = self._interp_chunk(
                 data, stn_xs, stn_ys, cell_xs, cell_ys, grid_shape, interp_args, vgs,
                 cntn_idxs, drft_arrs, stns_drft, fld_beg_row, fld_end_row, neb_sel_mthd,
@@ -550,21 +611,14 @@ class ChunkEngine:
                     stns_drft = np.ascontiguousarray(np.asarray(stns_drft)[tke])
                 n_stn = int(tke.size)
 
-        # ---- per-step host logic --------------------------------------------
+        # ---- per-step host logic (native: csrc/spx_plan.cu) ------------------
         t_host0 = time.perf_counter()
-        avail = ~np.isnan(data)
-        grp_of_step, grp_mask = availability_groups(avail)       # grps.py:57-101
-        n_grps = grp_mask.shape[0]
-        grp_n = np.count_nonzero(grp_mask, axis=1).astype(np.int64)
-        n_avail = grp_n[grp_of_step]
+        # availability groups (grps.py:57-101) and per-step flags (steps.py:760-765) in
+        # one pass over the data; byte masks are expanded only if a path asks for them
+        grp_of_step, grp_bits, grp_n, grp_first, n_avail, steps_flags = _lib.avail_groups(
+            data, float(min_var_thr), want_mask=False)
+        n_grps = int(grp_bits.shape[0])
         problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
-
-        if min_var_thr == -np.inf:
-            steps_flags = n_avail >= 1                               # nothing is below -inf
-        else:
-            with np.errstate(invalid='ignore'):
-                steps_flags = (np.where(avail, data, -np.inf) >= min_var_thr).any(axis=1)  # :760-765
-        row_sums = None
 
         def ref_means_of(idx):                                       # steps.py:276, on demand
             return np.nansum(data[idx], axis=1) / n_avail[idx]
@@ -573,26 +627,33 @@ class ChunkEngine:
 
         self.timing['host_groups'] = 1e3 * (time.perf_counter() - t_host0)
         # ---- device residents -----------------------------------------------
-        d_stn_x = self._dev(stn_xs)
-        d_stn_y = self._dev(stn_ys)
+        d_stn_x = self._dev_const(stn_xs)
+        d_stn_y = self._dev_const(stn_ys)
         d_cell_x, d_cell_y, d_pos = geo['d_cell_x'], geo['d_cell_y'], geo['d_pos']
         d_data = self._dev(data)
-        self._sync_uploads()
-        d_data0 = torch.nan_to_num(d_data, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
-        # availability masks on the device (+ one all-ones row = "every station")
-        d_grp_mask = self._dev(np.concatenate(
-            [grp_mask.view(np.uint8), np.ones((1, n_stn), dtype=np.uint8)], axis=0))
-        ctx = dict(
+        ctx = _LazyCtx(
             n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
             d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
-            d_data=d_data, d_data0=d_data0, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
+            d_data=d_data, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
             stn_xs=stn_xs, stn_ys=stn_ys,
             has_lo=int(min_var_cut is not None), has_hi=int(max_var_cut is not None),
             lo=float(min_var_cut) if min_var_cut is not None else 0.0,
             hi=float(max_var_cut) if max_var_cut is not None else 0.0,
-            grp_of_step=grp_of_step, grp_mask=grp_mask, grp_n=grp_n, n_avail=n_avail,
-            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'],
-            d_grp_mask=d_grp_mask)
+            grp_of_step=grp_of_step, grp_n=grp_n, n_avail=n_avail, n_grps=n_grps,
+            grp_first=grp_first,
+            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'])
+
+        def _d_data0():
+            self._sync_uploads()
+            return torch.nan_to_num(d_data, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
+
+        def _d_grp_mask():
+            # availability masks on the device (+ one all-ones row = "every station")
+            return self._dev(np.concatenate(
+                [ctx['grp_mask'].view(np.uint8), np.ones((1, n_stn), dtype=np.uint8)], axis=0))
+
+        ctx.lazy = dict(grp_mask=lambda: _lib.unpack_group_bits(grp_bits, n_stn),
+                        d_data0=_d_data0, d_grp_mask=_d_grp_mask)
 
         tdtype = torch.float64 if out_f64 else torch.float32
         # NaN marks cells outside the mask and steps without stations
@@ -736,7 +797,7 @@ class ChunkEngine:
         batch = max(1, int(self.aux_limit // max(per_grp, 1)))
         for b0 in range(0, grps.size, batch):
             gb = grps[b0:b0 + batch]
-            slot_of = np.full(ctx['grp_mask'].shape[0], -1, dtype=np.int32)
+            slot_of = np.full(ctx['n_grps'], -1, dtype=np.int32)
             slot_of[gb] = np.arange(gb.size, dtype=np.int32)
             st = steps[slot_of[grp_of_step[steps]] >= 0]
             nnb = self._nnb_index(ctx, gb)
@@ -862,7 +923,22 @@ class ChunkEngine:
             if mx <= cap:
                 break
             cap = mx
-        res = dict(struct=L, F=F, cap=cap, keep=(cnt, idx, val, d_bs, d_bo), max_near=mx)
+        keep = [cnt, idx, val, d_bs, d_bo]
+        if ctx['n_stn'] <= 65536 and self.local_tiles:
+            # distinct near stations per tile of 256 cells: the streamlined kernel stages
+            # their coefficient slices in shared memory
+            n_tiles = (n_cells + _lib.SPX_LOCAL_TILE - 1) // _lib.SPX_LOCAL_TILE
+            tile_cnt = torch.empty(n_tiles, dtype=_I32, device=self.device)
+            tile_stn = torch.empty((n_tiles, _lib.SPX_LOCAL_TILE_CAP), dtype=_I32,
+                                   device=self.device)
+            slot = torch.empty((cap, n_cells), dtype=torch.uint8, device=self.device)
+            L.n_stn = ctx['n_stn']
+            L.tile_cnt, L.tile_stn, L.slot = (tile_cnt.data_ptr(), tile_stn.data_ptr(),
+                                              slot.data_ptr())
+            _lib.check(self.lib.spx_local_tiles_dev(C.byref(L), self._stream()), 'local_tiles')
+            self._count('launches')
+            keep += [tile_cnt, tile_stn, slot]
+        res = dict(struct=L, F=F, cap=cap, keep=tuple(keep), max_near=mx)
         while len(self._local_cache) >= 4:
             self._local_cache.pop(next(iter(self._local_cache)))
         self._local_cache[key] = res
@@ -997,7 +1073,7 @@ class ChunkEngine:
         grps_all = np.unique(grp_of_step[steps])
         for b0 in range(0, grps_all.size, max_grps):
             gb = grps_all[b0:b0 + max_grps]
-            slot_of = np.full(ctx['grp_mask'].shape[0], -1, dtype=np.int32)
+            slot_of = np.full(ctx['n_grps'], -1, dtype=np.int32)
             slot_of[gb] = np.arange(gb.size, dtype=np.int32)
             st = steps[slot_of[grp_of_step[steps]] >= 0]
             # phase A: sum of weights over the available stations of each group
@@ -1027,7 +1103,7 @@ class ChunkEngine:
 
     # ---- kriging --------------------------------------------------------
     def _krige(self, ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs, stns_drft,
-               problem_steps, force_direct=False, ev_out=None):
+               problem_steps, force_direct=False, ev_out=None, no_fast=False):
         """OK / SK / EDK in dual form:
         Z[t, i] = rhs_i . A_g^-1 [z_t; 0]."""
         if not steps.size:
@@ -1037,7 +1113,7 @@ class ChunkEngine:
         n_drifts = 0 if kind != 2 else int(stns_drft.shape[1])
         n_border = {0: 1, 1: 0, 2: 1 + n_drifts}[kind]
         kpad = _pad_up(n_stn + n_border, 8)
-        grp_of_step, grp_mask, grp_n = ctx['grp_of_step'], ctx['grp_mask'], ctx['grp_n']
+        grp_of_step, grp_n = ctx['grp_of_step'], ctx['grp_n']
 
         K = types.SimpleNamespace(kind=kind, n_drifts=n_drifts, n_border=n_border, kpad=kpad,
                                   uniq_vgs=uniq_vgs, keep={})
@@ -1052,9 +1128,16 @@ class ChunkEngine:
             ctx['stns_drft_bytes'] = np.ascontiguousarray(stns_drft, dtype=np.float64).tobytes()
             bad_cells = np.where(np.isnan(drft).any(axis=0))[0]
 
+        if (self.native_plan and self.downdate and kind != 1 and not force_direct and
+                not no_fast and ev_out is None and not bad_cells.size):
+            fn = self._krige_fast(ctx, out, kind_name, K, steps, step_vg, uniq_vgs, drft,
+                                  drft_arrs, stns_drft, problem_steps)
+            if fn is not NotImplemented:
+                return fn
+
         # station lists per group (ascending station index = reference order); the
         # pseudo-group n_grps holds every station (the "full" system of the downdate)
-        n_grps = grp_mask.shape[0]
+        n_grps = ctx['n_grps']
         grps_used = np.unique(grp_of_step[steps])
         stn_off = np.zeros(n_grps + 1, dtype=np.int64)
         stn_off[grps_used] = np.concatenate([[0], np.cumsum(grp_n[grps_used])])[:-1]
@@ -1113,15 +1196,7 @@ class ChunkEngine:
 
         K.d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8))
 
-        # bound for the sum(lambda) screening: |rhs| <= max(vg bound, 1, |drift|)
-        bx0, bx1, by0, by1 = ctx['bbox']
-        max_dist = math.hypot(max(bx1, ctx['stn_xs'].max()) - min(bx0, ctx['stn_xs'].min()),
-                              max(by1, ctx['stn_ys'].max()) - min(by0, ctx['stn_ys'].min()))
-        rhs_bound = np.array([max(1.0, vg_abs_bound(v, max_dist)) for v in uniq_vgs])
-        if kind == 2:
-            with np.errstate(invalid='ignore'):
-                dmax = np.nanmax(np.abs(drft)) if np.isfinite(drft).any() else 1.0
-            rhs_bound = np.maximum(rhs_bound, dmax)
+        rhs_bound = self._rhs_bound(ctx, K, drft)
         K.rhs_bound = rhs_bound
 
         # ---- solve: downdated where it pays, direct LU otherwise ----------
@@ -1149,89 +1224,8 @@ class ChunkEngine:
         K.flags_event = torch.cuda.Event()
         K.flags_event.record(self._main_stream())
 
-        if K.local is not None:
-            coef2d = K.coef.view(-1, kpad)
-            for k in range(seg_vgs.size):
-                r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
-                nbr = self._local_neighbours(ctx, K, uniq_vgs[int(seg_vgs[k])], K.local[k])
-                base = nbr['F'] * coef2d[r0:r1, :n_stn].sum(dim=1)
-                if n_border >= 1:
-                    base = base + coef2d[r0:r1, n_stn]
-                base = base.contiguous()
-                L = nbr['struct']
-                L.coef = coef2d[r0:r1].data_ptr()
-                L.base = base.data_ptr()
-                L.n_rows = r1 - r0
-                L.kpad, L.n_stn, L.n_drifts = kpad, n_stn, n_drifts
-                L.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
-                L.row_dst = d_row_dst[r0:].data_ptr()
-                L.out = out.data_ptr()
-                L.out_ld = ctx['fld_size']
-                L.out_f64 = ctx['out_f64']
-                L.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
-                L.has_lo, L.has_hi, L.lo, L.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
-                L.rows_all_valid = 1          # row-major rows are exactly the kriged steps
-                L.coef_t, L.coef_t_ld = None, 0
-                if (not ctx['out_f64'] and n_drifts == 0 and ctx['d_pos'] is None):
-                    # transposed copy for the streamlined kernel (5 MB at 1250 x 504)
-                    ld_t = _pad_up(r1 - r0, 4)
-                    coef_t = torch.zeros((kpad, ld_t), dtype=_F64, device=self.device)
-                    coef_t[:, :r1 - r0] = coef2d[r0:r1].t()
-                    L.coef_t, L.coef_t_ld = coef_t.data_ptr(), ld_t
-                stream = self._stream()
-                ev = self._prof_begin()
-                _lib.check(self.lib.spx_estimate_local_dev(C.byref(L), stream), 'estimate_local')
-                self._prof_end(ev, 'k_estimate_local', 'hbm',
-                               (r1 - r0) * n_cells * (8 if ctx['out_f64'] else 4))
-                self._count('launches')
-                self._count('local_rows', r1 - r0)
-
-        if K.use_mv:
-            d_row_vg = self._dev(step_vg[K.steps_o].astype(np.int32))
-            g = _lib.spx_multivg()
-            g.coef = K.coef.data_ptr()
-            g.n_rows = int(K.steps_o.size)
-            g.kpad, g.n_stn, g.n_border = kpad, n_stn, n_border
-            g.stn_x, g.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
-            g.cell_x, g.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
-            g.n_cells = n_cells
-            g.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
-            g.vgs = K.d_vgs.data_ptr()
-            g.row_vg = d_row_vg.data_ptr()
-            g.covar_flag = int(kind == 1)
-            g.min_vg_val = ctx['min_vg_val']
-            g.row_dst = d_row_dst.data_ptr()
-            g.out = out.data_ptr()
-            g.out_ld = ctx['fld_size']
-            g.out_f64 = ctx['out_f64']
-            g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
-            g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
-            def _fast(vg_s):       # <= 2 Sph/Lin and <= 2 Exp/Gau terms plus nuggets
-                n_poly = n_exp = 0
-                for (t, _, _) in _lib.parse_vg_str(vg_s):
-                    if t in (2, 4):
-                        n_poly += 1
-                    elif t in (3, 5):
-                        n_exp += 1
-                    elif t != 1:
-                        return False
-                return n_poly <= 2 and n_exp <= 2
-            g.all_fast = int(all(_fast(vg_s) for vg_s in uniq_vgs))
-            with self._phase('multivg'):
-                _lib.check(self.lib.spx_estimate_multivg_dev(C.byref(g), self._stream()),
-                           'estimate_multivg')
-            self._count('launches')
-            self._count('multivg_evals', int(K.steps_o.size) * n_stn * n_cells)
-
-        # ---- main contraction: one launch per variogram segment ----------
-        for k in range(seg_vgs.size if not K.row_major else 0):
-            seg_coef = K.coef[seg_row0[k] * kpad:]
-            with self._phase('gemm'):
-                self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad,
-                           n_border=n_border, gen=_lib.GEN_VG, epi=_lib.EPI_FIELD,
-                           row_dst=d_row_dst[seg_row0[k]:], out=out,
-                           vg=_lib.make_vg(uniq_vgs[int(seg_vgs[k])]),
-                           covar_flag=int(kind == 1), cell_drift=K.d_cell_drift)
+        self._estimate(ctx, K, out, kind, (seg_vgs, seg_first, seg_cnt, seg_row0), d_row_dst,
+                       step_vg)
 
         if ev_out is not None:
             self._est_vars(ctx, K, ev_out)
@@ -1284,6 +1278,317 @@ class ChunkEngine:
             K.keep.clear()
 
         return deferred
+
+    def _ginv_key(self, ctx, K):
+        return (K.kind, K.n_drifts, ctx['min_vg_val'], ctx['stn_xs'].tobytes(),
+                ctx['stn_ys'].tobytes(),
+                None if K.d_stn_drift is None else ctx['stns_drft_bytes'])
+
+    def _rhs_bound(self, ctx, K, drft):
+        """Bound for the sum(lambda) screening: |rhs| <= max(vg bound, 1, |drift|)."""
+        bx0, bx1, by0, by1 = ctx['bbox']
+        max_dist = math.hypot(max(bx1, ctx['stn_xs'].max()) - min(bx0, ctx['stn_xs'].min()),
+                              max(by1, ctx['stn_ys'].max()) - min(by0, ctx['stn_ys'].min()))
+        rhs_bound = np.array([max(1.0, vg_abs_bound(v, max_dist)) for v in K.uniq_vgs])
+        if K.kind == 2:
+            with np.errstate(invalid='ignore'):
+                dmax = np.nanmax(np.abs(drft)) if np.isfinite(drft).any() else 1.0
+            rhs_bound = np.maximum(rhs_bound, dmax)
+        return rhs_bound
+
+    def _krige_fast(self, ctx, out, kind_name, K, steps, step_vg, uniq_vgs, drft, drft_arrs,
+                    stns_drft, problem_steps):
+        """The common case of _krige -- every system downdated from a cached full-system
+        inverse -- with the index work done by the native planner: per variogram ONE
+        planner call, one small upload, then station lists / Bt on the device, Ut = Bt G,
+        the downdate kernel (which also emits the transposed coefficients and base values
+        of the local estimator) and the estimate stage.  Returns NotImplemented when a
+        precondition fails (the general path then runs); anything unhealthy found later is
+        redone by the general path as well."""
+        lib = self.lib
+        n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
+        kpad, n_border, n_drifts, kind = K.kpad, K.n_border, K.n_drifts, K.kind
+        M = n_stn + n_border
+        if not self.ginv_cache:
+            return NotImplemented
+        steps = np.ascontiguousarray(steps, dtype=np.int32)
+        # steps ordered by variogram (stable), one segment per variogram
+        if len(uniq_vgs) == 1:
+            steps_o = steps
+            seg_vgs = np.zeros(1, dtype=np.int64)
+            seg_first = np.zeros(1, dtype=np.int64)
+            seg_cnt = np.array([steps.size], dtype=np.int64)
+        else:
+            vg_of = step_vg[steps]
+            order = np.argsort(vg_of, kind='stable')
+            steps_o = np.ascontiguousarray(steps[order])
+            seg_vgs, seg_first, seg_cnt = np.unique(vg_of[order], return_index=True,
+                                                    return_counts=True)
+        base_key = self._ginv_key(ctx, K)
+        ginvs = []
+        for v in seg_vgs:
+            hit = self._ginv_cache.get((base_key, uniq_vgs[int(v)]))
+            if hit is None:
+                return NotImplemented          # the general path builds and caches it
+            ginvs.append(hit)
+        # estimator choice exactly as in the general path
+        K.local = None
+        if self.local_support and n_drifts <= 4:
+            K.local = self._local_plan(ctx, [uniq_vgs[int(v)] for v in seg_vgs])
+        mv_smem = ((n_stn + n_border) * 64 + 4 * (n_stn + n_border) + 1024) * 8 + 4096
+        K.use_mv = bool(K.local is None and self.multivg and seg_vgs.size >= 8
+                        and steps_o.size / seg_vgs.size < 32 and mv_smem <= 220 * 1024)
+        K.row_major = K.use_mv or (K.local is not None)
+        seg_row0 = np.zeros(seg_vgs.size, dtype=np.int64)
+        if K.row_major:
+            row_of = np.arange(steps_o.size, dtype=np.int64)
+            total_rows = int(steps_o.size)
+            row_dst_np = steps_o
+        else:
+            row_of = np.empty(steps_o.size, dtype=np.int64)
+            acc = 0
+            for k in range(seg_vgs.size):
+                seg_row0[k] = acc
+                row_of[seg_first[k]:seg_first[k] + seg_cnt[k]] = acc + np.arange(seg_cnt[k])
+                acc += _pad_up(seg_cnt[k], _lib.SPX_BM)
+            total_rows = acc
+            row_dst_np = np.full(total_rows, -1, dtype=np.int32)
+            row_dst_np[row_of] = steps_o
+        # plans first: eligibility (every system downdated by the register kernel) is
+        # known before anything is queued
+        grp_of_step = ctx['grp_of_step']
+        grp_n32 = ctx.get('grp_n32')
+        if grp_n32 is None:
+            grp_n32 = ctx['grp_n32'] = np.ascontiguousarray(ctx['grp_n'], dtype=np.int32)
+        reg_max = lib.spx_krige_downdate_reg_max_r()
+        plans = []
+        for k in range(seg_vgs.size):
+            r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
+            st_k = steps_o[r0:r1]
+            rows_k = row_of[r0:r1]
+            hb = np.empty(lib.spx_downdate_plan_host_bytes(r1 - r0), dtype=np.uint8)
+            plan = _lib.spx_dd_plan()
+            _lib.check(lib.spx_downdate_plan_host(
+                grp_of_step.ctypes.data, grp_n32.ctypes.data, ctx['n_grps'], n_stn,
+                st_k.ctypes.data, rows_k.ctypes.data, r1 - r0, hb.ctypes.data, hb.size,
+                C.byref(plan)), 'downdate_plan_host')
+            if plan.n_sys < self.downdate_min_systems or plan.max_r > reg_max:
+                return NotImplemented
+            plans.append((plan, hb))
+
+        K.steps_o = steps_o
+        K.coef = torch.zeros(total_rows * kpad, dtype=_F64, device=self.device)
+        d_row_dst = self._dev(np.ascontiguousarray(row_dst_np, dtype=np.int32))
+        K.d_vgs = self._dev(_lib.vgs_to_numpy(uniq_vgs).view(np.uint8)) if K.use_mv else None
+        rhs_bound = self._rhs_bound(ctx, K, drft)
+        want_t = K.local is not None and self._local_wants_coef_t(ctx, n_drifts)
+        d_data = ctx['d_data']
+        fused = []
+        checks = []
+        n_sys_total = 0
+        with self._phase('solve_downdate'):
+            for k, (plan, hb) in enumerate(plans):
+                r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
+                n_sys, n_data, n_rhs = plan.n_sys, plan.n_data, plan.n_rhs
+                n_sys_total += n_sys
+                d_plan = self._arena_take(int(plan.n_bytes))
+                _lib.check(lib.spx_upload_dev(C.c_void_p(d_plan.data_ptr()),
+                                              C.c_void_p(hb.ctypes.data),
+                                              int(plan.n_upload_bytes), self._h2d_handle), 'upload')
+                self._h2d_dirty = True
+                pb = d_plan.data_ptr()
+                _lib.check(lib.spx_avail_lists_dev(
+                    self._ptr(d_data), n_stn, n_stn, C.c_void_p(pb + plan.off_bt_step + 4 * n_data),
+                    n_sys, C.c_void_p(pb + plan.off_sys_stn_off), C.c_void_p(pb + plan.off_stn_list),
+                    C.c_void_p(pb + plan.off_sys_miss_off), C.c_void_p(pb + plan.off_miss_list),
+                    self._stream()), 'avail_lists')
+                Bt = torch.empty((n_rhs, M), dtype=_F64, device=self.device)
+                _lib.check(lib.spx_build_bt_dev(
+                    self._ptr(d_data), n_stn, n_stn, C.c_void_p(pb + plan.off_bt_step), n_rhs,
+                    n_data, n_border, self._ptr(Bt), self._stream()), 'build_bt')
+                Ut = torch.matmul(Bt, ginvs[k])
+                self._count('launches', 3)
+                # resid [n_rhs] f64 (zero-initialised) followed by info [n_sys] i32
+                flags = torch.zeros(n_rhs + (n_sys + 1) // 2, dtype=_F64, device=self.device)
+                D = _lib.spx_downdate()
+                D.n_sys, D.n_stn, D.n_border, D.max_r = n_sys, n_stn, n_border, int(plan.max_r)
+                D.ginv = ginvs[k].data_ptr()
+                D.sys_r = pb + plan.off_sys_r
+                D.sys_miss_off = pb + plan.off_sys_miss_off
+                D.miss_list = pb + plan.off_miss_list
+                D.sys_n = pb + plan.off_sys_n
+                D.sys_stn_off = pb + plan.off_sys_stn_off
+                D.stn_list = pb + plan.off_stn_list
+                D.sys_rhs_off = pb + plan.off_sys_rhs_off
+                D.sys_rhs_cnt = pb + plan.off_sys_rhs_cnt
+                D.rhs_urow = pb + plan.off_rhs_urow
+                D.rhs_row = pb + plan.off_rhs_row
+                D.rhs_kind = pb + plan.off_rhs_kind
+                D.sys_order = pb + plan.off_sys_order
+                D.ut = Ut.data_ptr()
+                D.kpad = kpad
+                D.coef = K.coef.data_ptr()
+                D.coef_row_major = int(K.row_major)
+                D.resid = flags.data_ptr()
+                D.info = flags.data_ptr() + 8 * n_rhs
+                pre = None
+                if K.local is not None:
+                    # base / coef_t index rows relative to the segment start
+                    pre = dict(base=torch.empty(r1 - r0, dtype=_F64, device=self.device))
+                    tot = K.local[k][1]            # F of _local_neighbours (variogram form)
+                    F = tot if tot > ctx['min_vg_val'] else 0.0
+                    D.base = pre['base'].data_ptr() - 8 * r0
+                    D.base_f = float(F)
+                    if want_t:
+                        ld_t = _pad_up(r1 - r0, 4)
+                        pre['coef_t'] = torch.empty((kpad, ld_t), dtype=_F64, device=self.device)
+                        pre['ld_t'] = ld_t
+                        D.coef_t = pre['coef_t'].data_ptr() - 8 * r0
+                        D.coef_t_ld = ld_t
+                fused.append(pre)
+                _lib.check(lib.spx_krige_downdate_dev(C.byref(D), self._stream()), 'downdate')
+                self._count('launches')
+                self._count('ginv_cache_hits')
+                h_flags = self._fetch_async(flags)
+                pos_ones = hb[plan.off_pos_ones:plan.off_pos_ones + 8 * n_sys].view(np.int64)
+                checks.append((h_flags, pos_ones, n_rhs, n_sys, float(rhs_bound[int(seg_vgs[k])])))
+
+        flags_event = torch.cuda.Event()
+        flags_event.record(self._main_stream())
+        self._estimate(ctx, K, out, kind, (seg_vgs, seg_first, seg_cnt, seg_row0), d_row_dst,
+                       step_vg, fused=fused)
+        self.stats['n_systems'] = self.stats.get('n_systems', 0) + n_sys_total
+        self.stats['n_downdated'] = self.stats.get('n_downdated', 0) + n_sys_total
+        self._count('native_plans', len(plans))
+
+        def deferred():
+            """Health flags (already in pinned memory): an unhealthy elimination or a
+            system whose weights may not sum to one sends the whole call through the
+            general path, which knows every fallback of the reference."""
+            flags_event.synchronize()
+            unhealthy = False
+            flagged = 0
+            for h_flags, pos_ones, n_rhs, n_sys, bound in checks:
+                hf = h_flags.numpy()
+                info = hf[n_rhs:].view(np.int32)[:n_sys]
+                unhealthy |= bool((info != 0).any())
+                with np.errstate(invalid='ignore'):
+                    dev = hf[:n_rhs][pos_ones] * bound
+                flagged += int((~(dev <= self.lambda_tol)).sum())
+            if unhealthy or flagged:
+                self._count('downdate_redo' if unhealthy else 'fast_path_redo')
+                fn = self._krige(ctx, out, kind_name, steps, step_vg, uniq_vgs, drft_arrs,
+                                 stns_drft, problem_steps, force_direct=unhealthy, no_fast=True)
+                if fn is not None:
+                    fn()
+            else:
+                self.stats['n_flagged'] = self.stats.get('n_flagged', 0)
+
+        return deferred
+
+    @staticmethod
+    def _local_wants_coef_t(ctx, n_drifts):
+        """The streamlined local kernel (transposed coefficients) applies."""
+        return (not ctx['out_f64']) and n_drifts == 0 and ctx['d_pos'] is None
+
+    def _estimate(self, ctx, K, out, kind, segs, d_row_dst, step_vg, fused=None):
+        """Estimate stage of _krige: coefficient rows -> field rows, one variogram segment
+        at a time (local estimator / per-row-variogram estimator / DMMA contraction).
+        fused[k]: per-segment dict with 'base' / 'coef_t' / 'ld_t' already written by the
+        downdate kernel."""
+        seg_vgs, seg_first, seg_cnt, seg_row0 = segs
+        kpad, n_border, n_drifts = K.kpad, K.n_border, K.n_drifts
+        n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
+        if K.local is not None:
+            coef2d = K.coef.view(-1, kpad)
+            for k in range(seg_vgs.size):
+                r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
+                nbr = self._local_neighbours(ctx, K, K.uniq_vgs[int(seg_vgs[k])], K.local[k])
+                pre = fused[k] if fused is not None else None
+                if pre is not None and pre.get('base') is not None:
+                    base = pre['base']             # written by the downdate kernel
+                else:
+                    base = nbr['F'] * coef2d[r0:r1, :n_stn].sum(dim=1)
+                    if n_border >= 1:
+                        base = base + coef2d[r0:r1, n_stn]
+                    base = base.contiguous()
+                L = nbr['struct']
+                L.coef = coef2d[r0:r1].data_ptr()
+                L.base = base.data_ptr()
+                L.n_rows = r1 - r0
+                L.kpad, L.n_stn, L.n_drifts = kpad, n_stn, n_drifts
+                L.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
+                L.row_dst = d_row_dst[r0:].data_ptr()
+                L.out = out.data_ptr()
+                L.out_ld = ctx['fld_size']
+                L.out_f64 = ctx['out_f64']
+                L.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+                L.has_lo, L.has_hi, L.lo, L.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+                L.rows_all_valid = 1          # row-major rows are exactly the kriged steps
+                L.coef_t, L.coef_t_ld = None, 0
+                if pre is not None and pre.get('coef_t') is not None:
+                    L.coef_t, L.coef_t_ld = pre['coef_t'].data_ptr(), pre['ld_t']
+                elif self._local_wants_coef_t(ctx, n_drifts):
+                    # transposed copy for the streamlined kernel (5 MB at 1250 x 504)
+                    ld_t = _pad_up(r1 - r0, 4)
+                    coef_t = torch.zeros((kpad, ld_t), dtype=_F64, device=self.device)
+                    coef_t[:, :r1 - r0] = coef2d[r0:r1].t()
+                    L.coef_t, L.coef_t_ld = coef_t.data_ptr(), ld_t
+                stream = self._stream()
+                ev = self._prof_begin()
+                _lib.check(self.lib.spx_estimate_local_dev(C.byref(L), stream), 'estimate_local')
+                self._prof_end(ev, 'k_estimate_local', 'hbm',
+                               (r1 - r0) * n_cells * (8 if ctx['out_f64'] else 4))
+                self._count('launches')
+                self._count('local_rows', r1 - r0)
+
+        if K.use_mv:
+            d_row_vg = self._dev(step_vg[K.steps_o].astype(np.int32))
+            g = _lib.spx_multivg()
+            g.coef = K.coef.data_ptr()
+            g.n_rows = int(K.steps_o.size)
+            g.kpad, g.n_stn, g.n_border = kpad, n_stn, n_border
+            g.stn_x, g.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
+            g.cell_x, g.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
+            g.n_cells = n_cells
+            g.cell_drift = K.d_cell_drift.data_ptr() if K.d_cell_drift is not None else None
+            g.vgs = K.d_vgs.data_ptr()
+            g.row_vg = d_row_vg.data_ptr()
+            g.covar_flag = int(kind == 1)
+            g.min_vg_val = ctx['min_vg_val']
+            g.row_dst = d_row_dst.data_ptr()
+            g.out = out.data_ptr()
+            g.out_ld = ctx['fld_size']
+            g.out_f64 = ctx['out_f64']
+            g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+            g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            def _fast(vg_s):       # <= 2 Sph/Lin and <= 2 Exp/Gau terms plus nuggets
+                n_poly = n_exp = 0
+                for (t, _, _) in _lib.parse_vg_str(vg_s):
+                    if t in (2, 4):
+                        n_poly += 1
+                    elif t in (3, 5):
+                        n_exp += 1
+                    elif t != 1:
+                        return False
+                return n_poly <= 2 and n_exp <= 2
+            g.all_fast = int(all(_fast(vg_s) for vg_s in K.uniq_vgs))
+            with self._phase('multivg'):
+                _lib.check(self.lib.spx_estimate_multivg_dev(C.byref(g), self._stream()),
+                           'estimate_multivg')
+            self._count('launches')
+            self._count('multivg_evals', int(K.steps_o.size) * n_stn * n_cells)
+
+        # ---- main contraction: one launch per variogram segment ----------
+        for k in range(seg_vgs.size if not K.row_major else 0):
+            seg_coef = K.coef[seg_row0[k] * kpad:]
+            with self._phase('gemm'):
+                self._gemm(ctx, coef=seg_coef, n_rows=int(seg_cnt[k]), kpad=kpad,
+                           n_border=n_border, gen=_lib.GEN_VG, epi=_lib.EPI_FIELD,
+                           row_dst=d_row_dst[seg_row0[k]:], out=out,
+                           vg=_lib.make_vg(K.uniq_vgs[int(seg_vgs[k])]),
+                           covar_flag=int(kind == 1), cell_drift=K.d_cell_drift)
+
 
     # ---- pseudo-inverse path for numerically singular systems ---------------
     def _pinv_systems(self, ctx, out, K, sids, sv, v, coef_a):
@@ -1514,9 +1819,7 @@ class ChunkEngine:
         # Inverse of the full system of every variogram.  It depends on the station
         # set and the variogram only (not on the data), so it is kept across the
         # chunks of a job in a small cache.
-        base_key = (K.kind, K.n_drifts, ctx['min_vg_val'], ctx['stn_xs'].tobytes(),
-                    ctx['stn_ys'].tobytes(),
-                    None if K.d_stn_drift is None else ctx['stns_drft_bytes'])
+        base_key = self._ginv_key(ctx, K)
         ginv_of = {}
         need = []
         for v in vgs_here:

@@ -67,8 +67,8 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     sees them, equal the ctypes mirrors (a drifted mirror would corrupt arguments)."""
     import subprocess
     structs = {'spx_vg': 'ranges', 'spx_systems': 'max_m', 'spx_rhs': 'coef_row_major',
-               'spx_downdate': 'coef_row_major', 'spx_gemm': 'quad_slot',
-               'spx_multivg': 'all_fast', 'spx_local': 'rows_all_valid', 'spx_nrst': 'idw_exp'}
+               'spx_downdate': 'base_f', 'spx_dd_plan': 'n_bytes', 'spx_gemm': 'quad_slot',
+               'spx_multivg': 'all_fast', 'spx_local': 'slot', 'spx_nrst': 'idw_exp'}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "spx_b200.h"', 'int main(void){']
     for name, last in structs.items():
         src.append(f'printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {last}));')

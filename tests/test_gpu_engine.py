@@ -279,3 +279,105 @@ def test_local_estimator_is_used_and_matches_dense():
     for lab in ('OK', 'SK', 'EDK'):
         assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
         assert rel_err(got[lab], exp[lab], _floor(exp[lab])) <= KRG_TOL, lab
+
+
+@pytest.mark.parametrize('variant', ['local_f64', 'local_f32', 'dense', 'edk_two_vgs', 'flagged'])
+def test_native_planned_fast_path_matches_general_path(variant):
+    """Chunks after the first of a job (full-system inverse cached) are planned by the
+    native host planner and solved by one downdate launch per variogram that also emits
+    the local estimator's base / transposed coefficients (engine._krige_fast).  Same
+    numbers as the general NumPy-planned path and the oracle; repeated availability
+    patterns, a single-station step, a step without stations and a low-value step ride
+    along."""
+    from spinterps_b200.engine import ChunkEngine
+    n_steps = 40
+    p = make_problem(61, 130, n_steps, 45, 52, cell=4000.0, miss=0.15)
+    rng = np.random.default_rng(62)
+    data2 = rng.gamma(1.0, 5.0, size=p['data'].shape)
+    data2[rng.random(data2.shape) < 0.15] = np.nan
+    for t in (7, 8):                                               # same pattern as step 3
+        data2[t] = np.where(np.isnan(data2[3]), np.nan, rng.gamma(1.0, 5.0, size=data2.shape[1]))
+    data2[11, :] = np.nan
+    data2[11, 17] = 2.5                                            # single-station step
+    data2[12, :] = np.nan                                          # no station at all
+    data2[13] = np.where(np.isnan(data2[13]), np.nan, 0.01)        # below min_var_thr
+    vgs = [VG_C1] * n_steps
+    args = [('OK', None, 'OK')]
+    kw = dict(min_var_thr=0.1, min_var_cut=0.0)
+    dt = np.float64
+    local = True
+    if variant == 'local_f32':
+        dt = np.float32
+    elif variant == 'dense':
+        local = False
+    elif variant == 'flagged':
+        pass
+    elif variant == 'edk_two_vgs':
+        cx, cy = p['cell_xs'], p['cell_ys']
+        kw['drft_arrs'] = np.vstack([100 + 0.002 * cx + 0.001 * cy])
+        kw['stns_drft'] = np.column_stack([100 + 0.002 * p['stn_xs'] + 0.001 * p['stn_ys']])
+        args = [('EDK', None, 'EDK'), ('OK', None, 'OK')]
+        vgs = [VG_C1] * 20 + ['0.2 Nug(0.0) + 0.5 Sph(15000) + 0.3 Lin(30000)'] * 20
+    lambda_tol = None
+    if variant == 'flagged':
+        # a zero screening tolerance flags every system: the call is redone by the general
+        # path (exact per-cell sum(lambda) test)
+        lambda_tol = 0.0
+    kw.update(interp_args=args, vgs=vgs)
+    base = {k: v for k, v in p.items() if k != 'data'}
+
+    def run(native):
+        e = ChunkEngine()
+        e.local_support = local
+        e.native_plan = native
+        if lambda_tol is not None:
+            e.lambda_tol = lambda_tol
+        e.interp_chunk(p['data'], intrp_dtype=dt, **kw, **base)      # fills the caches
+        out, prob = e.interp_chunk(data2, intrp_dtype=dt, **kw, **base)
+        return e, out, prob
+
+    e1, got, prob1 = run(True)
+    e0, ref, prob0 = run(False)
+    assert e1.stats.get('native_plans', 0) >= 1 and e0.stats.get('native_plans', 0) == 0
+    assert prob1 == prob0 == [12]
+    if variant == 'flagged':
+        assert e1.stats.get('fast_path_redo', 0) + e1.stats.get('downdate_redo', 0) >= 1
+    else:
+        assert e1.stats.get('fast_path_redo', 0) + e1.stats.get('downdate_redo', 0) == 0
+    exp, _ = orc.interp_chunk(data2, intrp_dtype=np.float64, faithful=False, **kw, **base)
+    for lab in got:
+        assert np.array_equal(np.isnan(got[lab]), np.isnan(ref[lab])), lab
+        if dt == np.float32:
+            assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 3e-7, lab
+            assert rel_err(got[lab], exp[lab].astype(np.float32), _floor(exp[lab])) <= 3e-7, lab
+        elif variant == 'flagged':
+            assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-12, lab   # same path twice
+        else:
+            assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
+            assert rel_err(got[lab], exp[lab], _floor(exp[lab])) <= KRG_TOL, lab
+
+
+@pytest.mark.parametrize('n_stn,vg,note', [
+    (150, '0.1 Nug(0.0) + 0.9 Sph(20000)', 'few stations per tile: staged slices'),
+    (400, '0.1 Nug(0.0) + 0.9 Sph(45000)', '> 32 distinct stations per tile: global gathers'),
+])
+def test_local_kernel_tile_staging_is_bit_identical(n_stn, vg, note):
+    """The streamlined local kernel with the coefficient slices of a 256-cell tile staged
+    in shared memory (spx_local_tiles_dev) performs the same FMAs in the same order as the
+    variant that gathers from global memory: f32 fields must be identical bit for bit,
+    including tiles whose station list overflows (fallback inside the same kernel), a
+    ragged last tile and a ragged last row block."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(71, n_stn, 131, 61, 67, cell=3000.0, miss=0.1)
+    kw = dict(interp_args=[('OK', None, 'OK')], vgs=[vg] * 131, min_var_cut=0.0, **p)
+    outs = []
+    for tiles in (True, False):
+        e = ChunkEngine()
+        e.local_tiles = tiles
+        e.local_max_near = 64.0
+        got, _ = e.interp_chunk(intrp_dtype=np.float32, **kw)
+        assert e.stats.get('local_rows', 0) == 131
+        outs.append(got['OK'])
+    assert np.array_equal(outs[0], outs[1], equal_nan=True), note
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    assert rel_err(outs[0], exp['OK'].astype(np.float32), _floor(exp['OK'])) <= 3e-7

@@ -149,3 +149,127 @@ def test_main_configuration_surface(tmp_path):
     assert m._interp_crds_orig_shape[0] * m._interp_crds_orig_shape[1] == m._interp_x_crds_msh.size
     assert m._nc_y_crds[0] > m._nc_y_crds[-1]
     assert (tmp_path / 'o' / 'o.nc').exists()
+
+
+# ---- native host planner (csrc/spx_plan.cu) against the NumPy index logic ----------
+@pytest.mark.parametrize('seed,T,N,miss', [(0, 40, 7, 0.3), (1, 300, 65, 0.1), (2, 64, 128, 0.0),
+                                           (3, 500, 201, 0.02), (4, 50, 3, 0.7)])
+def test_native_avail_groups_match_numpy(seed, T, N, miss):
+    from spinterps_b200 import _lib
+    rng = np.random.default_rng(seed)
+    d = rng.gamma(1.0, 5.0, size=(T, N))
+    d[rng.random((T, N)) < miss] = np.nan
+    d[T // 2] = d[0]                       # a repeated availability pattern
+    if T > 45:
+        d[7] = np.nan                      # a step without stations
+    thr = 4.0
+    avail = ~np.isnan(d)
+    exp_gos, exp_mask = availability_groups(avail)
+    copy = np.full(T * N, -1.0)
+    gos, mask, grp_n, first, n_avail, flag = _lib.avail_groups(d, thr, data_copy=copy.ctypes.data)
+    assert np.array_equal(gos, exp_gos) and gos.dtype == np.int32
+    assert np.array_equal(mask, exp_mask) and mask.dtype == np.bool_
+    assert np.array_equal(grp_n, exp_mask.sum(axis=1))
+    assert np.array_equal(n_avail, avail.sum(axis=1))
+    assert all(gos[f] == g and not (gos[:f] == g).any() for g, f in enumerate(first))
+    with np.errstate(invalid='ignore'):
+        assert np.array_equal(flag, (np.where(avail, d, -np.inf) >= thr).any(axis=1))
+    assert np.array_equal(copy.reshape(T, N), d, equal_nan=True)
+    # -inf threshold: every step with a station passes; strided input (row pitch > N)
+    wide = np.full((T, N + 5), 7.0)
+    wide[:, :N] = d
+    gos2, mask2, _, _, n2, flag2 = _lib.avail_groups(wide[:, :N])
+    assert np.array_equal(gos2, exp_gos) and np.array_equal(mask2, exp_mask)
+    assert np.array_equal(flag2, n2 >= 1)
+    # packed words instead of byte masks
+    gos3, bits3, n3, _, _, _ = _lib.avail_groups(d, want_mask=False)
+    assert bits3.dtype == np.uint64 and bits3.shape == (exp_mask.shape[0], (N + 63) // 64)
+    assert np.array_equal(_lib.unpack_group_bits(bits3, N), exp_mask)
+    assert np.array_equal(gos3, exp_gos) and np.array_equal(n3, exp_mask.sum(axis=1))
+
+
+def _numpy_downdate_plan(grp_of_step, grp_mask, steps, rows):
+    """The index arrays engine._solve_downdate builds with NumPy (one variogram)."""
+    n_stn = grp_mask.shape[1]
+    grp_n = grp_mask.sum(axis=1)
+    grps = np.unique(grp_of_step[steps])
+    sys_of_row = np.searchsorted(grps, grp_of_step[steps])
+    r = (n_stn - grp_n[grps]).astype(np.int32)
+    ridx = np.argsort(sys_of_row, kind='stable')
+    cnt = np.bincount(sys_of_row, minlength=grps.size)
+    beg = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    nsys, n_data = grps.size, steps.size
+    rhs_off = beg + np.arange(nsys)
+    n_rhs = n_data + nsys
+    urow = np.empty(n_rhs, dtype=np.int32)
+    rrow = np.empty(n_rhs, dtype=np.int64)
+    rkind = np.zeros(n_rhs, dtype=np.int32)
+    pos_data = np.arange(n_data) + np.repeat(np.arange(nsys), cnt)
+    urow[pos_data] = np.arange(n_data)
+    rrow[pos_data] = rows[ridx]
+    pos_ones = rhs_off + cnt
+    urow[pos_ones] = n_data + np.arange(nsys)
+    rrow[pos_ones] = -1
+    rkind[pos_ones] = 1
+    return dict(
+        sys_grp=grps.astype(np.int32), sys_r=r, sys_n=grp_n[grps].astype(np.int32),
+        sys_miss_off=np.concatenate([[0], np.cumsum(r)])[:-1].astype(np.int64),
+        sys_stn_off=np.concatenate([[0], np.cumsum(grp_n[grps])])[:-1].astype(np.int64),
+        miss_list=np.concatenate([np.where(~grp_mask[g])[0] for g in grps] + [[]]).astype(np.int32),
+        stn_list=np.concatenate([np.where(grp_mask[g])[0] for g in grps] + [[]]).astype(np.int32),
+        sys_rhs_off=rhs_off.astype(np.int64), sys_rhs_cnt=(cnt + 1).astype(np.int32),
+        rhs_urow=urow, rhs_row=rrow, rhs_kind=rkind,
+        sys_order=np.argsort(-r, kind='stable').astype(np.int32),
+        bt_data_step=steps[ridx].astype(np.int32), pos_ones=pos_ones.astype(np.int64))
+
+
+@pytest.mark.parametrize('seed,T,N,miss', [(0, 60, 9, 0.3), (1, 400, 70, 0.05), (2, 30, 16, 0.0)])
+def test_native_downdate_plan_matches_numpy(seed, T, N, miss):
+    import ctypes as C
+    from spinterps_b200 import _lib
+    rng = np.random.default_rng(seed)
+    d = rng.gamma(1.0, 5.0, size=(T, N))
+    d[rng.random((T, N)) < miss] = np.nan
+    d[T // 3] = d[1]
+    d[T - 1] = d[1]
+    gos, mask, grp_n, _, n_avail, _ = _lib.avail_groups(d)
+    steps = np.where((n_avail >= 2) & (rng.random(T) < 0.8))[0].astype(np.int32)
+    rows = rng.permutation(steps.size).astype(np.int64)
+    exp = _numpy_downdate_plan(gos, mask, steps, rows)
+    lib = _lib.load()
+    nbytes = lib.spx_downdate_plan_host_bytes(steps.size)
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    plan = _lib.spx_dd_plan()
+    grp_n32 = grp_n.astype(np.int32)
+    _lib.check(lib.spx_downdate_plan_host(
+        gos.ctypes.data, grp_n32.ctypes.data, mask.shape[0], N,
+        steps.ctypes.data, rows.ctypes.data, steps.size, buf.ctypes.data, nbytes, C.byref(plan)))
+    assert plan.n_upload_bytes <= nbytes
+    assert plan.n_upload_bytes <= plan.n_bytes <= lib.spx_downdate_plan_bytes(steps.size, N)
+    # the device-filled station lists lie behind the uploaded prefix
+    assert min(plan.off_miss_list, plan.off_stn_list) >= plan.n_upload_bytes
+    assert plan.off_miss_list + 4 * plan.total_r <= plan.n_bytes
+    assert plan.off_stn_list + 4 * plan.total_n <= plan.n_bytes
+    ns, nd, nr = plan.n_sys, plan.n_data, plan.n_rhs
+    assert (ns, nd, nr) == (exp['sys_grp'].size, steps.size, steps.size + exp['sys_grp'].size)
+    assert plan.max_r == (int(exp['sys_r'].max()) if ns else 0)
+    assert plan.total_r == exp['miss_list'].size and plan.total_n == exp['stn_list'].size
+
+    def arr(name, dtype, n):
+        off = getattr(plan, 'off_' + name)
+        assert off % 16 == 0
+        return buf[off:off + n * np.dtype(dtype).itemsize].view(dtype)
+    for name, dtype, n in [('sys_grp', np.int32, ns), ('sys_r', np.int32, ns), ('sys_n', np.int32, ns),
+                           ('sys_miss_off', np.int64, ns), ('sys_stn_off', np.int64, ns),
+                           ('sys_rhs_off', np.int64, ns), ('sys_rhs_cnt', np.int32, ns),
+                           ('rhs_urow', np.int32, nr), ('rhs_row', np.int64, nr),
+                           ('rhs_kind', np.int32, nr), ('sys_order', np.int32, ns),
+                           ('pos_ones', np.int64, ns)]:
+        assert np.array_equal(arr(name, dtype, n), exp[name]), name
+    bt = arr('bt_step', np.int32, nr)
+    assert np.array_equal(bt[:nd], exp['bt_data_step'])
+    assert np.array_equal(gos[bt[nd:]], exp['sys_grp'])      # any step of the system's group
+    # too small a buffer is refused
+    assert lib.spx_downdate_plan_host(
+        gos.ctypes.data, grp_n32.ctypes.data, mask.shape[0], N,
+        steps.ctypes.data, rows.ctypes.data, steps.size, buf.ctypes.data, 64, C.byref(plan)) != 0
