@@ -1071,7 +1071,15 @@ constexpr int LOC_SLD = 130;    // row pitch of a staged coefficient slice (128 
 
 template <bool SM>
 __device__ __forceinline__ double2 ld_coef2(const double* p) {
-    if (SM) return *reinterpret_cast<const double2*>(p);
+    if (SM) {
+        // the pointer is known to be a shared-memory address only at run time: spell the
+        // state space out, otherwise the compiler emits generic loads (LD.E, not LDS)
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                     : "=d"(v.x), "=d"(v.y)
+                     : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
     return __ldg(reinterpret_cast<const double2*>(p));
 }
 
@@ -1173,58 +1181,89 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
 // shared-memory load: no L1 misses, a fraction of the latency of the global gathers
 // the untiled variant waits on.
 template <bool CLAMP, int ROWS, int CPT, bool TILE>
-__global__ void __launch_bounds__(256) k_estimate_local_fast(LocalEstArgs a) {
+__global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) {
     __shared__ __align__(16) double sbase[ROWS];
     __shared__ __align__(16) int64_t soff[ROWS];
     __shared__ __align__(16) double sct[TILE ? SPX_LOCAL_TILE_CAP * LOC_SLD : 2];
     static_assert(!TILE || (CPT == 1 && ROWS == 128), "tile variant: 256 cells x 128 rows");
+    const int tid = threadIdx.x;
     const int64_t r_beg = (int64_t)blockIdx.y * ROWS;
     const int nr = (int)min((int64_t)ROWS, a.n_rows - r_beg);
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
-        sbase[i] = a.base[r_beg + i];
-        soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
-    }
     const double* ct = a.coef_t + r_beg;
-    bool staged = false;
-    if (TILE) {
-        const int U = a.tile_cnt[blockIdx.x];
-        staged = U >= 0;                         // block-uniform
-        if (staged) {
-            const int32_t* __restrict__ tl = a.tile_stn + (int64_t)blockIdx.x * SPX_LOCAL_TILE_CAP;
-            const int r_lim = (int)min((int64_t)ROWS, a.coef_t_ld - r_beg);   // even
-            for (int i = threadIdx.x; i < U * (ROWS / 2); i += blockDim.x) {
-                const int s = i / (ROWS / 2), r2 = 2 * (i - s * (ROWS / 2));
-                if (r2 < r_lim)
-                    *reinterpret_cast<double2*>(sct + s * LOC_SLD + r2) = __ldg(
-                        reinterpret_cast<const double2*>(ct + (int64_t)tl[s] * a.coef_t_ld + r2));
-            }
-        }
-    }
-    __syncthreads();
-    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
-    if (c0 >= a.n_cells) return;                 // no further block-wide barrier below
+    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + tid) * CPT;
     const bool pair = (CPT == 2) && (c0 + 1 < a.n_cells);
-    int n[CPT];
-    const double* p0[CPT];
-    const double* p1[CPT];
+    // A block lives for only ROWS / 4 loop iterations, so the latency of its prologue
+    // matters: every table entry it may need is requested up front, unconditionally and
+    // independently (entries j >= cnt are unspecified and masked after arrival), instead
+    // of as a chain  cnt -> slot / val,  tile_cnt -> tile_stn -> slices.
+    int n[CPT], t0[CPT], t1[CPT];
     double v0[CPT], v1[CPT];
-    int nloc = 0;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
         const int64_t c = min(c0 + q, a.n_cells - 1);
-        n[q] = (q == 0 || pair) ? min(a.cnt[c], a.cap) : 0;
-        v0[q] = (0 < n[q]) ? a.val[c] : 0.0;
-        v1[q] = (1 < n[q]) ? a.val[a.n_cells + c] : 0.0;
+        n[q] = a.cnt[c];
+        t0[q] = TILE ? (int)a.slot[c] : a.idx[c];
+        t1[q] = TILE ? (int)a.slot[a.n_cells + c] : a.idx[a.n_cells + c];
+        v0[q] = a.val[c];
+        v1[q] = a.val[a.n_cells + c];
+    }
+    bool staged = false;
+    if (TILE) {
+        constexpr int SPT = SPX_LOCAL_TILE_CAP / 4;      // slices per thread (4 per pass)
+        const int32_t* __restrict__ tl = a.tile_stn + (int64_t)blockIdx.x * SPX_LOCAL_TILE_CAP;
+        const int U = a.tile_cnt[blockIdx.x];
+        int stn[SPT];
+#pragma unroll
+        for (int it = 0; it < SPT; ++it) stn[it] = tl[(tid >> 6) + 4 * it];
+        staged = U >= 0;                         // block-uniform
+        const int r2 = 2 * (tid & 63);
+        const int r_lim = (int)min((int64_t)ROWS, a.coef_t_ld - r_beg);   // even
+        double2 g[SPT];
+#pragma unroll
+        for (int it = 0; it < SPT; ++it) {
+            const int sl = (tid >> 6) + 4 * it;
+            if (sl < U && r2 < r_lim)
+                g[it] = __ldg(reinterpret_cast<const double2*>(
+                    ct + (int64_t)stn[it] * a.coef_t_ld + r2));
+        }
+        for (int i = tid; i < nr; i += 256) {
+            sbase[i] = a.base[r_beg + i];
+            soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
+        }
+#pragma unroll
+        for (int it = 0; it < SPT; ++it) {
+            const int sl = (tid >> 6) + 4 * it;
+            if (sl < U && r2 < r_lim)
+                *reinterpret_cast<double2*>(sct + sl * LOC_SLD + r2) = g[it];
+        }
+    } else {
+        for (int i = tid; i < nr; i += blockDim.x) {
+            sbase[i] = a.base[r_beg + i];
+            soff[i] = (int64_t)a.row_dst[r_beg + i] * a.out_ld;
+        }
+    }
+    __syncthreads();
+    if (c0 >= a.n_cells) return;                 // no further block-wide barrier below
+    const double* p0[CPT];
+    const double* p1[CPT];
+    int nloc = 0;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        n[q] = (q == 0 || pair) ? min(n[q], a.cap) : 0;
+        v0[q] = (0 < n[q]) ? v0[q] : 0.0;
+        v1[q] = (1 < n[q]) ? v1[q] : 0.0;
         if (TILE && staged) {
-            const int s0 = (0 < n[q]) ? a.slot[c] : 0;
-            const int s1 = (1 < n[q]) ? a.slot[a.n_cells + c] : 0;
-            p0[q] = sct + s0 * LOC_SLD;
-            p1[q] = sct + s1 * LOC_SLD;
+            p0[q] = sct + ((0 < n[q]) ? t0[q] : 0) * LOC_SLD;
+            p1[q] = sct + ((1 < n[q]) ? t1[q] : 0) * LOC_SLD;
         } else {
-            const int i0 = (0 < n[q]) ? a.idx[c] : 0;
-            const int i1 = (1 < n[q]) ? a.idx[a.n_cells + c] : 0;
-            p0[q] = ct + (int64_t)i0 * a.coef_t_ld;
-            p1[q] = ct + (int64_t)i1 * a.coef_t_ld;
+            int i0 = t0[q], i1 = t1[q];
+            if (TILE) {                          // overflowing tile: station ids instead of slots
+                const int64_t c = min(c0 + q, a.n_cells - 1);
+                i0 = a.idx[c];
+                i1 = a.idx[a.n_cells + c];
+            }
+            p0[q] = ct + (int64_t)((0 < n[q]) ? i0 : 0) * a.coef_t_ld;
+            p1[q] = ct + (int64_t)((1 < n[q]) ? i1 : 0) * a.coef_t_ld;
         }
         nloc = max(nloc, n[q]);
     }

@@ -359,7 +359,7 @@ def test_native_planned_fast_path_matches_general_path(variant):
 
 @pytest.mark.parametrize('n_stn,vg,note', [
     (150, '0.1 Nug(0.0) + 0.9 Sph(20000)', 'few stations per tile: staged slices'),
-    (400, '0.1 Nug(0.0) + 0.9 Sph(45000)', '> 32 distinct stations per tile: global gathers'),
+    (400, '0.1 Nug(0.0) + 0.9 Sph(40000)', '> 32 distinct stations per tile: global gathers'),
 ])
 def test_local_kernel_tile_staging_is_bit_identical(n_stn, vg, note):
     """The streamlined local kernel with the coefficient slices of a 256-cell tile staged
