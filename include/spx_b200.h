@@ -598,6 +598,28 @@ int spx_local_build_dev(const spx_local* l, void* stream);
 int spx_local_tiles_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
 
+/* ---- grid preparation ---------------------------------------------
+ * Points (cells, stations) inside or within buffer_dist of polygons given as outer rings
+ * (misc.py:407-540 chk_pt_cntmnt_in_polys_mp: OGR Contains on polygons buffered by the
+ * station / cell buffer distance, one Python call per point).  Edges (x1, y1) -> (x2, y2)
+ * of all rings, ering = ring id of each edge, non-decreasing; even-odd rule per ring,
+ * union over rings; with buffer_dist > 0 also every point closer than buffer_dist to an
+ * edge.  chunk_ymin / chunk_ymax (optional, both or neither): y-range of every chunk of
+ * spx_points_in_polygons_chunk() consecutive edges, used to skip chunks that cannot touch
+ * a block of points.  inside [n_pts] 0 / 1. */
+int spx_points_in_polygons_dev(const double* px, const double* py, int64_t n_pts,
+                               const double* ex1, const double* ey1, const double* ex2,
+                               const double* ey2, const int32_t* ering, int64_t n_edges,
+                               const double* chunk_ymin, const double* chunk_ymax,
+                               double buffer_dist, uint8_t* inside, void* stream);
+int spx_points_in_polygons_chunk(void);
+/* out[i] = ras[rows[i], cols[i]] of a row-major [n_rows, n_cols] raster; NaN where the value
+ * is np.isclose to the no-data value (has_ndv) or the index lies outside the raster
+ * (interp/drift.py:165-226: drift values at cells and stations). */
+int spx_sample_raster_dev(const double* ras, int64_t n_rows, int64_t n_cols, const int64_t* rows,
+                          const int64_t* cols, int64_t n, double ndv, int32_t has_ndv,
+                          double* out, void* stream);
+
 /* Host -> device copy of n_bytes on `stream` (cudaMemcpyAsync; from pageable memory the call
  * returns once the source has been staged).  The engine's small per-chunk uploads go
  * through this on a dedicated upload stream. */

@@ -729,3 +729,55 @@ def interp_chunk(
         assert np.all(pts_done), 'Some points not interpolated!'
 
     return flds, prblm_steps
+
+
+# ---------------------------------------------------------------------------
+# Grid preparation.  PARITY UNPINNED for this part: the reference
+# does it with OGR / GDAL (misc.py:407-540 ``chk_pt_cntmnt_in_polys_mp`` = Contains on
+# polygons buffered with geom.Buffer, interp/drift.py:165-226), which are absent from the
+# build container, so no reference output could be generated.  The functions below are
+# the checker for the CUDA kernels: the same formulas in plain NumPy (IEEE operations in
+# the same order, no FMA), pinned only by hand-made known answers in the tests.
+# ---------------------------------------------------------------------------
+def points_in_polygons(xs, ys, rings, buffer_dist=0.0):
+    """bool [n]: inside any ring by the even-odd crossing rule, or (buffer_dist > 0)
+    closer than buffer_dist to a ring edge."""
+    xs = np.asarray(xs, dtype=np.float64).ravel()
+    ys = np.asarray(ys, dtype=np.float64).ravel()
+    inside = np.zeros(xs.size, dtype=bool)
+    buf2 = np.float64(buffer_dist) * np.float64(buffer_dist)
+    for ring in rings:
+        r = np.asarray(ring, dtype=np.float64)
+        if r.shape[0] >= 2 and np.array_equal(r[0], r[-1]):
+            r = r[:-1]
+        nxt = np.roll(r, -1, axis=0)
+        parity = np.zeros(xs.size, dtype=bool)
+        for (ax, ay), (bx, by) in zip(r, nxt):
+            dx, dy = bx - ax, by - ay
+            strad = (ay > ys) != (by > ys)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                xi = dx * (ys - ay) / dy + ax
+            parity ^= strad & (xs < xi)
+            if buffer_dist > 0:
+                wx, wy = xs - ax, ys - ay
+                l2 = dx * dx + dy * dy
+                t = (wx * dx + wy * dy) / l2 if l2 > 0 else np.zeros_like(wx)
+                t = np.minimum(np.maximum(t, 0.0), 1.0)
+                qx, qy = wx - t * dx, wy - t * dy
+                inside |= (qx * qx + qy * qy) < buf2
+        inside |= parity
+    return inside
+
+
+def sample_raster(ras, rows, cols, ndv=None):
+    """interp/drift.py:190-198, :209-221: raster values at (row, col), no-data -> NaN."""
+    ras = np.asarray(ras, dtype=np.float64)
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    ok = (rows >= 0) & (rows < ras.shape[0]) & (cols >= 0) & (cols < ras.shape[1])
+    out = np.full(rows.shape, np.nan)
+    out[ok] = ras[rows[ok], cols[ok]]
+    if ndv is not None:
+        with np.errstate(invalid='ignore'):
+            out[np.isclose(ndv, out)] = np.nan
+    return out

@@ -244,6 +244,14 @@ _SIGS = {
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_int32, C.c_void_p]),
     'spx_copy_to_mapped_host_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'spx_points_in_polygons_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_void_p, C.c_void_p]),
+    'spx_points_in_polygons_chunk': (C.c_int, []),
+    'spx_sample_raster_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_double, C.c_int32, C.c_void_p,
+                                        C.c_void_p]),
     'spx_upload_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'spx_round_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),
     'spx_round_stats_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,

@@ -17,7 +17,7 @@ CSRC = PKG / 'csrc'
 LIBDIR = PKG / 'lib'
 LIB = LIBDIR / 'libspx_b200.so'
 SOURCES = ['spx_basic.cu', 'spx_solve.cu', 'spx_gemm.cu', 'spx_misc.cu', 'spx_nrst.cu',
-           'spx_plan.cu']
+           'spx_plan.cu', 'spx_prep.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default',

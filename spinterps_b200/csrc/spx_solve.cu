@@ -639,6 +639,96 @@ struct DdShared {
     double s_sgn;
 };
 
+// Scale row k1 (slot A1 of warp k1 % 16) by 1 / pivot, publish it and column k1 (register
+// column kb1 = A1 / 2 of lane k1 % 32 in every warp) into buffer `buf`; the column is
+// replaced by zeros except for the pivot, which becomes 1 / pivot (in-place inverse).
+template <int TA, int TB, int A1>
+__device__ __forceinline__ void dd_publish(double (&S)[TA][TB], DdShared& sm, int k1, int buf,
+                                           int wid, int lane) {
+    constexpr int kb1 = A1 >> 1;
+    const int kl1 = k1 & 31;
+    const bool prow = wid == (k1 & 15);
+    if (prow) {
+        const double pvv = __shfl_sync(0xffffffffu, S[A1][kb1], kl1);
+        const double inv = (pvv != 0.0) ? 1.0 / pvv : 1.0;
+        if (lane == 0) {
+            if (k1 == 0) sm.s_sgn = pvv;
+            const double sg = (k1 == 0) ? pvv : sm.s_sgn;
+            if (!(pvv * sg > 0.0) || !(fabs(pvv) < 1.0e300)) sm.s_fail = 1;
+        }
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            const double v = (b == kb1 && lane == kl1) ? inv : S[A1][b] * inv;
+            S[A1][b] = v;
+            sm.rowbuf[buf][lane + 32 * b] = v;
+        }
+    }
+    if (lane == kl1) {
+#pragma unroll
+        for (int a = 0; a < TA; ++a) {
+            const bool piv = prow && a == A1;
+            sm.colbuf[buf][wid + 16 * a] = piv ? 0.0 : S[a][kb1];
+            if (!piv) S[a][kb1] = 0.0;
+        }
+    }
+}
+
+// Elimination step k with look-ahead (A1 = register slot of row k + 1, -1 = none).
+template <int TA, int TB, int A1>
+__device__ __forceinline__ void dd_step(double (&S)[TA][TB], DdShared& sm, int k, int r, int wid,
+                                        int lane) {
+    const int cur = k & 1;
+    double u[TB], f[TA];
+#pragma unroll
+    for (int b = 0; b < TB; ++b) u[b] = sm.rowbuf[cur][lane + 32 * b];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) f[a] = sm.colbuf[cur][wid + 16 * a];
+    if (A1 >= 0) {
+        constexpr int A1c = A1 >= 0 ? A1 : 0;
+        constexpr int kb1 = A1c >> 1;
+        const int k1 = k + 1;
+        const bool nrow = wid == (k1 & 15);
+#pragma unroll
+        for (int a = 0; a < TA; ++a) S[a][kb1] = fma(-f[a], u[kb1], S[a][kb1]);
+        if (nrow) {
+#pragma unroll
+            for (int b = 0; b < TB; ++b)
+                if (b != kb1) S[A1c][b] = fma(-f[A1c], u[b], S[A1c][b]);
+        }
+        if (k1 < r) dd_publish<TA, TB, A1c>(S, sm, k1, cur ^ 1, wid, lane);
+#pragma unroll
+        for (int a = 0; a < TA; ++a) {
+            if (a == A1c && nrow) continue;
+#pragma unroll
+            for (int b = 0; b < TB; ++b)
+                if (b != kb1) S[a][b] = fma(-f[a], u[b], S[a][b]);
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < TA; ++a)
+#pragma unroll
+            for (int b = 0; b < TB; ++b) S[a][b] = fma(-f[a], u[b], S[a][b]);
+    }
+    __syncthreads();
+}
+
+// Columns 16 A0 .. 16 A0 + 15 (pivot rows in register slot A0), then the next slot.
+template <int TA, int TB, int A0>
+__device__ __forceinline__ void dd_sweep(double (&S)[TA][TB], DdShared& sm, int r, int wid,
+                                         int lane) {
+    if constexpr (A0 < TA) {
+#pragma unroll 1
+        for (int w = 0; w < 15; ++w) {           // rows 16 A0 + w + 1 share the slot A0
+            const int k = 16 * A0 + w;
+            if (k >= r) break;
+            dd_step<TA, TB, A0>(S, sm, k, r, wid, lane);
+        }
+        const int k = 16 * A0 + 15;              // the next row lives in slot A0 + 1
+        if (k < r) dd_step<TA, TB, (A0 + 1 < TA ? A0 + 1 : -1)>(S, sm, k, r, wid, lane);
+        dd_sweep<TA, TB, A0 + 1>(S, sm, r, wid, lane);
+    }
+}
+
 template <int TA, int TB>
 __device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShared& sm, int sys,
                                                   int r, int force_pivot) {
@@ -690,51 +780,14 @@ __device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShare
     if (tid == 0) s_fail = force_pivot;
     __syncthreads();
     if (!force_pivot) {
-#pragma unroll
-        for (int a0 = 0; a0 < TA; ++a0) {
-                        const int kb = a0 >> 1;          // 32-column slot of columns 16 a0 .. 16 a0 + 15
-#pragma unroll 1
-            for (int w = 0; w < 16; ++w) {
-                const int k = 16 * a0 + w;
-                if (k >= r) break;
-                const int cur = k & 1, kl = k & 31;
-                const bool prow = wid == w;
-                if (prow) {
-                    const double pvv = __shfl_sync(0xffffffffu, S[a0][kb], kl);
-                    const double inv = (pvv != 0.0) ? 1.0 / pvv : 1.0;
-                    if (lane == 0) {
-                        if (k == 0) s_sgn = pvv;
-                        const double sg = (k == 0) ? pvv : s_sgn;
-                        if (!(pvv * sg > 0.0) || !(fabs(pvv) < 1.0e300)) s_fail = 1;
-                    }
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        const double v = (b == kb && lane == kl) ? inv : S[a0][b] * inv;
-                        S[a0][b] = v;
-                        rowbuf[cur][lane + 32 * b] = v;
-                    }
-                }
-                if (lane == kl) {
-#pragma unroll
-                    for (int a = 0; a < TA; ++a) {
-                        const bool piv = prow && a == a0;
-                        colbuf[cur][wid + 16 * a] = piv ? 0.0 : S[a][kb];
-                        if (!piv) S[a][kb] = 0.0;
-                    }
-                }
-                __syncthreads();
-                double u[TB];
-#pragma unroll
-                for (int b = 0; b < TB; ++b) u[b] = rowbuf[cur][lane + 32 * b];
-#pragma unroll
-                for (int a = 0; a < TA; ++a) {
-                    const double f = colbuf[cur][wid + 16 * a];
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) S[a][b] = fma(-f, u[b], S[a][b]);
-                }
-            }
-        }
+        // Look-ahead: step k first brings row k + 1 and column k + 1 up to date, scales /
+        // publishes them for the next step (shuffle, division, shared-memory stores: the
+        // latency chain of the elimination) and only then applies the bulk of its rank-1
+        // update, so that the chain of step k + 1 hides behind the DFMAs of step k.  Every
+        // element still receives the same FMAs in the same order as without look-ahead.
+        dd_publish<TA, TB, 0>(S, sm, 0, 0, wid, lane);
         __syncthreads();
+        dd_sweep<TA, TB, 0>(S, sm, r, wid, lane);
     }
     const bool pivoted = s_fail != 0;
     if (pivoted) {

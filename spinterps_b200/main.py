@@ -21,7 +21,7 @@ flags.  Differences, all forced by what exists in this image:
 from __future__ import annotations
 
 import timeit
-from math import ceil
+from math import ceil, floor
 from pathlib import Path
 from threading import Lock
 
@@ -83,6 +83,7 @@ class SpInterpMain:
         self._max_steps_per_chunk = None
         self._min_vg_val = 0.0
         self._cell_mask_src = None
+        self._poly_rings = None
 
         self._vg_ser_set_flag = False
         self._out_dir_set_flag = False
@@ -258,6 +259,41 @@ class SpInterpMain:
                 'set_cell_selection_mask(mask_or_callable, cell_buffer_distance) instead') from exc
         raise NotImplementedError('polygon rasterisation is outside the hot path (SURVEY 8f-4)')
 
+    def set_cell_selection_polygons(self, polygons, station_select_buffer_distance,
+                                    interp_around_polys_flag=True,
+                                    polygon_cell_buffer_distance=None):
+        """``set_cell_selection_parameters`` (interp/data.py:349-461) with the polygons
+        given as arrays -- a list of (n, 2) outer rings -- instead of a shapefile.  Same
+        meaning of the other arguments: stations within ``station_select_buffer_distance``
+        of the polygons are kept (interp/bdpolys.py:80-170); with
+        ``interp_around_polys_flag`` only cells inside or within
+        ``polygon_cell_buffer_distance`` of a polygon are interpolated
+        (interp/prepare.py:244-288); the grid spans the polygons' extent +- that distance
+        (interp/prepare.py:107-137).  Containment runs on the GPU (prep.points_in_polygons).
+        The reference buffers with OGR (arcs of 30 segments per quadrant); here the exact
+        distance is used."""
+        rings = [np.asarray(r, dtype=np.float64) for r in polygons]
+        assert rings, 'Zero polygons in the polygons_shapefile!'
+        for r in rings:
+            assert r.ndim == 2 and r.shape[1] == 2 and r.shape[0] >= 3, (
+                f'Polygon not having enough points ({r.shape[0]})!')
+        assert isinstance(station_select_buffer_distance, (float, int)), (
+            'station_select_buffer_distance not a float or an int!')
+        assert 0 <= station_select_buffer_distance < np.inf, (
+            'station_select_buffer_distance not in between zero and infinity!')
+        assert isinstance(interp_around_polys_flag, bool), (
+            'interp_around_polys_flag not a boolean!')
+        if interp_around_polys_flag or polygon_cell_buffer_distance is not None:
+            assert isinstance(polygon_cell_buffer_distance, (float, int)), (
+                'polygon_cell_buffer_distance not a float or an int!')
+            assert 0 <= polygon_cell_buffer_distance < np.inf, (
+                'polygon_cell_buffer_distance not in between zero and infinity!')
+        self._poly_rings = rings
+        self._stn_bdist = float(station_select_buffer_distance)
+        self._ipoly_flag = interp_around_polys_flag
+        self._cell_bdist = float(polygon_cell_buffer_distance or 0.0)
+        self._cell_sel_prms_set = True
+
     def set_cell_selection_mask(self, mask, polygon_cell_buffer_distance=0.0):
         """Array-level replacement of the polygon cell selection
         (interp/prepare.py:244-288 produces exactly such a boolean ``_cntn_idxs``).
@@ -360,6 +396,16 @@ class SpInterpMain:
             if callable(dr):
                 rass.append(dr)
                 continue
+            if isinstance(dr, dict):
+                # array raster: values [rows, cols] (row 0 = north), corner and cell size,
+                # optional no-data value -- what interp/drift.py:25-163 reads from a GeoTIFF
+                assert {'values', 'x_min', 'y_max', 'cell_size'} <= set(dr), (
+                    'array drift raster needs values, x_min, y_max, cell_size')
+                vals = np.ascontiguousarray(dr['values'], dtype=np.float64)
+                assert vals.ndim == 2
+                rass.append(dict(values=vals, x_min=float(dr['x_min']), y_max=float(dr['y_max']),
+                                 cell_size=float(dr['cell_size']), ndv=dr.get('ndv')))
+                continue
             assert isinstance(dr, (str, Path)), (
                 'Supplied drift raster path is not a string or a pathlib.Path object!')
             raise ImportError('reading drift rasters needs GDAL; pass callables f(x, y) instead')
@@ -439,10 +485,26 @@ class SpInterpMain:
         # grid: interp/prepare.py:92-242
         assert self._cell_size is not None, 'Cell size unspecified!'
         cs = self._cell_size
-        x_min = self._crds_df['X'].min() - self._cell_bdist
-        x_max = self._crds_df['X'].max() + self._cell_bdist
-        y_min = self._crds_df['Y'].min() - self._cell_bdist
-        y_max = self._crds_df['Y'].max() + self._cell_bdist
+        if self._poly_rings is not None:
+            # stations near the polygons (interp/bdpolys.py:80-170), grid bounds from the
+            # polygons' extent (interp/prepare.py:107-137)
+            from . import prep
+            keep = prep.points_in_polygons(self._crds_df['X'].values, self._crds_df['Y'].values,
+                                           self._poly_rings, self._stn_bdist)
+            assert keep.any(), 'Found zero stations that are close enough to the polygons!'
+            fin_stns = self._crds_df.index[keep]
+            self._crds_df = self._crds_df.loc[fin_stns]
+            self._data_df = self._data_df.loc[:, self._data_df.columns.intersection(fin_stns)]
+            allv = np.concatenate(self._poly_rings, axis=0)
+            x_min, x_max = allv[:, 0].min(), allv[:, 0].max()
+            y_min, y_max = allv[:, 1].min(), allv[:, 1].max()
+        else:
+            x_min, x_max = self._crds_df['X'].min(), self._crds_df['X'].max()
+            y_min, y_max = self._crds_df['Y'].min(), self._crds_df['Y'].max()
+        x_min -= self._cell_bdist
+        x_max += self._cell_bdist
+        y_min -= self._cell_bdist
+        y_max += self._cell_bdist
         self._x_min, self._x_max, self._y_min, self._y_max = x_min, x_max, y_min, y_max
         max_col = int(ceil((x_max - x_min) / cs)) - 1
         max_row = int(ceil((y_max - y_min) / cs)) - 1
@@ -458,7 +520,14 @@ class SpInterpMain:
 
         # cell mask: interp/prepare.py:244-288
         self._cntn_idxs = None
-        if self._cell_mask_src is not None:
+        if self._poly_rings is not None and self._ipoly_flag:
+            from . import prep
+            m = prep.points_in_polygons(full_x, full_y, self._poly_rings, self._cell_bdist)
+            assert m.sum(), 'No cells selected for interpolation!'
+            self._interp_x_crds_msh = full_x[m]
+            self._interp_y_crds_msh = full_y[m]
+            self._cntn_idxs = m
+        elif self._cell_mask_src is not None:
             m = self._cell_mask_src
             m = np.asarray(m(full_x, full_y) if callable(m) else m, dtype=bool).ravel()
             assert m.shape == full_x.shape, 'cell mask does not match the grid!'
@@ -473,13 +542,33 @@ class SpInterpMain:
 
         # drift: interp/drift.py:25-226 reduced to sampling callables
         if self._edk_flag:
-            self._drft_arrs = np.vstack([
-                np.asarray(f(self._interp_x_crds_msh, self._interp_y_crds_msh), dtype=np.float64)
-                for f in self._drft_rass])
             sx, sy = self._crds_df['X'].values, self._crds_df['Y'].values
-            self._stns_drft_df = pd.DataFrame(
-                np.column_stack([np.asarray(f(sx, sy), dtype=np.float64)
-                                 for f in self._drft_rass]), index=self._crds_df.index)
+            cell_rows, stn_cols = [], []
+            for f in self._drft_rass:
+                if callable(f):
+                    cell_rows.append(np.asarray(
+                        f(self._interp_x_crds_msh, self._interp_y_crds_msh), dtype=np.float64))
+                    stn_cols.append(np.asarray(f(sx, sy), dtype=np.float64))
+                    continue
+                # array raster sampled on the GPU: interp/drift.py:165-226 (cells through
+                # the row / column window of interp/prepare.py:150-172, stations through
+                # int((x - x_min) / cell), int((y_max - y) / cell))
+                from . import prep
+                assert np.isclose(f['cell_size'], cs), 'Drift raster cell size != grid cell size!'
+                assert x_min >= f['x_min'] and y_max <= f['y_max'], (
+                    'Grid outside of the drift rasters!')
+                nr, nc = f['values'].shape
+                assert x_max <= f['x_min'] + nc * cs and y_min >= f['y_max'] - nr * cs, (
+                    'Grid outside of the drift rasters!')
+                min_col = int(floor((x_min - f['x_min']) / cs))
+                min_row = int(floor((f['y_max'] - y_max) / cs))
+                rr, cc = prep.drift_cell_indices(min_row, min_row + max_row, min_col,
+                                                 min_col + max_col, self._cntn_idxs)
+                cell_rows.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
+                rr, cc = prep.drift_point_indices(sx, sy, f['x_min'], f['y_max'], cs)
+                stn_cols.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
+            self._drft_arrs = np.vstack(cell_rows)
+            self._stns_drft_df = pd.DataFrame(np.column_stack(stn_cols), index=self._crds_df.index)
             fin = np.isfinite(self._stns_drft_df.values).all(axis=1)
             self._stns_drft_df = self._stns_drft_df.loc[fin]
 

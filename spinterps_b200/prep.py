@@ -1,0 +1,114 @@
+"""Grid preparation on the GPU.
+
+* ``points_in_polygons``: which cells / stations lie inside or within a buffer distance of
+  the selection polygons -- the reference buffers the polygons with OGR and calls
+  ``Contains`` once per point from Python (misc.py:407-540 ``chk_pt_cntmnt_in_polys_mp``,
+  used by interp/bdpolys.py:148 for stations and interp/prepare.py:266 for cells).
+* ``sample_raster`` / ``drift_at_cells`` / ``drift_at_points``: drift values at cells and
+  stations (interp/drift.py:165-226).
+
+Polygons are passed as arrays (outer rings); reading shapefiles / GeoTIFFs needs GDAL,
+which is outside this path.  torch is used for device memory only; no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _to_dev(a, dev):
+    if not a.flags.writeable:          # e.g. a read-only pandas view
+        a = a.copy()
+    return torch.from_numpy(a).to(dev)
+
+
+def rings_to_edges(rings):
+    """[(n_i, 2) outer rings] -> edge arrays x1, y1, x2, y2 (float64), ring id per edge
+    (int32, non-decreasing).  A ring is closed implicitly (last -> first vertex); a
+    repeated closing vertex just adds a zero-length edge, which is skipped."""
+    x1, y1, x2, y2, rid = [], [], [], [], []
+    for k, ring in enumerate(rings):
+        r = np.asarray(ring, dtype=np.float64)
+        assert r.ndim == 2 and r.shape[1] == 2, 'a ring is an (n, 2) array of x, y'
+        if r.shape[0] >= 2 and np.array_equal(r[0], r[-1]):
+            r = r[:-1]
+        assert r.shape[0] >= 3, f'Polygon not having enough points ({r.shape[0]})!'  # misc.py:415
+        nxt = np.roll(r, -1, axis=0)
+        x1.append(r[:, 0]); y1.append(r[:, 1]); x2.append(nxt[:, 0]); y2.append(nxt[:, 1])
+        rid.append(np.full(r.shape[0], k, dtype=np.int32))
+    cat = lambda v, dt: np.ascontiguousarray(np.concatenate(v), dtype=dt)  # noqa: E731
+    return (cat(x1, np.float64), cat(y1, np.float64), cat(x2, np.float64), cat(y2, np.float64),
+            cat(rid, np.int32))
+
+
+def points_in_polygons(xs, ys, rings, buffer_dist=0.0, device=None):
+    """bool [n]: point inside any ring (even-odd rule) or, with buffer_dist > 0, closer than
+    buffer_dist to any ring edge.  One kernel launch over all points
+    (spx_points_in_polygons_dev); the oracle states the same arithmetic in NumPy."""
+    _lib.require_gpu()
+    lib = _lib.load()
+    xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+    ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+    assert xs.shape == ys.shape
+    assert np.isfinite(buffer_dist) and buffer_dist >= 0
+    ex1, ey1, ex2, ey2, rid = rings_to_edges(rings)
+    ch = lib.spx_points_in_polygons_chunk()
+    n_e = ex1.size
+    starts = np.arange(0, n_e, ch)
+    cymin = np.minimum(np.minimum.reduceat(ey1, starts), np.minimum.reduceat(ey2, starts))
+    cymax = np.maximum(np.maximum.reduceat(ey1, starts), np.maximum.reduceat(ey2, starts))
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+    with torch.cuda.device(dev):
+        t = [_to_dev(a, dev) for a in (xs, ys, ex1, ey1, ex2, ey2, rid, cymin, cymax)]
+        out = torch.empty(xs.size, dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.spx_points_in_polygons_dev(
+            t[0].data_ptr(), t[1].data_ptr(), xs.size, t[2].data_ptr(), t[3].data_ptr(),
+            t[4].data_ptr(), t[5].data_ptr(), t[6].data_ptr(), n_e, t[7].data_ptr(),
+            t[8].data_ptr(), float(buffer_dist), out.data_ptr(), st), 'points_in_polygons')
+        return out.cpu().numpy().astype(bool)
+
+
+def sample_raster(ras, rows, cols, ndv=None, device=None):
+    """ras[rows, cols] with no-data (np.isclose to ndv) and out-of-raster -> NaN."""
+    _lib.require_gpu()
+    lib = _lib.load()
+    ras = np.ascontiguousarray(ras, dtype=np.float64)
+    assert ras.ndim == 2
+    rows = np.ascontiguousarray(rows, dtype=np.int64).ravel()
+    cols = np.ascontiguousarray(cols, dtype=np.int64).ravel()
+    assert rows.shape == cols.shape
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+    with torch.cuda.device(dev):
+        d_ras, d_r, d_c = (_to_dev(a, dev) for a in (ras, rows, cols))
+        out = torch.empty(rows.size, dtype=torch.float64, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.spx_sample_raster_dev(
+            d_ras.data_ptr(), ras.shape[0], ras.shape[1], d_r.data_ptr(), d_c.data_ptr(),
+            rows.size, 0.0 if ndv is None else float(ndv), int(ndv is not None),
+            out.data_ptr(), st), 'sample_raster')
+        return out.cpu().numpy()
+
+
+def drift_cell_indices(min_row, max_row, min_col, max_col, cntn_idxs=None):
+    """Raster (row, col) of every interpolation cell, interp/drift.py:175-188."""
+    cols = np.arange(min_col, max_col + 1, dtype=np.int64)
+    rows = np.arange(min_row, max_row + 1, dtype=np.int64)
+    cm, rm = np.meshgrid(cols, rows)
+    cm, rm = cm.ravel(), rm.ravel()
+    if cntn_idxs is not None:
+        cm, rm = cm[cntn_idxs], rm[cntn_idxs]
+    return rm, cm
+
+
+def drift_point_indices(xs, ys, ras_x_min, ras_y_max, cell_size):
+    """Raster (row, col) of points, interp/drift.py:209-210 (``int()`` truncates)."""
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    cols = np.trunc((xs - ras_x_min) / cell_size).astype(np.int64)
+    rows = np.trunc((ras_y_max - ys) / cell_size).astype(np.int64)
+    return rows, cols
