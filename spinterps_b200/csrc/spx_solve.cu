@@ -7,6 +7,8 @@
 //   _get_vars_arr_subset   interp/steps.py:170-243   (assembly)
 //   np.linalg.pinv         interp/steps.py:351       (factor; non-singular case)
 //   np.matmul(inv, rhs_i)  interp/steps.py:416       (dual form)
+#include <type_traits>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -968,13 +970,302 @@ __device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShare
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Blocked LU variant of the downdate (default for r <= DD_REG_MAX).
+//
+// The Gauss-Jordan kernel above pays one block-wide barrier and ~100 issued instructions
+// per warp for EVERY column of S (r ~ 100 columns, all 16 warps in lock step).  Here S
+// lives in shared memory and is factored in panels of DL_NB columns:
+//   * the panel (rows p.., DL_NB columns) is factored by ONE warp in registers -- the
+//     pivot row is broadcast by shuffles, no block barrier inside a panel;
+//   * the U block row is a per-column forward substitution (one thread per column);
+//   * the trailing update  S22 -= L21 U12  runs on the FP64 tensor cores (DMMA m8n8k4,
+//     two per 8 x 8 tile);
+//   * every right-hand side is solved by one warp (vector in registers, shuffles).
+// Three block barriers per panel instead of one per column, and two blocks per SM
+// (r <= 112) overlap each other's latency chains.  No pivoting: S is a principal
+// submatrix of the inverse of a (conditionally) definite system, hence definite; a zero,
+// non-finite or wrong-sign pivot flags the system and k_downdate_reg redoes it with
+// pivoting (repair pass).
+constexpr int DL_NB = 8;
+constexpr int DL_THREADS = 256;
+constexpr int DL_SMALL = 112;    // r <= DL_SMALL: two blocks per SM
+
+static size_t dl_smem_bytes(int rp) {
+    return ((size_t)(rp + 1) * rp + rp + (size_t)DD_RB * rp) * sizeof(double) + (size_t)rp * sizeof(int);
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int r_lo, int r_hi,
+                                                           int rp_max, int test_fail) {
+    extern __shared__ double dsm[];
+    __shared__ int s_info;
+    __shared__ double s_part[DD_RB][DL_THREADS / 32];
+    const int sys = d.sys_order ? d.sys_order[blockIdx.x] : blockIdx.x;
+    const int r = d.sys_r[sys];
+    if (r <= r_lo || r > r_hi) return;
+    const int n = d.sys_n[sys];
+    const int M = d.n_stn + d.n_border;
+    const int ld = rp_max + 1;                         // odd pitch
+    double* __restrict__ S = dsm;                      // [ld * rp_max] column-major
+    double* __restrict__ rdiag = S + (size_t)ld * rp_max;   // 1 / U[j, j]
+    double* __restrict__ ys = rdiag + rp_max;          // [DD_RB][rp_max]
+    int* __restrict__ mi = reinterpret_cast<int*>(ys + (size_t)DD_RB * rp_max);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t* __restrict__ miss = d.miss_list + d.sys_miss_off[sys];
+    const int32_t* __restrict__ stn = d.stn_list + d.sys_stn_off[sys];
+    const double* __restrict__ G = d.ginv;
+    if (test_fail && (sys & 1)) {                      // SPX_DD_LU_FAIL=1: exercise the repair pass
+        if (tid == 0) d.info[sys] = 1;
+        return;
+    }
+    if (tid == 0) s_info = 0;
+    for (int i = tid; i < r; i += DL_THREADS) mi[i] = miss[i];
+    __syncthreads();
+    const int rp = (r + 7) & ~7;                       // <= rp_max
+    // S = G[Mi, Mi] (row mi[j] of G read along ascending mi[i]; G symmetric), identity pad
+    for (int idx = tid; idx < rp * rp; idx += DL_THREADS) {
+        const int j = idx / rp, i = idx - j * rp;
+        S[i + (size_t)j * ld] = (i < r && j < r) ? G[(int64_t)mi[j] * M + mi[i]]
+                                                 : ((i == j) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+
+    double sgn = 0.0;                                  // sign of the first pivot (warp 0)
+    // ---- panel: rows p + lane + 32 q, columns p .. p + nb - 1, factored by ONE warp in
+    // registers (pivot row broadcast by shuffles)
+    auto panel = [&](int p) {
+        const int nb = min(DL_NB, r - p);
+        double a[NQ][DL_NB];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int i = p + lane + 32 * q;
+#pragma unroll
+            for (int c = 0; c < DL_NB; ++c)
+                a[q][c] = (i < r && c < nb) ? S[i + (size_t)(p + c) * ld] : 0.0;
+        }
+        int bad = 0;
+#pragma unroll
+        for (int jc = 0; jc < DL_NB; ++jc) {
+            if (jc < nb) {
+                const double piv = __shfl_sync(0xffffffffu, a[0][jc], jc);
+                if (p == 0 && jc == 0) sgn = piv;
+                if (!(piv * sgn > 0.0) || !(fabs(piv) < 1.0e300)) bad = bad ? bad : p + jc + 1;
+                const double rcp = (piv != 0.0) ? 1.0 / piv : 1.0;
+                if (lane == 0) rdiag[p + jc] = rcp;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (lane + 32 * q > jc) a[q][jc] *= rcp;
+#pragma unroll
+                for (int c = jc + 1; c < DL_NB; ++c) {
+                    const double u = __shfl_sync(0xffffffffu, a[0][c], jc);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane + 32 * q > jc) a[q][c] = fma(-a[q][jc], u, a[q][c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int i = p + lane + 32 * q;
+#pragma unroll
+            for (int c = 0; c < DL_NB; ++c)
+                if (i < r && c < nb) S[i + (size_t)(p + c) * ld] = a[q][c];
+        }
+        if (bad && lane == 0 && s_info == 0) s_info = bad;
+    };
+    // 8 x 8 tile of the trailing update  S22 -= L21 U12  (two DMMA m8n8k4)
+    const int fg = lane >> 2, ft = lane & 3;
+    auto tile_update = [&](int p, int i0, int c0) {
+        double* cp0 = S + i0 + fg + (size_t)(c0 + 2 * ft) * ld;
+        double c_lo = cp0[0], c_hi = cp0[ld];
+        const double a0 = -S[i0 + fg + (size_t)(p + ft) * ld];
+        const double a1 = -S[i0 + fg + (size_t)(p + 4 + ft) * ld];
+        const double b0 = S[p + ft + (size_t)(c0 + fg) * ld];
+        const double b1 = S[p + 4 + ft + (size_t)(c0 + fg) * ld];
+        dmma_lu(c_lo, c_hi, a0, b0);
+        dmma_lu(c_lo, c_hi, a1, b1);
+        cp0[0] = c_lo;
+        cp0[ld] = c_hi;
+    };
+    if (wid == 0 && r > 0) panel(0);
+    __syncthreads();
+    for (int p = 0; p + DL_NB < r; p += DL_NB) {
+        // ---- U block row: unit-lower forward substitution, one thread per column
+        for (int c = p + DL_NB + tid; c < rp; c += DL_THREADS) {
+            double x[DL_NB];
+#pragma unroll
+            for (int k = 0; k < DL_NB; ++k) x[k] = S[p + k + (size_t)c * ld];
+#pragma unroll
+            for (int k = 1; k < DL_NB; ++k)
+#pragma unroll
+                for (int kk = 0; kk < k; ++kk)
+                    x[k] = fma(-S[p + k + (size_t)(p + kk) * ld], x[kk], x[k]);
+#pragma unroll
+            for (int k = 1; k < DL_NB; ++k) S[p + k + (size_t)c * ld] = x[k];
+        }
+        __syncthreads();
+        // ---- trailing update with look-ahead: warp 0 updates the columns of the next
+        // panel and factors it right away while the other warps update the rest
+        const int o = p + DL_NB;
+        const int nt = (rp - o) >> 3;
+        if (wid == 0) {
+            for (int ti = 0; ti < nt; ++ti) tile_update(p, o + 8 * ti, o);
+            __syncwarp();
+            panel(o);
+        } else if (nt > 1) {
+            const int ntc = nt - 1;
+#pragma unroll 2
+            for (int tile = wid - 1; tile < nt * ntc; tile += DL_THREADS / 32 - 1) {
+                const int ti = tile / ntc, tj = tile - ti * ntc + 1;
+                tile_update(p, o + 8 * ti, o + 8 * tj);
+            }
+        }
+        __syncthreads();
+    }
+    if (s_info != 0) {                                 // block-uniform: left to the repair pass
+        if (tid == 0) d.info[sys] = s_info;
+        return;
+    }
+    if (tid == 0) d.info[sys] = 0;
+
+    // ---- right-hand sides, DD_RB at a time: y = S^-1 u_Mi, one warp per right-hand side
+    const int64_t q0 = d.sys_rhs_off[sys];
+    const int nq = d.sys_rhs_cnt[sys];
+    const int nk = n + d.n_border;
+    for (int base = 0; base < nq; base += DD_RB) {
+        const int nbq = min(DD_RB, nq - base);
+        if (wid < nbq && r > 0) {
+            const double* __restrict__ urow = d.ut + (int64_t)d.rhs_urow[q0 + base + wid] * M;
+            double x[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int i = lane + 32 * q;
+                x[q] = (i < r) ? urow[mi[i]] : 0.0;
+            }
+            // L y' = b (unit diagonal)
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq) {
+#pragma unroll 4
+                for (int jl = 0; jl < 32; ++jl) {
+                    const int j = 32 * qq + jl;
+                    if (j >= r) break;
+                    const double xj = __shfl_sync(0xffffffffu, x[qq], jl);
+                    const double* __restrict__ col = S + (size_t)j * ld;
+#pragma unroll
+                    for (int q = qq; q < NQ; ++q) {
+                        const int i = lane + 32 * q;
+                        if (i > j && i < r) x[q] = fma(-col[i], xj, x[q]);
+                    }
+                }
+            }
+            // U y = y'
+#pragma unroll
+            for (int qq = NQ - 1; qq >= 0; --qq) {
+#pragma unroll 4
+                for (int jl = 31; jl >= 0; --jl) {
+                    const int j = 32 * qq + jl;
+                    if (j >= r) continue;
+                    const double xj = __shfl_sync(0xffffffffu, x[qq] * rdiag[j], jl);
+                    if (lane == jl) x[qq] = xj;
+                    const double* __restrict__ col = S + (size_t)j * ld;
+#pragma unroll
+                    for (int q = 0; q <= qq; ++q) {
+                        const int i = lane + 32 * q;
+                        if (i < j) x[q] = fma(-col[i], xj, x[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int i = lane + 32 * q;
+                if (i < r) ys[(size_t)wid * rp_max + i] = x[q];
+            }
+        }
+        __syncthreads();
+        // c_K = u_K - G[K, Mi] y  for the nbq right-hand sides at once (two accumulators
+        // when the system has a single step: its data and the ones-vector)
+        const bool want_base = d.base != nullptr;
+        if (want_base && lane == 0) {
+#pragma unroll
+            for (int w = 0; w < DD_RB; ++w) s_part[w][wid] = 0.0;
+        }
+        auto emit = [&](auto wtag) {
+            constexpr int W = decltype(wtag)::value;
+            for (int i0 = 0; i0 < nk; i0 += DL_THREADS) {
+                const int i = i0 + tid;
+                const bool act = i < nk;
+                const int ki = !act ? 0 : ((i < n) ? stn[i] : (d.n_stn + (i - n)));
+                double acc[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    acc[w] = (act && w < nbq)
+                                 ? d.ut[(int64_t)d.rhs_urow[q0 + base + w] * M + ki] : 0.0;
+                if (act) {
+#pragma unroll 4
+                    for (int j = 0; j < r; ++j) {
+                        const double gv = G[(int64_t)mi[j] * M + ki];
+#pragma unroll
+                        for (int w = 0; w < W; ++w)
+                            acc[w] = fma(-gv, ys[(size_t)w * rp_max + j], acc[w]);
+                    }
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        if (w >= nbq) break;
+                        const int64_t q = q0 + base + w;
+                        const int64_t row = d.rhs_row[q];
+                        if (row >= 0) {
+                            d.coef[d.coef_row_major ? row * (int64_t)d.kpad + ki
+                                                    : coef_offset(row, ki, d.kpad)] = acc[w];
+                            if (d.coef_t) d.coef_t[(int64_t)ki * d.coef_t_ld + row] = acc[w];
+                        }
+                        if (d.rhs_kind[q] == 1)
+                            atomicAdd(&d.resid[q], fabs(acc[w] - ((i == n) ? 1.0 : 0.0)));
+                    }
+                }
+                if (want_base) {
+                    const double bf = !act ? 0.0 : ((i < n) ? d.base_f : ((i == n) ? 1.0 : 0.0));
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        double v = bf * acc[w];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0) s_part[w][wid] += v;
+                    }
+                }
+            }
+        };
+        if (nbq <= 2) emit(std::integral_constant<int, 2>{});
+        else emit(std::integral_constant<int, DD_RB>{});
+        if (d.coef_t) {           // missing stations: explicit zeros (the buffer is not pre-set)
+            for (int idx = tid; idx < nbq * r; idx += DL_THREADS) {
+                const int w = idx / r, j = idx - w * r;
+                const int64_t row = d.rhs_row[q0 + base + w];
+                if (row >= 0) d.coef_t[(int64_t)mi[j] * d.coef_t_ld + row] = 0.0;
+            }
+        }
+        __syncthreads();
+        if (want_base && tid < nbq) {
+            const int64_t row = d.rhs_row[q0 + base + tid];
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < DL_THREADS / 32; ++k) v += s_part[tid][k];
+            if (row >= 0) d.base[row] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // One launch for every tile shape: systems of different order run side by side (three
 // launches, one per shape, serialise behind each other's stragglers).
-__global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_max, int force_pivot) {
+__global__ void __launch_bounds__(512, 1) k_downdate_reg(spx_downdate d, int r_max, int force_pivot,
+                                                        int only_failed) {
     __shared__ DdShared sm;
     const int sys = d.sys_order ? d.sys_order[blockIdx.x] : blockIdx.x;
     const int r = d.sys_r[sys];
     if (r > r_max) return;               // left to the shared-memory kernel
+    // repair pass behind k_downdate_lu: only the systems it flagged (nothing written yet)
+    if (only_failed && d.info[sys] == 0) return;
     if (r <= 112) downdate_reg_body<7, 4>(d, sm, sys, r, force_pivot);
     else if (r <= 128) downdate_reg_body<8, 4>(d, sm, sys, r, force_pivot);
     else downdate_reg_body<10, 5>(d, sm, sys, r, force_pivot);
@@ -1093,6 +1384,16 @@ static bool dd_force_smem() {
     return v == 1;
 }
 
+// SPX_DD_LU=0 selects the register-resident Gauss-Jordan kernel instead of the blocked LU.
+static bool dd_use_lu() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPX_DD_LU");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int dd_force_pivot() {
     static int v = -1;
     if (v < 0) {
@@ -1140,10 +1441,42 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
     int smem_lo = 0;   // systems with r > smem_lo go to the shared-memory kernel
     if (!dd_force_smem()) {
         const int fp = dd_force_pivot();
-        k_downdate_reg<<<d->n_sys, 512, 0, st>>>(dd, DD_REG_MAX, fp);
-        SPX_CHECK_LAUNCH("k_downdate_reg");
-        if (dd.max_r <= DD_REG_MAX) return SPX_OK;
-        smem_lo = DD_REG_MAX;
+        if (dd_use_lu() && !fp) {
+            // blocked LU in shared memory; large systems first (one block per SM), then
+            // the bulk (two blocks per SM); flagged systems are redone with pivoting
+            int dev = 0, max_smem = 0;
+            SPX_CUDA(cudaGetDevice(&dev));
+            SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                            dev));
+            const size_t sm_big = dl_smem_bytes(DD_REG_MAX), sm_small = dl_smem_bytes(DL_SMALL);
+            static const int tf = (getenv("SPX_DD_LU_FAIL") && getenv("SPX_DD_LU_FAIL")[0] == '1');
+            if (sm_big + 1024 <= (size_t)max_smem) {
+                if (dd.max_r > DL_SMALL) {
+                    SPX_CUDA(cudaFuncSetAttribute(k_downdate_lu<5>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sm_big));
+                    k_downdate_lu<5><<<d->n_sys, DL_THREADS, sm_big, st>>>(dd, DL_SMALL, DD_REG_MAX,
+                                                                          DD_REG_MAX, tf);
+                    SPX_CHECK_LAUNCH("k_downdate_lu<5>");
+                }
+                SPX_CUDA(cudaFuncSetAttribute(k_downdate_lu<4>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sm_small));
+                k_downdate_lu<4><<<d->n_sys, DL_THREADS, sm_small, st>>>(dd, -1, DL_SMALL, DL_SMALL,
+                                                                        tf);
+                SPX_CHECK_LAUNCH("k_downdate_lu<4>");
+                k_downdate_reg<<<d->n_sys, 512, 0, st>>>(dd, DD_REG_MAX, 1, 1);
+                SPX_CHECK_LAUNCH("k_downdate_reg(repair)");
+                if (dd.max_r <= DD_REG_MAX) return SPX_OK;
+                smem_lo = DD_REG_MAX;
+            }
+        }
+        if (smem_lo == 0) {
+            k_downdate_reg<<<d->n_sys, 512, 0, st>>>(dd, DD_REG_MAX, fp, 0);
+            SPX_CHECK_LAUNCH("k_downdate_reg");
+            if (dd.max_r <= DD_REG_MAX) return SPX_OK;
+            smem_lo = DD_REG_MAX;
+        }
     }
     const size_t smem = dd_smem_bytes(dd.max_r);
     int dev = 0, max_smem = 0;

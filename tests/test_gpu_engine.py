@@ -111,16 +111,20 @@ def test_seeded_vs_oracle(eng, n_stn, n_steps, ny, nx, miss):
     _check(got, exp, 'seeded')
 
 
-@pytest.mark.parametrize('knob', ['SPX_DD_PIVOT', 'SPX_DD_SMEM'])
+@pytest.mark.parametrize('knob', ['SPX_DD_PIVOT=1', 'SPX_DD_SMEM=1', 'SPX_DD_LU=0',
+                                  'SPX_DD_LU_FAIL=1'])
 def test_downdate_kernel_variants(knob):
-    """The downdated solves have a fast path (Gauss-Jordan without pivoting, definite
-    S) with two fall-backs: pivoted elimination in registers and LU in shared memory.
-    The environment knobs force each of them; same parity bar."""
+    """The downdated solves run a blocked LU without pivoting (definite S) by default;
+    behind it: Gauss-Jordan in registers without / with pivoting (the latter also as the
+    repair pass for systems the LU flags -- SPX_DD_LU_FAIL makes it flag every other
+    system) and LU in shared memory with pivoting.  The environment knobs force each of
+    them; same parity bar."""
     import os
     import subprocess
     import sys
     env = dict(os.environ)
-    env[knob] = '1'
+    k, v = knob.split('=')
+    env[k] = v
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_engine.py', '-q', '-x',
                         '-m', 'gpu', '-k', 'test_seeded_vs_oracle and auto'],
