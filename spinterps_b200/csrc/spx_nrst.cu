@@ -919,6 +919,7 @@ struct LocalEstArgs {
     const int32_t* tile_cnt;    // optional tile tables (see spx_local)
     const int32_t* tile_stn;
     const uint8_t* slot;
+    int swap_grid;              // 1: blockIdx.x = row block, blockIdx.y = cell tile
 };
 
 // Distinct near stations of every tile of SPX_LOCAL_TILE cells: a station bitmap in shared
@@ -1139,14 +1140,16 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
         const longlong2 o23 = *reinterpret_cast<const longlong2*>(soff + r + 2);
         const int64_t o[4] = {o01.x, o01.y, o23.x, o23.y};
 #pragma unroll
+        // streaming stores (st.global.cs): the 5 GB field passes through L2 once and must
+        // not evict the ~30 MB of tables / coefficient slices every row block re-reads
         for (int u = 0; u < 4; ++u) {
             if (CPT == 2) {
                 if (pair)
-                    *reinterpret_cast<float2*>(outp + o[u]) = make_float2(f[0][u], f[CPT - 1][u]);
+                    __stcs(reinterpret_cast<float2*>(outp + o[u]), make_float2(f[0][u], f[CPT - 1][u]));
                 else
-                    outp[o[u]] = f[0][u];
+                    __stcs(outp + o[u], f[0][u]);
             } else {
-                outp[o[u]] = f[0][u];
+                __stcs(outp + o[u], f[0][u]);
             }
         }
     }
@@ -1168,7 +1171,7 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
                 fv = (fv < flo) ? flo : fv;
                 fv = (fv > fhi) ? fhi : fv;
             }
-            outp[soff[r] + q] = fv;
+            __stcs(outp + soff[r] + q, fv);
         }
     }
 }
@@ -1187,10 +1190,14 @@ __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) 
     __shared__ __align__(16) double sct[TILE ? SPX_LOCAL_TILE_CAP * LOC_SLD : 2];
     static_assert(!TILE || (CPT == 1 && ROWS == 128), "tile variant: 256 cells x 128 rows");
     const int tid = threadIdx.x;
-    const int64_t r_beg = (int64_t)blockIdx.y * ROWS;
+    // swap_grid: the row blocks of one cell tile are launched back to back, so that all
+    // but the first find the tile's tables and coefficient slices in L2
+    const unsigned bx = a.swap_grid ? blockIdx.y : blockIdx.x;     // cell tile
+    const unsigned by = a.swap_grid ? blockIdx.x : blockIdx.y;     // row block
+    const int64_t r_beg = (int64_t)by * ROWS;
     const int nr = (int)min((int64_t)ROWS, a.n_rows - r_beg);
     const double* ct = a.coef_t + r_beg;
-    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + tid) * CPT;
+    const int64_t c0 = ((int64_t)bx * blockDim.x + tid) * CPT;
     const bool pair = (CPT == 2) && (c0 + 1 < a.n_cells);
     // A block lives for only ROWS / 4 loop iterations, so the latency of its prologue
     // matters: every table entry it may need is requested up front, unconditionally and
@@ -1210,8 +1217,8 @@ __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) 
     bool staged = false;
     if (TILE) {
         constexpr int SPT = SPX_LOCAL_TILE_CAP / 4;      // slices per thread (4 per pass)
-        const int32_t* __restrict__ tl = a.tile_stn + (int64_t)blockIdx.x * SPX_LOCAL_TILE_CAP;
-        const int U = a.tile_cnt[blockIdx.x];
+        const int32_t* __restrict__ tl = a.tile_stn + (int64_t)bx * SPX_LOCAL_TILE_CAP;
+        const int U = a.tile_cnt[bx];
         int stn[SPT];
 #pragma unroll
         for (int it = 0; it < SPT; ++it) stn[it] = tl[(tid >> 6) + 4 * it];
@@ -1379,6 +1386,7 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
     a.tile_cnt = nullptr;
     a.tile_stn = nullptr;
     a.slot = nullptr;
+    a.swap_grid = 0;
     const int64_t row_blocks = (l->n_rows + LOC_ROWS - 1) / LOC_ROWS;
     if (row_blocks > 65535) {
         set_error("estimate_local: too many rows in one launch");
@@ -1402,6 +1410,12 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
         const int64_t per_blk = 256 * (int64_t)cpt;
         dim3 g1((unsigned)((l->n_cells + per_blk - 1) / per_blk),
                 (unsigned)((l->n_rows + rows - 1) / rows));
+        static const int swap_knob = getenv("SPX_LOCAL_SWAP") ? atoi(getenv("SPX_LOCAL_SWAP")) : 1;
+        a.swap_grid = 0;
+        if (swap_knob && g1.x <= 65535u) {
+            a.swap_grid = 1;
+            g1 = dim3(g1.y, g1.x);
+        }
 #define SPX_LOCAL_LAUNCH(CL, RW, CP) \
     k_estimate_local_fast<CL, RW, CP, false><<<g1, 256, 0, st>>>(a)
         static const int tile_knob = getenv("SPX_LOCAL_TILES") ? atoi(getenv("SPX_LOCAL_TILES")) : 1;

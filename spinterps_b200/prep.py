@@ -48,7 +48,7 @@ def rings_to_edges(rings):
 def points_in_polygons(xs, ys, rings, buffer_dist=0.0, device=None):
     """bool [n]: point inside any ring (even-odd rule) or, with buffer_dist > 0, closer than
     buffer_dist to any ring edge.  One kernel launch over all points
-    (spx_points_in_polygons_dev); the oracle states the same arithmetic in NumPy."""
+    (spx_points_in_polygons_dev)."""
     _lib.require_gpu()
     lib = _lib.load()
     xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
