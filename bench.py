@@ -316,6 +316,11 @@ def run_gpu(args):
             ms, ms_wall = float(t[0]), float(t[1])
         return ms, ms_wall
 
+    # Steady state needs more than 3 chunks: the first chunk of a job builds the inverse of
+    # the full station system and the near-station tables (cached afterwards), the upload
+    # arena ring has 4 slots that are allocated on first use, the caching allocator has
+    # to see the 5 GB field blocks once.  Untimed warm-up is therefore at least 8 chunks.
+    args.warmup = max(args.warmup, 8)
     run_resident(args.warmup)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)

@@ -1,0 +1,56 @@
+"""The resident (value) loop of bench.py alone, optionally under torch.distributed, to
+separate per-rank host cost from everything else bench.py does.
+   python scripts/value_loop.py [steps]            (CUDA_VISIBLE_DEVICES picks the GPU)
+   torchrun --nproc-per-node N scripts/value_loop.py [steps]"""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from spinterps_b200.engine import ChunkEngine
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+if world > 1 and os.environ.get('NO_DIST') != '1':
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+chunks = [bench.make_chunk(rank, v) for v in range(4)]
+eng = ChunkEngine()
+kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32)
+
+def run(n):
+    pend = None
+    t_sub = 0.0
+    for i in range(n):
+        t0 = time.perf_counter()
+        nxt = eng.submit_chunk(**kw, **chunks[i % 4])
+        t_sub += time.perf_counter() - t0
+        if pend is not None:
+            pend.result(to_host=False)
+        pend = nxt
+    pend.result(to_host=False)
+    return t_sub
+
+keep = []
+if os.environ.get('VL_PINNED') == '1':      # bench.py's pinned e2e buffers
+    keep = [torch.empty((bench.CHUNK_STEPS, bench.NY * bench.NX), dtype=torch.float32).pin_memory()
+            for _ in range(2)]
+if os.environ.get('VL_SAMPLER') == '1':
+    smp = bench.ClockSampler(local)
+    smp.start()
+if os.environ.get('VL_PROF') == '1':
+    eng.profile_gemm = True
+if os.environ.get('VL_FORK') == '1':
+    pass
+run(5)
+torch.cuda.synchronize()
+for rep in range(3):
+    t0 = time.perf_counter()
+    ts = run(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print('rank %d rep %d: %.3f ms/step (submit %.3f ms/step) affinity %d cores omp=%s' % (
+        rank, rep, 1e3 * dt / steps, 1e3 * ts / steps, len(os.sched_getaffinity(0)),
+        os.environ.get('OMP_NUM_THREADS')), flush=True)
