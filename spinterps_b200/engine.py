@@ -213,6 +213,7 @@ class ChunkEngine:
         self.sync_timing = False
         self.timing = {}
         self.total_launches = 0
+        self.h2d_bytes = 0           # bytes uploaded by the engine (host -> device)
         self.h2d_stream = torch.cuda.Stream(self.device)
         self._h2d_handle = C.c_void_p(self.h2d_stream.cuda_stream)
         self._h2d_dirty = False
@@ -290,6 +291,7 @@ class ChunkEngine:
         hit = self._const_cache.get(key)
         if hit is None:
             self._sync_uploads()
+            self.h2d_bytes += arr.nbytes
             hit = torch.from_numpy(arr.copy()).to(self.device)
             while len(self._const_cache) >= 16:
                 self._const_cache.pop(next(iter(self._const_cache)))
@@ -314,6 +316,7 @@ class ChunkEngine:
                 d = t.to(self.device, non_blocking=True)
             d.record_stream(main)
             self._h2d_dirty = True
+            self.h2d_bytes += arr.nbytes
             return d
         if arr.nbytes == 0:
             return torch.empty(arr.shape, dtype=tdt, device=self.device)
@@ -321,6 +324,7 @@ class ChunkEngine:
         _lib.check(self.lib.spx_upload_dev(C.c_void_p(d.data_ptr()), C.c_void_p(arr.ctypes.data),
                                            arr.nbytes, self._h2d_handle), 'upload')
         self._h2d_dirty = True
+        self.h2d_bytes += arr.nbytes
         return d.view(tdt).view(arr.shape)
 
     def _dev_pack(self, arrays):
@@ -1396,6 +1400,7 @@ class ChunkEngine:
                                               C.c_void_p(hb.ctypes.data),
                                               int(plan.n_upload_bytes), self._h2d_handle), 'upload')
                 self._h2d_dirty = True
+                self.h2d_bytes += int(plan.n_upload_bytes)
                 pb = d_plan.data_ptr()
                 _lib.check(lib.spx_avail_lists_dev(
                     self._ptr(d_data), n_stn, n_stn, C.c_void_p(pb + plan.off_bt_step + 4 * n_data),

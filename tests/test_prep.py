@@ -111,7 +111,7 @@ def test_main_with_polygons_and_array_drift_raster(tmp_path):
     rx0, ry1 = -2.0e4, 1.0e5
     rr, cc = np.meshgrid(np.arange(70), np.arange(80), indexing='ij')
     elev = 300.0 + 0.004 * (rx0 + (cc + 0.5) * cs) + 0.002 * (ry1 - (rr + 0.5) * cs)
-    elev[20:22, 30:33] = -9999.0
+    elev[27:29, 42:45] = -9999.0            # inside the second polygon
     m = SpInterpMain(verbose=False)
     m.set_data(data, crds)
     m.set_vgs_ser(pd.Series([vg] * T, index=tidx))
