@@ -978,11 +978,12 @@ __device__ __forceinline__ void downdate_reg_body(const spx_downdate& d, DdShare
 // lives in shared memory and is factored in panels of DL_NB columns:
 //   * the panel (rows p.., DL_NB columns) is factored by ONE warp in registers -- the
 //     pivot row is broadcast by shuffles, no block barrier inside a panel;
-//   * the U block row is a per-column forward substitution (one thread per column);
-//   * the trailing update  S22 -= L21 U12  runs on the FP64 tensor cores (DMMA m8n8k4,
-//     two per 8 x 8 tile);
+//   * S is symmetric: S = L D L^T, the U block row of the LU is D L21^T and needs no
+//     phase of its own;
+//   * the trailing update  S22 -= L21 D L21^T  (lower tiles only) runs on the FP64 tensor
+//     cores (DMMA m8n8k4, two per 8 x 8 tile);
 //   * every right-hand side is solved by one warp (vector in registers, shuffles).
-// Three block barriers per panel instead of one per column, and two blocks per SM
+// One block barrier per panel instead of one per column, and two blocks per SM
 // (r <= 112) overlap each other's latency chains.  No pivoting: S is a principal
 // submatrix of the inverse of a (conditionally) definite system, hence definite; a zero,
 // non-finite or wrong-sign pivot flags the system and k_downdate_reg redoes it with
@@ -992,7 +993,8 @@ constexpr int DL_THREADS = 256;
 constexpr int DL_SMALL = 112;    // r <= DL_SMALL: two blocks per SM
 
 static size_t dl_smem_bytes(int rp) {
-    return ((size_t)(rp + 1) * rp + rp + (size_t)DD_RB * rp) * sizeof(double) + (size_t)rp * sizeof(int);
+    return ((size_t)(rp + 1) * rp + 2 * rp + (size_t)DD_RB * rp) * sizeof(double) +
+           (size_t)rp * sizeof(int);
 }
 
 template <int NQ>
@@ -1008,8 +1010,9 @@ __global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int 
     const int M = d.n_stn + d.n_border;
     const int ld = rp_max + 1;                         // odd pitch
     double* __restrict__ S = dsm;                      // [ld * rp_max] column-major
-    double* __restrict__ rdiag = S + (size_t)ld * rp_max;   // 1 / U[j, j]
-    double* __restrict__ ys = rdiag + rp_max;          // [DD_RB][rp_max]
+    double* __restrict__ rdiag = S + (size_t)ld * rp_max;   // 1 / d_j
+    double* __restrict__ dg = rdiag + rp_max;          // d_j (pivots of S = L D L^T)
+    double* __restrict__ ys = dg + rp_max;             // [DD_RB][rp_max]
     int* __restrict__ mi = reinterpret_cast<int*>(ys + (size_t)DD_RB * rp_max);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int32_t* __restrict__ miss = d.miss_list + d.sys_miss_off[sys];
@@ -1052,7 +1055,10 @@ __global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int 
                 if (p == 0 && jc == 0) sgn = piv;
                 if (!(piv * sgn > 0.0) || !(fabs(piv) < 1.0e300)) bad = bad ? bad : p + jc + 1;
                 const double rcp = (piv != 0.0) ? 1.0 / piv : 1.0;
-                if (lane == 0) rdiag[p + jc] = rcp;
+                if (lane == 0) {
+                    rdiag[p + jc] = rcp;
+                    dg[p + jc] = piv;
+                }
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                     if (lane + 32 * q > jc) a[q][jc] *= rcp;
@@ -1074,15 +1080,18 @@ __global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int 
         }
         if (bad && lane == 0 && s_info == 0) s_info = bad;
     };
-    // 8 x 8 tile of the trailing update  S22 -= L21 U12  (two DMMA m8n8k4)
+    // 8 x 8 tile of the trailing update  S22 -= L21 D L21^T  (two DMMA m8n8k4).  S is
+    // symmetric, so the U block row of the LU is D L21^T: both operands come from the panel
+    // columns and only the lower tiles (and the diagonal ones, whose upper triangle the
+    // next panel reads) are kept up to date.
     const int fg = lane >> 2, ft = lane & 3;
     auto tile_update = [&](int p, int i0, int c0) {
         double* cp0 = S + i0 + fg + (size_t)(c0 + 2 * ft) * ld;
         double c_lo = cp0[0], c_hi = cp0[ld];
         const double a0 = -S[i0 + fg + (size_t)(p + ft) * ld];
         const double a1 = -S[i0 + fg + (size_t)(p + 4 + ft) * ld];
-        const double b0 = S[p + ft + (size_t)(c0 + fg) * ld];
-        const double b1 = S[p + 4 + ft + (size_t)(c0 + fg) * ld];
+        const double b0 = S[c0 + fg + (size_t)(p + ft) * ld] * dg[p + ft];
+        const double b1 = S[c0 + fg + (size_t)(p + 4 + ft) * ld] * dg[p + 4 + ft];
         dmma_lu(c_lo, c_hi, a0, b0);
         dmma_lu(c_lo, c_hi, a1, b1);
         cp0[0] = c_lo;
@@ -1091,35 +1100,21 @@ __global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int 
     if (wid == 0 && r > 0) panel(0);
     __syncthreads();
     for (int p = 0; p + DL_NB < r; p += DL_NB) {
-        // ---- U block row: unit-lower forward substitution, one thread per column
-        for (int c = p + DL_NB + tid; c < rp; c += DL_THREADS) {
-            double x[DL_NB];
-#pragma unroll
-            for (int k = 0; k < DL_NB; ++k) x[k] = S[p + k + (size_t)c * ld];
-#pragma unroll
-            for (int k = 1; k < DL_NB; ++k)
-#pragma unroll
-                for (int kk = 0; kk < k; ++kk)
-                    x[k] = fma(-S[p + k + (size_t)(p + kk) * ld], x[kk], x[k]);
-#pragma unroll
-            for (int k = 1; k < DL_NB; ++k) S[p + k + (size_t)c * ld] = x[k];
-        }
-        __syncthreads();
         // ---- trailing update with look-ahead: warp 0 updates the columns of the next
-        // panel and factors it right away while the other warps update the rest
+        // panel and factors it right away while the other warps update the remaining
+        // lower tiles; ONE block barrier per panel
         const int o = p + DL_NB;
         const int nt = (rp - o) >> 3;
         if (wid == 0) {
             for (int ti = 0; ti < nt; ++ti) tile_update(p, o + 8 * ti, o);
             __syncwarp();
             panel(o);
-        } else if (nt > 1) {
-            const int ntc = nt - 1;
-#pragma unroll 2
-            for (int tile = wid - 1; tile < nt * ntc; tile += DL_THREADS / 32 - 1) {
-                const int ti = tile / ntc, tj = tile - ti * ntc + 1;
-                tile_update(p, o + 8 * ti, o + 8 * tj);
-            }
+        } else {
+            int cnt = 0;
+            for (int ti = 1; ti < nt; ++ti)
+                for (int tj = 1; tj <= ti; ++tj, ++cnt)
+                    if (cnt % (DL_THREADS / 32 - 1) == wid - 1)
+                        tile_update(p, o + 8 * ti, o + 8 * tj);
         }
         __syncthreads();
     }
@@ -1159,20 +1154,24 @@ __global__ void __launch_bounds__(DL_THREADS) k_downdate_lu(spx_downdate d, int 
                     }
                 }
             }
-            // U y = y'
+            // D z = y'
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int i = lane + 32 * q;
+                if (i < r) x[q] *= rdiag[i];
+            }
+            // L^T y = z  (row j of L: S[j + i * ld], i < j)
 #pragma unroll
             for (int qq = NQ - 1; qq >= 0; --qq) {
 #pragma unroll 4
                 for (int jl = 31; jl >= 0; --jl) {
                     const int j = 32 * qq + jl;
                     if (j >= r) continue;
-                    const double xj = __shfl_sync(0xffffffffu, x[qq] * rdiag[j], jl);
-                    if (lane == jl) x[qq] = xj;
-                    const double* __restrict__ col = S + (size_t)j * ld;
+                    const double xj = __shfl_sync(0xffffffffu, x[qq], jl);
 #pragma unroll
                     for (int q = 0; q <= qq; ++q) {
                         const int i = lane + 32 * q;
-                        if (i < j) x[q] = fma(-col[i], xj, x[q]);
+                        if (i < j) x[q] = fma(-S[j + (size_t)i * ld], xj, x[q]);
                     }
                 }
             }
