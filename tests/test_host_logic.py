@@ -273,3 +273,27 @@ def test_native_downdate_plan_matches_numpy(seed, T, N, miss):
     assert lib.spx_downdate_plan_host(
         gos.ctypes.data, grp_n32.ctypes.data, mask.shape[0], N,
         steps.ctypes.data, rows.ctypes.data, steps.size, buf.ctypes.data, 64, C.byref(plan)) != 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints
+    ONE JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, 'bench.py', '--impl', 'reference', '--steps', '1',
+                        '--warmup', '0'], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'cell-steps/s' and d['value'] > 0
+    assert d['metric'].startswith('interpolated cell-steps/s')
+    assert d['higher_is_better'] is True and d['steps'] == 1 and d['warmup'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] and 'sample' in d['cpu_baseline']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'cell-steps/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
