@@ -63,7 +63,20 @@ N_VARIANTS = 4   # distinct chunks of time steps cycled through by the timed loo
 # ----------------------------------------------------------------- CPU arm
 
 def _cpu_worker(args):
-    (data, p, row0, row1) = args
+    (data, p, row0, row1, use_ref) = args
+    import contextlib
+    import io
+    if use_ref:
+        # the reference's own Cython + Python path, compiled into oracle/_ref
+        from oracle import ref_runner
+        ref_runner.load()
+        case = dict(data=data, stn_xs=p['stn_xs'], stn_ys=p['stn_ys'], cell_xs=p['cell_xs'],
+                    cell_ys=p['cell_ys'], grid_shape=p['grid_shape'], interp_args=INTERP_ARGS,
+                    vgs=[VG] * data.shape[0], fld_beg_row=row0, fld_end_row=row1)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_runner.run_case(case, intrp_dtype=np.float32)
+        return data.shape[0] * (row1 - row0) * p['grid_shape'][1], time.perf_counter() - t0
     from oracle import spinterp_oracle as orc
     t0 = time.perf_counter()
     flds, _ = orc.interp_chunk(
@@ -73,12 +86,24 @@ def _cpu_worker(args):
     return data.shape[0] * (row1 - row0) * p['grid_shape'][1], time.perf_counter() - t0
 
 
-def cpu_sample(p, n_cores, steps_per_core=1, rows=8):
-    """Oracle port, reference loop structure (faithful=True), multiprocess over
-    time chunks like interp/main.py:141-153; returns (cell_steps, seconds)."""
+def cpu_kind():
+    """'reference' when oracle/_ref (the reference compiled by oracle/build_ref.py) is
+    present, else 'port' (the NumPy oracle with the reference's loop structure)."""
+    try:
+        from oracle import ref_runner
+        return 'reference' if ref_runner.available() else 'port'
+    except Exception:
+        return 'port'
+
+
+def cpu_sample(p, n_cores, steps_per_core=1, rows=8, kind=None):
+    """The reference's CPU path, multiprocess over time chunks like
+    interp/main.py:141-153 (one fresh SpInterpSteps per task); returns
+    (cell_steps, seconds, n_steps, rows)."""
     import multiprocessing as mp
+    use_ref = (kind or cpu_kind()) == 'reference'
     n_steps = n_cores * steps_per_core
-    tasks = [(p['data'][i * steps_per_core:(i + 1) * steps_per_core], p, 0, rows)
+    tasks = [(p['data'][i * steps_per_core:(i + 1) * steps_per_core], p, 0, rows, use_ref)
              for i in range(n_cores)]
     ctx = mp.get_context('fork')
     t0 = time.perf_counter()
@@ -88,29 +113,35 @@ def cpu_sample(p, n_cores, steps_per_core=1, rows=8):
     return sum(r[0] for r in res), wall, n_steps, rows
 
 
+CPU_DESC = {'reference': "the reference's own interp/steps.py + cyth/interpmthds.pyx compiled "
+                         "into oracle/_ref, Pool(%d) over time chunks",
+            'port': 'oracle port with the reference loop structure, Pool(%d) over time chunks'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n_cores = len(os.sched_getaffinity(0))
+    kind = cpu_kind()
     p = make_chunk(0)
     vals = []
     for it in range(args.warmup + args.steps):
-        cs, wall, n_steps, rows = cpu_sample(p, n_cores, steps_per_core=1, rows=64)
+        cs, wall, n_steps, rows = cpu_sample(p, n_cores, steps_per_core=1, rows=64, kind=kind)
         if it >= args.warmup:
             vals.append((cs, wall))
     cs = sum(v[0] for v in vals)
     wall = sum(v[1] for v in vals)
     value = cs / wall
     sample = ('%d steps x %d grid rows x %d cols per bench step (same stations, missingness and '
-              'variogram as the GPU arm)' % (n_steps, rows, NX))
+              'variogram as the GPU arm); %s' % (n_steps, rows, NX, CPU_DESC[kind] % n_cores))
     line = {
         'impl': 'reference', 'metric': 'interpolated cell-steps/s (OK, FP64, f32 store)',
         'value': value, 'unit': 'cell-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': 'cell-steps/s', 'cores': n_cores, 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': 'cell-steps/s', 'cores': n_cores, 'kind': kind,
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'cell-steps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -340,6 +371,7 @@ def run_gpu(args):
     l0 = eng.total_launches
     ms, ms_wall = timed(run_resident, args.steps)
     launches_timed = eng.total_launches - l0
+    eng.collect_profile()
     kernel_events = eng.kernel_events
     eng.profile_gemm = False
     torch.cuda.synchronize()
@@ -351,7 +383,8 @@ def run_gpu(args):
         for name, bound, work, e0, e1 in events:
             d = by.setdefault(name, dict(bound=bound, work=0.0, ms=0.0, n=0))
             d['work'] += work
-            d['ms'] += e0.elapsed_time(e1)
+            # native submits report the milliseconds between their own CUDA events
+            d['ms'] += e0 if e1 is None else e0.elapsed_time(e1)
             d['n'] += 1
         if not by:
             return None
@@ -389,6 +422,7 @@ def run_gpu(args):
     eng.kernel_events = []
     n_dense = max(2, min(args.steps, 3))
     ms_dense, _ = timed(run_resident, n_dense)
+    eng.collect_profile()
     dense_dom = summarise(eng.kernel_events)
     eng.profile_gemm = False
     eng.local_support = True
@@ -439,11 +473,11 @@ def run_gpu(args):
         cpu_baseline = None
         if cpu_res is not None:
             cs, wall, n_steps_s, rows_s = cpu_res
-            sample = ('%d steps x %d grid rows x %d cols (same stations, missingness, variogram); '
-                      'oracle port with the reference loop structure, Pool(%d) over time chunks'
-                      % (n_steps_s, rows_s, NX, n_cores))
+            kind = cpu_kind()
+            sample = ('%d steps x %d grid rows x %d cols (same stations, missingness, variogram); %s'
+                      % (n_steps_s, rows_s, NX, CPU_DESC[kind] % n_cores))
             cpu_baseline = {'value': cs / wall, 'unit': 'cell-steps/s', 'cores': n_cores,
-                            'kind': 'port', 'sample': sample}
+                            'kind': kind, 'sample': sample}
         h2d = int(round(h2d_e2e_bytes / max(args.steps, 1)))   # counted by the engine
         line = {
             'metric': 'interpolated cell-steps/s (OK, FP64, f32 store)',

@@ -598,6 +598,83 @@ int spx_local_build_dev(const spx_local* l, void* stream);
 int spx_local_tiles_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
 
+/* ---- one native call per time chunk (the planned fast path) ------------------------
+ * The common case of the compute half of SpInterpSteps.interpolate_subset
+ * (interp/steps.py:673-833 for OK / EDK with neb_sel_mthd 'all'): every step of the chunk
+ * shares ONE variogram whose full-station inverse `ginv` is resident, and every
+ * availability group is solved by downdating it.  spx_fast_submit does, in one call,
+ *   host:   availability groups + per-step flags (spx_avail_groups_host), the downdate
+ *           descriptors (spx_downdate_plan_host), both written into pinned staging memory
+ *   device: data block + descriptors upload, station lists, Ut = Bt . ginv (own DMMA
+ *           kernel, Bt generated from the resident data), blocked LDL^T downdate, health
+ *           flags copied to mapped host memory  -- all on the job's SOLVE stream --
+ *           then the estimate (local estimator or DMMA contraction) on the caller's MAIN
+ *           stream behind an event.
+ * The solve stream is a separate high-priority stream: the latency-bound solves of chunk
+ * i+1 run underneath the HBM-bound estimate of chunk i.  Buffers live in a ring of
+ * n_slots slots; a slot is reused only after its estimate has finished.
+ * Nothing here allocates per chunk.  Steps the path does not handle itself (no station,
+ * one station, interp_steps_flag false) are only counted; the caller fills those rows. */
+typedef struct spx_fast_cfg {
+    int32_t n_stn, n_border, kpad;
+    int32_t max_steps;           /* largest chunk the job will see */
+    int32_t n_slots;             /* ring depth, 2..8 */
+    int32_t min_systems;         /* fewer systems than this: status 1 (not eligible) */
+    double min_var_thr;          /* interp/steps.py:760-765 */
+    const double* ginv;          /* device [M, M], M = n_stn + n_border, symmetric */
+    double lambda_bound;         /* |rhs| bound of the sum(lambda) screening */
+    double lambda_tol;
+    int32_t estimator;           /* 0: local (template `local`), 1: contraction (`gemm`) */
+    int32_t want_coef_t;         /* local: emit the transposed coefficients (streamlined kernel) */
+    double base_f;               /* local: F of spx_local */
+    spx_local local;             /* estimate templates: everything but coef / base / coef_t /
+                                    n_rows / row_dst / out is taken from here */
+    spx_gemm gemm;
+    int32_t profile;             /* record events around the estimate launch (spx_fast_times) */
+} spx_fast_cfg;
+
+typedef struct spx_fast_result {
+    int32_t status;              /* 0 queued, 1 not eligible (nothing was queued) */
+    int32_t slot;
+    int32_t n_grps, n_krige, n_sys, max_r;
+    int32_t n_none, n_single, n_mean;   /* steps left to the caller */
+    int32_t launches;            /* kernels queued by this call */
+    int64_t h2d_bytes;
+    const double* d_data;        /* the slot's device copy of the data block [n_steps, n_stn] */
+    double host_ms[6];           /* host time of the call: slot wait, group scan, plan, upload
+                                    calls, solve launches, estimate launch */
+} spx_fast_result;
+
+/* Device and pinned-host bytes one slot needs (the caller allocates n_slots of each). */
+int64_t spx_fast_slot_bytes(const spx_fast_cfg* cfg, int32_t pinned_host);
+/* dev_arena / host_arena: n_slots * spx_fast_slot_bytes(cfg, 0 / 1) bytes of device /
+ * pinned (mapped) host memory owned by the caller for the lifetime of the job. */
+int spx_fast_create(const spx_fast_cfg* cfg, void* dev_arena, void* host_arena, void** job);
+int spx_fast_destroy(void* job);
+/* data: HOST [n_steps, n_stn] row pitch ld (pageable or pinned).  out: device field
+ * [*, out_ld] of the template's dtype.  Per-step outputs (host, caller-allocated, n_steps
+ * entries; grp_bits [n_steps, ceil(n_stn / 64)]): as spx_avail_groups_host. */
+int spx_fast_submit(void* job, const double* data, int64_t n_steps, int64_t ld, void* out,
+                    void* main_stream, int32_t* grp_of_step, int32_t* grp_first,
+                    int32_t* grp_n, int32_t* n_avail, uint8_t* step_flag, uint64_t* grp_bits,
+                    spx_fast_result* res);
+/* Waits for the slot's solve phase and reads its health flags:
+ * verdict 0 healthy, 1 unhealthy elimination (info != 0), 2 sum(lambda) screening failed. */
+int spx_fast_check(void* job, int32_t slot, int32_t* verdict);
+/* Milliseconds of the slot's last estimate launch (profile = 1; waits for it). */
+int spx_fast_times(void* job, int32_t slot, float* estimate_ms, float* solve_ms);
+/* Timeline of a slot's last use relative to the solve start of slot `ref_slot` (profile = 1;
+ * waits for the slot's estimate): t_ms[0..3] = solve start, solve end, estimate start,
+ * estimate end.  A measuring aid for the overlap of the two streams. */
+int spx_fast_timeline(void* job, int32_t ref_slot, int32_t slot, float* t_ms);
+
+/* Ut[n_rows, M] = Bt . G with Bt generated from the resident data block exactly like
+ * spx_build_bt_dev (row i < n_data: data[src_step[i]] with NaN -> 0, else the availability
+ * mask; border columns zero) and G [M, M] symmetric; FP64 tensor-core (DMMA) tiles. */
+int spx_ut_gemm_dev(const double* data, int32_t n_stn, int64_t data_ld, const int32_t* src_step,
+                    int64_t n_rows, int64_t n_data, int32_t n_border, const double* ginv,
+                    double* ut, void* stream);
+
 /* ---- grid preparation ---------------------------------------------
  * Points (cells, stations) inside or within buffer_dist of polygons given as outer rings
  * (misc.py:407-540 chk_pt_cntmnt_in_polys_mp: OGR Contains on polygons buffered by the

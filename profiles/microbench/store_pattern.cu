@@ -55,6 +55,33 @@ __global__ void __launch_bounds__(256) k_store_bulk(float* out, int64_t ld, int 
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// same, but the block's tile is WC cells wide (one bulk store of WC * 4 bytes per row) and
+// 256 threads write one float each: the shape the local estimator's block has
+template <int TR, int WC, int RB>
+__global__ void __launch_bounds__(256) k_store_bulk_w(float* out, int64_t ld, int rows, int64_t cells, float v) {
+    extern __shared__ __align__(128) float tile[];   // [2][RB][WC]
+    const int64_t c0 = (int64_t)blockIdx.x * WC;
+    const int r0 = blockIdx.y * TR;
+    const int nc = (int)min((int64_t)WC, cells - c0);
+    int buf = 0;
+    for (int rb = r0; rb < min(rows, r0 + TR); rb += RB, buf ^= 1) {
+        float* t = tile + buf * RB * WC;
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int i = threadIdx.x; i < RB * WC; i += 256) t[i] = v + rb + (i / WC);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < RB && rb + threadIdx.x < rows) {
+            float* g = out + (int64_t)(rb + threadIdx.x) * ld + c0;
+            const uint32_t s = (uint32_t)__cvta_generic_to_shared(t + threadIdx.x * WC);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(g), "r"(s), "r"(nc * 4) : "memory");
+        }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -85,6 +112,12 @@ int main() {
         cudaFuncSetAttribute(k_store_bulk<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16 * 1024 * 4); \
         rep("k_store_bulk (TMA bulk store) TR=" #TR, time_ms([&] { k_store_bulk<TR><<<g, 256, 2 * 16 * 1024 * 4>>>(out, ld, rows, cells, 1.f); })); }
     RUNB(128) RUNB(64) RUNB(32)
+#define RUNW(TR, WC, RB) { dim3 g((unsigned)((cells + WC - 1) / WC), (rows + TR - 1) / TR); \
+        cudaFuncSetAttribute(k_store_bulk_w<TR, WC, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RB * WC * 4); \
+        rep("k_store_bulk_w TR=" #TR " WC=" #WC " RB=" #RB, time_ms([&] { k_store_bulk_w<TR, WC, RB><<<g, 256, 2 * RB * WC * 4>>>(out, ld, rows, cells, 1.f); })); }
+    RUNW(128, 256, 8) RUNW(128, 256, 16) RUNW(128, 256, 32) RUNW(128, 512, 8) RUNW(128, 512, 16)
+    RUNW(64, 256, 16) RUNW(256, 256, 16) RUNW(1250, 256, 16) RUNW(128, 1024, 8)
+    RUN(1, 16) RUN(1, 8)
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return 0;

@@ -18,6 +18,8 @@ if world > 1 and os.environ.get('NO_DIST') != '1':
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 chunks = [bench.make_chunk(rank, v) for v in range(4)]
 eng = ChunkEngine()
+if os.environ.get('VL_NATIVE') == '0':
+    eng.native_submit = False
 kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32)
 
 def run(n):
@@ -51,6 +53,6 @@ for rep in range(3):
     ts = run(steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print('rank %d rep %d: %.3f ms/step (submit %.3f ms/step) affinity %d cores omp=%s' % (
-        rank, rep, 1e3 * dt / steps, 1e3 * ts / steps, len(os.sched_getaffinity(0)),
-        os.environ.get('OMP_NUM_THREADS')), flush=True)
+    print('rank %d rep %d: %.3f ms/step (submit %.3f ms/step) native_submits=%s affinity %d cores' % (
+        rank, rep, 1e3 * dt / steps, 1e3 * ts / steps, eng.stats.get('native_submits'),
+        len(os.sched_getaffinity(0))), flush=True)

@@ -159,6 +159,23 @@ class spx_gemm(C.Structure):
                 ('lo', C.c_double), ('hi', C.c_double), ('quad_slot', C.c_int32)]
 
 
+class spx_fast_cfg(C.Structure):
+    _fields_ = [('n_stn', C.c_int32), ('n_border', C.c_int32), ('kpad', C.c_int32),
+                ('max_steps', C.c_int32), ('n_slots', C.c_int32), ('min_systems', C.c_int32),
+                ('min_var_thr', C.c_double), ('ginv', C.c_void_p),
+                ('lambda_bound', C.c_double), ('lambda_tol', C.c_double),
+                ('estimator', C.c_int32), ('want_coef_t', C.c_int32), ('base_f', C.c_double),
+                ('local', spx_local), ('gemm', spx_gemm), ('profile', C.c_int32)]
+
+
+class spx_fast_result(C.Structure):
+    _fields_ = [('status', C.c_int32), ('slot', C.c_int32), ('n_grps', C.c_int32),
+                ('n_krige', C.c_int32), ('n_sys', C.c_int32), ('max_r', C.c_int32),
+                ('n_none', C.c_int32), ('n_single', C.c_int32), ('n_mean', C.c_int32),
+                ('launches', C.c_int32), ('h2d_bytes', C.c_int64), ('d_data', C.c_void_p),
+                ('host_ms', C.c_double * 6)]
+
+
 _SIGS = {
     'spx_version': (C.c_int, []),
     'spx_last_error': (C.c_char_p, []),
@@ -256,6 +273,19 @@ _SIGS = {
     'spx_round_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),
     'spx_round_stats_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'spx_fast_slot_bytes': (C.c_int64, [C.POINTER(spx_fast_cfg), C.c_int32]),
+    'spx_fast_create': (C.c_int, [C.POINTER(spx_fast_cfg), C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_void_p)]),
+    'spx_fast_destroy': (C.c_int, [C.c_void_p]),
+    'spx_fast_submit': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(spx_fast_result)]),
+    'spx_fast_check': (C.c_int, [C.c_void_p, C.c_int32, c_i32p]),
+    'spx_fast_times': (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float)]),
+    'spx_fast_timeline': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    'spx_ut_gemm_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
 }

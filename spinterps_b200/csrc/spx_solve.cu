@@ -1447,7 +1447,12 @@ int spx_krige_downdate_dev(const spx_downdate* d, void* stream) {
             SPX_CUDA(cudaGetDevice(&dev));
             SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin,
                                             dev));
-            const size_t sm_big = dl_smem_bytes(DD_REG_MAX), sm_small = dl_smem_bytes(DL_SMALL);
+            const size_t sm_big = dl_smem_bytes(DD_REG_MAX);
+            size_t sm_small = dl_smem_bytes(DL_SMALL);
+            // SPX_DL_SOLO=1: one solve block per SM (shared-memory request above half an
+            // SM's), which leaves room for three estimate blocks of the previous chunk
+            static const int solo = (getenv("SPX_DL_SOLO") && getenv("SPX_DL_SOLO")[0] == '1');
+            if (solo && sm_small < (size_t)116 * 1024) sm_small = (size_t)116 * 1024;
             static const int tf = (getenv("SPX_DD_LU_FAIL") && getenv("SPX_DD_LU_FAIL")[0] == '1');
             if (sm_big + 1024 <= (size_t)max_smem) {
                 if (dd.max_r > DL_SMALL) {

@@ -191,6 +191,13 @@ class ChunkEngine:
         # all-downdated chunks are planned by the native host planner (csrc/spx_plan.cu)
         # instead of the NumPy index logic of _krige / _solve_downdate
         self.native_plan = True
+        # ... and, when the whole chunk shares one variogram, submitted by ONE native call
+        # (csrc/spx_chunk.cu) whose solve phase runs on a second stream underneath the
+        # estimate kernel of the previous chunk
+        self.native_submit = True
+        self.fast_slots = 4
+        self._fast_jobs = {}
+        self._fast_prof = {}      # (job id, slot) -> (kernel, bound, work) awaiting its time
         # full-system inverses are reused across chunks with the same stations and
         # variogram (they do not depend on the data)
         self.multivg = True      # per-row-variogram estimator for variogram series
@@ -201,6 +208,7 @@ class ChunkEngine:
         self.local_tiles = True     # shared-memory staging of the coefficient slices
         self._local_cache = {}
         self._geom_cache = {}
+        self._token_cache = {}    # id(array) -> (weakref, sampled fingerprint, content token)
         self.pinv_flagged = True  # np.linalg.pinv semantics for untrustworthy OK/EDK systems
         self.ginv_cache = True
         self.ginv_cache_size = 8
@@ -309,6 +317,39 @@ class ChunkEngine:
         self._h2d_dirty = True
         self.h2d_bytes += arr.nbytes
         return d.view(tdt).view(arr.shape), fut
+
+    def _array_token(self, arr):
+        """Content token of a per-job input array (cell coordinates, cell mask): the keys
+        of the cross-chunk caches.  The 16-byte content hash is computed once per array
+        OBJECT; later chunks that pass the same object only pay for a strided sample of
+        ~256 elements (the whole array when it has <= 4096), which detects in-place
+        edits (shifted / rescaled / re-projected coordinates) and sends them through a
+        full rehash.  Distinct objects with equal content share their token."""
+        import hashlib
+        import weakref
+        a = np.asarray(arr)
+        n = a.size
+        flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+        step = 1 if n <= 4096 else n // 256
+        fp = (a.shape, a.dtype.str, hash(flat[::step].tobytes()),
+              hash(flat[-1:].tobytes()))
+        ent = self._token_cache.get(id(arr))
+        if ent is not None and ent[0]() is arr and ent[1] == fp:
+            return ent[2]
+        tok = (a.shape, a.dtype.str,
+               hashlib.blake2b(np.ascontiguousarray(a).view(np.uint8).reshape(-1),
+                               digest_size=16).digest())
+        try:
+            ref = weakref.ref(arr)
+        except TypeError:                   # not weak-referenceable (e.g. a list): no caching
+            return tok
+        if len(self._token_cache) >= 64:
+            for k_ in [k_ for k_, v in self._token_cache.items() if v[0]() is None]:
+                del self._token_cache[k_]
+            while len(self._token_cache) >= 64:
+                self._token_cache.pop(next(iter(self._token_cache)))
+        self._token_cache[id(arr)] = (ref, fp, tok)
+        return tok
 
     def _dev_const(self, arr):
         """Device copy of a small per-job constant (station coordinates): cached by
@@ -550,11 +591,14 @@ class ChunkEngine:
         edk_flag = 'EDK' in interp_types
         if krg_types:
             assert vgs is not None
-            vgs = list(vgs)
-            if set(map(type, vgs)) != {str}:
+            if not isinstance(vgs, list):
+                vgs = list(vgs)
+            vg_set = set(vgs)
+            if any(type(v) is not str for v in vg_set):
                 vgs = [str(v) for v in vgs]
+                vg_set = set(vgs)
             assert len(vgs) == n_steps
-            assert 'nan' not in set(vgs), (          # steps.py:504-507
+            assert 'nan' not in vg_set, (            # steps.py:504-507
                 'NaN VGs not allowed! Use Nugget or any other appropriate one!')
         if neb_sel_mthd not in ('all', 'nrst', 'pie'):
             raise NotImplementedError(f"neighbor selection '{neb_sel_mthd}'")
@@ -591,13 +635,10 @@ class ChunkEngine:
         fld_beg_idx = fld_beg_row * fld_n_cols
         fld_end_idx = fld_end_row * fld_n_cols
         fld_size = (fld_end_row - fld_beg_row) * fld_n_cols
-        mid = cell_xs.size // 2
-        gkey = (cell_xs.__array_interface__['data'][0], cell_ys.__array_interface__['data'][0],
-                cell_xs.size, fld_beg_row, fld_end_row, fld_n_cols,
-                None if cntn_idxs is None else (np.asarray(cntn_idxs).__array_interface__['data'][0],
-                                                int(np.asarray(cntn_idxs).size)),
-                float(cell_xs[0]), float(cell_xs[-1]), float(cell_xs[mid]),
-                float(cell_ys[0]), float(cell_ys[-1]), float(cell_ys[mid]))
+        # keyed by CONTENT (see _array_token), not by buffer addresses
+        gkey = (self._array_token(cell_xs), self._array_token(cell_ys),
+                None if cntn_idxs is None else self._array_token(cntn_idxs),
+                fld_beg_row, fld_end_row, fld_n_cols)
         geo = self._geom_cache.get(gkey)
         if geo is None:
             if cntn_idxs is not None:
@@ -618,7 +659,7 @@ class ChunkEngine:
                        d_pos=self._dev(out_pos) if out_pos is not None else None,
                        bbox=(float(dst_xs.min()), float(dst_xs.max()), float(dst_ys.min()),
                              float(dst_ys.max())),
-                       fp=(int(dst_xs.size), float(dst_xs.sum()), float(dst_ys.sum())))
+                       fp=gkey)
             while len(self._geom_cache) >= 4:
                 self._geom_cache.pop(next(iter(self._geom_cache)))
             self._geom_cache[gkey] = geo
@@ -642,17 +683,43 @@ class ChunkEngine:
                     stns_drft = np.ascontiguousarray(np.asarray(stns_drft)[tke])
                 n_stn = int(tke.size)
 
-        # The data block goes to the device from a helper thread: a host -> device copy
-        # from pageable memory blocks its caller for the whole staging copy (0.4 ms for
-        # 5 MB), and both that call and the native planner below run without the GIL.
-        d_data, data_upload = self._dev_threaded(data)
+        d_stn_x = self._dev_const(stn_xs)
+        d_stn_y = self._dev_const(stn_ys)
+        d_cell_x, d_cell_y, d_pos = geo['d_cell_x'], geo['d_cell_y'], geo['d_pos']
+        ctx = _LazyCtx(
+            n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
+            d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
+            out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys, stn_xs=stn_xs, stn_ys=stn_ys,
+            has_lo=int(min_var_cut is not None), has_hi=int(max_var_cut is not None),
+            lo=float(min_var_cut) if min_var_cut is not None else 0.0,
+            hi=float(max_var_cut) if max_var_cut is not None else 0.0,
+            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'],
+            geom_key=gkey)
+        tdtype = torch.float64 if out_f64 else torch.float32
 
-        # ---- per-step host logic (native: csrc/spx_plan.cu) ------------------
+        # ---- one native call for the whole kriging label (csrc/spx_chunk.cu) ---------
+        fast = None
+        if (self.native_submit and self.native_plan and self.downdate and self.ginv_cache
+                and not nrst and not ev_flag and krg_types == ['OK'] and len(vg_set) == 1
+                and not self.sync_timing and not self.trace_launches):
+            fast = self._fast_submit(ctx, data, vgs[0], float(min_var_thr), tdtype,
+                                     interp_labels[interp_types.index('OK')])
+
         t_host0 = time.perf_counter()
-        # availability groups (grps.py:57-101) and per-step flags (steps.py:760-765) in
-        # one pass over the data; byte masks are expanded only if a path asks for them
-        grp_of_step, grp_bits, grp_n, grp_first, n_avail, steps_flags = _lib.avail_groups(
-            data, float(min_var_thr), want_mask=False)
+        if fast is not None:
+            grp_of_step, grp_bits, grp_n, grp_first, n_avail, steps_flags = fast['groups']
+            data_upload = None
+        else:
+            # The data block goes to the device from a helper thread: a host -> device copy
+            # from pageable memory blocks its caller for the whole staging copy (0.4 ms for
+            # 5 MB), and both that call and the native planner below run without the GIL.
+            d_data, data_upload = self._dev_threaded(data)
+            ctx['d_data'] = d_data
+            # availability groups (grps.py:57-101) and per-step flags (steps.py:760-765) in
+            # one pass over the data (native: csrc/spx_plan.cu); byte masks are expanded
+            # only if a path asks for them
+            grp_of_step, grp_bits, grp_n, grp_first, n_avail, steps_flags = _lib.avail_groups(
+                data, float(min_var_thr), want_mask=False)
         n_grps = int(grp_bits.shape[0])
         problem_steps = [int(s) for s in np.where(n_avail == 0)[0]]   # steps.py:677-688
 
@@ -662,27 +729,15 @@ class ChunkEngine:
         single_val_of = lambda idx: np.nansum(data[idx], axis=1)    # noqa: E731  n_avail == 1
 
         self.timing['host_groups'] = 1e3 * (time.perf_counter() - t_host0)
-        # ---- device residents -----------------------------------------------
-        d_stn_x = self._dev_const(stn_xs)
-        d_stn_y = self._dev_const(stn_ys)
-        d_cell_x, d_cell_y, d_pos = geo['d_cell_x'], geo['d_cell_y'], geo['d_pos']
         if data_upload is not None:
             data_upload.result()               # re-raises a failure of the copy
-        ctx = _LazyCtx(
-            n_steps=n_steps, n_stn=n_stn, n_cells=n_cells, fld_size=fld_size, out_f64=out_f64,
-            d_stn_x=d_stn_x, d_stn_y=d_stn_y, d_cell_x=d_cell_x, d_cell_y=d_cell_y, d_pos=d_pos,
-            d_data=d_data, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
-            stn_xs=stn_xs, stn_ys=stn_ys,
-            has_lo=int(min_var_cut is not None), has_hi=int(max_var_cut is not None),
-            lo=float(min_var_cut) if min_var_cut is not None else 0.0,
-            hi=float(max_var_cut) if max_var_cut is not None else 0.0,
-            grp_of_step=grp_of_step, grp_n=grp_n, n_avail=n_avail, n_grps=n_grps,
-            grp_first=grp_first,
-            min_vg_val=float(min_vg_val), nnb_cache={}, bbox=geo['bbox'], geom_fp=geo['fp'])
+        ctx.update(grp_of_step=grp_of_step, grp_n=grp_n, n_avail=n_avail, n_grps=n_grps,
+                   grp_first=grp_first)
 
         def _d_data0():
+            d = ctx['d_data']
             self._sync_uploads()
-            return torch.nan_to_num(d_data, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
+            return torch.nan_to_num(d, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
 
         def _d_grp_mask():
             # availability masks on the device (+ one all-ones row = "every station")
@@ -690,16 +745,23 @@ class ChunkEngine:
                 [ctx['grp_mask'].view(np.uint8), np.ones((1, n_stn), dtype=np.uint8)], axis=0))
 
         ctx.lazy = dict(grp_mask=lambda: _lib.unpack_group_bits(grp_bits, n_stn),
-                        d_data0=_d_data0, d_grp_mask=_d_grp_mask)
+                        d_data0=_d_data0, d_grp_mask=_d_grp_mask,
+                        d_data=lambda: self._dev(data))
 
-        tdtype = torch.float64 if out_f64 else torch.float32
         # NaN marks cells outside the mask and steps without stations
         # (steps.py:659-663); when every cell of every step is written the 4-byte
         # per cell-step prefill is skipped
         full_cover = (out_pos is None) and bool((n_avail >= 1).all())
         flds = {}
         for lab in interp_labels:
-            if full_cover and lab != 'EST_VARS_OK':
+            if fast is not None and lab == fast['label']:
+                flds[lab] = fast['out']
+                if out_pos is None and not full_cover:
+                    # allocated before the availability was known: NaN rows written now
+                    none_steps = np.where(n_avail == 0)[0]
+                    self._fill_rows(ctx, fast['out'], none_steps,
+                                    np.full(none_steps.size, np.nan), clamp=False)
+            elif full_cover and lab != 'EST_VARS_OK':
                 flds[lab] = torch.empty((n_steps, fld_size), dtype=tdtype, device=self.device)
             else:
                 flds[lab] = torch.full((n_steps, fld_size), float('nan'), dtype=tdtype,
@@ -716,7 +778,14 @@ class ChunkEngine:
             if single_steps.size:
                 self._fill_rows(ctx, out, single_steps, single_val_of(single_steps))
             multi = n_avail >= 2
-            if itype == 'NNB':
+            if fast is not None and lab == fast['label']:
+                # kriged steps are already queued (one variogram, not nugget-only)
+                if fast['res'].n_mean:
+                    mean_steps = np.where(multi & ~steps_flags)[0]   # steps.py:325-331
+                    self._fill_rows(ctx, out, mean_steps, ref_means_of(mean_steps))
+                deferred.append(self._fast_deferred(ctx, fast, out, multi & steps_flags,
+                                                    problem_steps))
+            elif itype == 'NNB':
                 self._nnb_label(ctx, out, np.where(multi)[0])
             elif itype == 'IDW' and nrst:
                 self._nrst(ctx, out, 'IDW', np.where(multi)[0], int(n_nebs),
@@ -960,7 +1029,9 @@ class ChunkEngine:
             if mx <= cap:
                 break
             cap = mx
-        keep = [cnt, idx, val, d_bs, d_bo]
+        # every tensor whose address sits in the cached struct stays referenced with it
+        keep = [cnt, idx, val, d_bs, d_bo, ctx['d_stn_x'], ctx['d_stn_y'], ctx['d_cell_x'],
+                ctx['d_cell_y']]
         if ctx['n_stn'] <= 65536 and self.local_tiles:
             # distinct near stations per tile of 256 cells: the streamlined kernel stages
             # their coefficient slices in shared memory
@@ -1332,6 +1403,222 @@ class ChunkEngine:
                 dmax = np.nanmax(np.abs(drft)) if np.isfinite(drft).any() else 1.0
             rhs_bound = np.maximum(rhs_bound, dmax)
         return rhs_bound
+
+    # ---- one native call per chunk (csrc/spx_chunk.cu) ---------------------------
+    def _fast_job(self, ctx, vg_s, min_var_thr, n_steps):
+        """The native job (ring of pre-allocated slots, solve stream, events) for this
+        station set / variogram / grid, created on first use.  None when the chunk
+        does not qualify: the full-system inverse is not cached yet (the general path
+        builds it), nugget-only variogram, ..."""
+        if check_full_nuggetness(vg_s, ctx['min_vg_val']):
+            return None
+        n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
+        n_border = 1
+        kpad = _pad_up(n_stn + n_border, 8)
+        K = types.SimpleNamespace(kind=0, n_drifts=0, n_border=n_border, kpad=kpad,
+                                  uniq_vgs=[vg_s], d_stn_drift=None)
+        gkey = (self._ginv_key(ctx, K), vg_s)
+        ginv = self._ginv_cache.get(gkey)
+        if ginv is None:
+            return None
+        jkey = (gkey, ctx['geom_key'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'], ctx['lo'],
+                ctx['hi'], min_var_thr, self.local_support, self.local_max_near,
+                self.local_tiles, self.lambda_tol, self.downdate_min_systems)
+        job = self._fast_jobs.get(jkey)
+        if job is not None and job['max_steps'] >= n_steps and job['ginv'] is ginv:
+            return job
+        if job is not None:
+            self._fast_job_close(jkey)
+        lib = self.lib
+        cfg = _lib.spx_fast_cfg()
+        cfg.n_stn, cfg.n_border, cfg.kpad = n_stn, n_border, kpad
+        cfg.max_steps = int(n_steps)
+        cfg.n_slots = int(self.fast_slots)
+        cfg.min_systems = int(self.downdate_min_systems)
+        cfg.min_var_thr = float(min_var_thr)
+        cfg.ginv = ginv.data_ptr()
+        cfg.lambda_bound = float(self._rhs_bound(ctx, K, None)[0])
+        cfg.lambda_tol = float(self.lambda_tol)
+        cfg.profile = 1
+        keep = [ginv, ctx['d_stn_x'], ctx['d_stn_y'], ctx['d_cell_x'], ctx['d_cell_y'],
+                ctx['d_pos']]
+        local = self._local_plan(ctx, [vg_s]) if self.local_support else None
+        if local is not None:
+            nbr = self._local_neighbours(ctx, K, vg_s, local[0])
+            keep.append(nbr)
+            L = nbr['struct']
+            L.kpad, L.n_stn, L.n_drifts = kpad, n_stn, 0
+            L.cell_drift = None
+            L.out_ld = ctx['fld_size']
+            L.out_f64 = ctx['out_f64']
+            L.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+            L.has_lo, L.has_hi, L.lo, L.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            L.rows_all_valid = 1
+            cfg.estimator = 0
+            cfg.want_coef_t = int(self._local_wants_coef_t(ctx, 0))
+            tot = local[0][1]
+            cfg.base_f = float(tot if tot > ctx['min_vg_val'] else 0.0)
+            cfg.local = L
+        else:
+            g = _lib.spx_gemm()
+            g.kpad, g.n_stn, g.n_border = kpad, n_stn, n_border
+            g.stn_x, g.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
+            g.cell_x, g.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
+            g.n_cells = n_cells
+            g.cell_drift = None
+            g.gen, g.covar_flag = _lib.GEN_VG, 0
+            g.vg = _lib.make_vg(vg_s)
+            g.min_vg_val = ctx['min_vg_val']
+            g.idw_exp, g.dist_scale = 0.0, 1.0
+            g.epi = _lib.EPI_FIELD
+            g.row_aux = None
+            g.out_ld = ctx['fld_size']
+            g.out_f64 = ctx['out_f64']
+            g.cell_pos = ctx['d_pos'].data_ptr() if ctx['d_pos'] is not None else None
+            g.aux = None
+            g.has_lo, g.has_hi, g.lo, g.hi = ctx['has_lo'], ctx['has_hi'], ctx['lo'], ctx['hi']
+            g.quad_slot = 0
+            cfg.estimator = 1
+            cfg.want_coef_t = 0
+            cfg.gemm = g
+        d_bytes = int(lib.spx_fast_slot_bytes(C.byref(cfg), 0))
+        h_bytes = int(lib.spx_fast_slot_bytes(C.byref(cfg), 1))
+        if d_bytes <= 0 or h_bytes <= 0:
+            return None
+        self._sync_uploads()
+        # tables built just now (first chunk of a job) are read by the solve stream
+        torch.cuda.current_stream(self.device).synchronize()
+        d_arena = torch.empty(cfg.n_slots * d_bytes, dtype=torch.uint8, device=self.device)
+        h_arena = torch.empty(cfg.n_slots * h_bytes, dtype=torch.uint8, pin_memory=True)
+        handle = C.c_void_p()
+        _lib.check(lib.spx_fast_create(C.byref(cfg), C.c_void_p(d_arena.data_ptr()),
+                                       C.c_void_p(h_arena.data_ptr()), C.byref(handle)),
+                   'fast_create')
+        W = (n_stn + 63) // 64
+        job = dict(handle=handle, cfg=cfg, keep=keep, d_arena=d_arena, h_arena=h_arena,
+                   max_steps=int(n_steps), ginv=ginv, estimator=int(cfg.estimator), W=W,
+                   next_slot=0, id=self._next_job_id(),
+                   res=_lib.spx_fast_result())
+        while len(self._fast_jobs) >= 2:
+            self._fast_job_close(next(iter(self._fast_jobs)))
+        self._fast_jobs[jkey] = job
+        return job
+
+    def _next_job_id(self):
+        self._fast_job_seq = getattr(self, '_fast_job_seq', 0) + 1
+        return self._fast_job_seq
+
+    def _fast_job_close(self, jkey):
+        job = self._fast_jobs.pop(jkey, None)
+        if job is not None:
+            self._fast_collect(job, all_slots=True)
+            _lib.check(self.lib.spx_fast_destroy(job['handle']), 'fast_destroy')
+
+    def close(self):
+        """Release the native jobs (their streams and events)."""
+        for jkey in list(self._fast_jobs):
+            self._fast_job_close(jkey)
+
+    def _fast_collect(self, job, slot=None, all_slots=False):
+        """Move the measured estimate times of finished slots into kernel_events
+        (profile_gemm): a slot's events are re-recorded when the ring comes round."""
+        slots = range(job['cfg'].n_slots) if all_slots else [slot]
+        for k in slots:
+            rec = self._fast_prof.pop((job['id'], k), None)
+            if rec is None:
+                continue
+            ms = C.c_float(0.0)
+            _lib.check(self.lib.spx_fast_times(job['handle'], k, C.byref(ms), None), 'fast_times')
+            self.kernel_events.append(rec + (float(ms.value), None))
+
+    def collect_profile(self):
+        """Finish kernel_events (synchronises the estimate launches still in flight)."""
+        for job in self._fast_jobs.values():
+            self._fast_collect(job, all_slots=True)
+
+    def _fast_submit(self, ctx, data, vg_s, min_var_thr, tdtype, label):
+        """Queue the whole kriging label of the chunk with one native call; None if
+        the chunk does not qualify (nothing queued then)."""
+        n_steps, n_stn = ctx['n_steps'], ctx['n_stn']
+        job = self._fast_job(ctx, vg_s, min_var_thr, n_steps)
+        if job is None:
+            return None
+        if job['estimator'] == 0 and not self.local_support:
+            return None
+        if self.profile_gemm or self._fast_prof:
+            self._fast_collect(job, slot=job['next_slot'])
+        if ctx['out_pos'] is None:
+            out = torch.empty((n_steps, ctx['fld_size']), dtype=tdtype, device=self.device)
+        else:
+            out = torch.full((n_steps, ctx['fld_size']), float('nan'), dtype=tdtype,
+                             device=self.device)
+        ints = np.empty((4, n_steps), dtype=np.int32)    # grp_of_step, grp_first, grp_n, n_avail
+        step_flag = np.empty(n_steps, dtype=np.uint8)
+        grp_bits = np.empty((n_steps, job['W']), dtype=np.uint64)
+        res = _lib.spx_fast_result()
+        self._sync_uploads()
+        self._main_stream()
+        _lib.check(self.lib.spx_fast_submit(
+            job['handle'], data.ctypes.data, n_steps, data.strides[0] // 8,
+            C.c_void_p(out.data_ptr()), self._main_handle, ints[0].ctypes.data,
+            ints[1].ctypes.data, ints[2].ctypes.data, ints[3].ctypes.data, step_flag.ctypes.data,
+            grp_bits.ctypes.data, C.byref(res)), 'fast_submit')
+        g = int(res.n_grps)
+        groups = (ints[0], grp_bits[:g], ints[2, :g].astype(np.int64), ints[1, :g],
+                  ints[3].astype(np.int64), step_flag.view(np.bool_))
+        if res.status != 0:
+            # not eligible (too few systems, too many missing stations): the grouping is
+            # still good, the general path takes the label
+            self._count('fast_not_eligible')
+            return dict(label=None, groups=groups, res=res, out=None, job=job)
+        job['next_slot'] = (int(res.slot) + 1) % job['cfg'].n_slots
+        hm = self.stats.setdefault('fast_host_ms', [0.0] * 6)
+        for i in range(6):
+            hm[i] += res.host_ms[i]
+        self._count('launches', int(res.launches))
+        self._count('native_submits')
+        self._count('n_systems', int(res.n_sys))
+        self._count('n_downdated', int(res.n_sys))
+        self._count('ginv_cache_hits')
+        self.h2d_bytes += int(res.h2d_bytes)
+        n_cells = ctx['n_cells']
+        esz = 8 if ctx['out_f64'] else 4
+        if job['estimator'] == 0:
+            self._count('local_rows', int(res.n_krige))
+            self._count('local_cache_hits')
+            rec = ('k_estimate_local', 'hbm', float(int(res.n_krige) * n_cells * esz))
+        else:
+            flop = 2.0 * int(res.n_krige) * job['cfg'].kpad * n_cells
+            self._count('gemm_launches')
+            self._count('gemm_flop', int(flop))
+            rec = ('k_estimate_gemm', 'tensor', flop)
+        if self.profile_gemm:
+            self._fast_prof[(job['id'], int(res.slot))] = rec
+        return dict(label=label, groups=groups, res=res, out=out, job=job, vg=vg_s)
+
+    def _fast_deferred(self, ctx, fast, out, krige_mask, problem_steps):
+        job, slot = fast['job'], int(fast['res'].slot)
+
+        def deferred():
+            """Health flags of the slot (mapped host memory): an unhealthy elimination or
+            a system whose weights may not sum to one sends the label through the general
+            path, which knows every fallback of the reference."""
+            verdict = C.c_int32(0)
+            _lib.check(self.lib.spx_fast_check(job['handle'], slot, C.byref(verdict)),
+                       'fast_check')
+            if verdict.value == 0:
+                self.stats['n_flagged'] = self.stats.get('n_flagged', 0)
+                return
+            unhealthy = verdict.value == 1
+            self._count('downdate_redo' if unhealthy else 'fast_path_redo')
+            steps = np.where(krige_mask)[0]
+            fn = self._krige(ctx, out, 'OK', steps, np.zeros(ctx['n_steps'], dtype=np.int32),
+                             [fast['vg']], None, None, problem_steps, force_direct=unhealthy,
+                             no_fast=True)
+            if fn is not None:
+                fn()
+
+        return deferred
 
     def _krige_fast(self, ctx, out, kind_name, K, steps, step_vg, uniq_vgs, drft, drft_arrs,
                     stns_drft, problem_steps):

@@ -285,14 +285,16 @@ def test_local_estimator_is_used_and_matches_dense():
         assert rel_err(got[lab], exp[lab], _floor(exp[lab])) <= KRG_TOL, lab
 
 
+@pytest.mark.parametrize('submit', ['native', 'python'])
 @pytest.mark.parametrize('variant', ['local_f64', 'local_f32', 'dense', 'edk_two_vgs', 'flagged'])
-def test_native_planned_fast_path_matches_general_path(variant):
+def test_native_planned_fast_path_matches_general_path(variant, submit):
     """Chunks after the first of a job (full-system inverse cached) are planned by the
     native host planner and solved by one downdate launch per variogram that also emits
-    the local estimator's base / transposed coefficients (engine._krige_fast).  Same
-    numbers as the general NumPy-planned path and the oracle; repeated availability
-    patterns, a single-station step, a step without stations and a low-value step ride
-    along."""
+    the local estimator's base / transposed coefficients (engine._krige_fast); with one
+    variogram per chunk the whole label is ONE native call whose solve phase runs on a
+    second stream (spx_fast_submit, submit == 'native').  Same numbers as the general
+    NumPy-planned path and the oracle; repeated availability patterns, a single-station
+    step, a step without stations and a low-value step ride along."""
     from spinterps_b200.engine import ChunkEngine
     n_steps = 40
     p = make_problem(61, 130, n_steps, 45, 52, cell=4000.0, miss=0.15)
@@ -334,6 +336,7 @@ def test_native_planned_fast_path_matches_general_path(variant):
         e = ChunkEngine()
         e.local_support = local
         e.native_plan = native
+        e.native_submit = native and submit == 'native'
         if lambda_tol is not None:
             e.lambda_tol = lambda_tol
         e.interp_chunk(p['data'], intrp_dtype=dt, **kw, **base)      # fills the caches
@@ -342,7 +345,11 @@ def test_native_planned_fast_path_matches_general_path(variant):
 
     e1, got, prob1 = run(True)
     e0, ref, prob0 = run(False)
-    assert e1.stats.get('native_plans', 0) >= 1 and e0.stats.get('native_plans', 0) == 0
+    if submit == 'native' and variant != 'edk_two_vgs':
+        assert e1.stats.get('native_submits', 0) == 1 and e1.stats.get('native_plans', 0) == 0
+    else:
+        assert e1.stats.get('native_plans', 0) >= 1 and e1.stats.get('native_submits', 0) == 0
+    assert e0.stats.get('native_plans', 0) == 0 and e0.stats.get('native_submits', 0) == 0
     assert prob1 == prob0 == [12]
     if variant == 'flagged':
         assert e1.stats.get('fast_path_redo', 0) + e1.stats.get('downdate_redo', 0) >= 1
@@ -385,3 +392,67 @@ def test_local_kernel_tile_staging_is_bit_identical(n_stn, vg, note):
     assert np.array_equal(outs[0], outs[1], equal_nan=True), note
     exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
     assert rel_err(outs[0], exp['OK'].astype(np.float32), _floor(exp['OK'])) <= 3e-7
+
+
+@pytest.mark.parametrize('n_stn,n_rows,n_data,n_border', [(130, 77, 50, 1), (500, 300, 200, 1),
+                                                           (64, 64, 64, 2), (33, 5, 3, 3)])
+def test_ut_gemm_matches_matmul(n_stn, n_rows, n_data, n_border):
+    """Ut = Bt . G on the FP64 tensor cores with Bt generated from the resident data block
+    (spx_ut_gemm_dev) against the dense product of the explicitly built Bt."""
+    import ctypes as C
+    import torch
+    from spinterps_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    T = 40
+    data = rng.gamma(1.0, 5.0, size=(T, n_stn))
+    data[rng.random(data.shape) < 0.2] = np.nan
+    M = n_stn + n_border
+    G = rng.normal(size=(M, M))
+    G = G + G.T
+    src = rng.integers(0, T, size=n_rows).astype(np.int32)
+    bt = np.zeros((n_rows, M))
+    fin = np.isfinite(data[src])
+    bt[:n_data, :n_stn] = np.where(fin[:n_data], data[src[:n_data]], 0.0)
+    bt[n_data:, :n_stn] = fin[n_data:].astype(float)
+    d_data = torch.from_numpy(data).cuda()
+    d_src = torch.from_numpy(src).cuda()
+    d_G = torch.from_numpy(G).cuda()
+    ut = torch.full((n_rows, M), float('nan'), dtype=torch.float64, device='cuda')
+    _lib.check(lib.spx_ut_gemm_dev(
+        C.c_void_p(d_data.data_ptr()), n_stn, n_stn, C.c_void_p(d_src.data_ptr()), n_rows, n_data,
+        n_border, C.c_void_p(d_G.data_ptr()), C.c_void_p(ut.data_ptr()),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'ut_gemm')
+    torch.cuda.synchronize()
+    exp = bt @ G
+    scale = np.abs(bt) @ np.abs(G) + 1e-300
+    assert np.max(np.abs(ut.cpu().numpy() - exp) / scale) <= 1e-14
+
+
+def test_native_submit_pipeline_many_chunks():
+    """Several chunks in flight through the native submit (ring of slots, solve stream
+    overlapping the previous estimate): every chunk's field equals the one computed alone by
+    the Python-planned path; chunk sizes vary (ragged last chunk)."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(81, 120, 64, 40, 50, cell=4000.0, miss=0.2)
+    base = {k: v for k, v in p.items() if k != 'data'}
+    kw = dict(interp_args=[('OK', None, 'OK')], intrp_dtype=np.float32, **base)
+    rng = np.random.default_rng(82)
+    chunks = []
+    for n in (64, 64, 30, 64, 17, 64, 64, 5, 64):
+        d = rng.gamma(1.0, 5.0, size=(n, 120))
+        d[rng.random(d.shape) < 0.2] = np.nan
+        chunks.append(d)
+    e1 = ChunkEngine()
+    e1.interp_chunk(chunks[0], vgs=[VG_C1] * 64, **kw)           # caches
+    pend = [e1.submit_chunk(d, vgs=[VG_C1] * d.shape[0], **kw) for d in chunks]
+    outs = [pd.result()[0]['OK'] for pd in pend]
+    assert e1.stats.get('native_submits', 0) == 1
+    e0 = ChunkEngine()
+    e0.native_submit = False
+    e0.interp_chunk(chunks[0], vgs=[VG_C1] * 64, **kw)
+    for d, got in zip(chunks, outs):
+        ref, _ = e0.interp_chunk(d, vgs=[VG_C1] * d.shape[0], **kw)
+        assert got.shape == ref['OK'].shape
+        assert rel_err(got, ref['OK'], _floor(ref['OK'])) <= 3e-7
+    e1.close()

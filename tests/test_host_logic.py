@@ -276,8 +276,9 @@ def test_native_downdate_plan_matches_numpy(seed, T, N, miss):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints
-    ONE JSON line with the keys the driver reads."""
+    """`bench.py --impl reference` (the CPU arm: the compiled reference of oracle/_ref, else
+    the oracle port, on the host cores) prints ONE JSON line with the keys the driver
+    reads."""
     import json
     import os
     import subprocess
@@ -292,7 +293,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['impl'] == 'reference' and d['unit'] == 'cell-steps/s' and d['value'] > 0
     assert d['metric'].startswith('interpolated cell-steps/s')
     assert d['higher_is_better'] is True and d['steps'] == 1 and d['warmup'] == 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    from oracle import ref_runner
+    kind = 'reference' if ref_runner.available() else 'port'   # oracle/_ref built or not
+    assert d['cpu_baseline']['kind'] == kind and d['cpu_baseline']['cores'] >= 1
     assert d['cpu_baseline']['value'] == d['value'] and 'sample' in d['cpu_baseline']
     assert d['e2e'] == {'value': d['value'], 'unit': 'cell-steps/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
