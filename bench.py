@@ -41,6 +41,7 @@ CHUNK_STEPS = 1250   # one rank's shard of config 2 (10,000 steps) on 8 x B200
 MISS = 0.2
 VG = '0.1 Nug(0.0) + 0.9 Sph(20000)'
 INTERP_ARGS = [('OK', None, 'OK')]
+NMRL_PRCN = 2        # decimals the writer rounds to (reference test/test_interp.py:46)
 WORKLOAD = ('C2 time shard (1/8 of its 10,000 steps): OK, 500 stations x %d daily steps (20%% '
             'missing, ~1 availability group per step) -> 1000x1000 grid, vg %s'
             % (CHUNK_STEPS, VG))
@@ -242,6 +243,192 @@ def dgemm_peak_tflops(torch, n=6144, reps=4):
     return 2.0 * n ** 3 / best / 1e9
 
 
+def hbm_peak():
+    hbm, src = 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+    mp = ROOT / 'MEASURED_PEAKS.json'
+    if mp.exists():
+        try:
+            hbm = float(json.loads(mp.read_text())['hbm_gbs'])
+            src = 'MEASURED_PEAKS.json hbm_gbs (copy, read + write)'
+        except Exception:
+            pass
+    return hbm, src
+
+
+def summarise_events(events):
+    """Per kernel: total time, work, launches; returns (dominant kernel dict, all)."""
+    by = {}
+    for name, bound, work, e0, e1 in events:
+        d = by.setdefault(name, dict(bound=bound, work=0.0, ms=0.0, n=0))
+        d['work'] += work
+        # native submits report the milliseconds between their own CUDA events
+        d['ms'] += e0 if e1 is None else e0.elapsed_time(e1)
+        d['n'] += 1
+    if not by:
+        return None, {}
+    name = max(by, key=lambda k_: by[k_]['ms'])
+    by[name]['kernel'] = name
+    return by[name], by
+
+
+def roofline_of(d, peak_f64, traffic_tbl=None):
+    if d is None:
+        return None
+    hbm, hbm_src = hbm_peak()
+    avg_ms = d['ms'] / d['n']
+    per_launch = d['work'] / d['n']
+    if d['bound'] == 'tensor':
+        ach = per_launch / (avg_ms / 1e3) / 1e12
+        peak, unit = peak_f64, 'TFLOP/s'
+        src = ('FP64 tensor: cuBLAS DGEMM 6144^3 via torch.matmul measured live in this '
+               'run (MEASURED_PEAKS.json has no FP64 entry); DMMA issue-rate '
+               'microbenchmark 37.15 TFLOP/s in profiles/microbench')
+    elif d['bound'] == 'alu':
+        ach = per_launch / (avg_ms / 1e3) / 1e12
+        peak, unit = 33.9, 'TFLOP/s'
+        src = 'FP64 ALU: DFMA issue-rate microbenchmark 33.9 TFLOP/s (profiles/microbench)'
+    else:
+        ach = per_launch / (avg_ms / 1e3) / 1e9
+        peak, unit, src = hbm, 'GB/s', hbm_src
+    t = (traffic_tbl or {}).get(d['kernel'], {})
+    return {'kernel': 'spx::' + d['kernel'], 'bound': d['bound'], 'achieved': ach,
+            'peak': peak, 'unit': unit, 'frac': ach / peak,
+            'traffic': t.get('dram_bytes_per_launch'),
+            'traffic_source': ('profiles/kernel_traffic.json: one `ncu --set full` capture of '
+                               'this kernel on this workload (static, not re-measured per run)'
+                               if t else None),
+            'algorithmic_per_launch': per_launch, 'avg_launch_ms': avg_ms,
+            'launches_timed': d['n'], 'peak_source': src}
+
+
+CONFIG_NOTE = {
+    'C1': 'C1: test_interp-style run, OK + IDW(2), 100 stations x 365 daily steps -> 200x200 grid',
+    'C3': 'C3 time chunk: EDK with an elevation drift, 300 stations x 250 of its 5,000 steps -> '
+          '2000x2000 grid, one variogram string per step',
+    'C4': 'C4 time chunk: IDW exponents {1,2,3,5}, 2,000 stations x 1,000 of its 20,000 hourly '
+          'steps -> 1000x1000 grid',
+    'C5': 'C5 time chunk: SK + OK, 1,000 stations x 100 of its 2,000 steps -> 4000x4000 grid with '
+          'an elliptic cell mask (~49 % of the cells)',
+}
+
+
+def run_config(args):
+    """`--config C1|C3|C4|C5`: one bench step = one time chunk of that BASELINE.json
+    configuration on every rank (weak scaling, as for the default C2 line)."""
+    import torch
+    import torch.distributed as dist
+    from spinterps_b200.engine import ChunkEngine
+    from tests.synth import CONFIG_CHUNK, config_problem
+
+    cfg = args.config
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    chunk = CONFIG_CHUNK[cfg]
+    variants = []
+    for v in range(2):
+        p, kw = config_problem(cfg, chunk, seed_shift=1 + 16 * rank + v)
+        variants.append((p, kw))
+    base = {k: v for k, v in variants[0][0].items() if k != 'data'}
+    n_labels = len(variants[0][1]['interp_args'])
+    G = int(variants[0][0]['cell_xs'].size)
+    cell_steps = n_labels * G * chunk
+    eng = ChunkEngine()
+    counter = [0]
+
+    def submit(**extra):
+        counter[0] += 1
+        p, kw = variants[counter[0] % 2]
+        return eng.submit_chunk(p['data'], intrp_dtype=np.float32, **base, **kw, **extra)
+
+    def run_resident(n):
+        pend = None
+        for _ in range(n):
+            nxt = submit()
+            if pend is not None:
+                pend.result(to_host=False)
+            pend = nxt
+        pend.result(to_host=False)
+
+    def run_e2e(n):
+        for _ in range(n):
+            submit(round_decimals=NMRL_PRCN, field_stats=True).result(to_host=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(n)
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    run_resident(max(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile_gemm = True
+    eng.kernel_events = []
+    l0 = eng.total_launches
+    ms = timed(run_resident, args.steps)
+    launches = eng.total_launches - l0
+    eng.collect_profile()
+    dom, by = summarise_events(eng.kernel_events)
+    eng.profile_gemm = False
+    stats = dict(eng.stats)
+    n_e2e = max(1, min(args.steps, 3))
+    run_e2e(1)
+    h2d0 = eng.h2d_bytes
+    d2h0 = eng._dl.d2h_bytes if eng._dl is not None else 0
+    ms_e2e = timed(run_e2e, n_e2e)
+    d2h = (eng._dl.d2h_bytes - d2h0) if eng._dl is not None else n_e2e * cell_steps * 4
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        peak_f64 = dgemm_peak_tflops(torch)
+        line = {
+            'metric': 'interpolated cell-steps/s (FP64 arithmetic, f32 store)',
+            'value': world * cell_steps * args.steps / (ms / 1e3), 'unit': 'cell-steps/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': CONFIG_NOTE[cfg], 'config': cfg, 'chunk_steps': chunk,
+                       'cells': G, 'labels': [a[2] for a in variants[0][1]['interp_args']],
+                       'parallelism': 'time-sharded x%d' % world,
+                       'l2': 'each step writes %.1f GB of fields (>> 126 MB L2)'
+                             % (cell_steps * 4 / 1e9)},
+            'e2e': {'value': world * cell_steps * n_e2e / (ms_e2e / 1e3), 'unit': 'cell-steps/s',
+                    'h2d_bytes_per_step': int((eng.h2d_bytes - h2d0) / n_e2e),
+                    'd2h_bytes_per_step': int(d2h / n_e2e), 'ms_per_step': ms_e2e / n_e2e,
+                    'note': 'submit_chunk(round_decimals=2, field_stats=True).result(): '
+                            'synchronous, the rounded fields come back as host arrays'},
+            'gpu_launches': int(launches),
+            'roofline': roofline_of(dom, peak_f64),
+            'kernels': {k_: {'ms_per_step': v['ms'] / args.steps, 'launches_per_step': v['n'] / args.steps,
+                             'bound': v['bound']} for k_, v in by.items()},
+            'engine_stats': {k_: (int(v_) if isinstance(v_, (int, np.integer)) else None)
+                             for k_, v_ in stats.items() if isinstance(v_, (int, np.integer))},
+            'cpu_baseline': None, 'clocks': sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -291,22 +478,74 @@ def run_gpu(args):
             pend = nxt
         pend.result(to_host=False)
 
-    # pinned host buffers for the end-to-end path (inputs and double-buffered outputs)
-    pin_out = [torch.empty((CHUNK_STEPS, NY * NX), dtype=torch.float32).pin_memory()
-               for _ in range(2)]
+    # ---- end-to-end path: host inputs (pinned), results back in host memory ------------
+    # The chunk goes through the public call with the output stage of the reference's writer
+    # (fields rounded to NMRL_PRCN decimals + per-step statistics on the device, like
+    # SpInterpMain.interpolate()).  Default transport: the rounded f32 field crosses PCIe as
+    # 16-bit codes and is decoded to the identical floats by host threads
+    # (spinterps_b200/transfer.py); `raw`: the f32 field itself into pinned memory (round 1).
+    from spinterps_b200.transfer import PackedDownloader
+    import concurrent.futures
     chunks_e2e = []
     for c in chunks:
         c2 = dict(c)
         c2['data'] = torch.from_numpy(c['data']).pin_memory().numpy()
         chunks_e2e.append(c2)
     copy_stream = torch.cuda.Stream()
-    copy_done = [None, None]
     checks = []
+    n_dec = int(os.environ.get('SPX_DECODE_THREADS', str(max(1, min(16, len(os.sched_getaffinity(0)) // world)))))
+    dl = PackedDownloader(torch.device('cuda', local_rank), CHUNK_STEPS, NY * NX, depth=2,
+                          n_threads=n_dec)
+    host_out = [np.empty((CHUNK_STEPS, NY * NX), dtype=np.float32) for _ in range(2)]
+    decoder = concurrent.futures.ThreadPoolExecutor(
+        max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
+    kw_e2e = dict(kw, round_decimals=NMRL_PRCN, field_stats=True)
+    raw_rows = [0]
 
-    def run_e2e(n):
-        """Same pipeline through the public call with HOST inputs; every chunk's
-        field is copied to pinned host memory on a copy stream that overlaps the
-        next chunk's compute."""
+    def run_e2e(n, decode=False):
+        """Pipeline: submit chunk i+1 | output stage + pack + D2H of chunk i.  At the end
+        of a step its result sits in (pinned) host memory in the lossless 2-byte form the
+        writer consumes (transfer.PackedField); decode=True additionally rebuilds the
+        whole f32 field in host memory (16 host threads, one chunk behind)."""
+        futs = [None, None]
+
+        def finish(ticket, k):
+            raw_rows[0] += dl.finish(ticket, host_out[k % 2])
+
+        def land(ticket):
+            pf = dl.wait(ticket)
+            raw_rows[0] += len(pf.raw)
+            checks.append(int(pf.codes[0, 0]))
+            dl.release(ticket)
+
+        def drain(pend, k):
+            flds, _ = pend.result(to_host=False)
+            if futs[k % 2] is not None:
+                futs[k % 2].result()                 # slot (and host buffer) k % 2 free again
+            ticket = dl.start(flds['OK'], NMRL_PRCN)
+            futs[k % 2] = decoder.submit(finish, ticket, k) if decode else \
+                decoder.submit(land, ticket)
+        pend = None
+        for k in range(n):
+            nxt = eng.submit_chunk(**kw_e2e, **next_chunk(chunks_e2e))
+            if pend is not None:
+                drain(pend, k - 1)
+            pend = nxt
+        drain(pend, n - 1)
+        for f in futs:
+            if f is not None:
+                f.result()
+
+    pin_out = []
+    copy_done = [None, None]
+
+    def run_e2e_raw(n):
+        """Round-1 transport for comparison: the rounded f32 field copied to pinned host
+        memory on a copy stream that overlaps the next chunk's compute."""
+        if not pin_out:
+            pin_out.extend(torch.empty((CHUNK_STEPS, NY * NX), dtype=torch.float32).pin_memory()
+                           for _ in range(2))
+
         def drain(pend, k):
             flds, _ = pend.result(to_host=False)
             buf = pin_out[k % 2]
@@ -321,13 +560,28 @@ def run_gpu(args):
             copy_done[k % 2] = ev
         pend = None
         for k in range(n):
-            nxt = eng.submit_chunk(**kw, **next_chunk(chunks_e2e))
+            nxt = eng.submit_chunk(**kw_e2e, **next_chunk(chunks_e2e))
             if pend is not None:
                 drain(pend, k - 1)
             pend = nxt
         drain(pend, n - 1)
         copy_stream.synchronize()
         checks.append(float(pin_out[(n - 1) % 2][0, 0]))
+
+    def d2h_ceiling_gbs(nbytes=1 << 30):
+        """Bare cudaMemcpyAsync device -> pinned host of 1 GiB, best of 3."""
+        src = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+        dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        best = float('inf')
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del src, dst
+        return nbytes / best / 1e6
 
     def timed(fn, n):
         import gc
@@ -360,8 +614,8 @@ def run_gpu(args):
     # the full station system and the near-station tables (cached afterwards), the upload
     # arena ring has 4 slots that are allocated on first use, the caching allocator has
     # to see the 5 GB field blocks once.  Untimed warm-up is therefore at least 8 chunks.
-    args.warmup = max(args.warmup, 8)
-    run_resident(args.warmup)
+    n_prime = max(args.warmup, 8)
+    run_resident(n_prime)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -378,27 +632,28 @@ def run_gpu(args):
     engine_stats = dict(eng.stats)
 
     def summarise(events):
-        """Dominant estimate kernel of the timed region: total time, work, rate."""
-        by = {}
-        for name, bound, work, e0, e1 in events:
-            d = by.setdefault(name, dict(bound=bound, work=0.0, ms=0.0, n=0))
-            d['work'] += work
-            # native submits report the milliseconds between their own CUDA events
-            d['ms'] += e0 if e1 is None else e0.elapsed_time(e1)
-            d['n'] += 1
-        if not by:
-            return None
-        name = max(by, key=lambda k_: by[k_]['ms'])
-        d = by[name]
-        d['kernel'] = name
-        return d
+        return summarise_events(events)[0]
 
     dom = summarise(kernel_events)
 
-    run_e2e(min(args.warmup, 2))
+    run_e2e(max(min(args.warmup, 3), 2))
     h2d0 = eng.h2d_bytes
+    d2h0 = dl.d2h_bytes
+    raw_rows[0] = 0
     ms_e2e, _ = timed(run_e2e, args.steps)
     h2d_e2e_bytes = eng.h2d_bytes - h2d0
+    d2h_e2e_bytes = dl.d2h_bytes - d2h0
+    e2e_raw_rows = raw_rows[0]
+    # ... with the whole f32 field rebuilt in host memory inside the timed region
+    n_dcd = max(2, min(args.steps, 5))
+    run_e2e(2, decode=True)
+    ms_e2e_dec, _ = timed(lambda n: run_e2e(n, decode=True), n_dcd)
+    # the same pipeline with the round-1 transport (f32 field into pinned memory)
+    n_raw = max(2, min(args.steps, 5))
+    run_e2e_raw(2)
+    ms_e2e_raw, _ = timed(run_e2e_raw, n_raw)
+    pin_out.clear()
+    d2h_peak = d2h_ceiling_gbs() if rank == 0 else None
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
@@ -427,20 +682,36 @@ def run_gpu(args):
     eng.profile_gemm = False
     eng.local_support = True
 
+    # ---- the one collective of the design: finished slabs -> writer rank (N > 1) --------
+    gather = None
+    if world > 1:
+        fld = eng.submit_chunk(**kw_e2e, **next_chunk(chunks_e2e)).result(to_host=False)[0]['OK']
+        nbytes = fld.numel() * 4
+        ring = [torch.empty_like(fld) for _ in range(2)] if rank == 0 else None
+
+        def gather_once(_n):
+            # the protocol of SpInterpMain.interpolate (dist.StreamedGather): the writer
+            # receives one slab at a time into a 2-slot ring
+            if rank == 0:
+                for r in range(1, world):
+                    dist.recv(ring[r % 2], src=r)
+            else:
+                dist.send(fld, dst=0)
+        gather_once(1)
+        ms_g, _ = timed(gather_once, 1)
+        gather = {'ms': ms_g, 'bytes_into_writer': int((world - 1) * nbytes),
+                  'gbs_into_writer': (world - 1) * nbytes / ms_g / 1e6,
+                  'nvlink_nominal_gbs_per_direction': 900.0,
+                  'note': 'NCCL send/recv of every other rank\'s rounded f32 chunk (5 GB each) to the '
+                          'writer GPU, one slab at a time into a 2-slot ring (no download)'}
+        del fld, ring
+
     value = world * cell_steps * args.steps / (ms / 1e3)
     e2e_value = world * cell_steps * args.steps / (ms_e2e / 1e3)
     value_dense = world * cell_steps * n_dense / (ms_dense / 1e3)
 
     if rank == 0:
         peak_f64 = dgemm_peak_tflops(torch)
-        hbm_peak, hbm_src = 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
-        mp = ROOT / 'MEASURED_PEAKS.json'
-        if mp.exists():
-            try:
-                hbm_peak = float(json.loads(mp.read_text())['hbm_gbs'])
-                hbm_src = 'MEASURED_PEAKS.json hbm_gbs (copy, read + write)'
-            except Exception:
-                pass
         traffic_tbl = {}
         tf = ROOT / 'profiles' / 'kernel_traffic.json'
         if tf.exists():
@@ -450,25 +721,7 @@ def run_gpu(args):
                 traffic_tbl = {}
 
         def roofline(d):
-            if d is None:
-                return None
-            avg_ms = d['ms'] / d['n']
-            per_launch = d['work'] / d['n']
-            if d['bound'] == 'tensor':
-                ach = per_launch / (avg_ms / 1e3) / 1e12
-                peak, unit = peak_f64, 'TFLOP/s'
-                src = ('FP64 tensor: cuBLAS DGEMM 6144^3 via torch.matmul measured live in this '
-                       'run (MEASURED_PEAKS.json has no FP64 entry); DMMA issue-rate '
-                       'microbenchmark 37.15 TFLOP/s in profiles/microbench')
-            else:
-                ach = per_launch / (avg_ms / 1e3) / 1e9
-                peak, unit, src = hbm_peak, 'GB/s', hbm_src
-            t = traffic_tbl.get(d['kernel'], {})
-            return {'kernel': 'spx::' + d['kernel'], 'bound': d['bound'], 'achieved': ach,
-                    'peak': peak, 'unit': unit, 'frac': ach / peak,
-                    'traffic': t.get('dram_bytes_per_launch'),
-                    'algorithmic_per_launch': per_launch, 'avg_launch_ms': avg_ms,
-                    'launches_timed': d['n'], 'peak_source': src}
+            return roofline_of(d, peak_f64, traffic_tbl)
 
         cpu_baseline = None
         if cpu_res is not None:
@@ -495,10 +748,31 @@ def run_gpu(args):
                           'variogram range of each cell) are cached across chunks' % N_VARIANTS,
                 'estimator': ('local (compact-support) estimator: %s' % bool(
                     engine_stats.get('local_rows'))),
-                'wall_ms_per_step': ms_wall / args.steps},
+                'wall_ms_per_step': ms_wall / args.steps,
+                'warmup_chunks_run': n_prime},
             'e2e': {'value': e2e_value, 'unit': 'cell-steps/s',
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(cell_steps * 4),
-                    'ms_per_step': ms_e2e / args.steps},
+                    'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': int(round(d2h_e2e_bytes / max(args.steps, 1))),
+                    'ms_per_step': ms_e2e / args.steps,
+                    'transport': 'output stage of the writer on the device (np.round to %d '
+                                 'decimals, per-step statistics); the rounded f32 field crosses '
+                                 'PCIe in its lossless 2-byte form (16-bit codes per row, '
+                                 'verified bit-exact on the device) and lands in pinned host '
+                                 'memory as transfer.PackedField, which the writer decodes one '
+                                 'step at a time' % NMRL_PRCN,
+                    'decoded_f32': {
+                        'value': world * cell_steps * n_dcd / (ms_e2e_dec / 1e3),
+                        'ms_per_step': ms_e2e_dec / n_dcd, 'decode_threads': n_dec,
+                        'note': 'same pipeline plus the decode of the WHOLE field to f32 in host '
+                                'memory inside the timed region'},
+                    'rows_sent_as_raw_f32': int(e2e_raw_rows),
+                    'd2h_gbs': d2h_e2e_bytes / max(ms_e2e, 1e-9) / 1e6,
+                    'd2h_ceiling_gbs': d2h_peak,
+                    'raw_f32_transport': {
+                        'value': world * cell_steps * n_raw / (ms_e2e_raw / 1e3),
+                        'ms_per_step': ms_e2e_raw / n_raw,
+                        'd2h_bytes_per_step': int(cell_steps * 4),
+                        'note': 'same pipeline, f32 field copied to pinned host memory'}},
             'gpu_launches': int(launches_timed),
             'roofline': roofline(dom),
             'step_breakdown': {'ms_per_step_traced': ms_tr / n_tr, 'entry_points': breakdown},
@@ -507,6 +781,7 @@ def run_gpu(args):
                         'through the fused variogram-fill + DMMA contraction',
                 'value': value_dense, 'unit': 'cell-steps/s', 'ms_per_step': ms_dense / n_dense,
                 'roofline': roofline(dense_dom)},
+            'gather': gather,
             'cpu_baseline': cpu_baseline,
             'clocks': sampler.summary(),
         }
@@ -521,9 +796,13 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='C2', choices=['C1', 'C2', 'C3', 'C4', 'C5'],
+                    help='BASELINE.json configuration (default C2: the headline workload)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config != 'C2':
+        run_config(args)
     else:
         run_gpu(args)
 

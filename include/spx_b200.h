@@ -597,6 +597,12 @@ int spx_local_build_dev(const spx_local* l, void* stream);
  * 65536). */
 int spx_local_tiles_dev(const spx_local* l, void* stream);
 int spx_estimate_local_dev(const spx_local* l, void* stream);
+/* Streamlined kernel: write the field through shared-memory staged row segments and bulk
+ * async (TMA) stores instead of per-lane streaming stores (needs 16-byte aligned rows:
+ * out_ld % 4 == 0, n_cells % 4 == 0).  on: 1 / 0, -1 = environment SPX_LOCAL_BULK (default
+ * 0: on B200 the staged variant measured 1.14 ms against 0.89 ms per 5 GB field, see
+ * DESIGN.md).  Returns the previous setting.  Results are bit-identical either way. */
+int spx_local_set_bulk(int on);
 
 /* ---- one native call per time chunk (the planned fast path) ------------------------
  * The common case of the compute half of SpInterpSteps.interpolate_subset
@@ -631,6 +637,9 @@ typedef struct spx_fast_cfg {
                                     n_rows / row_dst / out is taken from here */
     spx_gemm gemm;
     int32_t profile;             /* record events around the estimate launch (spx_fast_times) */
+    int32_t solve_stream;        /* 1: solve phase on the job's own high-priority stream (runs
+                                    beside the previous chunk's estimate), 0: on the caller's
+                                    stream in front of the estimate */
 } spx_fast_cfg;
 
 typedef struct spx_fast_result {
@@ -712,6 +721,33 @@ int spx_upload_dev(void* dst_dev, const void* src_host, int64_t n_bytes, void* s
 int64_t spx_round_stats_workspace(int64_t n_rows, int64_t row_len);
 int spx_round_stats_dev(void* fld, int32_t is_f64, int64_t n_rows, int64_t row_len, int64_t ld,
                         int32_t decimals, double* stats, void* workspace, void* stream);
+
+/* ---- lossless 2-byte transport of rounded f32 fields ------------------------------
+ * The netCDF writer stores np.round(fld, nmrl_prcn) as float32 (interp/steps.py:907-945):
+ * every value is fdiv(q, 10^d) for an integer q.  spx_pack_field_dev turns each row (time
+ * step) of such a field into 16-bit codes q - qmin (0xFFFF = NaN, 0xFFFE = -0.0) after VERIFYING, element
+ * by element, that the host's decode reproduces the float bit for bit; rows that do not
+ * qualify (not rounded, |q| >= 2^31, infinities, range > 65533) get mode SPX_PACK_RAW and
+ * are transferred as floats by the caller.  spx_unpack_field_host rebuilds the floats
+ * (threaded, AVX2).  Halves the device -> host bytes of a chunk. */
+#define SPX_PACK_U16 0
+#define SPX_PACK_RAW 2
+typedef struct spx_pack_row {
+    int32_t mode;                /* SPX_PACK_U16 / SPX_PACK_RAW */
+    int32_t qmin, qmax;          /* integer range of the row (qmin = offset of the codes) */
+    int32_t n_nan;
+} spx_pack_row;
+/* Codes per row of the packed buffer (row_len rounded up to a multiple of 8). */
+int64_t spx_pack_stride(int64_t row_len);
+/* fld: device f32 [n_rows, row_len] pitch ld; hdr: device [n_rows]; codes: device
+ * [n_rows, spx_pack_stride(row_len)] uint16.  decimals 0..9. */
+int spx_pack_field_dev(const float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
+                       int32_t decimals, spx_pack_row* hdr, uint16_t* codes, void* stream);
+/* HOST pointers.  Writes the rows of mode SPX_PACK_U16 into out [n_rows, row_len] pitch
+ * out_ld (raw rows are left untouched: the caller copies them).  n_threads <= 0: default. */
+int spx_unpack_field_host(const spx_pack_row* hdr, const uint16_t* codes, int64_t n_rows,
+                          int64_t row_len, int32_t decimals, float* out, int64_t out_ld,
+                          int32_t n_threads);
 
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field

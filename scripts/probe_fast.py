@@ -9,6 +9,7 @@ from spinterps_b200.engine import ChunkEngine
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 chunks = [bench.make_chunk(0, v) for v in range(4)]
 eng = ChunkEngine()
+eng.solve_stream = os.environ.get('PROBE_SOLVE_STREAM') == '1'
 kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32)
 pend = None
 for i in range(6):

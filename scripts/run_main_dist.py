@@ -1,6 +1,10 @@
-"""SpInterpMain under torchrun: every rank interpolates its time block, rank 0
-writes; compares the file with a single-rank oracle run.  Usage:
-torchrun --nproc-per-node N scripts/run_main_dist.py <out_dir>"""
+"""SpInterpMain.interpolate() on 1 rank or under torchrun: every rank interpolates its
+(time chunk x grid-row chunk) tasks, the writer rank receives the slabs over NCCL and
+writes.  Compares the file with the oracle and stores the raw fields as .npy so that runs
+with different world sizes can be compared bit for bit.  Usage:
+    python scripts/run_main_dist.py <out_dir> [row_chunks]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 \
+        scripts/run_main_dist.py <out_dir> [row_chunks]"""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -10,9 +14,12 @@ from spinterps_b200 import ncwriter
 from oracle import spinterp_oracle as orc
 
 rank = int(os.environ.get('RANK', 0)); local = int(os.environ.get('LOCAL_RANK', 0))
+world = int(os.environ.get('WORLD_SIZE', 1))
 torch.cuda.set_device(local)
-dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 out_dir = Path(sys.argv[1])
+row_chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(4)
 n_stn, T = 40, 23
 idx = pd.date_range('2001-03-01', periods=T, freq='D')
@@ -28,7 +35,10 @@ m.set_netcdf4_parameters('p.nc', 'mm', 'precip', 'days since 1900-01-01', 'grego
 m.set_interp_time_parameters('2001-03-01', '2001-03-23', 'D', '%Y-%m-%d')
 m.set_neighbor_selection_method('all'); m.set_misc_settings(cell_size=1500.0, max_steps_per_chunk=5)
 m.turn_ordinary_kriging_on(); m.turn_inverse_distance_weighting_on([2])
+if row_chunks:
+    m._grid_row_chunks_forced = row_chunks
 m.verify(); m.interpolate()
+print('rank', rank, 'gather', m.gather_stats, flush=True)
 if rank == 0:
     exp, _ = orc.interp_chunk(m._data_df.values, m._crds_df['X'].values, m._crds_df['Y'].values,
                               m._interp_x_crds_msh, m._interp_y_crds_msh, m._interp_crds_orig_shape,
@@ -37,10 +47,17 @@ if rank == 0:
     worst = 0.0
     for lab in ('OK', 'IDW_000'):
         ref = np.round(exp[lab], 2).reshape(T, ny, nx)
+        full = np.empty((T, ny, nx), dtype=np.float32)
         for t in range(T):
-            got = h.read(lab, t); assert not np.isnan(got).any(), (lab, t)
+            got = h.read(lab, t)
+            assert not np.isnan(got).any(), (lab, t, int(np.isnan(got).sum()), got.shape,
+                                             np.argwhere(np.isnan(got))[:5].tolist())
+            full[t] = got
             worst = max(worst, float(np.abs(got - ref[t]).max()))
+        np.save(out_dir / f'field_{lab}.npy', full)
     h.close()
-    print('DIST MAIN OK world', dist.get_world_size(), 'max |diff| after 2-decimal rounding', worst)
+    print('DIST MAIN OK world', world, 'row_chunks', row_chunks,
+          'max |diff| after 2-decimal rounding', worst)
     assert worst <= 0.0101
-dist.destroy_process_group()
+if world > 1:
+    dist.destroy_process_group()

@@ -159,13 +159,24 @@ class spx_gemm(C.Structure):
                 ('lo', C.c_double), ('hi', C.c_double), ('quad_slot', C.c_int32)]
 
 
+class spx_pack_row(C.Structure):
+    _fields_ = [('mode', C.c_int32), ('qmin', C.c_int32), ('qmax', C.c_int32),
+                ('n_nan', C.c_int32)]
+
+
+PACK_ROW_DTYPE = np.dtype([('mode', np.int32), ('qmin', np.int32), ('qmax', np.int32),
+                           ('n_nan', np.int32)])
+SPX_PACK_U16, SPX_PACK_RAW = 0, 2
+
+
 class spx_fast_cfg(C.Structure):
     _fields_ = [('n_stn', C.c_int32), ('n_border', C.c_int32), ('kpad', C.c_int32),
                 ('max_steps', C.c_int32), ('n_slots', C.c_int32), ('min_systems', C.c_int32),
                 ('min_var_thr', C.c_double), ('ginv', C.c_void_p),
                 ('lambda_bound', C.c_double), ('lambda_tol', C.c_double),
                 ('estimator', C.c_int32), ('want_coef_t', C.c_int32), ('base_f', C.c_double),
-                ('local', spx_local), ('gemm', spx_gemm), ('profile', C.c_int32)]
+                ('local', spx_local), ('gemm', spx_gemm), ('profile', C.c_int32),
+                ('solve_stream', C.c_int32)]
 
 
 class spx_fast_result(C.Structure):
@@ -240,6 +251,7 @@ _SIGS = {
     'spx_estimate_multivg_dev': (C.c_int, [C.POINTER(spx_multivg), C.c_void_p]),
     'spx_local_build_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_estimate_local_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
+    'spx_local_set_bulk': (C.c_int, [C.c_int]),
     'spx_local_tiles_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
@@ -286,6 +298,11 @@ _SIGS = {
     'spx_fast_timeline': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     'spx_ut_gemm_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'spx_pack_stride': (C.c_int64, [C.c_int64]),
+    'spx_pack_field_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    'spx_unpack_field_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                        C.c_void_p, C.c_int64, C.c_int32]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
 }

@@ -17,7 +17,7 @@ CSRC = PKG / 'csrc'
 LIBDIR = PKG / 'lib'
 LIB = LIBDIR / 'libspx_b200.so'
 SOURCES = ['spx_basic.cu', 'spx_solve.cu', 'spx_gemm.cu', 'spx_misc.cu', 'spx_nrst.cu',
-           'spx_plan.cu', 'spx_prep.cu', 'spx_chunk.cu']
+           'spx_plan.cu', 'spx_prep.cu', 'spx_chunk.cu', 'spx_pack.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default',
@@ -33,7 +33,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) +
+    for p in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.h')) +
                     [ROOT / 'include' / 'spx_b200.h', Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -43,7 +43,8 @@ def _digest():
 def _src_digest(src):
     """Digest of one translation unit: its source, every header, the flags."""
     h = hashlib.sha256()
-    for p in [CSRC / src] + sorted(CSRC.glob('*.cuh')) + [ROOT / 'include' / 'spx_b200.h']:
+    for p in ([CSRC / src] + sorted(CSRC.glob('*.cuh')) + sorted(CSRC.glob('*.h')) +
+              [ROOT / 'include' / 'spx_b200.h']):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(' '.join(NVCC_FLAGS).encode())

@@ -18,12 +18,15 @@
 namespace spx {
 
 // ------------------------------------------------------------------ Ut = Bt . G (DMMA)
-// 64 x 64 tile per block, 8 warps (4 along rows x 2 along columns), K chunks of 32 staged
-// in shared memory with pitch 36 (== 4 mod 16: conflict-free 8 x 4 fragment loads).  The A
-// operand (Bt) is never stored: it is the resident data block with NaN -> 0 (data rows) or
-// its availability mask (one row per system).  G is symmetric, so the col-major B fragment
-// B[k][n] = G[k][n] is read as G[n][k]: contiguous along k.
-constexpr int UT_BM = 64, UT_BN = 64, UT_BK = 32, UT_LD = UT_BK + 4;
+// 32 x 64 tile per block (640 blocks for 2500 x 501: one wave, several blocks per SM),
+// 8 warps (2 along rows x 4 along columns, 16 x 16 each), K chunks of 32 staged in shared
+// memory with pitch 36 (== 4 mod 16: conflict-free 8 x 4 fragment loads); the global loads
+// of chunk k + 1 are issued before the DMMA sweep of chunk k.  The A operand (Bt) is never
+// stored: it is the resident data block with NaN -> 0 (data rows) or its availability
+// mask (one row per system).  G is symmetric, so the col-major B fragment B[k][n] = G[k][n]
+// is read as G[n][k]: contiguous along k.
+constexpr int UT_BM = 32, UT_BN = 64, UT_BK = 32, UT_LD = UT_BK + 4;
+constexpr int UT_EA = (UT_BM * UT_BK) / 256, UT_EB = (UT_BN * UT_BK) / 256;
 
 __device__ __forceinline__ void dmma_ut(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) k_ut_gemm(const double* __restrict__ data
     __shared__ double Bs[UT_BN][UT_LD];
     __shared__ int64_t s_src[UT_BM];     // data row offset of each tile row, < 0 = beyond n_rows
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wr = wid >> 1, wc = wid & 1;
+    const int wr = wid >> 2, wc = wid & 3;
     const int64_t row0 = (int64_t)blockIdx.y * UT_BM;
     const int col0 = blockIdx.x * UT_BN;
     if (tid < UT_BM) {
@@ -49,41 +52,53 @@ __global__ void __launch_bounds__(256) k_ut_gemm(const double* __restrict__ data
         s_src[tid] = (r < n_rows) ? (int64_t)src_step[r] * data_ld : -1;
     }
     __syncthreads();
-    double acc[2][4][2];
+    double acc[2][2][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int fg = lane >> 2, ft = lane & 3;
-    for (int k0 = 0; k0 < M; k0 += UT_BK) {
+    const int kk_l = tid & 31, rr_l = tid >> 5;          // element (rr_l + 8 e, kk_l) of a tile
+    double ra[UT_EA], rb[UT_EB];
+    auto fetch = [&](int k0) {
+        const int c = k0 + kk_l;
 #pragma unroll
-        for (int e = 0; e < (UT_BM * UT_BK) / 256; ++e) {
-            const int idx = tid + 256 * e;
-            const int rr = idx >> 5, kk = idx & 31;
-            const int c = k0 + kk;
-            double v = 0.0;
+        for (int e = 0; e < UT_EA; ++e) {
+            const int rr = rr_l + 8 * e;
             const int64_t so = s_src[rr];
+            double v = 0.0;
             if (so >= 0 && c < n_stn) {
                 const double z = data[so + c];
                 const bool fin = (z == z);
                 v = (row0 + rr >= n_data) ? (fin ? 1.0 : 0.0) : (fin ? z : 0.0);
             }
-            As[rr][kk] = v;
-            const int n = col0 + rr;
-            Bs[rr][kk] = (n < M && c < M) ? G[(int64_t)n * M + c] : 0.0;
+            ra[e] = v;
         }
+#pragma unroll
+        for (int e = 0; e < UT_EB; ++e) {
+            const int n = col0 + rr_l + 8 * e;
+            rb[e] = (n < M && c < M) ? G[(int64_t)n * M + c] : 0.0;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < M; k0 += UT_BK) {
+#pragma unroll
+        for (int e = 0; e < UT_EA; ++e) As[rr_l + 8 * e][kk_l] = ra[e];
+#pragma unroll
+        for (int e = 0; e < UT_EB; ++e) Bs[rr_l + 8 * e][kk_l] = rb[e];
         __syncthreads();
+        if (k0 + UT_BK < M) fetch(k0 + UT_BK);
 #pragma unroll
         for (int kk = 0; kk < UT_BK; kk += 4) {
-            double af[2], bf[4];
+            double af[2], bf[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) af[i] = As[wr * 16 + 8 * i + fg][kk + ft];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[wc * 32 + 8 * j + fg][kk + ft];
+            for (int j = 0; j < 2; ++j) bf[j] = Bs[wc * 16 + 8 * j + fg][kk + ft];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_ut(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 2; ++j) dmma_ut(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         __syncthreads();
     }
@@ -92,8 +107,8 @@ __global__ void __launch_bounds__(256) k_ut_gemm(const double* __restrict__ data
         const int64_t r = row0 + wr * 16 + 8 * i + fg;
         if (r >= n_rows) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = col0 + wc * 32 + 8 * j + 2 * ft;
+        for (int j = 0; j < 2; ++j) {
+            const int c = col0 + wc * 16 + 8 * j + 2 * ft;
             if (c < M) ut[r * M + c] = acc[i][j][0];
             if (c + 1 < M) ut[r * M + c + 1] = acc[i][j][1];
         }
@@ -139,7 +154,7 @@ static FastLayout fast_layout(const spx_fast_cfg& c) {
 struct FastSlot {
     uint8_t* dev = nullptr;
     uint8_t* host = nullptr;
-    cudaEvent_t ev_solved = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_solved = nullptr, ev_done = nullptr, ev_up = nullptr;
     cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr, ev_s0 = nullptr;
     bool used = false;
     spx_dd_plan plan{};
@@ -214,6 +229,7 @@ int spx_fast_create(const spx_fast_cfg* cfg, void* dev_arena, void* host_arena, 
         SPX_CUDA(cudaEventCreateWithFlags(&s.ev_solved,
                                           cfg->profile ? cudaEventDefault : cudaEventDisableTiming));
         SPX_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        SPX_CUDA(cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
         if (cfg->profile) {
             SPX_CUDA(cudaEventCreate(&s.ev_e0));
             SPX_CUDA(cudaEventCreate(&s.ev_e1));
@@ -232,6 +248,7 @@ int spx_fast_destroy(void* job) {
         if (s.used) cudaEventSynchronize(s.ev_done);
         if (s.ev_solved) cudaEventDestroy(s.ev_solved);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.ev_up) cudaEventDestroy(s.ev_up);
         if (s.ev_e0) cudaEventDestroy(s.ev_e0);
         if (s.ev_e1) cudaEventDestroy(s.ev_e1);
         if (s.ev_s0) cudaEventDestroy(s.ev_s0);
@@ -259,7 +276,8 @@ int spx_fast_submit(void* job, const double* data, int64_t n_steps, int64_t ld, 
     const spx_fast_cfg& c = j->cfg;
     const FastLayout& L = j->L;
     const int N = c.n_stn, M = c.n_stn + c.n_border;
-    cudaStream_t st_main = (cudaStream_t)main_stream, st = j->solve;
+    cudaStream_t st_main = (cudaStream_t)main_stream;
+    cudaStream_t st = c.solve_stream ? j->solve : st_main;
     std::memset(res, 0, sizeof(*res));
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](int i) {
@@ -332,19 +350,27 @@ int spx_fast_submit(void* job, const double* data, int64_t n_steps, int64_t ld, 
     // ---- device: uploads + solve phase on the solve stream ------------------------------
     double* d_data = reinterpret_cast<double*>(s.dev + L.d_data);
     uint8_t* d_plan = s.dev + L.d_plan;
-    if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_s0, st));
+    // uploads on the job's own stream (they overlap the previous chunk's kernels whichever
+    // stream those run on); the solve phase waits for them
+    cudaStream_t st_up = j->solve;
     if (pinned && ld != N) {
         SPX_CUDA(cudaMemcpy2DAsync(d_data, 8 * (size_t)N, data, 8 * (size_t)ld, 8 * (size_t)N,
-                                   (size_t)n_steps, cudaMemcpyHostToDevice, st));
+                                   (size_t)n_steps, cudaMemcpyHostToDevice, st_up));
     } else {
         SPX_CUDA(cudaMemcpyAsync(d_data, pinned ? data : h_data, 8 * (size_t)n_steps * N,
-                                 cudaMemcpyHostToDevice, st));
+                                 cudaMemcpyHostToDevice, st_up));
     }
     SPX_CUDA(cudaMemcpyAsync(d_plan, h_plan, (size_t)plan.n_upload_bytes, cudaMemcpyHostToDevice,
-                             st));
+                             st_up));
     // row_dst sits behind the plan's device buffer
     int32_t* d_rowdst = reinterpret_cast<int32_t*>(d_plan + spx_downdate_plan_bytes(c.max_steps, N));
-    SPX_CUDA(cudaMemcpyAsync(d_rowdst, h_rowdst, 4 * (size_t)coef_rows, cudaMemcpyHostToDevice, st));
+    SPX_CUDA(cudaMemcpyAsync(d_rowdst, h_rowdst, 4 * (size_t)coef_rows, cudaMemcpyHostToDevice,
+                             st_up));
+    if (st != st_up) {
+        SPX_CUDA(cudaEventRecord(s.ev_up, st_up));
+        SPX_CUDA(cudaStreamWaitEvent(st, s.ev_up, 0));
+    }
+    if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_s0, st));
     res->h2d_bytes = 8 * n_steps * N + plan.n_upload_bytes + 4 * coef_rows;
     res->d_data = d_data;
     lap(3);
@@ -413,7 +439,7 @@ int spx_fast_submit(void* job, const double* data, int64_t n_steps, int64_t ld, 
 
     lap(4);
     // ---- estimate on the caller's stream behind the solve ------------------------------
-    SPX_CUDA(cudaStreamWaitEvent(st_main, s.ev_solved, 0));
+    if (c.solve_stream) SPX_CUDA(cudaStreamWaitEvent(st_main, s.ev_solved, 0));
     if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_e0, st_main));
     if (c.estimator == 0) {
         spx_local Lc = c.local;

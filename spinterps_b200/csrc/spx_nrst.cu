@@ -1086,14 +1086,38 @@ __device__ __forceinline__ double2 ld_coef2(const double* p) {
 
 // SM: the gathers read the tile's staged slices in shared memory (ct = its base, slice
 // pitch LOC_SLD, station -> a.slot) instead of the global transposed copy.
-template <int NG, bool CLAMP, int CPT, bool SM>
+// BULK (CPT == 1): the four values of a row group go to a shared-memory staging tile
+// stage[2][LOC_RB rows][256 cells]; every LOC_RB rows thread 0 hands the tile to the TMA
+// engine, one cp.async.bulk (shared -> global) per row segment of n_seg bytes, while the
+// block computes the next LOC_RB rows into the other buffer.  One named barrier per
+// LOC_RB rows; all 256 threads of the block run this loop (same trip count in every
+// warp-uniform NG variant).
+constexpr int LOC_RB = 8;
+
+__device__ __forceinline__ void bulk_rows_out(const float* tile, float* outp,
+                                              const int64_t* soff, int r0, int n_rows,
+                                              int n_seg) {
+    // caller: thread 0 only, after the barrier that published the tile
+    for (int i = 0; i < n_rows; ++i) {
+        float* g = outp + soff[r0 + i];
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tile + i * 256);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(g), "r"(sa), "r"(n_seg) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int NG, bool CLAMP, int CPT, bool SM, bool BULK = false>
 __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double* sbase,
                                              const int64_t* soff, int nr, int64_t c0,
                                              const int* n, const double* const* p0,
                                              const double* const* p1, const double* v0,
                                              const double* v1, float* outp, const double* ct,
-                                             float flo, float fhi, bool pair) {
+                                             float flo, float fhi, bool pair,
+                                             float* stage = nullptr, int n_seg = 0,
+                                             bool active = true) {
     int r = 0;
+    const int tid = threadIdx.x;
     for (; r + 4 <= nr; r += 4) {
         const double2 b01 = *reinterpret_cast<const double2*>(sbase + r);
         const double2 b23 = *reinterpret_cast<const double2*>(sbase + r + 2);
@@ -1136,6 +1160,24 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
                 }
             }
         }
+        if (BULK) {
+            float* st = stage + ((r / LOC_RB) & 1) * (LOC_RB * 256) + (r & (LOC_RB - 1)) * 256 + tid;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) st[u * 256] = f[0][u];
+            const bool last = r + 8 > nr;                  // no further full row group
+            if ((r & (LOC_RB - 1)) == LOC_RB - 4 || last) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the other buffer's previous copies must have read it before anyone refills it
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 0) {
+                    const int g0 = r & ~(LOC_RB - 1);
+                    bulk_rows_out(stage + ((r / LOC_RB) & 1) * (LOC_RB * 256), outp - tid, soff,
+                                  g0, r + 4 - g0, n_seg);
+                }
+            }
+            continue;
+        }
         const longlong2 o01 = *reinterpret_cast<const longlong2*>(soff + r);
         const longlong2 o23 = *reinterpret_cast<const longlong2*>(soff + r + 2);
         const int64_t o[4] = {o01.x, o01.y, o23.x, o23.y};
@@ -1152,6 +1194,10 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
                 __stcs(outp + o[u], f[0][u]);
             }
         }
+    }
+    if (BULK) {
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (!active) return;
     }
     for (; r < nr; ++r) {
 #pragma unroll
@@ -1183,12 +1229,14 @@ __device__ __forceinline__ void local_rows_t(const LocalEstArgs& a, const double
 // against 128 KB of output per block) and every gather of the row loop becomes a
 // shared-memory load: no L1 misses, a fraction of the latency of the global gathers
 // the untiled variant waits on.
-template <bool CLAMP, int ROWS, int CPT, bool TILE>
+template <bool CLAMP, int ROWS, int CPT, bool TILE, bool BULK = false>
 __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) {
+    extern __shared__ __align__(128) float stage[];      // BULK: [2][LOC_RB][256]
     __shared__ __align__(16) double sbase[ROWS];
     __shared__ __align__(16) int64_t soff[ROWS];
     __shared__ __align__(16) double sct[TILE ? SPX_LOCAL_TILE_CAP * LOC_SLD : 2];
     static_assert(!TILE || (CPT == 1 && ROWS == 128), "tile variant: 256 cells x 128 rows");
+    static_assert(!BULK || TILE, "bulk stores come with the tile variant");
     const int tid = threadIdx.x;
     // swap_grid: the row blocks of one cell tile are launched back to back, so that all
     // but the first find the tile's tables and coefficient slices in L2
@@ -1250,13 +1298,14 @@ __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) 
         }
     }
     __syncthreads();
-    if (c0 >= a.n_cells) return;                 // no further block-wide barrier below
+    const bool active = c0 < a.n_cells;
+    if (!BULK && !active) return;                // no further block-wide barrier below
     const double* p0[CPT];
     const double* p1[CPT];
     int nloc = 0;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
-        n[q] = (q == 0 || pair) ? min(n[q], a.cap) : 0;
+        n[q] = ((q == 0 || pair) && active) ? min(n[q], a.cap) : 0;
         v0[q] = (0 < n[q]) ? v0[q] : 0.0;
         v1[q] = (1 < n[q]) ? v1[q] : 0.0;
         if (TILE && staged) {
@@ -1278,8 +1327,11 @@ __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) 
     const float flo = a.has_lo ? (float)a.lo : -CUDART_INF_F;
     const float fhi = a.has_hi ? (float)a.hi : CUDART_INF_F;
     float* outp = reinterpret_cast<float*>(a.out) + c0;
-#define SPX_LOCAL_ROWS_CALL(NG, SM, CT) \
-    local_rows_t<NG, CLAMP, CPT, SM>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, CT, flo, fhi, pair)
+    // bytes of the tile's row segment (the last tile of a row may be short)
+    const int n_seg = (int)min((int64_t)256, a.n_cells - (int64_t)bx * 256) * 4;
+#define SPX_LOCAL_ROWS_CALL(NG, SM, CT)                                                       \
+    local_rows_t<NG, CLAMP, CPT, SM, BULK>(a, sbase, soff, nr, c0, n, p0, p1, v0, v1, outp, CT, \
+                                           flo, fhi, pair, stage, n_seg, active)
     if (TILE && staged) {
         if (nmax == 0) SPX_LOCAL_ROWS_CALL(0, true, sct);
         else if (nmax == 1) SPX_LOCAL_ROWS_CALL(1, true, sct);
@@ -1346,6 +1398,14 @@ extern "C" int spx_local_tiles_dev(const spx_local* l, void* stream) {
         l->cnt, l->idx, l->n_cells, l->cap, l->n_stn, l->tile_cnt, l->tile_stn, l->slot);
     SPX_CHECK_LAUNCH("k_local_tiles");
     return SPX_OK;
+}
+
+static int g_local_bulk = -1;       // -1: environment SPX_LOCAL_BULK (default off: measured slower)
+
+extern "C" int spx_local_set_bulk(int on) {
+    const int prev = g_local_bulk;
+    g_local_bulk = on;
+    return prev;
 }
 
 extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
@@ -1423,6 +1483,30 @@ extern "C" int spx_estimate_local_dev(const spx_local* l, void* stream) {
             a.tile_cnt = l->tile_cnt;
             a.tile_stn = l->tile_stn;
             a.slot = l->slot;
+            // bulk (TMA) stores of shared-memory staged row segments: 16-byte aligned rows
+            static const int bulk_env = getenv("SPX_LOCAL_BULK") ? atoi(getenv("SPX_LOCAL_BULK")) : 0;
+            const int bulk_knob = g_local_bulk < 0 ? bulk_env : g_local_bulk;
+            const bool bulk = bulk_knob && l->out_ld % 4 == 0 && l->n_cells % 4 == 0 &&
+                              (reinterpret_cast<uintptr_t>(l->out) & 15) == 0;
+            if (bulk) {
+                constexpr int stage_bytes = 2 * LOC_RB * 256 * (int)sizeof(float);
+                static bool attr_set = false;
+                if (!attr_set) {
+                    SPX_CUDA(cudaFuncSetAttribute(k_estimate_local_fast<true, 128, 1, true, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  stage_bytes));
+                    SPX_CUDA(cudaFuncSetAttribute(k_estimate_local_fast<false, 128, 1, true, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  stage_bytes));
+                    attr_set = true;
+                }
+                if (clamp)
+                    k_estimate_local_fast<true, 128, 1, true, true><<<g1, 256, stage_bytes, st>>>(a);
+                else
+                    k_estimate_local_fast<false, 128, 1, true, true><<<g1, 256, stage_bytes, st>>>(a);
+                SPX_CHECK_LAUNCH("k_estimate_local_fast(tile, bulk)");
+                return SPX_OK;
+            }
             if (clamp) k_estimate_local_fast<true, 128, 1, true><<<g1, 256, 0, st>>>(a);
             else k_estimate_local_fast<false, 128, 1, true><<<g1, 256, 0, st>>>(a);
             SPX_CHECK_LAUNCH("k_estimate_local_fast(tile)");

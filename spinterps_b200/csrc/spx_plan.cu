@@ -4,13 +4,22 @@
 // here (1250 groups per chunk of config 2) than the GPU needs for the chunk itself --
 // plus the one small kernel that builds the right-hand-side matrix of the downdate from
 // the resident data.
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <immintrin.h>
+#include <mutex>
+#include <sched.h>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "spx_b200.h"
 #include "spx_common.cuh"
+#include "spx_host_pool.h"
 
 namespace spx {
 
@@ -49,28 +58,144 @@ static void scan_row_sse2(const double* __restrict__ src, int n, double thr,
     *flag_io = flag;
 }
 
+// AVX2: 8 doubles per iteration; the "any value >= thr" flag is a running maximum
+// (max_pd keeps the accumulator when the new operand is NaN); `copy` (optional) receives
+// the row in the same pass, with non-temporal stores when it is 32-byte aligned (a pinned
+// staging buffer is written once and read by the DMA engine, never by this core).
 __attribute__((target("avx2"))) static void scan_row_avx2(const double* __restrict__ src, int n,
                                                           double thr, uint64_t* __restrict__ bits,
-                                                          int* flag_io) {
-    const __m256d thr4 = _mm256_set1_pd(thr);
-    int flag = *flag_io;
+                                                          int* flag_io, double* __restrict__ copy) {
+    __m256d vmax = _mm256_set1_pd(-__builtin_inf());
+    int any_inf_neg = 0;   // values equal to -inf compare >= thr only if thr is -inf itself
+    const bool nt = copy && ((reinterpret_cast<uintptr_t>(copy) & 31) == 0);
     for (int j0 = 0, w = 0; j0 < n; j0 += 64, ++w) {
         const int j1 = (n - j0 < 64) ? n - j0 : 64;
         uint64_t word = 0;
         int b = 0;
-        for (; b + 4 <= j1; b += 4) {
-            const __m256d v = _mm256_loadu_pd(src + j0 + b);
-            word |= (uint64_t)_mm256_movemask_pd(_mm256_cmp_pd(v, v, _CMP_ORD_Q)) << b;
-            flag |= _mm256_movemask_pd(_mm256_cmp_pd(v, thr4, _CMP_GE_OQ));
+        for (; b + 8 <= j1; b += 8) {
+            const __m256d v0 = _mm256_loadu_pd(src + j0 + b);
+            const __m256d v1 = _mm256_loadu_pd(src + j0 + b + 4);
+            const unsigned m0 = (unsigned)_mm256_movemask_pd(_mm256_cmp_pd(v0, v0, _CMP_ORD_Q));
+            const unsigned m1 = (unsigned)_mm256_movemask_pd(_mm256_cmp_pd(v1, v1, _CMP_ORD_Q));
+            word |= (uint64_t)(m0 | (m1 << 4)) << b;
+            vmax = _mm256_max_pd(v0, vmax);
+            vmax = _mm256_max_pd(v1, vmax);
+            if (copy) {
+                if (nt) {
+                    _mm256_stream_pd(copy + j0 + b, v0);
+                    _mm256_stream_pd(copy + j0 + b + 4, v1);
+                } else {
+                    _mm256_storeu_pd(copy + j0 + b, v0);
+                    _mm256_storeu_pd(copy + j0 + b + 4, v1);
+                }
+            }
         }
         for (; b < j1; ++b) {
             const double v = src[j0 + b];
             word |= (uint64_t)(v == v) << b;
-            flag |= (int)(v >= thr);
+            any_inf_neg |= (int)(v >= thr);
+            if (copy) copy[j0 + b] = v;
         }
         bits[w] = word;
     }
+    double m[4];
+    _mm256_storeu_pd(m, vmax);
+    const double mx = (m[0] > m[1] ? m[0] : m[1]) > (m[2] > m[3] ? m[2] : m[3])
+                          ? (m[0] > m[1] ? m[0] : m[1]) : (m[2] > m[3] ? m[2] : m[3]);
+    int flag = *flag_io | any_inf_neg;
+    if (thr == -__builtin_inf()) {
+        // every value that is not NaN counts: any available station (the running maximum
+        // starts at -inf and cannot tell "no value" from "a value of -inf")
+        for (int w = 0; w < (n + 63) / 64; ++w) flag |= (int)(bits[w] != 0);
+    } else {
+        flag |= (int)(mx >= thr);
+    }
     *flag_io = flag;
+}
+
+// HostPool (spx_host_pool.h): persistent helper threads, leaked on purpose -- the detached
+// workers wait on its condition variable until the process ends (a static object would be
+// destroyed under them at exit).
+struct HostPool::Impl {
+    std::mutex mu, call_mu;
+    std::condition_variable cv, done_cv;
+    const std::function<void(int, int)>* fn = nullptr;
+    uint64_t gen = 0;
+    int pending = 0;
+    int n_parts = 1;
+    int n_workers = 0;
+    int default_threads = 4;
+    pid_t owner_pid = 0;
+
+    void loop(int part) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* f;
+            int parts;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return gen != seen; });
+                seen = gen;
+                f = fn;
+                parts = n_parts;
+            }
+            if (part < parts) (*f)(part, parts);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) done_cv.notify_one();
+            }
+        }
+    }
+};
+
+HostPool& HostPool::get() {
+    static HostPool* p = new HostPool();
+    return *p;
+}
+
+HostPool::HostPool() : impl_(new Impl()) {
+    int n = 4;
+    if (const char* e = getenv("SPX_HOST_THREADS")) n = atoi(e);
+    if (n < 1) n = 1;
+    impl_->default_threads = n;
+    cpu_set_t set;
+    int hw = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);
+    int cap = 16;
+    if (hw > 0 && cap > hw) cap = hw;
+    if (n == 1 && getenv("SPX_HOST_THREADS")) cap = 1;       // SPX_HOST_THREADS=1: no helpers
+    impl_->n_workers = cap - 1;
+    impl_->owner_pid = getpid();
+    for (int i = 0; i < impl_->n_workers; ++i) {
+        Impl* im = impl_;
+        std::thread([im, i] { im->loop(i + 1); }).detach();
+    }
+}
+
+int HostPool::max_threads() const { return impl_->n_workers + 1; }
+
+void HostPool::run(const std::function<void(int, int)>& fn, int n_threads) {
+    Impl& im = *impl_;
+    int parts = n_threads > 0 ? n_threads : im.default_threads;
+    if (parts > im.n_workers + 1) parts = im.n_workers + 1;
+    // a forked child inherits the object but not the worker threads
+    if (parts <= 1 || getpid() != im.owner_pid) {
+        fn(0, 1);
+        return;
+    }
+    std::lock_guard<std::mutex> call_lock(im.call_mu);       // one job at a time
+    {
+        std::lock_guard<std::mutex> lk(im.mu);
+        im.fn = &fn;
+        im.n_parts = parts;
+        im.pending = im.n_workers;
+        ++im.gen;
+    }
+    im.cv.notify_all();
+    fn(0, parts);
+    std::unique_lock<std::mutex> lk(im.mu);
+    im.done_cv.wait(lk, [&] { return im.pending == 0; });
+    im.fn = nullptr;
 }
 
 // Bt rows of the downdate: row i < n_data is the data of step src_step[i] with NaN -> 0;
@@ -147,36 +272,60 @@ int spx_avail_groups_host(const double* data, int64_t n_steps, int32_t n_stn, in
         return SPX_EINVAL;
     }
     const int W = (n_stn + 63) / 64;
-    std::vector<uint64_t> bits((size_t)W);
+    // ---- pass 1 (parallel over rows): availability words, count, flag, hash, copy -------
+    static thread_local std::vector<uint64_t> row_bits;
+    static thread_local std::vector<uint64_t> row_hash;
+    row_bits.resize((size_t)n_steps * W);
+    row_hash.resize((size_t)n_steps);
+    uint64_t* rb = row_bits.data();
+    uint64_t* rh = row_hash.data();
+    const bool use_avx2 = __builtin_cpu_supports("avx2") != 0;
+    auto scan = [&](int part, int n_parts) {
+        const int64_t t0 = n_steps * part / n_parts, t1 = n_steps * (part + 1) / n_parts;
+        for (int64_t t = t0; t < t1; ++t) {
+            const double* __restrict__ src = data + t * ld;
+            uint64_t* __restrict__ bits = rb + t * W;
+            int flag = 0;
+            if (use_avx2) {
+                scan_row_avx2(src, n_stn, min_var_thr, bits, &flag,
+                              data_copy ? data_copy + t * (int64_t)n_stn : nullptr);
+            } else {
+                scan_row_sse2(src, n_stn, min_var_thr, bits, &flag);
+                if (data_copy)
+                    std::memcpy(data_copy + t * (int64_t)n_stn, src, sizeof(double) * n_stn);
+            }
+            int cnt = 0;
+            uint64_t h = 0x9e3779b97f4a7c15ULL;
+            for (int w = 0; w < W; ++w) {
+                cnt += __builtin_popcountll(bits[w]);
+                h = mix64(h ^ bits[w]);
+            }
+            rh[t] = h;
+            n_avail[t] = cnt;
+            step_flag[t] = (uint8_t)(flag != 0);
+        }
+        if (data_copy && use_avx2) _mm_sfence();       // non-temporal stores visible to the DMA
+    };
+    if (n_steps * (int64_t)n_stn >= (1 << 16))
+        HostPool::get().run(scan);
+    else
+        scan(0, 1);
+    // ---- pass 2 (sequential): groups in first-occurrence order ---------------------------
     std::vector<uint64_t> grp_bits;                    // [n_grps, W]
     grp_bits.reserve((size_t)W * 64);
     size_t cap = 16;
     while (cap < (size_t)n_steps * 2 + 2) cap <<= 1;
     std::vector<int32_t> table(cap, -1);
     int32_t n_grps = 0;
-    const bool use_avx2 = __builtin_cpu_supports("avx2") != 0;
     for (int64_t t = 0; t < n_steps; ++t) {
-        const double* __restrict__ src = data + t * ld;
-        int flag = 0;
-        int cnt = 0;
-        uint64_t h = 0x9e3779b97f4a7c15ULL;
-        if (use_avx2)
-            scan_row_avx2(src, n_stn, min_var_thr, bits.data(), &flag);
-        else
-            scan_row_sse2(src, n_stn, min_var_thr, bits.data(), &flag);
-        for (int w = 0; w < W; ++w) {
-            cnt += __builtin_popcountll(bits[w]);
-            h = mix64(h ^ bits[w]);
-        }
-        if (data_copy) std::memcpy(data_copy + t * (int64_t)n_stn, src, sizeof(double) * n_stn);
-        n_avail[t] = cnt;
-        step_flag[t] = (uint8_t)(flag != 0);
-        size_t slot = (size_t)h & (cap - 1);
+        const uint64_t* bits = rb + t * W;
+        const int cnt = n_avail[t];
+        size_t slot = (size_t)rh[t] & (cap - 1);
         int32_t g = -1;
         for (;;) {
             const int32_t cand = table[slot];
             if (cand < 0) break;
-            if (std::memcmp(&grp_bits[(size_t)cand * W], bits.data(), sizeof(uint64_t) * W) == 0) {
+            if (std::memcmp(&grp_bits[(size_t)cand * W], bits, sizeof(uint64_t) * W) == 0) {
                 g = cand;
                 break;
             }
@@ -185,11 +334,11 @@ int spx_avail_groups_host(const double* data, int64_t n_steps, int32_t n_stn, in
         if (g < 0) {
             g = n_grps++;
             table[slot] = g;
-            grp_bits.insert(grp_bits.end(), bits.begin(), bits.end());
+            grp_bits.insert(grp_bits.end(), bits, bits + W);
             grp_first[g] = (int32_t)t;
             grp_n[g] = cnt;
             if (grp_bits_out)
-                std::memcpy(grp_bits_out + (int64_t)g * W, bits.data(), sizeof(uint64_t) * W);
+                std::memcpy(grp_bits_out + (int64_t)g * W, bits, sizeof(uint64_t) * W);
             if (grp_mask) {
                 uint8_t* __restrict__ m = grp_mask + (int64_t)g * n_stn;
                 int j = 0;

@@ -20,6 +20,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import math
+import os
 import time
 import types
 
@@ -135,8 +136,13 @@ class PendingChunk:
             if not to_host:
                 return self.flds, self.problem_steps
             torch.cuda.current_stream(eng.device).synchronize()
-            return ({lab: t.cpu().numpy() for lab, t in self.flds.items()},
-                    self.problem_steps)
+            out = {}
+            for lab, t in self.flds.items():
+                dl = eng._packed_downloader(t, self.round_decimals)
+                # rounded f32 fields cross PCIe as 16-bit codes (transfer.py), bit-exact
+                out[lab] = (dl.download(t, self.round_decimals) if dl is not None
+                            else t.cpu().numpy())
+            return out, self.problem_steps
 
 
 class _TracedLib:
@@ -194,8 +200,9 @@ class ChunkEngine:
         # ... and, when the whole chunk shares one variogram, submitted by ONE native call
         # (csrc/spx_chunk.cu) whose solve phase runs on a second stream underneath the
         # estimate kernel of the previous chunk
-        self.native_submit = True
+        self.native_submit = os.environ.get('SPX_NATIVE_SUBMIT', '1') != '0'
         self.fast_slots = 4
+        self.solve_stream = False   # solve phase on its own stream (no gain)
         self._fast_jobs = {}
         self._fast_prof = {}      # (job id, slot) -> (kernel, bound, work) awaiting its time
         # full-system inverses are reused across chunks with the same stations and
@@ -233,6 +240,9 @@ class ChunkEngine:
         self._arena_events = [None] * self._N_ARENAS
         self._arena_k = 0
         self._const_cache = {}
+        # rounded float32 fields are downloaded as 16-bit codes and decoded on the host
+        self.packed_download = True
+        self._dl = None
         self.threaded_upload = True
         self._uploader = None
 
@@ -366,6 +376,15 @@ class ChunkEngine:
             self._const_cache[key] = hit
         return hit
 
+    def _dev_keep(self, arr):
+        """Device copy of an array that OUTLIVES the chunk (cached geometry, bin tables):
+        its own allocation -- the per-chunk upload arenas are recycled after four
+        chunks."""
+        arr = np.ascontiguousarray(arr)
+        self._sync_uploads()
+        self.h2d_bytes += arr.nbytes
+        return torch.from_numpy(arr.copy()).to(self.device)
+
     def _dev(self, arr, dtype=None):
         """Host -> device copy on a dedicated upload stream.  A pageable-memory
         cudaMemcpyAsync first synchronises its stream, so issuing it on the compute
@@ -470,6 +489,19 @@ class ChunkEngine:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(self._main_stream())
         self.kernel_events.append((name, bound, float(work), e0, e1))
+
+    def _packed_downloader(self, t, decimals, depth=2):
+        """The 2-byte transport (transfer.PackedDownloader) for a rounded f32 field that is
+        large enough to matter, else None."""
+        if (not self.packed_download or decimals is None or not (0 <= int(decimals) <= 9)
+                or t.dtype != torch.float32 or t.dim() != 2 or t.numel() < (1 << 20)
+                or t.shape[0] > 65535):
+            return None
+        dl = self._dl
+        if dl is None or dl.row_len != t.shape[1] or dl.max_rows < t.shape[0]:
+            from .transfer import PackedDownloader
+            dl = self._dl = PackedDownloader(self.device, t.shape[0], t.shape[1], depth=depth)
+        return dl
 
     def round_and_stats(self, fld, decimals=None):
         """Round a device field [T, cells] in place (None: leave it) and return its
@@ -653,17 +685,29 @@ class ChunkEngine:
                 out_pos = None
                 dst_xs = np.ascontiguousarray(cell_xs[fld_beg_idx:fld_end_idx], dtype=np.float64)
                 dst_ys = np.ascontiguousarray(cell_ys[fld_beg_idx:fld_end_idx], dtype=np.float64)
-            assert dst_xs.shape[0] > 0
+            empty = dst_xs.shape[0] == 0
             geo = dict(msh_idxs=msh_idxs, out_pos=out_pos, dst_xs=dst_xs, dst_ys=dst_ys,
-                       d_cell_x=self._dev(dst_xs), d_cell_y=self._dev(dst_ys),
-                       d_pos=self._dev(out_pos) if out_pos is not None else None,
-                       bbox=(float(dst_xs.min()), float(dst_xs.max()), float(dst_ys.min()),
-                             float(dst_ys.max())),
+                       d_cell_x=None if empty else self._dev_keep(dst_xs),
+                       d_cell_y=None if empty else self._dev_keep(dst_ys),
+                       d_pos=(self._dev_keep(out_pos) if (out_pos is not None and not empty)
+                              else None),
+                       bbox=(0.0, 0.0, 0.0, 0.0) if empty else (
+                           float(dst_xs.min()), float(dst_xs.max()), float(dst_ys.min()),
+                           float(dst_ys.max())),
                        fp=gkey)
             while len(self._geom_cache) >= 4:
                 self._geom_cache.pop(next(iter(self._geom_cache)))
             self._geom_cache[gkey] = geo
         out_pos, dst_xs, dst_ys = geo['out_pos'], geo['dst_xs'], geo['dst_ys']
+        if dst_xs.shape[0] == 0:
+            # no cell of this grid-row chunk is selected: the fields stay NaN
+            # (steps.py:659-663 pre-fills them) and nothing is computed
+            tdt0 = torch.float64 if out_f64 else torch.float32
+            flds0 = {lab: torch.full((n_steps, fld_size), float('nan'), dtype=tdt0,
+                                     device=self.device) for lab in interp_labels}
+            n_av0 = np.isfinite(data).sum(axis=1)
+            return PendingChunk(self, flds0, [int(s_) for s_ in np.where(n_av0 == 0)[0]], [],
+                                dict(self.stats))
         if drft_arrs is not None:
             drft_arrs = (drft_arrs[:, geo['msh_idxs']] if geo['msh_idxs'] is not None
                          else drft_arrs[:, fld_beg_idx:fld_end_idx])
@@ -1004,7 +1048,7 @@ class ChunkEngine:
              + np.floor((sx - x0) / R).astype(np.int64))
         order = np.argsort(b, kind='stable').astype(np.int32)
         bin_start = np.searchsorted(b[order], np.arange(nbx * nby + 1)).astype(np.int32)
-        d_bs, d_bo = self._dev(bin_start), self._dev(order)
+        d_bs, d_bo = self._dev_keep(bin_start), self._dev_keep(order)   # cached with the tables
         n_cells = ctx['n_cells']
         cap = 8
         while True:
@@ -1069,6 +1113,41 @@ class ChunkEngine:
                 'nrst_topk')
         self._count('launches')
         return nb, hsh
+
+    def neighbor_indices(self, stn_xs, stn_ys, cell_xs, cell_ys, neb_sel_mthd, n_nebs,
+                         n_pies=None, avail=None):
+        """``get_neb_idxs_and_grps`` of the reference (interp/grps.py:249-288) on the GPU:
+        the neighbour row of every cell (ascending station indices; 'nrst': the n_nebs
+        nearest, 'pie': round-robin over n_pies angular sectors) and the groups of cells
+        with identical rows -- groups in first-occurrence order, members ascending.
+        avail: optional bool [n_stn], only these stations are candidates.
+        Returns (all_neb_idxs int64 [n_cells, k], [int64 arrays])."""
+        assert neb_sel_mthd in ('nrst', 'pie')
+        stn_xs = np.ascontiguousarray(stn_xs, dtype=np.float64)
+        stn_ys = np.ascontiguousarray(stn_ys, dtype=np.float64)
+        cell_xs = np.ascontiguousarray(cell_xs, dtype=np.float64)
+        cell_ys = np.ascontiguousarray(cell_ys, dtype=np.float64)
+        n_stn, n_cells = int(stn_xs.size), int(cell_xs.size)
+        n_av = n_stn if avail is None else int(np.count_nonzero(avail))
+        k = int(min(n_nebs, n_av))
+        with torch.cuda.device(self.device):
+            self._begin_call()
+            self._n_pies = int(n_pies) if neb_sel_mthd == 'pie' else 0
+            d_mask = None if avail is None else self._dev(np.asarray(avail).astype(np.uint8))
+            nb, hsh = self._topk(self._dev(stn_xs), self._dev(stn_ys), n_stn, d_mask,
+                                 self._dev(cell_xs), self._dev(cell_ys), n_cells, k)
+            uh, inv = torch.unique(hsh, return_inverse=True)
+            rep = torch.full((int(uh.numel()),), n_cells, dtype=_I64, device=self.device)
+            rep.scatter_reduce_(0, inv, torch.arange(n_cells, device=self.device), 'amin')
+            order = torch.argsort(rep)                      # first-occurrence order
+            rank = torch.empty_like(order)
+            rank[order] = torch.arange(order.numel(), device=self.device)
+            grp_of_cell = rank[inv].cpu().numpy()
+            idxs = nb.cpu().numpy().astype(np.int64)
+        by = np.argsort(grp_of_cell, kind='stable')
+        bounds = np.searchsorted(grp_of_cell[by], np.arange(int(uh.numel()) + 1))
+        grps = [by[bounds[g]:bounds[g + 1]].astype(np.int64) for g in range(int(uh.numel()))]
+        return idxs, grps
 
     def _nrst_groups(self, ctx, g, n_nebs):
         """Neighbour rows and cell groups of availability group g, cached per
@@ -1423,7 +1502,7 @@ class ChunkEngine:
             return None
         jkey = (gkey, ctx['geom_key'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'], ctx['lo'],
                 ctx['hi'], min_var_thr, self.local_support, self.local_max_near,
-                self.local_tiles, self.lambda_tol, self.downdate_min_systems)
+                self.local_tiles, self.lambda_tol, self.downdate_min_systems, self.solve_stream)
         job = self._fast_jobs.get(jkey)
         if job is not None and job['max_steps'] >= n_steps and job['ginv'] is ginv:
             return job
@@ -1440,6 +1519,7 @@ class ChunkEngine:
         cfg.lambda_bound = float(self._rhs_bound(ctx, K, None)[0])
         cfg.lambda_tol = float(self.lambda_tol)
         cfg.profile = 1
+        cfg.solve_stream = int(bool(self.solve_stream))
         keep = [ginv, ctx['d_stn_x'], ctx['d_stn_y'], ctx['d_cell_x'], ctx['d_cell_y'],
                 ctx['d_pos']]
         local = self._local_plan(ctx, [vg_s]) if self.local_support else None
@@ -1497,7 +1577,7 @@ class ChunkEngine:
         W = (n_stn + 63) // 64
         job = dict(handle=handle, cfg=cfg, keep=keep, d_arena=d_arena, h_arena=h_arena,
                    max_steps=int(n_steps), ginv=ginv, estimator=int(cfg.estimator), W=W,
-                   next_slot=0, id=self._next_job_id(),
+                   next_slot=0, id=self._next_job_id(), refs=0, retired=False, unchecked={},
                    res=_lib.spx_fast_result())
         while len(self._fast_jobs) >= 2:
             self._fast_job_close(next(iter(self._fast_jobs)))
@@ -1509,10 +1589,19 @@ class ChunkEngine:
         return self._fast_job_seq
 
     def _fast_job_close(self, jkey):
+        """Drop a job from the cache; it is destroyed once no pending chunk refers to it
+        (a chunk's health check reads the job's slot)."""
         job = self._fast_jobs.pop(jkey, None)
         if job is not None:
+            job['retired'] = True
+            self._fast_job_release(job, 0)
+
+    def _fast_job_release(self, job, n=1):
+        job['refs'] -= n
+        if job.get('retired') and job['refs'] <= 0 and job['handle'] is not None:
             self._fast_collect(job, all_slots=True)
             _lib.check(self.lib.spx_fast_destroy(job['handle']), 'fast_destroy')
+            job['handle'] = None
 
     def close(self):
         """Release the native jobs (their streams and events)."""
@@ -1522,6 +1611,8 @@ class ChunkEngine:
     def _fast_collect(self, job, slot=None, all_slots=False):
         """Move the measured estimate times of finished slots into kernel_events
         (profile_gemm): a slot's events are re-recorded when the ring comes round."""
+        if job['handle'] is None:
+            return
         slots = range(job['cfg'].n_slots) if all_slots else [slot]
         for k in slots:
             rec = self._fast_prof.pop((job['id'], k), None)
@@ -1545,6 +1636,9 @@ class ChunkEngine:
             return None
         if job['estimator'] == 0 and not self.local_support:
             return None
+        early = job['unchecked'].get(job['next_slot'])
+        if early is not None:
+            early()          # the ring came round: read that chunk's health flags first
         if self.profile_gemm or self._fast_prof:
             self._fast_collect(job, slot=job['next_slot'])
         if ctx['out_pos'] is None:
@@ -1572,6 +1666,7 @@ class ChunkEngine:
             self._count('fast_not_eligible')
             return dict(label=None, groups=groups, res=res, out=None, job=job)
         job['next_slot'] = (int(res.slot) + 1) % job['cfg'].n_slots
+        job['refs'] += 1                 # released by the chunk's deferred health check
         hm = self.stats.setdefault('fast_host_ms', [0.0] * 6)
         for i in range(6):
             hm[i] += res.host_ms[i]
@@ -1598,14 +1693,24 @@ class ChunkEngine:
 
     def _fast_deferred(self, ctx, fast, out, krige_mask, problem_steps):
         job, slot = fast['job'], int(fast['res'].slot)
+        state = {'done': False}
 
         def deferred():
             """Health flags of the slot (mapped host memory): an unhealthy elimination or
             a system whose weights may not sum to one sends the label through the general
-            path, which knows every fallback of the reference."""
+            path, which knows every fallback of the reference.  Runs once: from
+            PendingChunk.result(), or earlier if the ring comes round to the slot."""
+            if state['done']:
+                return
+            state['done'] = True
+            if job['unchecked'].get(slot) is deferred:
+                del job['unchecked'][slot]
             verdict = C.c_int32(0)
-            _lib.check(self.lib.spx_fast_check(job['handle'], slot, C.byref(verdict)),
-                       'fast_check')
+            try:
+                _lib.check(self.lib.spx_fast_check(job['handle'], slot, C.byref(verdict)),
+                           'fast_check')
+            finally:
+                self._fast_job_release(job)
             if verdict.value == 0:
                 self.stats['n_flagged'] = self.stats.get('n_flagged', 0)
                 return
@@ -1618,6 +1723,7 @@ class ChunkEngine:
             if fn is not None:
                 fn()
 
+        job['unchecked'][slot] = deferred
         return deferred
 
     def _krige_fast(self, ctx, out, kind_name, K, steps, step_vg, uniq_vgs, drft, drft_arrs,

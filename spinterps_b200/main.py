@@ -658,22 +658,42 @@ class SpInterpMain:
         self._main_vrfd_flag = True
 
     # ------------------------------------------------------------------ interpolate
-    def _time_chunks(self):
+    def _grid_row_chunks(self, world, n_steps):
+        """Grid-row chunks, the reference's second task axis (interp/main.py:733-734,
+        :805-811).  One chunk unless (a) there are fewer time steps than 4 x ranks -- few
+        steps on a huge grid shard by rows instead of by time -- or (b) a single step's
+        fields do not fit an eighth of the free device memory."""
+        import torch
+        ny = int(self._interp_crds_orig_shape[0])
+        chunks = 1
+        if world > 1 and n_steps < 4 * world:
+            chunks = min(world, ny)
+        fld = int(np.prod(self._interp_crds_orig_shape)) * np.dtype(self._intrp_dtype).itemsize
+        per_step = fld * max(1, len(self._interp_args))
+        free, _ = torch.cuda.mem_get_info()
+        while chunks < ny and per_step / chunks > 0.125 * free:
+            chunks += 1
+        forced = getattr(self, '_grid_row_chunks_forced', None)   # test hook
+        if forced is not None:
+            chunks = int(forced)
+        return np.unique(np.linspace(0, ny, chunks + 1, dtype=np.int64))
+
+    def _time_chunks(self, n_row_chunks=1):
         """Time chunks sized for HBM instead of the reference's RAM model
-        (interp/main.py:652-859): the fields of one chunk may take a quarter of the
-        free device memory (two chunks are in flight)."""
+        (interp/main.py:652-859): the fields of one task may take a quarter of the
+        free device memory (two tasks are in flight)."""
         import torch
         n_steps = self._data_df.shape[0]
         fld = int(np.prod(self._interp_crds_orig_shape)) * np.dtype(self._intrp_dtype).itemsize
         free, _ = torch.cuda.mem_get_info()
-        per_step = fld * max(1, len(self._interp_args))
+        per_step = fld * max(1, len(self._interp_args)) / max(1, int(n_row_chunks))
         max_steps = max(1, int(0.25 * free // per_step))
         if self._max_steps_per_chunk is not None:
             max_steps = min(max_steps, self._max_steps_per_chunk)
         n_chunks = int(ceil(n_steps / max_steps))
         return np.unique(np.linspace(0, n_steps, n_chunks + 1, dtype=np.int64))
 
-    def _chunk_args(self, beg, end, n_chunks, lock):
+    def _chunk_args(self, beg, end, n_chunks, lock, row_beg=0, row_end=None):
         """interp/main.py:604-650."""
         data_df = self._data_df.iloc[beg:end]
         krg = any(a[0] in ('OK', 'SK', 'EDK') for a in self._interp_args)
@@ -683,13 +703,23 @@ class SpInterpMain:
             assert np.all(vgs_ser.values != 'nan'), (
                 'NaN VGs not allowed! Use Nugget or any other appropriate one!')
         edk = self._edk_flag
+        if row_end is None:
+            row_end = int(self._interp_crds_orig_shape[0])
         return (data_df, int(beg), int(end), n_chunks, self._interp_args, lock,
                 self._drft_arrs if edk else None, self._stns_drft_df if edk else None,
-                vgs_ser, rord, 0, int(self._interp_crds_orig_shape[0]))
+                vgs_ser, rord, int(row_beg), int(row_end))
 
     def interpolate(self):
-        """interp/main.py:74-236."""
+        """interp/main.py:74-236.  The job is a list of (time chunk x grid-row chunk)
+        tasks (dist.plan_tasks).  One rank: task i+1 is prepared and queued on the GPU
+        while the fields of task i are downloaded, reduced to statistics and written.
+        Several ranks (torch.distributed initialised): every rank interpolates its own
+        tasks; round by round the finished, rounded slabs travel over NCCL (NVLink) to
+        the writer rank, which holds at most two foreign slabs at a time, downloads and
+        writes them -- only that rank touches the file (HDF5 is single-writer).  Memory
+        on every GPU is bounded by the task size, not by the job size."""
         assert self._main_vrfd_flag, 'Call the verify method first!'
+        import torch
         import torch.distributed as tdist
         from . import dist as sdist
 
@@ -698,103 +728,120 @@ class SpInterpMain:
         n_steps = self._data_df.shape[0]
         multi = tdist.is_initialized() and tdist.get_world_size() > 1
         rank = tdist.get_rank() if multi else 0
+        world = tdist.get_world_size() if multi else 1
         writer = 0
-        if multi:
-            shard_b = sdist.shard_bounds(n_steps, tdist.get_world_size())
-            beg_all, end_all = int(shard_b[rank]), int(shard_b[rank + 1])
-        else:
-            beg_all, end_all = 0, n_steps
+        row_b = self._grid_row_chunks(world, n_steps)
+        time_b = self._time_chunks(row_b.size - 1)
+        if multi and row_b.size == 2 and time_b.size - 1 < world:
+            # fewer time chunks than ranks: one (or more) per rank
+            time_b = np.unique(np.linspace(0, n_steps, min(n_steps, world) + 1, dtype=np.int64))
+        labels = [a[2] for a in self._interp_args]
+        tasks = sdist.plan_tasks(time_b, row_b, world)
+        sg = sdist.StreamedGather(tasks, labels, writer=writer)
+        mine = sg.my_tasks()
+        n_cols = int(self._interp_crds_orig_shape[1])
         steps_cls = SpInterpSteps(self)
-        bounds = self._time_chunks()
-        bounds = np.unique(np.clip(bounds, beg_all, end_all))
-        if bounds.size < 2:
-            bounds = np.array([beg_all, end_all])
-        stats_rows = {}
-        if not multi:
-            # one chunk in flight: chunk i+1 is prepared and queued on the GPU while the
-            # fields of chunk i are downloaded, reduced to statistics and written
-            prev = None
-            for i in range(bounds.size - 1):
-                if bounds[i + 1] == bounds[i]:
-                    continue
-                args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
+        stats_acc = {}
+        dev = torch.device('cuda', torch.cuda.current_device())
+        tdt = torch.float32 if np.dtype(self._intrp_dtype) == np.float32 else torch.float64
+        eng = steps_cls._get_engine()
+        self.gather_stats = dict(tasks=len(tasks), mine=len(mine), rounds=sg.n_rounds)
+
+        def consume(task, lab, buf, st):
+            """Writer: one foreign slab (still on the GPU) -> host -> statistics + file."""
+            tb, te, rb, re = task[:4]
+            flds = InterpFields()
+            flds.rounded = True
+            flds.stats = {lab: st.cpu().numpy()}
+            dl = eng._packed_downloader(buf, int(self._nc_nmrl_prcn))
+            flds[lab] = (dl.download(buf, int(self._nc_nmrl_prcn)) if dl is not None
+                         else buf.cpu().numpy())
+            args = self._chunk_args(tb, te, 1, lock, rb, re)
+            out = (lock, tb, te, args[0], args[8], 1, [lab], flds, rb, re, args[9],
+                   args[0].index, timeit.default_timer())
+            self._collect_stats(out, stats_acc)
+            steps_cls._write_to_disk(out)
+
+        prev = None
+        for j in range(sg.n_rounds + 1):
+            cur = None
+            if j < len(mine):
+                tb, te, rb, re = mine[j][:4]
+                args = self._chunk_args(tb, te, 1, lock, rb, re)
                 cur = (steps_cls._submit_interp(args, output_stage=True), args,
                        timeit.default_timer())
-                if prev is not None:
-                    out = steps_cls._finish_interp(*prev)
-                    self._collect_stats(out, stats_rows)
-                    steps_cls._write_to_disk(out)
-                prev = cur
             if prev is not None:
-                out = steps_cls._finish_interp(*prev)
-                self._collect_stats(out, stats_rows)
-                steps_cls._write_to_disk(out)
-        else:
-            # every rank interpolates its block of time steps; the f32 slabs are sent
-            # to the writer rank over NCCL (NVLink) and only that rank touches the file
-            import torch
-            labels = [a[2] for a in self._interp_args]
-            fld = int(np.prod(self._interp_crds_orig_shape))
-            dev = torch.device('cuda', torch.cuda.current_device())
-            tdt = torch.float32 if np.dtype(self._intrp_dtype) == np.float32 else torch.float64
-            parts = []
-            for i in range(bounds.size - 1):
-                if bounds[i + 1] == bounds[i]:
-                    continue
-                args = self._chunk_args(bounds[i], bounds[i + 1], 1, lock)
-                pend = steps_cls._submit_interp(args, output_stage=True)
-                # rounded fields stay in HBM: they go to the writer over NVLink
-                parts.append(steps_cls._finish_interp(pend, args, to_host=False)[7])
-            eng = steps_cls._get_engine()
-            for lab in labels:
-                if parts:
-                    slab = torch.cat([p_[lab] for p_ in parts]) if len(parts) > 1 \
-                        else parts[0][lab]
-                else:
-                    slab = torch.empty((0, fld), dtype=tdt, device=dev)
-                full = sdist.gather_slabs(slab, shard_b, dst=writer)
                 if rank == writer:
-                    flds = InterpFields()
-                    flds.rounded = True
-                    flds.stats = {lab: eng.round_and_stats(full)}
-                    flds[lab] = full.cpu().numpy()
-                    del full
-                    args = self._chunk_args(0, n_steps, 1, lock)
-                    out = (lock, 0, n_steps, args[0], args[8], 1, [lab], flds, 0,
-                           int(self._interp_crds_orig_shape[0]), args[9], args[0].index,
-                           timeit.default_timer())
-                    self._collect_stats(out, stats_rows)
+                    out = steps_cls._finish_interp(*prev)
+                    self._collect_stats(out, stats_acc)
                     steps_cls._write_to_disk(out)
+                else:
+                    out = steps_cls._finish_interp(*prev, to_host=False)
+                    flds = out[7]
+                    sg.send({lab: flds[lab] for lab in labels},
+                            {lab: torch.from_numpy(np.ascontiguousarray(flds.stats[lab])).to(dev)
+                             for lab in labels})
+            if multi and rank == writer and j >= 1:
+                sg.receive_round(j - 1, n_cols, tdt, dev, consume)
+            prev = cur
+        sg.flush()
+        self.gather_stats['bytes_received'] = int(sg.bytes_received)
+        if multi:
             tdist.barrier()
         if rank == writer:
-            self._save_stats_sers(stats_rows)
+            from . import ncwriter
+            ncwriter.finalize(self._nc_file_path)      # chunk index written, file closed
+            self._save_stats_sers(self._finish_stats(stats_acc))
         if self._vb:
             print(f'Done with the interpolation in {timeit.default_timer() - t0:0.1f} seconds.')
 
     # ------------------------------------------------------------------ stats
-    def _collect_stats(self, out, stats_rows):
+    def _collect_stats(self, out, stats_acc):
         """Per-step min / mean / max / std / count of every field
         (interp/main.py:474-525 computes them by re-reading the netCDF; here they
-        are taken from the rounded field before it is written)."""
+        are taken from the rounded field before it is written).  A step may arrive in
+        several grid-row chunks: the parts are merged (Chan et al. for mean / M2)."""
         labels, flds, time_steps = out[6], out[7], out[11]
         dev_stats = getattr(flds, 'stats', None)
         for lab in labels:
             if lab == 'EST_VARS_OK':
                 continue
             if dev_stats is not None and lab in dev_stats:
-                st = dev_stats[lab]       # reduced on the GPU (spx_round_stats_dev)
-                stats = dict(min=st[0], mean=st[1], max=st[2], std=st[3], count=st[4])
+                st = np.asarray(dev_stats[lab], dtype=np.float64)   # spx_round_stats_dev
+                mn, mean, mx, std, cnt = st[0], st[1], st[2], st[3], st[4]
             else:
                 f = np.round(flds[lab], self._nc_nmrl_prcn)
                 with np.errstate(invalid='ignore'), np.testing.suppress_warnings() as sup:
                     sup.filter(RuntimeWarning)
-                    stats = dict(min=np.nanmin(f, axis=1), mean=np.nanmean(f, axis=1),
-                                 max=np.nanmax(f, axis=1), std=np.nanstd(f, axis=1),
-                                 count=np.isfinite(f).sum(axis=1).astype(np.float64))
-            for stat, vals in stats.items():
-                col = stats_rows.setdefault(f'{lab}_{stat}', {})
-                for t, v in zip(time_steps, vals):
-                    col[t] = np.float32(v)
+                    mn, mean, mx = (np.nanmin(f, axis=1), np.nanmean(f, axis=1),
+                                    np.nanmax(f, axis=1))
+                    std = np.nanstd(f, axis=1)
+                    cnt = np.isfinite(f).sum(axis=1).astype(np.float64)
+            acc = stats_acc.setdefault(lab, {})
+            for k, t in enumerate(time_steps):
+                n_b = float(cnt[k])
+                part = (n_b, float(mean[k]), float(std[k]) ** 2 * n_b, float(mn[k]), float(mx[k]))
+                a = acc.get(t)
+                if a is None or a[0] == 0.0:
+                    acc[t] = part if (a is None or n_b > 0.0) else a
+                elif n_b > 0.0:
+                    n = a[0] + n_b
+                    dlt = part[1] - a[1]
+                    acc[t] = (n, a[1] + dlt * (n_b / n), a[2] + part[2] + dlt * dlt * (a[0] * n_b / n),
+                              min(a[3], part[3]), max(a[4], part[4]))
+
+    @staticmethod
+    def _finish_stats(stats_acc):
+        stats_rows = {}
+        for lab, acc in stats_acc.items():
+            for t, (n, mean, m2, mn, mx) in acc.items():
+                vals = dict(min=mn, mean=mean, max=mx,
+                            std=np.sqrt(m2 / n) if n > 0 else np.nan, count=n)
+                if n == 0:
+                    vals.update(min=np.nan, mean=np.nan, max=np.nan)
+                for stat, v in vals.items():
+                    stats_rows.setdefault(f'{lab}_{stat}', {})[t] = np.float32(v)
+        return stats_rows
 
     def _save_stats_sers(self, stats_rows):
         data_df = self._data_df.sort_index()

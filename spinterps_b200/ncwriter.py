@@ -2,22 +2,22 @@
 
 Dimensions ``dimx, dimy, dimt``; variables ``X`` ('d'), ``Y`` ('d', descending),
 ``time`` ('i8', + units / calendar); one ``(dimt, dimy, dimx)`` variable of the
-field dtype per interpolation label with ``units`` / ``standard_name``; the 29
-``sett_*`` global attributes and ``Source``.
+field dtype per interpolation label, zlib-compressed (+ shuffle) in ``(1, ny, nx)``
+chunks, with ``units`` / ``standard_name``; the 29 ``sett_*`` global attributes and
+``Source``.
 
-With ``netCDF4`` installed the file is NETCDF4 with zlib compression and
-``(1, ny, nx)`` chunks exactly like the reference.  ``netCDF4`` is absent in the
-build image, so there is a NetCDF-3 (classic, 64-bit offset) fallback through
-``scipy.io.netcdf_file`` with the same dimensions, variables and attributes but
-no compression, and ``time`` stored as 'i4' pairs is avoided by using 'd' there
-(NetCDF-3 has no 64-bit integer).  Which backend wrote a file is recorded in the
-global attribute ``spx_backend``.
+Two backends write the SAME layout: the ``netCDF4`` package when it is installed, else the
+self-contained NetCDF-4 / HDF5 writer of ``nc4file.py`` (the build image has no netCDF4 /
+HDF5 library), whose field chunks are compressed by a pool of threads.  Which backend wrote
+a file is recorded in the global attribute ``spx_backend``.
 """
 from __future__ import annotations
 
 from pathlib import Path
 
 import numpy as np
+
+from . import nc4file
 
 try:  # pragma: no cover - not installed in the build image
     import netCDF4 as _nc4
@@ -47,22 +47,49 @@ class _NC4Handle:
         self._h.close()
 
 
-class _NC3Handle:
-    def __init__(self, path, mode):
-        from scipy.io import netcdf_file
-        self._h = netcdf_file(str(path), mode, mmap=False, version=2)
+class _SpxHandle:
+    """nc4file.Nc4Writer behind the same four calls.  A file stays open between
+    ``open_for_update`` calls of one process (``close`` only syncs: the chunk index is
+    written back, the file is complete on disk); ``finalize(path)`` closes it."""
+
+    def __init__(self, path):
+        self._w = nc4file.Nc4Writer(path, 'r+')
 
     def write(self, label, t_idx, row_beg, row_end, values):
-        self._h.variables[label][t_idx, row_beg:row_end, :] = values
+        ny = self._w.vars[label]['shape'][1]
+        if isinstance(t_idx, slice):
+            t0 = t_idx.start or 0
+            if row_beg == 0 and row_end == ny:
+                self._w.write_steps(label, t0, values)
+            else:
+                vals = np.asarray(values)
+                for i in range(vals.shape[0]):
+                    self._w.write_rows(label, t0 + i, row_beg, row_end, vals[i])
+        else:
+            self._w.write_rows(label, int(t_idx), row_beg, row_end, values)
 
     def read(self, label, t_idx):
-        return np.array(self._h.variables[label][t_idx])
+        return self._w.read_step(label, int(t_idx))
 
     def sync(self):
-        self._h.flush()
+        self._w.sync()
 
     def close(self):
-        self._h.close()
+        self._w.sync()
+
+
+class _SpxReadHandle:
+    def __init__(self, path):
+        self._r = nc4file.Nc4Reader(path)
+
+    def read(self, label, t_idx):
+        return self._r.read_step(label, int(t_idx))
+
+    def close(self):
+        self._r.close()
+
+
+_OPEN = {}
 
 
 def open_for_update(path):
@@ -70,13 +97,25 @@ def open_for_update(path):
     (the reference re-opens the file in 'r+' mode per task, steps.py:908)."""
     if _nc4 is not None:
         return _NC4Handle(path, 'r+')
-    return _NC3Handle(path, 'a')
+    key = str(Path(path).resolve())
+    h = _OPEN.get(key)
+    if h is None:
+        h = _OPEN[key] = _SpxHandle(path)
+    return h
+
+
+def finalize(path):
+    """Close the cached writer of ``path`` (no-op with the netCDF4 backend)."""
+    h = _OPEN.pop(str(Path(path).resolve()), None)
+    if h is not None:
+        h._w.close()
 
 
 def open_for_read(path):
     if _nc4 is not None:
         return _NC4Handle(path, 'r')
-    return _NC3Handle(path, 'r')
+    finalize(path)
+    return _SpxReadHandle(path)
 
 
 def time_numbers(time_rng, units, calendar, tfreq):
@@ -137,29 +176,25 @@ def create(path, x_crds, y_crds, time_vals, interp_args, field_dtype, var_units,
         h.close()
         return path
 
-    from scipy.io import netcdf_file
-    h = netcdf_file(str(path), 'w', mmap=False, version=2)
-    h.createDimension('dimx', nx)
-    h.createDimension('dimy', ny)
-    h.createDimension('dimt', nt)
-    h.createVariable(xlab, 'd', ('dimx',))[:] = x_crds
-    h.createVariable(ylab, 'd', ('dimy',))[:] = y_crds
-    tv = h.createVariable(tlab, 'd', ('dimt',))
-    tv[:] = np.asarray(time_vals, dtype=np.float64)
-    if time_units is not None:
-        tv.units = time_units
-        tv.calendar = time_calendar
-    tcode = 'f' if np.dtype(field_dtype) == np.float32 else 'd'
+    finalize(path)
+    variables = [
+        dict(name=xlab, dtype='f8', dims=('dimx',), data=np.asarray(x_crds, dtype=np.float64),
+             attrs=[]),
+        dict(name=ylab, dtype='f8', dims=('dimy',), data=np.asarray(y_crds, dtype=np.float64),
+             attrs=[]),
+        dict(name=tlab, dtype='i8', dims=('dimt',), data=np.asarray(time_vals, dtype=np.int64),
+             attrs=([('units', str(time_units)), ('calendar', str(time_calendar))]
+                    if time_units is not None else [])),
+    ]
     for arg in interp_args:
         name = arg[2]
-        v = h.createVariable(name, tcode, ('dimt', 'dimy', 'dimx'))
-        v[:] = np.nan
-        v.units = var_units
-        v.standard_name = var_label + (
-            f' ({name[:3]}_exp_{arg[3]})' if arg[0] == 'IDW' else f' ({name})')
-    for k, val in settings.items():
-        setattr(h, k, str(val))
-    h.spx_backend = 'scipy-netcdf3'
-    h.Source = str(path)
-    h.close()
+        std = var_label + (f' ({name[:3]}_exp_{arg[3]})' if arg[0] == 'IDW' else f' ({name})')
+        variables.append(dict(name=name, dtype=np.dtype(field_dtype), dims=('dimt', 'dimy', 'dimx'),
+                              data=None, chunk=(1, ny, nx), deflate=int(complevel),
+                              attrs=[('units', str(var_units)), ('standard_name', std)]))
+    gattrs = [(k, str(val)) for k, val in settings.items()]
+    gattrs += [('spx_backend', 'spx-hdf5'), ('Source', str(path))]
+    w = nc4file.Nc4Writer(path, 'w')
+    w.create([('dimx', nx), ('dimy', ny), ('dimt', nt)], variables, gattrs)
+    w.close()
     return path

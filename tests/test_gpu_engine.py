@@ -394,6 +394,34 @@ def test_local_kernel_tile_staging_is_bit_identical(n_stn, vg, note):
     assert rel_err(outs[0], exp['OK'].astype(np.float32), _floor(exp['OK'])) <= 3e-7
 
 
+@pytest.mark.parametrize('ny,nx,n_steps', [(60, 68, 131), (64, 64, 128), (33, 36, 9)])
+def test_local_kernel_bulk_stores_are_bit_identical(ny, nx, n_steps):
+    """The streamlined local kernel writing through shared-memory staged row segments and
+    bulk async (TMA) stores gives the same bits as the per-lane streaming stores: ragged
+    last cell tile (n_cells % 256 != 0), ragged row groups (n_steps % 8 != 0, % 4 != 0),
+    several row blocks."""
+    from spinterps_b200 import _lib
+    from spinterps_b200.engine import ChunkEngine
+    assert (ny * nx) % 4 == 0
+    p = make_problem(73, 150, n_steps, ny, nx, cell=3000.0, miss=0.1)
+    kw = dict(interp_args=[('OK', None, 'OK')], vgs=[VG_C1] * n_steps, min_var_cut=0.5, **p)
+    outs = []
+    lib = _lib.load()
+    prev = lib.spx_local_set_bulk(1)
+    try:
+        for bulk in (1, 0):
+            lib.spx_local_set_bulk(bulk)
+            e = ChunkEngine()
+            got, _ = e.interp_chunk(intrp_dtype=np.float32, **kw)
+            assert e.stats.get('local_rows', 0) == n_steps
+            outs.append(got['OK'])
+    finally:
+        lib.spx_local_set_bulk(prev)
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    assert rel_err(outs[0], exp['OK'].astype(np.float32), _floor(exp['OK'])) <= 3e-7
+
+
 @pytest.mark.parametrize('n_stn,n_rows,n_data,n_border', [(130, 77, 50, 1), (500, 300, 200, 1),
                                                            (64, 64, 64, 2), (33, 5, 3, 3)])
 def test_ut_gemm_matches_matmul(n_stn, n_rows, n_data, n_border):
@@ -456,3 +484,93 @@ def test_native_submit_pipeline_many_chunks():
         assert got.shape == ref['OK'].shape
         assert rel_err(got, ref['OK'], _floor(ref['OK'])) <= 3e-7
     e1.close()
+
+
+def _assert_same_neighbours(eng, mthd, n_nebs, n_pies, sx, sy, cx, cy, avail=None):
+    got_idx, got_grps = eng.neighbor_indices(sx, sy, cx, cy, mthd, n_nebs, n_pies=n_pies,
+                                             avail=avail)
+    if avail is None:
+        exp_idx, exp_grps = orc.get_neb_idxs_and_grps(mthd, n_nebs, cx, cy, sx, sy, n_pies=n_pies)
+    else:
+        keep = np.where(avail)[0]
+        loc_idx, exp_grps = orc.get_neb_idxs_and_grps(mthd, n_nebs, cx, cy, sx[keep], sy[keep],
+                                                      n_pies=n_pies)
+        exp_idx = keep[loc_idx]
+    assert got_idx.dtype == np.int64 and got_idx.shape == exp_idx.shape
+    assert np.array_equal(got_idx, exp_idx)                       # bit-exact index rows
+    assert len(got_grps) == len(exp_grps)
+    for a, b in zip(got_grps, exp_grps):                          # same groups, same order
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('name', ['e_nrst', 'h_pie'])
+def test_neighbour_and_cell_group_indices_bit_exact_on_golden_inputs(name):
+    """north_star: station grouping, neighbour and cell-selection indices bit-exact.  The
+    index arrays of spx_nrst_topk_dev / spx_pie_select_dev and the neighbour-hash cell
+    groups are compared DIRECTLY (not through the fields) with the oracle's
+    get_neb_idxs_and_grps (interp/grps.py:103-288) on the inputs of the reference-generated
+    golden cases, for all stations and for one availability subset."""
+    from spinterps_b200.engine import ChunkEngine
+    case, _ = load_case(name)
+    e = ChunkEngine()
+    mthd, k, npies = case['neb_sel_mthd'], case['n_nebs'], case.get('n_pies')
+    sx, sy, cx, cy = case['stn_xs'], case['stn_ys'], case['cell_xs'], case['cell_ys']
+    _assert_same_neighbours(e, mthd, k, npies, sx, sy, cx, cy)
+    avail = np.isfinite(case['data'][0])
+    if avail.sum() > k and not avail.all():
+        _assert_same_neighbours(e, mthd, k, npies, sx, sy, cx, cy, avail=avail)
+
+
+@pytest.mark.parametrize('mthd,n_stn,k,n_pies', [('nrst', 2000, 50, None), ('nrst', 1000, 64, None),
+                                                  ('pie', 300, 12, 4)])
+def test_neighbour_indices_bit_exact_large_station_sets(mthd, n_stn, k, n_pies):
+    """The reference's canonical setting (test/test_interp.py:101-103: nrst, 50
+    neighbours) at N = 2000 stations."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(93, n_stn, 2, 40, 50, cell=2500.0)
+    rng = np.random.default_rng(94)
+    avail = rng.random(n_stn) > 0.2
+    e = ChunkEngine()
+    _assert_same_neighbours(e, mthd, k, n_pies, p['stn_xs'], p['stn_ys'], p['cell_xs'],
+                            p['cell_ys'])
+    _assert_same_neighbours(e, mthd, k, n_pies, p['stn_xs'], p['stn_ys'], p['cell_xs'],
+                            p['cell_ys'], avail=avail)
+
+
+def test_cached_geometry_survives_the_upload_arena_ring():
+    """Seven chunks through ONE engine (the upload arenas are a ring of four): every label of
+    every chunk equals the result of a fresh engine.  (Device copies that outlive a chunk --
+    cell coordinates, bin tables -- must not live in a per-chunk arena.)"""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(95, 40, 35, 31, 39, cell=1500.0, miss=0.15)
+    base = {k: v for k, v in p.items() if k != 'data'}
+    args = [('OK', None, 'OK'), ('IDW', None, 'IDW_000', 2.0), ('NNB', None, 'NNB')]
+    eng = ChunkEngine()
+    eng_dense = ChunkEngine()
+    eng_dense.local_support = False
+    for i in range(7):
+        d = p['data'][5 * i:5 * i + 5]
+        kw = dict(interp_args=args, vgs=[VG_C1] * 5, intrp_dtype=np.float64, **base)
+        ref, _ = ChunkEngine().interp_chunk(d, **kw)
+        for e in (eng, eng_dense):
+            got, _ = e.interp_chunk(d, **kw)
+            for lab in ref:
+                assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, (i, lab)
+
+
+def test_geometry_cache_follows_in_place_coordinate_edits():
+    """The cross-chunk caches are keyed by content: shifting the coordinate arrays IN PLACE
+    (same buffers, same addresses) must give the fields of the shifted grid."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(96, 60, 6, 20, 25, cell=2000.0, miss=0.1)
+    kw = dict(interp_args=[('OK', None, 'OK'), ('IDW', None, 'IDW_000', 2.0)], vgs=[VG_C1] * 6,
+              intrp_dtype=np.float64)
+    eng = ChunkEngine()
+    a, _ = eng.interp_chunk(**kw, **p)
+    p['cell_xs'] += 700.0                     # in place
+    p['cell_ys'] -= 300.0
+    b, _ = eng.interp_chunk(**kw, **p)
+    ref, _ = ChunkEngine().interp_chunk(**kw, **p)
+    for lab in ref:
+        assert rel_err(b[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
+        assert rel_err(a[lab], ref[lab], _floor(ref[lab])) > 1e-6, lab   # the grids do differ

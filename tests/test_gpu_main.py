@@ -139,3 +139,54 @@ def test_round_stats_kernel(dtype):
         assert np.array_equal(st[4], exp[4])
         ok = ~np.isnan(exp)
         assert np.all(np.abs(st[ok] - exp[ok]) <= 1e-11 * np.maximum(1.0, np.abs(exp[ok])))
+
+
+@pytest.mark.parametrize('decimals,scale,special', [(2, 5.0, 'nan'), (1, 30.0, 'none'),
+                                                    (3, 2.0, 'wide'), (0, 100.0, 'inf'),
+                                                    (2, 5.0, 'unrounded')])
+def test_packed_download_is_bit_exact(decimals, scale, special):
+    """The 2-byte transport of rounded f32 fields (spx_pack_field_dev -> PCIe ->
+    spx_unpack_field_host) returns exactly the bytes of the rounded field: NaN rows and
+    cells, negative values, rows whose range exceeds 16 bits, infinities, a field that was
+    never rounded (every row falls back to raw floats), ragged row length."""
+    import torch
+    from spinterps_b200 import _lib
+    from spinterps_b200.engine import ChunkEngine
+    from spinterps_b200.transfer import PackedDownloader
+    eng = ChunkEngine()
+    rng = np.random.default_rng(11)
+    T, G = 37, 30011
+    f = (rng.gamma(1.0, scale, size=(T, G)) - 0.3 * scale).astype(np.float32)
+    if special == 'nan':
+        f[rng.random(f.shape) < 0.1] = np.nan
+        f[5] = np.nan
+    elif special == 'wide':
+        f[3, 100] = 1.0e5          # range of the row > 65534 codes -> raw
+        f[7] *= 1.0e6              # |q| beyond int32 -> raw
+    elif special == 'inf':
+        f[2, 17] = np.inf
+        f[9, 3] = -np.inf
+    d = torch.from_numpy(f).cuda()
+    if special != 'unrounded':
+        eng.round_and_stats(d, decimals)
+        exp = np.round(f, decimals)
+    else:
+        exp = f
+    assert np.array_equal(d.cpu().numpy(), exp, equal_nan=True)
+    dl = PackedDownloader(eng.device, T, G)
+    out = np.full((T, G), -7.0, dtype=np.float32)
+    n_raw = dl.finish(dl.start(d, decimals), out)
+    assert np.array_equal(out.view(np.uint32)[~np.isnan(exp)],
+                          exp.view(np.uint32)[~np.isnan(exp)])       # incl. the sign of zero
+    assert (np.signbit(exp) & (exp == 0)).any() or special != 'nan'   # -0.0 is exercised
+    assert np.array_equal(np.isnan(out), np.isnan(exp))
+    if special == 'unrounded':
+        assert n_raw >= T - 1
+    elif special == 'wide':
+        assert n_raw == 2
+    elif special == 'inf':
+        assert n_raw == 2
+    else:
+        assert n_raw == 0
+    # and through the public result() of a chunk
+    assert dl.d2h_bytes >= T * 2 * G

@@ -77,20 +77,21 @@ def test_output_file_layout(tmp_path):
     h.write('OK', 2, 3, 5, np.tile(fld[:, :1], (1, 10)))
     h.sync()
     h.close()
-    from scipy.io import netcdf_file
     if ncwriter.have_netcdf4():
         pytest.skip('netCDF4 backend: layout checked by the netCDF4 library itself')
-    f = netcdf_file(str(p), 'r', mmap=False)
+    ncwriter.finalize(p)
+    from spinterps_b200.nc4file import Nc4Reader
+    f = Nc4Reader(p)
     assert f.dimensions == {'dimx': 10, 'dimy': 8, 'dimt': 5}
-    assert np.array_equal(f.variables['X'][:], x) and np.array_equal(f.variables['Y'][:], y)
-    assert f.variables['Y'][0] > f.variables['Y'][-1]              # Y descending
-    assert f.variables['OK'].dimensions == ('dimt', 'dimy', 'dimx')
-    assert f.variables['OK'].standard_name == b'precip (OK)'
-    assert f.variables['IDW_000'].standard_name == b'precip (IDW_exp_2.0)'
-    assert f.variables['time'].units == b'days since 1900-01-01'
-    assert f.sett_cell_size == b'1000.0'
-    ok = f.variables['OK'][:]
-    assert np.isnan(ok[0]).all() and np.array_equal(ok[2, 3:5, 0], [0, 8])
+    assert np.array_equal(f.read_var('X'), x) and np.array_equal(f.read_var('Y'), y)
+    assert f.read_var('Y')[0] > f.read_var('Y')[-1]              # Y descending
+    assert f.datasets['OK']['dims'] == ('dimt', 'dimy', 'dimx')
+    assert f.datasets['OK']['attrs']['standard_name'] == 'precip (OK)'
+    assert f.datasets['IDW_000']['attrs']['standard_name'] == 'precip (IDW_exp_2.0)'
+    assert f.datasets['time']['attrs']['units'] == 'days since 1900-01-01'
+    assert f.root_attrs['sett_cell_size'] == '1000.0'
+    assert np.isnan(f.read_step('OK', 0)).all()
+    assert np.array_equal(f.read_step('OK', 2)[3:5, 0], [0, 8])
     f.close()
 
 
@@ -300,3 +301,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'cell-steps/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+def test_unpack_field_host_matches_numpy_division():
+    """Host decode of the 2-byte field transport (spx_unpack_field_host): float32(qmin + code)
+    / float32(10^d) with IEEE division, 0xFFFF -> NaN, raw rows untouched; threaded and
+    single-threaded, unaligned row pitch."""
+    import ctypes as C
+    from spinterps_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    T, G, d = 23, 1003, 2
+    stride = int(lib.spx_pack_stride(G))
+    assert stride % 8 == 0 and stride >= G
+    codes = rng.integers(0, 65536, size=(T, stride)).astype(np.uint16)
+    codes[:, ::7] = 0xFFFF
+    codes[:, 3::11] = 0xFFFE
+    hdr = np.zeros(T, dtype=_lib.PACK_ROW_DTYPE)
+    hdr['qmin'] = rng.integers(-40000, 40000, size=T)
+    hdr['mode'][[4, 11]] = _lib.SPX_PACK_RAW
+    p = np.float32(10.0 ** d)
+    exp = (hdr['qmin'][:, None].astype(np.int64) + codes[:, :G].astype(np.int64)).astype(
+        np.float32) / p
+    exp[codes[:, :G] == 0xFFFF] = np.nan
+    exp[codes[:, :G] == 0xFFFE] = -0.0
+    for n_threads, ld in ((1, G), (4, G + 3)):
+        out = np.full((T, ld), -1.0, dtype=np.float32)
+        _lib.check(lib.spx_unpack_field_host(hdr.ctypes.data, codes.ctypes.data, T, G, d,
+                                             out.ctypes.data, ld, n_threads), 'unpack')
+        got = out[:, :G]
+        keep = hdr['mode'] == _lib.SPX_PACK_U16
+        assert np.array_equal(got[keep], exp[keep], equal_nan=True)
+        assert np.array_equal(np.signbit(got[keep]), np.signbit(exp[keep]))
+        assert (got[~keep] == -1.0).all() and (out[:, G:] == -1.0).all()
