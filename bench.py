@@ -615,6 +615,13 @@ def run_gpu(args):
     # arena ring has 4 slots that are allocated on first use, the caching allocator has
     # to see the 5 GB field blocks once.  Untimed warm-up is therefore at least 8 chunks.
     n_prime = max(args.warmup, 8)
+    if world > 1:
+        # finish the (lazy) NCCL communicator set-up before anything is timed
+        t = torch.ones(1, device='cuda')
+        dist.all_reduce(t)
+        dist.barrier()
+        torch.cuda.synchronize()
+        n_prime = max(n_prime, 12)
     run_resident(n_prime)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)

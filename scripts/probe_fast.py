@@ -7,7 +7,13 @@ import bench
 from spinterps_b200.engine import ChunkEngine
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-chunks = [bench.make_chunk(0, v) for v in range(4)]
+rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+print('rank', rank, 'cores in affinity mask', len(os.sched_getaffinity(0)), flush=True)
+chunks = [bench.make_chunk(rank, v) for v in range(4)]
 eng = ChunkEngine()
 eng.solve_stream = os.environ.get('PROBE_SOLVE_STREAM') == '1'
 kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32)

@@ -506,11 +506,31 @@ class SpInterpMain:
         y_min -= self._cell_bdist
         y_max += self._cell_bdist
         self._x_min, self._x_max, self._y_min, self._y_max = x_min, x_max, y_min, y_max
-        max_col = int(ceil((x_max - x_min) / cs)) - 1
-        max_row = int(ceil((y_max - y_min) / cs)) - 1
-        assert 0 <= max_col and 0 <= max_row
-        xs = np.linspace(x_min + 0.5 * cs, x_min + 0.5 * cs + max_col * cs, max_col + 1)
-        ys = np.linspace(y_max - 0.5 * cs, y_max - 0.5 * cs - max_row * cs, max_row + 1)
+        arr_ras = [f for f in (self._drft_rass or []) if not callable(f)] if self._edk_flag else []
+        if arr_ras:
+            # with drift rasters the row / column window is RASTER-relative
+            # (interp/prepare.py:150-173): a grid origin that is not aligned to the raster
+            # spans one more column / row than ceil((x_max - x_min) / cell)
+            f0 = arr_ras[0]
+            nr0, nc0 = f0['values'].shape
+            assert np.isclose(f0['cell_size'], cs), 'Drift raster cell size != grid cell size!'
+            assert x_min >= f0['x_min'], 'Grid x_min outside of the drift rasters!'
+            assert x_max <= f0['x_min'] + nc0 * cs, 'Grid x_max outside of drift rasters!'
+            assert y_min >= f0['y_max'] - nr0 * cs, 'Grid y_min outside of the drift rasters!'
+            assert y_max <= f0['y_max'], 'Grid y_max outside of drift rasters!'
+            min_col = int(floor((x_min - f0['x_min']) / cs))
+            max_col = int(ceil((x_max - f0['x_min']) / cs)) - 1
+            min_row = int(floor((f0['y_max'] - y_max) / cs))
+            max_row = int(ceil((f0['y_max'] - y_min) / cs)) - 1
+        else:
+            min_col = min_row = 0
+            max_col = int(ceil((x_max - x_min) / cs)) - 1
+            max_row = int(ceil((y_max - y_min) / cs)) - 1
+        assert 0 <= min_col <= max_col, (min_col, max_col)
+        assert 0 <= min_row <= max_row, (min_row, max_row)
+        n_cols, n_rows = max_col - min_col + 1, max_row - min_row + 1
+        xs = np.linspace(x_min + 0.5 * cs, x_min + 0.5 * cs + (n_cols - 1) * cs, n_cols)
+        ys = np.linspace(y_max - 0.5 * cs, y_max - 0.5 * cs - (n_rows - 1) * cs, n_rows)
         mx, my = np.meshgrid(xs, ys)
         self._interp_crds_orig_shape = mx.shape
         self._nc_x_crds, self._nc_y_crds = xs, ys
@@ -560,17 +580,17 @@ class SpInterpMain:
                 nr, nc = f['values'].shape
                 assert x_max <= f['x_min'] + nc * cs and y_min >= f['y_max'] - nr * cs, (
                     'Grid outside of the drift rasters!')
-                min_col = int(floor((x_min - f['x_min']) / cs))
-                min_row = int(floor((f['y_max'] - y_max) / cs))
-                rr, cc = prep.drift_cell_indices(min_row, min_row + max_row, min_col,
-                                                 min_col + max_col, self._cntn_idxs)
+                assert np.isclose(f['x_min'], arr_ras[0]['x_min']) and np.isclose(
+                    f['y_max'], arr_ras[0]['y_max']), 'Drift rasters with different extents!'
+                rr, cc = prep.drift_cell_indices(min_row, max_row, min_col, max_col,
+                                                 self._cntn_idxs)
                 cell_rows.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
                 rr, cc = prep.drift_point_indices(sx, sy, f['x_min'], f['y_max'], cs)
                 stn_cols.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
             self._drft_arrs = np.vstack(cell_rows)
             self._stns_drft_df = pd.DataFrame(np.column_stack(stn_cols), index=self._crds_df.index)
-            fin = np.isfinite(self._stns_drft_df.values).all(axis=1)
-            self._stns_drft_df = self._stns_drft_df.loc[fin]
+            assert np.all(np.isfinite(self._stns_drft_df.values)), (   # interp/drift.py:221-222
+                'Invalid value(s) of drift(s) for stations in drift rasters!')
 
         self._out_dir.mkdir(exist_ok=True)
 

@@ -133,6 +133,12 @@ def test_main_with_polygons_and_array_drift_raster(tmp_path):
     allv = np.concatenate(rings)
     assert np.isclose(m._x_min, allv[:, 0].min() - 3000.0) and np.isclose(m._y_max, allv[:, 1].max() + 3000.0)
     ny, nx = m._interp_crds_orig_shape
+    # the grid's row / column window is RASTER-relative (interp/prepare.py:163-173): with an
+    # origin that is not aligned to the raster it spans max - min + 1 columns / rows
+    assert ((m._x_min - rx0) / cs) % 1.0 > 1e-6 and ((ry1 - m._y_max) / cs) % 1.0 > 1e-6
+    assert nx == (int(np.ceil((m._x_max - rx0) / cs)) - 1) - int(np.floor((m._x_min - rx0) / cs)) + 1
+    assert ny == (int(np.ceil((ry1 - m._y_min) / cs)) - 1) - int(np.floor((ry1 - m._y_max) / cs)) + 1
+    assert nx >= int(np.ceil((m._x_max - m._x_min) / cs)) and ny >= int(np.ceil((m._y_max - m._y_min) / cs))
     gx = m._x_min + cs * (np.arange(nx) + 0.5)
     gy = m._y_max - cs * (np.arange(ny) + 0.5)
     fx, fy = np.meshgrid(gx, gy)
