@@ -483,6 +483,14 @@ typedef struct spx_nrst {
     int32_t out_f64, has_lo, has_hi;
     double lo, hi;
     double idw_exp;
+    /* estimation variance (EST_VARS_OK, interp/steps.py:428-434): spx_nrst_solve_dev also
+     * writes A^-1 of the systems u_beg .. u_end - 1 into inv, spx_nrst_krige_dev turns it
+     * into sum(lambda * rhs) + lambda[n] per cell and writes ev_out next to out.  u_end = 0
+     * means n_grp; cells of systems outside the range are left alone (the caller walks the
+     * systems in slices that bound inv). */
+    double* inv;              /* [u_end - u_beg, m, m] or NULL */
+    void* ev_out;             /* field of the same layout as out, or NULL */
+    int32_t u_beg, u_end;
 } spx_nrst;
 
 int spx_nrst_max_neighbors(void);
@@ -495,7 +503,7 @@ int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
 /* 'pie' selection (interp/grps.py:168-247 with cyth/interpmthds.pyx:811-890): stations
  * binned into n_pies angular sectors around the cell, ranked by distance inside their
  * sector; nb = the first k stations in (rank, distance) order, indices ascending; hash
- * as above.  n_pies <= 64. */
+ * as above.  n_pies <= k. */
 int spx_pie_select_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
                        const uint8_t* mask, const double* cell_x, const double* cell_y,
                        int64_t n_cells, int32_t k, int32_t n_pies, int32_t* nb, int64_t* hash,

@@ -139,7 +139,9 @@ class spx_nrst(C.Structure):
                 ('coef', C.c_void_p), ('ovr', C.c_void_p), ('info', C.c_void_p),
                 ('cell_pos', C.c_void_p), ('out', C.c_void_p), ('out_ld', C.c_int64),
                 ('out_f64', C.c_int32), ('has_lo', C.c_int32), ('has_hi', C.c_int32),
-                ('lo', C.c_double), ('hi', C.c_double), ('idw_exp', C.c_double)]
+                ('lo', C.c_double), ('hi', C.c_double), ('idw_exp', C.c_double),
+                ('inv', C.c_void_p), ('ev_out', C.c_void_p), ('u_beg', C.c_int32),
+                ('u_end', C.c_int32)]
 
 
 class spx_gemm(C.Structure):

@@ -17,8 +17,11 @@
 
 namespace spx {
 
-constexpr int NRST_KMAX = 64;   // neighbours per cell
-constexpr int NRST_MMAX = 72;   // k + border
+// Neighbours per cell: the per-thread work arrays are sized at compile time; two variants
+// (<= 64: the reference's usual 10 - 50 neighbours; <= 160: as many as the shared-memory
+// LU of k_nrst_solve can hold).
+constexpr int NRST_KMAX = 160;  // neighbours per cell, largest variant
+constexpr int NRST_BMAX = 8;    // border rows / columns (1 + drifts)
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
     h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
@@ -27,6 +30,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
     return h;
 }
 
+template <int KMAX>
 __global__ void __launch_bounds__(128) k_topk(const double* __restrict__ stn_x,
                                               const double* __restrict__ stn_y, int n_stn,
                                               const uint8_t* __restrict__ mask,  // [n_stn] or null
@@ -37,8 +41,8 @@ __global__ void __launch_bounds__(128) k_topk(const double* __restrict__ stn_x,
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     const double x = cell_x[c], y = cell_y[c];
-    double bd[NRST_KMAX];
-    int bi[NRST_KMAX];
+    double bd[KMAX];
+    int bi[KMAX];
     int cnt = 0;
     for (int s = 0; s < n_stn; ++s) {
         if (mask != nullptr && !mask[s]) continue;
@@ -79,8 +83,7 @@ __global__ void __launch_bounds__(128) k_topk(const double* __restrict__ stn_x,
 // i.e. the nearest station of every sector, then the second nearest of every sector, ...
 // One thread per cell, one pass over the stations per rank level (k / n_pies levels).
 // Sector expression: pie_sector() in spx_common.cuh.
-constexpr int PIE_MAX = 64;
-
+template <int KMAX>
 __global__ void __launch_bounds__(128) k_pie_select(const double* __restrict__ stn_x,
                                                     const double* __restrict__ stn_y, int n_stn,
                                                     const uint8_t* __restrict__ mask,
@@ -92,9 +95,9 @@ __global__ void __launch_bounds__(128) k_pie_select(const double* __restrict__ s
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     const double x = cell_x[c], y = cell_y[c];
-    double last_d[PIE_MAX], cand_d[PIE_MAX];
-    int last_i[PIE_MAX], cand_i[PIE_MAX];
-    int sel[NRST_KMAX];
+    double last_d[KMAX], cand_d[KMAX];      // n_pies <= k <= KMAX
+    int last_i[KMAX], cand_i[KMAX];
+    int sel[KMAX];
     for (int p = 0; p < n_pies; ++p) { last_d[p] = -1.0; last_i[p] = -1; }
     int cnt = 0;
     while (cnt < k) {
@@ -161,11 +164,13 @@ struct NrstSolveArgs {
     double* coef;                 // [n_grp, n_t + 1, m]  (row n_t = ones-vector solution)
     double* ovr;                  // [n_grp, n_t]  NaN = krige, else the value to write
     int32_t* info;                // [n_grp]
+    double* inv;                  // optional [u_end - u_beg, m, m]: A^-1 (estimation variance)
+    int u_beg;                    // first system of this launch
 };
 
 __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
     extern __shared__ double ssm[];
-    const int u = blockIdx.x;
+    const int u = a.u_beg + blockIdx.x;
     const int k = a.k, m = a.k + a.n_border;
     const int ld = m | 1;
     double* S = ssm;                        // [ld * m] column-major
@@ -247,19 +252,24 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
     if (tid == 0) a.info[u] = s_info;
     // ---- right-hand sides: n_t data steps + the ones vector, one per warp
     double* y = ys + (size_t)wid * ld;
-    for (int q = wid; q <= a.n_t; q += 4) {
+    // with inv: m more right-hand sides, the unit vectors (columns of A^-1)
+    const int n_rhs = a.n_t + 1 + (a.inv ? m : 0);
+    for (int q = wid; q < n_rhs; q += 4) {
         const bool ones = (q == a.n_t);
+        const int unit = q - a.n_t - 1;                 // >= 0: unit vector e_unit
         double zmax = -CUDART_INF, zsum = 0.0;
         for (int i = lane; i < m; i += 32) {
             double v = 0.0;
-            if (i < k) {
+            if (unit >= 0) {
+                v = (i == unit) ? 1.0 : 0.0;
+            } else if (i < k) {
                 v = ones ? 1.0 : a.data[(int64_t)a.steps[q] * a.n_stn + st[i]];
                 if (!ones) { zmax = fmax(zmax, v); zsum += v; }
             }
             y[i] = v;
         }
         __syncwarp();
-        if (!ones) {
+        if (!ones && unit < 0) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
@@ -290,7 +300,9 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
             for (int i = lane; i < c; i += 32) y[i] = fma(-cc[i], xc, y[i]);
             __syncwarp();
         }
-        double* dst = a.coef + ((int64_t)u * (a.n_t + 1) + q) * m;
+        double* dst = (unit >= 0)
+                          ? a.inv + ((int64_t)(u - a.u_beg) * m + unit) * m
+                          : a.coef + ((int64_t)u * (a.n_t + 1) + q) * m;
         for (int i = lane; i < m; i += 32) dst[i] = y[i];
         __syncwarp();
     }
@@ -321,16 +333,21 @@ struct NrstEstArgs {
     double lo, hi;
     double idw_exp;
     double min_var_thr;
+    const double* inv;            // optional [u_end - u_beg, m, m] (k_nrst_solve)
+    void* ev_out;                 // optional estimation-variance field (same layout as out)
+    int u_beg, u_end;             // systems of this launch (cells of other systems skip)
 };
 
+template <int KMAX>
 __global__ void __launch_bounds__(128) k_nrst_krige(NrstEstArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     const int k = a.k, m = a.k + a.n_border;
     const int u = a.cell_grp[c];
+    if (u < a.u_beg || u >= a.u_end) return;
     const int32_t* __restrict__ st = a.nbu + (int64_t)u * k;
     const double x = a.cell_x[c], y = a.cell_y[c];
-    double rhs[NRST_MMAX];
+    double rhs[KMAX + NRST_BMAX];
     const int covar = (a.kind == SPX_KRG_SK);
     double dmin = CUDART_INF;
     int nn = st[0];
@@ -352,9 +369,27 @@ __global__ void __launch_bounds__(128) k_nrst_krige(NrstEstArgs a) {
     bool ok = fabs(lsum - 1.0) <= (1e-8 + 1e-5);
     if (!(lsum == lsum) || isinf(lsum) || a.info[u] != 0) ok = false;
     const int64_t col = a.cell_pos ? (int64_t)a.cell_pos[c] : c;
+    // estimation variance (steps.py:431-434): sum(lambda * rhs) + lambda[n] with
+    // lambda = A^-1 rhs; the same for every step of the system
+    double est_var = 0.0;
+    if (a.ev_out != nullptr && ok) {
+        const double* __restrict__ iv = a.inv + (int64_t)(u - a.u_beg) * m * m;
+        double lam_n = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double* __restrict__ ci = iv + (int64_t)i * m;    // column i = row i (symmetric)
+            double li = 0.0;
+            for (int j = 0; j < m; ++j) li = fma(ci[j], rhs[j], li);
+            est_var = fma(li, rhs[i], est_var);
+            if (i == k) lam_n = li;
+        }
+        est_var += lam_n;
+    }
     for (int q = 0; q < a.n_t; ++q) {
         const int t = a.steps[q];
         const double ov = a.ovr[(int64_t)u * a.n_t + q];
+        if (a.ev_out != nullptr)      // steps.py:329 (mean steps), :425-426 (NNB): 0
+            store_out(a.ev_out, (int64_t)t * a.out_ld + col, (ov == ov || !ok) ? 0.0 : est_var,
+                      a.out_f64);
         double v;
         if (ov == ov) {
             v = ov;
@@ -371,13 +406,14 @@ __global__ void __launch_bounds__(128) k_nrst_krige(NrstEstArgs a) {
 }
 
 // IDW over the cell's neighbours; nb = the per-cell neighbour rows of k_topk.
+template <int KMAX>
 __global__ void __launch_bounds__(128) k_nrst_idw(NrstEstArgs a, const int32_t* __restrict__ nb) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     const int k = a.k;
     const int32_t* __restrict__ st = nb + c * k;
     const double x = a.cell_x[c], y = a.cell_y[c];
-    double w[NRST_KMAX];
+    double w[KMAX];
     double dmax = 0.0;
     for (int j = 0; j < k; ++j) {
         w[j] = dist_rn(x, y, a.stn_x[st[j]], a.stn_y[st[j]]);
@@ -423,8 +459,13 @@ int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
         set_error("nrst_topk: k=%d outside 1..%d", k, NRST_KMAX);
         return SPX_EINVAL;
     }
-    k_topk<<<(unsigned)((n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, nb, hash);
+    const unsigned nblk = (unsigned)((n_cells + 127) / 128);
+    if (k <= 64)
+        k_topk<64><<<nblk, 128, 0, (cudaStream_t)stream>>>(stn_x, stn_y, n_stn, mask, cell_x,
+                                                          cell_y, n_cells, k, nb, hash);
+    else
+        k_topk<NRST_KMAX><<<nblk, 128, 0, (cudaStream_t)stream>>>(stn_x, stn_y, n_stn, mask, cell_x,
+                                                                 cell_y, n_cells, k, nb, hash);
     SPX_CHECK_LAUNCH("k_topk");
     return SPX_OK;
 }
@@ -434,13 +475,18 @@ int spx_pie_select_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
                        int64_t n_cells, int32_t k, int32_t n_pies, int32_t* nb, int64_t* hash,
                        void* stream) {
     if (n_cells == 0) return SPX_OK;
-    if (k < 1 || k > NRST_KMAX || n_pies < 1 || n_pies > PIE_MAX) {
-        set_error("pie_select: k=%d outside 1..%d or n_pies=%d outside 1..%d", k, NRST_KMAX,
-                  n_pies, PIE_MAX);
+    if (k < 1 || k > NRST_KMAX || n_pies < 1 || n_pies > k) {
+        set_error("pie_select: k=%d outside 1..%d or n_pies=%d outside 1..k", k, NRST_KMAX,
+                  n_pies);
         return SPX_EINVAL;
     }
-    k_pie_select<<<(unsigned)((n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, n_pies, nb, hash);
+    const unsigned nblk = (unsigned)((n_cells + 127) / 128);
+    if (k <= 64)
+        k_pie_select<64><<<nblk, 128, 0, (cudaStream_t)stream>>>(
+            stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, n_pies, nb, hash);
+    else
+        k_pie_select<NRST_KMAX><<<nblk, 128, 0, (cudaStream_t)stream>>>(
+            stn_x, stn_y, n_stn, mask, cell_x, cell_y, n_cells, k, n_pies, nb, hash);
     SPX_CHECK_LAUNCH("k_pie_select");
     return SPX_OK;
 }
@@ -452,9 +498,14 @@ int spx_nrst_solve_dev(const spx_nrst* n, void* stream) {
     }
     if (n->n_grp == 0) return SPX_OK;
     const int m = n->k + n->n_border;
-    if (n->k < 1 || n->k > NRST_KMAX || m > NRST_MMAX) {
-        set_error("nrst_solve: k=%d / m=%d outside the supported range (%d / %d)", n->k, m,
-                  NRST_KMAX, NRST_MMAX);
+    if (n->k < 1 || n->k > NRST_KMAX || n->n_border > NRST_BMAX) {
+        set_error("nrst_solve: k=%d / border=%d outside the supported range (%d / %d)", n->k,
+                  n->n_border, NRST_KMAX, NRST_BMAX);
+        return SPX_EINVAL;
+    }
+    const int u_beg = n->u_beg, u_end = (n->u_end > 0) ? n->u_end : n->n_grp;
+    if (u_beg < 0 || u_end > n->n_grp || u_beg >= u_end) {
+        set_error("nrst_solve: bad system range");
         return SPX_EINVAL;
     }
     NrstSolveArgs a;
@@ -478,13 +529,19 @@ int spx_nrst_solve_dev(const spx_nrst* n, void* stream) {
     a.coef = n->coef;
     a.ovr = n->ovr;
     a.info = n->info;
+    a.inv = n->inv;
+    a.u_beg = u_beg;
     const int ld = m | 1;
     const size_t smem = ((size_t)ld * m + 4 * (size_t)ld) * sizeof(double) +
                         ((size_t)m + n->k) * sizeof(int);
+    if (smem > 220 * 1024) {
+        set_error("nrst_solve: a system of %d unknowns does not fit shared memory", m);
+        return SPX_ENOMEM;
+    }
     if (smem > 48 * 1024)
         SPX_CUDA(cudaFuncSetAttribute(k_nrst_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    k_nrst_solve<<<n->n_grp, 128, smem, (cudaStream_t)stream>>>(a);
+    k_nrst_solve<<<(unsigned)(u_end - u_beg), 128, smem, (cudaStream_t)stream>>>(a);
     SPX_CHECK_LAUNCH("k_nrst_solve");
     return SPX_OK;
 }
@@ -521,6 +578,10 @@ static void fill_est(NrstEstArgs& a, const spx_nrst* n) {
     a.hi = n->hi;
     a.idw_exp = n->idw_exp;
     a.min_var_thr = n->min_var_thr;
+    a.inv = n->inv;
+    a.ev_out = n->ev_out;
+    a.u_beg = n->u_beg;
+    a.u_end = (n->u_end > 0) ? n->u_end : n->n_grp;
 }
 
 int spx_nrst_krige_dev(const spx_nrst* n, void* stream) {
@@ -529,13 +590,15 @@ int spx_nrst_krige_dev(const spx_nrst* n, void* stream) {
         return SPX_EINVAL;
     }
     if (n->n_cells == 0 || n->n_t == 0) return SPX_OK;
-    if (n->k + n->n_border > NRST_MMAX) {
-        set_error("nrst_krige: system too large");
+    if (n->k > NRST_KMAX || n->n_border > NRST_BMAX || (n->ev_out && !n->inv)) {
+        set_error("nrst_krige: system too large, or ev_out without inv");
         return SPX_EINVAL;
     }
     NrstEstArgs a;
     fill_est(a, n);
-    k_nrst_krige<<<(unsigned)((n->n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    const unsigned nblk = (unsigned)((n->n_cells + 127) / 128);
+    if (n->k <= 64) k_nrst_krige<64><<<nblk, 128, 0, (cudaStream_t)stream>>>(a);
+    else k_nrst_krige<NRST_KMAX><<<nblk, 128, 0, (cudaStream_t)stream>>>(a);
     SPX_CHECK_LAUNCH("k_nrst_krige");
     return SPX_OK;
 }
@@ -552,7 +615,9 @@ int spx_nrst_idw_dev(const spx_nrst* n, const int32_t* nb, void* stream) {
     }
     NrstEstArgs a;
     fill_est(a, n);
-    k_nrst_idw<<<(unsigned)((n->n_cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, nb);
+    const unsigned nblk = (unsigned)((n->n_cells + 127) / 128);
+    if (n->k <= 64) k_nrst_idw<64><<<nblk, 128, 0, (cudaStream_t)stream>>>(a, nb);
+    else k_nrst_idw<NRST_KMAX><<<nblk, 128, 0, (cudaStream_t)stream>>>(a, nb);
     SPX_CHECK_LAUNCH("k_nrst_idw");
     return SPX_OK;
 }

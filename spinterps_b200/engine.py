@@ -137,6 +137,25 @@ class PendingChunk:
                 return self.flds, self.problem_steps
             torch.cuda.current_stream(eng.device).synchronize()
             out = {}
+            if to_host == 'packed':
+                # rounded f32 fields stay in their 2-byte form on the host
+                # (transfer.PackedField over a downloader slot; the consumer calls
+                # ``.release()``); anything else comes back as an array
+                tickets = {}
+                for lab, t in self.flds.items():
+                    dl = eng._packed_downloader(t, self.round_decimals,
+                                                depth=max(2, len(self.flds)))
+                    if dl is not None:
+                        tickets[lab] = (dl, dl.start(t, self.round_decimals))
+                for lab, t in self.flds.items():
+                    if lab in tickets:
+                        dl, tk = tickets[lab]
+                        pf = dl.wait(tk)
+                        pf.release = (lambda dl=dl, tk=tk: dl.release(tk))
+                        out[lab] = pf
+                    else:
+                        out[lab] = t.cpu().numpy()
+                return out, self.problem_steps
             for lab, t in self.flds.items():
                 dl = eng._packed_downloader(t, self.round_decimals)
                 # rounded f32 fields cross PCIe as 16-bit codes (transfer.py), bit-exact
@@ -498,7 +517,8 @@ class ChunkEngine:
                 or t.shape[0] > 65535):
             return None
         dl = self._dl
-        if dl is None or dl.row_len != t.shape[1] or dl.max_rows < t.shape[0]:
+        if (dl is None or dl.row_len != t.shape[1] or dl.max_rows < t.shape[0]
+                or len(dl.slots) < depth):
             from .transfer import PackedDownloader
             dl = self._dl = PackedDownloader(self.device, t.shape[0], t.shape[1], depth=depth)
         return dl
@@ -643,17 +663,12 @@ class ChunkEngine:
             if neb_sel_mthd == 'pie':
                 assert isinstance(n_pies, (int, np.integer)) and 0 < n_pies <= n_nebs, (
                     'n_pies should be > 0 and <= n_neighbors!')
-                if n_pies > 64:
-                    raise NotImplementedError('n_pies > 64 is not supported')
                 self._n_pies = int(n_pies)
             if n_nebs >= n_stn:
                 nrst = False            # interp/prepare.py:434-463 falls back to 'all'
             elif n_nebs > self.lib.spx_nrst_max_neighbors():
                 raise NotImplementedError(
                     f'n_neighbors > {self.lib.spx_nrst_max_neighbors()} is not supported')
-            elif est_var_flag and 'OK' in interp_types:
-                raise NotImplementedError(
-                    'EST_VARS_OK with nrst / pie neighbours is not supported')
         ev_flag = bool(est_var_flag) and ('OK' in interp_types)
         if ev_flag:
             assert 'EST_VARS_OK' in interp_labels, 'est_var_flag needs an EST_VARS_OK label'
@@ -847,7 +862,11 @@ class ChunkEngine:
                 self._nrst(ctx, out, itype, np.where(multi)[0], int(n_nebs), step_vg=step_vg,
                            uniq_vgs=uniq_vgs, nug=nug, min_var_thr=float(min_var_thr),
                            drft_arrs=drft_arrs if itype == 'EDK' else None,
-                           stns_drft=stns_drft if itype == 'EDK' else None)
+                           stns_drft=stns_drft if itype == 'EDK' else None,
+                           ev_out=flds['EST_VARS_OK'] if (ev_flag and itype == 'OK') else None)
+                if ev_flag and itype == 'OK' and single_steps.size:
+                    self._fill_rows(ctx, flds['EST_VARS_OK'], single_steps,
+                                    np.zeros(single_steps.size), clamp=False)
             elif itype in ('OK', 'SK', 'EDK'):
                 uniq_vgs = list(dict.fromkeys(vgs))
                 vg_id = {v: k for k, v in enumerate(uniq_vgs)}
@@ -1171,7 +1190,7 @@ class ChunkEngine:
         return res
 
     def _nrst(self, ctx, out, itype, steps, n_nebs, step_vg=None, uniq_vgs=None, nug=None,
-              idw_exp=0.0, min_var_thr=-np.inf, drft_arrs=None, stns_drft=None):
+              idw_exp=0.0, min_var_thr=-np.inf, drft_arrs=None, stns_drft=None, ev_out=None):
         """Kriging / IDW with the k nearest available stations per cell
         (interp/steps.py:740-833 with neb_sel_mthd == 'nrst')."""
         if not steps.size:
@@ -1237,9 +1256,22 @@ class ChunkEngine:
                     N.n_t = n_t
                     N.step_bypass = d_byp.data_ptr()
                     N.coef, N.ovr, N.info = coef.data_ptr(), ovr.data_ptr(), info.data_ptr()
-                    _lib.check(lib.spx_nrst_solve_dev(C.byref(N), self._stream()), 'nrst_solve')
-                    _lib.check(lib.spx_nrst_krige_dev(C.byref(N), self._stream()), 'nrst_krige')
-                    self._count('launches', 2)
+                    if ev_out is None:
+                        N.inv, N.ev_out, N.u_beg, N.u_end = None, None, 0, 0
+                        _lib.check(lib.spx_nrst_solve_dev(C.byref(N), self._stream()), 'nrst_solve')
+                        _lib.check(lib.spx_nrst_krige_dev(C.byref(N), self._stream()), 'nrst_krige')
+                        self._count('launches', 2)
+                        continue
+                    # estimation variance: A^-1 of the systems, in slices that bound it
+                    per = max(1, int((self.aux_limit // 2) // (m * m * 8)))
+                    N.ev_out = ev_out.data_ptr()
+                    for u0 in range(0, n_grp, per):
+                        u1 = min(n_grp, u0 + per)
+                        inv = torch.empty((u1 - u0, m, m), dtype=_F64, device=self.device)
+                        N.inv, N.u_beg, N.u_end = inv.data_ptr(), u0, u1
+                        _lib.check(lib.spx_nrst_solve_dev(C.byref(N), self._stream()), 'nrst_solve')
+                        _lib.check(lib.spx_nrst_krige_dev(C.byref(N), self._stream()), 'nrst_krige')
+                        self._count('launches', 2)
             self.stats['nrst_systems'] = self.stats.get('nrst_systems', 0) + n_grp
 
     # ---- IDW ------------------------------------------------------------
@@ -1637,8 +1669,8 @@ class ChunkEngine:
         if job['estimator'] == 0 and not self.local_support:
             return None
         early = job['unchecked'].get(job['next_slot'])
-        if early is not None:
-            early()          # the ring came round: read that chunk's health flags first
+        if early is not None and early['run'] is not None:
+            early['run']()   # the ring came round: read that chunk's health flags first
         if self.profile_gemm or self._fast_prof:
             self._fast_collect(job, slot=job['next_slot'])
         if ctx['out_pos'] is None:
@@ -1693,7 +1725,10 @@ class ChunkEngine:
 
     def _fast_deferred(self, ctx, fast, out, krige_mask, problem_steps):
         job, slot = fast['job'], int(fast['res'].slot)
-        state = {'done': False}
+        # state <-> deferred is a reference cycle only until the check has run (it is cut
+        # there): the closure keeps the chunk's 5 GB field alive, and a cycle would leave its
+        # release to the garbage collector
+        state = {'done': False, 'run': None}
 
         def deferred():
             """Health flags of the slot (mapped host memory): an unhealthy elimination or
@@ -1703,7 +1738,8 @@ class ChunkEngine:
             if state['done']:
                 return
             state['done'] = True
-            if job['unchecked'].get(slot) is deferred:
+            state['run'] = None
+            if job['unchecked'].get(slot) is state:
                 del job['unchecked'][slot]
             verdict = C.c_int32(0)
             try:
@@ -1723,7 +1759,8 @@ class ChunkEngine:
             if fn is not None:
                 fn()
 
-        job['unchecked'][slot] = deferred
+        state['run'] = deferred
+        job['unchecked'][slot] = state
         return deferred
 
     def _krige_fast(self, ctx, out, kind_name, K, steps, step_vg, uniq_vgs, drft, drft_arrs,

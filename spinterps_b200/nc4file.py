@@ -397,21 +397,24 @@ class Nc4Writer:
             raw = _shuffle(raw, v['dtype'].itemsize)
         return name, t, zlib.compress(raw, v['level'])
 
-    def write_steps(self, name, t0, values):
-        """values [n, ny, nx] (or a transfer.PackedField of n rows): whole steps t0..t0+n-1,
-        compressed by the thread pool."""
+    def write_steps(self, name, t0, values, t_index=None):
+        """values [n, ny, nx] (or a transfer.PackedField of n rows): whole steps, compressed
+        by the thread pool.  Row i goes to step t0 + i, or to t_index[i] when given."""
         v = self.vars[name]
         ny, nx = v['shape'][1], v['shape'][2]
-        if hasattr(values, 'row'):                       # PackedField: decode inside the worker
+        packed = hasattr(values, 'row')                   # PackedField: decode inside the worker
+        n = values.shape[0] if packed else None
+        if not packed:
+            values = np.asarray(values).reshape(-1, ny, nx)
             n = values.shape[0]
-            for i in range(n):
-                self._submit(self._encode, name, t0 + i,
-                             lambda i=i: values.row(i).reshape(1, ny, nx))
+        for i in range(n):
+            t = int(t_index[i]) if t_index is not None else t0 + i
+            if packed:
+                self._submit(self._encode, name, t, lambda i=i: values.row(i).reshape(1, ny, nx))
+            else:
+                self._submit(self._encode, name, t, lambda i=i: values[i:i + 1])
+        if packed:
             self._drain()                                 # the packed buffers are a ring slot
-            return
-        values = np.asarray(values).reshape(-1, ny, nx)
-        for i in range(values.shape[0]):
-            self._submit(self._encode, name, t0 + i, lambda i=i: values[i:i + 1])
 
     def write_rows(self, name, t, row_beg, row_end, values):
         """Part of step t (grid-row chunk): read-modify-write of its (1, ny, nx) chunk."""

@@ -68,6 +68,11 @@ class _SpxHandle:
         else:
             self._w.write_rows(label, int(t_idx), row_beg, row_end, values)
 
+    def write_packed(self, label, t_index, packed):
+        """Whole steps in the 2-byte transport form (transfer.PackedField): row i goes to
+        step t_index[i]; decoded step by step inside the compression workers."""
+        self._w.write_steps(label, 0, packed, t_index=t_index)
+
     def read(self, label, t_idx):
         return self._w.read_step(label, int(t_idx))
 

@@ -98,7 +98,10 @@ class SpInterpSteps:
         if interp_beg_time is None:
             interp_beg_time = timeit.default_timer()
         interp_labels = [a[2] for a in interp_args]
-        raw, prblm = pend.result(to_host=to_host)
+        # to the host in the 2-byte transport form when the output stage rounded the fields:
+        # the writer decodes step by step (transfer.PackedField)
+        raw, prblm = pend.result(to_host=('packed' if (to_host and pend.round_decimals is not None)
+                                          else to_host))
         flds = InterpFields(raw)
         flds.rounded = pend.round_decimals is not None
         flds.stats = pend.field_stats
@@ -131,6 +134,22 @@ class SpInterpSteps:
             try:
                 for label in interp_labels:
                     flds = interp_flds_dict[label]
+                    if hasattr(flds, 'row'):              # transfer.PackedField (rounded)
+                        ny_all = self._interp_crds_orig_shape[0]
+                        if (hasattr(nc_hdl, 'write_packed') and fld_beg_row == 0
+                                and fld_end_row == ny_all):
+                            if vgs_ser is None:
+                                t_index = np.arange(beg_idx, end_idx)
+                            else:
+                                t_index = [int(vgs_rord_tidxs_ser.loc[t]) for t in time_steps]
+                            nc_hdl.write_packed(label, t_index, flds)
+                            flds.release()
+                            interp_flds_dict[label] = None
+                            nc_hdl.sync()
+                            continue
+                        dec = flds.decode()
+                        flds.release()
+                        flds = dec
                     if (np.issubdtype(flds.dtype, np.floating)
                             and not getattr(interp_flds_dict, 'rounded', False)):
                         np.round(flds, self._nc_nmrl_prcn, flds)

@@ -126,6 +126,8 @@ class PackedField:
         self.lib, self.hdr, self.codes, self.raw = lib, hdr, codes, raw
         self.row_len, self.decimals = int(row_len), int(decimals)
         self.shape = (int(hdr.shape[0]), self.row_len)
+        self.dtype = np.dtype(np.float32)
+        self.release = lambda: None          # set by the producer: frees the transfer slot
         self.nbytes = int(hdr.nbytes + codes.nbytes + sum(v.nbytes for v in raw.values()))
 
     def decode(self, out=None, n_threads=0):

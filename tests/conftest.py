@@ -38,3 +38,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Parity report of the GPU tests (floored and un-floored relative errors per case)."""
+    try:
+        from tests import test_gpu_engine as tge
+        if tge.PARITY_REPORT:
+            import json
+            out = ROOT / 'gpurun_out'
+            out.mkdir(exist_ok=True)
+            (out / 'parity_report.json').write_text(json.dumps(tge.PARITY_REPORT, indent=1))
+    except Exception:
+        pass

@@ -43,9 +43,30 @@ def _floor(ref):
     return max(1e-3, 0.01 * float(np.nanmax(np.abs(ref)))) if np.isfinite(ref).any() else 1e-3
 
 
+PARITY_REPORT = []      # written to gpurun_out/parity_report.json at the end of the session
+
+
+def _report(name, lab, got, ref, floor):
+    """Besides the floored relative error the tests assert on: the UN-floored maximum
+    relative error (over cells with |ref| > 0) and the share of cells whose |ref| lies
+    below the floor, i.e. for which the floor matters at all."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    m = np.isfinite(ref) & (ref != 0)
+    unfl = float((np.abs(got[m] - ref[m]) / np.abs(ref[m])).max()) if m.any() else 0.0
+    fin = np.isfinite(ref)
+    PARITY_REPORT.append(dict(
+        case=name, label=lab, floor=float(floor), rel_err_floored=rel_err(got, ref, floor),
+        rel_err_unfloored=unfl,
+        cells_below_floor=float((np.abs(ref[fin]) < floor).mean()) if fin.any() else 0.0,
+        max_abs_err=float(np.abs(got[fin] - ref[fin]).max()) if fin.any() else 0.0,
+        field_max=float(np.abs(ref[fin]).max()) if fin.any() else 0.0))
+
+
 def _check(got, exp, name):
     for lab, ref in exp.items():
         e = rel_err(got[lab], ref, _floor(ref))
+        _report(name, lab, got[lab], ref, _floor(ref))
         assert e <= _tol(lab), (name, lab, e)
 
 
@@ -574,3 +595,90 @@ def test_geometry_cache_follows_in_place_coordinate_edits():
     for lab in ref:
         assert rel_err(b[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
         assert rel_err(a[lab], ref[lab], _floor(ref[lab])) > 1e-6, lab   # the grids do differ
+
+
+def test_parity_at_1000_stations_sk_ok_mask():
+    """Config-5 shape at a grid the oracle finishes in seconds: 1,000 stations, SK + OK,
+    elliptic cell mask, missing data (several availability groups of ~900 stations)."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(105, 1000, 6, 30, 40, cell=100000.0 / 40, miss=0.1)
+    cx, cy = p['cell_xs'], p['cell_ys']
+    mask = ((cx - 5.0e4) / 4.0e4) ** 2 + ((cy - 3.7e4) / 3.0e4) ** 2 <= 1.0
+    assert 0.3 < mask.mean() < 0.8
+    p['cell_xs'], p['cell_ys'] = cx[mask], cy[mask]
+    kw = dict(interp_args=[('OK', None, 'OK'), ('SK', None, 'SK')], vgs=[VG_C1] * 6,
+              cntn_idxs=mask, intrp_dtype=np.float64, **p)
+    exp, _ = orc.interp_chunk(faithful=False, **kw)
+    for local in (True, False):
+        e = ChunkEngine()
+        e.local_support = local
+        got, _ = e.interp_chunk(**kw)
+        _check(got, exp, 'n1000_sk_ok_mask_%s' % ('local' if local else 'dense'))
+        assert np.array_equal(np.isnan(got['OK']), np.isnan(exp['OK']))
+
+
+def test_parity_at_2000_stations_idw_four_exponents():
+    """Config-4 shape: 2,000 stations, IDW exponents 1, 2, 3, 5 (kpad 2000: the contraction
+    keeps 8-16 cells per tile resident), missing data."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(104, 2000, 5, 20, 25, cell=4000.0, miss=0.1)
+    args = [('IDW', None, 'IDW_%03d' % i, float(e)) for i, e in enumerate((1, 2, 3, 5))]
+    kw = dict(interp_args=args, intrp_dtype=np.float64, **p)
+    exp, _ = orc.interp_chunk(faithful=False, **kw)
+    got, _ = ChunkEngine().interp_chunk(**kw)
+    _check(got, exp, 'n2000_idw_x4')
+
+
+@pytest.mark.parametrize('min_vg_val', [0.15, 0.6])
+def test_min_vg_val_through_the_local_estimator(min_vg_val):
+    """min_vg_val > 0 (cyth/interpmthds.pyx:203-216: variogram values <= min_vg_val become 0,
+    in A and in the right-hand sides) through the local estimator, the dense contraction and
+    the oracle."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(106, 90, 8, 33, 37, cell=2500.0, miss=0.15)
+    kw = dict(interp_args=[('OK', None, 'OK')], vgs=[VG_C1] * 8, min_vg_val=min_vg_val,
+              intrp_dtype=np.float64, **p)
+    exp, _ = orc.interp_chunk(faithful=False, **kw)
+    e1 = ChunkEngine()
+    got, _ = e1.interp_chunk(**kw)
+    assert e1.stats.get('local_rows', 0) > 0
+    e2 = ChunkEngine()
+    e2.local_support = False
+    ref, _ = e2.interp_chunk(**kw)
+    _check(got, exp, 'min_vg_val_%s_local' % min_vg_val)
+    _check(ref, exp, 'min_vg_val_%s_dense' % min_vg_val)
+
+
+@pytest.mark.parametrize('mthd,n_nebs,n_pies', [('nrst', 9, None), ('pie', 12, 4)])
+def test_est_vars_ok_with_nrst_and_pie(mthd, n_nebs, n_pies):
+    """EST_VARS_OK with per-cell neighbour selection (the reference computes it for any
+    neighbour method, interp/steps.py:428-434): sum(lambda * rhs) + lambda[n] from the
+    inverse of each cell group's system; 0 where NNB / the neighbour mean was written."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(35, 50, 6, 18, 22, cell=4000.0, miss=0.15)
+    p['data'][2, :] = np.where(np.isnan(p['data'][2, :]), np.nan, 0.02)
+    p['data'][4, 1:] = np.nan                                   # single-station step
+    args = [('OK', None, 'OK'), ('EST_VARS_OK', None, 'EST_VARS_OK')]
+    kw = dict(interp_args=args, vgs=[VG_C1] * 6, neb_sel_mthd=mthd, n_nebs=n_nebs, n_pies=n_pies,
+              min_var_thr=0.1, est_var_flag=True, **p)
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    got, _ = ChunkEngine().interp_chunk(intrp_dtype=np.float64, **kw)
+    _check(got, exp, 'est_vars_' + mthd)
+    assert np.nanmax(exp['EST_VARS_OK']) > 0.1 and (exp['EST_VARS_OK'] == 0).any()
+
+
+def test_nrst_with_100_neighbours():
+    """More than 64 neighbours per cell (the reference has no cap, interp/grps.py:147-166):
+    the 160-neighbour kernel variants, index rows bit-exact, OK / IDW fields vs the oracle."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(36, 260, 4, 12, 15, cell=5000.0, miss=0.1)
+    e = ChunkEngine()
+    _assert_same_neighbours(e, 'nrst', 100, None, p['stn_xs'], p['stn_ys'], p['cell_xs'],
+                            p['cell_ys'])
+    _assert_same_neighbours(e, 'pie', 100, 70, p['stn_xs'], p['stn_ys'], p['cell_xs'],
+                            p['cell_ys'])
+    kw = dict(interp_args=[('OK', None, 'OK'), ('IDW', None, 'IDW_000', 2.0)], vgs=[VG_C1] * 4,
+              neb_sel_mthd='nrst', n_nebs=100, **p)
+    exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
+    got, _ = e.interp_chunk(intrp_dtype=np.float64, **kw)
+    _check(got, exp, 'nrst_100')
