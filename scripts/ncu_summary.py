@@ -19,6 +19,10 @@ WANT = [
     'sm__warps_active.avg.pct_of_peak_sustained_active',
     'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+    'SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg',
+    'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+    'TPC.TriageCompute.sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
     'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
     'l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum',
     'lts__t_sectors_srcunit_tex_op_write.sum',

@@ -864,9 +864,6 @@ class ChunkEngine:
                            drft_arrs=drft_arrs if itype == 'EDK' else None,
                            stns_drft=stns_drft if itype == 'EDK' else None,
                            ev_out=flds['EST_VARS_OK'] if (ev_flag and itype == 'OK') else None)
-                if ev_flag and itype == 'OK' and single_steps.size:
-                    self._fill_rows(ctx, flds['EST_VARS_OK'], single_steps,
-                                    np.zeros(single_steps.size), clamp=False)
             elif itype in ('OK', 'SK', 'EDK'):
                 uniq_vgs = list(dict.fromkeys(vgs))
                 vg_id = {v: k for k, v in enumerate(uniq_vgs)}
