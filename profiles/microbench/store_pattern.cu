@@ -82,6 +82,23 @@ __global__ void __launch_bounds__(256) k_store_bulk_w(float* out, int64_t ld, in
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// persistent, row-synchronous: CPS blocks per SM; block b owns tiles b, b + P, ... and walks
+// the rows RG at a time (rows outer, tiles inner): the stores in flight across the GPU stay
+// within a few rows
+template <int RG>
+__global__ void __launch_bounds__(256) k_store_persist(float* out, int64_t ld, int rows, int64_t cells, float v) {
+    const int n_tiles = (int)((cells + 255) / 256);
+    for (int g = 0; g < rows; g += RG) {
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int64_t c = (int64_t)t * 256 + threadIdx.x;
+            if (c >= cells) continue;
+#pragma unroll
+            for (int u = 0; u < RG; ++u)
+                if (g + u < rows) __stcs(out + (int64_t)(g + u) * ld + c, v + g + u);
+        }
+    }
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -118,6 +135,8 @@ int main() {
     RUNW(128, 256, 8) RUNW(128, 256, 16) RUNW(128, 256, 32) RUNW(128, 512, 8) RUNW(128, 512, 16)
     RUNW(64, 256, 16) RUNW(256, 256, 16) RUNW(1250, 256, 16) RUNW(128, 1024, 8)
     RUN(1, 16) RUN(1, 8)
+#define RUNP(RG, CPS) rep("k_store_persist RG=" #RG " blocks/SM=" #CPS, time_ms([&] { k_store_persist<RG><<<148 * CPS, 256>>>(out, ld, rows, cells, 1.f); }));
+    RUNP(8, 3) RUNP(8, 5) RUNP(8, 8) RUNP(4, 8) RUNP(16, 4) RUNP(2, 8)
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return 0;

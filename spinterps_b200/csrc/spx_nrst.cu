@@ -1411,6 +1411,7 @@ __global__ void __launch_bounds__(256, 4) k_estimate_local_fast(LocalEstArgs a) 
 #undef SPX_LOCAL_ROWS_CALL
 }
 
+
 }  // namespace spx
 
 extern "C" int spx_local_build_dev(const spx_local* l, void* stream) {
