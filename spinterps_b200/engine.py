@@ -1040,9 +1040,16 @@ class ChunkEngine:
             plan.append((R, tot))
         return plan
 
-    def _local_neighbours(self, ctx, K, vg_s, plan_entry):
+    def _local_neighbours(self, ctx, K, vg_s, plan_entry, transient=None):
         """Stations within the range of every cell and their (vg - F) values;
-        depends on the geometry and the variogram only -> cached across chunks."""
+        depends on the geometry and the variogram only -> cached across chunks.
+
+        transient (a dict shared by the variograms of ONE call, see _estimate): a chunk
+        with more variograms than the cache holds (per-step variogram series) builds the
+        tables of each variogram into the same buffers, one after the other on the stream,
+        with uploads from the chunk arena, a capacity fixed once from the largest range
+        (stations within R are a subset of those within R_max) and no host synchronisation
+        per variogram."""
         R, tot = plan_entry
         covar = int(K.kind == 1)
         mv = ctx['min_vg_val']
@@ -1064,13 +1071,26 @@ class ChunkEngine:
              + np.floor((sx - x0) / R).astype(np.int64))
         order = np.argsort(b, kind='stable').astype(np.int32)
         bin_start = np.searchsorted(b[order], np.arange(nbx * nby + 1)).astype(np.int32)
-        d_bs, d_bo = self._dev_keep(bin_start), self._dev_keep(order)   # cached with the tables
         n_cells = ctx['n_cells']
-        cap = 8
-        while True:
-            cnt = torch.empty(n_cells, dtype=_I32, device=self.device)
-            idx = torch.empty((cap, n_cells), dtype=_I32, device=self.device)
-            val = torch.empty((cap, n_cells), dtype=_F64, device=self.device)
+        if transient is not None and transient.get('cap'):
+            d_bs, d_bo = self._dev(bin_start), self._dev(order)     # chunk arena
+        else:
+            d_bs, d_bo = self._dev_keep(bin_start), self._dev_keep(order)   # cached with the tables
+        tiles = ctx['n_stn'] <= 65536 and self.local_tiles
+        n_tiles = (n_cells + _lib.SPX_LOCAL_TILE - 1) // _lib.SPX_LOCAL_TILE
+
+        def buffers(cap):
+            out = dict(cnt=torch.empty(n_cells, dtype=_I32, device=self.device),
+                       idx=torch.empty((cap, n_cells), dtype=_I32, device=self.device),
+                       val=torch.empty((cap, n_cells), dtype=_F64, device=self.device))
+            if tiles:
+                out.update(tile_cnt=torch.empty(n_tiles, dtype=_I32, device=self.device),
+                           tile_stn=torch.empty((n_tiles, _lib.SPX_LOCAL_TILE_CAP), dtype=_I32,
+                                                device=self.device),
+                           slot=torch.empty((cap, n_cells), dtype=torch.uint8, device=self.device))
+            return out
+
+        def struct_for(buf, cap):
             L = _lib.spx_local()
             L.stn_x, L.stn_y = ctx['d_stn_x'].data_ptr(), ctx['d_stn_y'].data_ptr()
             L.bin_start, L.bin_stn = d_bs.data_ptr(), d_bo.data_ptr()
@@ -1079,38 +1099,48 @@ class ChunkEngine:
             L.cell_x, L.cell_y = ctx['d_cell_x'].data_ptr(), ctx['d_cell_y'].data_ptr()
             L.n_cells = n_cells
             L.cap = cap
-            L.cnt, L.idx, L.val = cnt.data_ptr(), idx.data_ptr(), val.data_ptr()
+            L.cnt, L.idx, L.val = buf['cnt'].data_ptr(), buf['idx'].data_ptr(), buf['val'].data_ptr()
             L.vg = _lib.make_vg(vg_s)
             L.covar_flag = covar
             L.min_vg_val = mv
+            return L
+
+        if transient is not None and transient.get('cap'):
+            cap, buf = transient['cap'], transient['buf']
+            mx = transient['max_near']
+            L = struct_for(buf, cap)
             _lib.check(self.lib.spx_local_build_dev(C.byref(L), self._stream()), 'local_build')
             self._count('launches')
-            mx = int(cnt.max().item())
-            if mx <= cap:
-                break
-            cap = mx
+        else:
+            cap = 8
+            while True:
+                buf = buffers(cap)
+                L = struct_for(buf, cap)
+                _lib.check(self.lib.spx_local_build_dev(C.byref(L), self._stream()), 'local_build')
+                self._count('launches')
+                mx = int(buf['cnt'].max().item())
+                if mx <= cap:
+                    break
+                cap = mx
         # every tensor whose address sits in the cached struct stays referenced with it
-        keep = [cnt, idx, val, d_bs, d_bo, ctx['d_stn_x'], ctx['d_stn_y'], ctx['d_cell_x'],
-                ctx['d_cell_y']]
-        if ctx['n_stn'] <= 65536 and self.local_tiles:
+        keep = [buf, d_bs, d_bo, ctx['d_stn_x'], ctx['d_stn_y'], ctx['d_cell_x'], ctx['d_cell_y']]
+        if tiles:
             # distinct near stations per tile of 256 cells: the streamlined kernel stages
             # their coefficient slices in shared memory
-            n_tiles = (n_cells + _lib.SPX_LOCAL_TILE - 1) // _lib.SPX_LOCAL_TILE
-            tile_cnt = torch.empty(n_tiles, dtype=_I32, device=self.device)
-            tile_stn = torch.empty((n_tiles, _lib.SPX_LOCAL_TILE_CAP), dtype=_I32,
-                                   device=self.device)
-            slot = torch.empty((cap, n_cells), dtype=torch.uint8, device=self.device)
             L.n_stn = ctx['n_stn']
-            L.tile_cnt, L.tile_stn, L.slot = (tile_cnt.data_ptr(), tile_stn.data_ptr(),
-                                              slot.data_ptr())
+            L.tile_cnt, L.tile_stn, L.slot = (buf['tile_cnt'].data_ptr(), buf['tile_stn'].data_ptr(),
+                                              buf['slot'].data_ptr())
             _lib.check(self.lib.spx_local_tiles_dev(C.byref(L), self._stream()), 'local_tiles')
             self._count('launches')
-            keep += [tile_cnt, tile_stn, slot]
         res = dict(struct=L, F=F, cap=cap, keep=tuple(keep), max_near=mx)
+        self.stats['local_max_near'] = mx
+        if transient is not None:
+            if not transient.get('cap'):         # the R_max build of the call: sizes the rest
+                transient.update(cap=cap, buf=buf, max_near=mx)
+            return res
         while len(self._local_cache) >= 4:
             self._local_cache.pop(next(iter(self._local_cache)))
         self._local_cache[key] = res
-        self.stats['local_max_near'] = mx
         return res
 
     # ---- 'nrst' neighbour selection ---------------------------------------
@@ -1966,9 +1996,18 @@ class ChunkEngine:
         n_stn, n_cells = ctx['n_stn'], ctx['n_cells']
         if K.local is not None:
             coef2d = K.coef.view(-1, kpad)
+            # more variograms than the table cache holds (per-step variogram series): the
+            # tables are built per variogram into shared buffers sized by the largest range
+            transient = None
+            if seg_vgs.size > 4:
+                transient = {}
+                k_max = int(np.argmax([pl[0] for pl in K.local]))
+                self._local_neighbours(ctx, K, K.uniq_vgs[int(seg_vgs[k_max])], K.local[k_max],
+                                       transient=transient)
             for k in range(seg_vgs.size):
                 r0, r1 = int(seg_first[k]), int(seg_first[k] + seg_cnt[k])
-                nbr = self._local_neighbours(ctx, K, K.uniq_vgs[int(seg_vgs[k])], K.local[k])
+                nbr = self._local_neighbours(ctx, K, K.uniq_vgs[int(seg_vgs[k])], K.local[k],
+                                             transient=transient)
                 pre = fused[k] if fused is not None else None
                 if pre is not None and pre.get('base') is not None:
                     base = pre['base']             # written by the downdate kernel

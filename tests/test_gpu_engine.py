@@ -683,3 +683,30 @@ def test_nrst_with_100_neighbours():
     exp, _ = orc.interp_chunk(intrp_dtype=np.float64, faithful=False, **kw)
     got, _ = e.interp_chunk(intrp_dtype=np.float64, **kw)
     _check(got, exp, 'nrst_100')
+
+
+def test_per_step_compact_variograms_share_transient_tables():
+    """Config-3 style: one compact variogram PER STEP (more than the table cache holds): the
+    neighbour tables of every variogram are built into shared buffers sized once from the
+    largest range; EDK with a drift and OK against the oracle, and against the dense path."""
+    from spinterps_b200.engine import ChunkEngine
+    T = 14
+    p = make_problem(107, 80, T, 30, 34, cell=3000.0, miss=0.1)
+    rng = np.random.default_rng(108)
+    vgs = ['%0.5f Nug(0.0) + %0.5f Sph(%0.5f)' % (rng.uniform(0, 0.2), rng.uniform(0.5, 1.5),
+                                                    rng.uniform(8e3, 2.5e4)) for _ in range(T)]
+    cx, cy = p['cell_xs'], p['cell_ys']
+    drft = np.vstack([300 + 0.002 * cx + 0.001 * cy])
+    sdrft = np.column_stack([300 + 0.002 * p['stn_xs'] + 0.001 * p['stn_ys']])
+    kw = dict(interp_args=[('EDK', None, 'EDK'), ('OK', None, 'OK')], vgs=vgs, drft_arrs=drft,
+              stns_drft=sdrft, intrp_dtype=np.float64, **p)
+    exp, _ = orc.interp_chunk(faithful=False, **kw)
+    e1 = ChunkEngine()
+    got, _ = e1.interp_chunk(**kw)
+    assert e1.stats.get('local_rows', 0) == 2 * T        # every step through the local estimator
+    _check(got, exp, 'per_step_compact_vgs')
+    e2 = ChunkEngine()
+    e2.local_support = False
+    ref, _ = e2.interp_chunk(**kw)
+    for lab in ref:
+        assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
