@@ -101,6 +101,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // (dist / scale) ** -p from the squared distance; small integer exponents avoid
 // pow().  Reference: w = 1 / d**p on max-normalised distances
 // (interp/steps.py:297-303, pyx:792); the common scale cancels in the ratio.
+// element (row, col) of the packed coefficient matrix (spx_coef_offset of the header)
+__device__ __forceinline__ int64_t gemm_coef_offset(int64_t row, int64_t col, int64_t kpad) {
+    const int64_t mt = row / SPX_BM, r = row % SPX_BM;
+    return (mt * (kpad / 4) + col / 4) * (SPX_BM * 4) + (r / 8) * 32 + (r % 8) * 4 + (col % 4);
+}
+
 __device__ __forceinline__ double idw_weight(double d2, double inv_scale, double p) {
     const double q2 = d2 * inv_scale * inv_scale;  // (d/scale)^2
     if (p == 2.0) return 1.0 / q2;
@@ -133,6 +139,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
     double* qs = cy + BN;                                              // [BN] quadratic forms
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(qs + BN);         // [n_stages]
     uint64_t* empty_bar = full_bar + n_stages;                         // [n_stages]
+    // IDW: station that coincides with the cell centre (distance 0), -1 = none
+    int* zk = reinterpret_cast<int*>(empty_bar + n_stages);            // [BN]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
             const int64_t c = cell0 + tid;
             cx[tid] = (c < a.n_cells) ? a.cell_x[c] : 0.0;
             cy[tid] = (c < a.n_cells) ? a.cell_y[c] : 0.0;
+            zk[tid] = -1;
         }
         __syncthreads();
         const int n_ent = KC * NT * 32;
@@ -193,7 +202,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                                            : vg_eval(a.vg, h, a.covar_flag, a.min_vg_val);
                     } else {
                         const double dx = cx[n] - sx[k], dy = cy[n] - sy[k];
-                        v = idw_weight(dx * dx + dy * dy, a.inv_scale, a.idw_exp);
+                        const double d2 = dx * dx + dy * dy;
+                        if (d2 == 0.0) {
+                            // a station exactly on the cell centre: weight inf.  The reference
+                            // (steps.py:293-313) gives NaN where that station is available and
+                            // simply leaves it out where it is missing; 0 * inf would turn the
+                            // latter into NaN too.  Its weight is dropped here, the
+                            // sum-of-weights epilogue (SPX_EPI_AUX) restores the NaN for the
+                            // groups that have the station.
+                            v = 0.0;
+                            zk[n] = k;
+                        } else {
+                            v = idw_weight(d2, a.inv_scale, a.idw_exp);
+                        }
                     }
                 } else if (k < a.n_stn + a.n_border) {
                     const int b = k - a.n_stn;
@@ -302,6 +323,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                         if (c >= a.n_cells) continue;
                         const bool has2 = (c + 1 < a.n_cells);
                         double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                        if (a.epi == SPX_EPI_AUX && a.gen == SPX_GEN_IDW) {
+                            // rows are availability masks (1 / 0): the coincident station is
+                            // part of this group -> sum of weights inf -> estimate NaN
+                            const int64_t R = row_base + i * 8 + g;
+                            const int n0 = j * 8 + t4 * 2;
+                            if (zk[n0] >= 0 && a.coef[gemm_coef_offset(R, zk[n0], a.kpad)] != 0.0)
+                                v0 = CUDART_NAN;
+                            if (zk[n0 + 1] >= 0 && a.coef[gemm_coef_offset(R, zk[n0 + 1], a.kpad)] != 0.0)
+                                v1 = CUDART_NAN;
+                        }
                         if (a.epi == SPX_EPI_AUX) {
                             double* dstp = a.aux + (int64_t)dst * a.n_cells + c;
                             if (has2 && ((a.n_cells & 1) == 0)) {
@@ -376,7 +407,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
 static size_t gemm_smem_bytes(int kpad, int nt, int n_stages) {
     const size_t dbl = (size_t)(kpad / 4) * nt * 32 + (size_t)n_stages * STAGE_DOUBLES +
                        2 * (size_t)kpad + 3 * (size_t)nt * 8;
-    return dbl * 8 + 2 * (size_t)n_stages * 8;
+    return dbl * 8 + 2 * (size_t)n_stages * 8 + (size_t)nt * 8 * sizeof(int);
 }
 
 struct GemmCfg {

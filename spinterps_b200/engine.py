@@ -1143,6 +1143,35 @@ class ChunkEngine:
         self._local_cache[key] = res
         return res
 
+    def _local_aux(self, ctx, K, vg_s, plan_entry, coef, n_rows, d_slots, aux):
+        """aux[d_slots[r], cell] = sum_k coef[r, k] * vg(dist(k, cell)) for ROW-MAJOR coef rows
+        through the local estimator (f64, no clamp): the per-cell sum(lambda) of
+        steps.py:418 for systems whose variogram is compactly supported."""
+        nbr = self._local_neighbours(ctx, K, vg_s, plan_entry)
+        coef2d = coef.view(-1, K.kpad)
+        base = nbr['F'] * coef2d[:n_rows, :ctx['n_stn']].sum(dim=1)
+        if K.n_border >= 1:
+            base = base + coef2d[:n_rows, ctx['n_stn']]
+        base = base.contiguous()
+        L = nbr['struct']
+        L.coef = coef2d.data_ptr()
+        L.base = base.data_ptr()
+        L.n_rows = int(n_rows)
+        L.kpad, L.n_stn, L.n_drifts = K.kpad, ctx['n_stn'], 0
+        L.cell_drift = None
+        L.row_dst = d_slots.data_ptr()
+        L.out = aux.data_ptr()
+        L.out_ld = ctx['n_cells']
+        L.out_f64 = 1
+        L.cell_pos = None
+        L.has_lo = L.has_hi = 0
+        L.lo = L.hi = 0.0
+        L.rows_all_valid = 1
+        L.coef_t, L.coef_t_ld = None, 0
+        _lib.check(self.lib.spx_estimate_local_dev(C.byref(L), self._stream()), 'estimate_local')
+        self._count('launches')
+        self._count('local_aux_rows', int(n_rows))
+
     # ---- 'nrst' neighbour selection ---------------------------------------
     def _topk(self, d_sx, d_sy, n_stn, d_mask, d_cx, d_cy, n_cells, k):
         nb = torch.empty((n_cells, k), dtype=_I32, device=self.device)
@@ -2095,7 +2124,7 @@ class ChunkEngine:
 
 
     # ---- pseudo-inverse path for numerically singular systems ---------------
-    def _pinv_systems(self, ctx, out, K, sids, sv, v, coef_a):
+    def _pinv_systems(self, ctx, out, K, sids, sv, v, coef_a, row_major=False):
         """np.linalg.pinv semantics (rcond = 1e-15) through a symmetric
         eigendecomposition on the device.  Rewrites the estimates of the steps of
         the listed systems and puts pinv(A) [1; 0] into the rows of ``coef_a`` that
@@ -2151,6 +2180,9 @@ class ChunkEngine:
                        cell_drift=K.d_cell_drift)
         # ones-vector rows into the caller's segment
         for full, st, row in blocks:
+            if row_major:
+                coef_a.view(-1, kpad)[row] = full[-1]
+                continue
             _lib.check(self.lib.spx_pack_rows_dev(
                 self._ptr(full[-1:].contiguous()), kpad, None, 1, kpad, kpad, 0,
                 self._ptr(coef_a), row, self._stream()), 'pack_rows')
@@ -2469,8 +2501,15 @@ class ChunkEngine:
             ok = fb[~singular[fb] | use_pinv[fb]]
             for v in np.unique(K.sys_vg[ok]):
                 sv = ok[K.sys_vg[ok] == v]
-                coef_a = torch.zeros(_pad_up(sv.size, _lib.SPX_BM) * K.kpad, dtype=_F64,
-                                     device=self.device)
+                # compact variogram: the ones-vector rows go through the local estimator
+                # (stations within range + the constant far field) instead of a contraction
+                # that regenerates the whole cells x stations tile for a handful of rows
+                loc = None
+                if (getattr(K, 'local', None) is not None and K.n_drifts == 0
+                        and self.local_support):
+                    loc = self._local_plan(ctx, [K.uniq_vgs[int(v)]])
+                rows_a = int(sv.size) if loc is not None else _pad_up(sv.size, _lib.SPX_BM)
+                coef_a = torch.zeros(rows_a * K.kpad, dtype=_F64, device=self.device)
                 sv_lu = sv[~use_pinv[sv]]
                 sv_pi = sv[use_pinv[sv]]
                 # ones-vector solutions, grouped by the kept factor batch
@@ -2483,10 +2522,15 @@ class ChunkEngine:
                     by_T[id(T)][2].append(row)
                 for T, ks, rows in by_T.values():
                     self._lu_solve(ctx, K, T, ks, np.ones(len(ks)), np.zeros(len(ks)), rows,
-                                   coef_a)
+                                   coef_a, row_major=loc is not None)
                 if sv_pi.size:
-                    self._pinv_systems(ctx, out, K, sv_pi, sv, int(v), coef_a)
+                    self._pinv_systems(ctx, out, K, sv_pi, sv, int(v), coef_a,
+                                       row_major=loc is not None)
                 d_slots = self._dev(np.searchsorted(fb, sv).astype(np.int32))
+                if loc is not None:
+                    self._local_aux(ctx, K, K.uniq_vgs[int(v)], loc[0], coef_a, int(sv.size),
+                                    d_slots, aux)
+                    continue
                 self._gemm(ctx, coef=coef_a, n_rows=int(sv.size), kpad=K.kpad,
                            n_border=K.n_border, gen=_lib.GEN_VG, epi=_lib.EPI_AUX,
                            row_dst=d_slots, aux=aux, vg=_lib.make_vg(K.uniq_vgs[int(v)]),

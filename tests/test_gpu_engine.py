@@ -710,3 +710,24 @@ def test_per_step_compact_variograms_share_transient_tables():
     ref, _ = e2.interp_chunk(**kw)
     for lab in ref:
         assert rel_err(got[lab], ref[lab], _floor(ref[lab])) <= 1e-11, lab
+
+
+def test_idw_station_on_a_cell_centre():
+    """A station exactly on a cell centre has weight inf (quirk Q7): NaN at that cell for the
+    steps where the station is available, and -- because the reference excludes missing
+    stations before it forms the weights (interp/steps.py:293-313) -- a finite value where it
+    is missing (0 * inf must not leak in)."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(109, 30, 8, 12, 14, cell=3000.0, miss=0.0)
+    p['stn_xs'][5], p['stn_ys'][5] = p['cell_xs'][40], p['cell_ys'][40]
+    p['data'][2:5, 5] = np.nan                       # missing for three steps
+    p['data'][6, [1, 7]] = np.nan                    # another availability group
+    args = [('IDW', None, 'IDW_000', 2.0), ('IDW', None, 'IDW_001', 3.0)]
+    kw = dict(interp_args=args, intrp_dtype=np.float64, **p)
+    with np.errstate(all='ignore'):
+        exp, _ = orc.interp_chunk(faithful=False, **kw)
+    got, _ = ChunkEngine().interp_chunk(**kw)
+    for lab in exp:
+        assert np.isnan(exp[lab][[0, 1, 5, 6, 7], 40]).all() and np.isfinite(exp[lab][2:5, 40]).all()
+        assert np.isfinite(exp[lab][:, np.arange(168) != 40]).all()
+    _check(got, exp, 'idw_station_on_cell_centre')
