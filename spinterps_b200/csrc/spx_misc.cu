@@ -349,7 +349,25 @@ __global__ void __launch_bounds__(RS_THREADS) k_round_stats(T* fld, int64_t row_
     if (VEC) {
         constexpr int W = 16 / sizeof(T);
         typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
-        for (int64_t i = beg + (int64_t)threadIdx.x * W; i < end; i += (int64_t)RS_THREADS * W) {
+        constexpr int64_t STEP = (int64_t)RS_THREADS * W;
+        int64_t i = beg + (int64_t)threadIdx.x * W;
+        // four independent 16-byte loads in flight per thread (one was latency-bound)
+        for (; i + 3 * STEP + W <= end; i += 4 * STEP) {
+            V v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<V*>(base + i + q * STEP);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                T* e = reinterpret_cast<T*>(&v[q]);
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    if (do_round) e[u] = round_dec<T>(e[u], pw);
+                    take(e[u]);
+                }
+                if (do_round) *reinterpret_cast<V*>(base + i + q * STEP) = v[q];
+            }
+        }
+        for (; i < end; i += STEP) {
             if (i + W <= end) {
                 V v = *reinterpret_cast<V*>(base + i);
                 T* e = reinterpret_cast<T*>(&v);
@@ -575,7 +593,7 @@ int spx_lambda_check_dev(const double* aux, int64_t n_slots, int64_t n_cells,
 
 static int rs_segments(int64_t n_rows, int64_t row_len) {
     // enough blocks to fill the GPU a few times over, at least 4096 elements each
-    int64_t seg = (148 * 16 + n_rows - 1) / n_rows;
+    int64_t seg = (148 * 64 + n_rows - 1) / n_rows;       // many more blocks than slots: no tail
     const int64_t max_seg = (row_len + 4095) / 4096;
     if (seg > max_seg) seg = max_seg;
     if (seg < 1) seg = 1;

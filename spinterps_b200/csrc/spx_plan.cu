@@ -154,13 +154,23 @@ HostPool& HostPool::get() {
 }
 
 HostPool::HostPool() : impl_(new Impl()) {
-    int n = 4;
-    if (const char* e = getenv("SPX_HOST_THREADS")) n = atoi(e);
-    if (n < 1) n = 1;
-    impl_->default_threads = n;
     cpu_set_t set;
     int hw = 0;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);
+    // default: 4 threads, fewer when several ranks share the host (torchrun exports
+    // LOCAL_WORLD_SIZE): half of this rank's share of the cores
+    int n = 4;
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int w = atoi(lw);
+        if (w > 1 && hw > 0) {
+            int share = hw / w / 2;
+            if (share < 1) share = 1;
+            if (share < n) n = share;
+        }
+    }
+    if (const char* e = getenv("SPX_HOST_THREADS")) n = atoi(e);
+    if (n < 1) n = 1;
+    impl_->default_threads = n;
     int cap = 16;
     if (hw > 0 && cap > hw) cap = hw;
     if (n == 1 && getenv("SPX_HOST_THREADS")) cap = 1;       // SPX_HOST_THREADS=1: no helpers
