@@ -496,17 +496,19 @@ def run_gpu(args):
     n_dec = int(os.environ.get('SPX_DECODE_THREADS', str(max(1, min(16, len(os.sched_getaffinity(0)) // world)))))
     dl = PackedDownloader(torch.device('cuda', local_rank), CHUNK_STEPS, NY * NX, depth=2,
                           n_threads=n_dec)
+    dls = {'default': dl}
     host_out = [np.empty((CHUNK_STEPS, NY * NX), dtype=np.float32) for _ in range(2)]
     decoder = concurrent.futures.ThreadPoolExecutor(
         max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
     kw_e2e = dict(kw, round_decimals=NMRL_PRCN, field_stats=True)
     raw_rows = [0]
 
-    def run_e2e(n, decode=False):
-        """Pipeline: submit chunk i+1 | output stage + pack + D2H of chunk i.  At the end
-        of a step its result sits in (pinned) host memory in the lossless 2-byte form the
-        writer consumes (transfer.PackedField); decode=True additionally rebuilds the
-        whole f32 field in host memory (16 host threads, one chunk behind)."""
+    def run_e2e(n, decode=False, which='default'):
+        """Pipeline: submit chunk i+1 | output stage + encode + D2H of chunk i.  At the end
+        of a step its result sits in (pinned) host memory in the lossless compact form the
+        writer consumes (transfer.DeltaField / PackedField); decode=True additionally
+        rebuilds the whole f32 field in host memory (host threads, one chunk behind)."""
+        dl = dls[which]
         futs = [None, None]
 
         def finish(ticket, k):
@@ -515,7 +517,7 @@ def run_gpu(args):
         def land(ticket):
             pf = dl.wait(ticket)
             raw_rows[0] += len(pf.raw)
-            checks.append(int(pf.codes[0, 0]))
+            checks.append(int(pf.nbytes))
             dl.release(ticket)
 
         def drain(pend, k):
@@ -655,8 +657,17 @@ def run_gpu(args):
     n_dcd = max(2, min(args.steps, 5))
     run_e2e(2, decode=True)
     ms_e2e_dec, _ = timed(lambda n: run_e2e(n, decode=True), n_dcd)
+    # the same pipeline with the 16-bit codes of the earlier transport
+    n_u16 = max(2, min(args.steps, 4))
+    ms_e2e_u16 = None
+    if dl.codec != 'u16':
+        dls['u16'] = PackedDownloader(torch.device('cuda', local_rank), CHUNK_STEPS, NY * NX,
+                                      depth=2, n_threads=n_dec, codec='u16')
+        run_e2e(2, which='u16')
+        ms_e2e_u16, _ = timed(lambda n: run_e2e(n, which='u16'), n_u16)
+        del dls['u16']
     # the same pipeline with the round-1 transport (f32 field into pinned memory)
-    n_raw = max(2, min(args.steps, 5))
+    n_raw = max(2, min(args.steps, 4))
     run_e2e_raw(2)
     ms_e2e_raw, _ = timed(run_e2e_raw, n_raw)
     pin_out.clear()
@@ -763,10 +774,19 @@ def run_gpu(args):
                     'ms_per_step': ms_e2e / args.steps,
                     'transport': 'output stage of the writer on the device (np.round to %d '
                                  'decimals, per-step statistics); the rounded f32 field crosses '
-                                 'PCIe in its lossless 2-byte form (16-bit codes per row, '
-                                 'verified bit-exact on the device) and lands in pinned host '
-                                 'memory as transfer.PackedField, which the writer decodes one '
-                                 'step at a time' % NMRL_PRCN,
+                                 'PCIe in a lossless compact form (codec %r: deltas of the '
+                                 'integer lattice along each row, bit-packed per 8 cells, every '
+                                 'value verified bit-exact on the device; size depends on the '
+                                 'field, see d2h_bytes_per_cell_step) and lands in pinned host '
+                                 'memory as transfer.DeltaField, which the writer decodes one '
+                                 'step at a time' % (NMRL_PRCN, dl.codec),
+                    'd2h_bytes_per_cell_step': d2h_e2e_bytes / max(args.steps, 1) / cell_steps,
+                    'fields_sent_through_fallback_codec': int(dl.fallbacks),
+                    'u16_transport': None if ms_e2e_u16 is None else {
+                        'value': world * cell_steps * n_u16 / (ms_e2e_u16 / 1e3),
+                        'ms_per_step': ms_e2e_u16 / n_u16,
+                        'd2h_bytes_per_step': int(CHUNK_STEPS * (16 + 2 * dl.stride)),
+                        'note': 'same pipeline, 16-bit codes per row (2 bytes per cell-step)'},
                     'decoded_f32': {
                         'value': world * cell_steps * n_dcd / (ms_e2e_dec / 1e3),
                         'ms_per_step': ms_e2e_dec / n_dcd, 'decode_threads': n_dec,

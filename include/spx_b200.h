@@ -757,6 +757,36 @@ int spx_unpack_field_host(const spx_pack_row* hdr, const uint16_t* codes, int64_
                           int64_t row_len, int32_t decimals, float* out, int64_t out_ld,
                           int32_t n_threads);
 
+/* ---- lossless delta transport of rounded f32 fields (variable rate) ------------------
+ * Same integer lattice as above, but neighbouring cells of an interpolated field differ by
+ * few lattice steps: every row is cut into tiles of SPX_DPACK_TILE cells, the chain of q
+ * along a tile is delta + zigzag coded and bit-packed per group of 8 cells with the
+ * group's own width (0..12, 14, 16 or 32 bits); NaN and -0.0 cells sit in per-tile bitmaps,
+ * a tile with a value that fails the bit-exact round-trip check is stored as raw floats.
+ * Each tile is one variable-size record in `payload`, tile_off[row * tiles + tile] is its
+ * offset in units of 4 bytes (record layout: csrc/spx_pack.cu).  Typical interpolated
+ * fields need 0.3-0.6 bytes per cell instead of 4 (interp/steps.py:907-945 writes the
+ * identical floats after the host decode). */
+#define SPX_DPACK_TILE 256
+/* Tiles per row; worst-case payload bytes of a field (every tile raw). */
+int64_t spx_dpack_tiles(int64_t row_len);
+int64_t spx_dpack_capacity(int64_t n_rows, int64_t row_len);
+/* fld: device f32 [n_rows, row_len] pitch ld, already rounded to `decimals` (0..9) places;
+ * tile_off: device uint32 [n_rows * spx_dpack_tiles(row_len)]; payload: device buffer of
+ * capacity_bytes (any size: records that do not fit are not written, their tile_off is
+ * 0xFFFFFFFF); counters: device uint64[2], written by the call: [0] = 4-byte words the
+ * records need in total (may exceed the capacity), [1] = 1 if a record did not fit.
+ * The order of the records in the payload is not deterministic; the decoded field is. */
+int spx_dpack_field_dev(const float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
+                        int32_t decimals, uint32_t* tile_off, void* payload,
+                        int64_t capacity_bytes, uint64_t* counters, void* stream);
+/* HOST pointers.  Decodes n_rows rows (tile_off points at the first of them) into out
+ * [n_rows, row_len] pitch out_ld; payload_bytes bounds every access.  n_threads <= 0:
+ * default, 1: on the calling thread (safe to call from several threads at once). */
+int spx_dunpack_rows_host(const uint32_t* tile_off, const void* payload, int64_t payload_bytes,
+                          int64_t n_rows, int64_t row_len, int32_t decimals, float* out,
+                          int64_t out_ld, int32_t n_threads);
+
 /* Copy a small device buffer into pinned (UVA-mapped) host memory with a kernel
  * instead of a DMA engine, so that the copy cannot queue behind a large field
  * download in flight; n_bytes and both pointers multiples of 4. */

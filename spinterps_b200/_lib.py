@@ -307,6 +307,12 @@ _SIGS = {
                                         C.c_void_p, C.c_int64, C.c_int32]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    'spx_dpack_tiles': (C.c_int64, [C.c_int64]),
+    'spx_dpack_capacity': (C.c_int64, [C.c_int64, C.c_int64]),
+    'spx_dpack_field_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'spx_dunpack_rows_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int32, C.c_void_p, C.c_int64, C.c_int32]),
 }
 
 EXPORTED = tuple(_SIGS)

@@ -1,0 +1,75 @@
+"""Delta transport (csrc/spx_pack.cu "dpack"): the C host decoder against the plain-Python
+statement of the format (tests/dpack_ref.py).  CPU only; the CUDA encoder is checked
+against the same decoder in tests/test_gpu_main.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from spinterps_b200 import _lib
+from tests import dpack_ref
+
+
+def c_decode(offs, payload, n_rows, row_len, decimals, n_threads=1, row0=0):
+    lib = _lib.load()
+    tiles = lib.spx_dpack_tiles(row_len)
+    out = np.full((n_rows, row_len + 3), 7.0, dtype=np.float32)
+    o = offs[row0 * tiles:]
+    _lib.check(lib.spx_dunpack_rows_host(
+        o.ctypes.data, payload.ctypes.data, payload.nbytes, n_rows, row_len, decimals,
+        out.ctypes.data, out.strides[0] // 4, n_threads), 'dunpack')
+    assert np.all(out[:, row_len:] == 7.0)
+    return out[:, :row_len]
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32),
+                          np.ascontiguousarray(b).view(np.uint32))
+
+
+@pytest.mark.parametrize('row_len', [1, 7, 256, 300, 1000])
+@pytest.mark.parametrize('decimals', [0, 2, 3])
+def test_decoder_matches_format(row_len, decimals):
+    rng = np.random.default_rng(row_len * 10 + decimals)
+    fld = dpack_ref.synth_field(rng, 5, row_len, decimals)
+    fld[1, ::5][~np.isnan(fld[1, ::5])] = -0.0
+    if row_len >= 300:
+        fld[2, 10] = np.float32(1.23456789)       # off the lattice: raw tile
+        fld[2, 290] = np.inf
+        fld[3, :] = np.float32(12.5) if decimals else np.float32(12.0)   # constant tiles
+        fld[4, 260:] = rng.normal(0, 1e6, row_len - 260).astype(np.float32).round(decimals)
+    offs, payload = dpack_ref.encode(fld, decimals)
+    # NaN payload bits are canonical (0x7FC00000) in both decoders; compare through isnan
+    want = fld.copy()
+    want[np.isnan(want)] = np.float32(np.nan)
+    got_py = dpack_ref.decode(offs, payload, *fld.shape, decimals)
+    got_c = c_decode(offs, payload, *fld.shape, decimals)
+    for got in (got_py, got_c):
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        fin = ~np.isnan(want)
+        assert same_bits(got[fin], want[fin])
+    # threaded decode and a row offset
+    got_t = c_decode(offs, payload, 3, row_len, decimals, n_threads=3, row0=2)
+    fin = ~np.isnan(want[2:])
+    assert same_bits(got_t[fin], want[2:][fin])
+
+
+def test_rate_on_a_smooth_field():
+    rng = np.random.default_rng(0)
+    fld = dpack_ref.synth_field(rng, 4, 2048, 2, nan_frac=0.0)
+    offs, payload = dpack_ref.encode(fld, 2)
+    assert payload.nbytes + offs.nbytes < 1.0 * fld.size          # < 1 byte per cell
+
+
+def test_decoder_rejects_bad_offsets():
+    rng = np.random.default_rng(1)
+    fld = dpack_ref.synth_field(rng, 2, 600, 2)
+    offs, payload = dpack_ref.encode(fld, 2)
+    lib = _lib.load()
+    out = np.empty_like(fld)
+    bad = offs.copy()
+    bad[1] = 0xFFFFFFFF
+    assert lib.spx_dunpack_rows_host(bad.ctypes.data, payload.ctypes.data, payload.nbytes, 2, 600, 2,
+                                     out.ctypes.data, 600, 1) != 0
+    assert lib.spx_dunpack_rows_host(offs.ctypes.data, payload.ctypes.data, 8, 2, 600, 2,
+                                     out.ctypes.data, 600, 1) != 0

@@ -141,12 +141,14 @@ def test_round_stats_kernel(dtype):
         assert np.all(np.abs(st[ok] - exp[ok]) <= 1e-11 * np.maximum(1.0, np.abs(exp[ok])))
 
 
+@pytest.mark.parametrize('codec', ['delta', 'u16'])
 @pytest.mark.parametrize('decimals,scale,special', [(2, 5.0, 'nan'), (1, 30.0, 'none'),
                                                     (3, 2.0, 'wide'), (0, 100.0, 'inf'),
                                                     (2, 5.0, 'unrounded')])
-def test_packed_download_is_bit_exact(decimals, scale, special):
-    """The 2-byte transport of rounded f32 fields (spx_pack_field_dev -> PCIe ->
-    spx_unpack_field_host) returns exactly the bytes of the rounded field: NaN rows and
+def test_packed_download_is_bit_exact(decimals, scale, special, codec):
+    """The compact transports of rounded f32 fields (delta: spx_dpack_field_dev -> PCIe ->
+    spx_dunpack_rows_host; u16: spx_pack_field_dev -> spx_unpack_field_host) return exactly
+    the bytes of the rounded field: NaN rows and
     cells, negative values, rows whose range exceeds 16 bits, infinities, a field that was
     never rounded (every row falls back to raw floats), ragged row length."""
     import torch
@@ -173,13 +175,20 @@ def test_packed_download_is_bit_exact(decimals, scale, special):
     else:
         exp = f
     assert np.array_equal(d.cpu().numpy(), exp, equal_nan=True)
-    dl = PackedDownloader(eng.device, T, G)
+    dl = PackedDownloader(eng.device, T, G, codec=codec)
     out = np.full((T, G), -7.0, dtype=np.float32)
     n_raw = dl.finish(dl.start(d, decimals), out)
     assert np.array_equal(out.view(np.uint32)[~np.isnan(exp)],
                           exp.view(np.uint32)[~np.isnan(exp)])       # incl. the sign of zero
     assert (np.signbit(exp) & (exp == 0)).any() or special != 'nan'   # -0.0 is exercised
     assert np.array_equal(np.isnan(out), np.isnan(exp))
+    if codec == 'delta':
+        # raw TILES instead of raw rows; a noise-like field (gamma noise, cell by cell) does
+        # not fit 1.25 bytes per cell and goes through the 16-bit codec
+        assert dl.d2h_bytes > 0 and dl.fallbacks in (0, 1)
+        if special == 'unrounded':
+            assert dl.fallbacks == 1         # every tile raw: > 4 bytes per cell
+        return
     if special == 'unrounded':
         assert n_raw >= T - 1
     elif special == 'wide':
@@ -190,3 +199,93 @@ def test_packed_download_is_bit_exact(decimals, scale, special):
         assert n_raw == 0
     # and through the public result() of a chunk
     assert dl.d2h_bytes >= T * 2 * G
+
+
+@pytest.mark.parametrize('row_len,pitch', [(1000, 1000), (777, 779), (256, 256), (5, 8)])
+def test_delta_encoder_follows_the_format(row_len, pitch):
+    """spx_dpack_field_dev against the plain-Python statement of the record format
+    (tests/dpack_ref.py): the records decode to the identical floats with the Python decoder
+    AND the C decoder, and they take exactly the bytes the Python encoder needs (NaN cells
+    and tiles, -0.0, off-lattice values -> raw tiles, constant tiles, ragged and unaligned
+    rows); a payload buffer that is too small is reported, never overrun."""
+    import ctypes as C
+    import torch
+    from spinterps_b200 import _lib
+    from tests import dpack_ref
+    lib = _lib.load()
+    rng = np.random.default_rng(row_len)
+    n_rows = 9
+    fld = dpack_ref.synth_field(rng, n_rows, row_len, 2)
+    fld[1, ::5][~np.isnan(fld[1, ::5])] = -0.0
+    fld[3, :] = np.float32(12.5)
+    if row_len >= 300:
+        fld[2, 10] = np.float32(1.23456789)
+        fld[2, 290] = np.inf
+        fld[4, 260:] = rng.normal(0, 1e6, row_len - 260).astype(np.float32).round(2)
+        fld[5, 100:140] = np.float32(3.0e9)           # |q| beyond int32
+    want_off, want_pay = dpack_ref.encode(fld, 2)
+    d = torch.full((n_rows, pitch), 99.0, dtype=torch.float32, device='cuda')
+    d[:, :row_len] = torch.from_numpy(fld).cuda()
+    tiles = int(lib.spx_dpack_tiles(row_len))
+    cap = int(lib.spx_dpack_capacity(n_rows, row_len))
+    offs = torch.zeros(n_rows * tiles, dtype=torch.int32, device='cuda')
+    pay = torch.full((cap + 64,), 0xAB, dtype=torch.uint8, device='cuda')
+    cnt = torch.full((2,), -1, dtype=torch.int64, device='cuda')
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.spx_dpack_field_dev(C.c_void_p(d.data_ptr()), n_rows, row_len, pitch, 2,
+                                       C.c_void_p(offs.data_ptr()), C.c_void_p(pay.data_ptr()),
+                                       cap, C.c_void_p(cnt.data_ptr()), st), 'dpack')
+    torch.cuda.synchronize()
+    h_cnt = cnt.cpu().numpy()
+    assert h_cnt[1] == 0 and h_cnt[0] * 4 == want_pay.nbytes
+    h_off = offs.cpu().numpy().view(np.uint32)
+    h_pay = pay.cpu().numpy()
+    assert np.all(h_pay[h_cnt[0] * 4:] == 0xAB)                  # nothing past the records
+    used = h_pay[:h_cnt[0] * 4].copy()
+    ok = ~np.isnan(fld)
+    got_py = dpack_ref.decode(h_off, used, n_rows, row_len, 2)
+    got_c = np.empty_like(fld)
+    _lib.check(lib.spx_dunpack_rows_host(h_off.ctypes.data, used.ctypes.data, used.nbytes, n_rows,
+                                         row_len, 2, got_c.ctypes.data, row_len, 2), 'dunpack')
+    for got in (got_py, got_c):
+        assert np.array_equal(np.isnan(got), ~ok)
+        assert np.array_equal(got.view(np.uint32)[ok], fld.view(np.uint32)[ok])
+    # record sizes tile by tile (the order in the payload is free)
+    def sizes(o, total):
+        srt = np.sort(o.astype(np.int64))
+        return dict(zip(srt.tolist(), np.diff(np.append(srt, total)).tolist()))
+    sz_g, sz_w = sizes(h_off, h_cnt[0]), sizes(want_off, want_pay.nbytes // 4)
+    assert [sz_g[int(o)] for o in h_off] == [sz_w[int(o)] for o in want_off]
+    # too small a buffer: flagged, the needed size still reported, no write past the end
+    small = (want_pay.nbytes // 2) // 4 * 4
+    pay.fill_(0xAB)
+    _lib.check(lib.spx_dpack_field_dev(C.c_void_p(d.data_ptr()), n_rows, row_len, pitch, 2,
+                                       C.c_void_p(offs.data_ptr()), C.c_void_p(pay.data_ptr()),
+                                       small, C.c_void_p(cnt.data_ptr()), st), 'dpack')
+    torch.cuda.synchronize()
+    h_cnt = cnt.cpu().numpy()
+    assert h_cnt[1] == 1 and h_cnt[0] * 4 == want_pay.nbytes
+    assert np.all(pay.cpu().numpy()[small:] == 0xAB)
+    assert (offs.cpu().numpy().view(np.uint32) == 0xFFFFFFFF).any()
+
+
+def test_delta_download_of_a_smooth_field_is_small():
+    """An interpolated field (the engine's own output) crosses PCIe in well under one byte
+    per cell and comes back bit for bit."""
+    import torch
+    from spinterps_b200.engine import ChunkEngine
+    from spinterps_b200.transfer import PackedDownloader
+    from tests.synth import make_problem
+    p = make_problem(5, 60, 24, 120, 1100, cell=1000.0, miss=0.2)
+    eng = ChunkEngine()
+    pend = eng.submit_chunk(interp_args=[('OK', None, 'OK')], vgs=['0.1 Nug(0.0) + 0.9 Sph(40000)'] * 24,
+                            intrp_dtype=np.float32, round_decimals=2, field_stats=True, **p)
+    flds, _ = pend.result(to_host=False)
+    d = flds['OK']
+    dl = PackedDownloader(eng.device, d.shape[0], d.shape[1], codec='delta')
+    got = dl.download(d, 2)
+    exp = d.cpu().numpy()
+    ok = ~np.isnan(exp)
+    assert np.array_equal(np.isnan(got), ~ok)
+    assert np.array_equal(got.view(np.uint32)[ok], exp.view(np.uint32)[ok])
+    assert dl.fallbacks == 0 and dl.d2h_bytes < 1.0 * exp.size

@@ -148,3 +148,28 @@ def test_packed_field_rows_go_straight_to_the_compressor(tmp_path):
         assert np.array_equal(fa.read_step('OK', t).ravel(), fld[t], equal_nan=True)
     fa.close()
     fb.close()
+
+
+def test_delta_field_rows_go_straight_to_the_compressor(tmp_path):
+    """The same for the delta transport form (transfer.DeltaField): the compression workers
+    decode their step concurrently, each on its own thread."""
+    from spinterps_b200 import _lib
+    from spinterps_b200.transfer import DeltaField
+    from tests import dpack_ref
+    nt, ny, nx = 12, 9, 37
+    rng = np.random.default_rng(3)
+    fld = dpack_ref.synth_field(rng, nt, ny * nx, 2)
+    fld[4, 50:60] = -0.0
+    offs, payload = dpack_ref.encode(fld, 2)
+    df = DeltaField(_lib.load(), offs, payload, nt, ny * nx, 2)
+    assert np.array_equal(df.decode().view(np.uint32)[~np.isnan(fld)],
+                          fld.view(np.uint32)[~np.isnan(fld)])
+    assert np.array_equal(df.row(7), fld[7], equal_nan=True)
+    pa, *_ = _make(tmp_path, nt, ny, nx)
+    wa = Nc4Writer(pa, 'r+', n_threads=4)
+    wa.write_steps('OK', 0, df)
+    wa.close()
+    fa = Nc4Reader(pa)
+    for t in range(nt):
+        assert np.array_equal(fa.read_step('OK', t).ravel(), fld[t], equal_nan=True)
+    fa.close()
