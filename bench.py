@@ -494,39 +494,33 @@ def run_gpu(args):
     copy_stream = torch.cuda.Stream()
     checks = []
     n_dec = int(os.environ.get('SPX_DECODE_THREADS', str(max(1, min(16, len(os.sched_getaffinity(0)) // world)))))
-    dl = PackedDownloader(torch.device('cuda', local_rank), CHUNK_STEPS, NY * NX, depth=2,
-                          n_threads=n_dec)
-    dls = {'default': dl}
     host_out = [np.empty((CHUNK_STEPS, NY * NX), dtype=np.float32) for _ in range(2)]
     decoder = concurrent.futures.ThreadPoolExecutor(
         max_workers=1, initializer=lambda: torch.cuda.set_device(local_rank))
     kw_e2e = dict(kw, round_decimals=NMRL_PRCN, field_stats=True)
-    raw_rows = [0]
 
-    def run_e2e(n, decode=False, which='default'):
-        """Pipeline: submit chunk i+1 | output stage + encode + D2H of chunk i.  At the end
-        of a step its result sits in (pinned) host memory in the lossless compact form the
-        writer consumes (transfer.DeltaField / PackedField); decode=True additionally
-        rebuilds the whole f32 field in host memory (host threads, one chunk behind)."""
-        dl = dls[which]
+    def run_e2e(n, decode=False):
+        """Pipeline: submit chunk i+1 | output stage + encode + D2H of chunk i, through the
+        engine's public PendingChunk.start_packed / finish_packed.  At the end of a step its
+        result sits in (pinned) host memory in the lossless compact form the writer consumes
+        (transfer.DeltaField / PackedField) together with the per-step statistics;
+        decode=True additionally rebuilds the whole f32 field in host memory (host threads,
+        one chunk behind)."""
         futs = [None, None]
 
-        def finish(ticket, k):
-            raw_rows[0] += dl.finish(ticket, host_out[k % 2])
-
-        def land(ticket):
-            pf = dl.wait(ticket)
-            raw_rows[0] += len(pf.raw)
+        def land(pend, handle, k):
+            out, _ = pend.finish_packed(handle)
+            pf = out['OK']
+            if decode:
+                pf.decode(host_out[k % 2], n_dec)
             checks.append(int(pf.nbytes))
-            dl.release(ticket)
+            assert pend.field_stats is not None
+            pf.release()
 
         def drain(pend, k):
-            flds, _ = pend.result(to_host=False)
             if futs[k % 2] is not None:
                 futs[k % 2].result()                 # slot (and host buffer) k % 2 free again
-            ticket = dl.start(flds['OK'], NMRL_PRCN)
-            futs[k % 2] = decoder.submit(finish, ticket, k) if decode else \
-                decoder.submit(land, ticket)
+            futs[k % 2] = decoder.submit(land, pend, pend.start_packed(), k)
         pend = None
         for k in range(n):
             nxt = eng.submit_chunk(**kw_e2e, **next_chunk(chunks_e2e))
@@ -646,13 +640,13 @@ def run_gpu(args):
     dom = summarise(kernel_events)
 
     run_e2e(max(min(args.warmup, 3), 2))
+    dl = eng._dl
     h2d0 = eng.h2d_bytes
     d2h0 = dl.d2h_bytes
-    raw_rows[0] = 0
     ms_e2e, _ = timed(run_e2e, args.steps)
     h2d_e2e_bytes = eng.h2d_bytes - h2d0
     d2h_e2e_bytes = dl.d2h_bytes - d2h0
-    e2e_raw_rows = raw_rows[0]
+    e2e_codec, e2e_fallbacks, u16_stride = dl.codec, dl.fallbacks, dl.stride
     # ... with the whole f32 field rebuilt in host memory inside the timed region
     n_dcd = max(2, min(args.steps, 5))
     run_e2e(2, decode=True)
@@ -660,12 +654,12 @@ def run_gpu(args):
     # the same pipeline with the 16-bit codes of the earlier transport
     n_u16 = max(2, min(args.steps, 4))
     ms_e2e_u16 = None
-    if dl.codec != 'u16':
-        dls['u16'] = PackedDownloader(torch.device('cuda', local_rank), CHUNK_STEPS, NY * NX,
-                                      depth=2, n_threads=n_dec, codec='u16')
-        run_e2e(2, which='u16')
-        ms_e2e_u16, _ = timed(lambda n: run_e2e(n, which='u16'), n_u16)
-        del dls['u16']
+    if e2e_codec != 'u16':
+        eng.transport = 'u16'
+        run_e2e(2)
+        ms_e2e_u16, _ = timed(run_e2e, n_u16)
+        eng.transport = None
+        eng._dl = dl = None
     # the same pipeline with the round-1 transport (f32 field into pinned memory)
     n_raw = max(2, min(args.steps, 4))
     run_e2e_raw(2)
@@ -774,25 +768,25 @@ def run_gpu(args):
                     'ms_per_step': ms_e2e / args.steps,
                     'transport': 'output stage of the writer on the device (np.round to %d '
                                  'decimals, per-step statistics); the rounded f32 field crosses '
-                                 'PCIe in a lossless compact form (codec %r: deltas of the '
-                                 'integer lattice along each row, bit-packed per 8 cells, every '
-                                 'value verified bit-exact on the device; size depends on the '
-                                 'field, see d2h_bytes_per_cell_step) and lands in pinned host '
+                                 'PCIe in a lossless compact form (codec %r: first / second '
+                                 'differences of np.round\'s integer lattice along each row, '
+                                 'bit-packed per 8 cells, produced by the same single pass over '
+                                 'the field; size depends on the field, see '
+                                 'd2h_bytes_per_cell_step) and lands in pinned host '
                                  'memory as transfer.DeltaField, which the writer decodes one '
-                                 'step at a time' % (NMRL_PRCN, dl.codec),
+                                 'step at a time' % (NMRL_PRCN, e2e_codec),
                     'd2h_bytes_per_cell_step': d2h_e2e_bytes / max(args.steps, 1) / cell_steps,
-                    'fields_sent_through_fallback_codec': int(dl.fallbacks),
+                    'fields_sent_through_fallback_codec': int(e2e_fallbacks),
                     'u16_transport': None if ms_e2e_u16 is None else {
                         'value': world * cell_steps * n_u16 / (ms_e2e_u16 / 1e3),
                         'ms_per_step': ms_e2e_u16 / n_u16,
-                        'd2h_bytes_per_step': int(CHUNK_STEPS * (16 + 2 * dl.stride)),
+                        'd2h_bytes_per_step': int(CHUNK_STEPS * (16 + 2 * u16_stride)),
                         'note': 'same pipeline, 16-bit codes per row (2 bytes per cell-step)'},
                     'decoded_f32': {
                         'value': world * cell_steps * n_dcd / (ms_e2e_dec / 1e3),
                         'ms_per_step': ms_e2e_dec / n_dcd, 'decode_threads': n_dec,
                         'note': 'same pipeline plus the decode of the WHOLE field to f32 in host '
                                 'memory inside the timed region'},
-                    'rows_sent_as_raw_f32': int(e2e_raw_rows),
                     'd2h_gbs': d2h_e2e_bytes / max(ms_e2e, 1e-9) / 1e6,
                     'd2h_ceiling_gbs': d2h_peak,
                     'raw_f32_transport': {

@@ -760,30 +760,45 @@ int spx_unpack_field_host(const spx_pack_row* hdr, const uint16_t* codes, int64_
 /* ---- lossless delta transport of rounded f32 fields (variable rate) ------------------
  * Same integer lattice as above, but neighbouring cells of an interpolated field differ by
  * few lattice steps: every row is cut into tiles of SPX_DPACK_TILE cells, the chain of q
- * along a tile is delta + zigzag coded and bit-packed per group of 8 cells with the
- * group's own width (0..12, 14, 16 or 32 bits); NaN and -0.0 cells sit in per-tile bitmaps,
- * a tile with a value that fails the bit-exact round-trip check is stored as raw floats.
- * Each tile is one variable-size record in `payload`, tile_off[row * tiles + tile] is its
- * offset in units of 4 bytes (record layout: csrc/spx_pack.cu).  Typical interpolated
- * fields need 0.3-0.6 bytes per cell instead of 4 (interp/steps.py:907-945 writes the
- * identical floats after the host decode). */
+ * along a tile is delta (first or second differences) + zigzag coded and bit-packed per
+ * group of 8 cells with the group's own width (0..12, 14, 16 or 32 bits); NaN and -0.0 cells
+ * sit in per-tile bitmaps, a tile with a value that is not on the lattice is stored as raw
+ * floats.  The records of SPX_DPACK_SEGMENT cells (32 tiles) are contiguous in `payload`,
+ * seg_off[row * segments + segment] is their offset in units of 4 bytes (record layout:
+ * csrc/spx_pack.cu).  Typical interpolated fields need 0.2-0.6 bytes per cell instead of 4;
+ * the host decode returns the identical floats (what interp/steps.py:907-945 writes).
+ *
+ * With SPX_DPACK_ROUND the call is the writer's whole output stage in one pass over the
+ * UNROUNDED field: np.round(fld, decimals) in float32 (interp/steps.py:907-912) -- the
+ * transported integers are np.round's own intermediate rint(x * 10^d) --, the per-step
+ * statistics of interp/main.py:474-525 (stats != NULL, layout as spx_round_stats_dev), the
+ * encoding; SPX_DPACK_WRITE_BACK also stores the rounded values to fld.  Without
+ * SPX_DPACK_ROUND the field must already be rounded; every value is then checked to
+ * round-trip bit for bit (else its tile travels raw) and fld is only read. */
 #define SPX_DPACK_TILE 256
-/* Tiles per row; worst-case payload bytes of a field (every tile raw). */
-int64_t spx_dpack_tiles(int64_t row_len);
+#define SPX_DPACK_SEGMENT 8192
+#define SPX_DPACK_ROUND 1
+#define SPX_DPACK_WRITE_BACK 2
+/* Segments per row; worst-case payload bytes of a field (every tile raw); bytes of the
+ * device workspace the statistics need. */
+int64_t spx_dpack_segments(int64_t row_len);
 int64_t spx_dpack_capacity(int64_t n_rows, int64_t row_len);
-/* fld: device f32 [n_rows, row_len] pitch ld, already rounded to `decimals` (0..9) places;
- * tile_off: device uint32 [n_rows * spx_dpack_tiles(row_len)]; payload: device buffer of
- * capacity_bytes (any size: records that do not fit are not written, their tile_off is
- * 0xFFFFFFFF); counters: device uint64[2], written by the call: [0] = 4-byte words the
- * records need in total (may exceed the capacity), [1] = 1 if a record did not fit.
- * The order of the records in the payload is not deterministic; the decoded field is. */
-int spx_dpack_field_dev(const float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
-                        int32_t decimals, uint32_t* tile_off, void* payload,
-                        int64_t capacity_bytes, uint64_t* counters, void* stream);
-/* HOST pointers.  Decodes n_rows rows (tile_off points at the first of them) into out
+int64_t spx_dpack_stats_workspace(int64_t n_rows, int64_t row_len);
+/* fld: device f32 [n_rows, row_len] pitch ld; decimals 0..9; stats: device double
+ * [5, n_rows] or NULL (then workspace may be NULL); seg_off: device uint32
+ * [n_rows * spx_dpack_segments(row_len)]; payload: device buffer of capacity_bytes (any size:
+ * segments that do not fit are not written, their seg_off is 0xFFFFFFFF); counters: device
+ * uint64[2], written by the call: [0] = 4-byte words the records need in total (may exceed
+ * the capacity), [1] = 1 if a segment did not fit.  The order of the segments in the payload
+ * is not deterministic; their content and the decoded field are. */
+int spx_dpack_field_dev(float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
+                        int32_t decimals, int32_t flags, double* stats, void* workspace,
+                        uint32_t* seg_off, void* payload, int64_t capacity_bytes,
+                        uint64_t* counters, void* stream);
+/* HOST pointers.  Decodes n_rows rows (seg_off points at the first of them) into out
  * [n_rows, row_len] pitch out_ld; payload_bytes bounds every access.  n_threads <= 0:
  * default, 1: on the calling thread (safe to call from several threads at once). */
-int spx_dunpack_rows_host(const uint32_t* tile_off, const void* payload, int64_t payload_bytes,
+int spx_dunpack_rows_host(const uint32_t* seg_off, const void* payload, int64_t payload_bytes,
                           int64_t n_rows, int64_t row_len, int32_t decimals, float* out,
                           int64_t out_ld, int32_t n_threads);
 

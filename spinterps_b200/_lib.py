@@ -169,6 +169,7 @@ class spx_pack_row(C.Structure):
 PACK_ROW_DTYPE = np.dtype([('mode', np.int32), ('qmin', np.int32), ('qmax', np.int32),
                            ('n_nan', np.int32)])
 SPX_PACK_U16, SPX_PACK_RAW = 0, 2
+SPX_DPACK_ROUND, SPX_DPACK_WRITE_BACK = 1, 2
 
 
 class spx_fast_cfg(C.Structure):
@@ -307,10 +308,12 @@ _SIGS = {
                                         C.c_void_p, C.c_int64, C.c_int32]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
-    'spx_dpack_tiles': (C.c_int64, [C.c_int64]),
+    'spx_dpack_segments': (C.c_int64, [C.c_int64]),
     'spx_dpack_capacity': (C.c_int64, [C.c_int64, C.c_int64]),
+    'spx_dpack_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),
     'spx_dpack_field_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_void_p]),
     'spx_dunpack_rows_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int32, C.c_void_p, C.c_int64, C.c_int32]),
 }

@@ -3,6 +3,7 @@
 #include <type_traits>
 
 #include "spx_common.cuh"
+#include "spx_stats.cuh"
 
 namespace spx {
 
@@ -271,50 +272,6 @@ static inline unsigned grid_y(int64_t n) { return (unsigned)(n < 1 ? 1 : (n > 65
 // before it is written (np.round: rint(x * 10^d) / 10^d, both operations rounded in that
 // dtype) and interp/main.py:474-525 re-reads the file to get per-step min / mean / max /
 // std / count.  Both in one pass over the field while it is still in HBM.
-struct StatPart {
-    double n, mean, m2, mn, mx, nfin;
-};
-
-__device__ __forceinline__ void stat_merge(StatPart& a, const StatPart& b) {
-    // Chan et al. pairwise update of (n, mean, M2)
-    if (b.n > 0.0) {
-        if (a.n == 0.0) {
-            a.n = b.n; a.mean = b.mean; a.m2 = b.m2;
-        } else {
-            const double n = a.n + b.n;
-            const double dlt = b.mean - a.mean;
-            a.mean += dlt * (b.n / n);
-            a.m2 += b.m2 + dlt * dlt * (a.n * b.n / n);
-            a.n = n;
-        }
-    }
-    a.mn = fmin(a.mn, b.mn);     // fmin / fmax ignore NaN: nanmin / nanmax
-    a.mx = fmax(a.mx, b.mx);
-    a.nfin += b.nfin;
-}
-
-__device__ __forceinline__ StatPart stat_shfl(const StatPart& a, int o) {
-    StatPart b;
-    b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
-    b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
-    b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
-    b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
-    b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
-    b.nfin = __shfl_xor_sync(0xffffffffu, a.nfin, o);
-    return b;
-}
-
-template <typename T>
-__device__ __forceinline__ T round_dec(T x, T p);
-template <>
-__device__ __forceinline__ float round_dec<float>(float x, float p) {
-    return __fdiv_rn(rintf(__fmul_rn(x, p)), p);
-}
-template <>
-__device__ __forceinline__ double round_dec<double>(double x, double p) {
-    return __ddiv_rn(rint(__dmul_rn(x, p)), p);
-}
-
 constexpr int RS_THREADS = 256;
 
 template <typename T, bool VEC>
@@ -425,6 +382,11 @@ __global__ void k_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, 
     stats[2 * n_rows + row] = any ? t.mx : CUDART_NAN;
     stats[3 * n_rows + row] = any ? sqrt(fmax(t.m2, 0.0) / t.n) : CUDART_NAN;
     stats[4 * n_rows + row] = t.nfin;
+}
+
+void launch_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, double* stats,
+                        cudaStream_t st) {
+    k_stats_final<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(parts, n_seg, n_rows, stats);
 }
 
 }  // namespace spx

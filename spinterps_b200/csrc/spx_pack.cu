@@ -19,6 +19,7 @@
 #include "spx_b200.h"
 #include "spx_common.cuh"
 #include "spx_host_pool.h"
+#include "spx_stats.cuh"
 
 namespace spx {
 
@@ -224,26 +225,39 @@ static void unpack_row_scalar(const uint16_t* src, int64_t n, int32_t qmin, floa
 //
 // A kriged / IDW field is smooth, so neighbouring cells of a row differ by few lattice
 // steps: q[c] - q[c-1] needs 0..6 bits where the 16-bit code above spends 16.  A row is cut
-// into tiles of 256 cells (one warp, 8 consecutive cells per lane).  Inside a tile the
-// chain f[c] = q[c] (valid cell) / f[c-1] (NaN cell), f[-1] = base = q of the first valid
-// cell, is delta coded (d = f[c] - f[c-1] modulo 2^32, zigzag), every group of 8 cells
-// (a lane) is bit-packed with its own width w in {0..12, 14, 16, 32} -- 8 values of w bits
-// are exactly w bytes -- and the tile becomes ONE variable-size record in a payload
-// buffer; records are allocated by one atomicAdd per block, tile_off[row, tile] points at
-// them (units of 4 bytes).  Record:
-//   word 0          mode: bits 0-1 kind (0 every cell NaN, 1 packed, 2 raw f32, 3 constant),
-//                   bit 2 NaN bitmap present, bit 3 -0.0 bitmap present
-//   kind 1          base int32 | 16 B width nibbles (lane l: byte l/2, low nibble = even
-//                   lane) | [32 B NaN bitmap: byte l = cells of lane l] | [32 B -0.0
-//                   bitmap] | payload, sum of the widths bytes | zero padding to 4 B
-//   kind 2          256 raw floats (a cell failed the bit-exact round-trip check, or the
-//                   packed record would not be smaller)
+// into tiles of 256 cells (one warp, 8 consecutive cells per lane) and segments of 32 tiles
+// (one thread block).  Inside a tile the chain f[c] = q[c] (valid cell) / f[c-1] (NaN cell),
+// f[-1] = base = q of the first valid cell, is delta coded (first differences, or second
+// differences when every cell of the tile is valid and that is smaller; arithmetic modulo
+// 2^32, zigzag), every group of 8 cells (a lane) is bit-packed with its own width w in
+// {0..12, 14, 16, 32} -- 8 values of w bits are exactly w bytes.  The records of a segment
+// follow one another in tile order, each padded to 4 bytes; the block builds them in shared
+// memory, reserves the words with ONE atomicAdd and copies them out compacted;
+// seg_off[row, segment] points at them (units of 4 bytes).  Tile record:
+//   byte 0          mode: bits 0-1 kind (0 every cell NaN, 1 packed, 2 raw f32, 3 constant),
+//                   bit 2 NaN bitmap present, bit 3 -0.0 bitmap present, bit 4 second differences
+//   kind 1          base int32 | group bitmap uint32 (bit l: lane l has w > 0) | width codes of
+//                   those groups, 4 bits each in group order (low nibble first) | [32 B NaN
+//                   bitmap: byte l = cells of lane l] | [32 B -0.0 bitmap] | payload, sum of the
+//                   widths bytes
+//   kind 2          256 raw floats (a value is not on the lattice / beyond int32, or the packed
+//                   record would not be smaller)
 //   kind 3          base int32 (all 256 cells equal)
 // The host decode (spx_dunpack_rows_host) rebuilds float(f) / 10^d: the identical bytes.
+//
+// The same kernel is the writer's whole output stage when asked (ROUND / STATS): it reads
+// the UNROUNDED field once, q = rint(x * 10^d) is np.round's own intermediate
+// (interp/steps.py:907-912), so no round-trip check is needed, the per-step statistics of
+// interp/main.py:474-525 are reduced from the rounded values on the way, and the rounded
+// field is written back only if the caller wants it in HBM as well.
 constexpr int DP_TILE = SPX_DPACK_TILE;
 constexpr int DP_WARPS = 8;
-constexpr int DP_RAW_WORDS = 1 + DP_TILE;                 // mode + 256 floats
-constexpr int DP_STAGE_WORDS = 280;                       // >= 2 + 4 + 8 + 8 + 256 + slack
+constexpr int DP_TPW = 4;                                 // tiles per warp
+constexpr int DP_SEG_TILES = DP_WARPS * DP_TPW;           // 32
+constexpr int DP_SEG_CELLS = DP_SEG_TILES * DP_TILE;      // 8192 == SPX_DPACK_SEGMENT
+constexpr int DP_RAW_BYTES = 1 + 4 * DP_TILE;             // mode + 256 floats
+constexpr int DP_SLOT_BYTES = (DP_RAW_BYTES + 3) / 4 * 4;   // 1028: a record padded to 4 bytes
+static_assert(DP_SEG_CELLS == SPX_DPACK_SEGMENT, "segment size");
 
 __host__ __device__ __forceinline__ int dp_width_of_code(int code) {
     return code < 13 ? code : (code == 13 ? 14 : (code == 14 ? 16 : 32));
@@ -251,79 +265,131 @@ __host__ __device__ __forceinline__ int dp_width_of_code(int code) {
 __device__ __forceinline__ int dp_code_of_width(int w) {
     return w <= 12 ? w : (w <= 14 ? 13 : (w <= 16 ? 14 : 15));
 }
+__device__ __forceinline__ uint32_t dp_zigzag(int d) {
+    return ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
+}
+__device__ __forceinline__ void dp_store_u32(uint8_t* at, uint32_t v) {
+    at[0] = (uint8_t)v; at[1] = (uint8_t)(v >> 8); at[2] = (uint8_t)(v >> 16); at[3] = (uint8_t)(v >> 24);
+}
 
-__global__ void __launch_bounds__(DP_WARPS * 32) k_dpack(
-    const float* __restrict__ fld, int64_t row_len, int64_t ld, int64_t tiles_per_row,
-    int64_t n_tiles, float p, int vec_ok, uint32_t* __restrict__ tile_off,
-    uint32_t* __restrict__ payload, unsigned long long cap_words,
-    unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t stage[DP_WARPS][DP_STAGE_WORDS];
-    __shared__ uint32_t rec_words[DP_WARPS];
-    __shared__ unsigned long long blk_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * DP_WARPS + warp;
-    const bool live = g < n_tiles;
-    const int64_t row = live ? g / tiles_per_row : 0;
-    const int64_t c0 = live ? (g - row * tiles_per_row) * DP_TILE + lane * 8 : 0;
-    const float* __restrict__ src = fld + row * ld + c0;
+// Results of the general per-tile path (NaN / -0.0 / off-lattice cells, row tails, input
+// that is already rounded): through local memory, these tiles are the minority.
+struct DpGen {
+    uint32_t z[8];
+    float r[8];                      // the (rounded) values of the lane's cells
+    int code, wq, pay, base, kind;   // kind: 0 no value at all, 2 raw, 1 otherwise
+    uint32_t nzg, m_nan, m_nz, any_nan, any_nz, order2;
+    int st_n, st_fin;
+    double st_s, st_q;
+    float st_mn, st_mx;
+};
 
-    float v[8];
-    uint32_t in_rng = 0;                     // bit j: cell c0 + j exists
-    if (live) {
-        if (vec_ok && c0 + 8 <= row_len) {
-            const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
-            const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            in_rng = 0xFFu;
-        } else {
+// first / second differences of a tile whose 256 cells are all valid: fills z / code / wq /
+// pay / nzg with the smaller of the two, returns 1 for second differences
+__device__ __forceinline__ uint32_t dp_deltas_all_valid(const int (&q)[8], int lane, uint32_t (&z)[8],
+                                                        int& base, int& code, int& wq, int& pay,
+                                                        uint32_t& nzg) {
+    const uint32_t FULL = 0xffffffffu;
+    base = __shfl_sync(FULL, q[0], 0);
+    int p1 = __shfl_up_sync(FULL, q[7], 1), p2 = __shfl_up_sync(FULL, q[6], 1);
+    if (lane == 0) { p1 = base; p2 = base; }
+    uint32_t z2[8], or1 = 0, or2 = 0;
+    int f = p1, dprev = (int)((uint32_t)p1 - (uint32_t)p2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool in = c0 + j < row_len;
-                v[j] = in ? src[j] : 0.0f;
-                in_rng |= (uint32_t)in << j;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    for (int j = 0; j < 8; ++j) {
+        const int d1 = (int)((uint32_t)q[j] - (uint32_t)f);
+        const int d2 = (int)((uint32_t)d1 - (uint32_t)dprev);
+        f = q[j];
+        dprev = d1;
+        z[j] = dp_zigzag(d1);
+        z2[j] = dp_zigzag(d2);
+        or1 |= z[j];
+        or2 |= z2[j];
     }
+    const int c1 = dp_code_of_width(32 - __clz(or1)), c2 = dp_code_of_width(32 - __clz(or2));
+    const int w1 = dp_width_of_code(c1), w2 = dp_width_of_code(c2);
+    const int pay1 = __reduce_add_sync(FULL, w1), pay2 = __reduce_add_sync(FULL, w2);
+    const uint32_t g1 = __ballot_sync(FULL, w1 > 0), g2 = __ballot_sync(FULL, w2 > 0);
+    const int s1 = pay1 + ((__popc(g1) + 1) >> 1), s2 = pay2 + ((__popc(g2) + 1) >> 1);
+    if (s2 < s1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = z2[j];
+        code = c2; wq = w2; pay = pay2; nzg = g2;
+        return 1u;
+    }
+    code = c1; wq = w1; pay = pay1; nzg = g1;
+    return 0u;
+}
+
+__device__ __noinline__ void dp_tile_general(const float* v, uint32_t in_rng, float p, int round,
+                                             int stats, double K, DpGen* g) {
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     int q[8];
     uint32_t m_val = 0, m_nan = 0, m_nz = 0, bad = 0;
+    int st_n = 0, st_fin = 0;
+    double st_s = 0.0, st_q = 0.0;
+    float st_mn = CUDART_INF_F, st_mx = -CUDART_INF_F;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         q[j] = 0;
+        g->r[j] = 0.0f;
         if (!((in_rng >> j) & 1u)) continue;
         const float x = v[j];
-        if (x != x) {
-            m_nan |= 1u << j;
-        } else if (__float_as_uint(x) == 0x80000000u) {
-            m_nz |= 1u << j;                 // -0.0: q = 0 in the chain, sign from the bitmap
-            m_val |= 1u << j;
+        float rr = x;
+        if (round) {
+            const float qf = rintf(__fmul_rn(x, p));
+            rr = __fdiv_rn(qf, p);                          // np.round(x, d) in float32
+            if (x != x) {
+                m_nan |= 1u << j;
+            } else if (fabsf(qf) < 2147483520.0f) {
+                q[j] = (int)qf;
+                m_val |= 1u << j;
+                if (__float_as_uint(qf) == 0x80000000u) m_nz |= 1u << j;
+            } else {
+                bad = 1;                                    // inf, or beyond int32: raw tile
+            }
         } else {
-            int qq = 0;
-            if (pack_q(x, p, qq)) {
-                q[j] = qq;
+            if (x != x) {
+                m_nan |= 1u << j;
+            } else if (__float_as_uint(x) == 0x80000000u) {
+                m_nz |= 1u << j;                            // -0.0: q = 0 in the chain
                 m_val |= 1u << j;
             } else {
-                bad = 1;
+                int qq = 0;
+                if (pack_q(x, p, qq)) { q[j] = qq; m_val |= 1u << j; }
+                else bad = 1;
             }
         }
+        g->r[j] = rr;
+        if (stats && rr == rr) {
+            const double d = (double)rr - K;
+            st_n += 1;
+            st_s += d;
+            st_q = fma(d, d, st_q);
+            st_mn = fminf(st_mn, rr);
+            st_mx = fmaxf(st_mx, rr);
+            st_fin += (fabsf(rr) <= 3.402823466e38f) ? 1 : 0;
+        }
     }
-    const uint32_t FULL = 0xffffffffu;
+    g->st_n = st_n; g->st_fin = st_fin; g->st_s = st_s; g->st_q = st_q;
+    g->st_mn = st_mn; g->st_mx = st_mx;
     const uint32_t any_bad = __ballot_sync(FULL, bad != 0);
     const uint32_t has_val = __ballot_sync(FULL, m_val != 0);
-    const uint32_t any_nan = __ballot_sync(FULL, m_nan != 0);
-    const uint32_t any_nz = __ballot_sync(FULL, m_nz != 0);
+    g->any_nan = __ballot_sync(FULL, m_nan != 0);
+    g->any_nz = __ballot_sync(FULL, m_nz != 0);
     const uint32_t all_val = __ballot_sync(FULL, m_val == 0xFFu);
-
-    // value in front of this lane's first cell: last valid q of the lower lanes, else base
-    int prev, base;
+    g->m_nan = m_nan;
+    g->m_nz = m_nz;
+    g->kind = any_bad ? 2 : (has_val ? 1 : 0);
+    uint32_t z[8];
+    int base, code, wq, pay;
+    uint32_t nzg;
+    g->order2 = 0;
     if (all_val == FULL) {
-        base = __shfl_sync(FULL, q[0], 0);
-        prev = __shfl_up_sync(FULL, q[7], 1);
-        if (lane == 0) prev = base;
+        g->order2 = dp_deltas_all_valid(q, lane, z, base, code, wq, pay, nzg);
     } else {
+        // value in front of this lane's first cell: last valid q of the lower lanes
         int lastq = 0, firstq = 0;
 #pragma unroll
         for (int j = 7; j >= 0; --j)
@@ -341,11 +407,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32) k_dpack(
         const int hx = __shfl_up_sync(FULL, has, 1);
         const int qx = __shfl_up_sync(FULL, lastq, 1);
         base = __shfl_sync(FULL, firstq, has_val ? __ffs(has_val) - 1 : 0);
-        prev = (lane > 0 && hx) ? qx : base;
-    }
-    uint32_t z[8], orz = 0;
-    {
-        int f = prev;
+        int f = (lane > 0 && hx) ? qx : base;
+        uint32_t orz = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int d = 0;
@@ -353,144 +416,343 @@ __global__ void __launch_bounds__(DP_WARPS * 32) k_dpack(
                 d = (int)((uint32_t)q[j] - (uint32_t)f);
                 f = q[j];
             }
-            z[j] = ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
+            z[j] = dp_zigzag(d);
             orz |= z[j];
         }
+        code = dp_code_of_width(32 - __clz(orz));
+        wq = dp_width_of_code(code);
+        pay = __reduce_add_sync(FULL, wq);
+        nzg = __ballot_sync(FULL, wq > 0);
     }
-    const int code = dp_code_of_width(32 - __clz(orz));
-    const int wq = dp_width_of_code(code);
-    int off = wq;                                  // inclusive prefix sum of the widths
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, off, o);
-        if (lane >= o) off += t;
-    }
-    const int pay = __shfl_sync(FULL, off, 31);
-    off -= wq;
-    int kind, words;
-    const int hdr_bytes = 8 + 16 + (any_nan ? 32 : 0) + (any_nz ? 32 : 0);
-    if (!has_val && !any_bad) { kind = 0; words = 1; }
-    else if (any_bad) { kind = 2; words = DP_RAW_WORDS; }
-    else if (pay == 0 && !any_nan && !any_nz) { kind = 3; words = 2; }
-    else {
-        kind = 1;
-        words = (hdr_bytes + pay + 3) >> 2;
-        if (words >= DP_RAW_WORDS) { kind = 2; words = DP_RAW_WORDS; }
-    }
-    if (!live) words = 0;
-    if (lane == 0) rec_words[warp] = (uint32_t)words;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
+    for (int j = 0; j < 8; ++j) g->z[j] = z[j];
+    g->code = code; g->wq = wq; g->pay = pay; g->base = base; g->nzg = nzg;
+}
+
+__device__ __forceinline__ void dp_load_tile(const float* rowp, int64_t c0, int64_t row_len,
+                                             int vec_ok, float (&v)[8], uint32_t& in_rng) {
+    if (vec_ok && c0 + 8 <= row_len) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(rowp + c0));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(rowp + c0) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        in_rng = 0xFFu;
+    } else {
+        in_rng = 0;
 #pragma unroll
-        for (int w = 0; w < DP_WARPS; ++w) tot += rec_words[w];
-        blk_base = atomicAdd(&counters[0], (unsigned long long)tot);
+        for (int j = 0; j < 8; ++j) {
+            const bool in = c0 + j < row_len;
+            v[j] = in ? rowp[c0 + j] : 0.0f;
+            in_rng |= (uint32_t)in << j;
+        }
     }
-    __syncthreads();
-    if (!live) return;
-    unsigned long long at = blk_base;
-    for (int w = 0; w < warp; ++w) at += rec_words[w];
-    if (at + (unsigned long long)words > cap_words) {          // does not fit: flagged, not written
+}
+
+template <bool ROUND, bool STATS>
+__global__ void __launch_bounds__(DP_WARPS * 32, 3) k_dpack(
+    const float* fld, float* wb, int64_t row_len, int64_t ld,
+    int64_t segs_per_row, float p, int vec_ok, uint32_t* __restrict__ seg_off,
+    uint32_t* __restrict__ payload, unsigned long long cap_words,
+    unsigned long long* __restrict__ counters, StatPart* __restrict__ parts) {
+    // one 4-byte aligned slot per tile of the segment; the records are compacted on the way out
+    __shared__ __align__(16) uint8_t stage[DP_SEG_TILES * DP_SLOT_BYTES];
+    __shared__ int rec_words[DP_SEG_TILES];
+    __shared__ int rec_pos[DP_SEG_TILES + 1];
+    __shared__ unsigned long long blk_base;
+    __shared__ StatPart sp[DP_WARPS];
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x / segs_per_row;
+    const int64_t seg = blockIdx.x - row * segs_per_row;
+    const float* rowp = fld + row * ld;
+    const int64_t seg_c0 = seg * DP_SEG_CELLS;
+
+    // statistics: shifted sums against the segment's first (rounded) value
+    double K = 0.0, st_s = 0.0, st_q = 0.0;
+    float st_mn = CUDART_INF_F, st_mx = -CUDART_INF_F;
+    int st_n = 0, st_fin = 0;
+    if (STATS) {
+        float x0 = rowp[seg_c0];
+        if (ROUND) x0 = __fdiv_rn(rintf(__fmul_rn(x0, p)), p);
+        K = (double)x0;
+        if (!(fabs(K) < 1.0e300)) K = 0.0;
+    }
+
+    float v[8], vn[8];
+    uint32_t in_rng, in_rng_n = 0;
+    dp_load_tile(rowp, seg_c0 + (int64_t)warp * DP_TILE + lane * 8, row_len, vec_ok, v, in_rng);
+#pragma unroll 1
+    for (int i = 0; i < DP_TPW; ++i) {
+        const int tile = i * DP_WARPS + warp;
+        const int64_t tile_c0 = seg_c0 + (int64_t)tile * DP_TILE;
+        if (i + 1 < DP_TPW)                        // the next tile's loads fly during this one
+            dp_load_tile(rowp, tile_c0 + (int64_t)DP_WARPS * DP_TILE + lane * 8, row_len, vec_ok,
+                         vn, in_rng_n);
+        if (tile_c0 >= row_len) {                  // past the end of the row: no record
+            if (lane == 0) rec_words[tile] = 0;
+        } else {
+            uint32_t z[8];
+            int base = 0, code = 0, wq = 0, pay = 0, kind = 1;
+            uint32_t nzg = 0, any_nan = 0, any_nz = 0, order2 = 0, m_nan = 0, m_nz = 0;
+            bool fast = false;
+            if (ROUND) {
+                // fast path: every cell of the tile exists, is finite, on the int32 lattice
+                // and not -0.0 -- then q = rint(x * 10^d) needs no further check
+                float qf[8];
+                uint32_t amax = 0, nzmin = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    qf[j] = rintf(__fmul_rn(v[j], p));
+                    const uint32_t u = __float_as_uint(qf[j]);
+                    amax = max(amax, u & 0x7fffffffu);
+                    nzmin = min(nzmin, u ^ 0x80000000u);
+                }
+                fast = __all_sync(FULL, in_rng == 0xFFu && amax < 0x4f000000u && nzmin != 0u);
+                if (fast) {
+                    int q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) q[j] = (int)qf[j];
+                    if (STATS || wb != nullptr) {
+                        float r[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) r[j] = __fdiv_rn(qf[j], p);
+                        if (STATS) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const double d = (double)r[j] - K;
+                                st_s += d;
+                                st_q = fma(d, d, st_q);
+                                st_mn = fminf(st_mn, r[j]);
+                                st_mx = fmaxf(st_mx, r[j]);
+                            }
+                            st_n += 8;
+                            st_fin += 8;
+                        }
+                        if (wb != nullptr) {
+                            float* o = wb + row * ld + tile_c0 + lane * 8;
+                            if (vec_ok) {
+                                __stcs(reinterpret_cast<float4*>(o),
+                                       make_float4(r[0], r[1], r[2], r[3]));
+                                __stcs(reinterpret_cast<float4*>(o) + 1,
+                                       make_float4(r[4], r[5], r[6], r[7]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = r[j];
+                            }
+                        }
+                    }
+                    order2 = dp_deltas_all_valid(q, lane, z, base, code, wq, pay, nzg);
+                }
+            }
+            if (!fast) {
+                float tmp[8];
+                DpGen g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tmp[j] = v[j];
+                dp_tile_general(tmp, in_rng, p, ROUND ? 1 : 0, STATS ? 1 : 0, K, &g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = g.z[j];
+                base = g.base; code = g.code; wq = g.wq; pay = g.pay; kind = g.kind;
+                nzg = g.nzg; any_nan = g.any_nan; any_nz = g.any_nz; order2 = g.order2;
+                m_nan = g.m_nan;
+                m_nz = g.m_nz;
+                if (STATS) {
+                    st_n += g.st_n; st_fin += g.st_fin; st_s += g.st_s; st_q += g.st_q;
+                    st_mn = fminf(st_mn, g.st_mn); st_mx = fmaxf(st_mx, g.st_mx);
+                }
+                if (ROUND && wb != nullptr) {
+                    float* o = wb + row * ld + tile_c0 + lane * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((in_rng >> j) & 1u) o[j] = g.r[j];
+                }
+                if (ROUND) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = g.r[j];       // raw tiles carry rounded values
+                }
+            }
+            int bytes;
+            if (kind == 2) { bytes = DP_RAW_BYTES; }
+            else if (kind == 0) { bytes = 1; }
+            else if (pay == 0 && !any_nan && !any_nz) { kind = 3; bytes = 5; }
+            else {
+                bytes = 9 + ((__popc(nzg) + 1) >> 1) + (any_nan ? 32 : 0) + (any_nz ? 32 : 0) + pay;
+                if (bytes >= DP_RAW_BYTES) { kind = 2; bytes = DP_RAW_BYTES; }
+            }
+            const int words = (bytes + 3) >> 2;
+            uint8_t* rb = stage + tile * DP_SLOT_BYTES;
+            if (lane == 0) {
+                rec_words[tile] = words;
+                rb[0] = (kind != 1) ? (uint8_t)kind
+                                    : (uint8_t)(1u | (any_nan ? 4u : 0u) | (any_nz ? 8u : 0u) |
+                                                (order2 << 4));
+                if (kind == 1 || kind == 3) dp_store_u32(rb + 1, (uint32_t)base);
+                if (kind == 1) dp_store_u32(rb + 5, nzg);
+                for (int k = bytes; k < words * 4; ++k) rb[k] = 0;     // padding to 4 bytes
+            }
+            if (kind == 2) {
+                uint8_t* o = rb + 1 + lane * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dp_store_u32(o + 4 * j, __float_as_uint(v[j]));
+            } else if (kind == 1) {
+                {   // width codes of the non-empty groups, two per byte
+                    const int idx = __popc(nzg & ((1u << lane) - 1u));
+                    const uint32_t above = (lane < 31) ? (nzg & ~((2u << lane) - 1u)) : 0u;
+                    const int nxt = above ? __ffs(above) - 1 : 0;
+                    const int c_hi = __shfl_sync(FULL, code, nxt);
+                    if (wq > 0 && (idx & 1) == 0)
+                        rb[9 + (idx >> 1)] = (uint8_t)(code | ((above ? c_hi : 0) << 4));
+                }
+                int off = wq;                      // exclusive prefix sum of the widths
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, off, o);
+                    if (lane >= o) off += t;
+                }
+                off -= wq;
+                int pos = 9 + ((__popc(nzg) + 1) >> 1);
+                if (any_nan) { rb[pos + lane] = (uint8_t)m_nan; pos += 32; }
+                if (any_nz) { rb[pos + lane] = (uint8_t)m_nz; pos += 32; }
+                uint8_t* out = rb + pos + off;
+                if (wq == 32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dp_store_u32(out + 4 * j, z[j]);
+                } else if (wq > 0) {
+                    const int w = wq;                          // 1..16
+                    const uint32_t a0 = z[0] | (z[1] << w), a1 = z[2] | (z[3] << w);
+                    const uint32_t a2 = z[4] | (z[5] << w), a3 = z[6] | (z[7] << w);
+                    const uint64_t b0 = (uint64_t)a0 | ((uint64_t)a1 << (2 * w));
+                    const uint64_t b1 = (uint64_t)a2 | ((uint64_t)a3 << (2 * w));
+                    uint64_t lo, hi;
+                    if (w == 16) { lo = b0; hi = b1; }
+                    else { lo = b0 | (b1 << (4 * w)); hi = b1 >> (64 - 4 * w); }
+                    const uint32_t l0 = (uint32_t)lo, l1 = (uint32_t)(lo >> 32);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < w) out[k] = (uint8_t)(l0 >> (8 * k));
+                    if (w > 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k + 4 < w) out[k + 4] = (uint8_t)(l1 >> (8 * k));
+                        for (int k = 8; k < w; ++k) { out[k] = (uint8_t)hi; hi >>= 8; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        in_rng = in_rng_n;
+    }
+    if (STATS) {
+        // one shift K for the whole block: the sums simply add up
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_n += __shfl_xor_sync(FULL, st_n, o);
+            st_fin += __shfl_xor_sync(FULL, st_fin, o);
+            st_s += __shfl_xor_sync(FULL, st_s, o);
+            st_q += __shfl_xor_sync(FULL, st_q, o);
+            st_mn = fminf(st_mn, __shfl_xor_sync(FULL, st_mn, o));
+            st_mx = fmaxf(st_mx, __shfl_xor_sync(FULL, st_mx, o));
+        }
         if (lane == 0) {
-            tile_off[g] = 0xFFFFFFFFu;
+            StatPart a;
+            a.n = (double)st_n; a.mean = st_s; a.m2 = st_q;      // raw sums, finished below
+            a.mn = (double)st_mn; a.mx = (double)st_mx; a.nfin = (double)st_fin;
+            sp[warp] = a;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int b = rec_words[lane];
+        int inc = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        rec_pos[lane] = inc - b;
+        if (lane == 31) {
+            rec_pos[32] = inc;
+            blk_base = atomicAdd(&counters[0], (unsigned long long)inc);
+        }
+    }
+    if (STATS && threadIdx.x == 32) {
+        StatPart t = sp[0];
+        for (int w = 1; w < DP_WARPS; ++w) {
+            t.n += sp[w].n; t.mean += sp[w].mean; t.m2 += sp[w].m2; t.nfin += sp[w].nfin;
+            t.mn = fmin(t.mn, sp[w].mn); t.mx = fmax(t.mx, sp[w].mx);
+        }
+        const double sum = t.mean, sq = t.m2;
+        t.mean = (t.n > 0.0) ? K + sum / t.n : 0.0;
+        t.m2 = (t.n > 0.0) ? sq - sum * (sum / t.n) : 0.0;
+        parts[blockIdx.x] = t;
+    }
+    __syncthreads();
+    const unsigned long long at = blk_base;
+    if (at + (unsigned long long)rec_pos[DP_SEG_TILES] > cap_words) {   // does not fit: flagged
+        if (threadIdx.x == 0) {
+            seg_off[blockIdx.x] = 0xFFFFFFFFu;
             atomicExch(&counters[1], 1ull);
         }
         return;
     }
-    uint32_t* __restrict__ dst = payload + at;
-    if (lane == 0) tile_off[g] = (uint32_t)at;
-    const uint32_t mode = (uint32_t)kind | (any_nan ? 4u : 0u) | (any_nz ? 8u : 0u);
-    if (kind == 0) {
-        if (lane == 0) dst[0] = 0u;
-        return;
+    if (threadIdx.x == 0) seg_off[blockIdx.x] = (uint32_t)at;
+    // the records, compacted in tile order: every warp moves the four it wrote
+#pragma unroll 1
+    for (int i = 0; i < DP_TPW; ++i) {
+        const int tile = i * DP_WARPS + warp;
+        const int words = rec_words[tile];
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(stage + tile * DP_SLOT_BYTES);
+        uint32_t* __restrict__ dst = payload + at + rec_pos[tile];
+        for (int k = lane; k < words; k += 32) dst[k] = src[k];
     }
-    if (kind == 3) {
-        if (lane == 0) { dst[0] = 3u; dst[1] = (uint32_t)base; }
-        return;
-    }
-    if (kind == 2) {
-        if (lane == 0) dst[0] = 2u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[1 + lane * 8 + j] = __float_as_uint(v[j]);
-        return;
-    }
-    // kind 1: build the record in shared memory, copy it out with coalesced words
-    uint32_t* st = stage[warp];
-    uint8_t* sb = reinterpret_cast<uint8_t*>(st);
-    if (lane == 0) { st[0] = mode; st[1] = (uint32_t)base; }
-    {
-        const int c_hi = __shfl_down_sync(FULL, code, 1);
-        if ((lane & 1) == 0) sb[8 + (lane >> 1)] = (uint8_t)(code | (c_hi << 4));
-    }
-    int pos = 24;
-    if (any_nan) { sb[pos + lane] = (uint8_t)m_nan; pos += 32; }
-    if (any_nz) { sb[pos + lane] = (uint8_t)m_nz; pos += 32; }
-    uint8_t* out = sb + pos + off;
-    if (wq == 32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            out[4 * j + 0] = (uint8_t)z[j];
-            out[4 * j + 1] = (uint8_t)(z[j] >> 8);
-            out[4 * j + 2] = (uint8_t)(z[j] >> 16);
-            out[4 * j + 3] = (uint8_t)(z[j] >> 24);
-        }
-    } else if (wq > 0) {
-        const int w = wq;                          // 1..16
-        const uint32_t a0 = z[0] | (z[1] << w), a1 = z[2] | (z[3] << w);
-        const uint32_t a2 = z[4] | (z[5] << w), a3 = z[6] | (z[7] << w);
-        const uint64_t b0 = (uint64_t)a0 | ((uint64_t)a1 << (2 * w));
-        const uint64_t b1 = (uint64_t)a2 | ((uint64_t)a3 << (2 * w));
-        uint64_t lo, hi;
-        if (w == 16) { lo = b0; hi = b1; }
-        else { lo = b0 | (b1 << (4 * w)); hi = b1 >> (64 - 4 * w); }
-        for (int i = 0; i < w && i < 8; ++i) { out[i] = (uint8_t)lo; lo >>= 8; }
-        for (int i = 8; i < w; ++i) { out[i] = (uint8_t)hi; hi >>= 8; }
-    }
-    const int end = pos + pay;
-    if (lane < ((4 - (end & 3)) & 3)) sb[end + lane] = 0;
-    __syncwarp();
-    for (int i = lane; i < words; i += 32) dst[i] = st[i];
 }
 
 // ------------------------------------------------------------------ host decode (dpack)
-static inline float dp_value(int32_t f, float p) { return (float)f / p; }
-
-// one tile; returns false on a malformed record
-static bool dunpack_tile(const uint32_t* rec, const uint32_t* pay_end, int n, float p, float* out) {
-    if (rec >= pay_end) return false;
+// one tile record at rec (n cells of it exist); returns the next record, nullptr if malformed
+static const uint8_t* dunpack_tile(const uint8_t* rec, const uint8_t* end, int n, float p,
+                                   float* out) {
+    if (rec >= end) return nullptr;
     const uint32_t mode = rec[0];
     const int kind = (int)(mode & 3u);
     const float nanv = __builtin_nanf("");
     if (kind == 0) {
         for (int c = 0; c < n; ++c) out[c] = nanv;
-        return true;
+        return rec + 4;
     }
     if (kind == 2) {
-        if (rec + DP_RAW_WORDS > pay_end) return false;
+        if (rec + DP_SLOT_BYTES > end) return nullptr;
         memcpy(out, rec + 1, sizeof(float) * (size_t)n);
-        return true;
+        return rec + DP_SLOT_BYTES;
     }
-    if (rec + 2 > pay_end) return false;
-    int32_t f = (int32_t)rec[1];
+    if (rec + 5 > end) return nullptr;
+    int32_t f;
+    memcpy(&f, rec + 1, 4);
     if (kind == 3) {
-        const float x = dp_value(f, p);
+        const float x = (float)f / p;
         for (int c = 0; c < n; ++c) out[c] = x;
-        return true;
+        return rec + 8;
     }
-    const uint8_t* b = reinterpret_cast<const uint8_t*>(rec);
-    const uint8_t* bend = reinterpret_cast<const uint8_t*>(pay_end);
-    const uint8_t* nib = b + 8;
+    if (rec + 9 > end) return nullptr;
+    uint32_t nzg;
+    memcpy(&nzg, rec + 5, 4);
+    const uint8_t* nib = rec + 9;
+    const uint8_t* pay = nib + ((__builtin_popcount(nzg) + 1) >> 1);
     const uint8_t* bm_nan = nullptr;
     const uint8_t* bm_nz = nullptr;
-    const uint8_t* pay = b + 24;
     if (mode & 4u) { bm_nan = pay; pay += 32; }
     if (mode & 8u) { bm_nz = pay; pay += 32; }
-    if (pay > bend) return false;
-    const int n_grp = (n + 7) >> 3;
-    for (int l = 0; l < n_grp; ++l) {
-        const int code = (nib[l >> 1] >> ((l & 1) * 4)) & 15;
-        const int w = dp_width_of_code(code);
-        if (pay + w > bend) return false;
+    if (pay > end) return nullptr;
+    const bool order2 = (mode & 16u) != 0;
+    int32_t d1 = 0;
+    int k = 0;                                     // index among the non-empty groups
+    for (int l = 0; l < 32; ++l) {
+        int w = 0;
+        if ((nzg >> l) & 1u) {
+            w = dp_width_of_code((nib[k >> 1] >> ((k & 1) * 4)) & 15);
+            ++k;
+        }
+        if (pay + w > end) return nullptr;
         uint32_t z[8];
         if (w == 32) {
             memcpy(z, pay, 32);
@@ -506,17 +768,22 @@ static bool dunpack_tile(const uint32_t* rec, const uint32_t* pay_end, int n, fl
             }
         }
         pay += w;
-        const uint32_t mn = bm_nan ? bm_nan[l] : 0u, mz = bm_nz ? bm_nz[l] : 0u;
         const int cnt = (n - l * 8) < 8 ? (n - l * 8) : 8;
+        if (cnt <= 0) continue;                    // groups past the end of the row: zero deltas
+        const uint32_t mn = bm_nan ? bm_nan[l] : 0u, mz = bm_nz ? bm_nz[l] : 0u;
         float* o = out + l * 8;
         for (int j = 0; j < cnt; ++j) {
             const int32_t d = (int32_t)(z[j] >> 1) ^ -(int32_t)(z[j] & 1u);
-            f = (int32_t)((uint32_t)f + (uint32_t)d);
-            o[j] = ((mn >> j) & 1u) ? nanv : (((mz >> j) & 1u) ? -0.0f : dp_value(f, p));
+            if (order2) {
+                d1 = (int32_t)((uint32_t)d1 + (uint32_t)d);
+                f = (int32_t)((uint32_t)f + (uint32_t)d1);
+            } else {
+                f = (int32_t)((uint32_t)f + (uint32_t)d);
+            }
+            o[j] = ((mn >> j) & 1u) ? nanv : (((mz >> j) & 1u) ? -0.0f : (float)f / p);
         }
-        // cells past the end of the row carry zero deltas: nothing to add
     }
-    return true;
+    return rec + (((pay - rec) + 3) & ~(ptrdiff_t)3);          // records are padded to 4 bytes
 }
 
 }  // namespace spx
@@ -584,18 +851,24 @@ int spx_unpack_field_host(const spx_pack_row* hdr, const uint16_t* codes, int64_
     return SPX_OK;
 }
 
-int64_t spx_dpack_tiles(int64_t row_len) {
-    return row_len <= 0 ? 0 : (row_len + DP_TILE - 1) / DP_TILE;
+int64_t spx_dpack_segments(int64_t row_len) {
+    return row_len <= 0 ? 0 : (row_len + DP_SEG_CELLS - 1) / DP_SEG_CELLS;
 }
 
 int64_t spx_dpack_capacity(int64_t n_rows, int64_t row_len) {
     if (n_rows <= 0 || row_len <= 0) return 0;
-    return n_rows * spx_dpack_tiles(row_len) * (int64_t)DP_RAW_WORDS * 4;
+    return n_rows * spx_dpack_segments(row_len) * (int64_t)(DP_SEG_TILES * DP_SLOT_BYTES);
 }
 
-int spx_dpack_field_dev(const float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
-                        int32_t decimals, uint32_t* tile_off, void* payload,
-                        int64_t capacity_bytes, uint64_t* counters, void* stream) {
+int64_t spx_dpack_stats_workspace(int64_t n_rows, int64_t row_len) {
+    if (n_rows <= 0 || row_len <= 0) return 0;
+    return n_rows * spx_dpack_segments(row_len) * (int64_t)sizeof(StatPart);
+}
+
+int spx_dpack_field_dev(float* fld, int64_t n_rows, int64_t row_len, int64_t ld,
+                        int32_t decimals, int32_t flags, double* stats, void* workspace,
+                        uint32_t* seg_off, void* payload, int64_t capacity_bytes,
+                        uint64_t* counters, void* stream) {
     if (n_rows < 0 || row_len < 0 || !counters) {
         set_error("dpack_field: bad argument");
         return SPX_EINVAL;
@@ -607,53 +880,76 @@ int spx_dpack_field_dev(const float* fld, int64_t n_rows, int64_t row_len, int64
         return SPX_ECUDA;
     }
     if (n_rows == 0 || row_len == 0) return SPX_OK;
-    if (!fld || !tile_off || !payload || ld < row_len || decimals < 0 || decimals > 9 ||
-        capacity_bytes < 0 || (reinterpret_cast<uintptr_t>(payload) & 3)) {
-        set_error("dpack_field: bad argument (decimals must be 0..9, payload 4-byte aligned)");
+    const bool do_round = (flags & SPX_DPACK_ROUND) != 0;
+    const bool write_back = (flags & SPX_DPACK_WRITE_BACK) != 0;
+    if (!fld || !seg_off || !payload || ld < row_len || decimals < 0 || decimals > 9 ||
+        capacity_bytes < 0 || (reinterpret_cast<uintptr_t>(payload) & 3) ||
+        (stats && !workspace) || (write_back && !do_round)) {
+        set_error("dpack_field: bad argument (decimals 0..9, payload 4-byte aligned, workspace "
+                  "with stats, write-back only with rounding)");
         return SPX_EINVAL;
     }
     unsigned long long cap_words = (unsigned long long)capacity_bytes / 4;
     if (cap_words > 0xFFFFFFFEull) cap_words = 0xFFFFFFFEull;      // offsets are 32-bit words
-    const int64_t tiles = spx_dpack_tiles(row_len);
-    const int64_t n_tiles = n_rows * tiles;
-    const int64_t n_blk = (n_tiles + DP_WARPS - 1) / DP_WARPS;
+    const int64_t segs = spx_dpack_segments(row_len);
+    const int64_t n_blk = n_rows * segs;
     if (n_blk > 0x7FFFFFFFll) {
         set_error("dpack_field: field too large for one call");
         return SPX_EINVAL;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(fld) & 15) == 0) && (ld % 4 == 0);
-    k_dpack<<<(unsigned)n_blk, DP_WARPS * 32, 0, st>>>(
-        fld, row_len, ld, tiles, n_tiles, pack_pow10(decimals), vec_ok, tile_off,
-        reinterpret_cast<uint32_t*>(payload), cap_words,
-        reinterpret_cast<unsigned long long*>(counters));
+    const float p = pack_pow10(decimals);
+    uint32_t* pay = reinterpret_cast<uint32_t*>(payload);
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counters);
+    StatPart* parts = reinterpret_cast<StatPart*>(workspace);
+    float* wb = write_back ? fld : nullptr;
+    const dim3 grid((unsigned)n_blk), block(DP_WARPS * 32);
+#define SPX_DPACK_LAUNCH(R, S)                                                                   \
+    k_dpack<R, S><<<grid, block, 0, st>>>(fld, wb, row_len, ld, segs, p, vec_ok, seg_off, pay,   \
+                                          cap_words, cnt, parts)
+    if (do_round) {
+        if (stats) SPX_DPACK_LAUNCH(true, true);
+        else SPX_DPACK_LAUNCH(true, false);
+    } else {
+        if (stats) SPX_DPACK_LAUNCH(false, true);
+        else SPX_DPACK_LAUNCH(false, false);
+    }
+#undef SPX_DPACK_LAUNCH
     SPX_CHECK_LAUNCH("k_dpack");
+    if (stats) {
+        launch_stats_final(parts, (int)segs, n_rows, stats, st);
+        SPX_CHECK_LAUNCH("k_stats_final");
+    }
     return SPX_OK;
 }
 
-int spx_dunpack_rows_host(const uint32_t* tile_off, const void* payload, int64_t payload_bytes,
+int spx_dunpack_rows_host(const uint32_t* seg_off, const void* payload, int64_t payload_bytes,
                           int64_t n_rows, int64_t row_len, int32_t decimals, float* out,
                           int64_t out_ld, int32_t n_threads) {
     if (n_rows == 0 || row_len == 0) return SPX_OK;
-    if (!tile_off || !payload || !out || out_ld < row_len || decimals < 0 || decimals > 9 ||
+    if (!seg_off || !payload || !out || out_ld < row_len || decimals < 0 || decimals > 9 ||
         payload_bytes < 0) {
         set_error("dunpack_rows: bad argument");
         return SPX_EINVAL;
     }
     const float p = pack_pow10(decimals);
-    const int64_t tiles = spx_dpack_tiles(row_len);
-    const uint32_t* pay = reinterpret_cast<const uint32_t*>(payload);
-    const uint32_t* pay_end = pay + payload_bytes / 4;
+    const int64_t segs = spx_dpack_segments(row_len);
+    const uint8_t* pay = reinterpret_cast<const uint8_t*>(payload);
+    const uint8_t* pay_end = pay + payload_bytes;
     int bad = 0;
     auto work = [&](int part, int n_parts) {
         for (int64_t r = part; r < n_rows; r += n_parts) {
-            const uint32_t* offs = tile_off + r * tiles;
             float* o = out + r * out_ld;
-            for (int64_t t = 0; t < tiles; ++t) {
-                const int64_t rest = row_len - t * DP_TILE;
-                const int n = rest < DP_TILE ? (int)rest : DP_TILE;
-                if (offs[t] == 0xFFFFFFFFu ||
-                    !dunpack_tile(pay + offs[t], pay_end, n, p, o + t * DP_TILE))
-                    __atomic_store_n(&bad, 1, __ATOMIC_RELAXED);
+            for (int64_t sg = 0; sg < segs; ++sg) {
+                const uint32_t at = seg_off[r * segs + sg];
+                const uint8_t* rec = (at == 0xFFFFFFFFu || (int64_t)at * 4 > payload_bytes)
+                                         ? nullptr : pay + (int64_t)at * 4;
+                for (int64_t c0 = sg * DP_SEG_CELLS;
+                     rec && c0 < row_len && c0 < (sg + 1) * DP_SEG_CELLS; c0 += DP_TILE) {
+                    const int64_t rest = row_len - c0;
+                    rec = dunpack_tile(rec, pay_end, rest < DP_TILE ? (int)rest : DP_TILE, p, o + c0);
+                }
+                if (!rec) __atomic_store_n(&bad, 1, __ATOMIC_RELAXED);
             }
         }
     };

@@ -93,14 +93,17 @@ class PendingChunk:
         self.done_event = torch.cuda.Event()
         self.done_event.record(torch.cuda.current_stream(engine.device))
 
-    def _output_stage(self):
+    def _output_stage(self, labels=None):
         eng = self.engine
-        if self._d_field_stats is not None or (
-                self.round_decimals is None and not self.want_field_stats):
-            return
+        if labels is None:
+            if self._d_field_stats is not None or (
+                    self.round_decimals is None and not self.want_field_stats):
+                return
+            self._d_field_stats = {}
         dec = -1 if self.round_decimals is None else int(self.round_decimals)
-        self._d_field_stats = {}
         for lab, t in self.flds.items():
+            if labels is not None and lab not in labels:
+                continue
             n_rows, row_len = t.shape
             st = torch.empty((5, n_rows), dtype=_F64, device=eng.device)
             for r0 in range(0, n_rows, 65535):
@@ -116,8 +119,84 @@ class PendingChunk:
                 st[:, r0:r1] = sub
             self._d_field_stats[lab] = st
 
+    def start_packed(self):
+        """Queue the writer's output stage and the compact download of every field; returns a
+        handle for ``finish_packed``.  Rounded float32 fields that are large enough go through
+        ONE pass over the unrounded field (np.round + per-step statistics + delta encoding,
+        spx_dpack_field_dev with SPX_DPACK_ROUND; the device copy stays unrounded) and cross
+        PCIe in the delta transport form; everything else takes the separate rounding /
+        statistics kernel and comes back as an array.  Nothing here waits for the GPU, so the
+        next chunk can be submitted before ``finish_packed`` is called."""
+        eng = self.engine
+        with torch.cuda.device(eng.device):
+            eng._begin_call()
+            for fn in self.deferred:
+                fn()
+            self.deferred = []
+            tickets = {}
+            if self._d_field_stats is None and self.round_decimals is not None:
+                dec = int(self.round_decimals)
+                self._d_field_stats = {}
+                rest = []
+                for lab, t in self.flds.items():
+                    dl = eng._packed_downloader(t, dec, depth=max(2, len(self.flds)))
+                    if dl is None or dl.codec != 'delta':
+                        rest.append(lab)
+                        continue
+                    st = (torch.empty((5, t.shape[0]), dtype=_F64, device=eng.device)
+                          if self.want_field_stats else None)
+                    tickets[lab] = (dl, dl.start(t, dec, round_here=True, stats=st,
+                                                 write_back=False))
+                    eng._count('launches', 1 if st is None else 2)
+                    if st is not None:
+                        self._d_field_stats[lab] = st
+                if rest:
+                    self._output_stage(labels=rest)
+                    for lab in rest:
+                        dl = eng._packed_downloader(self.flds[lab], dec,
+                                                    depth=max(2, len(self.flds)))
+                        if dl is not None:
+                            tickets[lab] = (dl, dl.start(self.flds[lab], dec))
+                if not self.want_field_stats:
+                    self._d_field_stats = None
+            else:
+                self._output_stage()
+                for lab, t in self.flds.items():
+                    dl = eng._packed_downloader(t, self.round_decimals,
+                                                depth=max(2, len(self.flds)))
+                    if dl is not None:
+                        tickets[lab] = (dl, dl.start(t, self.round_decimals))
+            hs = ev = None
+            if self._d_field_stats and self.field_stats is None:
+                hs = {lab: eng._fetch_async(t) for lab, t in self._d_field_stats.items()}
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(eng.device))
+            return dict(tickets=tickets, hs=hs, ev=ev)
+
+    def finish_packed(self, handle):
+        """({label: transfer.DeltaField / PackedField over a downloader slot -- the consumer
+        calls ``.release()`` -- or ndarray}, problem_steps)."""
+        eng = self.engine
+        with torch.cuda.device(eng.device):
+            if handle['hs'] is not None:
+                handle['ev'].synchronize()
+                self.field_stats = {lab: h.numpy().copy() for lab, h in handle['hs'].items()}
+            out = {}
+            tickets = handle['tickets']
+            for lab, t in self.flds.items():
+                if lab in tickets:
+                    dl, tk = tickets[lab]
+                    pf = dl.wait(tk)
+                    pf.release = (lambda dl=dl, tk=tk: dl.release(tk))
+                    out[lab] = pf
+                else:
+                    out[lab] = t.cpu().numpy()
+            return out, self.problem_steps
+
     def result(self, to_host=True):
         eng = self.engine
+        if to_host == 'packed':
+            return self.finish_packed(self.start_packed())
         with torch.cuda.device(eng.device):
             eng._begin_call()
             n0 = eng.total_launches
@@ -137,25 +216,6 @@ class PendingChunk:
                 return self.flds, self.problem_steps
             torch.cuda.current_stream(eng.device).synchronize()
             out = {}
-            if to_host == 'packed':
-                # rounded f32 fields stay in their 2-byte form on the host
-                # (transfer.PackedField over a downloader slot; the consumer calls
-                # ``.release()``); anything else comes back as an array
-                tickets = {}
-                for lab, t in self.flds.items():
-                    dl = eng._packed_downloader(t, self.round_decimals,
-                                                depth=max(2, len(self.flds)))
-                    if dl is not None:
-                        tickets[lab] = (dl, dl.start(t, self.round_decimals))
-                for lab, t in self.flds.items():
-                    if lab in tickets:
-                        dl, tk = tickets[lab]
-                        pf = dl.wait(tk)
-                        pf.release = (lambda dl=dl, tk=tk: dl.release(tk))
-                        out[lab] = pf
-                    else:
-                        out[lab] = t.cpu().numpy()
-                return out, self.problem_steps
             for lab, t in self.flds.items():
                 dl = eng._packed_downloader(t, self.round_decimals)
                 # rounded f32 fields cross PCIe as 16-bit codes (transfer.py), bit-exact
@@ -262,6 +322,7 @@ class ChunkEngine:
         # rounded float32 fields are downloaded as 16-bit codes and decoded on the host
         self.packed_download = True
         self._dl = None
+        self.transport = None          # codec of the packed download (None: transfer.default_codec())
         self.threaded_upload = True
         self._uploader = None
 
@@ -518,9 +579,10 @@ class ChunkEngine:
             return None
         dl = self._dl
         if (dl is None or dl.row_len != t.shape[1] or dl.max_rows < t.shape[0]
-                or len(dl.slots) < depth):
+                or len(dl.slots) < depth or (self.transport and dl.codec != self.transport)):
             from .transfer import PackedDownloader
-            dl = self._dl = PackedDownloader(self.device, t.shape[0], t.shape[1], depth=depth)
+            dl = self._dl = PackedDownloader(self.device, t.shape[0], t.shape[1], depth=depth,
+                                             codec=self.transport)
         return dl
 
     def round_and_stats(self, fld, decimals=None):

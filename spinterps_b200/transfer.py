@@ -56,7 +56,7 @@ class PackedDownloader:
         self.n_threads = int(n_threads)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.stride = int(self.lib.spx_pack_stride(self.row_len))
-        self.tiles = int(self.lib.spx_dpack_tiles(self.row_len))
+        self.segs = int(self.lib.spx_dpack_segments(self.row_len))
         self.slots = []
         self._u16 = None                 # fallback downloader (allocated on first use)
         self.fallbacks = 0               # fields that did not fit their delta buffer
@@ -66,7 +66,7 @@ class PackedDownloader:
             self.capacity = max(4096, min(worst, (cap + 4095) // 4096 * 4096))
             self.pay_stream = torch.cuda.Stream(self.device)
             self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
-            n_off = self.max_rows * self.tiles
+            n_off = self.max_rows * self.segs
             for _ in range(self.depth):
                 self.slots.append(dict(
                     d_off=torch.empty(n_off, dtype=torch.int32, device=self.device),
@@ -95,23 +95,41 @@ class PackedDownloader:
         return int(n_rows) * (16 + 2 * self.stride)
 
     # ------------------------------------------------------------------ start
-    def start(self, fld, decimals):
+    def start(self, fld, decimals, round_here=False, stats=None, write_back=True):
+        """Queue encoder + copies for ``fld`` (device float32 [n_rows, row_len], rounded to
+        ``decimals`` places).  codec 'delta' only: ``round_here=True`` takes the UNROUNDED
+        field and makes the call the whole output stage of the writer in one pass --
+        np.round, the per-step statistics into ``stats`` (device float64 [5, n_rows], or
+        None) and the encoding; ``write_back`` also leaves the rounded values in ``fld``."""
         assert fld.dtype == torch.float32 and fld.dim() == 2 and fld.stride(1) == 1
         n_rows, row_len = fld.shape
         assert n_rows <= self.max_rows and row_len == self.row_len
+        assert self.codec == 'delta' or (not round_here and stats is None)
         k = self._next
         s = self.slots[k]
         assert not s['busy'], 'more tickets in flight than slots'
         self._next = (k + 1) % len(self.slots)
         main = torch.cuda.current_stream(self.device)
         if self.codec == 'delta':
+            flags = (_lib.SPX_DPACK_ROUND if round_here else 0) | (
+                _lib.SPX_DPACK_WRITE_BACK if (round_here and write_back) else 0)
+            ws = None
+            if stats is not None:
+                assert stats.dtype == torch.float64 and tuple(stats.shape) == (5, n_rows) \
+                    and stats.is_contiguous()
+                ws = torch.empty(max(1, int(self.lib.spx_dpack_stats_workspace(n_rows, row_len))),
+                                 dtype=torch.uint8, device=self.device)
             _lib.check(self.lib.spx_dpack_field_dev(
-                C.c_void_p(fld.data_ptr()), n_rows, row_len, fld.stride(0), int(decimals),
+                C.c_void_p(fld.data_ptr()), n_rows, row_len, fld.stride(0), int(decimals), flags,
+                C.c_void_p(stats.data_ptr() if stats is not None else None),
+                C.c_void_p(ws.data_ptr() if ws is not None else None),
                 C.c_void_p(s['d_off'].data_ptr()), C.c_void_p(s['d_pay'].data_ptr()),
                 self.capacity, C.c_void_p(s['d_cnt'].data_ptr()),
                 C.c_void_p(main.cuda_stream)), 'dpack_field')
+            s['rounded_in_place'] = bool(round_here and write_back)
+            s['round_here'] = bool(round_here)
             self.copy_stream.wait_stream(main)
-            n_off = n_rows * self.tiles
+            n_off = n_rows * self.segs
             with torch.cuda.stream(self.copy_stream):
                 s['h_cnt'].copy_(s['d_cnt'], non_blocking=True)
                 s['h_off'][:n_off].copy_(s['d_off'][:n_off], non_blocking=True)
@@ -142,7 +160,7 @@ class PackedDownloader:
         torch.cuda.set_device(self.device)
         s['ev_meta'].synchronize()
         nbytes = int(s['h_cnt'][0]) * 4
-        meta = 16 + s['n_rows'] * self.tiles * 4
+        meta = 16 + s['n_rows'] * self.segs * 4
         if int(s['h_cnt'][1]) != 0 or nbytes > self.capacity:
             s['overflow'] = True
             self.d2h_bytes += meta
@@ -172,13 +190,24 @@ class PackedDownloader:
                                                  depth=1, n_threads=self.n_threads, codec='u16')
                 u = self._u16
                 d0 = u.d2h_bytes
-                pf = u.wait(u.start(s['fld'], s['decimals']))
+                fld = s['fld']
+                if s['round_here'] and not s['rounded_in_place']:
+                    # the fused pass left the field unrounded: round it now (np.round)
+                    ws = torch.empty(max(1, int(self.lib.spx_round_stats_workspace(
+                        fld.shape[0], fld.shape[1]))), dtype=torch.uint8, device=self.device)
+                    tmp = torch.empty((5, fld.shape[0]), dtype=torch.float64, device=self.device)
+                    _lib.check(self.lib.spx_round_stats_dev(
+                        C.c_void_p(fld.data_ptr()), 0, fld.shape[0], fld.shape[1], fld.stride(0),
+                        s['decimals'], C.c_void_p(tmp.data_ptr()), C.c_void_p(ws.data_ptr()),
+                        C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                        'round_stats')
+                pf = u.wait(u.start(fld, s['decimals']))
                 self.d2h_bytes += u.d2h_bytes - d0
                 s['fld'] = None
                 return pf
             s['ev'].synchronize()
             s['fld'] = None
-            offs = s['h_off'].numpy()[:n_rows * self.tiles].view(np.uint32)
+            offs = s['h_off'].numpy()[:n_rows * self.segs].view(np.uint32)
             pay = s['h_pay'].numpy()[:s['pay_bytes']]
             return DeltaField(self.lib, offs, pay, n_rows, self.row_len, s['decimals'])
         s['ev'].synchronize()
@@ -275,7 +304,7 @@ class DeltaField:
     def __init__(self, lib, offs, payload, n_rows, row_len, decimals):
         self.lib, self.offs, self.payload = lib, offs, payload
         self.row_len, self.decimals = int(row_len), int(decimals)
-        self.tiles = int(lib.spx_dpack_tiles(self.row_len))
+        self.segs = int(lib.spx_dpack_segments(self.row_len))
         self.shape = (int(n_rows), self.row_len)
         self.dtype = np.dtype(np.float32)
         self.raw = {}                        # no whole row travels raw in this form
@@ -284,7 +313,7 @@ class DeltaField:
 
     def _decode(self, r0, n, out_ptr, out_ld, n_threads):
         _lib.check(self.lib.spx_dunpack_rows_host(
-            self.offs[r0 * self.tiles:].ctypes.data, self.payload.ctypes.data,
+            self.offs[r0 * self.segs:].ctypes.data, self.payload.ctypes.data,
             self.payload.nbytes, n, self.row_len, self.decimals, out_ptr, out_ld,
             int(n_threads)), 'dunpack_rows')
 

@@ -12,7 +12,7 @@ from tests import dpack_ref
 
 def c_decode(offs, payload, n_rows, row_len, decimals, n_threads=1, row0=0):
     lib = _lib.load()
-    tiles = lib.spx_dpack_tiles(row_len)
+    tiles = lib.spx_dpack_segments(row_len)
     out = np.full((n_rows, row_len + 3), 7.0, dtype=np.float32)
     o = offs[row0 * tiles:]
     _lib.check(lib.spx_dunpack_rows_host(
@@ -27,7 +27,7 @@ def same_bits(a, b):
                           np.ascontiguousarray(b).view(np.uint32))
 
 
-@pytest.mark.parametrize('row_len', [1, 7, 256, 300, 1000])
+@pytest.mark.parametrize('row_len', [1, 7, 256, 300, 1000, 8192 + 700])
 @pytest.mark.parametrize('decimals', [0, 2, 3])
 def test_decoder_matches_format(row_len, decimals):
     rng = np.random.default_rng(row_len * 10 + decimals)
@@ -63,12 +63,12 @@ def test_rate_on_a_smooth_field():
 
 def test_decoder_rejects_bad_offsets():
     rng = np.random.default_rng(1)
-    fld = dpack_ref.synth_field(rng, 2, 600, 2)
+    fld = dpack_ref.synth_field(rng, 2, 600, 2, nan_frac=0.0)
     offs, payload = dpack_ref.encode(fld, 2)
     lib = _lib.load()
     out = np.empty_like(fld)
     bad = offs.copy()
-    bad[1] = 0xFFFFFFFF
+    bad[1] = 0xFFFFFFFF            # second row
     assert lib.spx_dunpack_rows_host(bad.ctypes.data, payload.ctypes.data, payload.nbytes, 2, 600, 2,
                                      out.ctypes.data, 600, 1) != 0
     assert lib.spx_dunpack_rows_host(offs.ctypes.data, payload.ctypes.data, 8, 2, 600, 2,

@@ -201,72 +201,140 @@ def test_packed_download_is_bit_exact(decimals, scale, special, codec):
     assert dl.d2h_bytes >= T * 2 * G
 
 
-@pytest.mark.parametrize('row_len,pitch', [(1000, 1000), (777, 779), (256, 256), (5, 8)])
-def test_delta_encoder_follows_the_format(row_len, pitch):
-    """spx_dpack_field_dev against the plain-Python statement of the record format
-    (tests/dpack_ref.py): the records decode to the identical floats with the Python decoder
-    AND the C decoder, and they take exactly the bytes the Python encoder needs (NaN cells
-    and tiles, -0.0, off-lattice values -> raw tiles, constant tiles, ragged and unaligned
-    rows); a payload buffer that is too small is reported, never overrun."""
+def _dpack(d, row_len, decimals, flags=0, stats=False, cap=None):
+    """spx_dpack_field_dev on a device tensor; returns (counters, seg_off, payload, stats)."""
     import ctypes as C
     import torch
     from spinterps_b200 import _lib
-    from tests import dpack_ref
     lib = _lib.load()
+    n_rows, pitch = d.shape
+    segs = int(lib.spx_dpack_segments(row_len))
+    if cap is None:
+        cap = int(lib.spx_dpack_capacity(n_rows, row_len))
+    offs = torch.zeros(n_rows * segs, dtype=torch.int32, device='cuda')
+    pay = torch.full((int(lib.spx_dpack_capacity(n_rows, row_len)) + 64,), 0xAB,
+                     dtype=torch.uint8, device='cuda')
+    cnt = torch.full((2,), -1, dtype=torch.int64, device='cuda')
+    st = torch.zeros((5, n_rows), dtype=torch.float64, device='cuda') if stats else None
+    ws = torch.empty(max(1, int(lib.spx_dpack_stats_workspace(n_rows, row_len))),
+                     dtype=torch.uint8, device='cuda') if stats else None
+    _lib.check(lib.spx_dpack_field_dev(
+        C.c_void_p(d.data_ptr()), n_rows, row_len, pitch, decimals, flags,
+        C.c_void_p(st.data_ptr() if stats else None), C.c_void_p(ws.data_ptr() if stats else None),
+        C.c_void_p(offs.data_ptr()), C.c_void_p(pay.data_ptr()), cap, C.c_void_p(cnt.data_ptr()),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'dpack')
+    torch.cuda.synchronize()
+    return (cnt.cpu().numpy(), offs.cpu().numpy().view(np.uint32), pay.cpu().numpy(),
+            st.cpu().numpy() if stats else None)
+
+
+def _c_decode(offs, used, n_rows, row_len, decimals):
+    from spinterps_b200 import _lib
+    out = np.empty((n_rows, row_len), dtype=np.float32)
+    _lib.check(_lib.load().spx_dunpack_rows_host(
+        offs.ctypes.data, used.ctypes.data, used.nbytes, n_rows, row_len, decimals,
+        out.ctypes.data, row_len, 2), 'dunpack')
+    return out
+
+
+@pytest.mark.parametrize('row_len,pitch', [(1000, 1000), (777, 779), (256, 256), (5, 8),
+                                           (8192 + 300, 8192 + 300), (3 * 8192, 3 * 8192)])
+def test_delta_encoder_follows_the_format(row_len, pitch):
+    """spx_dpack_field_dev against the plain-Python statement of the record format
+    (tests/dpack_ref.py): the records decode to the identical floats with the Python decoder
+    AND the C decoder, and every segment takes exactly the bytes the Python encoder needs
+    (NaN cells and tiles, -0.0, off-lattice values -> raw tiles, constant tiles, first and
+    second differences, ragged and unaligned rows); a payload buffer that is too small is
+    reported, never overrun."""
+    import torch
+    from tests import dpack_ref
     rng = np.random.default_rng(row_len)
-    n_rows = 9
+    n_rows = 9 if row_len < 5000 else 4
     fld = dpack_ref.synth_field(rng, n_rows, row_len, 2)
     fld[1, ::5][~np.isnan(fld[1, ::5])] = -0.0
     fld[3, :] = np.float32(12.5)
     if row_len >= 300:
         fld[2, 10] = np.float32(1.23456789)
         fld[2, 290] = np.inf
-        fld[4, 260:] = rng.normal(0, 1e6, row_len - 260).astype(np.float32).round(2)
-        fld[5, 100:140] = np.float32(3.0e9)           # |q| beyond int32
+        fld[n_rows - 1, 260:] = rng.normal(0, 1e6, row_len - 260).astype(np.float32).round(2)
+        fld[0, 100:140] = np.float32(3.0e9)           # |q| beyond int32
+    if row_len >= 1000:
+        # smooth, fully valid tiles: second differences win
+        fld[2, 512:1000] = np.round(np.linspace(0, 300, 488) ** 1.5, 2).astype(np.float32)
     want_off, want_pay = dpack_ref.encode(fld, 2)
+    want_words = dpack_ref.segment_sizes(fld, 2)
     d = torch.full((n_rows, pitch), 99.0, dtype=torch.float32, device='cuda')
     d[:, :row_len] = torch.from_numpy(fld).cuda()
-    tiles = int(lib.spx_dpack_tiles(row_len))
-    cap = int(lib.spx_dpack_capacity(n_rows, row_len))
-    offs = torch.zeros(n_rows * tiles, dtype=torch.int32, device='cuda')
-    pay = torch.full((cap + 64,), 0xAB, dtype=torch.uint8, device='cuda')
-    cnt = torch.full((2,), -1, dtype=torch.int64, device='cuda')
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.spx_dpack_field_dev(C.c_void_p(d.data_ptr()), n_rows, row_len, pitch, 2,
-                                       C.c_void_p(offs.data_ptr()), C.c_void_p(pay.data_ptr()),
-                                       cap, C.c_void_p(cnt.data_ptr()), st), 'dpack')
-    torch.cuda.synchronize()
-    h_cnt = cnt.cpu().numpy()
-    assert h_cnt[1] == 0 and h_cnt[0] * 4 == want_pay.nbytes
-    h_off = offs.cpu().numpy().view(np.uint32)
-    h_pay = pay.cpu().numpy()
-    assert np.all(h_pay[h_cnt[0] * 4:] == 0xAB)                  # nothing past the records
-    used = h_pay[:h_cnt[0] * 4].copy()
+    cnt, offs, pay, _ = _dpack(d, row_len, 2)
+    assert cnt[1] == 0 and cnt[0] * 4 == want_pay.nbytes
+    assert np.all(pay[cnt[0] * 4:] == 0xAB)                      # nothing past the records
+    used = pay[:cnt[0] * 4].copy()
     ok = ~np.isnan(fld)
-    got_py = dpack_ref.decode(h_off, used, n_rows, row_len, 2)
-    got_c = np.empty_like(fld)
-    _lib.check(lib.spx_dunpack_rows_host(h_off.ctypes.data, used.ctypes.data, used.nbytes, n_rows,
-                                         row_len, 2, got_c.ctypes.data, row_len, 2), 'dunpack')
-    for got in (got_py, got_c):
+    for got in (dpack_ref.decode(offs, used, n_rows, row_len, 2),
+                _c_decode(offs, used, n_rows, row_len, 2)):
         assert np.array_equal(np.isnan(got), ~ok)
         assert np.array_equal(got.view(np.uint32)[ok], fld.view(np.uint32)[ok])
-    # record sizes tile by tile (the order in the payload is free)
-    def sizes(o, total):
-        srt = np.sort(o.astype(np.int64))
-        return dict(zip(srt.tolist(), np.diff(np.append(srt, total)).tolist()))
-    sz_g, sz_w = sizes(h_off, h_cnt[0]), sizes(want_off, want_pay.nbytes // 4)
-    assert [sz_g[int(o)] for o in h_off] == [sz_w[int(o)] for o in want_off]
+    # segment by segment the same bytes as the Python encoder (their order in the payload is free)
+    segs = offs.size // n_rows
+    for i in range(offs.size):
+        a, b = int(offs[i]) * 4, int(want_off[i]) * 4
+        n = int(want_words[i]) * 4
+        assert np.array_equal(used[a:a + n], want_pay[b:b + n]), (i // segs, i % segs)
+    if row_len >= 1000:
+        assert (want_pay[[int(o) * 4 for o in want_off]] & 3 != 0).any()
     # too small a buffer: flagged, the needed size still reported, no write past the end
     small = (want_pay.nbytes // 2) // 4 * 4
-    pay.fill_(0xAB)
-    _lib.check(lib.spx_dpack_field_dev(C.c_void_p(d.data_ptr()), n_rows, row_len, pitch, 2,
-                                       C.c_void_p(offs.data_ptr()), C.c_void_p(pay.data_ptr()),
-                                       small, C.c_void_p(cnt.data_ptr()), st), 'dpack')
-    torch.cuda.synchronize()
-    h_cnt = cnt.cpu().numpy()
-    assert h_cnt[1] == 1 and h_cnt[0] * 4 == want_pay.nbytes
-    assert np.all(pay.cpu().numpy()[small:] == 0xAB)
-    assert (offs.cpu().numpy().view(np.uint32) == 0xFFFFFFFF).any()
+    cnt, offs2, pay2, _ = _dpack(d, row_len, 2, cap=small)
+    assert cnt[0] * 4 == want_pay.nbytes
+    if offs.size > 1:
+        assert cnt[1] == 1 and (offs2 == 0xFFFFFFFF).any()
+    assert np.all(pay2[small:] == 0xAB)
+
+
+@pytest.mark.parametrize('decimals,write_back', [(2, False), (2, True), (0, False), (3, True)])
+def test_fused_output_stage_matches_the_separate_kernels(decimals, write_back):
+    """SPX_DPACK_ROUND: one pass over the UNROUNDED field = np.round (bit-exact, incl. -0.0,
+    NaN, inf and values beyond int32) + the per-step statistics of spx_round_stats_dev + the
+    encoding."""
+    import torch
+    from spinterps_b200 import _lib
+    from spinterps_b200.engine import ChunkEngine
+    eng = ChunkEngine()
+    rng = np.random.default_rng(decimals)
+    T, G = 21, 20011
+    x = np.linspace(0, 40, G)
+    f = np.stack([8 * np.sin(x * rng.uniform(0.5, 2)) * rng.uniform(0, 2) + rng.uniform(-1, 4)
+                  for _ in range(T)]).astype(np.float32)
+    f[np.abs(f) < 0.004] *= -1.0                      # some round to -0.0
+    f[rng.random(f.shape) < 0.03] = np.nan
+    f[4] = np.nan
+    f[6, 100] = np.inf
+    f[7, 5000:5100] = 4.0e9
+    f[8, 300:900] = 0.0
+    exp = np.round(f, decimals)
+    d_ref = torch.from_numpy(f).cuda()
+    st_ref = eng.round_and_stats(d_ref, decimals)
+    assert np.array_equal(d_ref.cpu().numpy().view(np.uint32)[~np.isnan(exp)],
+                          exp.view(np.uint32)[~np.isnan(exp)])
+    d = torch.from_numpy(f).cuda()
+    flags = _lib.SPX_DPACK_ROUND | (_lib.SPX_DPACK_WRITE_BACK if write_back else 0)
+    cnt, offs, pay, st = _dpack(d, G, decimals, flags=flags, stats=True)
+    assert cnt[1] == 0
+    got = _c_decode(offs, pay[:cnt[0] * 4].copy(), T, G, decimals)
+    ok = ~np.isnan(exp)
+    assert np.array_equal(np.isnan(got), ~ok)
+    assert np.array_equal(got.view(np.uint32)[ok], exp.view(np.uint32)[ok])
+    assert (np.signbit(exp) & (exp == 0)).any()
+    after = d.cpu().numpy()
+    want_after = exp if write_back else f
+    assert np.array_equal(after.view(np.uint32)[ok], want_after.view(np.uint32)[ok])
+    assert np.array_equal(st[4], st_ref[4])                       # finite counts
+    assert np.array_equal(st[[0, 2]], st_ref[[0, 2]], equal_nan=True)   # min / max
+    rows = np.isfinite(st_ref).all(axis=0)                        # rows without inf / all-NaN
+    assert rows.sum() >= T - 3
+    assert np.all(np.abs(st[:, rows] - st_ref[:, rows])
+                  <= 1e-11 * np.maximum(1.0, np.abs(st_ref[:, rows])))
+    assert np.isnan(st[:4, 4]).all() and st[4, 4] == 0 and st_ref[4, 4] == 0
 
 
 def test_delta_download_of_a_smooth_field_is_small():
