@@ -625,11 +625,14 @@ def run_gpu(args):
         sampler.start()
     eng.profile_gemm = True
     eng.kernel_events = []
+    eng.solve_ms = []
     l0 = eng.total_launches
     ms, ms_wall = timed(run_resident, args.steps)
     launches_timed = eng.total_launches - l0
     eng.collect_profile()
     kernel_events = eng.kernel_events
+    solve_ms = list(eng.solve_ms)
+    sparse_job = next((j for j in eng._fast_jobs.values() if j['cfg'].sparse.n_comp > 0), None)
     eng.profile_gemm = False
     torch.cuda.synchronize()
     engine_stats = dict(eng.stats)
@@ -794,9 +797,24 @@ def run_gpu(args):
                         'ms_per_step': ms_e2e_raw / n_raw,
                         'd2h_bytes_per_step': int(cell_steps * 4),
                         'note': 'same pipeline, f32 field copied to pinned host memory'}},
+            'solve_phase': {
+                'ms_per_step': (sum(solve_ms) / len(solve_ms)) if solve_ms else None,
+                'method': ('sparse covariance form: the variogram is constant beyond its range, '
+                           'the OK matrix is F 11\' - C with C block diagonal over %d clusters of '
+                           'stations closer than the range (largest: %d stations); one warp per '
+                           'time step, O(n_stn) (spx_krige_sparse_ok_dev)'
+                           % (sparse_job['cfg'].sparse.n_comp, sparse_job['cfg'].sparse.max_size))
+                if sparse_job is not None else
+                'Ut = Bt.G on the FP64 tensor cores + LDL^T downdate of one r x r block per '
+                'availability group (spx_krige_downdate_dev)',
+                'note': 'CUDA events around the solve phase of every timed chunk (uploads -> '
+                        'coefficients ready); SPX_SPARSE_SOLVE=0 selects the downdate'},
             'gpu_launches': int(launches_timed),
             'roofline': roofline(dom),
-            'step_breakdown': {'ms_per_step_traced': ms_tr / n_tr, 'entry_points': breakdown},
+            'step_breakdown': {'ms_per_step_traced': ms_tr / n_tr, 'entry_points': breakdown,
+                               'note': 'separate traced pass through the Python-planned path '
+                                       '(downdated dense systems), events around every entry '
+                                       'point; the timed region above uses the native submit'},
             'dense_path': {
                 'note': 'same workload with the local estimator disabled: every estimate goes '
                         'through the fused variogram-fill + DMMA contraction',

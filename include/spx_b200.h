@@ -629,6 +629,39 @@ int spx_local_set_bulk(int on);
  * n_slots slots; a slot is reused only after its estimate has finished.
  * Nothing here allocates per chunk.  Steps the path does not handle itself (no station,
  * one station, interp_steps_flag false) are only counted; the caller fills those rows. */
+/* Sparse-covariance form of the ordinary-kriging systems of a compactly supported
+ * variogram (Nug + Sph / Lin terms).  Beyond the largest range every variogram value is the
+ * constant F, so the station matrix of interp/steps.py:199-216 is F 11' - C with C = F - vg
+ * SPARSE, and the system [F 11' - C, 1; 1', 0] [x; nu] = [z; 0] reduces to
+ * x = C^-1 (nu 1 - z), nu = (1' C^-1 z) / (1' C^-1 1).  C is block diagonal over the connected
+ * components of the graph "stations closer than the range"; with a missing station the
+ * blocks simply lose a row and a column.  When every component is small
+ * (<= SPX_SPARSE_MAX_COMP stations) a time step costs O(n_stn) instead of a dense
+ * factorisation: one warp per step solves the components (Cholesky in registers / local
+ * memory), reduces nu and writes the coefficient row.  Same linear system, same solution
+ * (to rounding) as the dense path. */
+#define SPX_SPARSE_MAX_COMP 8
+typedef struct spx_sparse_cov {
+    int32_t n_comp;              /* 0 = not used */
+    int32_t max_size;            /* largest component */
+    const int32_t* comp_off;     /* device [n_comp + 1]: members of component c are        */
+    const int32_t* comp_stn;     /* device [n_stn]:       comp_stn[comp_off[c] .. comp_off[c+1]) */
+    const int64_t* blk_off;      /* device [n_comp]: offset of the component's s x s block  */
+    double* blk;                 /* device: C = F - vg(d_ij), row-major per component       */
+} spx_sparse_cov;
+/* Fill sp->blk from the station coordinates (diagonal: vg(0), i.e. the nugget -- quirk Q1). */
+int spx_sparse_cov_blocks_dev(const double* stn_x, const double* stn_y, const spx_sparse_cov* sp,
+                              const spx_vg* vg, double min_vg_val, double base_f, void* stream);
+/* One warp per coefficient row: row i is the solution for time step row_step[i] of data
+ * (device [*, n_stn] pitch ld, NaN = missing).  Writes coef [n_rows, kpad] row-major (columns
+ * 0..n_stn: x and nu; the caller zeroes the padding), the transposed copy coef_t [kpad,
+ * coef_t_ld] (may be NULL), base[i] = base_f * sum(x) + nu, and adds the number of rows whose
+ * Cholesky failed to *info (device int32).  scratch: 2 * n_rows * n_stn doubles. */
+int spx_krige_sparse_ok_dev(const double* data, int32_t n_stn, int64_t ld, const int32_t* row_step,
+                            int64_t n_rows, const spx_sparse_cov* sp, double base_f, int32_t kpad,
+                            double* coef, double* coef_t, int64_t coef_t_ld, double* base,
+                            double* scratch, int32_t* info, void* stream);
+
 typedef struct spx_fast_cfg {
     int32_t n_stn, n_border, kpad;
     int32_t max_steps;           /* largest chunk the job will see */
@@ -648,6 +681,8 @@ typedef struct spx_fast_cfg {
     int32_t solve_stream;        /* 1: solve phase on the job's own high-priority stream (runs
                                     beside the previous chunk's estimate), 0: on the caller's
                                     stream in front of the estimate */
+    spx_sparse_cov sparse;       /* n_comp > 0 (estimator 0, n_border 1): the solve phase is
+                                    spx_krige_sparse_ok_dev instead of Ut = Bt.G + downdate */
 } spx_fast_cfg;
 
 typedef struct spx_fast_result {

@@ -172,6 +172,14 @@ SPX_PACK_U16, SPX_PACK_RAW = 0, 2
 SPX_DPACK_ROUND, SPX_DPACK_WRITE_BACK = 1, 2
 
 
+class spx_sparse_cov(C.Structure):
+    _fields_ = [('n_comp', C.c_int32), ('max_size', C.c_int32), ('comp_off', C.c_void_p),
+                ('comp_stn', C.c_void_p), ('blk_off', C.c_void_p), ('blk', C.c_void_p)]
+
+
+SPX_SPARSE_MAX_COMP = 8
+
+
 class spx_fast_cfg(C.Structure):
     _fields_ = [('n_stn', C.c_int32), ('n_border', C.c_int32), ('kpad', C.c_int32),
                 ('max_steps', C.c_int32), ('n_slots', C.c_int32), ('min_systems', C.c_int32),
@@ -179,7 +187,7 @@ class spx_fast_cfg(C.Structure):
                 ('lambda_bound', C.c_double), ('lambda_tol', C.c_double),
                 ('estimator', C.c_int32), ('want_coef_t', C.c_int32), ('base_f', C.c_double),
                 ('local', spx_local), ('gemm', spx_gemm), ('profile', C.c_int32),
-                ('solve_stream', C.c_int32)]
+                ('solve_stream', C.c_int32), ('sparse', spx_sparse_cov)]
 
 
 class spx_fast_result(C.Structure):
@@ -308,6 +316,12 @@ _SIGS = {
                                         C.c_void_p, C.c_int64, C.c_int32]),
     'spx_lambda_check_dev': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    'spx_sparse_cov_blocks_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(spx_sparse_cov),
+                                            C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    'spx_krige_sparse_ok_dev': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.POINTER(spx_sparse_cov), C.c_double, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     'spx_dpack_segments': (C.c_int64, [C.c_int64]),
     'spx_dpack_capacity': (C.c_int64, [C.c_int64, C.c_int64]),
     'spx_dpack_stats_workspace': (C.c_int64, [C.c_int64, C.c_int64]),

@@ -115,6 +115,152 @@ __global__ void __launch_bounds__(256) k_ut_gemm(const double* __restrict__ data
     }
 }
 
+// ------------------------------------------------------------------ sparse covariance solve
+// Ordinary kriging with a compactly supported variogram (include/spx_b200.h, spx_sparse_cov):
+// the station matrix is F 11' - C with C block diagonal over small connected components.
+constexpr int SP_MAX = SPX_SPARSE_MAX_COMP;
+
+__global__ void k_sparse_blocks(const double* __restrict__ stn_x, const double* __restrict__ stn_y,
+                                spx_sparse_cov sp, spx_vg vgh, double min_vg_val, double base_f) {
+    __shared__ VgDev vg;
+    if (threadIdx.x == 0) {
+        vg.n_terms = vgh.n_terms;
+        for (int i = 0; i < SPX_VG_MAX_TERMS; ++i) {
+            vg.types[i] = vgh.types[i];
+            vg.sills[i] = vgh.sills[i];
+            vg.ranges[i] = vgh.ranges[i];
+        }
+    }
+    __syncthreads();
+    for (int c = blockIdx.x; c < sp.n_comp; c += gridDim.x) {
+        const int o = sp.comp_off[c], s = sp.comp_off[c + 1] - o;
+        double* blk = sp.blk + sp.blk_off[c];
+        for (int e = threadIdx.x; e < s * s; e += blockDim.x) {
+            const int i = e / s, j = e - i * s;
+            const int a = sp.comp_stn[o + i], b = sp.comp_stn[o + j];
+            const double h = dist_rn(stn_x[a], stn_y[a], stn_x[b], stn_y[b]);
+            blk[e] = base_f - vg_eval(vg, h, 0, min_vg_val);       // same entries as k_assemble
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sparse_ok(
+    const double* __restrict__ data, int n_stn, int64_t ld, const int32_t* __restrict__ row_step,
+    int64_t n_rows, spx_sparse_cov sp, double base_f, int kpad, double* __restrict__ coef,
+    double* __restrict__ coef_t, int64_t coef_t_ld, double* __restrict__ base,
+    double* __restrict__ scr_a, double* __restrict__ scr_b, int32_t* __restrict__ info) {
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const double* __restrict__ z = data + (int64_t)row_step[row] * ld;
+    double* __restrict__ A = scr_a + row * n_stn;      // C^-1 1   (0 at missing stations)
+    double* __restrict__ B = scr_b + row * n_stn;      // C^-1 z
+    double sa = 0.0, sb = 0.0;
+    int fail = 0;
+    for (int c = lane; c < sp.n_comp; c += 32) {
+        const int o = sp.comp_off[c], s = sp.comp_off[c + 1] - o;
+        const double* __restrict__ blk = sp.blk + sp.blk_off[c];
+        if (s == 1) {
+            const int k = sp.comp_stn[o];
+            const double zz = z[k];
+            double a = 0.0, b = 0.0;
+            if (zz == zz) {
+                const double d = blk[0];
+                if (!(d > 0.0)) fail = 1;
+                a = 1.0 / d;
+                b = zz * a;
+            }
+            A[k] = a;
+            B[k] = b;
+            sa += a;
+            sb += b;
+            continue;
+        }
+        int idx[SP_MAX];
+        double L[SP_MAX * SP_MAX], ra[SP_MAX], rb[SP_MAX];
+        int m = 0;
+        for (int i = 0; i < s; ++i) {
+            const int k = sp.comp_stn[o + i];
+            const double zz = z[k];
+            if (zz == zz) {
+                idx[m] = i;
+                ra[m] = 1.0;
+                rb[m] = zz;
+                ++m;
+            } else {
+                A[k] = 0.0;
+                B[k] = 0.0;
+            }
+        }
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j <= i; ++j) L[i * SP_MAX + j] = blk[idx[i] * s + idx[j]];
+        // Cholesky C = L L', then both right-hand sides
+        for (int j = 0; j < m; ++j) {
+            double d = L[j * SP_MAX + j];
+            for (int k = 0; k < j; ++k) d = fma(-L[j * SP_MAX + k], L[j * SP_MAX + k], d);
+            if (!(d > 0.0)) { fail = 1; d = 1.0; }
+            const double dj = sqrt(d);
+            L[j * SP_MAX + j] = dj;
+            for (int i = j + 1; i < m; ++i) {
+                double v = L[i * SP_MAX + j];
+                for (int k = 0; k < j; ++k) v = fma(-L[i * SP_MAX + k], L[j * SP_MAX + k], v);
+                L[i * SP_MAX + j] = v / dj;
+            }
+        }
+        for (int i = 0; i < m; ++i) {
+            double va = ra[i], vb = rb[i];
+            for (int k = 0; k < i; ++k) {
+                va = fma(-L[i * SP_MAX + k], ra[k], va);
+                vb = fma(-L[i * SP_MAX + k], rb[k], vb);
+            }
+            ra[i] = va / L[i * SP_MAX + i];
+            rb[i] = vb / L[i * SP_MAX + i];
+        }
+        for (int i = m - 1; i >= 0; --i) {
+            double va = ra[i], vb = rb[i];
+            for (int k = i + 1; k < m; ++k) {
+                va = fma(-L[k * SP_MAX + i], ra[k], va);
+                vb = fma(-L[k * SP_MAX + i], rb[k], vb);
+            }
+            ra[i] = va / L[i * SP_MAX + i];
+            rb[i] = vb / L[i * SP_MAX + i];
+        }
+        for (int i = 0; i < m; ++i) {
+            const int k = sp.comp_stn[o + idx[i]];
+            A[k] = ra[i];
+            B[k] = rb[i];
+            sa += ra[i];
+            sb += rb[i];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(FULL, sa, o);
+        sb += __shfl_xor_sync(FULL, sb, o);
+    }
+    const double nu = sb / sa;
+    if (!(sa > 0.0) || !(fabs(nu) <= 1.7976931348623157e308)) fail = 1;
+    fail = __any_sync(FULL, fail);
+    __syncwarp();
+    double sx = 0.0;
+    double* __restrict__ crow = coef + row * (int64_t)kpad;
+    for (int k = lane; k < n_stn; k += 32) {
+        const double x = fma(nu, A[k], -B[k]);
+        crow[k] = x;
+        if (coef_t) coef_t[(int64_t)k * coef_t_ld + row] = x;
+        sx += x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(FULL, sx, o);
+    if (lane == 0) {
+        crow[n_stn] = nu;
+        if (coef_t) coef_t[(int64_t)n_stn * coef_t_ld + row] = nu;
+        base[row] = fma(base_f, sx, nu);
+        if (fail) atomicAdd(info, 1);
+    }
+}
+
 // ------------------------------------------------------------------ the job
 static inline int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
@@ -159,6 +305,7 @@ struct FastSlot {
     bool used = false;
     spx_dd_plan plan{};
     int64_t n_krige = 0;
+    bool sparse = false;
 };
 
 struct FastJob {
@@ -193,6 +340,40 @@ int spx_ut_gemm_dev(const double* data, int32_t n_stn, int64_t data_ld, const in
     k_ut_gemm<<<grid, 256, 0, (cudaStream_t)stream>>>(data, n_stn, data_ld, src_step, n_rows,
                                                      n_data, M, ginv, ut);
     SPX_CHECK_LAUNCH("k_ut_gemm");
+    return SPX_OK;
+}
+
+int spx_sparse_cov_blocks_dev(const double* stn_x, const double* stn_y, const spx_sparse_cov* sp,
+                              const spx_vg* vg, double min_vg_val, double base_f, void* stream) {
+    if (!stn_x || !stn_y || !sp || !vg || sp->n_comp < 1 || !sp->comp_off || !sp->comp_stn ||
+        !sp->blk_off || !sp->blk || sp->max_size < 1 || sp->max_size > SPX_SPARSE_MAX_COMP) {
+        set_error("sparse_cov_blocks: bad argument (components of at most %d stations)",
+                  SPX_SPARSE_MAX_COMP);
+        return SPX_EINVAL;
+    }
+    const int blocks = sp->n_comp < 1024 ? sp->n_comp : 1024;
+    k_sparse_blocks<<<blocks, 64, 0, (cudaStream_t)stream>>>(stn_x, stn_y, *sp, *vg, min_vg_val,
+                                                            base_f);
+    SPX_CHECK_LAUNCH("k_sparse_blocks");
+    return SPX_OK;
+}
+
+int spx_krige_sparse_ok_dev(const double* data, int32_t n_stn, int64_t ld, const int32_t* row_step,
+                            int64_t n_rows, const spx_sparse_cov* sp, double base_f, int32_t kpad,
+                            double* coef, double* coef_t, int64_t coef_t_ld, double* base,
+                            double* scratch, int32_t* info, void* stream) {
+    if (n_rows == 0) return SPX_OK;
+    if (!data || !row_step || !sp || !coef || !base || !scratch || !info || n_stn < 1 ||
+        ld < n_stn || kpad < n_stn + 1 || sp->n_comp < 1 || sp->max_size > SPX_SPARSE_MAX_COMP ||
+        (coef_t && coef_t_ld < n_rows)) {
+        set_error("krige_sparse_ok: bad argument");
+        return SPX_EINVAL;
+    }
+    const int64_t blocks = (n_rows + 7) / 8;
+    k_sparse_ok<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        data, n_stn, ld, row_step, n_rows, *sp, base_f, kpad, coef, coef_t, coef_t_ld, base,
+        scratch, scratch + n_rows * n_stn, info);
+    SPX_CHECK_LAUNCH("k_sparse_ok");
     return SPX_OK;
 }
 
@@ -332,6 +513,73 @@ int spx_fast_submit(void* job, const double* data, int64_t n_steps, int64_t ld, 
     }
     const int64_t coef_rows = (c.estimator == 1) ? (nk + SPX_BM - 1) / SPX_BM * SPX_BM : nk;
     for (int64_t i = nk; i < (c.estimator == 1 ? coef_rows : nk); ++i) h_rowdst[i] = -1;
+    if (c.sparse.n_comp > 0 && c.estimator == 0 && c.n_border == 1) {
+        // ---- sparse-covariance solve: no plan, no Ut, no factorisation of r x r blocks ----
+        res->n_sys = (int32_t)nk;
+        lap(2);
+        j->next = (k + 1) % c.n_slots;
+        s.used = true;
+        s.n_krige = nk;
+        s.sparse = true;
+        double* d_data = reinterpret_cast<double*>(s.dev + L.d_data);
+        uint8_t* d_plan = s.dev + L.d_plan;
+        cudaStream_t st_up = j->solve;
+        if (pinned && ld != N) {
+            SPX_CUDA(cudaMemcpy2DAsync(d_data, 8 * (size_t)N, data, 8 * (size_t)ld, 8 * (size_t)N,
+                                       (size_t)n_steps, cudaMemcpyHostToDevice, st_up));
+        } else {
+            SPX_CUDA(cudaMemcpyAsync(d_data, pinned ? data : h_data, 8 * (size_t)n_steps * N,
+                                     cudaMemcpyHostToDevice, st_up));
+        }
+        int32_t* d_rowdst =
+            reinterpret_cast<int32_t*>(d_plan + spx_downdate_plan_bytes(c.max_steps, N));
+        SPX_CUDA(cudaMemcpyAsync(d_rowdst, h_rowdst, 4 * (size_t)nk, cudaMemcpyHostToDevice, st_up));
+        if (st != st_up) {
+            SPX_CUDA(cudaEventRecord(s.ev_up, st_up));
+            SPX_CUDA(cudaStreamWaitEvent(st, s.ev_up, 0));
+        }
+        if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_s0, st));
+        res->h2d_bytes = 8 * n_steps * N + 4 * nk;
+        res->d_data = d_data;
+        lap(3);
+        uint8_t* d_flags = s.dev + L.d_flags;
+        SPX_CUDA(cudaMemsetAsync(d_flags, 0, 8, st));
+        double* d_coef = reinterpret_cast<double*>(s.dev + L.d_coef);
+        SPX_CUDA(cudaMemsetAsync(d_coef, 0, 8 * (size_t)nk * c.kpad, st));
+        double* d_base = reinterpret_cast<double*>(s.dev + L.d_base);
+        double* d_coef_t = c.want_coef_t ? reinterpret_cast<double*>(s.dev + L.d_coef_t) : nullptr;
+        const int64_t ld_t = (nk + 3) / 4 * 4;
+        rc = spx_krige_sparse_ok_dev(d_data, N, N, d_rowdst, nk, &c.sparse, c.base_f, c.kpad,
+                                     d_coef, d_coef_t, ld_t, d_base,
+                                     reinterpret_cast<double*>(s.dev + L.d_ut),
+                                     reinterpret_cast<int32_t*>(d_flags), st);
+        if (rc != SPX_OK) return rc;
+        rc = spx_copy_to_mapped_host_dev(s.host + L.h_flags, d_flags, 8, st);
+        if (rc != SPX_OK) return rc;
+        SPX_CUDA(cudaEventRecord(s.ev_solved, st));
+        res->launches = 2;
+        lap(4);
+        if (c.solve_stream) SPX_CUDA(cudaStreamWaitEvent(st_main, s.ev_solved, 0));
+        if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_e0, st_main));
+        spx_local Lc = c.local;
+        Lc.coef = d_coef;
+        Lc.base = d_base;
+        Lc.n_rows = nk;
+        Lc.row_dst = d_rowdst;
+        Lc.out = out;
+        Lc.rows_all_valid = 1;
+        Lc.coef_t = d_coef_t;
+        Lc.coef_t_ld = d_coef_t ? ld_t : 0;
+        rc = spx_estimate_local_dev(&Lc, st_main);
+        if (rc != SPX_OK) return rc;
+        if (c.profile) SPX_CUDA(cudaEventRecord(s.ev_e1, st_main));
+        SPX_CUDA(cudaEventRecord(s.ev_done, st_main));
+        lap(5);
+        res->launches += 1;
+        res->status = 0;
+        return SPX_OK;
+    }
+    s.sparse = false;
     spx_dd_plan& plan = s.plan;
     rc = spx_downdate_plan_host(grp_of_step, grp_n, n_grps, N, h_rowdst, rows, nk, h_plan,
                                 spx_downdate_plan_host_bytes(c.max_steps), &plan);
@@ -477,6 +725,10 @@ int spx_fast_check(void* job, int32_t slot, int32_t* verdict) {
     }
     FastSlot& s = j->slots[slot];
     SPX_CUDA(cudaEventSynchronize(s.ev_solved));
+    if (s.sparse) {                        // number of rows whose Cholesky failed
+        *verdict = (*reinterpret_cast<const volatile int32_t*>(s.host + j->L.h_flags) != 0) ? 1 : 0;
+        return SPX_OK;
+    }
     const spx_dd_plan& plan = s.plan;
     const uint8_t* hf = s.host + j->L.h_flags;
     const double* resid = reinterpret_cast<const double*>(hf);

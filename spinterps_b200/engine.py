@@ -322,7 +322,11 @@ class ChunkEngine:
         # rounded float32 fields are downloaded as 16-bit codes and decoded on the host
         self.packed_download = True
         self._dl = None
+        self.solve_ms = []             # solve-phase times of profiled native submits (profile_gemm)
         self.transport = None          # codec of the packed download (None: transfer.default_codec())
+        # ordinary kriging with a compact variogram whose stations form small clusters:
+        # solve the block-diagonal covariance form instead of the downdated dense systems
+        self.sparse_solve = os.environ.get('SPX_SPARSE_SOLVE', '1') != '0'
         self.threaded_upload = True
         self._uploader = None
 
@@ -1652,7 +1656,8 @@ class ChunkEngine:
             return None
         jkey = (gkey, ctx['geom_key'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'], ctx['lo'],
                 ctx['hi'], min_var_thr, self.local_support, self.local_max_near,
-                self.local_tiles, self.lambda_tol, self.downdate_min_systems, self.solve_stream)
+                self.local_tiles, self.lambda_tol, self.downdate_min_systems, self.solve_stream,
+                self.sparse_solve)
         job = self._fast_jobs.get(jkey)
         if job is not None and job['max_steps'] >= n_steps and job['ginv'] is ginv:
             return job
@@ -1689,6 +1694,10 @@ class ChunkEngine:
             tot = local[0][1]
             cfg.base_f = float(tot if tot > ctx['min_vg_val'] else 0.0)
             cfg.local = L
+            sp = self._sparse_cov(ctx, vg_s, local[0][0], cfg.base_f) if self.sparse_solve else None
+            if sp is not None:
+                keep.append(sp)
+                cfg.sparse = sp['struct']
         else:
             g = _lib.spx_gemm()
             g.kpad, g.n_stn, g.n_border = kpad, n_stn, n_border
@@ -1734,6 +1743,53 @@ class ChunkEngine:
         self._fast_jobs[jkey] = job
         return job
 
+    def _sparse_cov(self, ctx, vg_s, R, base_f):
+        """Connected components of the graph "stations closer than the variogram range" and
+        their covariance blocks F - vg(d) on the device (spx_sparse_cov), or None when a
+        component has more than SPX_SPARSE_MAX_COMP stations: beyond the range the variogram
+        is the constant F, so the ordinary-kriging matrix is F 11' - C with C block diagonal
+        over these components and a time step is solved in O(n_stn)
+        (spx_krige_sparse_ok_dev) instead of a dense factorisation -- same system, same
+        solution to rounding."""
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        from scipy.spatial import cKDTree
+        n = ctx['n_stn']
+        xy = np.column_stack([ctx['stn_xs'], ctx['stn_ys']])
+        # a little beyond R: pairs at exactly the range have vg == F anyway (C entry 0)
+        pairs = cKDTree(xy).query_pairs(R * (1.0 + 1e-12) + 1e-9, output_type='ndarray')
+        if pairs.shape[0] > 8 * n:
+            return None
+        g = coo_matrix((np.ones(pairs.shape[0], dtype=np.int8), (pairs[:, 0], pairs[:, 1])),
+                       shape=(n, n))
+        n_comp, lab = connected_components(g, directed=False)
+        sizes = np.bincount(lab, minlength=n_comp)
+        if sizes.max() > _lib.SPX_SPARSE_MAX_COMP:
+            return None
+        order = np.argsort(lab, kind='stable').astype(np.int32)       # members by component
+        comp_off = np.zeros(n_comp + 1, dtype=np.int32)
+        np.cumsum(sizes, out=comp_off[1:])
+        blk_off = np.zeros(n_comp, dtype=np.int64)
+        np.cumsum((sizes.astype(np.int64) ** 2)[:-1], out=blk_off[1:])
+        n_blk = int((sizes.astype(np.int64) ** 2).sum())
+        d_off = torch.from_numpy(comp_off).to(self.device)
+        d_stn = torch.from_numpy(order).to(self.device)
+        d_boff = torch.from_numpy(blk_off).to(self.device)
+        d_blk = torch.empty(n_blk, dtype=_F64, device=self.device)
+        sp = _lib.spx_sparse_cov()
+        sp.n_comp, sp.max_size = int(n_comp), int(sizes.max())
+        sp.comp_off, sp.comp_stn = d_off.data_ptr(), d_stn.data_ptr()
+        sp.blk_off, sp.blk = d_boff.data_ptr(), d_blk.data_ptr()
+        vg = _lib.make_vg(vg_s)
+        _lib.check(self.lib.spx_sparse_cov_blocks_dev(
+            C.c_void_p(ctx['d_stn_x'].data_ptr()), C.c_void_p(ctx['d_stn_y'].data_ptr()),
+            C.byref(sp), C.byref(vg), float(ctx['min_vg_val']), float(base_f), self._stream()),
+            'sparse_cov_blocks')
+        self._count('launches')
+        self._count('sparse_cov_jobs')
+        return dict(struct=sp, tensors=(d_off, d_stn, d_boff, d_blk), n_comp=int(n_comp),
+                    max_size=int(sizes.max()))
+
     def _next_job_id(self):
         self._fast_job_seq = getattr(self, '_fast_job_seq', 0) + 1
         return self._fast_job_seq
@@ -1768,9 +1824,11 @@ class ChunkEngine:
             rec = self._fast_prof.pop((job['id'], k), None)
             if rec is None:
                 continue
-            ms = C.c_float(0.0)
-            _lib.check(self.lib.spx_fast_times(job['handle'], k, C.byref(ms), None), 'fast_times')
+            ms, ms_solve = C.c_float(0.0), C.c_float(0.0)
+            _lib.check(self.lib.spx_fast_times(job['handle'], k, C.byref(ms), C.byref(ms_solve)),
+                       'fast_times')
             self.kernel_events.append(rec + (float(ms.value), None))
+            self.solve_ms.append(float(ms_solve.value))
 
     def collect_profile(self):
         """Finish kernel_events (synchronises the estimate launches still in flight)."""

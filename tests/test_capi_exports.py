@@ -69,7 +69,8 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     structs = {'spx_vg': 'ranges', 'spx_systems': 'max_m', 'spx_rhs': 'coef_row_major',
                'spx_downdate': 'base_f', 'spx_dd_plan': 'n_bytes', 'spx_gemm': 'quad_slot',
                'spx_multivg': 'all_fast', 'spx_local': 'slot', 'spx_nrst': 'u_end',
-               'spx_fast_cfg': 'solve_stream', 'spx_pack_row': 'n_nan', 'spx_fast_result': 'host_ms'}
+               'spx_fast_cfg': 'sparse', 'spx_pack_row': 'n_nan', 'spx_fast_result': 'host_ms',
+               'spx_sparse_cov': 'blk'}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "spx_b200.h"', 'int main(void){']
     for name, last in structs.items():
         src.append(f'printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {last}));')

@@ -731,3 +731,64 @@ def test_idw_station_on_a_cell_centre():
         assert np.isnan(exp[lab][[0, 1, 5, 6, 7], 40]).all() and np.isfinite(exp[lab][2:5, 40]).all()
         assert np.isfinite(exp[lab][:, np.arange(168) != 40]).all()
     _check(got, exp, 'idw_station_on_cell_centre')
+
+
+@pytest.mark.parametrize('vg', ['0.1 Nug(0.0) + 0.9 Sph(9000)',
+                                '0.2 Nug(0.0) + 0.5 Sph(6000) + 0.3 Lin(11000)'])
+@pytest.mark.parametrize('dt', [np.float64, np.float32])
+def test_sparse_covariance_solve_matches_downdate_and_oracle(vg, dt):
+    """Ordinary kriging with a compact variogram whose stations form small clusters: the
+    native submit solves the block-diagonal covariance form F 11' - C in O(n_stn) per step
+    (spx_krige_sparse_ok_dev) instead of downdating dense systems.  Same numbers as the
+    downdate path and the oracle; single-station / empty / low-value steps ride along."""
+    from spinterps_b200.engine import ChunkEngine
+    n_steps = 48
+    p = make_problem(71, 220, n_steps, 64, 70, cell=4000.0, miss=0.2)
+    rng = np.random.default_rng(72)
+    data2 = rng.gamma(1.0, 5.0, size=p['data'].shape)
+    data2[rng.random(data2.shape) < 0.2] = np.nan
+    data2[5, :] = np.nan
+    data2[5, 40] = 3.5                                             # single-station step
+    data2[6, :] = np.nan                                           # no station at all
+    data2[9] = np.where(np.isnan(data2[9]), np.nan, 0.01)          # below min_var_thr
+    kw = dict(min_var_thr=0.1, min_var_cut=0.0, interp_args=[('OK', None, 'OK')],
+              vgs=[vg] * n_steps)
+    base = {k: v for k, v in p.items() if k != 'data'}
+
+    def run(sparse):
+        e = ChunkEngine()
+        e.sparse_solve = sparse
+        e.interp_chunk(p['data'], intrp_dtype=dt, **kw, **base)      # fills the caches
+        out, prob = e.interp_chunk(data2, intrp_dtype=dt, **kw, **base)
+        return e, out, prob
+
+    e1, got, prob1 = run(True)
+    e0, ref, prob0 = run(False)
+    assert e1.stats.get('native_submits', 0) == 1 and e1.stats.get('sparse_cov_jobs', 0) == 1
+    assert e0.stats.get('native_submits', 0) == 1 and e0.stats.get('sparse_cov_jobs', 0) == 0
+    assert e1.stats.get('fast_path_redo', 0) + e1.stats.get('downdate_redo', 0) == 0
+    assert prob1 == prob0 == [6]
+    exp, _ = orc.interp_chunk(data2, intrp_dtype=np.float64, faithful=False, **kw, **base)
+    g, r, x = got['OK'], ref['OK'], exp['OK']
+    assert np.array_equal(np.isnan(g), np.isnan(r))
+    if dt == np.float32:
+        assert rel_err(g, r, _floor(r)) <= 3e-7
+        assert rel_err(g, x.astype(np.float32), _floor(x)) <= 3e-7
+    else:
+        assert rel_err(g, r, _floor(r)) <= 1e-10
+        assert rel_err(g, x, _floor(x)) <= KRG_TOL
+
+
+def test_sparse_covariance_solve_needs_small_clusters():
+    """Stations that chain up within the range (one big component) keep the downdate."""
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(73, 150, 30, 40, 44, cell=4000.0, miss=0.15)
+    kw = dict(interp_args=[('OK', None, 'OK')], vgs=[VG_C1] * 30)
+    base = {k: v for k, v in p.items() if k != 'data'}
+    e = ChunkEngine()
+    e.interp_chunk(p['data'], intrp_dtype=np.float64, **kw, **base)
+    got, _ = e.interp_chunk(p['data'][::-1].copy(), intrp_dtype=np.float64, **kw, **base)
+    assert e.stats.get('native_submits', 0) == 1 and e.stats.get('sparse_cov_jobs', 0) == 0
+    exp, _ = orc.interp_chunk(p['data'][::-1].copy(), intrp_dtype=np.float64, faithful=False,
+                              **kw, **base)
+    assert rel_err(got['OK'], exp['OK'], _floor(exp['OK'])) <= KRG_TOL
