@@ -644,6 +644,9 @@ int spx_local_set_bulk(int on);
 typedef struct spx_sparse_cov {
     int32_t n_comp;              /* 0 = not used */
     int32_t max_size;            /* largest component */
+    int32_t n_single;            /* components are sorted by size: the first n_single have one
+                                    station (comp_off[c] == blk_off[c] == c for them) */
+    int32_t reserved;
     const int32_t* comp_off;     /* device [n_comp + 1]: members of component c are        */
     const int32_t* comp_stn;     /* device [n_stn]:       comp_stn[comp_off[c] .. comp_off[c+1]) */
     const int64_t* blk_off;      /* device [n_comp]: offset of the component's s x s block  */

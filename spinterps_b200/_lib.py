@@ -173,7 +173,8 @@ SPX_DPACK_ROUND, SPX_DPACK_WRITE_BACK = 1, 2
 
 
 class spx_sparse_cov(C.Structure):
-    _fields_ = [('n_comp', C.c_int32), ('max_size', C.c_int32), ('comp_off', C.c_void_p),
+    _fields_ = [('n_comp', C.c_int32), ('max_size', C.c_int32), ('n_single', C.c_int32),
+                ('reserved', C.c_int32), ('comp_off', C.c_void_p),
                 ('comp_stn', C.c_void_p), ('blk_off', C.c_void_p), ('blk', C.c_void_p)]
 
 

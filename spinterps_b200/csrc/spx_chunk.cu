@@ -158,23 +158,54 @@ __global__ void __launch_bounds__(256) k_sparse_ok(
     double* __restrict__ B = scr_b + row * n_stn;      // C^-1 z
     double sa = 0.0, sb = 0.0;
     int fail = 0;
-    for (int c = lane; c < sp.n_comp; c += 32) {
+    // components are sorted by size: the first n_single are single stations (member list and
+    // block offset == component index), then pairs, then the rest -- lanes of a warp run the
+    // same code almost everywhere
+    for (int c = lane; c < sp.n_single; c += 32) {
+        const int k = sp.comp_stn[c];
+        const double zz = z[k];
+        double a = 0.0, b = 0.0;
+        if (zz == zz) {
+            const double d = sp.blk[c];
+            if (!(d > 0.0)) fail = 1;
+            a = 1.0 / d;
+            b = zz * a;
+        }
+        A[k] = a;
+        B[k] = b;
+        sa += a;
+        sb += b;
+    }
+    for (int c = sp.n_single + lane; c < sp.n_comp; c += 32) {
         const int o = sp.comp_off[c], s = sp.comp_off[c + 1] - o;
         const double* __restrict__ blk = sp.blk + sp.blk_off[c];
-        if (s == 1) {
-            const int k = sp.comp_stn[o];
-            const double zz = z[k];
-            double a = 0.0, b = 0.0;
-            if (zz == zz) {
-                const double d = blk[0];
-                if (!(d > 0.0)) fail = 1;
-                a = 1.0 / d;
-                b = zz * a;
+        if (s == 2) {
+            const int k0 = sp.comp_stn[o], k1 = sp.comp_stn[o + 1];
+            const double z0 = z[k0], z1 = z[k1];
+            const bool h0 = (z0 == z0), h1 = (z1 == z1);
+            const double c00 = blk[0], c01 = blk[1], c11 = blk[3];
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            if (h0 && h1) {
+                const double det = fma(c00, c11, -c01 * c01);
+                if (!(det > 0.0) || !(c00 > 0.0)) fail = 1;
+                const double inv = 1.0 / det;
+                a0 = (c11 - c01) * inv;
+                a1 = (c00 - c01) * inv;
+                b0 = fma(c11, z0, -c01 * z1) * inv;
+                b1 = fma(c00, z1, -c01 * z0) * inv;
+            } else if (h0) {
+                if (!(c00 > 0.0)) fail = 1;
+                a0 = 1.0 / c00;
+                b0 = z0 * a0;
+            } else if (h1) {
+                if (!(c11 > 0.0)) fail = 1;
+                a1 = 1.0 / c11;
+                b1 = z1 * a1;
             }
-            A[k] = a;
-            B[k] = b;
-            sa += a;
-            sb += b;
+            A[k0] = a0; B[k0] = b0;
+            A[k1] = a1; B[k1] = b1;
+            sa += a0 + a1;
+            sb += b0 + b1;
             continue;
         }
         int idx[SP_MAX];
@@ -365,6 +396,7 @@ int spx_krige_sparse_ok_dev(const double* data, int32_t n_stn, int64_t ld, const
     if (n_rows == 0) return SPX_OK;
     if (!data || !row_step || !sp || !coef || !base || !scratch || !info || n_stn < 1 ||
         ld < n_stn || kpad < n_stn + 1 || sp->n_comp < 1 || sp->max_size > SPX_SPARSE_MAX_COMP ||
+        sp->n_single < 0 || sp->n_single > sp->n_comp ||
         (coef_t && coef_t_ld < n_rows)) {
         set_error("krige_sparse_ok: bad argument");
         return SPX_EINVAL;

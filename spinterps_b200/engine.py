@@ -1766,6 +1766,12 @@ class ChunkEngine:
         sizes = np.bincount(lab, minlength=n_comp)
         if sizes.max() > _lib.SPX_SPARSE_MAX_COMP:
             return None
+        # components by size (singles first: the kernel's lanes then share their code path),
+        # members of a component by station index
+        rank = np.empty(n_comp, dtype=np.int64)
+        rank[np.argsort(sizes, kind='stable')] = np.arange(n_comp)
+        lab = rank[lab]
+        sizes = np.bincount(lab, minlength=n_comp)
         order = np.argsort(lab, kind='stable').astype(np.int32)       # members by component
         comp_off = np.zeros(n_comp + 1, dtype=np.int32)
         np.cumsum(sizes, out=comp_off[1:])
@@ -1778,6 +1784,7 @@ class ChunkEngine:
         d_blk = torch.empty(n_blk, dtype=_F64, device=self.device)
         sp = _lib.spx_sparse_cov()
         sp.n_comp, sp.max_size = int(n_comp), int(sizes.max())
+        sp.n_single = int((sizes == 1).sum())
         sp.comp_off, sp.comp_stn = d_off.data_ptr(), d_stn.data_ptr()
         sp.blk_off, sp.blk = d_boff.data_ptr(), d_blk.data_ptr()
         vg = _lib.make_vg(vg_s)
