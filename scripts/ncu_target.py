@@ -1,4 +1,4 @@
-"""A few chunks of the bench workload through the public call with the packed download:
+"""A few chunks of the bench workload through the public call with the fused output stage + delta download:
 the target of the `ncu --set full` captures (every hot kernel appears once per chunk)."""
 import os, sys
 import numpy as np, torch
@@ -13,5 +13,6 @@ eng = ChunkEngine()
 kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32,
           round_decimals=bench.NMRL_PRCN, field_stats=True)
 for i in range(n):
-    out, _ = eng.submit_chunk(**kw, **chunks[i % 2]).result(to_host=True)
-    print(i, float(np.nanmean(out['OK'][:3])), eng.stats.get('native_submits'), flush=True)
+    out, _ = eng.submit_chunk(**kw, **chunks[i % 2]).result(to_host='packed')
+    print(i, out['OK'].nbytes, eng.stats.get('native_submits'), flush=True)
+    out['OK'].release()

@@ -144,7 +144,7 @@ __global__ void k_sparse_blocks(const double* __restrict__ stn_x, const double* 
     }
 }
 
-__global__ void __launch_bounds__(256) k_sparse_ok(
+__global__ void __launch_bounds__(128) k_sparse_ok(
     const double* __restrict__ data, int n_stn, int64_t ld, const int32_t* __restrict__ row_step,
     int64_t n_rows, spx_sparse_cov sp, double base_f, int kpad, double* __restrict__ coef,
     double* __restrict__ coef_t, int64_t coef_t_ld, double* __restrict__ base,
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) k_sparse_ok(
     // components are sorted by size: the first n_single are single stations (member list and
     // block offset == component index), then pairs, then the rest -- lanes of a warp run the
     // same code almost everywhere
+#pragma unroll 4
     for (int c = lane; c < sp.n_single; c += 32) {
         const int k = sp.comp_stn[c];
         const double zz = z[k];
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256) k_sparse_ok(
     __syncwarp();
     double sx = 0.0;
     double* __restrict__ crow = coef + row * (int64_t)kpad;
+#pragma unroll 4
     for (int k = lane; k < n_stn; k += 32) {
         const double x = fma(nu, A[k], -B[k]);
         crow[k] = x;
@@ -401,8 +403,8 @@ int spx_krige_sparse_ok_dev(const double* data, int32_t n_stn, int64_t ld, const
         set_error("krige_sparse_ok: bad argument");
         return SPX_EINVAL;
     }
-    const int64_t blocks = (n_rows + 7) / 8;
-    k_sparse_ok<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    const int64_t blocks = (n_rows + 3) / 4;           // 4 warps per block: spread over the SMs
+    k_sparse_ok<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
         data, n_stn, ld, row_step, n_rows, *sp, base_f, kpad, coef, coef_t, coef_t_ld, base,
         scratch, scratch + n_rows * n_stn, info);
     SPX_CHECK_LAUNCH("k_sparse_ok");

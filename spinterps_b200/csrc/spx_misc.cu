@@ -371,11 +371,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_round_stats(T* fld, int64_t row_
     }
 }
 
-__global__ void k_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, double* stats) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row: lanes merge every 32nd segment, then a shuffle tree (Chan et al.)
+__global__ void __launch_bounds__(128) k_stats_final(const StatPart* __restrict__ parts, int n_seg,
+                                                     int64_t n_rows, double* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
-    StatPart t = parts[row * n_seg];
-    for (int sgi = 1; sgi < n_seg; ++sgi) stat_merge(t, parts[row * n_seg + sgi]);
+    StatPart t;
+    t.n = 0.0; t.mean = 0.0; t.m2 = 0.0; t.mn = CUDART_INF; t.mx = -CUDART_INF; t.nfin = 0.0;
+    for (int sgi = lane; sgi < n_seg; sgi += 32) stat_merge(t, parts[row * n_seg + sgi]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const StatPart b = stat_shfl(t, o);
+        stat_merge(t, b);
+    }
+    if (lane != 0) return;
     const bool any = t.n > 0.0;
     stats[0 * n_rows + row] = any ? t.mn : CUDART_NAN;
     stats[1 * n_rows + row] = any ? t.mean : CUDART_NAN;
@@ -386,7 +396,7 @@ __global__ void k_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, 
 
 void launch_stats_final(const StatPart* parts, int n_seg, int64_t n_rows, double* stats,
                         cudaStream_t st) {
-    k_stats_final<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(parts, n_seg, n_rows, stats);
+    k_stats_final<<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(parts, n_seg, n_rows, stats);
 }
 
 }  // namespace spx
@@ -605,7 +615,7 @@ int spx_round_stats_dev(void* fld, int32_t is_f64, int64_t n_rows, int64_t row_l
             (float*)fld, row_len, ld, seg_len, do_round, (float)pw, parts);
     }
     SPX_CHECK_LAUNCH("k_round_stats");
-    k_stats_final<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(parts, n_seg, n_rows, stats);
+    launch_stats_final(parts, n_seg, n_rows, stats, st);
     SPX_CHECK_LAUNCH("k_stats_final");
     return SPX_OK;
 }
