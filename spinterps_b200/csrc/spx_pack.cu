@@ -786,6 +786,124 @@ static const uint8_t* dunpack_tile(const uint8_t* rec, const uint8_t* end, int n
     return rec + (((pay - rec) + 3) & ~(ptrdiff_t)3);          // records are padded to 4 bytes
 }
 
+// The same decoder with AVX2 + BMI2: a group of 8 cells is unpacked with PDEP, zigzag-decoded,
+// prefix-summed (twice for second differences) and divided 8 lanes at a time.
+#define SPX_AVX2_BMI2 __attribute__((target("avx2,bmi2")))
+
+SPX_AVX2_BMI2 static inline __m256i dp_prefix8(__m256i d) {
+    __m256i s = _mm256_add_epi32(d, _mm256_slli_si256(d, 4));
+    s = _mm256_add_epi32(s, _mm256_slli_si256(s, 8));                  // prefix inside each half
+    const __m256i lo_tot = _mm256_permutevar8x32_epi32(s, _mm256_set1_epi32(3));
+    return _mm256_add_epi32(s, _mm256_blend_epi32(_mm256_setzero_si256(), lo_tot, 0xF0));
+}
+
+SPX_AVX2_BMI2 static const uint8_t* dunpack_tile_avx2(const uint8_t* rec, const uint8_t* end, int n,
+                                                      float p, float* out) {
+    if (rec >= end) return nullptr;
+    const uint32_t mode = rec[0];
+    const int kind = (int)(mode & 3u);
+    if (kind != 1 && kind != 3) return dunpack_tile(rec, end, n, p, out);
+    if (rec + 5 > end) return nullptr;
+    int32_t f;
+    memcpy(&f, rec + 1, 4);
+    const __m256 vp = _mm256_set1_ps(p);
+    if (kind == 3) {
+        const __m256 x = _mm256_set1_ps((float)f / p);
+        int c = 0;
+        for (; c + 8 <= n; c += 8) _mm256_storeu_ps(out + c, x);
+        for (; c < n; ++c) out[c] = (float)f / p;
+        return rec + 8;
+    }
+    if (rec + 9 > end) return nullptr;
+    uint32_t nzg;
+    memcpy(&nzg, rec + 5, 4);
+    const uint8_t* nib = rec + 9;
+    const uint8_t* pay = nib + ((__builtin_popcount(nzg) + 1) >> 1);
+    const uint8_t* bm_nan = nullptr;
+    const uint8_t* bm_nz = nullptr;
+    if (mode & 4u) { bm_nan = pay; pay += 32; }
+    if (mode & 8u) { bm_nz = pay; pay += 32; }
+    if (pay > end) return nullptr;
+    const bool order2 = (mode & 16u) != 0;
+    const float nanv = __builtin_nanf("");
+    const __m256i one = _mm256_set1_epi32(1);
+    const __m256i ramp = _mm256_setr_epi32(1, 2, 3, 4, 5, 6, 7, 8);
+    int32_t d1 = 0;
+    int k = 0;
+    for (int l = 0; l < 32; ++l) {
+        int w = 0;
+        if ((nzg >> l) & 1u) {
+            w = dp_width_of_code((nib[k >> 1] >> ((k & 1) * 4)) & 15);
+            ++k;
+        }
+        if (pay + w > end) return nullptr;
+        const int cnt = (n - l * 8) < 8 ? (n - l * 8) : 8;
+        __m256i fv;
+        if (w == 0) {
+            if (cnt <= 0) continue;
+            if (!order2 || d1 == 0) {
+                fv = _mm256_set1_epi32(f);
+            } else {
+                fv = _mm256_add_epi32(_mm256_set1_epi32(f),
+                                      _mm256_mullo_epi32(_mm256_set1_epi32(d1), ramp));
+                f = (int32_t)((uint32_t)f + 8u * (uint32_t)d1);
+            }
+        } else {
+            __m256i z;
+            if (w == 32) {
+                z = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(pay));
+            } else {
+                uint64_t lo = 0, hi = 0;
+                if (pay + 16 <= end) {
+                    memcpy(&lo, pay, 8);
+                    memcpy(&hi, pay + 8, 8);
+                } else {
+                    uint8_t tmp[16] = {0};
+                    memcpy(tmp, pay, (size_t)w);
+                    memcpy(&lo, tmp, 8);
+                    memcpy(&hi, tmp + 8, 8);
+                }
+                if (w <= 8) {
+                    const uint64_t m = 0x0101010101010101ull * ((1ull << w) - 1ull);
+                    z = _mm256_cvtepu8_epi32(_mm_cvtsi64_si128((long long)_pdep_u64(lo, m)));
+                } else {
+                    const uint64_t m = 0x0001000100010001ull * ((1ull << w) - 1ull);
+                    const uint64_t a = lo;
+                    const uint64_t b = (w == 16) ? hi : ((lo >> (4 * w)) | (hi << (64 - 4 * w)));
+                    const __m128i x = _mm_set_epi64x((long long)_pdep_u64(b, m),
+                                                     (long long)_pdep_u64(a, m));
+                    z = _mm256_cvtepu16_epi32(x);
+                }
+            }
+            pay += w;
+            if (cnt <= 0) continue;
+            const __m256i d = _mm256_xor_si256(
+                _mm256_srli_epi32(z, 1),
+                _mm256_sub_epi32(_mm256_setzero_si256(), _mm256_and_si256(z, one)));
+            __m256i s = dp_prefix8(d);
+            if (order2) {
+                const __m256i d1v = _mm256_add_epi32(_mm256_set1_epi32(d1), s);
+                d1 = _mm256_extract_epi32(d1v, 7);
+                s = dp_prefix8(d1v);
+            }
+            fv = _mm256_add_epi32(_mm256_set1_epi32(f), s);
+            f = _mm256_extract_epi32(fv, 7);
+        }
+        const __m256 x = _mm256_div_ps(_mm256_cvtepi32_ps(fv), vp);
+        float* o = out + l * 8;
+        const uint32_t mn = bm_nan ? bm_nan[l] : 0u, mz = bm_nz ? bm_nz[l] : 0u;
+        if (cnt == 8 && !(mn | mz)) {
+            _mm256_storeu_ps(o, x);
+        } else {
+            float tmp[8];
+            _mm256_storeu_ps(tmp, x);
+            for (int j = 0; j < cnt; ++j)
+                o[j] = ((mn >> j) & 1u) ? nanv : (((mz >> j) & 1u) ? -0.0f : tmp[j]);
+        }
+    }
+    return rec + (((pay - rec) + 3) & ~(ptrdiff_t)3);
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -937,6 +1055,11 @@ int spx_dunpack_rows_host(const uint32_t* seg_off, const void* payload, int64_t 
     const uint8_t* pay = reinterpret_cast<const uint8_t*>(payload);
     const uint8_t* pay_end = pay + payload_bytes;
     int bad = 0;
+    static const bool scalar_only = []() {
+        const char* e = std::getenv("SPX_DUNPACK_SCALAR");
+        return e && e[0] == '1';
+    }();
+    const bool fast = !scalar_only && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
     auto work = [&](int part, int n_parts) {
         for (int64_t r = part; r < n_rows; r += n_parts) {
             float* o = out + r * out_ld;
@@ -947,7 +1070,9 @@ int spx_dunpack_rows_host(const uint32_t* seg_off, const void* payload, int64_t 
                 for (int64_t c0 = sg * DP_SEG_CELLS;
                      rec && c0 < row_len && c0 < (sg + 1) * DP_SEG_CELLS; c0 += DP_TILE) {
                     const int64_t rest = row_len - c0;
-                    rec = dunpack_tile(rec, pay_end, rest < DP_TILE ? (int)rest : DP_TILE, p, o + c0);
+                    const int nc = rest < DP_TILE ? (int)rest : DP_TILE;
+                    rec = fast ? dunpack_tile_avx2(rec, pay_end, nc, p, o + c0)
+                               : dunpack_tile(rec, pay_end, nc, p, o + c0);
                 }
                 if (!rec) __atomic_store_n(&bad, 1, __ATOMIC_RELAXED);
             }

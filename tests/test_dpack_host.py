@@ -73,3 +73,25 @@ def test_decoder_rejects_bad_offsets():
                                      out.ctypes.data, 600, 1) != 0
     assert lib.spx_dunpack_rows_host(offs.ctypes.data, payload.ctypes.data, 8, 2, 600, 2,
                                      out.ctypes.data, 600, 1) != 0
+
+
+def test_decoder_special_tiles():
+    """Linear ramps (second differences all zero: empty groups with a running slope),
+    quadratics, jumps that need 14 / 16 / 32-bit groups, wrap-around of the int32 chain."""
+    c = np.arange(1500, dtype=np.float64)
+    rows = [
+        0.03 * c,                                        # ramp
+        -0.07 * c + 5.0,
+        0.0001 * (c - 700) ** 2,                          # quadratic
+        np.where((c // 9) % 2 == 0, 120.0, -95.5),       # jumps of ~2e4 lattice steps
+        np.where((c // 5) % 2 == 0, 2.0e7, -2.0e7),      # jumps of 4e9: wraps modulo 2^32
+        np.cumsum(np.random.default_rng(5).integers(-3000, 3000, 1500)) * 0.01,
+        np.r_[np.full(700, 3.25), 0.05 * c[:800]],       # plateau, then a ramp
+    ]
+    fld = np.round(np.array(rows).astype(np.float32), 2)
+    offs, payload = dpack_ref.encode(fld, 2)
+    modes = payload[(offs.astype(np.int64) * 4)]
+    assert (modes & 16).any()                            # second differences are in use
+    got_c = c_decode(offs, payload, *fld.shape, 2)
+    got_py = dpack_ref.decode(offs, payload, *fld.shape, 2)
+    assert same_bits(got_py, fld) and same_bits(got_c, fld)
