@@ -123,7 +123,8 @@ def run(cfg, steps_limit):
             del f
         pend = nxt
         for k_, v_ in eng.stats.items():
-            stats[k_] = stats.get(k_, 0) + v_
+            if isinstance(v_, (int, float)):
+                stats[k_] = stats.get(k_, 0) + v_
     f, _ = pend.result(to_host=False)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t_beg

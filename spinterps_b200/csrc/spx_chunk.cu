@@ -420,7 +420,8 @@ int64_t spx_fast_slot_bytes(const spx_fast_cfg* cfg, int32_t pinned_host) {
 
 int spx_fast_create(const spx_fast_cfg* cfg, void* dev_arena, void* host_arena, void** job_out) {
     if (!cfg || !dev_arena || !host_arena || !job_out || cfg->n_stn < 1 || cfg->n_border < 1 ||
-        cfg->max_steps < 1 || cfg->n_slots < 2 || cfg->n_slots > 8 || !cfg->ginv ||
+        cfg->max_steps < 1 || cfg->n_slots < 2 || cfg->n_slots > 8 ||
+        (!cfg->ginv && !(cfg->sparse.n_comp > 0 && cfg->estimator == 0 && cfg->n_border == 1)) ||
         cfg->kpad % 4 != 0 || cfg->kpad < cfg->n_stn + cfg->n_border ||
         (cfg->estimator != 0 && cfg->estimator != 1)) {
         set_error("fast_create: bad configuration");

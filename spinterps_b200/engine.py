@@ -322,6 +322,7 @@ class ChunkEngine:
         # rounded float32 fields are downloaded as 16-bit codes and decoded on the host
         self.packed_download = True
         self._dl = None
+        self._fast_jobs_none = set()   # job keys without inverse for which the sparse form was ruled out
         self.solve_ms = []             # solve-phase times of profiled native submits (profile_gemm)
         self.transport = None          # codec of the packed download (None: transfer.default_codec())
         # ordinary kriging with a compact variogram whose stations form small clusters:
@@ -1652,15 +1653,18 @@ class ChunkEngine:
                                   uniq_vgs=[vg_s], d_stn_drift=None)
         gkey = (self._ginv_key(ctx, K), vg_s)
         ginv = self._ginv_cache.get(gkey)
-        if ginv is None:
-            return None
+        if ginv is None and not (self.sparse_solve and self.local_support):
+            return None           # no sparse form either: the general path builds the inverse
         jkey = (gkey, ctx['geom_key'], ctx['out_f64'], ctx['has_lo'], ctx['has_hi'], ctx['lo'],
                 ctx['hi'], min_var_thr, self.local_support, self.local_max_near,
                 self.local_tiles, self.lambda_tol, self.downdate_min_systems, self.solve_stream,
                 self.sparse_solve)
         job = self._fast_jobs.get(jkey)
-        if job is not None and job['max_steps'] >= n_steps and job['ginv'] is ginv:
+        if job is not None and job['max_steps'] >= n_steps and (
+                job['ginv'] is ginv or job['cfg'].sparse.n_comp > 0):
             return job
+        if ginv is None and jkey in self._fast_jobs_none:
+            return None           # the sparse form does not apply here (checked before)
         if job is not None:
             self._fast_job_close(jkey)
         lib = self.lib
@@ -1670,7 +1674,7 @@ class ChunkEngine:
         cfg.n_slots = int(self.fast_slots)
         cfg.min_systems = int(self.downdate_min_systems)
         cfg.min_var_thr = float(min_var_thr)
-        cfg.ginv = ginv.data_ptr()
+        cfg.ginv = ginv.data_ptr() if ginv is not None else None
         cfg.lambda_bound = float(self._rhs_bound(ctx, K, None)[0])
         cfg.lambda_tol = float(self.lambda_tol)
         cfg.profile = 1
@@ -1720,6 +1724,10 @@ class ChunkEngine:
             cfg.estimator = 1
             cfg.want_coef_t = 0
             cfg.gemm = g
+        if ginv is None and cfg.sparse.n_comp == 0:
+            # neither a cached inverse of the full station system nor the sparse form
+            self._fast_jobs_none.add(jkey)
+            return None
         d_bytes = int(lib.spx_fast_slot_bytes(C.byref(cfg), 0))
         h_bytes = int(lib.spx_fast_slot_bytes(C.byref(cfg), 1))
         if d_bytes <= 0 or h_bytes <= 0:

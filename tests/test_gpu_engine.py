@@ -755,17 +755,27 @@ def test_sparse_covariance_solve_matches_downdate_and_oracle(vg, dt):
               vgs=[vg] * n_steps)
     base = {k: v for k, v in p.items() if k != 'data'}
 
+    first = {}
+
     def run(sparse):
         e = ChunkEngine()
         e.sparse_solve = sparse
-        e.interp_chunk(p['data'], intrp_dtype=dt, **kw, **base)      # fills the caches
+        out0, _ = e.interp_chunk(p['data'], intrp_dtype=dt, **kw, **base)   # fills the caches
+        first[sparse] = (dict(e.stats), out0['OK'])
         out, prob = e.interp_chunk(data2, intrp_dtype=dt, **kw, **base)
         return e, out, prob
 
     e1, got, prob1 = run(True)
     e0, ref, prob0 = run(False)
-    assert e1.stats.get('native_submits', 0) == 1 and e1.stats.get('sparse_cov_jobs', 0) == 1
-    assert e0.stats.get('native_submits', 0) == 1 and e0.stats.get('sparse_cov_jobs', 0) == 0
+    # the sparse form needs no inverse of the full station system: already the FIRST chunk of
+    # a job goes through the native submit; without it the general path runs first
+    assert first[True][0].get('native_submits', 0) == 1 and first[True][0].get('sparse_cov_jobs', 0) == 1
+    assert first[False][0].get('native_submits', 0) == 0
+    assert rel_err(first[True][1], first[False][1], _floor(first[False][1])) <= (3e-7 if dt == np.float32 else 1e-10)
+    assert e1.stats.get('native_submits', 0) == 1
+    assert any(j['cfg'].sparse.n_comp > 0 for j in e1._fast_jobs.values())
+    assert e0.stats.get('native_submits', 0) == 1
+    assert not any(j['cfg'].sparse.n_comp > 0 for j in e0._fast_jobs.values())
     assert e1.stats.get('fast_path_redo', 0) + e1.stats.get('downdate_redo', 0) == 0
     assert prob1 == prob0 == [6]
     exp, _ = orc.interp_chunk(data2, intrp_dtype=np.float64, faithful=False, **kw, **base)
