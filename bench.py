@@ -165,6 +165,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = threading.Event()
         self.nvml = None
+        self._max_sm = None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -182,7 +183,9 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self):
         nv = self.nvml
         sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        if self._max_sm is None:                       # constant: asked once
+            self._max_sm = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        mx = self._max_sm
         try:
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
         except Exception:
@@ -211,7 +214,10 @@ class ClockSampler(threading.Thread):
                         self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
+            # 10 samples per second: every NVML query takes the driver's lock, which on an
+            # 8-GPU box holds up the kernel launches of all ranks for a moment; the timed
+            # regions of a run add up to seconds, so the median clock is still well sampled
+            self.stop_flag.wait(0.1 if self.nvml is not None else 0.25)
 
     def summary(self):
         if not self.samples:

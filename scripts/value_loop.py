@@ -17,6 +17,9 @@ if world > 1 and os.environ.get('NO_DIST') != '1':
     import torch.distributed as dist
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 chunks = [bench.make_chunk(rank, v) for v in range(4)]
+if os.environ.get('VL_PINNED_IN') == '1':   # station data in pinned host memory
+    for c in chunks:
+        c['data'] = torch.from_numpy(c['data']).pin_memory().numpy()
 eng = ChunkEngine()
 if os.environ.get('VL_NATIVE') == '0':
     eng.native_submit = False
@@ -53,6 +56,28 @@ for rep in range(3):
     ts = run(steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print('rank %d rep %d: %.3f ms/step (submit %.3f ms/step) native_submits=%s affinity %d cores' % (
-        rank, rep, 1e3 * dt / steps, 1e3 * ts / steps, eng.stats.get('native_submits'),
-        len(os.sched_getaffinity(0))), flush=True)
+    print('rank %d rep %d: %.3f ms/step (submit %.3f ms/step) native_submits=%s affinity %d cores; '
+          'native host ms of the last chunk [slot wait, scan, plan, uploads, solve, estimate] %s' % (
+              rank, rep, 1e3 * dt / steps, 1e3 * ts / steps, eng.stats.get('native_submits'),
+              len(os.sched_getaffinity(0)),
+              ['%.3f' % v for v in eng.stats.get('fast_host_ms', [])]), flush=True)
+
+if os.environ.get('VL_PROF') == '1':
+    eng.collect_profile()
+    est = sorted(e[3] for e in eng.kernel_events[-steps:])
+    sol = sorted(eng.solve_ms[-steps:])
+    job = next(iter(eng._fast_jobs.values()))
+    ptrs = {'d_arena': job['d_arena'].data_ptr()}
+    for i, k in enumerate(job['keep']):
+        if isinstance(k, dict):
+            for name, t in k.items():
+                if torch.is_tensor(t):
+                    ptrs['%d.%s' % (i, name)] = t.data_ptr()
+                elif isinstance(t, (tuple, list)):
+                    for j, tt in enumerate(t):
+                        if torch.is_tensor(tt):
+                            ptrs['%d.%s%d' % (i, name, j)] = tt.data_ptr()
+    print('rank %d estimate ms min/med/max %.3f %.3f %.3f  solve ms min/med/max %.3f %.3f %.3f' % (
+        rank, est[0], est[len(est) // 2], est[-1], sol[0], sol[len(sol) // 2], sol[-1]))
+    print('rank %d ptrs' % rank, {k: hex(v) for k, v in ptrs.items()})
+    print('rank %d mem' % rank, torch.cuda.memory_allocated() >> 20, torch.cuda.memory_reserved() >> 20)
