@@ -19,6 +19,7 @@ outputs left in HBM), `e2e` (host buffers in, pinned host buffers out),
 host cores).
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -473,16 +474,20 @@ def run_gpu(args):
         counter[0] += 1
         return pool[counter[0] % len(pool)]
 
+    PIPE_DEPTH = 2
+
     def run_resident(n):
-        """n chunks, pipelined one deep: chunk i+1 is prepared and queued while
-        chunk i runs; outputs stay in HBM."""
-        pend = None
+        """n chunks, pipelined: up to PIPE_DEPTH chunks are prepared and queued ahead of the
+        one whose result is taken (the host runs ahead of the GPU, so a slow host moment --
+        eight ranks share the host's cores -- does not starve the device); outputs stay in
+        HBM."""
+        pend = collections.deque()
         for _ in range(n):
-            nxt = eng.submit_chunk(**kw, **next_chunk(chunks))
-            if pend is not None:
-                pend.result(to_host=False)
-            pend = nxt
-        pend.result(to_host=False)
+            if len(pend) == PIPE_DEPTH:
+                pend.popleft().result(to_host=False)
+            pend.append(eng.submit_chunk(**kw, **next_chunk(chunks)))
+        while pend:
+            pend.popleft().result(to_host=False)
 
     # ---- end-to-end path: host inputs (pinned), results back in host memory ------------
     # The chunk goes through the public call with the output stage of the reference's writer
@@ -767,7 +772,8 @@ def run_gpu(args):
                 'grid': [NY, NX], 'missing': MISS, 'parallelism': 'time-sharded x%d' % world,
                 'l2': 'each step writes a %.1f GB field (>> 126 MB L2) between reuses'
                       % (cell_steps * 4 / 1e9),
-                'pipeline': 'chunk i+1 is prepared/queued while chunk i runs (engine.submit_chunk)',
+                'pipeline': 'up to %d chunks are prepared / queued ahead of the one whose result is '
+                            'taken (engine.submit_chunk)' % PIPE_DEPTH,
                 'chunks': '%d distinct chunks of time steps cycled; data-independent per-job '
                           'structures (inverse of the full station system, stations within the '
                           'variogram range of each cell) are cached across chunks' % N_VARIANTS,

@@ -25,17 +25,21 @@ if os.environ.get('VL_NATIVE') == '0':
     eng.native_submit = False
 kw = dict(interp_args=bench.INTERP_ARGS, vgs=[bench.VG] * bench.CHUNK_STEPS, intrp_dtype=np.float32)
 
+DEPTH = int(os.environ.get('VL_DEPTH', '2'))
+
+
 def run(n):
-    pend = None
+    import collections
+    pend = collections.deque()
     t_sub = 0.0
     for i in range(n):
+        if len(pend) == DEPTH:
+            pend.popleft().result(to_host=False)
         t0 = time.perf_counter()
-        nxt = eng.submit_chunk(**kw, **chunks[i % 4])
+        pend.append(eng.submit_chunk(**kw, **chunks[i % 4]))
         t_sub += time.perf_counter() - t0
-        if pend is not None:
-            pend.result(to_host=False)
-        pend = nxt
-    pend.result(to_host=False)
+    while pend:
+        pend.popleft().result(to_host=False)
     return t_sub
 
 keep = []
