@@ -611,6 +611,11 @@ int spx_estimate_local_dev(const spx_local* l, void* stream);
  * 0: on B200 the staged variant measured 1.14 ms against 0.89 ms per 5 GB field, see
  * DESIGN.md).  Returns the previous setting.  Results are bit-identical either way. */
 int spx_local_set_bulk(int on);
+/* spx_estimate_gemm_dev splits a large K (kpad >~ 1000: at most 16 cells fit beside a full-K
+ * tile) over up to max_passes launches whose partial sums travel through a stream-ordered f64
+ * scratch in HBM; 0 / 1 = never, -1 = environment SPX_GEMM_KSPLIT (default 4).  Returns the
+ * previous setting (test / measurement aid). */
+int spx_gemm_set_ksplit(int max_passes);
 
 /* ---- one native call per time chunk (the planned fast path) ------------------------
  * The common case of the compute half of SpInterpSteps.interpolate_subset

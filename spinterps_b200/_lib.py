@@ -264,6 +264,7 @@ _SIGS = {
     'spx_local_build_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_estimate_local_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_local_set_bulk': (C.c_int, [C.c_int]),
+    'spx_gemm_set_ksplit': (C.c_int, [C.c_int]),
     'spx_local_tiles_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

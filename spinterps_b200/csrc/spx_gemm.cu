@@ -55,6 +55,14 @@ struct GemmArgs {
     double lo, hi;
     int n_stages;
     int quad_slot;
+    // K split over several passes (large K: few cells fit beside a full-K B tile): this
+    // launch covers the k-chunks [kc_lo, kc_lo + kc_n) of 4 columns each; the accumulators
+    // start from part_in (f64 [n_rows, n_cells], NULL = zero) and, when part_out is set, are
+    // stored there raw instead of going through the epilogue (which only the last pass runs)
+    int kc_lo, kc_n;
+    const double* part_in;
+    double* part_out;
+    int* zk_glob;       // IDW: station on the cell centre, found by whichever pass holds it
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -126,15 +134,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
     constexpr int GEMM_THREADS = (CW + 1) * 32;
     constexpr int RW = SPX_BM / CW;   // rows per warp
     constexpr int MI = RW / 8;        // 8-row MMA tiles per warp
-    const int KC = a.kpad >> 2;
-    const int n_ksteps = a.kpad / BK;
+    const int KC = a.kc_n;                  // k-chunks of this pass (all of them: kpad / 4)
+    const int KC_ALL = a.kpad >> 2;
+    const int k_lo = a.kc_lo * 4;           // first coefficient column of this pass
+    const int k_n = a.kc_n * 4;
+    const int n_ksteps = k_n / BK;
     const int n_stages = a.n_stages;
 
     double* Bs = reinterpret_cast<double*>(smem_raw);                  // [KC][NT][32]
     double* As = Bs + (size_t)KC * NT * 32;                            // [stage][2][32][32]
-    double* sx = As + (size_t)n_stages * STAGE_DOUBLES;                // [kpad] station x
-    double* sy = sx + a.kpad;                                          // [kpad] station y
-    double* cx = sy + a.kpad;                                          // [BN]
+    double* sx = As + (size_t)n_stages * STAGE_DOUBLES;                // [k_n] station x
+    double* sy = sx + k_n;                                             // [k_n] station y
+    double* cx = sy + k_n;                                             // [BN]
     double* cy = cx + BN;                                              // [BN]
     double* qs = cy + BN;                                              // [BN] quadratic forms
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(qs + BN);         // [n_stages]
@@ -154,9 +165,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int k = tid; k < a.kpad; k += GEMM_THREADS) {
-        sx[k] = (k < a.n_stn) ? a.stn_x[k] : 0.0;
-        sy[k] = (k < a.n_stn) ? a.stn_y[k] : 0.0;
+    for (int k = tid; k < k_n; k += GEMM_THREADS) {
+        sx[k] = (k_lo + k < a.n_stn) ? a.stn_x[k_lo + k] : 0.0;
+        sy[k] = (k_lo + k < a.n_stn) ? a.stn_y[k_lo + k] : 0.0;
     }
     __syncthreads();
 
@@ -189,12 +200,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
             const int q = idx >> 5;
             const int j = q % NT;
             const int kc = q / NT;
-            const int k = kc * 4 + (ln & 3);
+            const int k = kc * 4 + (ln & 3);          // column inside this pass
+            const int kg = k_lo + k;                  // coefficient column
             const int n = j * 8 + (ln >> 2);
             const int64_t c = cell0 + n;
             double v = 0.0;
             if (c < a.n_cells) {
-                if (k < a.n_stn) {
+                if (kg < a.n_stn) {
                     if (a.gen == SPX_GEN_VG) {
                         const double dx = cx[n] - sx[k], dy = cy[n] - sy[k];
                         const double h = sqrt(dx * dx + dy * dy);
@@ -211,19 +223,24 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                             // sum-of-weights epilogue (SPX_EPI_AUX) restores the NaN for the
                             // groups that have the station.
                             v = 0.0;
-                            zk[n] = k;
+                            zk[n] = kg;
+                            if (a.zk_glob) a.zk_glob[c] = kg;
                         } else {
                             v = idw_weight(d2, a.inv_scale, a.idw_exp);
                         }
                     }
-                } else if (k < a.n_stn + a.n_border) {
-                    const int b = k - a.n_stn;
+                } else if (kg < a.n_stn + a.n_border) {
+                    const int b = kg - a.n_stn;
                     v = (b == 0) ? 1.0 : a.cell_drift[(int64_t)(b - 1) * a.n_cells + c];
                 }
             }
             Bs[idx] = v;
         }
         __syncthreads();
+        if (a.zk_glob && !a.part_out) {     // last pass: stations found by the earlier ones
+            if (tid < BN && cell0 + tid < a.n_cells && zk[tid] < 0) zk[tid] = a.zk_glob[cell0 + tid];
+            __syncthreads();
+        }
 
         if (warp == CONSUMER_WARPS) {
             // ---- producer: stream coefficient stages ----------------------
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                 int s = stage;
                 uint32_t ph = phase;
                 for (int64_t mt = 0; mt < n_mtiles; ++mt) {
-                    const double* src = a.coef + (size_t)mt * KC * (SPX_BM * 4);
+                    const double* src = a.coef + ((size_t)mt * KC_ALL + a.kc_lo) * (SPX_BM * 4);
                     for (int ks = 0; ks < n_ksteps; ++ks) {
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -267,6 +284,26 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                if (a.part_in && active) {             // sums of the earlier K passes
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        const int64_t R = row_base + i * 8 + g;
+                        if (R >= a.n_rows) continue;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const int64_t c = cell0 + j * 8 + t4 * 2;       // even
+                            const double* src = a.part_in + R * a.n_cells + c;
+                            if (c + 1 < a.n_cells && (a.n_cells & 1) == 0) {
+                                const double2 v = __ldcs(reinterpret_cast<const double2*>(src));
+                                acc[i][j][0] = v.x;
+                                acc[i][j][1] = v.y;
+                            } else {
+                                if (c < a.n_cells) acc[i][j][0] = __ldcs(src);
+                                if (c + 1 < a.n_cells) acc[i][j][1] = __ldcs(src + 1);
+                            }
+                        }
+                    }
+                }
 
                 for (int ks = 0; ks < n_ksteps; ++ks) {
                     mbar_wait(&full_bar[s], ph);
@@ -293,6 +330,26 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
                     if (++s == n_stages) { s = 0; ph ^= 1; }
                 }
                 if (!active) continue;
+                if (a.part_out) {                      // not the last K pass: raw sums
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        const int64_t R = row_base + i * 8 + g;
+                        if (R >= a.n_rows) continue;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const int64_t c = cell0 + j * 8 + t4 * 2;       // even
+                            double* dstp = a.part_out + R * a.n_cells + c;
+                            if (c + 1 < a.n_cells && (a.n_cells & 1) == 0) {
+                                __stcs(reinterpret_cast<double2*>(dstp),
+                                       make_double2(acc[i][j][0], acc[i][j][1]));
+                            } else {
+                                if (c < a.n_cells) __stcs(dstp, acc[i][j][0]);
+                                if (c + 1 < a.n_cells) __stcs(dstp + 1, acc[i][j][1]);
+                            }
+                        }
+                    }
+                    continue;
+                }
                 // ---- epilogue -------------------------------------------
                 const bool pair_ok = (a.cell_pos == nullptr) && ((a.out_ld & 1) == 0);
 #pragma unroll
@@ -404,6 +461,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_estimate_gemm(const GemmAr
     }
 }
 
+// kpad: the K extent held by one launch (all of it, or one pass of a K split)
 static size_t gemm_smem_bytes(int kpad, int nt, int n_stages) {
     const size_t dbl = (size_t)(kpad / 4) * nt * 32 + (size_t)n_stages * STAGE_DOUBLES +
                        2 * (size_t)kpad + 3 * (size_t)nt * 8;
@@ -415,7 +473,8 @@ struct GemmCfg {
     size_t smem;
 };
 
-static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
+static int pick_config(const spx_gemm* g, GemmCfg* cfg, int k_extent = 0) {
+    const int kpad = k_extent > 0 ? k_extent : g->kpad;
     int dev = 0, max_smem = 0, n_sm = 0;
     SPX_CUDA(cudaGetDevice(&dev));
     SPX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -428,7 +487,7 @@ static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
         if (force_nt > 0 && nt > force_nt) continue;
         for (int st = max_st; st >= 2; --st) {
             if (st == 2 && nt > 1) continue;  // prefer fewer cells over a 2-deep ring
-            const size_t sm = gemm_smem_bytes(g->kpad, nt, st);
+            const size_t sm = gemm_smem_bytes(kpad, nt, st);
             if (sm <= (size_t)max_smem) {
                 // do not use tiles wider than the problem
                 int use_nt = nt;
@@ -449,6 +508,7 @@ static int pick_config(const spx_gemm* g, GemmCfg* cfg) {
 }
 
 static int g_consumer_warps = 16;  // SPX_GEMM_WARPS=8|16 overrides (tuning knob)
+static int g_ksplit = -1;          // largest number of K passes (-1: SPX_GEMM_KSPLIT, default 4; 0 / 1: off)
 
 template <int NT>
 static int launch(const GemmArgs& a, const GemmCfg& cfg, cudaStream_t st) {
@@ -504,6 +564,12 @@ using namespace spx;
 
 extern "C" {
 
+int spx_gemm_set_ksplit(int max_passes) {
+    const int prev = g_ksplit;
+    g_ksplit = max_passes;
+    return prev;
+}
+
 int spx_estimate_gemm_config(const spx_gemm* g, int* cells_per_block, int* n_stages,
                              int* smem_bytes, int* grid) {
     int rc = validate(g);
@@ -558,17 +624,97 @@ int spx_estimate_gemm_dev(const spx_gemm* g, void* stream) {
     a.hi = g->hi;
     a.n_stages = cfg.n_stages;
     a.quad_slot = g->quad_slot;
+    a.kc_lo = 0;
+    a.kc_n = g->kpad / 4;
+    a.part_in = nullptr;
+    a.part_out = nullptr;
+    a.zk_glob = nullptr;
 
     cudaStream_t st = (cudaStream_t)stream;
-    switch (cfg.nt) {
-        case 8: return launch<8>(a, cfg, st);
-        case 6: return launch<6>(a, cfg, st);
-        case 5: return launch<5>(a, cfg, st);
-        case 4: return launch<4>(a, cfg, st);
-        case 3: return launch<3>(a, cfg, st);
-        case 2: return launch<2>(a, cfg, st);
-        default: return launch<1>(a, cfg, st);
+    auto run = [&](const GemmCfg& c) -> int {
+        a.n_stages = c.n_stages;
+        switch (c.nt) {
+            case 8: return launch<8>(a, c, st);
+            case 6: return launch<6>(a, c, st);
+            case 5: return launch<5>(a, c, st);
+            case 4: return launch<4>(a, c, st);
+            case 3: return launch<3>(a, c, st);
+            case 2: return launch<2>(a, c, st);
+            default: return launch<1>(a, c, st);
+        }
+    };
+    // ---- large K: split it over passes --------------------------------------------------
+    // With a full-K B tile only 8-16 cells fit next to it at kpad ~ 2000 and every coefficient
+    // fragment feeds one or two DMMAs: the kernel is then bound by shared-memory traffic
+    // (0.53 of the FP64 tensor peak).  P passes over K / P columns each hold 4-5 cell groups
+    // like the kpad ~ 500 case (0.84); the partial sums travel through HBM as f64
+    // [n_rows, n_cells] (16 bytes per row and cell and extra pass: ~3 ms per 10 GB against
+    // hundreds of ms of contraction), the epilogue runs in the last pass only.
+    if (g_ksplit < 0) g_ksplit = getenv("SPX_GEMM_KSPLIT") ? atoi(getenv("SPX_GEMM_KSPLIT")) : 4;
+    const int split_knob = g_ksplit;
+    const int64_t part_bytes = g->n_rows * g->n_cells * (int64_t)sizeof(double);
+    if (cfg.nt <= 2 && split_knob >= 2 && g->epi != SPX_EPI_QUADFORM &&
+        part_bytes <= (int64_t)24 << 30 && g->n_cells >= 64) {
+        const int kc_all = g->kpad / 4;
+        int best_p = 1;
+        GemmCfg best = cfg;
+        for (int P = 2; P <= split_knob && P <= 8; ++P) {
+            int kc_pass = (kc_all + P - 1) / P;
+            kc_pass += kc_pass & 1;                        // stages hold two k-chunks
+            GemmCfg c;
+            if (pick_config(g, &c, kc_pass * 4) != SPX_OK) continue;
+            if (c.nt > best.nt) { best = c; best_p = P; }
+            if (c.nt >= 5) break;
+        }
+        if (best_p > 1) {
+            static bool pool_set = false;
+            if (!pool_set) {                               // keep freed blocks for the next call
+                int dev = 0;
+                cudaMemPool_t pool;
+                SPX_CUDA(cudaGetDevice(&dev));
+                SPX_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+                uint64_t keep = ~0ull;
+                SPX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+                pool_set = true;
+            }
+            double* part = nullptr;
+            int* zkg = nullptr;
+            if (cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)part_bytes, st) !=
+                cudaSuccess) {
+                cudaGetLastError();                        // no room for the partial sums:
+                return run(cfg);                           // one pass over the full K
+            }
+            if (g->gen == SPX_GEN_IDW) {
+                if (cudaMallocAsync(reinterpret_cast<void**>(&zkg),
+                                    sizeof(int) * (size_t)g->n_cells, st) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaFreeAsync(part, st);
+                    return run(cfg);
+                }
+                SPX_CUDA(cudaMemsetAsync(zkg, 0xFF, sizeof(int) * (size_t)g->n_cells, st));
+            }
+            int kc_pass = (kc_all + best_p - 1) / best_p;
+            kc_pass += kc_pass & 1;
+            int rc2 = SPX_OK;
+            for (int pss = 0, lo = 0; lo < kc_all && rc2 == SPX_OK; ++pss, lo += kc_pass) {
+                const int n = (kc_all - lo < kc_pass) ? kc_all - lo : kc_pass;   // even: kpad % 8 == 0
+                const bool last = lo + n >= kc_all;
+                a.kc_lo = lo;
+                a.kc_n = n;
+                a.part_in = pss ? part : nullptr;
+                a.part_out = last ? nullptr : part;
+                a.zk_glob = zkg;
+                GemmCfg c = best;
+                if (n != kc_pass && pick_config(g, &c, n * 4) != SPX_OK) c = best;
+                c.smem = gemm_smem_bytes(n * 4, c.nt, c.n_stages);
+                rc2 = run(c);
+            }
+            cudaFreeAsync(part, st);
+            if (zkg) cudaFreeAsync(zkg, st);
+            return rc2;
+        }
     }
+    return run(cfg);
 }
 
 }  // extern "C"

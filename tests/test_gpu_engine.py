@@ -802,3 +802,41 @@ def test_sparse_covariance_solve_needs_small_clusters():
     exp, _ = orc.interp_chunk(p['data'][::-1].copy(), intrp_dtype=np.float64, faithful=False,
                               **kw, **base)
     assert rel_err(got['OK'], exp['OK'], _floor(exp['OK'])) <= KRG_TOL
+
+
+@pytest.mark.parametrize('kind', ['idw', 'ok'])
+def test_gemm_k_split_matches_single_pass(kind):
+    """Large K (>~ 1000 stations): the contraction runs in several passes over K whose partial
+    sums travel through HBM (spx_gemm_set_ksplit); same numbers as one pass over the full K
+    (different summation order: 1e-13), incl. a station on a cell centre that is found in a
+    pass other than the last one, missing data and a ragged number of cells."""
+    from spinterps_b200 import _lib
+    from spinterps_b200.engine import ChunkEngine
+    lib = _lib.load()
+    p = make_problem(131, 1300, 6, 33, 37, cell=3000.0, miss=0.1)
+    p['stn_xs'][7], p['stn_ys'][7] = p['cell_xs'][400], p['cell_ys'][400]     # first K pass
+    p['data'][:, 7] = 4.5
+    p['data'][2, 7] = np.nan
+    if kind == 'idw':
+        args = [('IDW', None, 'IDW_000', 2.0), ('IDW', None, 'IDW_001', 3.0)]
+        kw = dict(interp_args=args, intrp_dtype=np.float64, **p)
+    else:
+        kw = dict(interp_args=[('OK', None, 'OK')], vgs=['0.1 Nug(0.0) + 0.9 Exp(60000)'] * 6,
+                  intrp_dtype=np.float64, **p)
+    outs = {}
+    prev = lib.spx_gemm_set_ksplit(4)
+    try:
+        for passes in (4, 0):
+            lib.spx_gemm_set_ksplit(passes)
+            e = ChunkEngine()
+            e.local_support = False
+            outs[passes], _ = e.interp_chunk(**kw)
+    finally:
+        lib.spx_gemm_set_ksplit(prev)
+    for lab in outs[0]:
+        a, b = outs[4][lab], outs[0][lab]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), lab
+        assert rel_err(a, b, _floor(b)) <= 1e-12, lab
+    if kind == 'idw':
+        assert np.isnan(outs[4]['IDW_000'][[0, 1, 3, 4, 5], 400]).all()
+        assert np.isfinite(outs[4]['IDW_000'][2, 400])
