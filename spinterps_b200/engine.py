@@ -57,6 +57,46 @@ def availability_groups(avail):
     return grp_of_step, grp_mask
 
 
+def station_clusters(sx, sy, R, max_size):
+    """Connected components of the graph "stations closer than R" as labels 0..n_comp-1 per
+    station, or None when a component has more than ``max_size`` stations (or the graph is
+    dense).  NumPy only: importing scipy here would cost the first chunk of a job 0.4 s."""
+    sx = np.asarray(sx, dtype=np.float64)
+    sy = np.asarray(sy, dtype=np.float64)
+    n = sx.size
+    # a little beyond R: pairs at exactly the range have vg == F anyway (their C entry is 0)
+    r2 = (R * (1.0 + 1e-12) + 1e-9) ** 2
+    ei, ej = [], []
+    n_pairs = 0
+    for b0 in range(0, n, 2048):                      # row blocks of the distance matrix
+        b1 = min(n, b0 + 2048)
+        d2 = (sx[b0:b1, None] - sx[None, :]) ** 2 + (sy[b0:b1, None] - sy[None, :]) ** 2
+        ii, jj = np.nonzero(d2 < r2)
+        keep = jj > ii + b0
+        ei.append(ii[keep] + b0)
+        ej.append(jj[keep])
+        n_pairs += int(keep.sum())
+        if n_pairs > 8 * n:
+            return None                               # dense graph: no small clusters
+    ei, ej = np.concatenate(ei), np.concatenate(ej)
+    # min-label propagation converges within the diameter of the largest component, so more
+    # than max_size rounds means a component that is too large
+    lab = np.arange(n, dtype=np.int64)
+    for _ in range(int(max_size) + 1):
+        new = lab.copy()
+        np.minimum.at(new, ei, lab[ej])
+        np.minimum.at(new, ej, lab[ei])
+        if np.array_equal(new, lab):
+            break
+        lab = new
+    else:
+        return None
+    _, lab = np.unique(lab, return_inverse=True)
+    if np.bincount(lab).max() > max_size:
+        return None
+    return lab
+
+
 class _LazyCtx(dict):
     """Per-chunk context; entries of ``lazy`` (byte masks, NaN -> 0 data, ...) are built on
     first use -- the common path needs none of them."""
@@ -1760,41 +1800,11 @@ class ChunkEngine:
         (spx_krige_sparse_ok_dev) instead of a dense factorisation -- same system, same
         solution to rounding."""
         n = ctx['n_stn']
-        sx, sy = ctx['stn_xs'], ctx['stn_ys']
-        # pairs closer than R (a little beyond: pairs at exactly the range have vg == F anyway,
-        # their C entry is 0), row blocks of the distance matrix; NumPy only -- importing
-        # scipy here would cost the first chunk of a job 0.4 s
-        r2 = (R * (1.0 + 1e-12) + 1e-9) ** 2
-        ei, ej = [], []
-        n_pairs = 0
-        for b0 in range(0, n, 2048):
-            b1 = min(n, b0 + 2048)
-            d2 = (sx[b0:b1, None] - sx[None, :]) ** 2 + (sy[b0:b1, None] - sy[None, :]) ** 2
-            ii, jj = np.nonzero(d2 < r2)
-            keep = jj > ii + b0
-            ei.append(ii[keep] + b0)
-            ej.append(jj[keep])
-            n_pairs += int(keep.sum())
-            if n_pairs > 8 * n:
-                return None                       # dense graph: no small clusters
-        ei, ej = np.concatenate(ei), np.concatenate(ej)
-        # connected components by min-label propagation: converges within the diameter of the
-        # largest component, so more than max_size rounds means a component that is too large
-        lab = np.arange(n, dtype=np.int64)
-        for _ in range(_lib.SPX_SPARSE_MAX_COMP + 1):
-            new = lab.copy()
-            np.minimum.at(new, ei, lab[ej])
-            np.minimum.at(new, ej, lab[ei])
-            if np.array_equal(new, lab):
-                break
-            lab = new
-        else:
+        lab = station_clusters(ctx['stn_xs'], ctx['stn_ys'], R, _lib.SPX_SPARSE_MAX_COMP)
+        if lab is None:
             return None
-        _, lab = np.unique(lab, return_inverse=True)
         n_comp = int(lab.max()) + 1
         sizes = np.bincount(lab, minlength=n_comp)
-        if sizes.max() > _lib.SPX_SPARSE_MAX_COMP:
-            return None
         # components by size (singles first: the kernel's lanes then share their code path),
         # members of a component by station index
         rank = np.empty(n_comp, dtype=np.int64)

@@ -334,3 +334,29 @@ def test_unpack_field_host_matches_numpy_division():
         assert np.array_equal(got[keep], exp[keep], equal_nan=True)
         assert np.array_equal(np.signbit(got[keep]), np.signbit(exp[keep]))
         assert (got[~keep] == -1.0).all() and (out[:, G:] == -1.0).all()
+
+
+@pytest.mark.parametrize('seed,n,ny,nx,R,expect', [(2, 500, 1000, 1000, 20000.0, True),
+                                                   (71, 220, 256, 280, 11000.0, True),
+                                                   (73, 150, 160, 176, 20000.0, False),
+                                                   (5, 3000, 300, 300, 2500.0, False)])
+def test_station_clusters_match_scipy_components(seed, n, ny, nx, R, expect):
+    """engine.station_clusters (the partition behind the sparse-covariance solve): same
+    connected components as scipy's, None when one has more than 8 stations."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    from spinterps_b200.engine import station_clusters
+    from tests.synth import make_problem
+    p = make_problem(seed, n, 2, ny, nx, cell=1000.0)
+    sx, sy = p['stn_xs'], p['stn_ys']
+    pairs = cKDTree(np.column_stack([sx, sy])).query_pairs(R, output_type='ndarray')
+    n_comp, ref = connected_components(
+        coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n)), directed=False)
+    lab = station_clusters(sx, sy, R, 8)
+    if not expect:
+        assert lab is None and np.bincount(ref).max() > 8
+        return
+    assert lab is not None and lab.max() + 1 == n_comp
+    assert len(set(zip(lab.tolist(), ref.tolist()))) == n_comp        # same partition
+    assert np.bincount(lab).max() <= 8
