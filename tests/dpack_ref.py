@@ -51,7 +51,7 @@ def _size(codes, pay):
     return len(pay) + (sum(1 for c in codes if c) + 1) // 2
 
 
-def encode_tile(x, p, rounded_input=True):
+def encode_tile(x, p):
     """Record (bytes) of one tile; x float32 [n <= 256]."""
     n = x.size
     bits = x.view(np.uint32)
