@@ -732,13 +732,81 @@ def interp_chunk(
 
 
 # ---------------------------------------------------------------------------
-# Grid preparation.  PARITY UNPINNED for this part: the reference
-# does it with OGR / GDAL (misc.py:407-540 ``chk_pt_cntmnt_in_polys_mp`` = Contains on
-# polygons buffered with geom.Buffer, interp/drift.py:165-226), which are absent from the
-# build container, so no reference output could be generated.  The functions below are
-# the checker for the CUDA kernels: the same formulas in plain NumPy (IEEE operations in
-# the same order, no FMA), pinned only by hand-made known answers in the tests.
+# Grid preparation.  The reference does the geometric part with OGR /
+# GDAL (misc.py:407-540 ``chk_pt_cntmnt_in_polys_mp`` = Contains on polygons buffered with
+# geom.Buffer, interp/drift.py:25-226), which are absent from the build container.
+# Parity is pinned as far as the reference's own code goes: ``tests/golden/p*_prep_*.npz``
+# are outputs of the reference's preparation methods run unmodified over in-memory
+# stand-ins for the two libraries (``tests/golden/make_golden_prep.py``) -- bounds, row /
+# column window, cell centres, the containment search around the predicate, the cell mask,
+# the selected stations, drift values of cells and stations.  NOT pinned: GEOS's own
+# predicates on points closer to an outline than the sagitta of its buffer arcs (30
+# segments per quadrant) -- the fixtures hold no such point, and here the exact distance is
+# used.  The functions below are the checker for the CUDA kernels: the same formulas in
+# plain NumPy (IEEE operations in the same order, no FMA).
 # ---------------------------------------------------------------------------
+def prepare_grid(stn_xs, stn_ys, cell_size, cell_bdist=0.0, rings=None, raster_geo=None):
+    """Bounds (interp/prepare.py:107-137), row / column window (:150-182) and cell-centre
+    coordinates (:188-199) of the interpolation grid.
+
+    rings : outer rings of the selection polygons or None (bounds from the stations).
+    raster_geo : (x_min, y_max, n_rows, n_cols) of the drift rasters or None; their bounds
+    are rounded to 6 decimals (interp/drift.py:134-152) and the window is relative to them.
+    Returns (bounds [x_min, x_max, y_min, y_max], window [min_row, max_row, min_col,
+    max_col], x coordinates [n_cols], y coordinates [n_rows])."""
+    import math
+    if rings is not None:
+        allv = np.concatenate([np.asarray(r, dtype=np.float64) for r in rings], axis=0)
+        x_min, x_max = allv[:, 0].min(), allv[:, 0].max()
+        y_min, y_max = allv[:, 1].min(), allv[:, 1].max()
+    else:
+        x_min, x_max = np.min(stn_xs), np.max(stn_xs)
+        y_min, y_max = np.min(stn_ys), np.max(stn_ys)
+    x_min -= cell_bdist
+    x_max += cell_bdist
+    y_min -= cell_bdist
+    y_max += cell_bdist
+    if raster_geo is not None:
+        rx_min, ry_max, n_rows, n_cols = raster_geo
+        rx_min, rx_max, ry_min, ry_max = np.round(
+            (rx_min, rx_min + n_cols * cell_size, ry_max - n_rows * cell_size, ry_max), 6)
+        assert x_min >= rx_min and x_max <= rx_max and y_min >= ry_min and y_max <= ry_max
+        min_col = int(math.floor((x_min - rx_min) / cell_size))
+        max_col = int(math.ceil((x_max - rx_min) / cell_size)) - 1
+        min_row = int(math.floor((ry_max - y_max) / cell_size))
+        max_row = int(math.ceil((ry_max - y_min) / cell_size)) - 1
+    else:
+        min_col = min_row = 0
+        max_col = int(math.ceil((x_max - x_min) / cell_size)) - 1
+        max_row = int(math.ceil((y_max - y_min) / cell_size)) - 1
+    assert 0 <= min_col <= max_col and 0 <= min_row <= max_row
+    strt_x = x_min + (0.5 * cell_size)
+    end_x = strt_x + ((max_col - min_col) * cell_size)
+    strt_y = y_max - (0.5 * cell_size)
+    end_y = strt_y - ((max_row - min_row) * cell_size)
+    xs = np.linspace(strt_x, end_x, (max_col - min_col + 1))
+    ys = np.linspace(strt_y, end_y, (max_row - min_row + 1))
+    return (np.array([x_min, x_max, y_min, y_max]),
+            np.array([min_row, max_row, min_col, max_col], dtype=np.int64), xs, ys)
+
+
+def drift_window_indices(window, cntn_idxs=None):
+    """Raster (row, col) of every (selected) grid cell, interp/drift.py:175-188."""
+    min_row, max_row, min_col, max_col = (int(v) for v in window)
+    cols, rows = np.meshgrid(np.arange(min_col, max_col + 1), np.arange(min_row, max_row + 1))
+    rows, cols = rows.ravel(), cols.ravel()
+    if cntn_idxs is not None:
+        rows, cols = rows[cntn_idxs], cols[cntn_idxs]
+    return rows, cols
+
+
+def drift_station_indices(stn_xs, stn_ys, ras_x_min, ras_y_max, cell_size):
+    """Raster (row, col) of the stations, interp/drift.py:209-210 (``int()`` truncates)."""
+    cols = np.array([int((x - ras_x_min) / cell_size) for x in np.asarray(stn_xs)], dtype=np.int64)
+    rows = np.array([int((ras_y_max - y) / cell_size) for y in np.asarray(stn_ys)], dtype=np.int64)
+    return rows, cols
+
+
 def points_in_polygons(xs, ys, rings, buffer_dist=0.0):
     """bool [n]: inside any ring by the even-odd crossing rule, or (buffer_dist > 0)
     closer than buffer_dist to a ring edge."""

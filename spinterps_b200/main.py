@@ -483,6 +483,10 @@ class SpInterpMain:
             self._time_rng = self._data_df.index
 
         # grid: interp/prepare.py:92-242
+        arr_ras = [f for f in (self._drft_rass or []) if not callable(f)] if self._edk_flag else []
+        if arr_ras:
+            # the drift rasters decide the cell size (interp/prepare.py:549-550)
+            self._cell_size = arr_ras[0]['cell_size']
         assert self._cell_size is not None, 'Cell size unspecified!'
         cs = self._cell_size
         if self._poly_rings is not None:
@@ -506,28 +510,42 @@ class SpInterpMain:
         y_min -= self._cell_bdist
         y_max += self._cell_bdist
         self._x_min, self._x_max, self._y_min, self._y_max = x_min, x_max, y_min, y_max
-        arr_ras = [f for f in (self._drft_rass or []) if not callable(f)] if self._edk_flag else []
         if arr_ras:
             # with drift rasters the row / column window is RASTER-relative
             # (interp/prepare.py:150-173): a grid origin that is not aligned to the raster
-            # spans one more column / row than ceil((x_max - x_min) / cell)
+            # spans one more column / row than ceil((x_max - x_min) / cell).  Raster bounds
+            # rounded to 6 decimals like interp/drift.py:134-152
             f0 = arr_ras[0]
             nr0, nc0 = f0['values'].shape
-            assert np.isclose(f0['cell_size'], cs), 'Drift raster cell size != grid cell size!'
-            assert x_min >= f0['x_min'], 'Grid x_min outside of the drift rasters!'
-            assert x_max <= f0['x_min'] + nc0 * cs, 'Grid x_max outside of drift rasters!'
-            assert y_min >= f0['y_max'] - nr0 * cs, 'Grid y_min outside of the drift rasters!'
-            assert y_max <= f0['y_max'], 'Grid y_max outside of drift rasters!'
-            min_col = int(floor((x_min - f0['x_min']) / cs))
-            max_col = int(ceil((x_max - f0['x_min']) / cs)) - 1
-            min_row = int(floor((f0['y_max'] - y_max) / cs))
-            max_row = int(ceil((f0['y_max'] - y_min) / cs)) - 1
+            for f in arr_ras:
+                assert np.isclose(f['cell_size'], cs), (
+                    f"Drift raster's cell width {f['cell_size']} unequal to the one used {cs}!")
+                assert f['values'].shape == (nr0, nc0) and np.isclose(
+                    f['x_min'], f0['x_min']) and np.isclose(f['y_max'], f0['y_max']), (
+                        'Drift rasters have dissimilar spatial properties!')
+                assert (f['ndv'] is None) == (f0['ndv'] is None) and (
+                    f['ndv'] is None or np.isclose(f['ndv'], f0['ndv'])), (
+                        'Drift rasters have dissimilar spatial properties!')
+            dx_min, dx_max, dy_min, dy_max = (float(v) for v in np.round(
+                (f0['x_min'], f0['x_min'] + nc0 * cs, f0['y_max'] - nr0 * cs, f0['y_max']), 6))
+            self._drft_x_min, self._drft_x_max = dx_min, dx_max
+            self._drft_y_min, self._drft_y_max = dy_min, dy_max
+            assert x_min >= dx_min, 'Grid x_min outside of the drift rasters!'
+            assert x_max <= dx_max, 'Grid x_max outside of drift rasters!'
+            assert y_min >= dy_min, 'Grid y_min outside of the drift rasters!'
+            assert y_max <= dy_max, 'Grid y_max outside of drift rasters!'
+            min_col = int(floor((x_min - dx_min) / cs))
+            max_col = int(ceil((x_max - dx_min) / cs)) - 1
+            min_row = int(floor((dy_max - y_max) / cs))
+            max_row = int(ceil((dy_max - y_min) / cs)) - 1
         else:
             min_col = min_row = 0
             max_col = int(ceil((x_max - x_min) / cs)) - 1
             max_row = int(ceil((y_max - y_min) / cs)) - 1
         assert 0 <= min_col <= max_col, (min_col, max_col)
         assert 0 <= min_row <= max_row, (min_row, max_row)
+        self._min_row, self._max_row = min_row, max_row
+        self._min_col, self._max_col = min_col, max_col
         n_cols, n_rows = max_col - min_col + 1, max_row - min_row + 1
         xs = np.linspace(x_min + 0.5 * cs, x_min + 0.5 * cs + (n_cols - 1) * cs, n_cols)
         ys = np.linspace(y_max - 0.5 * cs, y_max - 0.5 * cs - (n_rows - 1) * cs, n_rows)
@@ -574,19 +592,12 @@ class SpInterpMain:
                 # the row / column window of interp/prepare.py:150-172, stations through
                 # int((x - x_min) / cell), int((y_max - y) / cell))
                 from . import prep
-                assert np.isclose(f['cell_size'], cs), 'Drift raster cell size != grid cell size!'
-                assert x_min >= f['x_min'] and y_max <= f['y_max'], (
-                    'Grid outside of the drift rasters!')
-                nr, nc = f['values'].shape
-                assert x_max <= f['x_min'] + nc * cs and y_min >= f['y_max'] - nr * cs, (
-                    'Grid outside of the drift rasters!')
-                assert np.isclose(f['x_min'], arr_ras[0]['x_min']) and np.isclose(
-                    f['y_max'], arr_ras[0]['y_max']), 'Drift rasters with different extents!'
+                ndv = arr_ras[0]['ndv']         # interp/drift.py:154: the first raster's
                 rr, cc = prep.drift_cell_indices(min_row, max_row, min_col, max_col,
                                                  self._cntn_idxs)
-                cell_rows.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
-                rr, cc = prep.drift_point_indices(sx, sy, f['x_min'], f['y_max'], cs)
-                stn_cols.append(prep.sample_raster(f['values'], rr, cc, f['ndv']))
+                cell_rows.append(prep.sample_raster(f['values'], rr, cc, ndv))
+                rr, cc = prep.drift_point_indices(sx, sy, self._drft_x_min, self._drft_y_max, cs)
+                stn_cols.append(prep.sample_raster(f['values'], rr, cc, ndv))
             self._drft_arrs = np.vstack(cell_rows)
             self._stns_drft_df = pd.DataFrame(np.column_stack(stn_cols), index=self._crds_df.index)
             assert np.all(np.isfinite(self._stns_drft_df.values)), (   # interp/drift.py:221-222

@@ -1,7 +1,7 @@
 """Grid preparation: point-in-polygon cell / station selection and
-drift raster sampling.  The oracle (NumPy) is pinned by hand-made known answers -- the
-reference does this part with OGR / GDAL, which are absent ("parity unpinned" for this
-row) -- and the CUDA kernels must reproduce the oracle exactly (integer / index work)."""
+drift raster sampling: hand-made known answers for the oracle (NumPy) and seeded
+comparisons of the CUDA kernels with it (integer / index work: exact).  The fixtures
+produced by the reference's own preparation code are in ``test_prep_golden.py``."""
 import numpy as np
 import pytest
 
