@@ -500,6 +500,12 @@ int spx_nrst_max_neighbors(void);
 int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
                       const uint8_t* mask, const double* cell_x, const double* cell_y,
                       int64_t n_cells, int32_t k, int32_t* nb, int64_t* hash, void* stream);
+/* spx_nrst_topk_dev has two kernels with identical results: one warp per cell (distances
+ * as 64-bit keys in shared memory, k-th smallest by bisection with warp-wide counting,
+ * default) and one thread per cell (sorted insertion; used when the keys of four cells do
+ * not fit into shared memory: n_stn > 6,400).  on: 1 / 0, -1 = environment SPX_TOPK_WARP
+ * (default 1).  Returns the previous setting. */
+int spx_nrst_set_topk_warp(int on);
 /* 'pie' selection (interp/grps.py:168-247 with cyth/interpmthds.pyx:811-890): stations
  * binned into n_pies angular sectors around the cell, ranked by distance inside their
  * sector; nb = the first k stations in (rank, distance) order, indices ascending; hash

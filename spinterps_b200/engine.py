@@ -838,9 +838,17 @@ class ChunkEngine:
         if nrst:
             # stations never among the n_nebs nearest of any cell are dropped up-front
             # (interp/steps.py:592-608, quirk Q9)
-            nb0, _ = self._topk(self._dev(stn_xs), self._dev(stn_ys), n_stn, None,
-                                self._dev(dst_xs), self._dev(dst_ys), n_cells, int(n_nebs))
-            tke = torch.unique(nb0).cpu().numpy()
+            # depends on the coordinates only: once per job and geometry, not per chunk
+            pkey = (stn_xs.tobytes(), stn_ys.tobytes(), int(n_nebs), int(self._n_pies))
+            prune = geo.setdefault('nrst_prune', {})
+            tke = prune.get(pkey)
+            if tke is None:
+                nb0, _ = self._topk(self._dev_const(stn_xs), self._dev_const(stn_ys), n_stn, None,
+                                    geo['d_cell_x'], geo['d_cell_y'], n_cells, int(n_nebs))
+                tke = torch.unique(nb0).cpu().numpy()
+                while len(prune) >= 4:
+                    prune.pop(next(iter(prune)))
+                prune[pkey] = tke
             if tke.size != n_stn:
                 stn_xs = np.ascontiguousarray(stn_xs[tke])
                 stn_ys = np.ascontiguousarray(stn_ys[tke])

@@ -558,6 +558,58 @@ def test_neighbour_indices_bit_exact_large_station_sets(mthd, n_stn, k, n_pies):
                             p['cell_ys'], avail=avail)
 
 
+@pytest.mark.parametrize('n_stn,k,lattice', [(77, 10, True), (500, 100, False), (1000, 50, True),
+                                              (2500, 160, False), (33, 40, False)])
+def test_topk_warp_kernel_equals_the_insertion_kernel(n_stn, k, lattice):
+    """spx_nrst_topk_dev has a warp-per-cell kernel (bisection on the distance keys) and a
+    thread-per-cell kernel (sorted insertion): rows AND hashes identical, with equidistant
+    stations (lattice coordinates: ties go to the lower index), masks, k > 64, k > number
+    of available stations (padded with -1) and a station count that is not a multiple of 32."""
+    import torch
+    from spinterps_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n_stn + k)
+    if lattice:
+        sx = rng.integers(0, 12, n_stn).astype(np.float64) * 1000.0
+        sy = rng.integers(0, 12, n_stn).astype(np.float64) * 1000.0
+        cx = rng.integers(0, 24, 3000).astype(np.float64) * 500.0
+        cy = rng.integers(0, 24, 3000).astype(np.float64) * 500.0
+    else:
+        sx, sy = rng.uniform(0, 1e5, n_stn), rng.uniform(0, 1e5, n_stn)
+        cx, cy = rng.uniform(0, 1e5, 3001), rng.uniform(0, 1e5, 3001)
+    dev = torch.device('cuda:0')
+    d_sx, d_sy = torch.from_numpy(sx).to(dev), torch.from_numpy(sy).to(dev)
+    d_cx, d_cy = torch.from_numpy(cx).to(dev), torch.from_numpy(cy).to(dev)
+    masks = [None, torch.from_numpy((rng.random(n_stn) > 0.3).astype(np.uint8)).to(dev)]
+    prev = lib.spx_nrst_set_topk_warp(1)
+    try:
+        for d_mask in masks:
+            res = []
+            for warp in (1, 0):
+                lib.spx_nrst_set_topk_warp(warp)
+                nb = torch.full((cx.size, k), -7, dtype=torch.int32, device=dev)
+                hsh = torch.full((cx.size,), -7, dtype=torch.int64, device=dev)
+                _lib.check(lib.spx_nrst_topk_dev(
+                    d_sx.data_ptr(), d_sy.data_ptr(), n_stn,
+                    None if d_mask is None else d_mask.data_ptr(), d_cx.data_ptr(),
+                    d_cy.data_ptr(), cx.size, k, nb.data_ptr(), hsh.data_ptr(), None), 'topk')
+                torch.cuda.synchronize()
+                res.append((nb.cpu().numpy(), hsh.cpu().numpy()))
+            assert np.array_equal(res[0][0], res[1][0])
+            assert np.array_equal(res[0][1], res[1][1])
+            # against NumPy: the k smallest (distance, index) pairs, indices ascending
+            ok = np.ones(n_stn, bool) if d_mask is None else d_mask.cpu().numpy().astype(bool)
+            for c in rng.integers(0, cx.size, 25):
+                dx, dy = cx[c] - sx, cy[c] - sy
+                d = np.sqrt(dx * dx + dy * dy)
+                cand = np.flatnonzero(ok)
+                sel = np.sort(cand[np.lexsort((cand, d[cand]))][:k])
+                exp = np.concatenate([sel, np.full(k - sel.size, -1)])
+                assert np.array_equal(res[0][0][c], exp), c
+    finally:
+        lib.spx_nrst_set_topk_warp(prev)
+
+
 def test_cached_geometry_survives_the_upload_arena_ring():
     """Seven chunks through ONE engine (the upload arenas are a ring of four): every label of
     every chunk equals the result of a fresh engine.  (Device copies that outlive a chunk --
