@@ -506,6 +506,12 @@ int spx_nrst_topk_dev(const double* stn_x, const double* stn_y, int32_t n_stn,
  * not fit into shared memory: n_stn > 6,400).  on: 1 / 0, -1 = environment SPX_TOPK_WARP
  * (default 1).  Returns the previous setting. */
 int spx_nrst_set_topk_warp(int on);
+/* spx_nrst_solve_dev runs the substitutions of the right-hand sides either with one thread
+ * per right-hand side (up to 128 side by side in shared memory; systems up to ~70 unknowns,
+ * default) or with one warp per right-hand side (any size); same operations in the same
+ * order, identical coefficients.  on: 1 / 0, -1 = environment SPX_NRST_THREAD_RHS (default
+ * 1).  Returns the previous setting. */
+int spx_nrst_set_thread_rhs(int on);
 /* 'pie' selection (interp/grps.py:168-247 with cyth/interpmthds.pyx:811-890): stations
  * binned into n_pies angular sectors around the cell, ranked by distance inside their
  * sector; nb = the first k stations in (rank, distance) order, indices ascending; hash

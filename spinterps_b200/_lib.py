@@ -268,6 +268,7 @@ _SIGS = {
     'spx_local_tiles_dev': (C.c_int, [C.POINTER(spx_local), C.c_void_p]),
     'spx_nrst_max_neighbors': (C.c_int, []),
     'spx_nrst_set_topk_warp': (C.c_int, [C.c_int]),
+    'spx_nrst_set_thread_rhs': (C.c_int, [C.c_int]),
     'spx_nrst_topk_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),

@@ -273,6 +273,8 @@ struct NrstSolveArgs {
     int32_t* info;                // [n_grp]
     double* inv;                  // optional [u_end - u_beg, m, m]: A^-1 (estimation variance)
     int u_beg;                    // first system of this launch
+    int tb;                       // > 0: right-hand sides per batch, one THREAD each; 0: one warp each
+    int y_doubles;                // doubles of the right-hand side area behind the matrix
 };
 
 __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
@@ -281,8 +283,8 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
     const int k = a.k, m = a.k + a.n_border;
     const int ld = m | 1;
     double* S = ssm;                        // [ld * m] column-major
-    double* ys = S + (size_t)ld * m;        // [4][ld]
-    int* pv = reinterpret_cast<int*>(ys + 4 * (size_t)ld);   // [m]
+    double* ys = S + (size_t)ld * m;        // [4][ld], or [m][tb | 1] (thread per right-hand side)
+    int* pv = reinterpret_cast<int*>(ys + (size_t)a.y_doubles);   // [m]
     int* st = pv + m;                       // [k]
     __shared__ double red_v[4];
     __shared__ int red_i[4];
@@ -357,10 +359,81 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
         __syncthreads();
     }
     if (tid == 0) a.info[u] = s_info;
-    // ---- right-hand sides: n_t data steps + the ones vector, one per warp
-    double* y = ys + (size_t)wid * ld;
     // with inv: m more right-hand sides, the unit vectors (columns of A^-1)
     const int n_rhs = a.n_t + 1 + (a.inv ? m : 0);
+    if (a.tb > 0) {
+        // ---- right-hand sides, one per THREAD: a.tb of them at a time side by side in shared
+        // memory (Y[i][q], odd pitch), every thread runs the two substitutions of its own
+        // column -- the same operations in the same order as the warp-per-right-hand-side
+        // path below, but tb independent dependency chains per block instead of 4, and the
+        // matrix entries are warp-wide broadcasts.
+        const int tbp = a.tb | 1;
+        double* Y = ys;
+        for (int q0 = 0; q0 < n_rhs; q0 += a.tb) {
+            const int nq = min(a.tb, n_rhs - q0);
+            if (tid < nq) {
+                const int q = q0 + tid;
+                const bool ones = (q == a.n_t);
+                const int unit = q - a.n_t - 1;             // >= 0: unit vector e_unit
+                double* y = Y + tid;
+                if (unit >= 0) {
+                    for (int i = 0; i < m; ++i) y[(size_t)i * tbp] = (i == unit) ? 1.0 : 0.0;
+                } else if (ones) {
+                    for (int i = 0; i < m; ++i) y[(size_t)i * tbp] = (i < k) ? 1.0 : 0.0;
+                } else {
+                    const double* __restrict__ z = a.data + (int64_t)a.steps[q] * a.n_stn;
+                    double zmax = -CUDART_INF, zsum = 0.0;
+                    for (int i = 0; i < k; ++i) {
+                        const double v = z[st[i]];
+                        zmax = fmax(zmax, v);
+                        zsum += v;
+                        y[(size_t)i * tbp] = v;
+                    }
+                    for (int i = k; i < m; ++i) y[(size_t)i * tbp] = 0.0;
+                    // steps.py:760-765 (all values below the threshold) and :325-331
+                    const bool bypass = !(zmax >= a.min_var_thr) || a.step_bypass[q];
+                    a.ovr[(int64_t)u * a.n_t + q] = bypass ? (zsum / k) : CUDART_NAN;
+                }
+                for (int c = 0; c < m; ++c) {
+                    const int p = pv[c];
+                    if (p != c) {
+                        const double t = y[(size_t)c * tbp];
+                        y[(size_t)c * tbp] = y[(size_t)p * tbp];
+                        y[(size_t)p * tbp] = t;
+                    }
+                }
+                for (int c = 0; c < m - 1; ++c) {
+                    const double xc = y[(size_t)c * tbp];
+                    const double* cc = S + (size_t)c * ld;
+#pragma unroll 4
+                    for (int i = c + 1; i < m; ++i)
+                        y[(size_t)i * tbp] = fma(-cc[i], xc, y[(size_t)i * tbp]);
+                }
+                for (int c = m - 1; c >= 0; --c) {
+                    const double* cc = S + (size_t)c * ld;
+                    const double xc = y[(size_t)c * tbp] / cc[c];
+                    y[(size_t)c * tbp] = xc;
+#pragma unroll 4
+                    for (int i = 0; i < c; ++i)
+                        y[(size_t)i * tbp] = fma(-cc[i], xc, y[(size_t)i * tbp]);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nq * m; idx += 128) {       // coalesced rows out
+                const int ql = idx / m, i = idx - ql * m;
+                const int q = q0 + ql;
+                const int unit = q - a.n_t - 1;
+                double* dst = (unit >= 0)
+                                  ? a.inv + ((int64_t)(u - a.u_beg) * m + unit) * m
+                                  : a.coef + ((int64_t)u * (a.n_t + 1) + q) * m;
+                dst[i] = Y[(size_t)i * tbp + ql];
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    // ---- right-hand sides: n_t data steps + the ones vector, one per warp
+    double* y = ys + (size_t)wid * ld;
     for (int q = wid; q < n_rhs; q += 4) {
         const bool ones = (q == a.n_t);
         const int unit = q - a.n_t - 1;                 // >= 0: unit vector e_unit
@@ -559,6 +632,13 @@ extern "C" {
 int spx_nrst_max_neighbors(void) { return NRST_KMAX; }
 
 static int g_topk_warp = -1;        // -1: environment SPX_TOPK_WARP (default 1)
+static int g_nrst_thread_rhs = -1;  // -1: environment SPX_NRST_THREAD_RHS (default 1)
+
+int spx_nrst_set_thread_rhs(int on) {
+    const int prev = g_nrst_thread_rhs;
+    g_nrst_thread_rhs = on;
+    return prev;
+}
 
 int spx_nrst_set_topk_warp(int on) {
     const int prev = g_topk_warp;
@@ -666,7 +746,27 @@ int spx_nrst_solve_dev(const spx_nrst* n, void* stream) {
     a.inv = n->inv;
     a.u_beg = u_beg;
     const int ld = m | 1;
-    const size_t smem = ((size_t)ld * m + 4 * (size_t)ld) * sizeof(double) +
+    // right-hand sides per batch with one thread each: balanced batches of at most 128, as
+    // long as the block stays below ~74 KB (three blocks per SM); larger systems keep the
+    // warp-per-right-hand-side substitution, which needs four vectors only
+    static const int rhs_env = getenv("SPX_NRST_THREAD_RHS") ? atoi(getenv("SPX_NRST_THREAD_RHS")) : 1;
+    const int rhs_knob = g_nrst_thread_rhs < 0 ? rhs_env : g_nrst_thread_rhs;
+    const int n_rhs = n->n_t + 1 + (n->inv ? m : 0);
+    a.tb = 0;
+    a.y_doubles = 4 * ld;
+    if (rhs_knob) {
+        const size_t budget = 74u * 1024u;
+        const size_t fixed = (size_t)ld * m * sizeof(double) + ((size_t)m + n->k) * sizeof(int);
+        int tb_max = 0;
+        if (budget > fixed) tb_max = (int)((budget - fixed) / ((size_t)m * sizeof(double))) - 1;
+        tb_max = std::min(tb_max, 128);
+        if (tb_max >= 32) {
+            const int n_batch = (n_rhs + tb_max - 1) / tb_max;
+            a.tb = (n_rhs + n_batch - 1) / n_batch;
+            a.y_doubles = std::max(4 * ld, m * (a.tb | 1));
+        }
+    }
+    const size_t smem = ((size_t)ld * m + (size_t)a.y_doubles) * sizeof(double) +
                         ((size_t)m + n->k) * sizeof(int);
     if (smem > 220 * 1024) {
         set_error("nrst_solve: a system of %d unknowns does not fit shared memory", m);

@@ -720,6 +720,38 @@ def test_est_vars_ok_with_nrst_and_pie(mthd, n_nebs, n_pies):
     assert np.nanmax(exp['EST_VARS_OK']) > 0.1 and (exp['EST_VARS_OK'] == 0).any()
 
 
+@pytest.mark.parametrize('n_steps', [5, 150])
+def test_nrst_solve_thread_and_warp_substitutions_agree(n_steps):
+    """k_nrst_solve substitutes either with one thread or with one warp per right-hand side
+    (same operations in the same order): identical OK / EDK / EST_VARS_OK fields; 150 steps
+    need two batches of right-hand sides."""
+    from spinterps_b200 import _lib
+    from spinterps_b200.engine import ChunkEngine
+    p = make_problem(37, 90, n_steps, 16, 21, cell=4000.0, miss=0.1)
+    rng = np.random.default_rng(38)
+    drft = rng.normal(500.0, 100.0, size=(1, p['cell_xs'].size))
+    sdrft = rng.normal(500.0, 100.0, size=(90, 1))
+    args = [('OK', None, 'OK'), ('EDK', None, 'EDK'), ('EST_VARS_OK', None, 'EST_VARS_OK')]
+    kw = dict(interp_args=args, vgs=[VG_C1] * n_steps, neb_sel_mthd='nrst', n_nebs=12,
+              est_var_flag=True, drft_arrs=drft, stns_drft=sdrft, intrp_dtype=np.float64, **p)
+    lib = _lib.load()
+    prev = lib.spx_nrst_set_thread_rhs(1)
+    try:
+        outs = []
+        for mode in (1, 0):
+            lib.spx_nrst_set_thread_rhs(mode)
+            got, _ = ChunkEngine().interp_chunk(**kw)
+            outs.append(got)
+    finally:
+        lib.spx_nrst_set_thread_rhs(prev)
+    for lab in ('OK', 'EDK', 'EST_VARS_OK'):
+        assert np.isfinite(outs[0][lab]).mean() > 0.9
+        assert np.array_equal(outs[0][lab], outs[1][lab], equal_nan=True), lab
+    if n_steps == 5:
+        exp, _ = orc.interp_chunk(faithful=False, **kw)
+        _check(outs[0], {lab: exp[lab] for lab in ('OK', 'EST_VARS_OK')}, 'nrst_thread_rhs')
+
+
 def test_nrst_with_100_neighbours():
     """More than 64 neighbours per cell (the reference has no cap, interp/grps.py:147-166):
     the 160-neighbour kernel variants, index rows bit-exact, OK / IDW fields vs the oracle."""
