@@ -351,10 +351,30 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
         if (pvv != 0.0)
             for (int i = c + 1 + tid; i < m; i += 128) cc[i] = cc[i] / pvv;
         __syncthreads();
-        for (int j = c + 1 + wid; j < m; j += 4) {
-            double* cj = S + (size_t)j * ld;
-            const double ucj = cj[c];
-            for (int i = c + 1 + lane; i < m; i += 32) cj[i] = fma(-cc[i], ucj, cj[i]);
+        // rank-1 update, four columns per warp and pass (loads of all four before the stores:
+        // same arithmetic per element, a quarter of the dependent shared-memory round trips)
+        for (int j = c + 1 + wid; j < m; j += 16) {
+            double* cj[4];
+            double uc[4];
+            bool on[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int jj = j + 4 * r;
+                on[r] = jj < m;
+                cj[r] = S + (size_t)min(jj, m - 1) * ld;
+                uc[r] = cj[r][c];
+            }
+            for (int i = c + 1 + lane; i < m; i += 32) {
+                const double l = cc[i];
+                double v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[r] = cj[r][i];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[r] = fma(-l, uc[r], v[r]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (on[r]) cj[r][i] = v[r];
+            }
         }
         __syncthreads();
     }
@@ -402,20 +422,73 @@ __global__ void __launch_bounds__(128) k_nrst_solve(NrstSolveArgs a) {
                         y[(size_t)p * tbp] = t;
                     }
                 }
-                for (int c = 0; c < m - 1; ++c) {
-                    const double xc = y[(size_t)c * tbp];
-                    const double* cc = S + (size_t)c * ld;
-#pragma unroll 4
-                    for (int i = c + 1; i < m; ++i)
-                        y[(size_t)i * tbp] = fma(-cc[i], xc, y[(size_t)i * tbp]);
+                // Both substitutions in dot-product form, four rows at a time in registers:
+                // every row still receives its updates in the order of the column sweeps
+                // of the warp path (forward: c ascending, backward: c descending, then the
+                // division), so the results are bit-identical, but the inner loops hold no
+                // shared-memory stores and four independent FMA chains.
+                for (int i0 = 1; i0 < m; i0 += 4) {
+                    const int i1 = min(i0 + 1, m - 1), i2 = min(i0 + 2, m - 1), i3 = min(i0 + 3, m - 1);
+                    double a0 = y[(size_t)i0 * tbp], a1 = y[(size_t)i1 * tbp];
+                    double a2 = y[(size_t)i2 * tbp], a3 = y[(size_t)i3 * tbp];
+#pragma unroll 2
+                    for (int c = 0; c < i0; ++c) {
+                        const double yc = y[(size_t)c * tbp];
+                        const double* col = S + (size_t)c * ld;
+                        a0 = fma(-col[i0], yc, a0);
+                        a1 = fma(-col[i1], yc, a1);
+                        a2 = fma(-col[i2], yc, a2);
+                        a3 = fma(-col[i3], yc, a3);
+                    }
+                    y[(size_t)i0 * tbp] = a0;
+                    if (i0 + 1 < m) {
+                        a1 = fma(-S[(i0 + 1) + (size_t)i0 * ld], a0, a1);
+                        y[(size_t)(i0 + 1) * tbp] = a1;
+                    }
+                    if (i0 + 2 < m) {
+                        a2 = fma(-S[(i0 + 2) + (size_t)i0 * ld], a0, a2);
+                        a2 = fma(-S[(i0 + 2) + (size_t)(i0 + 1) * ld], a1, a2);
+                        y[(size_t)(i0 + 2) * tbp] = a2;
+                    }
+                    if (i0 + 3 < m) {
+                        a3 = fma(-S[(i0 + 3) + (size_t)i0 * ld], a0, a3);
+                        a3 = fma(-S[(i0 + 3) + (size_t)(i0 + 1) * ld], a1, a3);
+                        a3 = fma(-S[(i0 + 3) + (size_t)(i0 + 2) * ld], a2, a3);
+                        y[(size_t)(i0 + 3) * tbp] = a3;
+                    }
                 }
-                for (int c = m - 1; c >= 0; --c) {
-                    const double* cc = S + (size_t)c * ld;
-                    const double xc = y[(size_t)c * tbp] / cc[c];
-                    y[(size_t)c * tbp] = xc;
-#pragma unroll 4
-                    for (int i = 0; i < c; ++i)
-                        y[(size_t)i * tbp] = fma(-cc[i], xc, y[(size_t)i * tbp]);
+                for (int i0 = m - 1; i0 >= 0; i0 -= 4) {
+                    const int i1 = max(i0 - 1, 0), i2 = max(i0 - 2, 0), i3 = max(i0 - 3, 0);
+                    double a0 = y[(size_t)i0 * tbp], a1 = y[(size_t)i1 * tbp];
+                    double a2 = y[(size_t)i2 * tbp], a3 = y[(size_t)i3 * tbp];
+#pragma unroll 2
+                    for (int c = m - 1; c > i0; --c) {
+                        const double xc = y[(size_t)c * tbp];
+                        const double* col = S + (size_t)c * ld;
+                        a0 = fma(-col[i0], xc, a0);
+                        a1 = fma(-col[i1], xc, a1);
+                        a2 = fma(-col[i2], xc, a2);
+                        a3 = fma(-col[i3], xc, a3);
+                    }
+                    const double x0 = a0 / S[i0 + (size_t)i0 * ld];
+                    y[(size_t)i0 * tbp] = x0;
+                    if (i0 - 1 >= 0) {
+                        a1 = fma(-S[(i0 - 1) + (size_t)i0 * ld], x0, a1);
+                        const double x1 = a1 / S[(i0 - 1) + (size_t)(i0 - 1) * ld];
+                        y[(size_t)(i0 - 1) * tbp] = x1;
+                        if (i0 - 2 >= 0) {
+                            a2 = fma(-S[(i0 - 2) + (size_t)i0 * ld], x0, a2);
+                            a2 = fma(-S[(i0 - 2) + (size_t)(i0 - 1) * ld], x1, a2);
+                            const double x2 = a2 / S[(i0 - 2) + (size_t)(i0 - 2) * ld];
+                            y[(size_t)(i0 - 2) * tbp] = x2;
+                            if (i0 - 3 >= 0) {
+                                a3 = fma(-S[(i0 - 3) + (size_t)i0 * ld], x0, a3);
+                                a3 = fma(-S[(i0 - 3) + (size_t)(i0 - 1) * ld], x1, a3);
+                                a3 = fma(-S[(i0 - 3) + (size_t)(i0 - 2) * ld], x2, a3);
+                                y[(size_t)(i0 - 3) * tbp] = a3 / S[(i0 - 3) + (size_t)(i0 - 3) * ld];
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
