@@ -1,7 +1,7 @@
 """Golden fixtures for the grid preparation from the
 UNMODIFIED reference.  Build container only (needs /root/reference):
 
-    python tests/golden/make_golden_prep.py
+    python tests/golden/make_golden_prep.py [--out DIR]
 
 The reference prepares the grid with OGR / GDAL, which are absent here.  This script runs
 the reference's own methods --
@@ -58,6 +58,9 @@ def check_margins(gis, xs, ys, rings, buf, what):
             worst = min(worst, d, abs(d - buf) - sag if buf > 0 else np.inf)
     assert worst > 1e-3, (what, worst)
     return worst
+
+
+OUT = HERE          # --out DIR writes the fixtures elsewhere (the regeneration test)
 
 
 def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdist=0.0,
@@ -143,7 +146,7 @@ def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdis
         out['drft_bounds'] = np.array([p._drft_x_min, p._drft_x_max, p._drft_y_min, p._drft_y_max])
         out['drft_arrs'] = p._drft_arrs
         out['stns_drft'] = p._stns_drft_df.loc[sel].values.astype(np.float64)
-    np.savez_compressed(HERE / f'{name}.npz', **out)
+    np.savez_compressed(OUT / f'{name}.npz', **out)
     print(name, 'grid', tuple(out['grid_shape']), 'cells', out['cell_xs'].size,
           'stations', len(sel), 'of', n_stn,
           'NaN drift cells', int(np.isnan(out['drft_arrs']).sum()) if rasters else '-')
@@ -214,4 +217,7 @@ def main():
 
 
 if __name__ == '__main__':
+    if '--out' in sys.argv:
+        OUT = Path(sys.argv[sys.argv.index('--out') + 1])
+        OUT.mkdir(parents=True, exist_ok=True)
     main()

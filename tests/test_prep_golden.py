@@ -30,6 +30,20 @@ def _raster_geo(d):
     return (x_min, y_max) + d['rasters'][0].shape
 
 
+@pytest.mark.skipif(not Path('/root/reference/interp/prepare.py').exists(),
+                    reason='needs the reference sources (build container only)')
+def test_fixtures_regenerate_from_the_reference(tmp_path):
+    """The committed fixtures ARE what the reference's preparation code produces: the
+    generating script, run again in a fresh process, writes byte-identical files."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(GOLD / 'make_golden_prep.py'), '--out', str(tmp_path)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in CASES:
+        assert (tmp_path / f'{name}.npz').read_bytes() == (GOLD / f'{name}.npz').read_bytes(), name
+
+
 @pytest.mark.parametrize('name', CASES)
 def test_oracle_preparation_matches_the_reference(name):
     d = _load(name)
