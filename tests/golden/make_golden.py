@@ -3,7 +3,7 @@
 Run in the build container only (needs /root/reference; ~1 min for the Cython
 build):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--out DIR]
 
 It imports the reference package from /root/reference exactly as SURVEY.md
 section 8c describes (pyximport with a writable build dir, MagicMock stubs for
@@ -23,6 +23,7 @@ import numpy as np
 import pandas as pd
 
 HERE = Path(__file__).resolve().parent
+OUT = HERE          # --out DIR writes the fixtures elsewhere (the regeneration test)
 REF = Path('/root/reference')
 
 
@@ -331,7 +332,7 @@ def save_case(name, case, flds):
             d[key] = np.asarray(val)
     for lab, arr in flds.items():
         d['out__' + lab] = arr
-    np.savez_compressed(HERE / f'{name}.npz', **d)
+    np.savez_compressed(OUT / f'{name}.npz', **d)
 
 
 def install_pie_shim(im):
@@ -352,7 +353,7 @@ def install_pie_shim(im):
 def main():
     im, SpInterpSteps, misc = import_reference()
     install_pie_shim(im)
-    np.savez_compressed(HERE / 'kats.npz', **kats(im, misc))
+    np.savez_compressed(OUT / 'kats.npz', **kats(im, misc))
     if '--kats-only' in sys.argv:
         return
     only = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--only=')]
@@ -367,4 +368,7 @@ def main():
 
 
 if __name__ == '__main__':
+    if '--out' in sys.argv:
+        OUT = Path(sys.argv[sys.argv.index('--out') + 1])
+        OUT.mkdir(parents=True, exist_ok=True)
     main()

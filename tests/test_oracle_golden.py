@@ -92,3 +92,20 @@ def test_oracle_matches_reference(name, faithful):
         if name == 'f_vg_families':
             tol = 1e-6  # ill-conditioned Gau/Pow systems amplify gemv-vs-gemm noise
         assert rel_err(flds[lab], ref) <= tol, (name, lab, rel_err(flds[lab], ref))
+
+
+@pytest.mark.skipif(not __import__('pathlib').Path('/root/reference/interp/steps.py').exists(),
+                    reason='needs the reference sources (build container only)')
+def test_fixtures_regenerate_from_the_reference(tmp_path):
+    """The committed fixtures ARE outputs of the unmodified reference: the generating script,
+    run again in a fresh process (pyximport build of the reference's Cython module), writes
+    byte-identical files."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(GOLDEN / 'make_golden.py'), '--out', str(tmp_path)],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    names = sorted(p.name for p in tmp_path.glob('*.npz'))
+    assert set(names) >= {f'{c}.npz' for c in CASES} | {'kats.npz'}
+    for n in names:
+        assert (tmp_path / n).read_bytes() == (GOLDEN / n).read_bytes(), n
