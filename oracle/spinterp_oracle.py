@@ -745,13 +745,69 @@ def interp_chunk(
 # used.  The functions below are the checker for the CUDA kernels: the same formulas in
 # plain NumPy (IEEE operations in the same order, no FMA).
 # ---------------------------------------------------------------------------
-def prepare_grid(stn_xs, stn_ys, cell_size, cell_bdist=0.0, rings=None, raster_geo=None):
-    """Bounds (interp/prepare.py:107-137), row / column window (:150-182) and cell-centre
-    coordinates (:188-199) of the interpolation grid.
+def aligned_grid_bounds(align, extent, cell_bdist):
+    """misc.py:743-885 ``get_aligned_shp_bds_and_cell_size``: the extent (+- cell_bdist) of
+    the polygons -- or, without polygons, of the alignment raster itself -- moved outwards
+    to the raster's cell lattice.  align = (x_min, y_max, cell_size, n_rows, n_cols)."""
+    rx_min, ry_max, cs, n_rows, n_cols = align
+    rel_cell_err = 1e-5
+    abs_cell_err = abs(cs * rel_cell_err)
+    rx_max = rx_min + (n_cols * cs)                       # misc.py:657-658
+    ry_min = ry_max - (n_rows * cs)
+    if extent is not None:
+        sx_min, sx_max, sy_min, sy_max = extent
+        if cell_bdist:
+            sx_min -= cell_bdist
+            sx_max += cell_bdist
+            sy_min -= cell_bdist
+            sy_max += cell_bdist
+    else:
+        sx_min, sx_max, sy_min, sy_max = rx_min, rx_max, ry_min, ry_max
+    if sx_min < rx_min:
+        assert abs(sx_min - rx_min) <= abs_cell_err
+    if sx_max > rx_max:
+        assert abs(sx_max - rx_max) <= abs_cell_err
+    if sy_min < ry_min:
+        assert abs(sy_min - ry_min) <= abs_cell_err
+    if sy_max > ry_max:
+        assert abs(sy_max - ry_max) <= abs_cell_err
+    if not np.isclose(sx_min, rx_min, rtol=0, atol=rel_cell_err):
+        rem = ((sx_min - rx_min) / cs) % 1
+        adj = rem * cs
+        ax_min = sx_min - adj
+    else:
+        ax_min = rx_min
+    if not np.isclose(sy_max, ry_max, rtol=0, atol=rel_cell_err):
+        rem = ((ry_max - sy_max) / cs) % 1
+        adj = rem * cs
+        ay_max = sy_max + adj
+    else:
+        ay_max = ry_max
+    if not np.isclose(sx_max, rx_max, rtol=0, atol=rel_cell_err):
+        rem = ((sx_max - rx_min) / cs) % 1
+        adj = rem * cs
+        ax_max = sx_max + (cs - adj)
+    else:
+        ax_max = rx_max
+    if not np.isclose(sy_min, ry_min, rtol=0, atol=rel_cell_err):
+        rem = ((ry_max - sy_min) / cs) % 1
+        adj = rem * cs
+        ay_min = sy_min - (cs - adj)
+    else:
+        ay_min = ry_min
+    assert ax_min >= rx_min and ax_max <= rx_max and ay_min >= ry_min and ay_max <= ry_max
+    return ax_min, ax_max, ay_min, ay_max
+
+
+def prepare_grid(stn_xs, stn_ys, cell_size, cell_bdist=0.0, rings=None, raster_geo=None,
+                 align=None):
+    """Bounds (interp/prepare.py:107-137, or :45-90 with an alignment raster), row / column
+    window (:150-182) and cell-centre coordinates (:188-199) of the interpolation grid.
 
     rings : outer rings of the selection polygons or None (bounds from the stations).
     raster_geo : (x_min, y_max, n_rows, n_cols) of the drift rasters or None; their bounds
     are rounded to 6 decimals (interp/drift.py:134-152) and the window is relative to them.
+    align : (x_min, y_max, cell_size, n_rows, n_cols) of the alignment raster or None.
     Returns (bounds [x_min, x_max, y_min, y_max], window [min_row, max_row, min_col,
     max_col], x coordinates [n_cols], y coordinates [n_rows])."""
     import math
@@ -762,6 +818,11 @@ def prepare_grid(stn_xs, stn_ys, cell_size, cell_bdist=0.0, rings=None, raster_g
     else:
         x_min, x_max = np.min(stn_xs), np.max(stn_xs)
         y_min, y_max = np.min(stn_ys), np.max(stn_ys)
+    if align is not None:
+        x_min, x_max, y_min, y_max = aligned_grid_bounds(
+            align, (float(x_min), float(x_max), float(y_min), float(y_max)) if rings is not None
+            else None, cell_bdist)
+        cell_bdist = 0.0
     x_min -= cell_bdist
     x_max += cell_bdist
     y_min -= cell_bdist

@@ -309,8 +309,28 @@ class SpInterpMain:
         self._ipoly_flag = True
 
     def set_alignment_raster(self, align_raster):
-        """interp/data.py:463-494 -- needs GDAL (absent here)."""
-        raise ImportError('set_alignment_raster needs GDAL; set cell_size in set_misc_settings')
+        """interp/data.py:463-494.  The grid bounds are snapped to the cell lattice of this
+        raster and its cell size is used (interp/prepare.py:45-90).  Array level: a dict
+        with the raster's geometry -- ``x_min``, ``y_max``, ``cell_size`` and ``n_rows`` /
+        ``n_cols`` (or ``values``, whose shape gives them); reading a raster file needs GDAL."""
+        if isinstance(align_raster, dict):
+            assert {'x_min', 'y_max', 'cell_size'} <= set(align_raster), (
+                'array alignment raster needs x_min, y_max, cell_size and n_rows / n_cols')
+            if 'values' in align_raster:
+                n_rows, n_cols = np.asarray(align_raster['values']).shape
+            else:
+                n_rows, n_cols = int(align_raster['n_rows']), int(align_raster['n_cols'])
+            cs = float(align_raster['cell_size'])
+            assert 0 < cs < np.inf and n_rows > 0 and n_cols > 0
+            self._algn_ras = dict(x_min=float(align_raster['x_min']),
+                                  y_max=float(align_raster['y_max']), cell_size=cs,
+                                  n_rows=int(n_rows), n_cols=int(n_cols))
+            self._algn_ras_set_flag = True
+            return
+        assert isinstance(align_raster, (str, Path)), (
+            'align_raster has to be a string or a pathlib.Path object!')
+        raise ImportError('reading an alignment raster file needs GDAL; pass its geometry as '
+                          'a dict (x_min, y_max, cell_size, n_rows, n_cols)')
 
     def set_neighbor_selection_method(self, selection_method, n_neighbors=None, n_pies=None):
         """interp/data.py:496-588."""
@@ -484,9 +504,12 @@ class SpInterpMain:
 
         # grid: interp/prepare.py:92-242
         arr_ras = [f for f in (self._drft_rass or []) if not callable(f)] if self._edk_flag else []
-        if arr_ras:
+        if arr_ras and not self._algn_ras_set_flag:
             # the drift rasters decide the cell size (interp/prepare.py:549-550)
             self._cell_size = arr_ras[0]['cell_size']
+        if self._algn_ras_set_flag:
+            # ... unless an alignment raster is set (interp/prepare.py:553-555, :45-90)
+            self._cell_size = self._algn_ras['cell_size']
         assert self._cell_size is not None, 'Cell size unspecified!'
         cs = self._cell_size
         if self._poly_rings is not None:
@@ -505,10 +528,20 @@ class SpInterpMain:
         else:
             x_min, x_max = self._crds_df['X'].min(), self._crds_df['X'].max()
             y_min, y_max = self._crds_df['Y'].min(), self._crds_df['Y'].max()
-        x_min -= self._cell_bdist
-        x_max += self._cell_bdist
-        y_min -= self._cell_bdist
-        y_max += self._cell_bdist
+        if self._algn_ras_set_flag:
+            # bounds snapped outwards to the alignment raster's lattice; without polygons
+            # the grid is the raster's extent (interp/prepare.py:45-90, misc.py:743-885)
+            from . import prep
+            a = self._algn_ras
+            (x_min, x_max, y_min, y_max), _ = prep.aligned_bounds(
+                a['x_min'], a['y_max'], a['cell_size'], a['n_rows'], a['n_cols'],
+                (x_min, x_max, y_min, y_max) if self._poly_rings is not None else None,
+                self._cell_bdist)
+        else:
+            x_min -= self._cell_bdist
+            x_max += self._cell_bdist
+            y_min -= self._cell_bdist
+            y_max += self._cell_bdist
         self._x_min, self._x_max, self._y_min, self._y_max = x_min, x_max, y_min, y_max
         if arr_ras:
             # with drift rasters the row / column window is RASTER-relative

@@ -112,3 +112,54 @@ def drift_point_indices(xs, ys, ras_x_min, ras_y_max, cell_size):
     cols = np.trunc((xs - ras_x_min) / cell_size).astype(np.int64)
     rows = np.trunc((ras_y_max - ys) / cell_size).astype(np.int64)
     return rows, cols
+
+
+def aligned_bounds(ras_x_min, ras_y_max, ras_cell_size, ras_n_rows, ras_n_cols,
+                   extent=None, cell_bdist=0.0):
+    """Grid bounds snapped outwards to the cell lattice of an alignment raster
+    (misc.py:743-885 ``get_aligned_shp_bds_and_cell_size``; host arithmetic).
+
+    extent: (x_min, x_max, y_min, y_max) of the selection polygons, or None -- then the
+    grid is the raster's own extent (the reference's ``bounds_shp_file == 'None'``).
+    Returns ((x_min, x_max, y_min, y_max), cell_size)."""
+    rel_cell_err = 1e-5
+    cs = float(ras_cell_size)
+    abs_cell_err = abs(cs * rel_cell_err)
+    ras_min_x, ras_max_y = float(ras_x_min), float(ras_y_max)
+    ras_max_x = ras_min_x + (ras_n_cols * cs)                  # misc.py:657-658
+    ras_min_y = ras_max_y - (ras_n_rows * cs)
+    if extent is not None:
+        x0, x1, y0, y1 = (float(v) for v in extent)
+        if cell_bdist:
+            x0 -= cell_bdist
+            x1 += cell_bdist
+            y0 -= cell_bdist
+            y1 += cell_bdist
+    else:
+        x0, x1, y0, y1 = ras_min_x, ras_max_x, ras_min_y, ras_max_y
+    assert not (x0 < ras_min_x) or abs(x0 - ras_min_x) <= abs_cell_err, (
+        f'bounds_shp x_min ({x0}) < align_raster x_min ({ras_min_x})!')
+    assert not (x1 > ras_max_x) or abs(x1 - ras_max_x) <= abs_cell_err, (
+        f'bounds_shp x_max ({x1}) < align_raster x_max ({ras_max_x})!')
+    assert not (y0 < ras_min_y) or abs(y0 - ras_min_y) <= abs_cell_err, (
+        f'bounds_shp y_min ({y0}) < align_raster y_min ({ras_min_y})!')
+    assert not (y1 > ras_max_y) or abs(y1 - ras_max_y) <= abs_cell_err, (
+        f'bounds_shp y_max ({y1}) < align_raster y_max ({ras_max_y})!')
+
+    def near(a, b):
+        return bool(np.isclose(a, b, rtol=0, atol=rel_cell_err))
+
+    # west / north edges move out to the lattice line at or before them, east / south edges
+    # to the line after them (one whole cell further when they sit on a line already)
+    ax0 = ras_min_x if near(x0, ras_min_x) else x0 - (((x0 - ras_min_x) / cs) % 1) * cs
+    ay1 = ras_max_y if near(y1, ras_max_y) else y1 + (((ras_max_y - y1) / cs) % 1) * cs
+    ax1 = ras_max_x if near(x1, ras_max_x) else x1 + (cs - (((x1 - ras_min_x) / cs) % 1) * cs)
+    ay0 = ras_min_y if near(y0, ras_min_y) else y0 - (cs - (((ras_max_y - y0) / cs) % 1) * cs)
+    for rem in ((ax1 - ax0) % cs, (ay1 - ay0) % cs):
+        assert near(rem, 0.0) or near(rem, cs), 'adjusted bounds off the alignment lattice'
+    assert ax0 >= ras_min_x, f'Adjusted bounds_shp x_min ({ax0}) < align_raster x_min ({ras_min_x})!'
+    assert ax1 <= ras_max_x, f'Adjusted bounds_shp x_max ({ax1}) < align_raster x_max ({ras_max_x})!'
+    assert ay0 >= ras_min_y, f'Adjusted bounds_shp y_min ({ay0}) < align_raster y_min ({ras_min_y})!'
+    assert ay1 <= ras_max_y, f'Adjusted bounds_shp y_max ({ay1}) < align_raster y_max ({ras_max_y})!'
+    return (ax0, ax1, ay0, ay1), cs
+

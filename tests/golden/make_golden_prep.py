@@ -7,6 +7,8 @@ The reference prepares the grid with OGR / GDAL, which are absent here.  This sc
 the reference's own methods --
 
     SpInterpPrepare._cmpt_corner_coordinates      interp/prepare.py:92-146
+    SpInterpPrepare._cmpt_aligned_coordinates     interp/prepare.py:45-90
+        -> misc.get_aligned_shp_bds_and_cell_size (misc.py:743-885)
     SpInterpBoundaryPolygons._select_nearest_stations   interp/bdpolys.py:26-182
         -> misc.get_all_polys_in_shp / linearize_sub_polys / chk_pt_cntmnt_in_polys_mp
            (misc.py:221-286, :372-404, :407-540)
@@ -64,7 +66,7 @@ OUT = HERE          # --out DIR writes the fixtures elsewhere (the regeneration 
 
 
 def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdist=0.0,
-             cell_bdist=0.0, ipoly=True, rasters=None):
+             cell_bdist=0.0, ipoly=True, rasters=None, align=None):
     prep_mod, misc = mods
     n_stn = stn_xs.size
     labels = [f'S{i:05d}' for i in range(n_stn)]
@@ -82,7 +84,12 @@ def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdis
     p._stn_bdist = float(stn_bdist)
     p._ipoly_flag = bool(ipoly)
     p._cell_sel_prms_set = rings is not None
-    p._algn_ras_set_flag = False
+    p._algn_ras_set_flag = align is not None
+    p._poly_shp = None
+    if align is not None:       # (x_min, y_max, cell_size, n_rows, n_cols): geometry only
+        p._algn_ras = Path(f'/standin/{name}_align.tif')
+        gis.add_raster(p._algn_ras, np.zeros((align[3], align[4])), align[0], align[1],
+                       align[2], None)
     p._poly_simplify_tol_ratio = 0.0
     p._plot_figs_flag = False
     p._edk_flag = rasters is not None
@@ -99,7 +106,10 @@ def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdis
     # interp/prepare.py:549-594, the GIS-dependent half of _prepare in its order
     if p._edk_flag and (not p._algn_ras_set_flag):
         p._cell_size = misc.get_ras_props(str(p._drft_rass[0]))[6]
-    p._cmpt_corner_coordinates()
+    if p._algn_ras_set_flag:
+        p._cmpt_aligned_coordinates()       # updates the cell size to the raster's
+    else:
+        p._cmpt_corner_coordinates()
     assert p._cell_size is not None
     if p._cell_sel_prms_set:
         p._select_nearest_stations()
@@ -125,6 +135,7 @@ def run_case(mods, gis, name, *, stn_xs, stn_ys, cell_size, rings=None, stn_bdis
         stn_bdist=np.float64(stn_bdist), cell_bdist=np.float64(cell_bdist), ipoly=np.bool_(ipoly),
         n_rings=np.int64(0 if rings is None else len(rings)),
         n_rasters=np.int64(0 if rasters is None else len(rasters)),
+        align=np.array([np.nan] * 5 if align is None else align, dtype=np.float64),
         cell_size=np.float64(p._cell_size),
         bounds=np.array([p._x_min, p._x_max, p._y_min, p._y_max]),
         window=np.array([p._min_row, p._max_row, p._min_col, p._max_col], dtype=np.int64),
@@ -214,6 +225,30 @@ def main():
     run_case(mods, gis, 'p4_prep_polys_nobuf_aligned', stn_xs=xs, stn_ys=ys, cell_size=None,
              rings=rings, stn_bdist=0.0, cell_bdist=0.0, ipoly=True,
              rasters=[dict(values=ras, x_min=rx0, y_max=ry1, cell_size=cs, ndv=None)])
+
+
+    # p5: alignment raster + polygons (stations and cells by buffer) + a drift raster on
+    # the same lattice: bounds snapped outwards to the alignment lattice, cell size from it
+    rng = np.random.default_rng(25)
+    xs = rng.uniform(0, 9e4, 60)
+    ys = rng.uniform(0, 7e4, 60)
+    rings = [star(3.3e4, 3.1e4, 2.0e4, 1.1e4, n=6, rot=0.4), star(6.4e4, 4.4e4, 1.4e4, 1.1e4, n=7)]
+    cs = 1500.0
+    ax0, ay1 = -3.0e4 + 137.0, 1.2e5 + 61.0          # lattice origin unrelated to the polygons
+    ras = rng.normal(400.0, 50.0, (110, 120))
+    ras[50:52, 60:63] = -32768.0
+    run_case(mods, gis, 'p5_prep_align_polys_edk', stn_xs=xs, stn_ys=ys, cell_size=None,
+             rings=rings, stn_bdist=1.2e4, cell_bdist=2450.0, ipoly=True,
+             rasters=[dict(values=ras, x_min=ax0 - 3 * cs, y_max=ay1 + 2 * cs, cell_size=cs,
+                           ndv=-32768.0)],
+             align=(ax0, ay1, cs, 100, 110))
+
+    # p6: alignment raster alone: the grid is the raster's extent
+    rng = np.random.default_rng(26)
+    xs = rng.uniform(1.0e4, 5.0e4, 30)
+    ys = rng.uniform(1.0e4, 4.0e4, 30)
+    run_case(mods, gis, 'p6_prep_align_only', stn_xs=xs, stn_ys=ys, cell_size=999.0,
+             align=(5.0e3 + 0.25, 4.5e4 - 0.75, 1250.0, 30, 38))
 
 
 if __name__ == '__main__':

@@ -13,7 +13,7 @@ from oracle import spinterp_oracle as orc
 
 GOLD = Path(__file__).parent / 'golden'
 CASES = ['p1_prep_polys_edk', 'p2_prep_plain', 'p3_prep_polys_stations',
-         'p4_prep_polys_nobuf_aligned']
+         'p4_prep_polys_nobuf_aligned', 'p5_prep_align_polys_edk', 'p6_prep_align_only']
 
 
 def _load(name):
@@ -28,6 +28,12 @@ def _raster_geo(d):
         return None
     x_min, y_max = d['raster_geo'][:2]
     return (x_min, y_max) + d['rasters'][0].shape
+
+
+def _align(d):
+    """(x_min, y_max, cell_size, n_rows, n_cols) of the alignment raster or None."""
+    a = d['align']
+    return None if np.isnan(a[0]) else (float(a[0]), float(a[1]), float(a[2]), int(a[3]), int(a[4]))
 
 
 @pytest.mark.skipif(not Path('/root/reference/interp/prepare.py').exists(),
@@ -48,10 +54,19 @@ def test_fixtures_regenerate_from_the_reference(tmp_path):
 def test_oracle_preparation_matches_the_reference(name):
     d = _load(name)
     cs = float(d['cell_size'])
-    if d['rasters']:
+    if _align(d) is not None:
+        assert cs == _align(d)[2]               # prepare.py:553-555: the alignment raster's
+    elif d['rasters']:
         assert cs == d['raster_geo'][2] and np.isnan(d['cell_size_in'])   # prepare.py:549-550
     bounds, window, xs, ys = orc.prepare_grid(
-        d['stn_xs'], d['stn_ys'], cs, float(d['cell_bdist']), d['rings'], _raster_geo(d))
+        d['stn_xs'], d['stn_ys'], cs, float(d['cell_bdist']), d['rings'], _raster_geo(d),
+        _align(d))
+    if _align(d) is not None:
+        # on the alignment lattice, and (with polygons) not aligned before the adjustment
+        ax0, ay1 = _align(d)[:2]
+        for v, o in ((bounds[0], ax0), (bounds[1], ax0), (bounds[2], ay1), (bounds[3], ay1)):
+            r = ((v - o) / cs) % 1.0
+            assert min(r, 1.0 - r) < 1e-6
     assert np.array_equal(bounds, d['bounds'])
     assert np.array_equal(window, d['window'])
     assert np.array_equal(xs, d['nc_x_crds']) and np.array_equal(ys, d['nc_y_crds'])
@@ -148,6 +163,9 @@ def test_main_preparation_matches_the_reference(name, tmp_path):
     if d['rings'] is not None:
         m.set_cell_selection_polygons(d['rings'], float(d['stn_bdist']), bool(d['ipoly']),
                                       float(d['cell_bdist']))
+    if _align(d) is not None:
+        ax0, ay1, acs, anr, anc = _align(d)
+        m.set_alignment_raster(dict(x_min=ax0, y_max=ay1, cell_size=acs, n_rows=anr, n_cols=anc))
     if d['rasters']:
         rx_min, ry_max, rcs, ndv = d['raster_geo']
         m.turn_external_drift_kriging_on([
