@@ -5,12 +5,14 @@ interp/prepare.py:510-729) in front of the GPU engine.
 Same setter names, argument meaning, ``assert``-style validation and call-order
 flags.  Differences, all forced by what exists in this image:
 
-* GIS inputs (polygon shapefile, alignment / drift GeoTIFFs) need GDAL/OGR, which
-  is not installed; ``set_cell_selection_parameters`` / ``set_alignment_raster``
-  / raster paths in ``turn_external_drift_kriging_on`` raise ``ImportError``
-  unless ``osgeo`` is importable.  Array-level equivalents are provided:
-  ``set_cell_selection_mask`` (callable or bool array -> ``_cntn_idxs``) and
-  callables ``f(x, y)`` as drift "rasters".
+* GIS inputs: the reference reads them with GDAL/OGR, which is not installed.  The
+  path-taking setters read the two simple file formats themselves (gisio.py: ESRI
+  shapefile polygons for ``set_cell_selection_parameters``, ESRI ASCII grids for
+  ``set_alignment_raster`` / ``turn_external_drift_kriging_on``; a GeoTIFF path raises
+  ``ImportError``), and array-level forms take data read by anything else:
+  ``set_cell_selection_polygons`` (rings), ``set_cell_selection_mask`` (callable or bool
+  array -> ``_cntn_idxs``), dict rasters (values + geometry) and callables ``f(x, y)`` as
+  drift "rasters".  Containment, buffers and raster sampling run on the GPU (prep.py).
 * The scheduler (``_get_thread_steps_idxs``: RAM-driven time / grid-row chunks
   mapped over a process pool) is replaced by time chunks sized for HBM, pipelined
   on one GPU, and by time-sharding across ranks when ``torch.distributed`` is
@@ -250,14 +252,27 @@ class SpInterpMain:
                                       interp_around_polys_flag=True,
                                       polygon_cell_buffer_distance=None,
                                       simplify_tolerance_ratio=0.0):
-        """interp/data.py:349-461 -- needs OGR (absent here)."""
-        try:
-            from osgeo import ogr  # noqa: F401
-        except Exception as exc:  # noqa: BLE001
-            raise ImportError(
-                'set_cell_selection_parameters needs GDAL/OGR to read the polygons; use '
-                'set_cell_selection_mask(mask_or_callable, cell_buffer_distance) instead') from exc
-        raise NotImplementedError('polygon rasterisation is outside the hot path (SURVEY 8f-4)')
+        """interp/data.py:349-461.  The polygons are read from the ``.shp`` file without OGR
+        (gisio.read_shp_polygons: every ring becomes a polygon, like misc.py:221-286) and
+        handed to ``set_cell_selection_polygons``.  ``simplify_tolerance_ratio`` > 0 would
+        need GEOS (``SimplifyPreserveTopology``)."""
+        assert isinstance(polygons_shapefile, (str, Path)), (
+            'polygons_shapefile has to be a string or a pathlib.Path object!')
+        polygons_shapefile = Path(polygons_shapefile).absolute()
+        assert polygons_shapefile.exists(), 'polygons_shapefile does not exist!'
+        assert polygons_shapefile.is_file(), 'polygons_shapefile is not a file!'
+        assert isinstance(simplify_tolerance_ratio, float), 'simplify_tolerance_ratio not a float!'
+        assert simplify_tolerance_ratio >= 0, 'Invalid simplify_tolerance_ratio!'
+        if simplify_tolerance_ratio:
+            raise NotImplementedError('simplifying the polygons needs GEOS; pass 0.0')
+        assert isinstance(polygon_cell_buffer_distance, (float, int)), (
+            'polygon_cell_buffer_distance should be a float or an int '
+            'if interp_around_polys_flag is True!')
+        from . import gisio
+        self.set_cell_selection_polygons(gisio.read_shp_polygons(polygons_shapefile),
+                                         station_select_buffer_distance,
+                                         interp_around_polys_flag, polygon_cell_buffer_distance)
+        self._poly_shp = polygons_shapefile
 
     def set_cell_selection_polygons(self, polygons, station_select_buffer_distance,
                                     interp_around_polys_flag=True,
@@ -312,7 +327,8 @@ class SpInterpMain:
         """interp/data.py:463-494.  The grid bounds are snapped to the cell lattice of this
         raster and its cell size is used (interp/prepare.py:45-90).  Array level: a dict
         with the raster's geometry -- ``x_min``, ``y_max``, ``cell_size`` and ``n_rows`` /
-        ``n_cols`` (or ``values``, whose shape gives them); reading a raster file needs GDAL."""
+        ``n_cols`` (or ``values``, whose shape gives them); a path to an ESRI ASCII grid is read
+        by gisio.read_raster, any other raster file needs GDAL."""
         if isinstance(align_raster, dict):
             assert {'x_min', 'y_max', 'cell_size'} <= set(align_raster), (
                 'array alignment raster needs x_min, y_max, cell_size and n_rows / n_cols')
@@ -329,8 +345,11 @@ class SpInterpMain:
             return
         assert isinstance(align_raster, (str, Path)), (
             'align_raster has to be a string or a pathlib.Path object!')
-        raise ImportError('reading an alignment raster file needs GDAL; pass its geometry as '
-                          'a dict (x_min, y_max, cell_size, n_rows, n_cols)')
+        align_raster = Path(align_raster).absolute()
+        assert align_raster.exists(), 'align_raster does not exist!'
+        assert align_raster.is_file(), 'align_raster is not a file!'
+        from . import gisio
+        self.set_alignment_raster(gisio.read_raster(align_raster))   # ESRI ASCII grid, else GDAL
 
     def set_neighbor_selection_method(self, selection_method, n_neighbors=None, n_pies=None):
         """interp/data.py:496-588."""
@@ -408,8 +427,9 @@ class SpInterpMain:
         self._spk_flag = False
 
     def turn_external_drift_kriging_on(self, drift_rasters):
-        """interp/main.py:284-336.  Elements may be callables ``f(x, y)`` (array
-        level) or raster paths (need GDAL)."""
+        """interp/main.py:284-336.  Elements may be callables ``f(x, y)``, array rasters
+        (dicts) or raster paths (ESRI ASCII grids are read here, gisio.read_ascii_grid;
+        other formats need GDAL)."""
         assert hasattr(drift_rasters, '__iter__')
         rass = []
         for dr in drift_rasters:
@@ -428,7 +448,13 @@ class SpInterpMain:
                 continue
             assert isinstance(dr, (str, Path)), (
                 'Supplied drift raster path is not a string or a pathlib.Path object!')
-            raise ImportError('reading drift rasters needs GDAL; pass callables f(x, y) instead')
+            dr = Path(dr).absolute()
+            assert dr.exists(), 'Supplied drift raster path does not point to a file!'
+            assert dr.is_file(), 'Supplied drift raster path does not point to a file!'
+            from . import gisio
+            ras = gisio.read_raster(dr)                 # ESRI ASCII grid, else needs GDAL
+            ras['values'] = np.ascontiguousarray(ras['values'], dtype=np.float64)
+            rass.append(ras)
         self._drft_rass = tuple(rass)
         self._n_drft_rass = len(rass)
         assert self._n_drft_rass, 'Zero drift rasters were supplied!'

@@ -7,8 +7,8 @@
 * ``sample_raster`` / ``drift_at_cells`` / ``drift_at_points``: drift values at cells and
   stations (interp/drift.py:165-226).
 
-Polygons are passed as arrays (outer rings); reading shapefiles / GeoTIFFs needs GDAL,
-which is outside this path.  torch is used for device memory only; no CPU fallback.
+Polygons are passed as arrays (rings) and rasters as arrays + geometry; gisio.py reads them
+from ESRI shapefiles / ASCII grids, other formats need GDAL, which is outside this path.  torch is used for device memory only; no CPU fallback.
 """
 from __future__ import annotations
 
