@@ -1,4 +1,4 @@
-"""Readers for the two simplest GIS file formats, so that the path-taking setters of the
+"""Readers for three simple GIS file formats, so that the path-taking setters of the
 reference (``set_cell_selection_parameters(polygons_shapefile, ...)``, interp/data.py:349-461;
 ``turn_external_drift_kriging_on([raster paths])``, interp/main.py:291-343;
 ``set_alignment_raster(path)``, interp/data.py:463-494) work without GDAL / OGR for
@@ -8,10 +8,12 @@ reference (``set_cell_selection_parameters(polygons_shapefile, ...)``, interp/da
   (misc.py:221-286) recurses into the rings of a multi-ring geometry and wraps each one
   ("Polygons with holes do not get interpolated! Just accept them anyway.");
 * ESRI ASCII grids (``.asc``): ``ncols / nrows / xllcorner|xllcenter / yllcorner|yllcenter /
-  cellsize / NODATA_value`` followed by the rows from north to south.
+  cellsize / NODATA_value`` followed by the rows from north to south;
+* single-band GeoTIFFs (``.tif``) when Pillow is importable (pixels by libtiff, the
+  georeferencing tags are interpreted here).
 
-Anything else (GeoTIFF, projections, other vector formats) still needs GDAL: the array
-forms of the setters take data read by whatever the caller has.
+Anything else (projections, rotated rasters, other vector formats) still needs GDAL: the
+array forms of the setters take data read by whatever the caller has.
 Format: ESRI Shapefile Technical Description (1998), main file: a 100-byte header (file code
 9994 big-endian, version 1000 and shape type little-endian), then records of (record number,
 content length in 16-bit words; both big-endian) + content (shape type, box, numParts,
@@ -104,10 +106,67 @@ def read_ascii_grid(path):
                 cell_size=cs, ndv=ndv)
 
 
+def read_geotiff(path):
+    """Single-band GeoTIFF -> dict(values, x_min, y_max, cell_size, ndv), what
+    ``misc.get_ras_props`` + ``ReadAsArray`` give the reference (misc.py:630-686,
+    interp/drift.py:55-83).  The pixels are decoded by Pillow (libtiff; strips or tiles, raw /
+    LZW / deflate, 8 / 16 / 32-bit integers and 32-bit floats); the georeferencing is taken
+    from the GeoTIFF tags here: ModelPixelScale (33550) + ModelTiepoint (33922), or an
+    unrotated ModelTransformation (34264); a PixelIsPoint raster (GTRasterTypeGeoKey 1025 = 2
+    in the GeoKeyDirectory 34735) is shifted by half a cell like GDAL's geotransform; the
+    no-data value comes from GDAL_NODATA (42113)."""
+    try:
+        from PIL import Image
+    except Exception as exc:  # noqa: BLE001
+        raise ImportError('reading a GeoTIFF needs Pillow or GDAL; pass the raster as a '
+                          'dict(values, x_min, y_max, cell_size, ndv)') from exc
+    Image.MAX_IMAGE_PIXELS = None
+    with Image.open(path) as img:
+        tags = dict(img.tag_v2) if hasattr(img, 'tag_v2') else {}
+        if len(img.getbands()) != 1:
+            raise ValueError(f'{path}: {len(img.getbands())} bands, expected a single-band raster')
+        vals = np.array(img)
+    if vals.ndim != 2:
+        raise ValueError(f'{path}: not a 2-D raster')
+    scale = tags.get(33550)
+    tie = tags.get(33922)
+    mat = tags.get(34264)
+    if scale is not None and tie is not None:
+        sx, sy = float(scale[0]), float(scale[1])
+        i, j, _, x, y = (float(v) for v in tie[:5])
+        x_min, y_max = x - i * sx, y + j * sy
+    elif mat is not None and len(mat) == 16:
+        if float(mat[1]) != 0.0 or float(mat[4]) != 0.0:
+            raise ValueError(f'{path}: rotated rasters are not supported')
+        sx, sy = float(mat[0]), -float(mat[5])
+        x_min, y_max = float(mat[3]), float(mat[7])
+    else:
+        raise ValueError(f'{path}: no GeoTIFF georeferencing tags')
+    keys = tags.get(34735)
+    if keys is not None:
+        keys = [int(k) for k in keys]
+        for q in range(4, len(keys) - 3, 4):
+            if keys[q] == 1025 and keys[q + 1] == 0 and keys[q + 3] == 2:    # PixelIsPoint
+                x_min -= 0.5 * sx
+                y_max += 0.5 * sy
+    if not np.isclose(sx, sy):
+        raise ValueError(f'{path}: cells are not square ({sx}, {sy})')
+    ndv = tags.get(42113)
+    if ndv is not None:
+        ndv = float(str(ndv).strip().strip('\x00'))
+        if np.isnan(ndv):
+            ndv = None
+    return dict(values=np.ascontiguousarray(vals, dtype=np.float64), x_min=x_min, y_max=y_max,
+                cell_size=sx, ndv=ndv)
+
+
 def read_raster(path):
-    """Dispatch on the file type; only ESRI ASCII grids are readable without GDAL."""
+    """Dispatch on the file type: ESRI ASCII grids (no dependency) and GeoTIFFs (Pillow);
+    everything else needs GDAL."""
     p = Path(path)
     if p.suffix.lower() in ('.asc', '.txt'):
         return read_ascii_grid(p)
+    if p.suffix.lower() in ('.tif', '.tiff'):
+        return read_geotiff(p)
     raise ImportError(f'reading {p.suffix or p.name} rasters needs GDAL; pass the raster as a '
-                      'dict(values, x_min, y_max, cell_size, ndv) or as an ESRI ASCII grid')
+                      'dict(values, x_min, y_max, cell_size, ndv), a GeoTIFF or an ESRI ASCII grid')

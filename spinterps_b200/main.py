@@ -6,10 +6,10 @@ Same setter names, argument meaning, ``assert``-style validation and call-order
 flags.  Differences, all forced by what exists in this image:
 
 * GIS inputs: the reference reads them with GDAL/OGR, which is not installed.  The
-  path-taking setters read the two simple file formats themselves (gisio.py: ESRI
-  shapefile polygons for ``set_cell_selection_parameters``, ESRI ASCII grids for
-  ``set_alignment_raster`` / ``turn_external_drift_kriging_on``; a GeoTIFF path raises
-  ``ImportError``), and array-level forms take data read by anything else:
+  path-taking setters read the simple file formats themselves (gisio.py: ESRI
+  shapefile polygons for ``set_cell_selection_parameters``, ESRI ASCII grids and
+  single-band GeoTIFFs for ``set_alignment_raster`` / ``turn_external_drift_kriging_on``),
+  and array-level forms take data read by anything else:
   ``set_cell_selection_polygons`` (rings), ``set_cell_selection_mask`` (callable or bool
   array -> ``_cntn_idxs``), dict rasters (values + geometry) and callables ``f(x, y)`` as
   drift "rasters".  Containment, buffers and raster sampling run on the GPU (prep.py).

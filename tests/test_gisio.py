@@ -1,5 +1,5 @@
 """File forms of the reference's GIS inputs without GDAL / OGR (spinterps_b200/gisio.py):
-ESRI shapefile polygons -> rings, ESRI ASCII grids -> array rasters, and the path-taking
+ESRI shapefile polygons -> rings, ESRI ASCII grids and GeoTIFFs -> array rasters, and the path-taking
 setters of SpInterpMain (interp/data.py:349-494, interp/main.py:291-343) on top of them."""
 import struct
 
@@ -79,7 +79,57 @@ def test_ascii_grid(tmp_path):
     assert (r2['x_min'], r2['y_max'], r2['ndv']) == (1000.5, 3250.25, None)
     assert np.array_equal(r2['values'], vals)
     with pytest.raises(ImportError):
-        gisio.read_raster(tmp_path / 'dem.tif')
+        gisio.read_raster(tmp_path / 'dem.img')
+
+
+def _write_geotiff(path, arr, tags, compression=None):
+    from PIL import Image, TiffImagePlugin
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    for tag, (typ, val) in tags.items():
+        ifd[tag] = val
+        ifd.tagtype[tag] = typ
+    kw = {} if compression is None else {'compression': compression}
+    Image.fromarray(arr).save(path, tiffinfo=ifd, **kw)
+
+
+def test_geotiff(tmp_path):
+    pytest.importorskip('PIL')
+    rng = np.random.default_rng(1)
+    elev = rng.normal(600.0, 150.0, (37, 53)).astype(np.float32)
+    elev[3, 4] = -9999.0
+    DOUBLE, ASCII, SHORT = 12, 2, 3
+    base = {33550: (DOUBLE, (1000.0, 1000.0, 0.0)),
+            33922: (DOUBLE, (0.0, 0.0, 0.0, 280000.5, 5650000.25, 0.0)),
+            42113: (ASCII, '-9999')}
+    for comp in (None, 'tiff_deflate', 'tiff_lzw'):
+        p = tmp_path / f'elev_{comp}.tif'
+        _write_geotiff(p, elev, base, comp)
+        r = gisio.read_raster(p)
+        assert r['values'].dtype == np.float64 and np.array_equal(r['values'], elev.astype(np.float64))
+        assert (r['x_min'], r['y_max'], r['cell_size'], r['ndv']) == (280000.5, 5650000.25, 1000.0,
+                                                                      -9999.0)
+    # tiepoint at another pixel, PixelIsPoint (half a cell towards north-west), integer data
+    dem = rng.integers(-50, 2500, (20, 31)).astype(np.int32)
+    tags = {33550: (DOUBLE, (250.0, 250.0, 0.0)),
+            33922: (DOUBLE, (2.0, 3.0, 0.0, 1000.0, 9000.0, 0.0)),
+            34735: (SHORT, (1, 1, 0, 2, 1024, 0, 1, 1, 1025, 0, 1, 2))}
+    p = tmp_path / 'dem_point.tif'
+    _write_geotiff(p, dem, tags)
+    r = gisio.read_geotiff(p)
+    assert np.array_equal(r['values'], dem.astype(np.float64)) and r['ndv'] is None
+    assert (r['x_min'], r['y_max'], r['cell_size']) == (1000.0 - 2 * 250.0 - 125.0,
+                                                        9000.0 + 3 * 250.0 + 125.0, 250.0)
+    # ModelTransformation instead of scale + tiepoint
+    mat = (500.0, 0.0, 0.0, 12000.0, 0.0, -500.0, 0.0, 48000.0, 0.0, 0.0, 0.0, 0.0,
+           0.0, 0.0, 0.0, 1.0)
+    p = tmp_path / 'dem_matrix.tif'
+    _write_geotiff(p, dem, {34264: (DOUBLE, mat)})
+    r = gisio.read_geotiff(p)
+    assert (r['x_min'], r['y_max'], r['cell_size']) == (12000.0, 48000.0, 500.0)
+    p = tmp_path / 'plain.tif'
+    _write_geotiff(p, dem, {})
+    with pytest.raises(ValueError):
+        gisio.read_geotiff(p)
 
 
 def test_main_setters_take_the_files(tmp_path):
